@@ -1,0 +1,157 @@
+/*
+ * kagnn_b200.h -- C ABI of libkagnn_b200.so: the B200 (sm_100a) forward path of KAGNN's
+ * KAN layers fused with the GCN / GIN / GINE neighbour aggregation that feeds them.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; memory is caller-owned;
+ *     nothing is allocated or retained by the library (explicit workspace queries instead);
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*) and re-entrant;
+ *   - return value: 0 on success, a negative KAGNN_E* code otherwise (kagnn_strerror());
+ *   - all floating-point data is fp32 row-major with an explicit leading dimension (elements);
+ *     graph indices are int32 once in CSR form (int64 COO only at kagnn_csr_build);
+ *   - there is no CPU fallback: an unsupported configuration is an error.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the KAGNN
+ * repository root; nc = node_classification_clean, gc = graph_classification,
+ * gr = graph_regression).
+ */
+#ifndef KAGNN_B200_H
+#define KAGNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KAGNN_VERSION 100 /* 0.1.0 */
+
+enum {
+    KAGNN_OK = 0,
+    KAGNN_EINVAL = -1,      /* bad shape / null pointer / inconsistent arguments          */
+    KAGNN_EUNSUPPORTED = -2,/* valid request outside what the kernels implement           */
+    KAGNN_EALIGN = -3,      /* pointer or leading dimension not aligned as required       */
+    KAGNN_EWORKSPACE = -4,  /* workspace too small (see the *_workspace query)            */
+    KAGNN_ECUDA = -5,       /* a CUDA runtime call / kernel launch failed                 */
+    KAGNN_EINDEX = -6       /* edge_index / batch entry out of range                      */
+};
+
+/* Basis family of one KAN layer. */
+enum {
+    KAGNN_BASIS_BSPLINE = 0, /* ekan.KANLinear      (nc/ekan.py:7-162)        */
+    KAGNN_BASIS_RBF = 1      /* fastkan.FastKANLayer (nc/fastkan.py:49-85)    */
+};
+
+/* Aggregation that produces the row tile fed to the KAN chain. */
+enum {
+    KAGNN_AGG_NONE = 0,     /* rows of x as they are (bare KANLinear / KAN / FastKAN)                           */
+    KAGNN_AGG_GIN = 1,      /* self_scale*x_i + sum_{j->i} x_j             (PyG GINConv;  nc/models.py:48-56)   */
+    KAGNN_AGG_GINE = 2,     /* self_scale*x_i + sum relu(x_j + e_ji)       (PyG GINEConv; gr/models.py:98)      */
+    KAGNN_AGG_WEIGHTED = 3, /* self_weight[i]*x_i + sum w_e x_j            (PyG GCNConv;  nc/models.py:31-37)   */
+    KAGNN_AGG_SEGMENT_SUM = 4,  /* sum of rows rowptr[i]..rowptr[i+1]      (global_add_pool;  gc/models.py:117) */
+    KAGNN_AGG_SEGMENT_MEAN = 5  /* ... divided by max(count,1)             (global_mean_pool; gc/models.py:192) */
+};
+
+enum { KAGNN_ACT_NONE = 0, KAGNN_ACT_SILU = 1 };
+
+/* y = act(x * scale[c] + shift[c]) per column c; NULL scale = 1, NULL shift = 0.
+ * Carries GCNConv's bias, eval-mode BatchNorm1d (nc/models.py:197) and gc.KAGCN's silu (gc/models.py:190). */
+typedef struct KagnnAffine {
+    const float* scale;
+    const float* shift;
+    int32_t act;
+    int32_t _pad;
+} KagnnAffine;
+
+/* One KAN layer, weights pre-packed by kagnn_pack_kan_weights(). */
+typedef struct KagnnKanLayer {
+    int32_t basis;          /* KAGNN_BASIS_*                                                                */
+    int32_t in_features;
+    int32_t out_features;
+    int32_t grid_size;      /* B-spline: G.  RBF: num_grids                                                  */
+    int32_t spline_order;   /* B-spline: k (1..4).  RBF: ignored                                             */
+    float t0;               /* B-spline: first knot t_0 = lo - k*h (nc/ekan.py:28-37).  RBF: grid_min        */
+    float h;                /* B-spline: knot spacing.  RBF: spacing of the centres                          */
+    float inv_denominator;  /* RBF: 1/denominator (nc/fastkan.py:44).  B-spline: ignored                     */
+    const float* packed_w;  /* [in][slots+1][out_pad4]: slots = G+k (B-spline) or G (RBF); last = base weight */
+    const float* base_bias; /* RBF base_linear.bias (out) or NULL                                            */
+    const float* ln_weight; /* RBF LayerNorm weight (in) or NULL = no LayerNorm                              */
+    const float* ln_bias;   /* RBF LayerNorm bias (in) or NULL                                               */
+} KagnnKanLayer;
+
+/* Input side of the fused layer: where rows come from and how they are aggregated. */
+typedef struct KagnnAggregate {
+    int32_t mode;             /* KAGNN_AGG_*                                                                 */
+    int32_t num_cols;         /* feature width F of x                                                        */
+    const float* x;           /* (num_src_rows, F), leading dimension ldx                                    */
+    int64_t ldx;
+    const int32_t* src_index; /* optional: row j of the logical x is x[src_index[j]] (embedding lookup)      */
+    const int32_t* rowptr;    /* (num_rows+1) CSR over destination rows (or segment pointers for pooling)    */
+    const int32_t* col;       /* (nnz) source row per CSR entry; NULL for the SEGMENT modes                  */
+    const float* edge_weight; /* WEIGHTED: (nnz) in CSR order                                                */
+    const float* self_weight; /* WEIGHTED: (num_rows) weight of x_i; NULL = self_scale                       */
+    float self_scale;         /* GIN / GINE: 1 + eps                                                         */
+    int32_t _pad;
+    const float* edge_feat;   /* GINE: edge features, row r = edge_feat[edge_index_of(r)*ld_edge ...]         */
+    int64_t ld_edge;
+    const int32_t* edge_row;  /* GINE: (nnz) row of edge_feat for each CSR entry (perm or table code)        */
+} KagnnAggregate;
+
+/* ---- library ------------------------------------------------------------------------------------ */
+int kagnn_version(void);
+const char* kagnn_strerror(int code);
+/* Number of SMs / max dynamic shared memory of the current device (for host-side planning). */
+int kagnn_device_info(int32_t* num_sms, int32_t* max_smem_bytes, int32_t* cc_major, int32_t* cc_minor);
+
+/* ---- graph ingestion (replaces what PyG's MessagePassing.propagate / gcn_norm redo per call) ------ */
+/* COO int64 edge_index (2,E) row-major [src row; dst row] (PyG flow source_to_target) ->
+ * destination-sorted CSR (stable: entries of one row keep their COO order).
+ * perm[p] = original edge id of CSR entry p.  Workspace: kagnn_csr_build_workspace(E, N). */
+size_t kagnn_csr_build_workspace(int64_t num_edges, int64_t num_nodes);
+int kagnn_csr_build(const int64_t* edge_index, int64_t num_edges, int64_t num_nodes, int64_t num_src_nodes,
+                    int32_t* rowptr, int32_t* col, int32_t* perm,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* Sorted batch vector (N) int64 -> segment pointers (B+1) int32 (PyG global_*_pool's `batch`). */
+int kagnn_segment_ptr(const int64_t* batch, int64_t num_nodes, int64_t num_graphs, int32_t* ptr, void* stream);
+
+/* PyG gcn_norm(add_self_loops=True) on the CSR: existing self loops get weight 0, every node gets a
+ * self weight dinv[i]^2 * loop_w, other entries dinv[src]*w*dinv[dst]; deg = in-degree at the target.
+ * edge_weight_in: optional user weights in CSR order (NULL = ones).  dinv: (N) scratch/output. */
+int kagnn_gcn_norm(const int32_t* rowptr, const int32_t* col, int64_t num_nodes, const float* edge_weight_in,
+                   float* edge_weight_out, float* self_weight_out, float* dinv, void* stream);
+
+/* ---- weights -------------------------------------------------------------------------------------- */
+/* scaled_spline_weight (nc/ekan.py:146-152) folded while packing:
+ * packed[(i*(S+1)+c)*out_pad4 + o] = spline_w[o,i,c]*scaler[o,i] (c<S), base_w[o,i] (c==S).
+ * spline_w is (out,in,S) contiguous -- also the layout of fastkan's spline_linear.weight (out,in*G). */
+size_t kagnn_packed_weight_elems(int32_t in_features, int32_t out_features, int32_t slots);
+int kagnn_pack_kan_weights(const float* base_w, const float* spline_w, const float* spline_scaler_or_null,
+                           int32_t in_features, int32_t out_features, int32_t slots,
+                           float* packed, void* stream);
+
+/* ---- the hot path -------------------------------------------------------------------------------------
+ * One launch: tile = aggregate(x) -> pre affine -> [optional store to agg_out] -> KAN layer 0 .. n_layers-1
+ * (intermediate activations never leave the SM) -> post affine -> y.
+ *   GIN  layer (nc/models.py:48-56 + :196-197):  mode GIN,  layers = the conv's KAN, post = eval BatchNorm
+ *   GCN  layer (nc/models.py:31-37):             mode WEIGHTED over h = KAN(x), pre = bias (+BN / silu),
+ *                                                layers = the NEXT conv's KAN (fusion boundary shifted half a layer)
+ *   bare KANLinear.forward (nc/ekan.py:154-162): mode NONE, n_layers = 1
+ *   readout (gc/models.py:117-118):              mode SEGMENT_SUM, layers = the readout KAN
+ * n_layers may be 0 (pure aggregation into agg_out).  num_rows = destination rows (nodes or graphs). */
+int kagnn_fused_layer_fwd(const KagnnAggregate* agg, int64_t num_rows,
+                          const KagnnAffine* pre_or_null,
+                          float* agg_out_or_null, int64_t ld_agg_out,
+                          int32_t n_layers, const KagnnKanLayer* layers_host,
+                          const KagnnAffine* post_or_null,
+                          float* y, int64_t ldy, void* stream);
+
+/* Row gather out[r,:] = x[index[r],:] (halo send-buffer packing for the node-sharded multi-GPU path). */
+int kagnn_gather_rows(const float* x, int64_t ldx, const int32_t* index, int64_t num_rows, int32_t num_cols,
+                      float* out, int64_t ld_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KAGNN_B200_H */

@@ -1,0 +1,215 @@
+"""Message-passing layers with the PyG call surface the reference's models rely on, executed by the fused
+sm_100a kernel.
+
+torch_geometric (pinned 2.5.3 by the reference, ``requirements.txt:4``) is not available in this environment, so
+``GCNConv`` / ``GINConv`` / ``GINEConv`` here are self-contained modules that keep PyG's attribute and
+``state_dict`` names (``lin``, ``bias``, ``nn``, ``eps``), constructor arguments and ``forward`` signatures:
+
+* ``GCNConv(x, edge_index, edge_weight=None)``: ``out = D^-1/2 (A'+I) D^-1/2 . lin(x) + bias``
+* ``GINConv(x, edge_index, size=None)``:        ``out = nn((1+eps) x_i + sum_j x_j)``
+* ``GINEConv(x, edge_index, edge_attr)``:       ``out = nn((1+eps) x_i + sum_j relu(x_j + e_ji))``
+
+and the KAN-ised subclasses of node_classification_clean/models.py:27-92, graph_classification/models.py:153-243
+and graph_regression/models.py:162-216 (``KANLayer``, ``KAGCNConv``, ``GIKANLayer``, ``FKANLayer``,
+``FASTKAGCNConv``, ``GIFASTKANLayer``, ``KAGCN_Layer``, ``FASTKAGCN_Layer``).
+
+Each layer is usable on its own (one launch for GIN/GINE, two for GCN: KAN then aggregation); the model classes
+additionally fuse across layer boundaries (models_*.py).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch import nn
+
+from . import _lib as L
+from . import ops
+from .ekan import KAN, KANLinear, _module_backend_guard
+from .fastkan import FastKAN, FastKANLayer
+from .graph import GraphCSR, get_graph
+
+Tensor = torch.Tensor
+
+
+def make_kan(num_features, hidden_dim, out_dim, hidden_layers, grid_size, spline_order):
+    """node_classification_clean/models.py:19-21."""
+    sizes = [num_features] + [hidden_dim] * (hidden_layers - 1) + [out_dim]
+    return KAN(layers_hidden=sizes, grid_size=grid_size, spline_order=spline_order)
+
+
+def make_fastkan(num_features, hidden_dim, out_dim, hidden_layers, grid_size):
+    """node_classification_clean/models.py:23-25."""
+    sizes = [num_features] + [hidden_dim] * (hidden_layers - 1) + [out_dim]
+    return FastKAN(layers_hidden=sizes, num_grids=grid_size)
+
+
+def _is_kan(m) -> bool:
+    return hasattr(m, "kernel_specs")
+
+
+class _MessagePassing(nn.Module):
+    """The slice of PyG's MessagePassing surface that callers of these layers touch."""
+    aggr = "add"
+    flow = "source_to_target"
+    node_dim = -2
+
+    def _graph(self, x: Tensor, edge_index) -> GraphCSR:
+        if isinstance(edge_index, GraphCSR):
+            return edge_index
+        return get_graph(edge_index, x.size(0))
+
+
+class GCNConv(_MessagePassing):
+    def __init__(self, in_channels: int, out_channels: int, bias: bool = True, **kwargs):
+        super().__init__()
+        if kwargs.get("improved") or kwargs.get("cached") or kwargs.get("normalize") is False or kwargs.get("add_self_loops") is False:
+            raise NotImplementedError("only GCNConv's default options are used by the reference and implemented")
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.lin = nn.Linear(in_channels, out_channels, bias=False)
+        if bias:
+            self.bias = nn.Parameter(torch.zeros(out_channels))
+        else:
+            self.register_parameter("bias", None)
+
+    def reset_parameters(self):
+        if hasattr(self.lin, "reset_parameters"):
+            self.lin.reset_parameters()
+        if self.bias is not None:
+            nn.init.zeros_(self.bias)
+
+    def transform(self, x: Tensor) -> Tensor:
+        """``self.lin(x)``: a KAN (one launch) or whatever module the user plugged in."""
+        return self.lin(x)
+
+    def aggregate_transformed(self, h: Tensor, graph: GraphCSR, edge_weight: Optional[Tensor] = None,
+                              out: Optional[Tensor] = None, extra: Optional[ops.Affine] = None) -> Tensor:
+        w, sw = graph.gcn_weights(edge_weight)
+        pre = extra if extra is not None else (ops.Affine(shift=self.bias.detach()) if self.bias is not None else None)
+        agg = ops.AggSpec(L.AGG_WEIGHTED, h, graph.rowptr, graph.col, edge_weight=w, self_weight=sw)
+        return ops.fused_layer(agg, graph.num_nodes, [], pre=pre, agg_out=out)
+
+    def forward(self, x: Tensor, edge_index, edge_weight: Optional[Tensor] = None) -> Tensor:
+        _module_backend_guard(x, list(self.parameters()))
+        g = self._graph(x, edge_index)
+        return self.aggregate_transformed(self.transform(x).to(torch.float32), g, edge_weight)
+
+
+class GINConv(_MessagePassing):
+    def __init__(self, nn: nn.Module, eps: float = 0.0, train_eps: bool = False, **kwargs):
+        super().__init__()
+        self.nn = nn
+        self.initial_eps = float(eps)
+        if train_eps:
+            self.eps = torch.nn.Parameter(torch.tensor([self.initial_eps]))
+        else:
+            self.register_buffer("eps", torch.tensor([self.initial_eps]))
+        self._eps_host = (None, None)
+
+    def reset_parameters(self):
+        for m in self.nn.modules():
+            if m is not self.nn and hasattr(m, "reset_parameters"):
+                m.reset_parameters()
+        self.eps.data.fill_(self.initial_eps)
+
+    def eps_value(self) -> float:
+        key = (self.eps.data_ptr(), self.eps._version)
+        if self._eps_host[0] != key:
+            self._eps_host = (key, float(self.eps.detach().cpu()))
+        return self._eps_host[1]
+
+    def _agg_spec(self, x: Tensor, g: GraphCSR) -> ops.AggSpec:
+        return ops.AggSpec(L.AGG_GIN, x, g.rowptr, g.col, self_scale=1.0 + self.eps_value())
+
+    def forward(self, x: Tensor, edge_index, size=None, out: Optional[Tensor] = None,
+                post: Optional[ops.Affine] = None, **agg_kw) -> Tensor:
+        _module_backend_guard(x, list(self.parameters()))
+        g = self._graph(x, edge_index)
+        agg = self._agg_spec(x.to(torch.float32), g, **agg_kw)
+        if _is_kan(self.nn):
+            specs = self.nn.kernel_specs()
+            if len(specs) <= L.MAX_LAYERS:
+                return ops.fused_layer(agg, g.num_nodes, specs, post=post, out=out)
+        h = self.nn(ops.fused_layer(agg, g.num_nodes, []))
+        if post is not None or out is not None:
+            raise NotImplementedError("fused epilogue needs a KAN/FastKAN as GINConv.nn")
+        return h
+
+
+class GINEConv(GINConv):
+    def __init__(self, nn: nn.Module, eps: float = 0.0, train_eps: bool = False, edge_dim: Optional[int] = None, **kwargs):
+        super().__init__(nn, eps, train_eps)
+        if edge_dim is not None:
+            raise NotImplementedError("edge_dim is never used by the reference (graph_regression/models.py:98)")
+        self.lin = None
+
+    def _agg_spec(self, x: Tensor, g: GraphCSR, edge_feat: Tensor = None, edge_row: Tensor = None) -> ops.AggSpec:
+        return ops.AggSpec(L.AGG_GINE, x, g.rowptr, g.col, self_scale=1.0 + self.eps_value(), edge_feat=edge_feat,
+                           edge_row=edge_row)
+
+    def forward(self, x: Tensor, edge_index, edge_attr: Tensor = None, size=None, out: Optional[Tensor] = None,
+                post: Optional[ops.Affine] = None, edge_row: Optional[Tensor] = None) -> Tensor:
+        """``edge_attr`` is (E, F) in COO order (PyG semantics).  Internal callers may instead pass a small
+        feature table plus ``edge_row`` (CSR-ordered row ids into it)."""
+        if edge_attr is None:
+            raise ValueError("GINEConv needs edge_attr")
+        g = self._graph(x, edge_index)
+        if edge_row is None:
+            if edge_attr.size(0) != g.csr.nnz or edge_attr.size(-1) != x.size(-1):
+                raise ValueError("Node and edge feature dimensionalities do not match")
+            edge_row = g.perm
+        return super().forward(x, g, out=out, post=post, edge_feat=edge_attr.to(torch.float32), edge_row=edge_row)
+
+
+# ---- KAN-ised layers (same names / signatures as the reference) ----------------------------------------------------
+class KANLayer(KANLinear):
+    def __init__(self, input_dim, output_dim, grid_size=4, spline_order=3):
+        super().__init__(in_features=input_dim, out_features=output_dim, grid_size=grid_size, spline_order=spline_order)
+
+
+class FKANLayer(FastKANLayer):
+    def __init__(self, input_dim, output_dim, num_grids=4):
+        super().__init__(input_dim=input_dim, output_dim=output_dim, num_grids=num_grids)
+        self.input_dim, self.output_dim, self.num_grids = input_dim, output_dim, num_grids
+
+    def reset_parameters(self):
+        self.__init__(self.input_dim, self.output_dim, self.num_grids)
+
+
+class KAGCNConv(GCNConv):
+    def __init__(self, in_feat: int, out_feat: int, grid_size: int = 4, spline_order: int = 3):
+        super().__init__(in_feat, out_feat)
+        self.lin = KANLayer(in_feat, out_feat, grid_size, spline_order)
+
+
+class FASTKAGCNConv(GCNConv):
+    def __init__(self, in_feat: int, out_feat: int, grid_size: int = 4):
+        super().__init__(in_channels=in_feat, out_channels=out_feat)
+        self.grid_size = grid_size
+        self.lin = FKANLayer(in_feat, out_feat, num_grids=grid_size)
+
+
+class GIKANLayer(GINConv):
+    def __init__(self, in_feat: int, out_feat: int, grid_size: int = 4, spline_order: int = 3, hidden_dim: int = 16,
+                 nb_layers: int = 2):
+        super().__init__(make_kan(in_feat, hidden_dim, out_feat, nb_layers, grid_size, spline_order))
+
+
+class GIFASTKANLayer(GINConv):
+    def __init__(self, in_feat: int, out_feat: int, grid_size: int = 4, hidden_dim: int = 16, nb_layers: int = 2):
+        super().__init__(make_fastkan(in_feat, hidden_dim, out_feat, nb_layers, grid_size))
+
+
+# graph_classification / graph_regression spell the GCN layers differently
+KAGCN_Layer = KAGCNConv
+FASTKAGCN_Layer = FASTKAGCNConv
+
+
+class KAGATConv(nn.Module):
+    """GAT variants are outside the hot path."""
+
+    def __init__(self, *a, **kw):
+        raise NotImplementedError("GAT-based KAN layers are out of scope of the B200 hot path")
+
+
+FASTKAGATConv = KAGAT_Layer = FASTKAGAT_Layer = KAGATConv

@@ -1,0 +1,30 @@
+// Shared helpers for libkagnn_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/kagnn_b200.h"
+
+#define KAGNN_MAX_LAYERS 8
+
+#define KAGNN_CUDA_TRY(expr)                         \
+    do {                                             \
+        cudaError_t _e = (expr);                     \
+        if (_e != cudaSuccess) return KAGNN_ECUDA;   \
+    } while (0)
+
+#define KAGNN_LAUNCH_CHECK()                                  \
+    do {                                                      \
+        if (cudaGetLastError() != cudaSuccess) return KAGNN_ECUDA; \
+    } while (0)
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int pad4(int v) { return (v + 3) & ~3; }
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+struct DeviceProps {
+    int num_sms;
+    int max_smem;
+    int cc_major, cc_minor;
+};
+// cached per device; returns KAGNN_OK / KAGNN_ECUDA
+int kagnn_get_props(DeviceProps* out);

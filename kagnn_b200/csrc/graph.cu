@@ -1,0 +1,219 @@
+// Graph ingestion for the fused layer: COO -> destination-sorted CSR, segment pointers, gcn_norm,
+// row gather.  Replaces the per-forward index handling of PyG's MessagePassing.propagate /
+// gcn_norm (call sites: node_classification_clean/models.py:31-37,48-56) with device kernels whose
+// results are cached per graph by the host side.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__global__ void coo_keys_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_t E,
+                                int64_t n_dst, int64_t n_src, int32_t* __restrict__ keys,
+                                int32_t* __restrict__ vals, int32_t* __restrict__ err) {
+    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    int64_t s = src[e], d = dst[e];
+    bool bad = (d < 0) | (d >= n_dst) | (s < 0) | (s >= n_src);
+    if (bad) {
+        atomicOr(err, 1);
+        d = 0;
+    }
+    keys[e] = (int32_t)d;
+    vals[e] = (int32_t)e;
+}
+
+__global__ void csr_fill_kernel(const int64_t* __restrict__ src, const int32_t* __restrict__ sorted_eid, int64_t E,
+                                int64_t n_src, int32_t* __restrict__ col, int32_t* __restrict__ perm) {
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= E) return;
+    int32_t e = sorted_eid[p];
+    int64_t s = src[e];
+    if (s < 0 || s >= n_src) s = 0;  // flagged by coo_keys_kernel; keep reads in bounds
+    col[p] = (int32_t)s;
+    perm[p] = e;
+}
+
+// ptr[i] = first position p with sorted[p] >= i  (i = 0..n)
+template <typename T>
+__global__ void lower_bound_ptr_kernel(const T* __restrict__ sorted, int64_t len, int64_t n, int32_t* __restrict__ ptr) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i > n) return;
+    int64_t lo = 0, hi = len;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if ((int64_t)sorted[mid] < i) lo = mid + 1; else hi = mid;
+    }
+    ptr[i] = (int32_t)lo;
+}
+
+// one warp per destination row: deg = loop_w + sum_{col != i} w ; dinv = deg^-1/2 (0 if deg == 0)
+__global__ void gcn_degree_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n,
+                                  const float* __restrict__ w_in, float* __restrict__ dinv,
+                                  float* __restrict__ self_w) {
+    int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    int beg = rowptr[row], end = rowptr[row + 1];
+    float deg = 0.f;
+    int last_loop = -1;
+    for (int e = beg + lane; e < end; e += 32) {
+        if (col[e] == (int32_t)row) last_loop = e;           // e grows per lane: keeps the last one
+        else deg += w_in ? w_in[e] : 1.f;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        deg += __shfl_xor_sync(0xffffffffu, deg, o);
+        last_loop = max(last_loop, __shfl_xor_sync(0xffffffffu, last_loop, o));
+    }
+    if (lane == 0) {
+        // add_remaining_self_loops: an existing loop donates its weight, otherwise fill value 1
+        float loop_w = (last_loop >= 0 && w_in) ? w_in[last_loop] : 1.f;
+        deg += loop_w;
+        float di = deg > 0.f ? 1.0f / sqrtf(deg) : 0.f;
+        if (!(deg > 0.f) || isinf(di)) di = 0.f;
+        dinv[row] = di;
+        self_w[row] = di * loop_w * di;
+    }
+}
+
+__global__ void gcn_edge_weight_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n,
+                                       const float* __restrict__ w_in, const float* __restrict__ dinv,
+                                       float* __restrict__ w_out) {
+    int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    int beg = rowptr[row], end = rowptr[row + 1];
+    float di = dinv[row];
+    for (int e = beg + lane; e < end; e += 32) {
+        int c = col[e];
+        float w = w_in ? w_in[e] : 1.f;
+        w_out[e] = (c == (int32_t)row) ? 0.f : dinv[c] * w * di;
+    }
+}
+
+template <bool VEC>
+__global__ void gather_rows_kernel(const float* __restrict__ x, int64_t ldx, const int32_t* __restrict__ index,
+                                   int64_t rows, int cols, float* __restrict__ out, int64_t ld_out) {
+    int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    const float* src = x + (int64_t)index[r] * ldx;
+    float* dst = out + r * ld_out;
+    if (VEC) {
+        for (int c = lane * 4; c < cols; c += 128)
+            *reinterpret_cast<float4*>(dst + c) = __ldg(reinterpret_cast<const float4*>(src + c));
+    } else {
+        for (int c = lane; c < cols; c += 32) dst[c] = __ldg(src + c);
+    }
+}
+
+inline int bits_for(int64_t n) {
+    int b = 1;
+    while (b < 31 && ((int64_t)1 << b) < n) ++b;
+    return b;
+}
+
+struct CsrWorkspace {
+    int32_t* err;
+    int32_t *keys_in, *keys_out, *vals_in, *vals_out;
+    void* cub_tmp;
+    size_t cub_bytes;
+    size_t total;
+};
+
+inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+CsrWorkspace carve(void* base, int64_t E) {
+    CsrWorkspace w{};
+    size_t off = 0;
+    char* b = static_cast<char*>(base);
+    auto take = [&](size_t bytes) { char* p = b ? b + off : nullptr; off += align256(bytes); return p; };
+    w.err = reinterpret_cast<int32_t*>(take(256));
+    size_t eb = (size_t)(E > 0 ? E : 1) * sizeof(int32_t);
+    w.keys_in = reinterpret_cast<int32_t*>(take(eb));
+    w.keys_out = reinterpret_cast<int32_t*>(take(eb));
+    w.vals_in = reinterpret_cast<int32_t*>(take(eb));
+    w.vals_out = reinterpret_cast<int32_t*>(take(eb));
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const int32_t*)nullptr, (int32_t*)nullptr,
+                                    (const int32_t*)nullptr, (int32_t*)nullptr, (int)(E > 0 ? E : 1), 0, 31);
+    w.cub_bytes = cub_bytes;
+    w.cub_tmp = take(cub_bytes);
+    w.total = off;
+    return w;
+}
+
+}  // namespace
+
+extern "C" size_t kagnn_csr_build_workspace(int64_t num_edges, int64_t num_nodes) {
+    (void)num_nodes;
+    if (num_edges < 0) return 0;
+    return carve(nullptr, num_edges).total;
+}
+
+extern "C" int kagnn_csr_build(const int64_t* edge_index, int64_t E, int64_t N, int64_t N_src, int32_t* rowptr,
+                               int32_t* col, int32_t* perm, void* workspace, size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (E < 0 || N < 0 || N_src < 0 || !rowptr) return KAGNN_EINVAL;
+    if (E > 0 && (!edge_index || !col || !perm)) return KAGNN_EINVAL;
+    if (E >= INT32_MAX || N >= INT32_MAX || N_src >= INT32_MAX) return KAGNN_EUNSUPPORTED;
+    if (!workspace) return KAGNN_EWORKSPACE;
+    CsrWorkspace w = carve(workspace, E);
+    if (workspace_bytes < w.total) return KAGNN_EWORKSPACE;
+    KAGNN_CUDA_TRY(cudaMemsetAsync(w.err, 0, sizeof(int32_t), stream));
+    if (E == 0) {
+        KAGNN_CUDA_TRY(cudaMemsetAsync(rowptr, 0, (size_t)(N + 1) * sizeof(int32_t), stream));
+        return KAGNN_OK;
+    }
+    const int64_t* src = edge_index;
+    const int64_t* dst = edge_index + E;
+    unsigned blocks = (unsigned)ceil_div64(E, kThreads);
+    coo_keys_kernel<<<blocks, kThreads, 0, stream>>>(src, dst, E, N, N_src, w.keys_in, w.vals_in, w.err);
+    KAGNN_LAUNCH_CHECK();
+    size_t cub_bytes = w.cub_bytes;
+    KAGNN_CUDA_TRY(cub::DeviceRadixSort::SortPairs(w.cub_tmp, cub_bytes, w.keys_in, w.keys_out, w.vals_in, w.vals_out,
+                                                   (int)E, 0, bits_for(N), stream));
+    csr_fill_kernel<<<blocks, kThreads, 0, stream>>>(src, w.vals_out, E, N_src, col, perm);
+    KAGNN_LAUNCH_CHECK();
+    lower_bound_ptr_kernel<int32_t><<<(unsigned)ceil_div64(N + 1, kThreads), kThreads, 0, stream>>>(w.keys_out, E, N, rowptr);
+    KAGNN_LAUNCH_CHECK();
+    return KAGNN_OK;
+}
+
+extern "C" int kagnn_segment_ptr(const int64_t* batch, int64_t N, int64_t B, int32_t* ptr, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (N < 0 || B < 0 || !ptr || (N > 0 && !batch)) return KAGNN_EINVAL;
+    if (N >= INT32_MAX || B >= INT32_MAX) return KAGNN_EUNSUPPORTED;
+    lower_bound_ptr_kernel<int64_t><<<(unsigned)ceil_div64(B + 1, kThreads), kThreads, 0, stream>>>(batch, N, B, ptr);
+    KAGNN_LAUNCH_CHECK();
+    return KAGNN_OK;
+}
+
+extern "C" int kagnn_gcn_norm(const int32_t* rowptr, const int32_t* col, int64_t N, const float* w_in, float* w_out,
+                              float* self_w, float* dinv, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (N < 0 || !rowptr || !self_w || !dinv) return KAGNN_EINVAL;
+    if (N == 0) return KAGNN_OK;
+    unsigned blocks = (unsigned)ceil_div64(N * 32, kThreads);
+    gcn_degree_kernel<<<blocks, kThreads, 0, stream>>>(rowptr, col, N, w_in, dinv, self_w);
+    KAGNN_LAUNCH_CHECK();
+    gcn_edge_weight_kernel<<<blocks, kThreads, 0, stream>>>(rowptr, col, N, w_in, dinv, w_out);
+    KAGNN_LAUNCH_CHECK();
+    return KAGNN_OK;
+}
+
+extern "C" int kagnn_gather_rows(const float* x, int64_t ldx, const int32_t* index, int64_t rows, int32_t cols,
+                                 float* out, int64_t ld_out, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (rows < 0 || cols < 0 || (rows > 0 && (!x || !index || !out))) return KAGNN_EINVAL;
+    if (rows == 0 || cols == 0) return KAGNN_OK;
+    unsigned blocks = (unsigned)ceil_div64(rows * 32, kThreads);
+    bool vec = aligned16(x) && aligned16(out) && (ldx % 4 == 0) && (ld_out % 4 == 0) && (cols % 4 == 0);
+    if (vec) gather_rows_kernel<true><<<blocks, kThreads, 0, stream>>>(x, ldx, index, rows, cols, out, ld_out);
+    else gather_rows_kernel<false><<<blocks, kThreads, 0, stream>>>(x, ldx, index, rows, cols, out, ld_out);
+    KAGNN_LAUNCH_CHECK();
+    return KAGNN_OK;
+}

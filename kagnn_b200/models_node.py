@@ -1,0 +1,158 @@
+"""Node-level models: ``GKAN_Nodes`` / ``GFASTKAN_Nodes`` with the constructor signature, module tree,
+``state_dict`` keys and ``forward(x, edge_index)`` of node_classification_clean/models.py:150-257.
+
+Execution plan in eval mode (BatchNorm folded to an affine, dropout is the identity):
+
+* ``conv_type='gin'``: one launch per layer = CSR gather-sum -> conv's KAN chain -> BatchNorm affine -> store into
+  the layer's column slice of the skip-concat buffer; then one launch for ``lay_out`` over the concat buffer.
+* ``conv_type='gcn'``: ``out = A_hat . KAN(x) + b`` puts the KAN *before* the aggregation, so the fusion boundary is
+  shifted half a layer: launch 0 = KAN_1(x); launch l = [aggregate(A_hat, t_l) + b_l -> BN_l -> store h_l into the
+  concat buffer -> KAN_{l+1}(h_l)]; the last launch has no KAN; then ``lay_out``.
+
+In training mode (batch-statistics BatchNorm, dropout) each conv still runs fused, BN/dropout run as torch modules
+between launches (SURVEY.md section 8f rank 2 is the fused training epilogue)."""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+from torch import nn
+
+from . import _lib as L
+from . import ops
+from .conv import (FASTKAGCNConv, GIFASTKANLayer, GIKANLayer, KAGCNConv, GCNConv, GINConv)
+from .ekan import KANLinear, _module_backend_guard
+from .fastkan import FastKANLayer
+from .graph import get_graph
+
+Tensor = torch.Tensor
+
+
+class _BNFold:
+    """eval-mode BatchNorm1d as (scale, shift), optionally folding a preceding bias; cached per parameter version."""
+
+    def __init__(self):
+        self._key = None
+        self._val = None
+
+    def get(self, bn: nn.BatchNorm1d, pre_bias: Optional[Tensor] = None):
+        ts = [bn.weight, bn.bias, bn.running_mean, bn.running_var] + ([pre_bias] if pre_bias is not None else [])
+        key = tuple((t.data_ptr(), t._version) for t in ts if t is not None)
+        if key != self._key:
+            with torch.no_grad():
+                inv = torch.rsqrt(bn.running_var.double() + bn.eps)
+                scale = inv * (bn.weight.double() if bn.weight is not None else 1.0)
+                mean = bn.running_mean.double()
+                if pre_bias is not None:
+                    mean = mean - pre_bias.double()
+                shift = (bn.bias.double() if bn.bias is not None else 0.0) - mean * scale
+                self._val = ops.Affine(scale.float().contiguous(), shift.float().contiguous())
+            self._key = key
+        return self._val
+
+
+def bn_is_foldable(bn: nn.BatchNorm1d) -> bool:
+    return (not bn.training) and bn.track_running_stats and bn.running_mean is not None
+
+
+class _NodeModel(nn.Module):
+    """Shared forward of GKAN_Nodes / GFASTKAN_Nodes."""
+    convs: nn.ModuleList
+    bns: nn.ModuleList
+
+    def _init_common(self, skip: bool, dropout: float):
+        self.skip = skip
+        self.dropout = nn.Dropout(dropout)
+        self._folds = [_BNFold() for _ in self.bns]
+
+    def _fusable(self) -> bool:
+        drop_off = (not self.training) or self.dropout.p == 0.0
+        return drop_off and all(bn_is_foldable(bn) for bn in self.bns)
+
+    def forward(self, x: Tensor, edge_index: Tensor) -> Tensor:
+        _module_backend_guard(x, list(self.parameters()))
+        x = x.to(torch.float32)
+        n, f = x.shape
+        g = get_graph(edge_index, n)
+        hid = self.bns[0].num_features if len(self.bns) else 0
+        n_mp = len(self.convs)
+        if not self._fusable():
+            return self._forward_unfused(x, g)
+        width = f + n_mp * hid
+        if self.skip:
+            buf = torch.empty(n, width, dtype=torch.float32, device=x.device)
+            buf[:, :f].copy_(x)
+            cur = buf[:, :f]
+        else:
+            buf = None
+            cur = x
+        is_gcn = isinstance(self.convs[0], GCNConv)
+        t = self.convs[0].transform(cur) if is_gcn else None
+        for l, (conv, bn) in enumerate(zip(self.convs, self.bns)):
+            dst = buf[:, f + l * hid: f + (l + 1) * hid] if self.skip else torch.empty(n, hid, dtype=torch.float32, device=x.device)
+            if is_gcn:
+                pre = self._folds[l].get(bn, conv.bias.detach() if conv.bias is not None else None)
+                nxt = self.convs[l + 1].lin.kernel_specs() if l + 1 < n_mp else []
+                w, sw = g.gcn_weights()
+                agg = ops.AggSpec(L.AGG_WEIGHTED, t, g.rowptr, g.col, edge_weight=w, self_weight=sw)
+                t = ops.fused_layer(agg, n, nxt, pre=pre, agg_out=dst)
+            else:
+                conv(cur, g, out=dst, post=self._folds[l].get(bn))
+            cur = dst
+        return self.lay_out(buf if self.skip else cur)
+
+    def _forward_unfused(self, x: Tensor, g) -> Tensor:
+        feats = [x]
+        for conv, bn in zip(self.convs, self.bns):
+            x = conv(x, g)
+            x = bn(x)
+            x = self.dropout(x)
+            feats.append(x)
+        if self.skip:
+            x = torch.cat(feats, dim=1)
+        return self.lay_out(x)
+
+
+class GKAN_Nodes(_NodeModel):
+    def __init__(self, conv_type: str, mp_layers: int, num_features: int, hidden_channels: int, num_classes: int,
+                 skip: bool = True, grid_size: int = 4, spline_order: int = 3, hidden_layers: int = 2, dropout: float = 0.,
+                 heads=4):
+        super().__init__()
+        if conv_type == "gat":
+            raise NotImplementedError("GAT variants are out of scope of the B200 hot path (SURVEY.md section 2)")
+        if conv_type not in ("gcn", "gin"):
+            raise ValueError("unknown conv_type")
+        self.convs = nn.ModuleList()
+        self.bns = nn.ModuleList()
+        for i in range(mp_layers):
+            fin = num_features if i == 0 else hidden_channels
+            if conv_type == "gcn":
+                self.convs.append(KAGCNConv(fin, hidden_channels, grid_size, spline_order))
+            else:
+                self.convs.append(GIKANLayer(fin, hidden_channels, grid_size, spline_order, hidden_channels, hidden_layers))
+            self.bns.append(nn.BatchNorm1d(hidden_channels))
+        dim_out = num_features + mp_layers * hidden_channels if skip else hidden_channels
+        self.lay_out = KANLinear(dim_out, num_classes, grid_size=grid_size, spline_order=spline_order)
+        self._init_common(skip, dropout)
+
+
+class GFASTKAN_Nodes(_NodeModel):
+    def __init__(self, conv_type: str, mp_layers: int, num_features: int, hidden_channels: int, num_classes: int,
+                 skip: bool = True, grid_size: int = 4, hidden_layers: int = 2, dropout: float = 0., heads=4):
+        super().__init__()
+        if conv_type == "gat":
+            raise NotImplementedError("GAT variants are out of scope of the B200 hot path (SURVEY.md section 2)")
+        if conv_type not in ("gcn", "gin"):
+            raise ValueError("unknown conv_type")
+        self.convs = nn.ModuleList()
+        self.bns = nn.ModuleList()
+        for i in range(mp_layers):
+            fin = num_features if i == 0 else hidden_channels
+            if conv_type == "gcn":
+                self.convs.append(FASTKAGCNConv(fin, hidden_channels, grid_size))
+            else:
+                self.convs.append(GIFASTKANLayer(fin, hidden_channels, grid_size, hidden_channels, hidden_layers))
+            self.bns.append(nn.BatchNorm1d(hidden_channels))
+        dim_out = num_features + mp_layers * hidden_channels if skip else hidden_channels
+        self.lay_out = FastKANLayer(dim_out, num_classes, num_grids=grid_size)
+        self._init_common(skip, dropout)

@@ -1,0 +1,273 @@
+"""Thin tensor -> (pointer, sizes, stream) wrappers over the C ABI (include/kagnn_b200.h).
+
+torch is used for device memory and streams only; every arithmetic step below runs in libkagnn_b200.so.
+Nothing here falls back to torch math: a CPU tensor or a missing library raises."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib as L
+
+Tensor = torch.Tensor
+
+# launch counter: bench.py reports how many of OUR kernels ran inside the timed region
+launch_count = 0
+# optional per-launch timing: set to a list and every fused launch appends (label, start_event, end_event)
+fused_timing = None
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: Optional[Tensor]) -> Optional[C.c_void_p]:
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _need_cuda(t: Tensor, name: str, dtype=None) -> None:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"kagnn_b200: {name} must be a CUDA tensor (the sm_100a path has no CPU fallback)")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"kagnn_b200: {name} must be {dtype}, got {t.dtype}")
+
+
+def _rows(t: Tensor, name: str) -> int:
+    """Leading dimension of a 2-D fp32 row-major (possibly column-sliced) tensor."""
+    _need_cuda(t, name, torch.float32)
+    if t.dim() != 2 or (t.size(1) > 1 and t.stride(1) != 1):
+        raise ValueError(f"kagnn_b200: {name} must be 2-D with unit column stride")
+    return t.stride(0) if t.size(0) > 1 else max(t.stride(0), t.size(1))
+
+
+# ---------------------------------------------------------------------------------------------------
+# graph ingestion
+# ---------------------------------------------------------------------------------------------------
+@dataclass
+class CSR:
+    """Destination-sorted CSR of a COO ``edge_index`` (PyG flow source_to_target)."""
+    rowptr: Tensor        # (num_rows+1,) int32
+    col: Tensor           # (nnz,) int32 source row of each entry
+    perm: Tensor          # (nnz,) int32 original edge id of each entry
+    num_rows: int
+    num_src: int
+    err_flag: Tensor      # int32 scalar: non-zero if an index was out of range
+
+    @property
+    def nnz(self) -> int:
+        return int(self.col.numel())
+
+    def validate(self) -> None:
+        """Synchronising range check (the build itself never syncs)."""
+        if int(self.err_flag.item()) != 0:
+            raise IndexError("kagnn_b200: edge_index contains node ids outside [0, num_nodes)")
+
+
+def csr_build(edge_index: Tensor, num_nodes: int, num_src_nodes: Optional[int] = None) -> CSR:
+    global launch_count
+    _need_cuda(edge_index, "edge_index", torch.int64)
+    if edge_index.dim() != 2 or edge_index.size(0) != 2:
+        raise ValueError("edge_index must have shape (2, E)")
+    ei = edge_index.contiguous()
+    E = ei.size(1)
+    nsrc = num_nodes if num_src_nodes is None else num_src_nodes
+    dev = ei.device
+    rowptr = torch.empty(num_nodes + 1, dtype=torch.int32, device=dev)
+    col = torch.empty(E, dtype=torch.int32, device=dev)
+    perm = torch.empty(E, dtype=torch.int32, device=dev)
+    wbytes = L.lib().kagnn_csr_build_workspace(E, num_nodes)
+    ws = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+    L.check(L.lib().kagnn_csr_build(_p(ei), E, num_nodes, nsrc, _p(rowptr), _p(col), _p(perm), _p(ws), wbytes, _stream()),
+            "csr_build")
+    launch_count += 5 if E else 0
+    return CSR(rowptr, col, perm, num_nodes, nsrc, ws[:4].view(torch.int32))
+
+
+def segment_ptr(batch: Tensor, num_graphs: int) -> Tensor:
+    global launch_count
+    _need_cuda(batch, "batch", torch.int64)
+    b = batch.contiguous()
+    ptr = torch.empty(num_graphs + 1, dtype=torch.int32, device=b.device)
+    L.check(L.lib().kagnn_segment_ptr(_p(b), b.numel(), num_graphs, _p(ptr), _stream()), "segment_ptr")
+    launch_count += 1
+    return ptr
+
+
+def gcn_norm(csr: CSR, edge_weight_csr: Optional[Tensor] = None):
+    """PyG gcn_norm on the CSR -> (edge_weight (nnz), self_weight (N), dinv (N))."""
+    global launch_count
+    dev = csr.rowptr.device
+    n = csr.num_rows
+    w = torch.empty(csr.nnz, dtype=torch.float32, device=dev)
+    sw = torch.empty(n, dtype=torch.float32, device=dev)
+    dinv = torch.empty(n, dtype=torch.float32, device=dev)
+    if edge_weight_csr is not None:
+        _need_cuda(edge_weight_csr, "edge_weight", torch.float32)
+        edge_weight_csr = edge_weight_csr.contiguous()
+    L.check(L.lib().kagnn_gcn_norm(_p(csr.rowptr), _p(csr.col), n, _p(edge_weight_csr), _p(w), _p(sw), _p(dinv), _stream()),
+            "gcn_norm")
+    launch_count += 2
+    return w, sw, dinv
+
+
+def gather_rows(x: Tensor, index: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    global launch_count
+    ldx = _rows(x, "x")
+    _need_cuda(index, "index", torch.int32)
+    if out is None:
+        out = torch.empty(index.numel(), x.size(1), dtype=torch.float32, device=x.device)
+    ldo = _rows(out, "out")
+    L.check(L.lib().kagnn_gather_rows(_p(x), ldx, _p(index), index.numel(), x.size(1), _p(out), ldo, _stream()), "gather_rows")
+    launch_count += 1
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# weights
+# ---------------------------------------------------------------------------------------------------
+def pack_kan_weights(base_w: Optional[Tensor], spline_w: Tensor, scaler: Optional[Tensor], in_f: int, out_f: int,
+                     slots: int) -> Tensor:
+    global launch_count
+    _need_cuda(spline_w, "spline_weight", torch.float32)
+    n = L.lib().kagnn_packed_weight_elems(in_f, out_f, slots)
+    packed = torch.empty(n, dtype=torch.float32, device=spline_w.device)
+    bw = None if base_w is None else base_w.detach().contiguous()
+    sc = None if scaler is None else scaler.detach().contiguous()
+    L.check(L.lib().kagnn_pack_kan_weights(_p(bw), _p(spline_w.detach().contiguous()), _p(sc), in_f, out_f, slots, _p(packed),
+                                           _stream()), "pack_kan_weights")
+    launch_count += 1
+    return packed
+
+
+# ---------------------------------------------------------------------------------------------------
+# the fused layer
+# ---------------------------------------------------------------------------------------------------
+@dataclass
+class KanLayerSpec:
+    basis: int
+    in_features: int
+    out_features: int
+    grid_size: int
+    spline_order: int
+    t0: float
+    h: float
+    inv_denominator: float
+    packed_w: Tensor
+    base_bias: Optional[Tensor] = None
+    ln_weight: Optional[Tensor] = None
+    ln_bias: Optional[Tensor] = None
+
+    def fill(self, s: L.KagnnKanLayer) -> None:
+        s.basis, s.in_features, s.out_features = self.basis, self.in_features, self.out_features
+        s.grid_size, s.spline_order = self.grid_size, self.spline_order
+        s.t0, s.h, s.inv_denominator = self.t0, self.h, self.inv_denominator
+        s.packed_w = self.packed_w.data_ptr()
+        s.base_bias = None if self.base_bias is None else self.base_bias.data_ptr()
+        s.ln_weight = None if self.ln_weight is None else self.ln_weight.data_ptr()
+        s.ln_bias = None if self.ln_bias is None else self.ln_bias.data_ptr()
+
+
+@dataclass
+class Affine:
+    scale: Optional[Tensor] = None
+    shift: Optional[Tensor] = None
+    act: int = L.ACT_NONE
+
+    def struct(self) -> L.KagnnAffine:
+        for t, n in ((self.scale, "scale"), (self.shift, "shift")):
+            if t is not None:
+                _need_cuda(t, n, torch.float32)
+                if not t.is_contiguous():
+                    raise ValueError("affine vectors must be contiguous")
+        return L.KagnnAffine(None if self.scale is None else self.scale.data_ptr(),
+                             None if self.shift is None else self.shift.data_ptr(), self.act, 0)
+
+
+@dataclass
+class AggSpec:
+    mode: int
+    x: Tensor
+    rowptr: Optional[Tensor] = None
+    col: Optional[Tensor] = None
+    edge_weight: Optional[Tensor] = None
+    self_weight: Optional[Tensor] = None
+    self_scale: float = 1.0
+    edge_feat: Optional[Tensor] = None
+    edge_row: Optional[Tensor] = None
+    src_index: Optional[Tensor] = None
+
+    def struct(self) -> L.KagnnAggregate:
+        ldx = _rows(self.x, "x")
+        s = L.KagnnAggregate()
+        s.mode, s.num_cols = self.mode, self.x.size(1)
+        s.x, s.ldx = self.x.data_ptr(), ldx
+        for name in ("src_index", "rowptr", "col", "edge_row"):
+            t = getattr(self, name)
+            if t is not None:
+                _need_cuda(t, name, torch.int32)
+                setattr(s, name, t.data_ptr())
+        for name in ("edge_weight", "self_weight"):
+            t = getattr(self, name)
+            if t is not None:
+                _need_cuda(t, name, torch.float32)
+                setattr(s, name, t.data_ptr())
+        s.self_scale = float(self.self_scale)
+        if self.edge_feat is not None:
+            s.ld_edge = _rows(self.edge_feat, "edge_feat")
+            s.edge_feat = self.edge_feat.data_ptr()
+        return s
+
+
+def _launch_fused(agg: AggSpec, num_rows: int, layers: Sequence[KanLayerSpec], pre, post, agg_out, y) -> int:
+    if fused_timing is not None:
+        label = "agg%d[%d]%s" % (agg.mode, agg.x.size(1), "".join("->%d" % sp.out_features for sp in layers))
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        code = _launch_fused_raw(agg, num_rows, layers, pre, post, agg_out, y)
+        ev1.record()
+        fused_timing.append((label, ev0, ev1))
+        return code
+    return _launch_fused_raw(agg, num_rows, layers, pre, post, agg_out, y)
+
+
+def _launch_fused_raw(agg: AggSpec, num_rows: int, layers: Sequence[KanLayerSpec], pre, post, agg_out, y) -> int:
+    arr = (L.KagnnKanLayer * max(len(layers), 1))()
+    for i, sp in enumerate(layers):
+        sp.fill(arr[i])
+    a = agg.struct()
+    pre_s = pre.struct() if pre is not None else None
+    post_s = post.struct() if post is not None else None
+    return L.lib().kagnn_fused_layer_fwd(
+        C.byref(a), num_rows, C.byref(pre_s) if pre_s is not None else None,
+        _p(agg_out), _rows(agg_out, "agg_out") if agg_out is not None else 0,
+        len(layers), arr, C.byref(post_s) if post_s is not None else None,
+        _p(y), _rows(y, "y") if y is not None else 0, _stream())
+
+
+def fused_layer(agg: AggSpec, num_rows: int, layers: Sequence[KanLayerSpec], pre: Optional[Affine] = None,
+                post: Optional[Affine] = None, agg_out: Optional[Tensor] = None, out: Optional[Tensor] = None) -> Optional[Tensor]:
+    """tile = aggregate(x) -> pre -> [agg_out] -> KAN chain -> post -> out, in one launch
+    (kagnn_fused_layer_fwd).  Returns ``out`` (allocated if None and there is at least one layer)."""
+    global launch_count
+    if len(layers) > L.MAX_LAYERS:
+        raise NotImplementedError(f"KAN chains deeper than {L.MAX_LAYERS} are not supported")
+    dev = agg.x.device
+    if layers and out is None:
+        out = torch.empty(num_rows, layers[-1].out_features, dtype=torch.float32, device=dev)
+    if not layers and agg_out is None:
+        agg_out = torch.empty(num_rows, agg.x.size(1), dtype=torch.float32, device=dev)
+    if num_rows == 0:
+        return out if layers else agg_out
+    code = _launch_fused(agg, num_rows, layers, pre, post, agg_out, out)
+    launch_count += 1
+    if code == L.E_UNSUPPORTED and layers and (agg.mode != L.AGG_NONE or pre is not None or agg.src_index is not None):
+        # the aggregated tile is too wide for shared memory: aggregate to HBM, then stream the chain
+        tmp = agg_out if agg_out is not None else torch.empty(num_rows, agg.x.size(1), dtype=torch.float32, device=dev)
+        L.check(_launch_fused(agg, num_rows, [], pre, None, tmp, None), "fused_layer(aggregate)")
+        code = _launch_fused(AggSpec(L.AGG_NONE, tmp), num_rows, layers, None, post, None, out)
+        launch_count += 1
+    L.check(code, "fused_layer")
+    return out if layers else agg_out

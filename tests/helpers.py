@@ -46,3 +46,49 @@ def oracle_run(meta, inputs, sd, dtype=torch.float32):
     if kind == "gr":
         return K.gr_kagin_forward(sd, data, dtype=dtype) if fam.endswith("GIN") else K.gr_kagcn_forward(sd, data, dtype=dtype)
     raise ValueError(kind)
+
+
+# ---- product-side construction for the golden cases (used by the GPU parity tests) ------------------------------
+def build_product_model(meta, sd, device="cuda"):
+    """Instantiate the kagnn_b200 model that corresponds to a golden case and load the reference state_dict."""
+    import kagnn_b200 as kb
+    kind = meta["kind"]
+    sd = {k: v for k, v in sd.items() if not k.startswith("__")}
+    if kind == "kan_linear":
+        out_f, in_f, s = sd["spline_weight"].shape
+        m = kb.KANLinear(in_f, out_f, grid_size=meta["G"], spline_order=meta["k"])
+    elif kind == "kan_chain":
+        n = len([k for k in sd if k.endswith("base_weight")])
+        sizes = [sd["layers.0.base_weight"].shape[1]] + [sd[f"layers.{i}.base_weight"].shape[0] for i in range(n)]
+        m = kb.KAN(sizes, grid_size=meta["G"], spline_order=meta["k"])
+    elif kind == "fastkan_chain":
+        n = len([k for k in sd if k.endswith("base_linear.weight")])
+        sizes = [sd["layers.0.base_linear.weight"].shape[1]] + [sd[f"layers.{i}.base_linear.weight"].shape[0] for i in range(n)]
+        m = kb.FastKAN(sizes, num_grids=meta["G"])
+    elif kind == "node":
+        if meta["fast"]:
+            m = kb.GFASTKAN_Nodes(meta["conv_type"], meta["mp_layers"], meta["num_features"], meta["hidden"], meta["classes"],
+                                  skip=meta["skip"], grid_size=meta["G"], hidden_layers=meta["hidden_layers"])
+        else:
+            m = kb.GKAN_Nodes(meta["conv_type"], meta["mp_layers"], meta["num_features"], meta["hidden"], meta["classes"],
+                              skip=meta["skip"], grid_size=meta["G"], spline_order=meta["k"], hidden_layers=meta["hidden_layers"])
+    elif kind == "gc":
+        m = getattr(kb.models_graph, meta["family"])(*meta["args"])
+    elif kind == "gr":
+        m = getattr(kb.models_regr, meta["family"])(*meta["args"])
+    else:
+        raise ValueError(kind)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(device)
+    m.train(bool(meta.get("training", False)))
+    return m
+
+
+def product_run(meta, inputs, model, device="cuda"):
+    inp = {k: v.to(device) for k, v in inputs.items()}
+    with torch.no_grad():
+        if meta["kind"] in ("kan_linear", "kan_chain", "fastkan_chain"):
+            return model(inp["x"])
+        if meta["kind"] == "node":
+            return model(inp["x"], inp["edge_index"])
+        return model(K.Batch(inp["x"], inp["edge_index"], inp["batch"], inp.get("edge_attr")))
