@@ -147,6 +147,13 @@ int kagnn_fused_layer_fwd(const KagnnAggregate* agg, int64_t num_rows,
                           const KagnnAffine* post_or_null,
                           float* y, int64_t ldy, void* stream);
 
+/* Self-test of the tcgen05 machinery (descriptor encodings, TMEM addressing, bulk TMA, bf16 hi/lo split):
+ * D (128 x N) = A (128 x K) . B (N x K)^T, fp32 in/out, nprod = 1 (bf16 hi only) or 3 (hi/lo compensated).
+ * N multiple of 16 in [16,256], K multiple of 16.  Used by tests only; no reference counterpart. */
+size_t kagnn_tc_selftest_workspace(int32_t N, int32_t K);
+int kagnn_tc_selftest(const float* A, const float* B, int32_t N, int32_t K, float* D, int32_t nprod,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
 /* Row gather out[r,:] = x[index[r],:] (halo send-buffer packing for the node-sharded multi-GPU path). */
 int kagnn_gather_rows(const float* x, int64_t ldx, const int32_t* index, int64_t num_rows, int32_t num_cols,
                       float* out, int64_t ld_out, void* stream);

@@ -65,6 +65,9 @@ _SIGNATURES = {
     "kagnn_fused_layer_fwd": (C.c_int, [C.POINTER(KagnnAggregate), C.c_int64, C.POINTER(KagnnAffine), C.c_void_p, C.c_int64,
                                         C.c_int32, C.POINTER(KagnnKanLayer), C.POINTER(KagnnAffine), C.c_void_p, C.c_int64,
                                         C.c_void_p]),
+    "kagnn_tc_selftest_workspace": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "kagnn_tc_selftest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t,
+                                    C.c_void_p]),
     "kagnn_gather_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
 }
 

@@ -203,7 +203,9 @@ __device__ __forceinline__ void expand_bspline(const LayerDev& L, float x, float
             for (int r = 0; r <= d; ++r) b[r] = nb[r];
         }
     }
-    for (int c = 0; c < S; ++c) a[c * BM] = 0.f;
+    // +-inf: the reference's recursion multiplies (x - t_j) = inf by a zero indicator -> every basis is NaN (ekan.py:96-105)
+    const float fill = isinf(x) ? __int_as_float(0x7fc00000) : 0.f;
+    for (int c = 0; c < S; ++c) a[c * BM] = fill;
     if (valid) {
 #pragma unroll
         for (int r = 0; r <= 4; ++r) {

@@ -28,6 +28,19 @@ def _p(t: Optional[Tensor]) -> Optional[C.c_void_p]:
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+_dummies = {}
+
+
+def _addr(t: Tensor) -> int:
+    """Device address; an empty tensor (edgeless graph) still yields a valid non-null pointer."""
+    if t.numel() > 0:
+        return t.data_ptr()
+    key = (t.device, t.dtype)
+    if key not in _dummies:
+        _dummies[key] = torch.zeros(4, dtype=t.dtype, device=t.device)
+    return _dummies[key].data_ptr()
+
+
 def _need_cuda(t: Tensor, name: str, dtype=None) -> None:
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
         raise RuntimeError(f"kagnn_b200: {name} must be a CUDA tensor (the sm_100a path has no CPU fallback)")
@@ -203,21 +216,21 @@ class AggSpec:
         ldx = _rows(self.x, "x")
         s = L.KagnnAggregate()
         s.mode, s.num_cols = self.mode, self.x.size(1)
-        s.x, s.ldx = self.x.data_ptr(), ldx
+        s.x, s.ldx = _addr(self.x), ldx
         for name in ("src_index", "rowptr", "col", "edge_row"):
             t = getattr(self, name)
             if t is not None:
                 _need_cuda(t, name, torch.int32)
-                setattr(s, name, t.data_ptr())
+                setattr(s, name, _addr(t))
         for name in ("edge_weight", "self_weight"):
             t = getattr(self, name)
             if t is not None:
                 _need_cuda(t, name, torch.float32)
-                setattr(s, name, t.data_ptr())
+                setattr(s, name, _addr(t))
         s.self_scale = float(self.self_scale)
         if self.edge_feat is not None:
             s.ld_edge = _rows(self.edge_feat, "edge_feat")
-            s.edge_feat = self.edge_feat.data_ptr()
+            s.edge_feat = _addr(self.edge_feat)
         return s
 
 
@@ -271,3 +284,20 @@ def fused_layer(agg: AggSpec, num_rows: int, layers: Sequence[KanLayerSpec], pre
         launch_count += 1
     L.check(code, "fused_layer")
     return out if layers else agg_out
+
+
+def tc_selftest(a: Tensor, b: Tensor, nprod: int = 3) -> Tensor:
+    """D = A @ B^T for one 128-row tile through the tcgen05 path (kagnn_tc_selftest); tests only."""
+    global launch_count
+    _need_cuda(a, "A", torch.float32)
+    _need_cuda(b, "B", torch.float32)
+    a, b = a.contiguous(), b.contiguous()
+    if a.size(0) != 128 or a.size(1) != b.size(1):
+        raise ValueError("A must be (128, K) and B (N, K)")
+    n, k = b.size(0), b.size(1)
+    d = torch.empty(128, n, dtype=torch.float32, device=a.device)
+    wb = L.lib().kagnn_tc_selftest_workspace(n, k)
+    ws = torch.empty(max(wb, 16), dtype=torch.uint8, device=a.device)
+    L.check(L.lib().kagnn_tc_selftest(_p(a), _p(b), n, k, _p(d), nprod, _p(ws), wb, _stream()), "tc_selftest")
+    launch_count += 2
+    return d
