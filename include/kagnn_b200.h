@@ -78,6 +78,7 @@ typedef struct KagnnKanLayer {
     const float* base_bias; /* RBF base_linear.bias (out) or NULL                                            */
     const float* ln_weight; /* RBF LayerNorm weight (in) or NULL = no LayerNorm                              */
     const float* ln_bias;   /* RBF LayerNorm bias (in) or NULL                                               */
+    const void* packed_w_tc;/* optional: weights packed by kagnn_pack_kan_weights_tc() -> enables the tcgen05 path   */
 } KagnnKanLayer;
 
 /* Input side of the fused layer: where rows come from and how they are aggregated. */
@@ -131,6 +132,12 @@ int kagnn_pack_kan_weights(const float* base_w, const float* spline_w, const flo
                            int32_t in_features, int32_t out_features, int32_t slots,
                            float* packed, void* stream);
 
+/* Tensor-core layout of the same weights: bf16 hi/lo pairs in the UMMA K-major canonical layout, chunked in the
+ * order the tcgen05 kernel streams them (kagnn_b200/csrc/fused_tc.cu).  Supported: slots <= 8, out <= 256. */
+size_t kagnn_packed_weight_tc_bytes(int32_t in_features, int32_t out_features);
+int kagnn_pack_kan_weights_tc(const float* base_w, const float* spline_w, const float* spline_scaler_or_null,
+                              int32_t in_features, int32_t out_features, int32_t slots, void* packed, void* stream);
+
 /* ---- the hot path -------------------------------------------------------------------------------------
  * One launch: tile = aggregate(x) -> pre affine -> [optional store to agg_out] -> KAN layer 0 .. n_layers-1
  * (intermediate activations never leave the SM) -> post affine -> y.
@@ -146,6 +153,12 @@ int kagnn_fused_layer_fwd(const KagnnAggregate* agg, int64_t num_rows,
                           int32_t n_layers, const KagnnKanLayer* layers_host,
                           const KagnnAffine* post_or_null,
                           float* y, int64_t ldy, void* stream);
+
+/* Which kernel kagnn_fused_layer_fwd may use: AUTO = tcgen05 path when every layer carries packed_w_tc and the
+ * shapes fit (spline_order <= 3, G+k <= 8 or RBF G <= 8, out <= 256), else the general fp32 kernel.  Both are GPU paths. */
+enum { KAGNN_PATH_AUTO = 0, KAGNN_PATH_FP32 = 1, KAGNN_PATH_TC = 2 };
+int kagnn_set_path(int mode);
+int kagnn_get_launch_counters(int64_t* tc_launches, int64_t* fp32_launches);
 
 /* Self-test of the tcgen05 machinery (descriptor encodings, TMEM addressing, bulk TMA, bf16 hi/lo split):
  * D (128 x N) = A (128 x K) . B (N x K)^T, fp32 in/out, nprod = 1 (bf16 hi only) or 3 (hi/lo compensated).

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libkagnn_b200.so")
 BASIS_BSPLINE, BASIS_RBF = 0, 1
 AGG_NONE, AGG_GIN, AGG_GINE, AGG_WEIGHTED, AGG_SEGMENT_SUM, AGG_SEGMENT_MEAN = range(6)
 ACT_NONE, ACT_SILU = 0, 1
+PATH_AUTO, PATH_FP32, PATH_TC = 0, 1, 2
 MAX_LAYERS = 8
 
 _ERRORS = {-1: ValueError, -2: NotImplementedError, -3: ValueError, -4: RuntimeError, -5: RuntimeError, -6: IndexError}
@@ -30,6 +31,7 @@ class KagnnKanLayer(C.Structure):
         ("grid_size", C.c_int32), ("spline_order", C.c_int32),
         ("t0", C.c_float), ("h", C.c_float), ("inv_denominator", C.c_float),
         ("packed_w", C.c_void_p), ("base_bias", C.c_void_p), ("ln_weight", C.c_void_p), ("ln_bias", C.c_void_p),
+        ("packed_w_tc", C.c_void_p),
     ]
 
 
@@ -65,6 +67,10 @@ _SIGNATURES = {
     "kagnn_fused_layer_fwd": (C.c_int, [C.POINTER(KagnnAggregate), C.c_int64, C.POINTER(KagnnAffine), C.c_void_p, C.c_int64,
                                         C.c_int32, C.POINTER(KagnnKanLayer), C.POINTER(KagnnAffine), C.c_void_p, C.c_int64,
                                         C.c_void_p]),
+    "kagnn_packed_weight_tc_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "kagnn_pack_kan_weights_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "kagnn_set_path": (C.c_int, [C.c_int]),
+    "kagnn_get_launch_counters": (C.c_int, [C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "kagnn_tc_selftest_workspace": (C.c_size_t, [C.c_int32, C.c_int32]),
     "kagnn_tc_selftest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t,
                                     C.c_void_p]),

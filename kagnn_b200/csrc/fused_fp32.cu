@@ -14,6 +14,7 @@
 //                (node_classification_clean/models.py:196-201).
 // Intermediate activations of a KAN chain stay in shared memory.
 #include "common.cuh"
+#include "stage.cuh"
 
 namespace {
 
@@ -30,10 +31,10 @@ struct LayerDev {
 };
 
 struct FusedParams {
-    KagnnAggregate agg;
+    StageParams st;
     long long num_rows;
-    KagnnAffine pre, post;
-    int has_pre, has_post;
+    KagnnAffine post;
+    int has_post;
     float* agg_out;
     long long ld_agg_out;
     float* y;
@@ -43,135 +44,6 @@ struct FusedParams {
     int n_tiles, vec;
     LayerDev layers[KAGNN_MAX_LAYERS];
 };
-
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
-
-__device__ __forceinline__ float apply_affine(const KagnnAffine& a, int c, float v) {
-    if (a.scale) v *= __ldg(a.scale + c);
-    if (a.shift) v += __ldg(a.shift + c);
-    if (a.act == KAGNN_ACT_SILU) v = silu_f(v);
-    return v;
-}
-
-template <bool VEC>
-__device__ __forceinline__ void ldw(const float* p, float (&v)[4]) {
-    if (VEC) {
-        float4 t = __ldg(reinterpret_cast<const float4*>(p));
-        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-    } else {
-        v[0] = __ldg(p);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// STAGE: one warp produces one aggregated row (all feature columns) into dst (shared or global).
-// ---------------------------------------------------------------------------------------------------
-template <bool VEC>
-__device__ void stage_row(const FusedParams& p, long long i, float* __restrict__ dst, float* __restrict__ dst2, int lane) {
-    constexpr int W = VEC ? 4 : 1;
-    const KagnnAggregate& a = p.agg;
-    const int F = a.num_cols;
-    const int mode = a.mode;
-    int beg = 0, end = 0;
-    if (mode != KAGNN_AGG_NONE) {
-        beg = __ldg(a.rowptr + i);
-        end = __ldg(a.rowptr + i + 1);
-    }
-    const bool segment = (mode == KAGNN_AGG_SEGMENT_SUM) || (mode == KAGNN_AGG_SEGMENT_MEAN);
-    float self_s = 1.0f;
-    if (mode == KAGNN_AGG_GIN || mode == KAGNN_AGG_GINE) self_s = a.self_scale;
-    if (mode == KAGNN_AGG_WEIGHTED) self_s = a.self_weight ? __ldg(a.self_weight + i) : a.self_scale;
-    const float out_scale = (mode == KAGNN_AGG_SEGMENT_MEAN) ? 1.0f / (float)max(end - beg, 1) : 1.0f;
-    const long long self_row = a.src_index ? (long long)__ldg(a.src_index + i) : i;
-
-    for (int c0 = 0; c0 < F; c0 += 64 * W) {
-        const int ca = c0 + lane * W, cb = ca + 32 * W;
-        const bool va = ca < F, vb = cb < F;
-        float acc_a[4] = {0.f, 0.f, 0.f, 0.f}, acc_b[4] = {0.f, 0.f, 0.f, 0.f};
-        if (!segment) {
-            const float* xr = a.x + self_row * a.ldx;
-            float t[4];
-            if (va) { ldw<VEC>(xr + ca, t);
-#pragma unroll
-                for (int q = 0; q < W; ++q) acc_a[q] = self_s * t[q]; }
-            if (vb) { ldw<VEC>(xr + cb, t);
-#pragma unroll
-                for (int q = 0; q < W; ++q) acc_b[q] = self_s * t[q]; }
-        }
-        for (int e0 = beg; e0 < end; e0 += 32) {
-            const int cnt = min(32, end - e0);
-            int my_j = 0, my_er = 0;
-            float my_w = 1.0f;
-            if (lane < cnt) {
-                my_j = a.col ? __ldg(a.col + e0 + lane) : (e0 + lane);
-                if (a.src_index) my_j = __ldg(a.src_index + my_j);
-                if (mode == KAGNN_AGG_WEIGHTED) my_w = __ldg(a.edge_weight + e0 + lane);
-                if (mode == KAGNN_AGG_GINE) my_er = __ldg(a.edge_row + e0 + lane);
-            }
-            for (int t0 = 0; t0 < cnt; t0 += 4) {
-                float va4[4][4], vb4[4][4], ea4[4][4], eb4[4][4], w4[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int src_lane = min(t0 + u, cnt - 1);
-                    const int j = __shfl_sync(0xffffffffu, my_j, src_lane);
-                    w4[u] = __shfl_sync(0xffffffffu, my_w, src_lane);
-                    const int er = __shfl_sync(0xffffffffu, my_er, src_lane);
-                    const bool on = (t0 + u) < cnt;
-                    const float* xr = a.x + (long long)j * a.ldx;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) { va4[u][q] = 0.f; vb4[u][q] = 0.f; ea4[u][q] = 0.f; eb4[u][q] = 0.f; }
-                    if (on && va) ldw<VEC>(xr + ca, va4[u]);
-                    if (on && vb) ldw<VEC>(xr + cb, vb4[u]);
-                    if (mode == KAGNN_AGG_GINE) {
-                        const float* er_p = a.edge_feat + (long long)er * a.ld_edge;
-                        if (on && va) ldw<VEC>(er_p + ca, ea4[u]);
-                        if (on && vb) ldw<VEC>(er_p + cb, eb4[u]);
-                    }
-                    if (!on) w4[u] = 0.f;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const bool on = (t0 + u) < cnt;
-                    if (mode == KAGNN_AGG_GINE) {
-                        if (on) {
-#pragma unroll
-                            for (int q = 0; q < W; ++q) {
-                                acc_a[q] += fmaxf(va4[u][q] + ea4[u][q], 0.f);
-                                acc_b[q] += fmaxf(vb4[u][q] + eb4[u][q], 0.f);
-                            }
-                        }
-                    } else if (mode == KAGNN_AGG_WEIGHTED) {
-#pragma unroll
-                        for (int q = 0; q < W; ++q) {
-                            acc_a[q] = fmaf(w4[u], va4[u][q], acc_a[q]);
-                            acc_b[q] = fmaf(w4[u], vb4[u][q], acc_b[q]);
-                        }
-                    } else {
-                        if (on) {
-#pragma unroll
-                            for (int q = 0; q < W; ++q) { acc_a[q] += va4[u][q]; acc_b[q] += vb4[u][q]; }
-                        }
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < W; ++q) {
-            if (va) {
-                float v = acc_a[q] * out_scale;
-                if (p.has_pre) v = apply_affine(p.pre, ca + q, v);
-                dst[ca + q] = v;
-                if (dst2) dst2[ca + q] = v;
-            }
-            if (vb) {
-                float v = acc_b[q] * out_scale;
-                if (p.has_pre) v = apply_affine(p.pre, cb + q, v);
-                dst[cb + q] = v;
-                if (dst2) dst2[cb + q] = v;
-            }
-        }
-    }
-}
 
 // ---------------------------------------------------------------------------------------------------
 // Basis expansion of one (row, feature) pair into column r of the [slot][BM] block at `a`.
@@ -350,7 +222,7 @@ __global__ void __launch_bounds__(NT) fused_layer_kernel(const __grid_constant__
         const int nrows = (int)min((long long)BM, p.num_rows - row0);
         if (p.n_layers == 0) {  // pure aggregation straight to global
             for (int r = warp; r < nrows; r += NWARPS)
-                stage_row<VEC>(p, row0 + r, p.agg_out + (row0 + r) * p.ld_agg_out, nullptr, lane);
+                stage_row<VEC>(p.st, row0 + r, p.agg_out + (row0 + r) * p.ld_agg_out, nullptr, lane);
             continue;
         }
         const float* cur;
@@ -361,14 +233,14 @@ __global__ void __launch_bounds__(NT) fused_layer_kernel(const __grid_constant__
             for (int r = warp; r < BM; r += NWARPS) {
                 float* drow = bufA + (size_t)r * p.ld_a;
                 if (r < nrows) {
-                    stage_row<VEC>(p, row0 + r, drow, p.agg_out ? p.agg_out + (row0 + r) * p.ld_agg_out : nullptr, lane);
+                    stage_row<VEC>(p.st, row0 + r, drow, p.agg_out ? p.agg_out + (row0 + r) * p.ld_agg_out : nullptr, lane);
                 } else {
-                    for (int c = lane; c < p.agg.num_cols; c += 32) drow[c] = 0.f;
+                    for (int c = lane; c < p.st.agg.num_cols; c += 32) drow[c] = 0.f;
                 }
             }
             cur = bufA; ld_cur = p.ld_a; cur_rows = BM;
         } else {
-            cur = p.agg.x + row0 * p.agg.ldx; ld_cur = p.agg.ldx; cur_rows = nrows;
+            cur = p.st.agg.x + row0 * p.st.agg.ldx; ld_cur = p.st.agg.ldx; cur_rows = nrows;
         }
         for (int l = 0; l < p.n_layers; ++l) {
             const LayerDev& L = p.layers[l];
@@ -386,35 +258,23 @@ __global__ void __launch_bounds__(NT) fused_layer_kernel(const __grid_constant__
 
 }  // namespace
 
-extern "C" int kagnn_fused_layer_fwd(const KagnnAggregate* agg, int64_t num_rows, const KagnnAffine* pre,
-                                     float* agg_out, int64_t ld_agg_out, int32_t n_layers,
-                                     const KagnnKanLayer* layers, const KagnnAffine* post, float* y, int64_t ldy,
-                                     void* stream_) {
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    if (!agg || num_rows < 0 || n_layers < 0 || n_layers > KAGNN_MAX_LAYERS) return KAGNN_EINVAL;
-    if (n_layers > 0 && (!layers || !y)) return KAGNN_EINVAL;
-    if (n_layers == 0 && !agg_out) return KAGNN_EINVAL;
-    if (agg->mode < KAGNN_AGG_NONE || agg->mode > KAGNN_AGG_SEGMENT_MEAN) return KAGNN_EINVAL;
-    if (agg->num_cols <= 0 || !agg->x || agg->ldx < agg->num_cols) return KAGNN_EINVAL;
-    if (agg->mode != KAGNN_AGG_NONE && !agg->rowptr) return KAGNN_EINVAL;
-    const bool segment = agg->mode == KAGNN_AGG_SEGMENT_SUM || agg->mode == KAGNN_AGG_SEGMENT_MEAN;
-    if (agg->mode != KAGNN_AGG_NONE && !segment && !agg->col) return KAGNN_EINVAL;
-    if (agg->mode == KAGNN_AGG_WEIGHTED && !agg->edge_weight) return KAGNN_EINVAL;
-    if (agg->mode == KAGNN_AGG_GINE && (!agg->edge_feat || !agg->edge_row || agg->ld_edge < agg->num_cols)) return KAGNN_EINVAL;
-    if (agg_out && ld_agg_out < agg->num_cols) return KAGNN_EINVAL;
+int kagnn_fused_fwd_fp32(const KagnnAggregate* agg, int64_t num_rows, const KagnnAffine* pre, float* agg_out,
+                         int64_t ld_agg_out, int32_t n_layers, const KagnnKanLayer* layers, const KagnnAffine* post,
+                         float* y, int64_t ldy, cudaStream_t stream) {
+    int vrc = kagnn_validate_fused_args(agg, num_rows, agg_out, ld_agg_out, n_layers, layers, y);
+    if (vrc != KAGNN_OK) return vrc;
     if (num_rows == 0) return KAGNN_OK;
-    if (num_rows > (int64_t)INT32_MAX * 32) return KAGNN_EUNSUPPORTED;
 
     DeviceProps props{};
     int rc = kagnn_get_props(&props);
     if (rc != KAGNN_OK) return rc;
 
     FusedParams p{};
-    p.agg = *agg;
+    p.st.agg = *agg;
+    p.st.has_pre = pre != nullptr;
+    if (pre) p.st.pre = *pre;
     p.num_rows = num_rows;
-    p.has_pre = pre != nullptr;
     p.has_post = post != nullptr;
-    if (pre) p.pre = *pre;
     if (post) p.post = *post;
     p.agg_out = agg_out;
     p.ld_agg_out = ld_agg_out;

@@ -140,8 +140,13 @@ class KANLinear(nn.Module):
             packed = ops.pack_kan_weights(self.base_weight, self.spline_weight,
                                           self.spline_scaler if self.enable_standalone_scale_spline else None,
                                           self.in_features, self.out_features, slots)
+            scaler = self.spline_scaler if self.enable_standalone_scale_spline else None
+            packed_tc = None
+            if ops.tc_supported(L.BASIS_BSPLINE, self.grid_size, self.spline_order, self.out_features):
+                packed_tc = ops.pack_kan_weights_tc(self.base_weight, self.spline_weight, scaler, self.in_features,
+                                                    self.out_features, slots)
             self._cache_spec = ops.KanLayerSpec(L.BASIS_BSPLINE, self.in_features, self.out_features, self.grid_size,
-                                                self.spline_order, t0, h, 0.0, packed)
+                                                self.spline_order, t0, h, 0.0, packed, packed_w_tc=packed_tc)
             self._cache_key = key
         return self._cache_spec
 

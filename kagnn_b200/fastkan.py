@@ -84,6 +84,10 @@ class FastKANLayer(nn.Module):
                     raise NotImplementedError("non-uniform RBF centres are not supported by the sm_100a path")
             packed = ops.pack_kan_weights(self.base_linear.weight if self.use_base_update else None,
                                           self.spline_linear.weight, None, self.input_dim, self.output_dim, G)
+            packed_tc = None
+            if ops.tc_supported(L.BASIS_RBF, G, 0, self.output_dim):
+                packed_tc = ops.pack_kan_weights_tc(self.base_linear.weight if self.use_base_update else None,
+                                                    self.spline_linear.weight, None, self.input_dim, self.output_dim, G)
             ln = self.layernorm
             if ln is not None and abs(ln.eps - 1e-5) > 1e-12:
                 raise NotImplementedError("LayerNorm eps other than 1e-5 is not supported")
@@ -91,7 +95,7 @@ class FastKANLayer(nn.Module):
                 L.BASIS_RBF, self.input_dim, self.output_dim, G, 0, gmin, step, 1.0 / float(self.rbf.denominator), packed,
                 base_bias=self.base_linear.bias.detach() if self.use_base_update else None,
                 ln_weight=None if ln is None else ln.weight.detach(),
-                ln_bias=None if ln is None else ln.bias.detach())
+                ln_bias=None if ln is None else ln.bias.detach(), packed_w_tc=packed_tc)
             self._cache_key = key
         return self._cache_spec
 

@@ -155,6 +155,41 @@ def pack_kan_weights(base_w: Optional[Tensor], spline_w: Tensor, scaler: Optiona
     return packed
 
 
+def tc_supported(basis: int, grid_size: int, spline_order: int, out_features: int) -> bool:
+    """Shapes the tcgen05 kernel handles (8 slots per feature, <= 4 non-zero bases, N <= 256)."""
+    if out_features > 256:
+        return False
+    if basis == L.BASIS_BSPLINE:
+        return 1 <= spline_order <= 3 and grid_size + spline_order <= 8
+    return 1 <= grid_size <= 8
+
+
+def pack_kan_weights_tc(base_w: Optional[Tensor], spline_w: Tensor, scaler: Optional[Tensor], in_f: int, out_f: int,
+                        slots: int) -> Tensor:
+    """bf16 hi/lo weights in the UMMA canonical layout, chunked for the tcgen05 kernel."""
+    global launch_count
+    _need_cuda(spline_w, "spline_weight", torch.float32)
+    nbytes = L.lib().kagnn_packed_weight_tc_bytes(in_f, out_f)
+    packed = torch.empty(nbytes, dtype=torch.uint8, device=spline_w.device)
+    bw = None if base_w is None else base_w.detach().contiguous()
+    sc = None if scaler is None else scaler.detach().contiguous()
+    L.check(L.lib().kagnn_pack_kan_weights_tc(_p(bw), _p(spline_w.detach().contiguous()), _p(sc), in_f, out_f, slots, _p(packed),
+                                              _stream()), "pack_kan_weights_tc")
+    launch_count += 2
+    return packed
+
+
+def set_path(mode: int) -> None:
+    """PATH_AUTO / PATH_FP32 / PATH_TC (see kagnn_set_path)."""
+    L.check(L.lib().kagnn_set_path(mode), "set_path")
+
+
+def launch_counters():
+    a, b = C.c_int64(0), C.c_int64(0)
+    L.lib().kagnn_get_launch_counters(C.byref(a), C.byref(b))
+    return {"tc": a.value, "fp32": b.value}
+
+
 # ---------------------------------------------------------------------------------------------------
 # the fused layer
 # ---------------------------------------------------------------------------------------------------
@@ -172,6 +207,7 @@ class KanLayerSpec:
     base_bias: Optional[Tensor] = None
     ln_weight: Optional[Tensor] = None
     ln_bias: Optional[Tensor] = None
+    packed_w_tc: Optional[Tensor] = None
 
     def fill(self, s: L.KagnnKanLayer) -> None:
         s.basis, s.in_features, s.out_features = self.basis, self.in_features, self.out_features
@@ -181,6 +217,7 @@ class KanLayerSpec:
         s.base_bias = None if self.base_bias is None else self.base_bias.data_ptr()
         s.ln_weight = None if self.ln_weight is None else self.ln_weight.data_ptr()
         s.ln_bias = None if self.ln_bias is None else self.ln_bias.data_ptr()
+        s.packed_w_tc = None if self.packed_w_tc is None else self.packed_w_tc.data_ptr()
 
 
 @dataclass

@@ -40,7 +40,7 @@ def test_host_only_queries_need_no_gpu():
 def test_struct_layouts_match_the_header():
     from kagnn_b200 import _lib
     assert ctypes.sizeof(_lib.KagnnAffine) == 24
-    assert ctypes.sizeof(_lib.KagnnKanLayer) == 64
+    assert ctypes.sizeof(_lib.KagnnKanLayer) == 72
     assert ctypes.sizeof(_lib.KagnnAggregate) == 96
 
 

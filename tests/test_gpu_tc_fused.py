@@ -1,0 +1,161 @@
+"""GPU parity tests of the tcgen05 fused kernel (fused_tc.cu): forced onto the tensor-core path, compared with the
+CPU oracle and with the general fp32 kernel on the same inputs.  Tolerance 1e-4 relative (BASELINE.json)."""
+import pytest
+import torch
+
+from oracle import kagnn_oracle as K
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _sd_cpu(m):
+    return {k: v.detach().cpu() for k, v in m.state_dict().items()}
+
+
+@pytest.fixture
+def tc_only():
+    from kagnn_b200 import ops, _lib as L
+    ops.set_path(L.PATH_TC)
+    yield
+    ops.set_path(L.PATH_AUTO)
+
+
+@pytest.mark.parametrize("G,k,fin,fout,n", [
+    (5, 3, 16, 16, 128), (5, 3, 128, 64, 1000), (5, 3, 64, 64, 4097), (4, 3, 7, 1, 130), (5, 3, 320, 40, 513),
+    (2, 2, 33, 17, 64), (3, 1, 5, 200, 77), (5, 3, 128, 128, 2048), (5, 3, 1433, 32, 300), (5, 3, 256, 256, 500),
+])
+def test_kan_linear_tc(tc_only, G, k, fin, fout, n):
+    import kagnn_b200 as kb
+    from kagnn_b200 import ops
+    torch.manual_seed(G * 1000 + fin)
+    m = kb.KANLinear(fin, fout, grid_size=G, spline_order=k)
+    x = torch.randn(n, fin) * 0.9
+    y_ref = K._kan_layer_from_sd(_sd_cpu(m), "", x)
+    c0 = ops.launch_counters()["tc"]
+    with torch.no_grad():
+        y = m.cuda()(x.cuda()).cpu()
+    assert ops.launch_counters()["tc"] == c0 + 1
+    assert K.rel_err(y, y_ref) <= TOL
+
+
+def test_kan_special_values_tc(tc_only):
+    import kagnn_b200 as kb
+    torch.manual_seed(3)
+    m = kb.KANLinear(6, 5, grid_size=5, spline_order=3)
+    knots = m.grid[0].clone()
+    x = torch.zeros(8, 6)
+    x[0] = knots[:6]
+    x[1] = knots[6:12]
+    x[2] = 1e4
+    x[3] = -1e4
+    x[4] = torch.tensor([0.0, -0.0, 1e-30, -1e-30, 2.2, -2.2])
+    x[5] = float("inf")
+    x[6] = float("nan")
+    x[7] = torch.nextafter(knots[-1], torch.tensor(0.0))
+    y_ref = K._kan_layer_from_sd(_sd_cpu(m), "", x)
+    with torch.no_grad():
+        y = m.cuda()(x.cuda()).cpu()
+    fin = torch.isfinite(y_ref).all(1)
+    assert K.rel_err(y[fin], y_ref[fin]) <= TOL
+    assert torch.isnan(y[6]).all() and torch.isnan(y[5]).all()
+
+
+@pytest.mark.parametrize("sizes,G,k,n", [([128, 64, 64], 5, 3, 3000), ([64, 64, 64], 5, 3, 777), ([128, 128, 128], 5, 3, 515),
+                                         ([30, 9, 9, 9, 9, 3], 4, 2, 129), ([320, 40], 5, 3, 1000)])
+def test_kan_chain_tc(tc_only, sizes, G, k, n):
+    import kagnn_b200 as kb
+    torch.manual_seed(len(sizes) + G)
+    m = kb.KAN(sizes, grid_size=G, spline_order=k)
+    x = torch.randn(n, sizes[0])
+    y_ref = K.kan_chain(_sd_cpu(m), "layers.", x)
+    with torch.no_grad():
+        y = m.cuda()(x.cuda()).cpu()
+    assert K.rel_err(y, y_ref) <= TOL
+
+
+@pytest.mark.parametrize("sizes,G,n", [([256, 256, 256], 8, 700), ([7, 256, 256], 8, 333), ([64, 32, 16, 8, 4], 5, 129),
+                                       ([20, 200], 3, 70), ([1433, 16], 4, 100)])
+def test_fastkan_tc(tc_only, sizes, G, n):
+    import kagnn_b200 as kb
+    torch.manual_seed(len(sizes) * 17 + G)
+    m = kb.FastKAN(sizes, num_grids=G)
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.dim() == 1 and p.requires_grad:
+                p.add_(torch.randn_like(p) * 0.1)
+    x = torch.randn(n, sizes[0]) * 2.0
+    y_ref = K.fastkan_chain(_sd_cpu(m), "layers.", x)
+    with torch.no_grad():
+        y = m.cuda()(x.cuda()).cpu()
+    assert K.rel_err(y, y_ref) <= TOL
+
+
+def _rand_graph(n, e, seed):
+    g = torch.Generator().manual_seed(seed)
+    ei = torch.randint(0, n, (2, e), generator=g)
+    if e > 20:
+        ei[1, :10] = ei[0, :10]
+        ei[:, 10:15] = ei[:, 15:20]
+    return ei
+
+
+def test_fused_gin_layer_tc_matches_oracle_and_fp32(tc_only):
+    import kagnn_b200 as kb
+    from kagnn_b200 import ops, _lib as L
+    torch.manual_seed(5)
+    n, e, f, h = 5000, 40000, 128, 64
+    ei = _rand_graph(n, e, 99)
+    x = torch.randn(n, f) * 0.5
+    gin = kb.GIKANLayer(f, h, 5, 3, h, 2)
+    sd = _sd_cpu(gin)
+    ref = K.gin_conv(x, ei, lambda t: K.kan_chain(sd, "nn.layers.", t))
+    gin = gin.cuda()
+    with torch.no_grad():
+        out_tc = gin(x.cuda(), ei.cuda()).cpu()
+        ops.set_path(L.PATH_FP32)
+        out_fp = gin(x.cuda(), ei.cuda()).cpu()
+        ops.set_path(L.PATH_TC)
+    assert K.rel_err(out_tc, ref) <= TOL
+    assert K.rel_err(out_fp, ref) <= TOL
+    assert K.rel_err(out_tc, out_fp) <= 5e-5
+
+
+def test_gine_and_gcn_tc(tc_only):
+    import kagnn_b200 as kb
+    torch.manual_seed(6)
+    n, e, f, h = 700, 5000, 32, 16
+    ei = _rand_graph(n, e, 7)
+    x = torch.randn(n, f)
+    ea = torch.randn(e, f)
+    gine = kb.GINEConv(kb.make_kan(f, 16, h, 2, 4, 3))
+    sd = _sd_cpu(gine)
+    ref = K.gine_conv(x, ei, ea, lambda t: K.kan_chain(sd, "nn.layers.", t))
+    with torch.no_grad():
+        out = gine.cuda()(x.cuda(), ei.cuda(), ea.cuda()).cpu()
+    assert K.rel_err(out, ref) <= TOL
+
+
+def test_node_model_auto_path_uses_tc_and_matches():
+    import kagnn_b200 as kb
+    from kagnn_b200 import ops
+    torch.manual_seed(12)
+    n, e, f = 20000, 150000, 128
+    for conv in ("gin", "gcn"):
+        m = kb.GKAN_Nodes(conv, 3, f, 64, 40, skip=True, grid_size=5, spline_order=3, hidden_layers=2).eval()
+        with torch.no_grad():
+            for name, b in m.named_buffers():
+                if name.endswith("running_var"):
+                    b.uniform_(0.01, 0.05)
+            for name, p_ in m.named_parameters():
+                if name.endswith("bias") and p_.dim() == 1:
+                    p_.normal_(0, 0.2)
+        ei = _rand_graph(n, e, 3)
+        x = torch.randn(n, f) * 0.3
+        y_ref = K.node_model_forward(_sd_cpu(m), conv, x, ei, True)
+        c0 = ops.launch_counters()
+        with torch.no_grad():
+            y = m.cuda()(x.cuda(), ei.cuda()).cpu()
+        c1 = ops.launch_counters()
+        assert c1["tc"] - c0["tc"] >= 4, (c0, c1)
+        assert K.rel_err(y, y_ref) <= TOL, conv
