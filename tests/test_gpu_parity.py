@@ -16,8 +16,17 @@ def _sd_cpu(m):
     return {k: v.detach().cpu() for k, v in m.state_dict().items()}
 
 
+@pytest.fixture(params=["auto", "fp32"])
+def path_mode(request):
+    """auto = tcgen05 kernel wherever it applies; fp32 = force the general CUDA-core kernel (both are GPU paths)."""
+    from kagnn_b200 import ops, _lib as L
+    ops.set_path(L.PATH_FP32 if request.param == "fp32" else L.PATH_AUTO)
+    yield request.param
+    ops.set_path(L.PATH_AUTO)
+
+
 @pytest.mark.parametrize("name", golden_names())
-def test_golden_vectors(name):
+def test_golden_vectors(name, path_mode):
     meta, inputs, sd, y_ref = load_golden(name)
     model = build_product_model(meta, sd)
     y = product_run(meta, inputs, model).cpu()
