@@ -97,6 +97,12 @@ typedef struct KagnnAggregate {
     const float* edge_feat;   /* GINE: edge features, row r = edge_feat[edge_index_of(r)*ld_edge ...]         */
     int64_t ld_edge;
     const int32_t* edge_row;  /* GINE: (nnz) row of edge_feat for each CSR entry (perm or table code)        */
+    /* Node-sharded graphs: source rows >= num_local_src are halo rows (copies of rows owned by other ranks,
+     * filled by the per-layer all-to-all) and live in a second matrix: row j reads
+     * x_halo[(j - num_local_src) * ld_halo ...].  x_halo == NULL: every source row is in x.                  */
+    const float* x_halo;
+    int64_t ld_halo;
+    int64_t num_local_src;
 } KagnnAggregate;
 
 /* ---- library ------------------------------------------------------------------------------------ */
@@ -122,6 +128,13 @@ int kagnn_segment_ptr(const int64_t* batch, int64_t num_nodes, int64_t num_graph
  * edge_weight_in: optional user weights in CSR order (NULL = ones).  dinv: (N) scratch/output. */
 int kagnn_gcn_norm(const int32_t* rowptr, const int32_t* col, int64_t num_nodes, const float* edge_weight_in,
                    float* edge_weight_out, float* self_weight_out, float* dinv, void* stream);
+/* The two halves of kagnn_gcn_norm, for node-sharded graphs where dinv of halo source rows comes from their owners:
+ * kagnn_gcn_degree fills dinv / self_weight of the num_nodes destination rows; kagnn_gcn_edge_weight reads
+ * dinv_src[col[e]] (col may address halo rows, dinv_src has num_src entries) and dinv_dst[row]. */
+int kagnn_gcn_degree(const int32_t* rowptr, const int32_t* col, int64_t num_nodes, const float* edge_weight_in,
+                     float* self_weight_out, float* dinv, void* stream);
+int kagnn_gcn_edge_weight(const int32_t* rowptr, const int32_t* col, int64_t num_nodes, const float* edge_weight_in,
+                          const float* dinv_src, const float* dinv_dst, float* edge_weight_out, void* stream);
 
 /* ---- weights -------------------------------------------------------------------------------------- */
 /* scaled_spline_weight (nc/ekan.py:146-152) folded while packing:
@@ -167,7 +180,8 @@ size_t kagnn_tc_selftest_workspace(int32_t N, int32_t K);
 int kagnn_tc_selftest(const float* A, const float* B, int32_t N, int32_t K, float* D, int32_t nprod,
                       void* workspace, size_t workspace_bytes, void* stream);
 
-/* Row gather out[r,:] = x[index[r],:] (halo send-buffer packing for the node-sharded multi-GPU path). */
+/* Row gather out[r,:] = x[index[r],:] (halo send-buffer packing for the node-sharded multi-GPU path);
+ * index == NULL copies rows 0..num_rows-1 (strided row copy). */
 int kagnn_gather_rows(const float* x, int64_t ldx, const int32_t* index, int64_t num_rows, int32_t num_cols,
                       float* out, int64_t ld_out, void* stream);
 

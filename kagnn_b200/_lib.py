@@ -43,6 +43,7 @@ class KagnnAggregate(C.Structure):
         ("edge_weight", C.c_void_p), ("self_weight", C.c_void_p),
         ("self_scale", C.c_float), ("_pad", C.c_int32),
         ("edge_feat", C.c_void_p), ("ld_edge", C.c_int64), ("edge_row", C.c_void_p),
+        ("x_halo", C.c_void_p), ("ld_halo", C.c_int64), ("num_local_src", C.c_int64),
     ]
 
 
@@ -62,6 +63,9 @@ _SIGNATURES = {
                                   C.c_void_p, C.c_size_t, C.c_void_p]),
     "kagnn_segment_ptr": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "kagnn_gcn_norm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "kagnn_gcn_degree": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "kagnn_gcn_edge_weight": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p]),
     "kagnn_packed_weight_elems": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "kagnn_pack_kan_weights": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "kagnn_fused_layer_fwd": (C.c_int, [C.POINTER(KagnnAggregate), C.c_int64, C.POINTER(KagnnAffine), C.c_void_p, C.c_int64,

@@ -23,6 +23,8 @@ int kagnn_validate_fused_args(const KagnnAggregate* agg, int64_t num_rows, const
     if (agg->mode == KAGNN_AGG_WEIGHTED && !agg->edge_weight) return KAGNN_EINVAL;
     if (agg->mode == KAGNN_AGG_GINE && (!agg->edge_feat || !agg->edge_row || agg->ld_edge < agg->num_cols)) return KAGNN_EINVAL;
     if (agg_out && ld_agg_out < agg->num_cols) return KAGNN_EINVAL;
+    if (agg->x_halo && (agg->ld_halo < agg->num_cols || agg->num_local_src < 0)) return KAGNN_EINVAL;
+    if (agg->x_halo && (agg->mode == KAGNN_AGG_NONE || agg->src_index)) return KAGNN_EINVAL;
     if (num_rows > (int64_t)INT32_MAX * 32) return KAGNN_EUNSUPPORTED;
 
     return KAGNN_OK;

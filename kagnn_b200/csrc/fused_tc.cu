@@ -557,6 +557,7 @@ int kagnn_fused_fwd_tc(const KagnnAggregate* agg, int64_t num_rows, const KagnnA
 
     bool vec = (agg->num_cols % 4 == 0) && aligned16(agg->x) && (agg->ldx % 4 == 0);
     if (agg->mode == KAGNN_AGG_GINE) vec = vec && aligned16(agg->edge_feat) && (agg->ld_edge % 4 == 0);
+    if (agg->x_halo) vec = vec && aligned16(agg->x_halo) && (agg->ld_halo % 4 == 0);
     p.vec = vec;
     p.y_vec = aligned16(y) && (ldy % 4 == 0);
 

@@ -81,12 +81,12 @@ __global__ void gcn_degree_kernel(const int32_t* __restrict__ rowptr, const int3
 
 __global__ void gcn_edge_weight_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n,
                                        const float* __restrict__ w_in, const float* __restrict__ dinv,
-                                       float* __restrict__ w_out) {
+                                       const float* __restrict__ dinv_dst, float* __restrict__ w_out) {
     int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (row >= n) return;
     int beg = rowptr[row], end = rowptr[row + 1];
-    float di = dinv[row];
+    float di = dinv_dst[row];
     for (int e = beg + lane; e < end; e += 32) {
         int c = col[e];
         float w = w_in ? w_in[e] : 1.f;
@@ -100,7 +100,7 @@ __global__ void gather_rows_kernel(const float* __restrict__ x, int64_t ldx, con
     int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (r >= rows) return;
-    const float* src = x + (int64_t)index[r] * ldx;
+    const float* src = x + (int64_t)(index ? index[r] : (int32_t)r) * ldx;
     float* dst = out + r * ld_out;
     if (VEC) {
         for (int c = lane * 4; c < cols; c += 128)
@@ -192,23 +192,39 @@ extern "C" int kagnn_segment_ptr(const int64_t* batch, int64_t N, int64_t B, int
     return KAGNN_OK;
 }
 
-extern "C" int kagnn_gcn_norm(const int32_t* rowptr, const int32_t* col, int64_t N, const float* w_in, float* w_out,
-                              float* self_w, float* dinv, void* stream_) {
+extern "C" int kagnn_gcn_degree(const int32_t* rowptr, const int32_t* col, int64_t N, const float* w_in, float* self_w,
+                                float* dinv, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (N < 0 || !rowptr || !self_w || !dinv) return KAGNN_EINVAL;
     if (N == 0) return KAGNN_OK;
     unsigned blocks = (unsigned)ceil_div64(N * 32, kThreads);
     gcn_degree_kernel<<<blocks, kThreads, 0, stream>>>(rowptr, col, N, w_in, dinv, self_w);
     KAGNN_LAUNCH_CHECK();
-    gcn_edge_weight_kernel<<<blocks, kThreads, 0, stream>>>(rowptr, col, N, w_in, dinv, w_out);
+    return KAGNN_OK;
+}
+
+extern "C" int kagnn_gcn_edge_weight(const int32_t* rowptr, const int32_t* col, int64_t N, const float* w_in,
+                                     const float* dinv_src, const float* dinv_dst, float* w_out, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (N < 0 || !rowptr || !dinv_src || !dinv_dst) return KAGNN_EINVAL;
+    if (N == 0) return KAGNN_OK;
+    unsigned blocks = (unsigned)ceil_div64(N * 32, kThreads);
+    gcn_edge_weight_kernel<<<blocks, kThreads, 0, stream>>>(rowptr, col, N, w_in, dinv_src, dinv_dst, w_out);
     KAGNN_LAUNCH_CHECK();
     return KAGNN_OK;
+}
+
+extern "C" int kagnn_gcn_norm(const int32_t* rowptr, const int32_t* col, int64_t N, const float* w_in, float* w_out,
+                              float* self_w, float* dinv, void* stream_) {
+    int rc = kagnn_gcn_degree(rowptr, col, N, w_in, self_w, dinv, stream_);
+    if (rc != KAGNN_OK) return rc;
+    return kagnn_gcn_edge_weight(rowptr, col, N, w_in, dinv, dinv, w_out, stream_);
 }
 
 extern "C" int kagnn_gather_rows(const float* x, int64_t ldx, const int32_t* index, int64_t rows, int32_t cols,
                                  float* out, int64_t ld_out, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    if (rows < 0 || cols < 0 || (rows > 0 && (!x || !index || !out))) return KAGNN_EINVAL;
+    if (rows < 0 || cols < 0 || (rows > 0 && (!x || !out))) return KAGNN_EINVAL;
     if (rows == 0 || cols == 0) return KAGNN_OK;
     unsigned blocks = (unsigned)ceil_div64(rows * 32, kThreads);
     bool vec = aligned16(x) && aligned16(out) && (ldx % 4 == 0) && (ld_out % 4 == 0) && (cols % 4 == 0);

@@ -25,6 +25,12 @@ __device__ __forceinline__ float apply_affine(const KagnnAffine& a, int c, float
     return v;
 }
 
+// source row j of the (possibly node-sharded) feature matrix: owned rows in x, halo rows in x_halo
+__device__ __forceinline__ const float* src_row(const KagnnAggregate& a, long long j) {
+    if (a.x_halo != nullptr && j >= a.num_local_src) return a.x_halo + (j - a.num_local_src) * a.ld_halo;
+    return a.x + j * a.ldx;
+}
+
 template <bool VEC>
 __device__ __forceinline__ void ldw(const float* p, float (&v)[4]) {
     if (VEC) {
@@ -89,7 +95,7 @@ __device__ void stage_row(const StageParams& p, long long i, float* __restrict__
                     w4[u] = __shfl_sync(0xffffffffu, my_w, src_lane);
                     const int er = __shfl_sync(0xffffffffu, my_er, src_lane);
                     const bool on = (t0 + u) < cnt;
-                    const float* xr = a.x + (long long)j * a.ldx;
+                    const float* xr = src_row(a, j);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) { va4[u][q] = 0.f; vb4[u][q] = 0.f; ea4[u][q] = 0.f; eb4[u][q] = 0.f; }
                     if (on && va) ldw<VEC>(xr + ca, va4[u]);

@@ -35,7 +35,10 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const float* __restric
     uint64_t* bars = reinterpret_cast<uint64_t*>(b_lo + b_bytes);   // [0] B landed, [1] MMAs done
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
     const int tid = threadIdx.x, warp = tid >> 5;
-    const uint32_t ncols = tc::tmem_cols_pow2((uint32_t)N);
+    const bool a_in_tmem = nprod >= 10;      // 11 / 13: A operand handed over in tensor memory (tcgen05.st + TS-form MMA)
+    if (a_in_tmem) nprod -= 10;
+    const uint32_t a_col = (uint32_t)((N + 31) & ~31);
+    const uint32_t ncols = tc::tmem_cols_pow2(a_in_tmem ? a_col + (uint32_t)K : (uint32_t)N);
 
     if (warp == 0) tc::tmem_alloc(tmem_slot, ncols);
     if (tid == 32) {
@@ -53,16 +56,24 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const float* __restric
         tc::bulk_g2s(b_hi, Bp, 2 * b_bytes, &bars[0]);     // hi and lo are contiguous in the packed buffer
     }
     // A: thread = row, one 16-byte vector per slab
+    const uint32_t lane_base_st = (uint32_t)(warp * 32) << 16;
     for (int kc = 0; kc < kcs; ++kc) {
         float v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = A[(size_t)tid * K + kc * 8 + i];
         uint4 hi, lo;
         tc::split8(v, hi, lo);
-        *reinterpret_cast<uint4*>(a_hi + (size_t)kc * 2048 + tid * 16) = hi;
-        *reinterpret_cast<uint4*>(a_lo + (size_t)kc * 2048 + tid * 16) = lo;
+        if (a_in_tmem) {   // hi at columns a_col + 4kc.., lo at a_col + K/2 + 4kc..
+            tc::tmem_st4(tmem_base + lane_base_st + a_col + 4u * kc, hi.x, hi.y, hi.z, hi.w);
+            tc::tmem_st4(tmem_base + lane_base_st + a_col + (uint32_t)K / 2 + 4u * kc, lo.x, lo.y, lo.z, lo.w);
+        } else {
+            *reinterpret_cast<uint4*>(a_hi + (size_t)kc * 2048 + tid * 16) = hi;
+            *reinterpret_cast<uint4*>(a_lo + (size_t)kc * 2048 + tid * 16) = lo;
+        }
     }
+    if (a_in_tmem) tc::tmem_st_wait();
     tc::fence_proxy_async_smem();
+    tc::tc_fence_before_sync();
     __syncthreads();
 
     if (tid == 0) {
@@ -76,6 +87,16 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const float* __restric
             const uint64_t dal = tc::smem_desc(tc::smem_u32(a_lo) + ks * 2 * lbo_a, lbo_a, 128);
             const uint64_t dbh = tc::smem_desc(tc::smem_u32(b_hi) + ks * 2 * lbo_b, lbo_b, 128);
             const uint64_t dbl = tc::smem_desc(tc::smem_u32(b_lo) + ks * 2 * lbo_b, lbo_b, 128);
+            if (a_in_tmem) {
+                const uint32_t tah = tmem_base + a_col + 8u * ks, tal = tah + (uint32_t)K / 2;
+                tc::umma_bf16_ts(tmem_base, tah, dbh, idesc, acc);
+                acc = 1;
+                if (nprod >= 3) {
+                    tc::umma_bf16_ts(tmem_base, tah, dbl, idesc, 1);
+                    tc::umma_bf16_ts(tmem_base, tal, dbh, idesc, 1);
+                }
+                continue;
+            }
             tc::umma_bf16(tmem_base, dah, dbh, idesc, acc);
             acc = 1;
             if (nprod >= 3) {
@@ -111,6 +132,7 @@ extern "C" int kagnn_tc_selftest(const float* A, const float* B, int32_t N, int3
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (!A || !B || !D || !workspace) return KAGNN_EINVAL;
     if (N < 16 || N > 256 || (N % 16) != 0 || K < 16 || (K % 16) != 0) return KAGNN_EUNSUPPORTED;
+    if (nprod >= 10 && ((N + 31) & ~31) + K > 512) return KAGNN_EUNSUPPORTED;   // A and D share the 512 TMEM columns
     if (workspace_bytes < kagnn_tc_selftest_workspace(N, K)) return KAGNN_EWORKSPACE;
     if (!aligned16(workspace)) return KAGNN_EALIGN;
     DeviceProps props{};

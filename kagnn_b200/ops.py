@@ -126,14 +126,48 @@ def gcn_norm(csr: CSR, edge_weight_csr: Optional[Tensor] = None):
     return w, sw, dinv
 
 
-def gather_rows(x: Tensor, index: Tensor, out: Optional[Tensor] = None) -> Tensor:
+def gcn_degree(csr: CSR, edge_weight_csr: Optional[Tensor] = None):
+    """First half of gcn_norm: (self_weight (N), dinv (N)) of the destination rows."""
+    global launch_count
+    dev = csr.rowptr.device
+    sw = torch.empty(csr.num_rows, dtype=torch.float32, device=dev)
+    dinv = torch.empty(csr.num_rows, dtype=torch.float32, device=dev)
+    L.check(L.lib().kagnn_gcn_degree(_p(csr.rowptr), _p(csr.col), csr.num_rows, _p(edge_weight_csr), _p(sw), _p(dinv),
+                                     _stream()), "gcn_degree")
+    launch_count += 1
+    return sw, dinv
+
+
+def gcn_edge_weight(csr: CSR, dinv_src: Tensor, dinv_dst: Tensor, edge_weight_csr: Optional[Tensor] = None) -> Tensor:
+    """Second half of gcn_norm: w_e = dinv_src[col_e] * w_e * dinv_dst[row]; dinv_src covers halo rows too."""
+    global launch_count
+    _need_cuda(dinv_src, "dinv_src", torch.float32)
+    _need_cuda(dinv_dst, "dinv_dst", torch.float32)
+    if dinv_src.numel() < csr.num_src or dinv_dst.numel() < csr.num_rows:
+        raise ValueError("dinv vectors shorter than the graph")
+    w = torch.empty(csr.nnz, dtype=torch.float32, device=csr.rowptr.device)
+    L.check(L.lib().kagnn_gcn_edge_weight(_p(csr.rowptr), _p(csr.col), csr.num_rows, _p(edge_weight_csr),
+                                          _p(dinv_src.contiguous()), _p(dinv_dst.contiguous()), _p(w), _stream()),
+            "gcn_edge_weight")
+    launch_count += 1
+    return w
+
+
+def gather_rows(x: Tensor, index: Optional[Tensor], out: Optional[Tensor] = None, num_rows: Optional[int] = None) -> Tensor:
+    """out[r] = x[index[r]] (halo send-buffer packing); ``index=None`` copies the first ``num_rows`` rows."""
     global launch_count
     ldx = _rows(x, "x")
-    _need_cuda(index, "index", torch.int32)
+    if index is not None:
+        _need_cuda(index, "index", torch.int32)
+        num_rows = index.numel()
+    elif num_rows is None:
+        num_rows = x.size(0)
     if out is None:
-        out = torch.empty(index.numel(), x.size(1), dtype=torch.float32, device=x.device)
+        out = torch.empty(num_rows, x.size(1), dtype=torch.float32, device=x.device)
     ldo = _rows(out, "out")
-    L.check(L.lib().kagnn_gather_rows(_p(x), ldx, _p(index), index.numel(), x.size(1), _p(out), ldo, _stream()), "gather_rows")
+    if num_rows == 0:
+        return out
+    L.check(L.lib().kagnn_gather_rows(_p(x), ldx, _p(index), num_rows, x.size(1), _p(out), ldo, _stream()), "gather_rows")
     launch_count += 1
     return out
 
@@ -248,6 +282,7 @@ class AggSpec:
     edge_feat: Optional[Tensor] = None
     edge_row: Optional[Tensor] = None
     src_index: Optional[Tensor] = None
+    x_halo: Optional[Tensor] = None       # node-sharded graphs: source rows >= x.size(0) live here (dist.py)
 
     def struct(self) -> L.KagnnAggregate:
         ldx = _rows(self.x, "x")
@@ -268,6 +303,12 @@ class AggSpec:
         if self.edge_feat is not None:
             s.ld_edge = _rows(self.edge_feat, "edge_feat")
             s.edge_feat = _addr(self.edge_feat)
+        if self.x_halo is not None:
+            if self.x_halo.size(1) != self.x.size(1):
+                raise ValueError("x_halo must have the same number of columns as x")
+            s.ld_halo = _rows(self.x_halo, "x_halo")
+            s.x_halo = _addr(self.x_halo)
+            s.num_local_src = self.x.size(0)
         return s
 
 

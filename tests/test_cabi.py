@@ -41,7 +41,7 @@ def test_struct_layouts_match_the_header():
     from kagnn_b200 import _lib
     assert ctypes.sizeof(_lib.KagnnAffine) == 24
     assert ctypes.sizeof(_lib.KagnnKanLayer) == 72
-    assert ctypes.sizeof(_lib.KagnnAggregate) == 96
+    assert ctypes.sizeof(_lib.KagnnAggregate) == 120
 
 
 def test_no_cpu_fallback():
