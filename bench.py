@@ -200,7 +200,9 @@ def main():
     if dist_on:
         from kagnn_b200 import dist as kdist
         runner = kdist.ShardedNodeModel(model, rank, world, n_local)
-        plan = runner.prepare(ei_host.to(dev))
+        ei_glob = ei_host.to(dev)
+        ei_glob[1] += rank * n_local                                     # targets: this rank's node range, global ids
+        plan = runner.prepare(ei_glob)
         x_dev = x_host.to(dev)
         step = lambda: runner.forward(x_dev, plan)                       # noqa: E731
     else:

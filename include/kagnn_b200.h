@@ -172,6 +172,11 @@ int kagnn_fused_layer_fwd(const KagnnAggregate* agg, int64_t num_rows,
 enum { KAGNN_PATH_AUTO = 0, KAGNN_PATH_FP32 = 1, KAGNN_PATH_TC = 2 };
 int kagnn_set_path(int mode);
 int kagnn_get_launch_counters(int64_t* tc_launches, int64_t* fp32_launches);
+/* The tensor-core path has two kernels: the pipelined one (A operand in tensor memory, fused_tc2.cu; B-spline chains up
+ * to 128 wide) and the general one (A in shared memory, fused_tc.cu).  variant 0 = pipelined first (default),
+ * 1 = general only.  kagnn_get_tc2_launches counts launches of the pipelined kernel. */
+int kagnn_set_tc_variant(int variant);
+int64_t kagnn_get_tc2_launches(void);
 
 /* Self-test of the tcgen05 machinery (descriptor encodings, TMEM addressing, bulk TMA, bf16 hi/lo split):
  * D (128 x N) = A (128 x K) . B (N x K)^T, fp32 in/out, nprod = 1 (bf16 hi only) or 3 (hi/lo compensated).

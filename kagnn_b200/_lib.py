@@ -8,7 +8,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libkagnn_b200.so")
+LIB_PATH = os.environ.get("KAGNN_LIB") or os.path.join(_HERE, "lib", "libkagnn_b200.so")
 
 # enums (mirror include/kagnn_b200.h)
 BASIS_BSPLINE, BASIS_RBF = 0, 1
@@ -75,6 +75,8 @@ _SIGNATURES = {
     "kagnn_pack_kan_weights_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "kagnn_set_path": (C.c_int, [C.c_int]),
     "kagnn_get_launch_counters": (C.c_int, [C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "kagnn_set_tc_variant": (C.c_int, [C.c_int]),
+    "kagnn_get_tc2_launches": (C.c_int64, []),
     "kagnn_tc_selftest_workspace": (C.c_size_t, [C.c_int32, C.c_int32]),
     "kagnn_tc_selftest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t,
                                     C.c_void_p]),

@@ -11,15 +11,18 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
-LIB = os.path.join(LIBDIR, "libkagnn_b200.so")
-STAMP = os.path.join(LIBDIR, "libkagnn_b200.stamp")
+# development aid: KAGNN_LIB_SUFFIX=_x KAGNN_NVCC_EXTRA="-DFOO=1" builds lib/libkagnn_b200_x.so next to the product library
+# (load it with KAGNN_LIB=<path>), so two kernel variants can be timed in one GPU session
+_SUFFIX = os.environ.get("KAGNN_LIB_SUFFIX", "")
+LIB = os.path.join(LIBDIR, f"libkagnn_b200{_SUFFIX}.so")
+STAMP = os.path.join(LIBDIR, f"libkagnn_b200{_SUFFIX}.stamp")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
-]
+] + os.environ.get("KAGNN_NVCC_EXTRA", "").split()
 
 
 def _nvcc() -> str:
@@ -61,7 +64,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = []
     procs = []
     for src in sources():
-        obj = os.path.join(LIBDIR, os.path.basename(src)[:-3] + ".o")
+        obj = os.path.join(LIBDIR, os.path.basename(src)[:-3] + _SUFFIX + ".o")
         cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")

@@ -118,8 +118,8 @@ class GINConv(_MessagePassing):
             self._eps_host = (key, float(self.eps.detach().cpu()))
         return self._eps_host[1]
 
-    def _agg_spec(self, x: Tensor, g: GraphCSR) -> ops.AggSpec:
-        return ops.AggSpec(L.AGG_GIN, x, g.rowptr, g.col, self_scale=1.0 + self.eps_value())
+    def _agg_spec(self, x: Tensor, g: GraphCSR, x_halo: Optional[Tensor] = None) -> ops.AggSpec:
+        return ops.AggSpec(L.AGG_GIN, x, g.rowptr, g.col, self_scale=1.0 + self.eps_value(), x_halo=x_halo)
 
     def forward(self, x: Tensor, edge_index, size=None, out: Optional[Tensor] = None,
                 post: Optional[ops.Affine] = None, **agg_kw) -> Tensor:
@@ -143,9 +143,10 @@ class GINEConv(GINConv):
             raise NotImplementedError("edge_dim is never used by the reference (graph_regression/models.py:98)")
         self.lin = None
 
-    def _agg_spec(self, x: Tensor, g: GraphCSR, edge_feat: Tensor = None, edge_row: Tensor = None) -> ops.AggSpec:
+    def _agg_spec(self, x: Tensor, g: GraphCSR, edge_feat: Tensor = None, edge_row: Tensor = None,
+                  x_halo: Optional[Tensor] = None) -> ops.AggSpec:
         return ops.AggSpec(L.AGG_GINE, x, g.rowptr, g.col, self_scale=1.0 + self.eps_value(), edge_feat=edge_feat,
-                           edge_row=edge_row)
+                           edge_row=edge_row, x_halo=x_halo)
 
     def forward(self, x: Tensor, edge_index, edge_attr: Tensor = None, size=None, out: Optional[Tensor] = None,
                 post: Optional[ops.Affine] = None, edge_row: Optional[Tensor] = None) -> Tensor:

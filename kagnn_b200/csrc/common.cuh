@@ -36,5 +36,8 @@ int kagnn_fused_fwd_fp32(const KagnnAggregate* agg, int64_t num_rows, const Kagn
 int kagnn_fused_fwd_tc(const KagnnAggregate* agg, int64_t num_rows, const KagnnAffine* pre, float* agg_out,
                        int64_t ld_agg_out, int32_t n_layers, const KagnnKanLayer* layers, const KagnnAffine* post, float* y,
                        int64_t ldy, cudaStream_t stream);
+int kagnn_fused_fwd_tc2(const KagnnAggregate* agg, int64_t num_rows, const KagnnAffine* pre, float* agg_out,
+                        int64_t ld_agg_out, int32_t n_layers, const KagnnKanLayer* layers, const KagnnAffine* post, float* y,
+                        int64_t ldy, cudaStream_t stream);
 int kagnn_validate_fused_args(const KagnnAggregate* agg, int64_t num_rows, const float* agg_out, int64_t ld_agg_out,
                               int32_t n_layers, const KagnnKanLayer* layers, const float* y);

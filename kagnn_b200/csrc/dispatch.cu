@@ -7,7 +7,8 @@
 
 namespace {
 std::atomic<int> g_path_mode{KAGNN_PATH_AUTO};
-std::atomic<long long> g_count_tc{0}, g_count_fp32{0};
+std::atomic<long long> g_count_tc{0}, g_count_fp32{0}, g_count_tc2{0};
+std::atomic<int> g_tc_variant{0};   // 0 = auto, 1 = only the shared-memory-A kernel (fused_tc.cu); tests/benchmarks
 }  // namespace
 
 int kagnn_validate_fused_args(const KagnnAggregate* agg, int64_t num_rows, const float* agg_out, int64_t ld_agg_out,
@@ -36,6 +37,14 @@ extern "C" int kagnn_set_path(int mode) {
     return KAGNN_OK;
 }
 
+extern "C" int kagnn_set_tc_variant(int variant) {
+    if (variant != 0 && variant != 1) return KAGNN_EINVAL;
+    g_tc_variant.store(variant);
+    return KAGNN_OK;
+}
+
+extern "C" int64_t kagnn_get_tc2_launches(void) { return g_count_tc2.load(); }
+
 extern "C" int kagnn_get_launch_counters(int64_t* tc_launches, int64_t* fp32_launches) {
     if (tc_launches) *tc_launches = g_count_tc.load();
     if (fp32_launches) *fp32_launches = g_count_fp32.load();
@@ -55,7 +64,17 @@ extern "C" int kagnn_fused_layer_fwd(const KagnnAggregate* agg, int64_t num_rows
         if (have_tc) {
             // run the shared argument checks of the fp32 path first?  No: fused_tc validates what it touches and
             // returns KAGNN_EUNSUPPORTED for anything it cannot run, in which case the general kernel takes over.
-            int rc = kagnn_fused_fwd_tc(agg, num_rows, pre, agg_out, ld_agg_out, n_layers, layers, post, y, ldy, stream);
+            int rc = KAGNN_EUNSUPPORTED;
+            if (g_tc_variant.load() != 1) {      // pipelined kernel (A operand in TMEM) first; it declines what it cannot run
+                rc = kagnn_fused_fwd_tc2(agg, num_rows, pre, agg_out, ld_agg_out, n_layers, layers, post, y, ldy, stream);
+                if (rc == KAGNN_OK) {
+                    g_count_tc.fetch_add(1);
+                    g_count_tc2.fetch_add(1);
+                    return rc;
+                }
+                if (rc != KAGNN_EUNSUPPORTED) return rc;
+            }
+            rc = kagnn_fused_fwd_tc(agg, num_rows, pre, agg_out, ld_agg_out, n_layers, layers, post, y, ldy, stream);
             if (rc == KAGNN_OK) {
                 g_count_tc.fetch_add(1);
                 return rc;

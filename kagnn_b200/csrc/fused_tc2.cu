@@ -1,0 +1,692 @@
+// kagnn_fused_layer_fwd -- pipelined tensor-core path for B-spline KAN chains (tcgen05, A operand in TMEM), sm_100a.
+//
+// Same contract as fused_fp32.cu / fused_tc.cu (tile = aggregate(x) -> pre-affine -> KAN chain -> post-affine -> y, one
+// persistent launch per GNN layer), restructured so that the three resources of the layer run concurrently:
+//
+//   gather warps   (8)  CSR gather-sum of the NEXT 128-row tile, one "unit" (128 rows x 64/128 feature columns) at a
+//                       time into a shared-memory ring: row pointers and column indices are fetched once per warp
+//                       (16 rows) and the neighbour rows of those 16 rows are streamed as ONE flattened list with 8
+//                       independent 128-bit loads in flight per warp -- L2/HBM latency is paid once per batch, not once
+//                       per row, and is hidden behind the basis producers of the current tile;
+//   producer warps (8)  thread = row.  For every 8 input features the closed-form uniform cubic (or order 1/2) B-spline
+//                       basis (node_classification_clean/ekan.py:79-112 restricted to its k+1 non-zeros), split into
+//                       bf16 hi + lo, is placed into the 8 coefficient slots of the feature with one byte-permute per
+//                       32-bit word (selectors from a 12-row shared LUT indexed by the knot interval) and written with
+//                       tcgen05.st straight into TENSOR MEMORY, which tcgen05.mma reads as its A operand: the expanded
+//                       (N, in, G+k) tensor of the reference exists neither in HBM nor in shared memory;
+//   MMA warp       (1)  one thread issues, per K = 16 step, A_hi.W_hi + A_hi.W_lo + A_lo.W_hi (bf16 x bf16 -> fp32 in
+//                       TMEM; error ~2^-17, inside BASELINE.json's 1e-4);  W chunks arrive by bulk TMA (loader warp);
+//   chained KAN layers read their input rows back from the TMEM accumulator of the previous layer (two accumulator
+//   regions, alternated per layer across tiles so the epilogue of tile t overlaps the first MMAs of tile t+1).
+//
+// Supported here: B-spline layers with one common spline_order k <= 3, G + k <= 8, every width of the chain <= 128
+// outputs.  Anything else returns KAGNN_EUNSUPPORTED and the dispatcher falls back to fused_tc.cu / fused_fp32.cu.
+#include "common.cuh"
+#include "stage.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int NPW = 8;                       // producer warps (two warpgroups)
+constexpr int NGW = 8;                       // gather warps
+constexpr int NPROD = NPW * 32;
+constexpr int NTHREADS = (NPW + NGW + 2) * 32;
+constexpr int WARP_MMA = NPW + NGW;
+constexpr int WARP_LOAD = NPW + NGW + 1;
+constexpr int RPW = BM / NGW;                // rows per gather warp
+constexpr int MAX_STAGE = 4;                 // A stages in TMEM (64 columns each) / B stages in shared memory
+constexpr int MAX_UNITS = 4;                 // x-tile ring slots
+constexpr uint32_t TMEM_A0 = 256;            // columns [0,256): two accumulator regions of 128; [256,512): A stages
+constexpr int LUT_ROWS = 12;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kMagic = 12582912.0f;        // 1.5 * 2^23: u + kMagic (round down) = floor(u) + kMagic
+
+struct LayerT2 {
+    int F, F_pad, N, N_pad, n_chunks;
+    float c0, inv_h, lim;                    // u = x * inv_h + c0 (= (x - t0)/h); valid iff 0 <= u < lim = G + 2k
+    const uint8_t* wtc;
+};
+
+struct Tc2Params {
+    KagnnAggregate agg;
+    KagnnAffine pre, post;
+    int has_pre, has_post;
+    long long num_rows;
+    float* agg_out;
+    long long ld_agg_out;
+    float* y;
+    long long ldy;
+    int n_layers, n_tiles, y_vec;
+    int uw, xld, n_units, units_per_tile, unit_floats;   // x-tile ring geometry
+    int ns, bstage_bytes;                                 // A/B stage ring depth, bytes of one B stage
+    LayerT2 layers[KAGNN_MAX_LAYERS];
+};
+
+struct ChunkInfo {
+    int group, j, n_oct, nk;
+    bool base;
+    uint32_t b_off, b_bytes;
+};
+__device__ __forceinline__ ChunkInfo chunk_info(const LayerT2& L, int q) {
+    ChunkInfo c;
+    c.group = q / 9;
+    c.j = q - 9 * c.group;
+    c.n_oct = min(8, L.F_pad / 8 - 8 * c.group);
+    c.base = (c.j >= c.n_oct);
+    c.nk = c.base ? c.n_oct : 8;
+    c.b_off = (uint32_t)(c.group * 9 + c.j) * 256u * (uint32_t)L.N_pad;
+    c.b_bytes = 32u * (uint32_t)c.nk * (uint32_t)L.N_pad;
+    return c;
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// silu(x) = x / (1 + exp(-x)); "+ (x - x)" turns +inf into NaN like the reference's spline branch does (inf * 0)
+__device__ __forceinline__ float silu_nan(float x) { return __fdividef(x, 1.0f + ex2_approx(-kLog2e * x)) + (x - x); }
+
+// prmt.b32 with the full PTX semantics (selector nibble bit 3 = replicate the sign of the selected byte); the
+// __byte_perm intrinsic masks the selector with 0x7777 and cannot be used for that
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+__device__ __forceinline__ uint32_t pack_trunc(float lo_elem, float hi_elem) {   // two fp32 -> bf16x2 by truncation
+    return prmt(__float_as_uint(lo_elem), __float_as_uint(hi_elem), 0x7632u);
+}
+__device__ __forceinline__ float trunc_residual(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack_rn(float lo_elem, float hi_elem) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+    return r;
+}
+
+// One input value -> the 8 coefficient slots of its feature as bf16 hi (4 words) and lo (4 words).
+// Uniform knots t_j = t0 + j h (ekan.py:28-37): interval j = floor(u), the k+1 non-zero bases B_{j-k..j} are the local
+// polynomials of the fractional position; outside [t_0, t_last) and for NaN every basis is 0 (half-open indicator, :95).
+template <int K>
+__device__ __forceinline__ void bspline_slots(const LayerT2& L, const uint4* __restrict__ lut, float x, uint32_t* hi, uint32_t* lo) {
+    const float u = fmaf(x, L.inv_h, L.c0);
+    const float t = __fadd_rd(u, kMagic);
+    const bool valid = (u >= 0.0f) && (u < L.lim);
+    const float fr = valid ? (u - (t - kMagic)) : 0.0f;
+    const int idx = valid ? (__float_as_int(t) - 0x4B400000 + (3 - K)) : (LUT_ROWS - 1);
+    float b0, b1, b2 = 0.f, b3 = 0.f;
+    if (K == 3) {
+        const float omf = 1.0f - fr, f2 = fr * fr;
+        b0 = omf * omf * (omf * (1.0f / 6.0f));
+        b3 = f2 * (fr * (1.0f / 6.0f));
+        b1 = fmaf(f2, fmaf(fr, 0.5f, -1.0f), 2.0f / 3.0f);
+        b2 = fmaf(fr, fmaf(fr, fmaf(fr, -0.5f, 0.5f), 0.5f), 1.0f / 6.0f);
+    } else if (K == 2) {
+        const float omf = 1.0f - fr;
+        b0 = 0.5f * omf * omf;
+        b2 = 0.5f * fr * fr;
+        b1 = fmaf(fr, omf, 0.5f);            // (-2 fr^2 + 2 fr + 1) / 2
+    } else {
+        b0 = 1.0f - fr;
+        b1 = fr;
+    }
+    // every value is >= 0, so hi = truncation to bf16 and lo = bf16(b - hi) are >= 0 too: their sign bits are 0, which
+    // lets the byte-permute synthesise the zero slots by sign replication (selector nibble 9)
+    const uint32_t h01 = pack_trunc(b0, b1), h23 = pack_trunc(b2, b3);
+    const uint32_t l01 = pack_rn(trunc_residual(b0), trunc_residual(b1));
+    const uint32_t l23 = (K >= 2) ? pack_rn(trunc_residual(b2), trunc_residual(b3)) : 0u;
+    const uint4 sel = lut[idx];
+    hi[0] = prmt(h01, h23, sel.x);
+    hi[1] = prmt(h01, h23, sel.y);
+    hi[2] = prmt(h01, h23, sel.z);
+    hi[3] = prmt(h01, h23, sel.w);
+    lo[0] = prmt(l01, l23, sel.x);
+    lo[1] = prmt(l01, l23, sel.y);
+    lo[2] = prmt(l01, l23, sel.z);
+    lo[3] = prmt(l01, l23, sel.w);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// GATHER: one warp aggregates RPW destination rows of one unit (column block [c0, c0 + ucols)) into the ring slot.
+// ---------------------------------------------------------------------------------------------------------------------
+template <bool VEC>
+__device__ __forceinline__ void ldp4(const float* __restrict__ ptr, bool on, float (&v)[4], const bool (&cv)[4]) {
+    if (VEC) {
+        if (on && cv[0]) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(ptr));
+            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        } else {
+            v[0] = v[1] = v[2] = v[3] = 0.f;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = (on && cv[i]) ? __ldg(ptr + 32 * i) : 0.f;
+    }
+}
+__device__ __forceinline__ const float* shfl_ptr(const float* p, int src_lane) {
+    const unsigned long long v = reinterpret_cast<unsigned long long>(p);
+    const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src_lane), hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src_lane);
+    return reinterpret_cast<const float*>(((unsigned long long)hi << 32) | lo);
+}
+
+// One gather warp, one unit: RPW destination rows x the unit's column block.  The self term of a row is treated as one
+// more entry in front of the row's CSR entries ("virtual" entries), so the warp walks ONE flattened list
+//     [self_0, nbrs of row 0..., self_1, nbrs of row 1..., ...]
+// in batches of 32 (lane-parallel: row lookup, column index, source-row pointer, weight) and sub-batches of U
+// independent 128-bit row loads; sums are kept in registers in CSR order (deterministic, no atomics) and a finished row
+// gets the mean scale / pre-affine (GCNConv bias, eval BatchNorm, SiLU) and is parked in the ring slot (and agg_out).
+template <bool VEC, bool GINE>
+__device__ __forceinline__ void gather_unit(const Tc2Params& p, long long row0, int c0, int ucols, float* __restrict__ xsu, int gw,
+                                            int lane) {
+    constexpr int U = GINE ? 4 : 8;
+    const KagnnAggregate& a = p.agg;
+    const int F = a.num_cols, mode = a.mode, xld = p.xld;
+    const bool segment = (mode == KAGNN_AGG_SEGMENT_SUM) || (mode == KAGNN_AGG_SEGMENT_MEAN);
+    const int rl0 = gw * RPW;
+    const int cl = VEC ? 4 * lane : lane;                  // lane -> 4 columns: VEC c0+4*lane+i, scalar c0+lane+32*i
+    const int cbase = c0 + cl;
+    bool cv[4], cin[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int lc = cl + (VEC ? i : 32 * i);
+        cin[i] = lc < ucols;
+        cv[i] = cin[i] && (c0 + lc) < F;
+    }
+    if (mode == KAGNN_AGG_NONE && !p.has_pre && !p.agg_out) {
+        // plain row tile (bare KANLinear / KAN chain input): coalesced copy, rows past the end zero-filled
+#pragma unroll 1
+        for (int rb = 0; rb < RPW; rb += 8) {
+            float v[8][4];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const long long r = row0 + rl0 + rb + u;
+                const bool on = r < p.num_rows;
+                ldp4<VEC>(a.x + (on ? r : 0) * a.ldx + cbase, on, v[u], cv);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                float* d = xsu + (rl0 + rb + u) * xld + cl;
+                if (VEC) {
+                    if (cin[0]) *reinterpret_cast<float4*>(d) = make_float4(v[u][0], v[u][1], v[u][2], v[u][3]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (cin[i]) d[32 * i] = v[u][i];
+                }
+            }
+        }
+        return;
+    }
+    float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p.has_pre) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int c = cbase + (VEC ? i : 32 * i);
+            if (cv[i] && p.pre.scale) sc[i] = __ldg(p.pre.scale + c);
+            if (cv[i] && p.pre.shift) sh[i] = __ldg(p.pre.shift + c);
+        }
+    }
+    const bool pre_silu = p.has_pre && p.pre.act == KAGNN_ACT_SILU;
+    const int self1 = segment ? 0 : 1;                     // pooling has no self term
+    // lane l <= RPW: CSR pointer of row l and the virtual start of row l (CSR pointer + one self entry per earlier row)
+    int rp = 0;
+    if (mode != KAGNN_AGG_NONE) {
+        long long r = row0 + rl0 + min(lane, RPW);
+        if (r > p.num_rows) r = p.num_rows;
+        rp = __ldg(a.rowptr + r);
+    }
+    const int vs = rp + self1 * min(lane, RPW);
+    const int v_beg = __shfl_sync(0xffffffffu, vs, 0), v_end = __shfl_sync(0xffffffffu, vs, RPW);
+    int cur = 0, cur_vend = __shfl_sync(0xffffffffu, vs, 1);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+
+    auto finish_row = [&]() {
+        const long long r = row0 + rl0 + cur;
+        const bool rv = r < p.num_rows;
+        float os = 1.0f;
+        if (mode == KAGNN_AGG_SEGMENT_MEAN)
+            os = 1.0f / (float)max(__shfl_sync(0xffffffffu, rp, cur + 1) - __shfl_sync(0xffffffffu, rp, cur), 1);
+        float o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float t = acc[i] * os;
+            if (p.has_pre) {
+                t = fmaf(t, sc[i], sh[i]);
+                if (pre_silu) t = __fdividef(t, 1.0f + ex2_approx(-kLog2e * t));
+            }
+            o[i] = (cv[i] && rv) ? t : 0.f;
+            acc[i] = 0.f;
+        }
+        float* d = xsu + (rl0 + cur) * xld + cl;
+        if (VEC) {
+            if (cin[0]) *reinterpret_cast<float4*>(d) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (cin[i]) d[32 * i] = o[i];
+        }
+        if (p.agg_out && rv) {
+            float* g = p.agg_out + r * p.ld_agg_out + cbase;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (cv[i]) g[VEC ? i : 32 * i] = o[i];
+        }
+        ++cur;
+        cur_vend = __shfl_sync(0xffffffffu, vs, min(cur + 1, RPW));
+    };
+
+#pragma unroll 1
+    for (int vbase = v_beg; vbase < v_end; vbase += 32) {
+        const int cnt = min(32, v_end - vbase);
+        // ---- lane-parallel: virtual entry vbase+lane -> (source-row pointer, weight, self flag) ----------------------
+        const int ve = vbase + lane;
+        int r = 0;
+#pragma unroll
+        for (int l = 1; l <= RPW; ++l) r += (__shfl_sync(0xffffffffu, vs, l) <= ve) ? 1 : 0;
+        r = min(r, RPW - 1);
+        const int vs_r = __shfl_sync(0xffffffffu, vs, r), rp_r = __shfl_sync(0xffffffffu, rp, r);
+        const bool is_self = (self1 != 0) && (ve == vs_r);
+        const float* my_row = a.x;
+        const float* my_erow = a.edge_feat;
+        float my_w = 0.0f;
+        int my_flag = 0;                                   // bit 0: load the row, bit 1: self entry
+        if (lane < cnt) {
+            if (is_self) {
+                const long long rg = row0 + rl0 + r;
+                if (rg < p.num_rows) {
+                    const long long sr = a.src_index ? (long long)__ldg(a.src_index + rg) : rg;
+                    my_row = a.x + sr * a.ldx;
+                    my_w = a.self_scale;
+                    if (mode == KAGNN_AGG_NONE) my_w = 1.0f;
+                    if (mode == KAGNN_AGG_WEIGHTED && a.self_weight) my_w = __ldg(a.self_weight + rg);
+                    my_flag = 3;
+                }
+            } else {
+                const int e = rp_r + (ve - vs_r) - self1;
+                int j = a.col ? __ldg(a.col + e) : e;
+                if (a.src_index) j = __ldg(a.src_index + j);
+                my_row = src_row(a, j);
+                my_w = (mode == KAGNN_AGG_WEIGHTED) ? __ldg(a.edge_weight + e) : 1.0f;
+                if (GINE) my_erow = a.edge_feat + (long long)__ldg(a.edge_row + e) * a.ld_edge;
+                my_flag = 1;
+            }
+        }
+#pragma unroll 1
+        for (int t0 = 0; t0 < cnt; t0 += U) {
+            float v[U][4], ev[GINE ? U : 1][4], w[U];
+            int fl[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                fl[u] = __shfl_sync(0xffffffffu, my_flag, t0 + u);
+                w[u] = __shfl_sync(0xffffffffu, my_w, t0 + u);
+                const bool on = (fl[u] & 1) != 0;
+                ldp4<VEC>(shfl_ptr(my_row, t0 + u) + cbase, on, v[u], cv);
+                if (GINE) ldp4<VEC>(shfl_ptr(my_erow, t0 + u) + cbase, on && !(fl[u] & 2), ev[u], cv);
+            }
+            // consume: entries [done, lim) of the sub-batch belong to the current row; a row boundary inside it
+            // finishes the row (possibly several empty ones) and continues -- all warp-uniform
+            const int n_sub = min(U, cnt - t0), e0 = vbase + t0;
+            int done = 0;
+            for (;;) {
+                const int lim = min(n_sub, cur_vend - e0);
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (u >= done && u < lim) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            if (GINE) acc[i] += (fl[u] & 2) ? w[u] * v[u][i] : fmaxf(v[u][i] + ev[u][i], 0.f);
+                            else acc[i] = fmaf(w[u], v[u][i], acc[i]);      // w = 1 for plain sums
+                        }
+                    }
+                }
+                if (lim >= n_sub) break;
+                done = max(done, lim);
+                finish_row();
+            }
+        }
+    }
+    while (cur < RPW) finish_row();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_constant__ Tc2Params p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    float* xs = reinterpret_cast<float*>(smem);
+    uint8_t* bst = smem + (size_t)p.n_units * p.unit_floats * sizeof(float);
+    uint4* lut = reinterpret_cast<uint4*>(bst + (size_t)p.ns * p.bstage_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(lut + LUT_ROWS);
+    uint64_t* xs_full = bars;
+    uint64_t* xs_empty = bars + MAX_UNITS;
+    uint64_t* a_full = bars + 2 * MAX_UNITS;
+    uint64_t* b_full = a_full + MAX_STAGE;
+    uint64_t* empty = b_full + MAX_STAGE;
+    uint64_t* acc_full = empty + MAX_STAGE;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (warp == WARP_MMA) tc::tmem_alloc(tmem_slot, 512);
+    if (tid == WARP_LOAD * 32) {
+        for (int s = 0; s < MAX_UNITS; ++s) {
+            tc::mbar_init(&xs_full[s], NGW);
+            tc::mbar_init(&xs_empty[s], NPW);
+        }
+        for (int s = 0; s < MAX_STAGE; ++s) {
+            tc::mbar_init(&a_full[s], 128);
+            tc::mbar_init(&b_full[s], 1);
+            tc::mbar_init(&empty[s], 1);
+        }
+        tc::mbar_init(acc_full, 1);
+        tc::mbar_fence_init();
+    }
+    if (tid < LUT_ROWS) {
+        // row r <-> slot offset s = r - 3 of the first non-zero basis (r = 11: every slot zero).  Output byte q of the
+        // 16-byte slot vector takes source byte q - 2s of (b0 b1 | b2 b3) when that is in 0..7, else the replicated
+        // (zero) sign bit of source byte 1.
+        uint32_t w[4];
+        for (int m = 0; m < 4; ++m) {
+            uint32_t sel = 0;
+            for (int n = 0; n < 4; ++n) {
+                const int src = 4 * m + n - 2 * (tid - 3);
+                const uint32_t nib = (tid < LUT_ROWS - 1 && src >= 0 && src <= 7) ? (uint32_t)src : 9u;
+                sel |= nib << (4 * n);
+            }
+            w[m] = sel;
+        }
+        lut[tid] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < NPW) {
+        // ============================== BASIS PRODUCERS / EPILOGUE =============================================
+        const int wg = warp >> 2;
+        const int row = tid & 127;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        uint32_t cq = 0, lc = 0, uc0 = 0;                  // running chunk / layer / unit counters
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            const long long row0 = (long long)tile * BM;
+            const int nrows = (int)min((long long)BM, p.num_rows - row0);
+            for (int l = 0; l < p.n_layers; ++l, ++lc) {
+                const LayerT2& L = p.layers[l];
+                uint32_t src_t = 0;
+                int cur_unit = -1;
+                const float* xrow = nullptr;
+                if (l > 0) {
+                    tc::mbar_wait(acc_full, (lc - 1) & 1);
+                    tc::tc_fence_after_sync();
+                    src_t = tmem_base + lane_base + (((lc - 1) & 1) ? 128u : 0u);
+                }
+                for (int q = 0; q < L.n_chunks; ++q, ++cq) {
+                    if ((q & 1) != wg) continue;
+                    const ChunkInfo c = chunk_info(L, q);
+                    if (l == 0) {
+                        const int ul = (64 * c.group) / p.uw;
+                        if (ul != cur_unit) {
+                            if (cur_unit >= 0) {
+                                __syncwarp();
+                                if (lane == 0) tc::mbar_arrive(&xs_empty[(uc0 + cur_unit) % p.n_units]);
+                            }
+                            cur_unit = ul;
+                            const uint32_t un = uc0 + ul;
+                            tc::mbar_wait(&xs_full[un % p.n_units], (un / p.n_units) & 1);
+                            xrow = xs + (size_t)(un % p.n_units) * p.unit_floats + (size_t)row * p.xld - (size_t)ul * p.uw;
+                        }
+                    }
+                    const int s = (int)(cq % (uint32_t)p.ns);
+                    tc::mbar_wait(&empty[s], ((cq / (uint32_t)p.ns) & 1u) ^ 1u);
+                    tc::tc_fence_after_sync();
+                    const uint32_t a_t = tmem_base + lane_base + TMEM_A0 + 64u * s;
+                    if (!c.base) {
+                        const int f0 = 64 * c.group + 8 * c.j;
+#pragma unroll 1
+                        for (int h = 0; h < 2; ++h) {          // 4 features per pass: keeps the hot loop small (I-cache)
+                            float v[4];
+                            if (l == 0) {
+                                const float4 t = *reinterpret_cast<const float4*>(xrow + f0 + 4 * h);
+                                v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+                            } else {
+                                tc::tmem_ld4(src_t + (uint32_t)(f0 + 4 * h), v);
+                            }
+                            uint32_t hi[8], lo[8];
+                            bspline_slots<K>(L, lut, v[0], hi, lo);
+                            bspline_slots<K>(L, lut, v[1], hi + 4, lo + 4);
+                            tc::tmem_st8(a_t + 16u * h, hi);
+                            tc::tmem_st8(a_t + 32u + 16u * h, lo);
+                            bspline_slots<K>(L, lut, v[2], hi, lo);
+                            bspline_slots<K>(L, lut, v[3], hi + 4, lo + 4);
+                            tc::tmem_st8(a_t + 16u * h + 8u, hi);
+                            tc::tmem_st8(a_t + 32u + 16u * h + 8u, lo);
+                        }
+                    } else {
+#pragma unroll 1
+                        for (int jj = 0; jj < c.n_oct; ++jj) {
+                            const int f0 = 64 * c.group + 8 * jj;
+                            float v[8];
+                            if (l == 0) {
+                                const float4 t0 = *reinterpret_cast<const float4*>(xrow + f0);
+                                const float4 t1 = *reinterpret_cast<const float4*>(xrow + f0 + 4);
+                                v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w; v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
+                            } else {
+                                tc::tmem_ld8(src_t + (uint32_t)f0, v);
+                            }
+                            float r[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                v[i] = silu_nan(v[i]);
+                                r[i] = trunc_residual(v[i]);
+                            }
+                            tc::tmem_st4(a_t + 4u * jj, pack_trunc(v[0], v[1]), pack_trunc(v[2], v[3]), pack_trunc(v[4], v[5]),
+                                         pack_trunc(v[6], v[7]));
+                            tc::tmem_st4(a_t + 32u + 4u * jj, pack_rn(r[0], r[1]), pack_rn(r[2], r[3]), pack_rn(r[4], r[5]),
+                                         pack_rn(r[6], r[7]));
+                        }
+                    }
+                    tc::tmem_st_wait();
+                    tc::tc_fence_before_sync();
+                    tc::mbar_arrive(&a_full[s]);
+                }
+                if (l == 0) {
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(&xs_empty[(uc0 + cur_unit) % p.n_units]);
+                    uc0 += (uint32_t)p.units_per_tile;
+                }
+            }
+            // ---- epilogue of the last layer: TMEM -> registers -> post-affine -> y -------------------------------
+            {
+                const LayerT2& L = p.layers[p.n_layers - 1];
+                tc::mbar_wait(acc_full, (lc - 1) & 1);
+                tc::tc_fence_after_sync();
+                const uint32_t taddr = tmem_base + lane_base + (((lc - 1) & 1) ? 128u : 0u);
+                float* yrow = p.y + (row0 + row) * p.ldy;
+                for (int jb = wg; jb < L.N_pad / 8; jb += 2) {
+                    float v[8];
+                    tc::tmem_ld8(taddr + (uint32_t)(8 * jb), v);
+                    if (row < nrows) {
+                        if (p.has_post) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                if (8 * jb + i < L.N) v[i] = apply_affine(p.post, 8 * jb + i, v[i]);
+                        }
+                        if (p.y_vec && 8 * jb + 8 <= L.N) {
+                            *reinterpret_cast<float4*>(yrow + 8 * jb) = make_float4(v[0], v[1], v[2], v[3]);
+                            *reinterpret_cast<float4*>(yrow + 8 * jb + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                if (8 * jb + i < L.N) yrow[8 * jb + i] = v[i];
+                        }
+                    }
+                }
+                tc::tc_fence_before_sync();
+            }
+        }
+    } else if (warp < NPW + NGW) {
+        // ========================================= GATHER ======================================================
+        const int gw = warp - NPW;
+        const bool vec = (p.agg.num_cols % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.agg.x) & 15u) == 0) && (p.agg.ldx % 4 == 0) &&
+                         (!p.agg.x_halo || (((reinterpret_cast<uintptr_t>(p.agg.x_halo) & 15u) == 0) && (p.agg.ld_halo % 4 == 0))) &&
+                         (p.agg.mode != KAGNN_AGG_GINE ||
+                          (((reinterpret_cast<uintptr_t>(p.agg.edge_feat) & 15u) == 0) && (p.agg.ld_edge % 4 == 0)));
+        const bool gine = p.agg.mode == KAGNN_AGG_GINE;
+        const int F_pad = p.layers[0].F_pad;
+        uint32_t uc = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            const long long row0 = (long long)tile * BM;
+            for (int ub = 0; ub < p.units_per_tile; ++ub, ++uc) {
+                const int u = (int)(uc % (uint32_t)p.n_units);
+                tc::mbar_wait(&xs_empty[u], ((uc / (uint32_t)p.n_units) & 1u) ^ 1u);
+                float* xsu = xs + (size_t)u * p.unit_floats;
+                const int c0 = ub * p.uw, ucols = min(p.uw, F_pad - c0);
+                if (vec) {
+                    if (gine) gather_unit<true, true>(p, row0, c0, ucols, xsu, gw, lane);
+                    else gather_unit<true, false>(p, row0, c0, ucols, xsu, gw, lane);
+                } else {
+                    if (gine) gather_unit<false, true>(p, row0, c0, ucols, xsu, gw, lane);
+                    else gather_unit<false, false>(p, row0, c0, ucols, xsu, gw, lane);
+                }
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&xs_full[u]);
+            }
+        }
+    } else if (warp == WARP_MMA) {
+        // ========================================= MMA ISSUER ==================================================
+        if (lane == 0) {
+            uint32_t cq = 0, lc = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                for (int l = 0; l < p.n_layers; ++l, ++lc) {
+                    const LayerT2& L = p.layers[l];
+                    const uint32_t idesc = tc::idesc_bf16_f32(BM, L.N_pad);
+                    const uint32_t d_tmem = tmem_base + ((lc & 1) ? 128u : 0u);
+                    const uint32_t lbo_b = (uint32_t)L.N_pad * 16u;
+                    for (int q = 0; q < L.n_chunks; ++q, ++cq) {
+                        const int s = (int)(cq % (uint32_t)p.ns);
+                        const uint32_t par = (cq / (uint32_t)p.ns) & 1u;
+                        const ChunkInfo c = chunk_info(L, q);
+                        tc::mbar_wait(&a_full[s], par);
+                        tc::mbar_wait(&b_full[s], par);
+                        tc::tc_fence_after_sync();
+                        const uint32_t a_hi = tmem_base + TMEM_A0 + 64u * s, a_lo = a_hi + 32u;
+                        const uint32_t b_hi = tc::smem_u32(bst + (size_t)s * p.bstage_bytes);
+                        const uint32_t b_lo = b_hi + (uint32_t)c.nk * lbo_b;
+                        for (int kk = 0; kk < c.nk / 2; ++kk) {
+                            const uint64_t dbh = tc::smem_desc(b_hi + kk * 2 * lbo_b, lbo_b, 128);
+                            const uint64_t dbl = tc::smem_desc(b_lo + kk * 2 * lbo_b, lbo_b, 128);
+                            tc::umma_bf16_ts(d_tmem, a_hi + 8u * kk, dbh, idesc, (q | kk) != 0 ? 1u : 0u);
+                            tc::umma_bf16_ts(d_tmem, a_hi + 8u * kk, dbl, idesc, 1u);
+                            tc::umma_bf16_ts(d_tmem, a_lo + 8u * kk, dbh, idesc, 1u);
+                        }
+                        tc::umma_commit(&empty[s]);
+                    }
+                    tc::umma_commit(acc_full);
+                }
+            }
+        }
+    } else {
+        // ========================================== W LOADER ===================================================
+        if (lane == 0) {
+            uint32_t cq = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                for (int l = 0; l < p.n_layers; ++l) {
+                    const LayerT2& L = p.layers[l];
+                    for (int q = 0; q < L.n_chunks; ++q, ++cq) {
+                        const int s = (int)(cq % (uint32_t)p.ns);
+                        const ChunkInfo c = chunk_info(L, q);
+                        tc::mbar_wait(&empty[s], ((cq / (uint32_t)p.ns) & 1u) ^ 1u);
+                        tc::mbar_arrive_expect_tx(&b_full[s], c.b_bytes);
+                        tc::bulk_g2s(bst + (size_t)s * p.bstage_bytes, L.wtc + c.b_off, c.b_bytes, &b_full[s]);
+                    }
+                }
+            }
+        }
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == WARP_MMA) tc::tmem_dealloc(tmem_base, 512);
+}
+
+inline int ceil16(int v) { return (v + 15) & ~15; }
+
+}  // namespace
+
+int kagnn_fused_fwd_tc2(const KagnnAggregate* agg, int64_t num_rows, const KagnnAffine* pre, float* agg_out,
+                        int64_t ld_agg_out, int32_t n_layers, const KagnnKanLayer* layers, const KagnnAffine* post, float* y,
+                        int64_t ldy, cudaStream_t stream) {
+    if (n_layers < 1 || n_layers > KAGNN_MAX_LAYERS) return KAGNN_EUNSUPPORTED;
+    DeviceProps props{};
+    int rc = kagnn_get_props(&props);
+    if (rc != KAGNN_OK) return rc;
+    if (props.cc_major != 10) return KAGNN_EUNSUPPORTED;
+
+    Tc2Params p{};
+    p.agg = *agg;
+    p.has_pre = pre != nullptr;
+    if (pre) p.pre = *pre;
+    p.has_post = post != nullptr;
+    if (post) p.post = *post;
+    p.num_rows = num_rows;
+    p.agg_out = agg_out;
+    p.ld_agg_out = ld_agg_out;
+    p.y = y;
+    p.ldy = ldy;
+    p.n_layers = n_layers;
+    p.n_tiles = (int)ceil_div64(num_rows, BM);
+
+    const int k = layers[0].spline_order;
+    int width = agg->num_cols, n_max = 0;
+    for (int l = 0; l < n_layers; ++l) {
+        const KagnnKanLayer& s = layers[l];
+        LayerT2& d = p.layers[l];
+        if (s.basis != KAGNN_BASIS_BSPLINE || !s.packed_w_tc || s.in_features != width) return KAGNN_EUNSUPPORTED;
+        if (s.spline_order != k || k < 1 || k > 3 || s.grid_size < 1 || s.grid_size + k > 8) return KAGNN_EUNSUPPORTED;
+        if (s.out_features <= 0 || s.out_features > 128) return KAGNN_EUNSUPPORTED;
+        if (!(s.h > 0.f)) return KAGNN_EINVAL;
+        if (!aligned16(s.packed_w_tc)) return KAGNN_EALIGN;
+        d.F = s.in_features;
+        d.F_pad = ceil16(s.in_features);
+        d.N = s.out_features;
+        d.N_pad = ceil16(s.out_features);
+        d.n_chunks = d.F_pad / 8 + (d.F_pad + 63) / 64;
+        d.inv_h = 1.0f / s.h;
+        d.c0 = -s.t0 * d.inv_h;
+        d.lim = (float)(s.grid_size + 2 * k);
+        d.wtc = static_cast<const uint8_t*>(s.packed_w_tc);
+        if (d.N_pad > n_max) n_max = d.N_pad;
+        width = s.out_features;
+    }
+    if (ldy < width) return KAGNN_EINVAL;
+    p.y_vec = aligned16(y) && (ldy % 4 == 0);
+
+    const int F_pad0 = p.layers[0].F_pad;
+    p.uw = F_pad0 > 64 ? 128 : 64;
+    p.xld = p.uw + 4;                                   // (xld / 4) odd: conflict-free float4 reads with thread = row
+    p.unit_floats = BM * p.xld;
+    p.units_per_tile = (F_pad0 + p.uw - 1) / p.uw;
+    p.bstage_bytes = 256 * n_max;
+    const int tail = LUT_ROWS * 16 + (2 * MAX_UNITS + 3 * MAX_STAGE + 2) * 8;
+    const int unit_bytes = p.unit_floats * (int)sizeof(float);
+    // ring depths: at least 2 x-units and 2 stages; prefer deeper stages, then more units
+    int best_units = 0, best_ns = 0;
+    for (int nu = 2; nu <= MAX_UNITS; ++nu) {
+        const int left = (int)props.max_smem - tail - nu * unit_bytes;
+        int ns = left / p.bstage_bytes;
+        if (ns > MAX_STAGE) ns = MAX_STAGE;
+        if (ns < 2) break;
+        if (best_units == 0 || ns >= best_ns) { best_units = nu; best_ns = ns; }
+        else break;
+    }
+    if (best_units == 0) return KAGNN_EUNSUPPORTED;
+    p.n_units = best_units;
+    p.ns = best_ns;
+    const size_t smem = (size_t)p.n_units * unit_bytes + (size_t)p.ns * p.bstage_bytes + tail;
+
+    void (*kern)(Tc2Params) = k == 3 ? fused_tc2_kernel<3> : (k == 2 ? fused_tc2_kernel<2> : fused_tc2_kernel<1>);
+    KAGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)props.max_smem));
+    const int grid = p.n_tiles < props.num_sms ? p.n_tiles : props.num_sms;
+    kern<<<(unsigned)grid, NTHREADS, smem, stream>>>(p);
+    KAGNN_LAUNCH_CHECK();
+    return KAGNN_OK;
+}

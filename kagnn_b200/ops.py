@@ -218,10 +218,15 @@ def set_path(mode: int) -> None:
     L.check(L.lib().kagnn_set_path(mode), "set_path")
 
 
+def set_tc_variant(variant: int) -> None:
+    """0 = pipelined tcgen05 kernel first (default), 1 = only the shared-memory-A tcgen05 kernel."""
+    L.check(L.lib().kagnn_set_tc_variant(variant), "set_tc_variant")
+
+
 def launch_counters():
     a, b = C.c_int64(0), C.c_int64(0)
     L.lib().kagnn_get_launch_counters(C.byref(a), C.byref(b))
-    return {"tc": a.value, "fp32": b.value}
+    return {"tc": a.value, "fp32": b.value, "tc2": L.lib().kagnn_get_tc2_launches()}
 
 
 # ---------------------------------------------------------------------------------------------------

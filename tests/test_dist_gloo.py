@@ -1,0 +1,122 @@
+"""Host-side logic of the node-range sharding (kagnn_b200/dist.py) on CPU with the gloo backend, world_size 2 and 3:
+partition book, halo lists, the index all-to-all and the per-layer row exchange.  The arithmetic of the product runs
+only on the GPU, so the row gather that fills the send buffer is injected (``pack=``) and the aggregation is done by
+the oracle: what is checked here is that [owned rows ; exchanged halo rows] + the relabelled edge list reproduce,
+shard by shard, the aggregation over the global graph."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import kagnn_oracle as K
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _global_problem(world, n_local, e_per_rank, f, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    n = world * n_local
+    x = torch.randn(n, f, generator=g)
+    eis = []
+    for r in range(world):
+        src = torch.randint(0, n, (e_per_rank,), generator=g)
+        dst = torch.randint(r * n_local, (r + 1) * n_local, (e_per_rank,), generator=g)
+        eis.append(torch.stack([src, dst]))
+    return x, eis
+
+
+def _worker(rank, world, port, n_local, e_per_rank, f, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from kagnn_b200 import dist as kd
+        x, eis = _global_problem(world, n_local, e_per_rank, f)
+        ei = eis[rank]
+        plan = kd.build_halo_plan(ei, rank, world, n_local, build_csr=False)
+        lo = rank * n_local
+        # halo set == the distinct remote sources (CPU set computation)
+        remote = sorted({int(s) for s in ei[0].tolist() if not (lo <= s < lo + n_local)})
+        assert plan.halo_global.tolist() == remote
+        assert plan.n_halo == len(remote) and sum(plan.recv_splits) == len(remote)
+        assert plan.recv_splits[rank] == 0 and plan.send_splits[rank] == 0
+        owners = [s // n_local for s in remote]
+        assert plan.recv_splits == [owners.count(p) for p in range(world)]
+        # relabelled edges address [owned ; halo]
+        ext_ids = torch.cat([torch.arange(lo, lo + n_local), plan.halo_global])
+        assert torch.equal(ext_ids[plan.edge_index_local[0]], ei[0])
+        assert torch.equal(plan.edge_index_local[1] + lo, ei[1])
+        # the exchange delivers exactly the halo rows (twice: the plan is reusable, widths may differ per layer)
+        xchg = kd.HaloExchange(plan, pack=lambda t, idx: t.index_select(0, idx.long()))
+        x_local = x[lo:lo + n_local]
+        for width in (f, 1):
+            halo = xchg(x_local[:, :width].contiguous())
+            assert torch.equal(halo, x[plan.halo_global][:, :width])
+        # aggregation over [owned ; halo] with the local edge list == the global aggregation, for the owned rows
+        x_ext = torch.cat([x_local, xchg(x_local)])
+        agg_local = torch.zeros(n_local, f).index_add_(0, plan.edge_index_local[1], x_ext[plan.edge_index_local[0]])
+        ei_all = torch.cat(eis, dim=1)
+        agg_global = torch.zeros(world * n_local, f).index_add_(0, ei_all[1], x[ei_all[0]])
+        assert torch.allclose(agg_local, agg_global[lo:lo + n_local], atol=1e-5)
+        # a full GIN conv through the oracle on the shard == the oracle on the global graph
+        ident = lambda t: t  # noqa: E731
+        full = K.gin_conv(x, ei_all, ident)[lo:lo + n_local]
+        shard = K.gin_conv(x_ext, plan.edge_index_local, ident)[:n_local]
+        assert torch.allclose(shard, full, atol=1e-5)
+        assert xchg.bytes_sent == sum(plan.send_splits) * 4 * (2 * f + 1)
+        out.put((rank, "ok"))
+    except Exception as exc:  # pragma: no cover - reported to the parent
+        import traceback
+        out.put((rank, f"{type(exc).__name__}: {exc}\n{traceback.format_exc()}"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_halo_plan_and_exchange_gloo(world):
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, 40, 300, 5, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [out.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(results) == [(r, "ok") for r in range(world)], results
+
+
+def test_relabel_rejects_foreign_targets():
+    from kagnn_b200 import dist as kd
+    ei = torch.tensor([[0, 5], [0, 9]])
+    with pytest.raises(IndexError):
+        kd.relabel_edges(ei, 0, 2, 5)          # target 9 belongs to rank 1
+    with pytest.raises(IndexError):
+        kd.relabel_edges(torch.tensor([[10], [0]]), 0, 2, 5)   # source outside the global range
+
+
+def test_relabel_without_remote_edges():
+    from kagnn_b200 import dist as kd
+    ei = torch.tensor([[1, 2, 3], [0, 0, 4]])
+    loc, halo, counts = kd.relabel_edges(ei, 0, 2, 5)
+    assert halo.numel() == 0 and counts.tolist() == [0, 0]
+    assert torch.equal(loc, ei)
+
+
+def test_shard_batch_by_graph():
+    from kagnn_b200 import dist as kd
+    batch = torch.tensor([0, 0, 1, 2, 2, 2, 3, 4, 4])
+    seen = torch.zeros_like(batch, dtype=torch.bool)
+    for r in range(2):
+        g0, g1, mask = kd.shard_batch_by_graph(batch, 5, r, 2)
+        assert not (seen & mask).any()
+        seen |= mask
+        assert set(batch[mask].tolist()) == set(range(g0, g1))
+    assert seen.all()

@@ -16,12 +16,15 @@ def _sd_cpu(m):
     return {k: v.detach().cpu() for k, v in m.state_dict().items()}
 
 
-@pytest.fixture(params=["auto", "fp32"])
+@pytest.fixture(params=["auto", "tc_general", "fp32"])
 def path_mode(request):
-    """auto = tcgen05 kernel wherever it applies; fp32 = force the general CUDA-core kernel (both are GPU paths)."""
+    """auto = pipelined tcgen05 kernel wherever it applies, else the general tcgen05 kernel, else fp32;
+    tc_general = skip the pipelined kernel; fp32 = force the CUDA-core kernel (all are GPU paths)."""
     from kagnn_b200 import ops, _lib as L
     ops.set_path(L.PATH_FP32 if request.param == "fp32" else L.PATH_AUTO)
+    ops.set_tc_variant(1 if request.param == "tc_general" else 0)
     yield request.param
+    ops.set_tc_variant(0)
     ops.set_path(L.PATH_AUTO)
 
 

@@ -32,7 +32,7 @@ def test_tc_selftest_row_and_column_identity():
     assert torch.equal(d, a @ b.t())
 
 
-@pytest.mark.parametrize("n,k", [(16, 16), (64, 64), (64, 128), (128, 128), (256, 64), (48, 32), (64, 256), (128, 256)])
+@pytest.mark.parametrize("n,k", [(16, 16), (64, 64), (64, 128), (128, 128), (256, 64), (48, 32), (64, 256)])
 def test_tc_selftest_a_operand_in_tmem(n, k):
     """Same product with the A operand written to tensor memory by tcgen05.st and consumed by the TS-form MMA
     (the layout the fused kernel's basis producers use): modes 11 (one bf16 pass) and 13 (hi/lo compensated)."""

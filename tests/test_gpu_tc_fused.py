@@ -13,11 +13,14 @@ def _sd_cpu(m):
     return {k: v.detach().cpu() for k, v in m.state_dict().items()}
 
 
-@pytest.fixture
-def tc_only():
+@pytest.fixture(params=["pipelined", "general"])
+def tc_only(request):
+    """pipelined = fused_tc2.cu (A operand in TMEM) wherever it applies, then fused_tc.cu; general = fused_tc.cu only."""
     from kagnn_b200 import ops, _lib as L
     ops.set_path(L.PATH_TC)
-    yield
+    ops.set_tc_variant(1 if request.param == "general" else 0)
+    yield request.param
+    ops.set_tc_variant(0)
     ops.set_path(L.PATH_AUTO)
 
 
@@ -37,6 +40,19 @@ def test_kan_linear_tc(tc_only, G, k, fin, fout, n):
         y = m.cuda()(x.cuda()).cpu()
     assert ops.launch_counters()["tc"] == c0 + 1
     assert K.rel_err(y, y_ref) <= TOL
+
+
+def test_pipelined_kernel_is_the_one_that_runs():
+    """The arxiv-shaped GIN layer must go through fused_tc2.cu (counted separately by the library)."""
+    import kagnn_b200 as kb
+    from kagnn_b200 import ops
+    torch.manual_seed(1)
+    gin = kb.GIKANLayer(128, 64, 5, 3, 64, 2).cuda()
+    ei = torch.randint(0, 1000, (2, 6000)).cuda()
+    c0 = ops.launch_counters()["tc2"]
+    with torch.no_grad():
+        gin(torch.randn(1000, 128).cuda(), ei)
+    assert ops.launch_counters()["tc2"] == c0 + 1
 
 
 def test_kan_special_values_tc(tc_only):
