@@ -38,7 +38,7 @@ constexpr int RPW = BM / NGW;                // rows per gather warp
 constexpr int MAX_STAGE = 4;                 // A stages in TMEM (64 columns each) / B stages in shared memory
 constexpr int MAX_UNITS = 4;                 // x-tile ring slots
 constexpr uint32_t TMEM_A0 = 256;            // columns [0,256): two accumulator regions of 128; [256,512): A stages
-constexpr int LUT_ROWS = 12;
+constexpr int LUT_ROWS = 13;                  // per layer: knot interval j = -1 .. 11 (row j + 1)
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kMagic = 12582912.0f;        // 1.5 * 2^23: u + kMagic (round down) = floor(u) + kMagic
 
@@ -109,12 +109,14 @@ __device__ __forceinline__ uint32_t pack_rn(float lo_elem, float hi_elem) {
 // Uniform knots t_j = t0 + j h (ekan.py:28-37): interval j = floor(u), the k+1 non-zero bases B_{j-k..j} are the local
 // polynomials of the fractional position; outside [t_0, t_last) and for NaN every basis is 0 (half-open indicator, :95).
 template <int K>
-__device__ __forceinline__ void bspline_slots(const LayerT2& L, const uint4* __restrict__ lut, float x, uint32_t* hi, uint32_t* lo) {
-    const float u = fmaf(x, L.inv_h, L.c0);
+__device__ __forceinline__ void bspline_slots(float inv_h, float c0, float limp, const uint4* __restrict__ lut, float x, uint32_t* hi,
+                                              uint32_t* lo) {
+    // u clamped to [-0.5, lim + 0.5]: out-of-range inputs and NaN (fmaxf drops it) land in interval -1 or lim, whose LUT rows
+    // select nothing; the fractional position stays in [0, 1) so every basis value below is finite and >= 0
+    const float u = fminf(fmaxf(fmaf(x, inv_h, c0), -0.5f), limp);
     const float t = __fadd_rd(u, kMagic);
-    const bool valid = (u >= 0.0f) && (u < L.lim);
-    const float fr = valid ? (u - (t - kMagic)) : 0.0f;
-    const int idx = valid ? (__float_as_int(t) - 0x4B400000 + (3 - K)) : (LUT_ROWS - 1);
+    const float fr = u - (t - kMagic);
+    const int idx = __float_as_int(t) - (0x4B400000 - 1);
     float b0, b1, b2 = 0.f, b3 = 0.f;
     if (K == 3) {
         const float omf = 1.0f - fr, f2 = fr * fr;
@@ -349,6 +351,170 @@ __device__ __forceinline__ void gather_unit(const Tc2Params& p, long long row0, 
     while (cur < RPW) finish_row();
 }
 
+
+// A row of zeros in device memory: list entries that do not exist (tail of the last batch, rows past the end of the graph)
+// point here, so every load of a sub-batch is unconditional and the U loads are all in flight together.
+__device__ float g_zero_row[4096];
+
+// Fast gather (128-bit path, no edge features): same flattened list as gather_unit, restructured for memory-level
+// parallelism and a short instruction stream:
+//   * every entry of a sub-batch is loaded unconditionally from a valid address (missing entries -> g_zero_row with
+//     weight 0), so ptxas keeps the U 128-bit loads independent instead of chaining predicated load + move pairs;
+//   * the column index / edge weight of the NEXT batch of 32 entries are fetched before the current batch is consumed;
+//   * a finished row is parked raw (one STS.128); mean scale, pre-affine and the agg_out store run in a post-pass over
+//     the warp's 16 rows only when the layer has any of them (a plain GIN layer has none).
+template <bool WEIGHTED>
+__device__ __forceinline__ void gather_unit_fast(const Tc2Params& p, long long row0, int c0, int ucols, float* __restrict__ xsu,
+                                                 int gw, int lane) {
+    constexpr int U = 8;
+    const KagnnAggregate& a = p.agg;
+    const int F = a.num_cols, mode = a.mode, xld = p.xld;
+    const bool segment = (mode == KAGNN_AGG_SEGMENT_SUM) || (mode == KAGNN_AGG_SEGMENT_MEAN);
+    const int rl0 = gw * RPW;
+    const int cl = 4 * lane;
+    const bool cin0 = cl < ucols;
+    const bool cv0 = cin0 && (c0 + cl) < F;
+    const int cload = cv0 ? (c0 + cl) : 0;                 // lanes past the last column re-read column 0 and discard it
+    const int self1 = segment ? 0 : 1;
+    int rp = 0;
+    if (mode != KAGNN_AGG_NONE) {
+        long long r = row0 + rl0 + min(lane, RPW);
+        if (r > p.num_rows) r = p.num_rows;
+        rp = __ldg(a.rowptr + r);
+    }
+    const int vs = rp + self1 * min(lane, RPW);
+    const int v_beg = __shfl_sync(0xffffffffu, vs, 0), v_end = __shfl_sync(0xffffffffu, vs, RPW);
+    int cur = 0, cur_vend = __shfl_sync(0xffffffffu, vs, 1);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float* const dst0 = xsu + rl0 * xld + cl;
+
+    auto finish_row = [&]() {
+        if (cin0) {
+            const float4 o = cv0 ? make_float4(acc[0], acc[1], acc[2], acc[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(dst0 + cur * xld) = o;
+        }
+        acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+        ++cur;
+        cur_vend = (cur < RPW) ? __shfl_sync(0xffffffffu, vs, min(cur + 1, RPW)) : 0x7fffffff;
+    };
+    // lane-parallel description of list entry vbase + lane: row lookup, self flag, CSR entry id; the index / weight loads
+    // are issued here and consumed one batch later
+    struct Meta {
+        int r, e, col;
+        float w;
+        bool self_, on;
+    };
+    auto prep = [&](int vbase) {
+        Meta m;
+        const int ve = vbase + lane;
+        int r = 0;
+#pragma unroll
+        for (int step = RPW / 2; step >= 1; step >>= 1) {
+            const int t = __shfl_sync(0xffffffffu, vs, r + step);
+            r += (t <= ve) ? step : 0;
+        }
+        const int vs_r = __shfl_sync(0xffffffffu, vs, r), rp_r = __shfl_sync(0xffffffffu, rp, r);
+        m.r = r;
+        m.on = ve < v_end;
+        m.self_ = (self1 != 0) && (ve == vs_r);
+        m.e = rp_r + (ve - vs_r) - self1;
+        m.col = m.e;
+        m.w = 1.0f;
+        if (m.on && !m.self_) {
+            if (a.col) m.col = __ldg(a.col + m.e);
+            if (WEIGHTED) m.w = __ldg(a.edge_weight + m.e);
+        }
+        return m;
+    };
+
+    Meta nxt = prep(v_beg);
+#pragma unroll 1
+    for (int vbase = v_beg; vbase < v_end; vbase += 32) {
+        const Meta m = nxt;
+        if (vbase + 32 < v_end) nxt = prep(vbase + 32);
+        const float* my_row = g_zero_row;
+        float my_w = 0.0f;
+        if (m.on) {
+            if (m.self_) {
+                const long long rg = row0 + rl0 + m.r;
+                if (rg < p.num_rows) {
+                    const long long sr = a.src_index ? (long long)__ldg(a.src_index + rg) : rg;
+                    my_row = a.x + sr * a.ldx;
+                    my_w = (mode == KAGNN_AGG_NONE) ? 1.0f : a.self_scale;
+                    if (WEIGHTED && a.self_weight) my_w = __ldg(a.self_weight + rg);
+                }
+            } else {
+                int j = m.col;
+                if (a.src_index) j = __ldg(a.src_index + j);
+                my_row = src_row(a, j);
+                my_w = m.w;
+            }
+        }
+        const int cnt = min(32, v_end - vbase);
+#pragma unroll 1
+        for (int t0 = 0; t0 < cnt; t0 += U) {
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(shfl_ptr(my_row, t0 + u) + cload));
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = vbase + t0 + u;
+                const float w = __shfl_sync(0xffffffffu, my_w, t0 + u);
+                while (e >= cur_vend) finish_row();        // warp-uniform; also steps over empty rows
+                acc[0] = fmaf(w, v[u].x, acc[0]);
+                acc[1] = fmaf(w, v[u].y, acc[1]);
+                acc[2] = fmaf(w, v[u].z, acc[2]);
+                acc[3] = fmaf(w, v[u].w, acc[3]);
+            }
+        }
+    }
+    while (cur < RPW) finish_row();
+
+    const bool pre_silu = p.has_pre && p.pre.act == KAGNN_ACT_SILU;
+    if (p.has_pre || p.agg_out || mode == KAGNN_AGG_SEGMENT_MEAN) {
+        // post-pass: every lane revisits the values it parked itself (no synchronisation needed)
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.has_pre && cv0) {
+            if (p.pre.scale) sc = __ldg(reinterpret_cast<const float4*>(p.pre.scale + c0 + cl));
+            if (p.pre.shift) sh = __ldg(reinterpret_cast<const float4*>(p.pre.shift + c0 + cl));
+        }
+        const bool pre_vec = (!p.pre.scale || (reinterpret_cast<uintptr_t>(p.pre.scale) & 15u) == 0) &&
+                             (!p.pre.shift || (reinterpret_cast<uintptr_t>(p.pre.shift) & 15u) == 0);
+        if (p.has_pre && cv0 && !pre_vec) {
+            const int c = c0 + cl;
+            if (p.pre.scale) sc = make_float4(__ldg(p.pre.scale + c), __ldg(p.pre.scale + c + 1), __ldg(p.pre.scale + c + 2), __ldg(p.pre.scale + c + 3));
+            if (p.pre.shift) sh = make_float4(__ldg(p.pre.shift + c), __ldg(p.pre.shift + c + 1), __ldg(p.pre.shift + c + 2), __ldg(p.pre.shift + c + 3));
+        }
+        const bool out_vec = p.agg_out && ((reinterpret_cast<uintptr_t>(p.agg_out) & 15u) == 0) && (p.ld_agg_out % 4 == 0);
+#pragma unroll 1
+        for (int rr = 0; rr < RPW; ++rr) {
+            const long long r = row0 + rl0 + rr;
+            const bool rv = r < p.num_rows;
+            float os = 1.0f;
+            if (mode == KAGNN_AGG_SEGMENT_MEAN)
+                os = 1.0f / (float)max(__shfl_sync(0xffffffffu, rp, rr + 1) - __shfl_sync(0xffffffffu, rp, rr), 1);
+            if (!cin0) continue;
+            float4 t = *reinterpret_cast<const float4*>(dst0 + rr * xld);
+            float o[4] = {t.x * os, t.y * os, t.z * os, t.w * os};
+            const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (p.has_pre) {
+                    o[i] = fmaf(o[i], scv[i], shv[i]);
+                    if (pre_silu) o[i] = __fdividef(o[i], 1.0f + ex2_approx(-kLog2e * o[i]));
+                }
+                if (!(cv0 && rv)) o[i] = 0.f;
+            }
+            *reinterpret_cast<float4*>(dst0 + rr * xld) = make_float4(o[0], o[1], o[2], o[3]);
+            if (p.agg_out && rv && cv0) {
+                float* g = p.agg_out + r * p.ld_agg_out + c0 + cl;
+                if (out_vec) *reinterpret_cast<float4*>(g) = make_float4(o[0], o[1], o[2], o[3]);
+                else { g[0] = o[0]; g[1] = o[1]; g[2] = o[2]; g[3] = o[3]; }
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 template <int K>
 __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_constant__ Tc2Params p) {
@@ -356,7 +522,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
     float* xs = reinterpret_cast<float*>(smem);
     uint8_t* bst = smem + (size_t)p.n_units * p.unit_floats * sizeof(float);
     uint4* lut = reinterpret_cast<uint4*>(bst + (size_t)p.ns * p.bstage_bytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(lut + LUT_ROWS);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(lut + KAGNN_MAX_LAYERS * LUT_ROWS);
     uint64_t* xs_full = bars;
     uint64_t* xs_empty = bars + MAX_UNITS;
     uint64_t* a_full = bars + 2 * MAX_UNITS;
@@ -373,23 +539,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
             tc::mbar_init(&xs_empty[s], NPW);
         }
         for (int s = 0; s < MAX_STAGE; ++s) {
-            tc::mbar_init(&a_full[s], 128);
+            tc::mbar_init(&a_full[s], NPROD);
             tc::mbar_init(&b_full[s], 1);
             tc::mbar_init(&empty[s], 1);
         }
         tc::mbar_init(acc_full, 1);
         tc::mbar_fence_init();
     }
-    if (tid < LUT_ROWS) {
-        // row r <-> slot offset s = r - 3 of the first non-zero basis (r = 11: every slot zero).  Output byte q of the
-        // 16-byte slot vector takes source byte q - 2s of (b0 b1 | b2 b3) when that is in 0..7, else the replicated
-        // (zero) sign bit of source byte 1.
+    if (tid < p.n_layers * LUT_ROWS) {
+        // per layer, row q <-> knot interval j = q - 1.  A valid interval (0 <= j < G + 2k) puts its first non-zero basis
+        // into slot s = j - K: output byte b of the 16-byte slot vector takes source byte b - 2s of (b0 b1 | b2 b3) when that
+        // is in 0..7, else the replicated (zero) sign bit of source byte 1.  Rows of intervals outside the knot range select
+        // nothing (every slot zero).
+        const int l = tid / LUT_ROWS, j = tid - l * LUT_ROWS - 1;
+        const bool inside = j >= 0 && j < (int)p.layers[l].lim;
         uint32_t w[4];
         for (int m = 0; m < 4; ++m) {
             uint32_t sel = 0;
             for (int n = 0; n < 4; ++n) {
-                const int src = 4 * m + n - 2 * (tid - 3);
-                const uint32_t nib = (tid < LUT_ROWS - 1 && src >= 0 && src <= 7) ? (uint32_t)src : 9u;
+                const int src = 4 * m + n - 2 * (j - K);
+                const uint32_t nib = (inside && src >= 0 && src <= 7) ? (uint32_t)src : 9u;
                 sel |= nib << (4 * n);
             }
             w[m] = sel;
@@ -403,6 +572,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
 
     if (warp < NPW) {
         // ============================== BASIS PRODUCERS / EPILOGUE =============================================
+        // Both warpgroups work on EVERY chunk: warpgroup wg expands features 4wg..4wg+3 of a spline chunk (octets of parity
+        // wg of a SiLU chunk), so the two halves of a chunk are produced concurrently and the groups stay balanced.
         const int wg = warp >> 2;
         const int row = tid & 127;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
@@ -412,6 +583,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
             const int nrows = (int)min((long long)BM, p.num_rows - row0);
             for (int l = 0; l < p.n_layers; ++l, ++lc) {
                 const LayerT2& L = p.layers[l];
+                const float inv_h = L.inv_h, c0f = L.c0, limp = L.lim + 0.5f;
+                const uint4* lutL = lut + l * LUT_ROWS;
+                const int n_chunks = L.n_chunks;
                 uint32_t src_t = 0;
                 int cur_unit = -1;
                 const float* xrow = nullptr;
@@ -420,8 +594,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                     tc::tc_fence_after_sync();
                     src_t = tmem_base + lane_base + (((lc - 1) & 1) ? 128u : 0u);
                 }
-                for (int q = 0; q < L.n_chunks; ++q, ++cq) {
-                    if ((q & 1) != wg) continue;
+                int s = (int)(cq % (uint32_t)p.ns);
+                uint32_t par = ((cq / (uint32_t)p.ns) & 1u) ^ 1u;
+                for (int q = 0; q < n_chunks; ++q) {
                     const ChunkInfo c = chunk_info(L, q);
                     if (l == 0) {
                         const int ul = (64 * c.group) / p.uw;
@@ -436,34 +611,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                             xrow = xs + (size_t)(un % p.n_units) * p.unit_floats + (size_t)row * p.xld - (size_t)ul * p.uw;
                         }
                     }
-                    const int s = (int)(cq % (uint32_t)p.ns);
-                    tc::mbar_wait(&empty[s], ((cq / (uint32_t)p.ns) & 1u) ^ 1u);
+                    tc::mbar_wait(&empty[s], par);
                     tc::tc_fence_after_sync();
                     const uint32_t a_t = tmem_base + lane_base + TMEM_A0 + 64u * s;
                     if (!c.base) {
-                        const int f0 = 64 * c.group + 8 * c.j;
-#pragma unroll 1
-                        for (int h = 0; h < 2; ++h) {          // 4 features per pass: keeps the hot loop small (I-cache)
-                            float v[4];
-                            if (l == 0) {
-                                const float4 t = *reinterpret_cast<const float4*>(xrow + f0 + 4 * h);
-                                v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-                            } else {
-                                tc::tmem_ld4(src_t + (uint32_t)(f0 + 4 * h), v);
-                            }
-                            uint32_t hi[8], lo[8];
-                            bspline_slots<K>(L, lut, v[0], hi, lo);
-                            bspline_slots<K>(L, lut, v[1], hi + 4, lo + 4);
-                            tc::tmem_st8(a_t + 16u * h, hi);
-                            tc::tmem_st8(a_t + 32u + 16u * h, lo);
-                            bspline_slots<K>(L, lut, v[2], hi, lo);
-                            bspline_slots<K>(L, lut, v[3], hi + 4, lo + 4);
-                            tc::tmem_st8(a_t + 16u * h + 8u, hi);
-                            tc::tmem_st8(a_t + 32u + 16u * h + 8u, lo);
+                        const int f0 = 64 * c.group + 8 * c.j + 4 * wg;
+                        float v[4];
+                        if (l == 0) {
+                            const float4 t = *reinterpret_cast<const float4*>(xrow + f0);
+                            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+                        } else {
+                            tc::tmem_ld4(src_t + (uint32_t)f0, v);
                         }
+                        uint32_t hi[8], lo[8], hi2[8], lo2[8];
+                        bspline_slots<K>(inv_h, c0f, limp, lutL, v[0], hi, lo);
+                        bspline_slots<K>(inv_h, c0f, limp, lutL, v[1], hi + 4, lo + 4);
+                        bspline_slots<K>(inv_h, c0f, limp, lutL, v[2], hi2, lo2);
+                        bspline_slots<K>(inv_h, c0f, limp, lutL, v[3], hi2 + 4, lo2 + 4);
+                        tc::tmem_st8(a_t + 16u * wg, hi);
+                        tc::tmem_st8(a_t + 32u + 16u * wg, lo);
+                        tc::tmem_st8(a_t + 16u * wg + 8u, hi2);
+                        tc::tmem_st8(a_t + 32u + 16u * wg + 8u, lo2);
                     } else {
 #pragma unroll 1
-                        for (int jj = 0; jj < c.n_oct; ++jj) {
+                        for (int jj = wg; jj < c.n_oct; jj += 2) {
                             const int f0 = 64 * c.group + 8 * jj;
                             float v[8];
                             if (l == 0) {
@@ -488,7 +659,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                     tc::tmem_st_wait();
                     tc::tc_fence_before_sync();
                     tc::mbar_arrive(&a_full[s]);
+                    if (++s == p.ns) { s = 0; par ^= 1u; }
                 }
+                cq += (uint32_t)n_chunks;
                 if (l == 0) {
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(&xs_empty[(uc0 + cur_unit) % p.n_units]);
@@ -532,6 +705,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                          (p.agg.mode != KAGNN_AGG_GINE ||
                           (((reinterpret_cast<uintptr_t>(p.agg.edge_feat) & 15u) == 0) && (p.agg.ld_edge % 4 == 0)));
         const bool gine = p.agg.mode == KAGNN_AGG_GINE;
+        const bool plain_copy = p.agg.mode == KAGNN_AGG_NONE && !p.has_pre && !p.agg_out && !p.agg.src_index;
         const int F_pad = p.layers[0].F_pad;
         uint32_t uc = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
@@ -543,7 +717,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                 const int c0 = ub * p.uw, ucols = min(p.uw, F_pad - c0);
                 if (vec) {
                     if (gine) gather_unit<true, true>(p, row0, c0, ucols, xsu, gw, lane);
-                    else gather_unit<true, false>(p, row0, c0, ucols, xsu, gw, lane);
+                    else if (plain_copy) gather_unit<true, false>(p, row0, c0, ucols, xsu, gw, lane);
+                    else if (p.agg.mode == KAGNN_AGG_WEIGHTED) gather_unit_fast<true>(p, row0, c0, ucols, xsu, gw, lane);
+                    else gather_unit_fast<false>(p, row0, c0, ucols, xsu, gw, lane);
                 } else {
                     if (gine) gather_unit<false, true>(p, row0, c0, ucols, xsu, gw, lane);
                     else gather_unit<false, false>(p, row0, c0, ucols, xsu, gw, lane);
@@ -658,6 +834,7 @@ int kagnn_fused_fwd_tc2(const KagnnAggregate* agg, int64_t num_rows, const Kagnn
         width = s.out_features;
     }
     if (ldy < width) return KAGNN_EINVAL;
+    if (agg->num_cols > 4096) return KAGNN_EUNSUPPORTED;   // g_zero_row covers 4096 columns
     p.y_vec = aligned16(y) && (ldy % 4 == 0);
 
     const int F_pad0 = p.layers[0].F_pad;
@@ -666,7 +843,7 @@ int kagnn_fused_fwd_tc2(const KagnnAggregate* agg, int64_t num_rows, const Kagnn
     p.unit_floats = BM * p.xld;
     p.units_per_tile = (F_pad0 + p.uw - 1) / p.uw;
     p.bstage_bytes = 256 * n_max;
-    const int tail = LUT_ROWS * 16 + (2 * MAX_UNITS + 3 * MAX_STAGE + 2) * 8;
+    const int tail = KAGNN_MAX_LAYERS * LUT_ROWS * 16 + (2 * MAX_UNITS + 3 * MAX_STAGE + 2) * 8;
     const int unit_bytes = p.unit_floats * (int)sizeof(float);
     // ring depths: at least 2 x-units and 2 stages; prefer deeper stages, then more units
     int best_units = 0, best_ns = 0;
