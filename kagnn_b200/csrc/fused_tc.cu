@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc_kernel(const __grid_cons
                     const LayerTC& L = p.layers[l];
                     const uint32_t idesc = tc::idesc_bf16_f32(BM, L.N_pad);
                     const uint32_t d_tmem = tmem_base + ((l & 1) ? (uint32_t)p.tmem_r1 : 0u);
-                    const uint32_t lbo_b = (uint32_t)L.N_pad * 16u;
+                    const uint32_t lbo_b = (uint32_t)L.N_pad * 32u;     // k-core slab = hi rows + lo rows
                     for (int q = 0; q < L.n_chunks; ++q, ++cq) {
                         const int s = (int)(cq % (uint32_t)p.n_stage);
                         const uint32_t use = cq / (uint32_t)p.n_stage;
@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc_kernel(const __grid_cons
                         const uint32_t a_hi = tc::smem_u32(stages + (size_t)s * p.stage_bytes);
                         const uint32_t a_lo = a_hi + A_HALF;
                         const uint32_t b_hi = a_hi + 2 * A_HALF;
-                        const uint32_t b_lo = b_hi + (uint32_t)c.nk * lbo_b;
+                        const uint32_t b_lo = b_hi + (uint32_t)L.N_pad * 16u;
                         for (int kk = 0; kk < c.nk / 2; ++kk) {
                             const uint64_t dah = tc::smem_desc(a_hi + kk * 4096, 2048, 128);
                             const uint64_t dal = tc::smem_desc(a_lo + kk * 4096, 2048, 128);
@@ -435,13 +435,12 @@ __global__ void pack_tc_kernel(const float* __restrict__ base_w, const float* __
     const int n = (int)(idx % N_pad);
     const int kc = (int)(idx / N_pad);
     float v[8];
-    int group, j_chunk, kc_in_chunk, nk;
+    int group, j_chunk, kc_in_chunk;
     if (kc < F_pad) {
         const int f = kc;
         group = f / 64;
         j_chunk = (f % 64) / 8;
         kc_in_chunk = f % 8;
-        nk = 8;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             float w = 0.f;
@@ -457,7 +456,6 @@ __global__ void pack_tc_kernel(const float* __restrict__ base_w, const float* __
         const int n_oct = min(8, F_pad / 8 - 8 * group);
         j_chunk = n_oct;                   // the base chunk follows the group's spline chunks
         kc_in_chunk = o % 8;
-        nk = n_oct;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const int f = 8 * o + e;
@@ -467,8 +465,10 @@ __global__ void pack_tc_kernel(const float* __restrict__ base_w, const float* __
     uint4 hi, lo;
     tc::split8(v, hi, lo);
     uint8_t* chunk = out + (size_t)(group * 9 + j_chunk) * 256u * (size_t)N_pad;
-    *reinterpret_cast<uint4*>(chunk + ((size_t)kc_in_chunk * N_pad + n) * 16) = hi;
-    *reinterpret_cast<uint4*>(chunk + ((size_t)nk * N_pad + (size_t)kc_in_chunk * N_pad + n) * 16) = lo;
+    // k-core slab kc of a chunk = [hi rows 0..N_pad-1 | lo rows 0..N_pad-1] (2 * N_pad * 16 bytes): the hi and lo halves of
+    // one slab are adjacent, so [W_hi | W_lo] is also ONE UMMA B operand of 2 * N_pad rows (fused_tc2.cu stacks them along N)
+    *reinterpret_cast<uint4*>(chunk + ((size_t)(2 * kc_in_chunk) * N_pad + n) * 16) = hi;
+    *reinterpret_cast<uint4*>(chunk + ((size_t)(2 * kc_in_chunk + 1) * N_pad + n) * 16) = lo;
 }
 
 inline int ceil16(int v) { return (v + 15) & ~15; }

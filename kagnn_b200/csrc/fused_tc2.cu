@@ -25,6 +25,21 @@
 #include "stage.cuh"
 #include "tc_common.cuh"
 
+// Optional timeline trace of CTA 0 (development builds only: KAGNN_NVCC_EXTRA="-DKAGNN_TRACE=1"): clock stamps per role,
+// event counter and event kind into a caller-provided buffer (scripts/trace_tc2.py).
+#ifdef KAGNN_TRACE
+__device__ unsigned long long* g_trace = nullptr;
+#define TR(role, k, evt)                                                                                           \
+    do {                                                                                                             \
+        if (blockIdx.x == 0 && g_trace && (k) < 512) g_trace[(((role) * 512) + (k)) * 8 + (evt)] = clock64();        \
+    } while (0)
+extern "C" int kagnn_debug_set_trace(unsigned long long* buf) {
+    return cudaMemcpyToSymbol(g_trace, &buf, sizeof(buf)) == cudaSuccess ? 0 : -5;
+}
+#else
+#define TR(role, k, evt) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int BM = 128;
@@ -44,6 +59,7 @@ constexpr float kMagic = 12582912.0f;        // 1.5 * 2^23: u + kMagic (round do
 
 struct LayerT2 {
     int F, F_pad, N, N_pad, n_chunks;
+    int stack;                               // 1: [W_hi | W_lo] is one B operand (N_pad <= 64): accumulator = [hi.hi + lo.hi | hi.lo]
     float c0, inv_h, lim;                    // u = x * inv_h + c0 (= (x - t0)/h); valid iff 0 <= u < lim = G + 2k
     const uint8_t* wtc;
 };
@@ -525,9 +541,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
     uint64_t* bars = reinterpret_cast<uint64_t*>(lut + KAGNN_MAX_LAYERS * LUT_ROWS);
     uint64_t* xs_full = bars;
     uint64_t* xs_empty = bars + MAX_UNITS;
-    uint64_t* a_full = bars + 2 * MAX_UNITS;
-    uint64_t* b_full = a_full + MAX_STAGE;
-    uint64_t* empty = b_full + MAX_STAGE;
+    uint64_t* full = bars + 2 * MAX_UNITS;        // A stage written by all producers AND W chunk landed (one wait for the MMA)
+    uint64_t* empty = full + MAX_STAGE;
     uint64_t* acc_full = empty + MAX_STAGE;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -539,8 +554,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
             tc::mbar_init(&xs_empty[s], NPW);
         }
         for (int s = 0; s < MAX_STAGE; ++s) {
-            tc::mbar_init(&a_full[s], NPROD);
-            tc::mbar_init(&b_full[s], 1);
+            tc::mbar_init(&full[s], NPROD + 1);
             tc::mbar_init(&empty[s], 1);
         }
         tc::mbar_init(acc_full, 1);
@@ -586,13 +600,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                 const float inv_h = L.inv_h, c0f = L.c0, limp = L.lim + 0.5f;
                 const uint4* lutL = lut + l * LUT_ROWS;
                 const int n_chunks = L.n_chunks;
-                uint32_t src_t = 0;
+                uint32_t src_t = 0, src_lo = 0;               // src_lo != 0: previous layer's accumulator is stacked
                 int cur_unit = -1;
                 const float* xrow = nullptr;
                 if (l > 0) {
+                    if (lane == 0 && (warp & 3) == 0) TR(4 + wg, lc, 0);
                     tc::mbar_wait(acc_full, (lc - 1) & 1);
+                    if (lane == 0 && (warp & 3) == 0) TR(4 + wg, lc, 1);
                     tc::tc_fence_after_sync();
                     src_t = tmem_base + lane_base + (((lc - 1) & 1) ? 128u : 0u);
+                    src_lo = p.layers[l - 1].stack ? (uint32_t)p.layers[l - 1].N_pad : 0u;
                 }
                 int s = (int)(cq % (uint32_t)p.ns);
                 uint32_t par = ((cq / (uint32_t)p.ns) & 1u) ^ 1u;
@@ -607,11 +624,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                             }
                             cur_unit = ul;
                             const uint32_t un = uc0 + ul;
+                            if (lane == 0 && (warp & 3) == 0) TR(wg, cq + q, 0);
                             tc::mbar_wait(&xs_full[un % p.n_units], (un / p.n_units) & 1);
+                            if (lane == 0 && (warp & 3) == 0) TR(wg, cq + q, 1);
                             xrow = xs + (size_t)(un % p.n_units) * p.unit_floats + (size_t)row * p.xld - (size_t)ul * p.uw;
                         }
                     }
+                    if (lane == 0 && (warp & 3) == 0) TR(wg, cq + q, 2);
                     tc::mbar_wait(&empty[s], par);
+                    if (lane == 0 && (warp & 3) == 0) TR(wg, cq + q, 3);
                     tc::tc_fence_after_sync();
                     const uint32_t a_t = tmem_base + lane_base + TMEM_A0 + 64u * s;
                     if (!c.base) {
@@ -622,6 +643,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                             v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
                         } else {
                             tc::tmem_ld4(src_t + (uint32_t)f0, v);
+                            if (src_lo) {
+                                float v2[4];
+                                tc::tmem_ld4(src_t + src_lo + (uint32_t)f0, v2);
+                                v[0] += v2[0]; v[1] += v2[1]; v[2] += v2[2]; v[3] += v2[3];
+                            }
                         }
                         uint32_t hi[8], lo[8], hi2[8], lo2[8];
                         bspline_slots<K>(inv_h, c0f, limp, lutL, v[0], hi, lo);
@@ -643,6 +669,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                                 v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w; v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
                             } else {
                                 tc::tmem_ld8(src_t + (uint32_t)f0, v);
+                                if (src_lo) {
+                                    float v2[8];
+                                    tc::tmem_ld8(src_t + src_lo + (uint32_t)f0, v2);
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) v[i] += v2[i];
+                                }
                             }
                             float r[8];
 #pragma unroll
@@ -658,7 +690,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                     }
                     tc::tmem_st_wait();
                     tc::tc_fence_before_sync();
-                    tc::mbar_arrive(&a_full[s]);
+                    tc::mbar_arrive(&full[s]);
+                    if (lane == 0 && (warp & 3) == 0) TR(wg, cq + q, 4);
                     if (++s == p.ns) { s = 0; par ^= 1u; }
                 }
                 cq += (uint32_t)n_chunks;
@@ -671,13 +704,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
             // ---- epilogue of the last layer: TMEM -> registers -> post-affine -> y -------------------------------
             {
                 const LayerT2& L = p.layers[p.n_layers - 1];
+                if (lane == 0 && (warp & 3) == 0) TR(4 + wg, lc, 2);
                 tc::mbar_wait(acc_full, (lc - 1) & 1);
+                if (lane == 0 && (warp & 3) == 0) TR(4 + wg, lc, 3);
                 tc::tc_fence_after_sync();
                 const uint32_t taddr = tmem_base + lane_base + (((lc - 1) & 1) ? 128u : 0u);
                 float* yrow = p.y + (row0 + row) * p.ldy;
                 for (int jb = wg; jb < L.N_pad / 8; jb += 2) {
                     float v[8];
                     tc::tmem_ld8(taddr + (uint32_t)(8 * jb), v);
+                    if (L.stack) {
+                        float v2[8];
+                        tc::tmem_ld8(taddr + (uint32_t)(L.N_pad + 8 * jb), v2);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] += v2[i];
+                    }
                     if (row < nrows) {
                         if (p.has_post) {
 #pragma unroll
@@ -695,6 +736,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                     }
                 }
                 tc::tc_fence_before_sync();
+                if (lane == 0 && (warp & 3) == 0) TR(4 + wg, lc, 4);
             }
         }
     } else if (warp < NPW + NGW) {
@@ -712,7 +754,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
             const long long row0 = (long long)tile * BM;
             for (int ub = 0; ub < p.units_per_tile; ++ub, ++uc) {
                 const int u = (int)(uc % (uint32_t)p.n_units);
+                if (lane == 0 && gw == 0) TR(6, uc, 0);
                 tc::mbar_wait(&xs_empty[u], ((uc / (uint32_t)p.n_units) & 1u) ^ 1u);
+                if (lane == 0 && gw == 0) TR(6, uc, 1);
                 float* xsu = xs + (size_t)u * p.unit_floats;
                 const int c0 = ub * p.uw, ucols = min(p.uw, F_pad - c0);
                 if (vec) {
@@ -726,38 +770,58 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                 }
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&xs_full[u]);
+                if (lane == 0 && gw == 0) TR(6, uc, 2);
             }
         }
     } else if (warp == WARP_MMA) {
         // ========================================= MMA ISSUER ==================================================
-        if (lane == 0) {
-            uint32_t cq = 0, lc = 0;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-                for (int l = 0; l < p.n_layers; ++l, ++lc) {
-                    const LayerT2& L = p.layers[l];
-                    const uint32_t idesc = tc::idesc_bf16_f32(BM, L.N_pad);
-                    const uint32_t d_tmem = tmem_base + ((lc & 1) ? 128u : 0u);
-                    const uint32_t lbo_b = (uint32_t)L.N_pad * 16u;
-                    for (int q = 0; q < L.n_chunks; ++q, ++cq) {
-                        const int s = (int)(cq % (uint32_t)p.ns);
-                        const uint32_t par = (cq / (uint32_t)p.ns) & 1u;
-                        const ChunkInfo c = chunk_info(L, q);
-                        tc::mbar_wait(&a_full[s], par);
-                        tc::mbar_wait(&b_full[s], par);
-                        tc::tc_fence_after_sync();
+        // The whole warp walks the loops (uniform control flow, descriptor arithmetic on the uniform datapath); one elected
+        // lane issues.  Per K = 16 step: stacked layers (N_pad <= 64) issue A_hi.[W_hi | W_lo] (N = 2 N_pad) + A_lo.W_hi,
+        // wider layers the three products separately.
+        uint32_t cq = 0, lc = 0;
+        int s = 0;
+        uint32_t par = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            for (int l = 0; l < p.n_layers; ++l, ++lc) {
+                const LayerT2& L = p.layers[l];
+                const int n_chunks = L.n_chunks, stack = L.stack;
+                const uint32_t idesc_n = tc::idesc_bf16_f32(BM, L.N_pad);
+                const uint32_t idesc_2n = tc::idesc_bf16_f32(BM, 2 * L.N_pad);
+                const uint32_t d_tmem = tmem_base + ((lc & 1) ? 128u : 0u);
+                const uint32_t lbo_b = (uint32_t)L.N_pad * 32u;          // k-core slab = hi rows + lo rows
+                const uint32_t lo_off = (uint32_t)L.N_pad;               // (N_pad * 16 bytes) >> 4: hi -> lo rows of a slab
+                const uint32_t kk_step = (2u * lbo_b) >> 4;              // two slabs per MMA
+                for (int q = 0; q < n_chunks; ++q, ++cq) {
+                    const ChunkInfo c = chunk_info(L, q);
+                    if (lane == 0) TR(2, cq, 0);
+                    tc::mbar_wait(&full[s], par);
+                    if (lane == 0) TR(2, cq, 2);
+                    tc::tc_fence_after_sync();
+                    if (tc::elect_one()) {
                         const uint32_t a_hi = tmem_base + TMEM_A0 + 64u * s, a_lo = a_hi + 32u;
-                        const uint32_t b_hi = tc::smem_u32(bst + (size_t)s * p.bstage_bytes);
-                        const uint32_t b_lo = b_hi + (uint32_t)c.nk * lbo_b;
-                        for (int kk = 0; kk < c.nk / 2; ++kk) {
-                            const uint64_t dbh = tc::smem_desc(b_hi + kk * 2 * lbo_b, lbo_b, 128);
-                            const uint64_t dbl = tc::smem_desc(b_lo + kk * 2 * lbo_b, lbo_b, 128);
-                            tc::umma_bf16_ts(d_tmem, a_hi + 8u * kk, dbh, idesc, (q | kk) != 0 ? 1u : 0u);
-                            tc::umma_bf16_ts(d_tmem, a_hi + 8u * kk, dbl, idesc, 1u);
-                            tc::umma_bf16_ts(d_tmem, a_lo + 8u * kk, dbh, idesc, 1u);
+                        const uint64_t d0 = tc::smem_desc(tc::smem_u32(bst + (size_t)s * p.bstage_bytes), lbo_b, 128);
+                        const int nkk = c.nk >> 1;
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            if (kk < nkk) {
+                                const uint64_t dbh = d0 + (uint64_t)(kk * kk_step);
+                                const uint32_t acc = (q | kk) != 0 ? 1u : 0u;
+                                if (stack) {
+                                    tc::umma_bf16_ts(d_tmem, a_hi + 8u * kk, dbh, idesc_2n, acc);
+                                    tc::umma_bf16_ts(d_tmem, a_lo + 8u * kk, dbh, idesc_n, 1u);
+                                } else {
+                                    tc::umma_bf16_ts(d_tmem, a_hi + 8u * kk, dbh, idesc_n, acc);
+                                    tc::umma_bf16_ts(d_tmem, a_hi + 8u * kk, dbh + lo_off, idesc_n, 1u);
+                                    tc::umma_bf16_ts(d_tmem, a_lo + 8u * kk, dbh, idesc_n, 1u);
+                                }
+                            }
                         }
                         tc::umma_commit(&empty[s]);
+                        if (q == n_chunks - 1) tc::umma_commit(acc_full);
                     }
-                    tc::umma_commit(acc_full);
+                    __syncwarp();
+                    if (lane == 0) TR(2, cq, 3);
+                    if (++s == p.ns) { s = 0; par ^= 1u; }
                 }
             }
         }
@@ -771,9 +835,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                     for (int q = 0; q < L.n_chunks; ++q, ++cq) {
                         const int s = (int)(cq % (uint32_t)p.ns);
                         const ChunkInfo c = chunk_info(L, q);
+                        TR(3, cq, 0);
                         tc::mbar_wait(&empty[s], ((cq / (uint32_t)p.ns) & 1u) ^ 1u);
-                        tc::mbar_arrive_expect_tx(&b_full[s], c.b_bytes);
-                        tc::bulk_g2s(bst + (size_t)s * p.bstage_bytes, L.wtc + c.b_off, c.b_bytes, &b_full[s]);
+                        TR(3, cq, 1);
+                        tc::mbar_arrive_expect_tx(&full[s], c.b_bytes);
+                        tc::bulk_g2s(bst + (size_t)s * p.bstage_bytes, L.wtc + c.b_off, c.b_bytes, &full[s]);
                     }
                 }
             }
@@ -826,6 +892,7 @@ int kagnn_fused_fwd_tc2(const KagnnAggregate* agg, int64_t num_rows, const Kagnn
         d.N = s.out_features;
         d.N_pad = ceil16(s.out_features);
         d.n_chunks = d.F_pad / 8 + (d.F_pad + 63) / 64;
+        d.stack = d.N_pad <= 64 ? 1 : 0;
         d.inv_h = 1.0f / s.h;
         d.c0 = -s.t0 * d.inv_h;
         d.lim = (float)(s.grid_size + 2 * k);
@@ -843,7 +910,7 @@ int kagnn_fused_fwd_tc2(const KagnnAggregate* agg, int64_t num_rows, const Kagnn
     p.unit_floats = BM * p.xld;
     p.units_per_tile = (F_pad0 + p.uw - 1) / p.uw;
     p.bstage_bytes = 256 * n_max;
-    const int tail = KAGNN_MAX_LAYERS * LUT_ROWS * 16 + (2 * MAX_UNITS + 3 * MAX_STAGE + 2) * 8;
+    const int tail = KAGNN_MAX_LAYERS * LUT_ROWS * 16 + (2 * MAX_UNITS + 2 * MAX_STAGE + 2) * 8;
     const int unit_bytes = p.unit_floats * (int)sizeof(float);
     // ring depths: at least 2 x-units and 2 stages; prefer deeper stages, then more units
     int best_units = 0, best_ns = 0;
