@@ -43,10 +43,15 @@ extern "C" int kagnn_debug_set_trace(unsigned long long* buf) {
 namespace {
 
 constexpr int BM = 128;
-constexpr int NPW = 8;                       // producer warps (two warpgroups)
+#ifndef KAGNN_TC2_NPW
+#define KAGNN_TC2_NPW 16
+#endif
+constexpr int NPW = KAGNN_TC2_NPW;           // producer warps: 2 or 4 warpgroups, each expands 8 / NWG features of every chunk
+constexpr int NWG = NPW / 4;
+constexpr int FPW = 8 / NWG;                 // features per warpgroup per spline chunk
 constexpr int NGW = 8;                       // gather warps
 constexpr int NPROD = NPW * 32;
-constexpr int NTHREADS = (NPW + NGW + 2) * 32;
+constexpr int NTHREADS = (NPW + NGW + 4) * 32;   // + MMA, W loader and two idle warps (whole warpgroups for setmaxnreg)
 constexpr int WARP_MMA = NPW + NGW;
 constexpr int WARP_LOAD = NPW + NGW + 1;
 constexpr int RPW = BM / NGW;                // rows per gather warp
@@ -585,9 +590,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < NPW) {
+        if (NPW == 16) tc::reg_dec<64>();
         // ============================== BASIS PRODUCERS / EPILOGUE =============================================
-        // Both warpgroups work on EVERY chunk: warpgroup wg expands features 4wg..4wg+3 of a spline chunk (octets of parity
-        // wg of a SiLU chunk), so the two halves of a chunk are produced concurrently and the groups stay balanced.
+        // Every warpgroup works on EVERY chunk: warpgroup wg expands FPW features of a spline chunk (every NWG-th octet of a
+        // SiLU chunk), so the parts of a chunk are produced concurrently and the groups stay balanced.
         const int wg = warp >> 2;
         const int row = tid & 127;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
@@ -604,9 +610,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                 int cur_unit = -1;
                 const float* xrow = nullptr;
                 if (l > 0) {
-                    if (lane == 0 && (warp & 3) == 0) TR(4 + wg, lc, 0);
+                    if (lane == 0 && (warp & 3) == 0 && wg < 2) TR(4 + wg, lc, 0);
                     tc::mbar_wait(acc_full, (lc - 1) & 1);
-                    if (lane == 0 && (warp & 3) == 0) TR(4 + wg, lc, 1);
+                    if (lane == 0 && (warp & 3) == 0 && wg < 2) TR(4 + wg, lc, 1);
                     tc::tc_fence_after_sync();
                     src_t = tmem_base + lane_base + (((lc - 1) & 1) ? 128u : 0u);
                     src_lo = p.layers[l - 1].stack ? (uint32_t)p.layers[l - 1].N_pad : 0u;
@@ -624,43 +630,51 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                             }
                             cur_unit = ul;
                             const uint32_t un = uc0 + ul;
-                            if (lane == 0 && (warp & 3) == 0) TR(wg, cq + q, 0);
+                            if (lane == 0 && (warp & 3) == 0 && wg < 2) TR(wg, cq + q, 0);
                             tc::mbar_wait(&xs_full[un % p.n_units], (un / p.n_units) & 1);
-                            if (lane == 0 && (warp & 3) == 0) TR(wg, cq + q, 1);
+                            if (lane == 0 && (warp & 3) == 0 && wg < 2) TR(wg, cq + q, 1);
                             xrow = xs + (size_t)(un % p.n_units) * p.unit_floats + (size_t)row * p.xld - (size_t)ul * p.uw;
                         }
                     }
-                    if (lane == 0 && (warp & 3) == 0) TR(wg, cq + q, 2);
+                    if (lane == 0 && (warp & 3) == 0 && wg < 2) TR(wg, cq + q, 2);
                     tc::mbar_wait(&empty[s], par);
-                    if (lane == 0 && (warp & 3) == 0) TR(wg, cq + q, 3);
+                    if (lane == 0 && (warp & 3) == 0 && wg < 2) TR(wg, cq + q, 3);
                     tc::tc_fence_after_sync();
                     const uint32_t a_t = tmem_base + lane_base + TMEM_A0 + 64u * s;
                     if (!c.base) {
-                        const int f0 = 64 * c.group + 8 * c.j + 4 * wg;
-                        float v[4];
+                        const int f0 = 64 * c.group + 8 * c.j + FPW * wg;
+                        float v[FPW];
                         if (l == 0) {
-                            const float4 t = *reinterpret_cast<const float4*>(xrow + f0);
-                            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+                            if (FPW == 4) {
+                                const float4 t = *reinterpret_cast<const float4*>(xrow + f0);
+                                v[0] = t.x; v[1] = t.y; v[FPW - 2] = t.z; v[FPW - 1] = t.w;
+                            } else {
+                                const float2 t = *reinterpret_cast<const float2*>(xrow + f0);
+                                v[0] = t.x; v[1] = t.y;
+                            }
                         } else {
-                            tc::tmem_ld4(src_t + (uint32_t)f0, v);
+                            tc::tmem_ldn<FPW>(src_t + (uint32_t)f0, v);
                             if (src_lo) {
-                                float v2[4];
-                                tc::tmem_ld4(src_t + src_lo + (uint32_t)f0, v2);
-                                v[0] += v2[0]; v[1] += v2[1]; v[2] += v2[2]; v[3] += v2[3];
+                                float v2[FPW];
+                                tc::tmem_ldn<FPW>(src_t + src_lo + (uint32_t)f0, v2);
+#pragma unroll
+                                for (int i = 0; i < FPW; ++i) v[i] += v2[i];
                             }
                         }
-                        uint32_t hi[8], lo[8], hi2[8], lo2[8];
-                        bspline_slots<K>(inv_h, c0f, limp, lutL, v[0], hi, lo);
-                        bspline_slots<K>(inv_h, c0f, limp, lutL, v[1], hi + 4, lo + 4);
-                        bspline_slots<K>(inv_h, c0f, limp, lutL, v[2], hi2, lo2);
-                        bspline_slots<K>(inv_h, c0f, limp, lutL, v[3], hi2 + 4, lo2 + 4);
-                        tc::tmem_st8(a_t + 16u * wg, hi);
-                        tc::tmem_st8(a_t + 32u + 16u * wg, lo);
-                        tc::tmem_st8(a_t + 16u * wg + 8u, hi2);
-                        tc::tmem_st8(a_t + 32u + 16u * wg + 8u, lo2);
+                        uint32_t hi[FPW / 2][8], lo[FPW / 2][8];
+#pragma unroll
+                        for (int i = 0; i < FPW; i += 2) {
+                            bspline_slots<K>(inv_h, c0f, limp, lutL, v[i], hi[i / 2], lo[i / 2]);
+                            bspline_slots<K>(inv_h, c0f, limp, lutL, v[i + 1], hi[i / 2] + 4, lo[i / 2] + 4);
+                        }
+#pragma unroll
+                        for (int i = 0; i < FPW; i += 2) {
+                            tc::tmem_st8(a_t + 4u * (uint32_t)(FPW * wg + i), hi[i / 2]);
+                            tc::tmem_st8(a_t + 32u + 4u * (uint32_t)(FPW * wg + i), lo[i / 2]);
+                        }
                     } else {
 #pragma unroll 1
-                        for (int jj = wg; jj < c.n_oct; jj += 2) {
+                        for (int jj = wg; jj < c.n_oct; jj += NWG) {
                             const int f0 = 64 * c.group + 8 * jj;
                             float v[8];
                             if (l == 0) {
@@ -691,7 +705,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                     tc::tmem_st_wait();
                     tc::tc_fence_before_sync();
                     tc::mbar_arrive(&full[s]);
-                    if (lane == 0 && (warp & 3) == 0) TR(wg, cq + q, 4);
+                    if (lane == 0 && (warp & 3) == 0 && wg < 2) TR(wg, cq + q, 4);
                     if (++s == p.ns) { s = 0; par ^= 1u; }
                 }
                 cq += (uint32_t)n_chunks;
@@ -704,13 +718,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
             // ---- epilogue of the last layer: TMEM -> registers -> post-affine -> y -------------------------------
             {
                 const LayerT2& L = p.layers[p.n_layers - 1];
-                if (lane == 0 && (warp & 3) == 0) TR(4 + wg, lc, 2);
+                if (lane == 0 && (warp & 3) == 0 && wg < 2) TR(4 + wg, lc, 2);
                 tc::mbar_wait(acc_full, (lc - 1) & 1);
-                if (lane == 0 && (warp & 3) == 0) TR(4 + wg, lc, 3);
+                if (lane == 0 && (warp & 3) == 0 && wg < 2) TR(4 + wg, lc, 3);
                 tc::tc_fence_after_sync();
                 const uint32_t taddr = tmem_base + lane_base + (((lc - 1) & 1) ? 128u : 0u);
                 float* yrow = p.y + (row0 + row) * p.ldy;
-                for (int jb = wg; jb < L.N_pad / 8; jb += 2) {
+                for (int jb = wg; jb < L.N_pad / 8; jb += NWG) {
                     float v[8];
                     tc::tmem_ld8(taddr + (uint32_t)(8 * jb), v);
                     if (L.stack) {
@@ -736,11 +750,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                     }
                 }
                 tc::tc_fence_before_sync();
-                if (lane == 0 && (warp & 3) == 0) TR(4 + wg, lc, 4);
+                if (lane == 0 && (warp & 3) == 0 && wg < 2) TR(4 + wg, lc, 4);
             }
         }
     } else if (warp < NPW + NGW) {
         // ========================================= GATHER ======================================================
+        if (NPW == 16) tc::reg_inc<104>();
         const int gw = warp - NPW;
         const bool vec = (p.agg.num_cols % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.agg.x) & 15u) == 0) && (p.agg.ldx % 4 == 0) &&
                          (!p.agg.x_halo || (((reinterpret_cast<uintptr_t>(p.agg.x_halo) & 15u) == 0) && (p.agg.ld_halo % 4 == 0))) &&
@@ -774,6 +789,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
             }
         }
     } else if (warp == WARP_MMA) {
+        if (NPW == 16) tc::reg_dec<40>();
         // ========================================= MMA ISSUER ==================================================
         // The whole warp walks the loops (uniform control flow, descriptor arithmetic on the uniform datapath); one elected
         // lane issues.  Per K = 16 step: stacked layers (N_pad <= 64) issue A_hi.[W_hi | W_lo] (N = 2 N_pad) + A_lo.W_hi,
@@ -826,8 +842,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
             }
         }
     } else {
-        // ========================================== W LOADER ===================================================
-        if (lane == 0) {
+        // ========================================== W LOADER (+ two idle warps) ================================
+        if (NPW == 16) tc::reg_dec<40>();
+        if (warp == WARP_LOAD && lane == 0) {
             uint32_t cq = 0;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
                 for (int l = 0; l < p.n_layers; ++l) {

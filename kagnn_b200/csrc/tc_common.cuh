@@ -31,6 +31,12 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// register rebalancing between warp roles (whole warpgroups): data-movement / issue warps give registers to the gather warps
+template <int N>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+
 // ---- mbarrier ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -120,6 +126,19 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, float (&v)[2]) {
+    uint32_t r[2];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    v[0] = __uint_as_float(r[0]);
+    v[1] = __uint_as_float(r[1]);
+}
+template <int N>
+__device__ __forceinline__ void tmem_ldn(uint32_t taddr, float (&v)[N]);
+template <>
+__device__ __forceinline__ void tmem_ldn<2>(uint32_t taddr, float (&v)[2]) { tmem_ld2(taddr, v); }
+template <>
+__device__ __forceinline__ void tmem_ldn<4>(uint32_t taddr, float (&v)[4]) { tmem_ld4(taddr, v); }
 __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
