@@ -36,13 +36,23 @@ __device__ unsigned long long* g_trace = nullptr;
 extern "C" int kagnn_debug_set_trace(unsigned long long* buf) {
     return cudaMemcpyToSymbol(g_trace, &buf, sizeof(buf)) == cudaSuccess ? 0 : -5;
 }
+#define TRL(role, k, evt) TR(role, k, evt)            // tile-level events (cheap: a few per tile)
+#if KAGNN_TRACE >= 2
+#define TRC(role, k, evt) TR(role, k, evt)            // per-chunk events (each costs ~100 cycles: perturbs the producers)
 #else
-#define TR(role, k, evt) do { } while (0)
+#define TRC(role, k, evt) do { } while (0)
+#endif
+#else
+#define TRL(role, k, evt) do { } while (0)
+#define TRC(role, k, evt) do { } while (0)
 #endif
 
 namespace {
 
 constexpr int BM = 128;
+#ifndef KAGNN_TC2_GATHER_U
+#define KAGNN_TC2_GATHER_U 16           // 128-bit row loads in flight per gather warp
+#endif
 #ifndef KAGNN_TC2_NPW
 #define KAGNN_TC2_NPW 16
 #endif
@@ -79,27 +89,31 @@ struct Tc2Params {
     float* y;
     long long ldy;
     int n_layers, n_tiles, y_vec;
-    int uw, xld, n_units, units_per_tile, unit_floats;   // x-tile ring geometry
+    int uw, uw_shift, xld, n_units, units_per_tile, unit_floats;   // x-tile ring geometry (uw = 1 << uw_shift = 64 or 128)
     int ns, bstage_bytes;                                 // A/B stage ring depth, bytes of one B stage
     LayerT2 layers[KAGNN_MAX_LAYERS];
 };
 
-struct ChunkInfo {
-    int group, j, n_oct, nk;
-    bool base;
-    uint32_t b_off, b_bytes;
+// Chunk order of one layer: per group of 64 input features, up to 8 spline chunks (8 features x 8 slots, K = 64) followed by
+// one SiLU chunk (the group's n_oct feature octets, K = 8 n_oct).  Every role walks the same sequence with this cursor
+// (no divisions in the per-chunk paths).
+struct ChunkCursor {
+    int group, j, n_oct, octs;
+    __device__ __forceinline__ explicit ChunkCursor(int F_pad) : group(0), j(0), n_oct(min(8, F_pad >> 3)), octs(F_pad >> 3) {}
+    __device__ __forceinline__ bool base() const { return j == n_oct; }
+    __device__ __forceinline__ int nk() const { return j == n_oct ? n_oct : 8; }
+    __device__ __forceinline__ uint32_t b_off(int N_pad) const { return (uint32_t)(group * 9 + j) * 256u * (uint32_t)N_pad; }
+    __device__ __forceinline__ uint32_t b_bytes(int N_pad) const { return 32u * (uint32_t)nk() * (uint32_t)N_pad; }
+    __device__ __forceinline__ void next() {
+        if (j == n_oct) {
+            ++group;
+            j = 0;
+            n_oct = min(8, octs - 8 * group);
+        } else {
+            ++j;
+        }
+    }
 };
-__device__ __forceinline__ ChunkInfo chunk_info(const LayerT2& L, int q) {
-    ChunkInfo c;
-    c.group = q / 9;
-    c.j = q - 9 * c.group;
-    c.n_oct = min(8, L.F_pad / 8 - 8 * c.group);
-    c.base = (c.j >= c.n_oct);
-    c.nk = c.base ? c.n_oct : 8;
-    c.b_off = (uint32_t)(c.group * 9 + c.j) * 256u * (uint32_t)L.N_pad;
-    c.b_bytes = 32u * (uint32_t)c.nk * (uint32_t)L.N_pad;
-    return c;
-}
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -387,7 +401,7 @@ __device__ float g_zero_row[4096];
 template <bool WEIGHTED>
 __device__ __forceinline__ void gather_unit_fast(const Tc2Params& p, long long row0, int c0, int ucols, float* __restrict__ xsu,
                                                  int gw, int lane) {
-    constexpr int U = 8;
+    constexpr int U = KAGNN_TC2_GATHER_U;
     const KagnnAggregate& a = p.agg;
     const int F = a.num_cols, mode = a.mode, xld = p.xld;
     const bool segment = (mode == KAGNN_AGG_SEGMENT_SUM) || (mode == KAGNN_AGG_SEGMENT_MEAN);
@@ -449,6 +463,9 @@ __device__ __forceinline__ void gather_unit_fast(const Tc2Params& p, long long r
     };
 
     Meta nxt = prep(v_beg);
+#ifdef KAGNN_TRACE
+    int trk = 0;
+#endif
 #pragma unroll 1
     for (int vbase = v_beg; vbase < v_end; vbase += 32) {
         const Meta m = nxt;
@@ -474,9 +491,15 @@ __device__ __forceinline__ void gather_unit_fast(const Tc2Params& p, long long r
         const int cnt = min(32, v_end - vbase);
 #pragma unroll 1
         for (int t0 = 0; t0 < cnt; t0 += U) {
+#ifdef KAGNN_TRACE
+            if (lane == 0 && gw == 0 && row0 >= 148 * BM && row0 < 149 * BM) { TRL(7, trk, 0); }
+#endif
             float4 v[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(shfl_ptr(my_row, t0 + u) + cload));
+#ifdef KAGNN_TRACE
+            if (lane == 0 && gw == 0 && row0 >= 148 * BM && row0 < 149 * BM) { TRL(7, trk, 1); }    // CTA 0's second tile
+#endif
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int e = vbase + t0 + u;
@@ -486,7 +509,13 @@ __device__ __forceinline__ void gather_unit_fast(const Tc2Params& p, long long r
                 acc[1] = fmaf(w, v[u].y, acc[1]);
                 acc[2] = fmaf(w, v[u].z, acc[2]);
                 acc[3] = fmaf(w, v[u].w, acc[3]);
+#ifdef KAGNN_TRACE
+                if (u == 0 && lane == 0 && gw == 0 && row0 >= 148 * BM && row0 < 149 * BM) { TRL(7, trk, 2); }
+#endif
             }
+#ifdef KAGNN_TRACE
+            if (lane == 0 && gw == 0 && row0 >= 148 * BM && row0 < 149 * BM) { TRL(7, trk, 3); ++trk; }
+#endif
         }
     }
     while (cur < RPW) finish_row();
@@ -550,6 +579,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
     uint64_t* empty = full + MAX_STAGE;
     uint64_t* acc_full = empty + MAX_STAGE;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+    float* post_sc = reinterpret_cast<float*>(tmem_slot + 2);     // post-affine of the last layer (<= 128 columns each)
+    float* post_sh = post_sc + 128;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (warp == WARP_MMA) tc::tmem_alloc(tmem_slot, 512);
@@ -564,6 +595,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
         }
         tc::mbar_init(acc_full, 1);
         tc::mbar_fence_init();
+    }
+    if (tid >= 128 && tid < 256) {
+        const int c = tid - 128;
+        const bool on = p.has_post && c < p.layers[p.n_layers - 1].N;
+        post_sc[c] = (on && p.post.scale) ? __ldg(p.post.scale + c) : 1.0f;
+        post_sh[c] = (on && p.post.shift) ? __ldg(p.post.shift + c) : 0.0f;
     }
     if (tid < p.n_layers * LUT_ROWS) {
         // per layer, row q <-> knot interval j = q - 1.  A valid interval (0 <= j < G + 2k) puts its first non-zero basis
@@ -610,19 +647,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                 int cur_unit = -1;
                 const float* xrow = nullptr;
                 if (l > 0) {
-                    if (lane == 0 && (warp & 3) == 0 && wg < 2) TR(4 + wg, lc, 0);
+                    if (lane == 0 && (warp & 3) == 0 && wg < 2) TRL(4 + wg, lc, 0);
                     tc::mbar_wait(acc_full, (lc - 1) & 1);
-                    if (lane == 0 && (warp & 3) == 0 && wg < 2) TR(4 + wg, lc, 1);
+                    if (lane == 0 && (warp & 3) == 0 && wg < 2) TRL(4 + wg, lc, 1);
                     tc::tc_fence_after_sync();
                     src_t = tmem_base + lane_base + (((lc - 1) & 1) ? 128u : 0u);
                     src_lo = p.layers[l - 1].stack ? (uint32_t)p.layers[l - 1].N_pad : 0u;
                 }
                 int s = (int)(cq % (uint32_t)p.ns);
                 uint32_t par = ((cq / (uint32_t)p.ns) & 1u) ^ 1u;
-                for (int q = 0; q < n_chunks; ++q) {
-                    const ChunkInfo c = chunk_info(L, q);
-                    if (l == 0) {
-                        const int ul = (64 * c.group) / p.uw;
+                ChunkCursor c(L.F_pad);
+                for (int q = 0; q < n_chunks; ++q, c.next()) {
+                    if (l == 0 && c.j == 0) {
+                        const int ul = (64 * c.group) >> p.uw_shift;
                         if (ul != cur_unit) {
                             if (cur_unit >= 0) {
                                 __syncwarp();
@@ -630,18 +667,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                             }
                             cur_unit = ul;
                             const uint32_t un = uc0 + ul;
-                            if (lane == 0 && (warp & 3) == 0 && wg < 2) TR(wg, cq + q, 0);
-                            tc::mbar_wait(&xs_full[un % p.n_units], (un / p.n_units) & 1);
-                            if (lane == 0 && (warp & 3) == 0 && wg < 2) TR(wg, cq + q, 1);
+                            if (lane == 0 && (warp & 3) == 0 && wg < 2) TRL(wg, cq + q, 0);
+                            tc::mbar_wait_relaxed(&xs_full[un % p.n_units], (un / p.n_units) & 1);
+                            if (lane == 0 && (warp & 3) == 0 && wg < 2) TRL(wg, cq + q, 1);
                             xrow = xs + (size_t)(un % p.n_units) * p.unit_floats + (size_t)row * p.xld - (size_t)ul * p.uw;
                         }
                     }
-                    if (lane == 0 && (warp & 3) == 0 && wg < 2) TR(wg, cq + q, 2);
-                    tc::mbar_wait(&empty[s], par);
-                    if (lane == 0 && (warp & 3) == 0 && wg < 2) TR(wg, cq + q, 3);
+                    if (lane == 0 && (warp & 3) == 0 && wg < 2) TRC(wg, cq + q, 2);
+                    tc::mbar_wait_relaxed(&empty[s], par);
+                    if (lane == 0 && (warp & 3) == 0 && wg < 2) TRC(wg, cq + q, 3);
                     tc::tc_fence_after_sync();
                     const uint32_t a_t = tmem_base + lane_base + TMEM_A0 + 64u * s;
-                    if (!c.base) {
+                    if (!c.base()) {
                         const int f0 = 64 * c.group + 8 * c.j + FPW * wg;
                         float v[FPW];
                         if (l == 0) {
@@ -667,6 +704,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                             bspline_slots<K>(inv_h, c0f, limp, lutL, v[i], hi[i / 2], lo[i / 2]);
                             bspline_slots<K>(inv_h, c0f, limp, lutL, v[i + 1], hi[i / 2] + 4, lo[i / 2] + 4);
                         }
+                        if (lane == 0 && (warp & 3) == 0 && wg < 2) TRC(wg, cq + q, 5);
 #pragma unroll
                         for (int i = 0; i < FPW; i += 2) {
                             tc::tmem_st8(a_t + 4u * (uint32_t)(FPW * wg + i), hi[i / 2]);
@@ -702,10 +740,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                                          pack_rn(r[6], r[7]));
                         }
                     }
+                    if (lane == 0 && (warp & 3) == 0 && wg < 2) TRC(wg, cq + q, 6);
                     tc::tmem_st_wait();
+                    if (lane == 0 && (warp & 3) == 0 && wg < 2) TRC(wg, cq + q, 7);
                     tc::tc_fence_before_sync();
                     tc::mbar_arrive(&full[s]);
-                    if (lane == 0 && (warp & 3) == 0 && wg < 2) TR(wg, cq + q, 4);
+                    if (lane == 0 && (warp & 3) == 0 && wg < 2) TRC(wg, cq + q, 4);
                     if (++s == p.ns) { s = 0; par ^= 1u; }
                 }
                 cq += (uint32_t)n_chunks;
@@ -718,9 +758,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
             // ---- epilogue of the last layer: TMEM -> registers -> post-affine -> y -------------------------------
             {
                 const LayerT2& L = p.layers[p.n_layers - 1];
-                if (lane == 0 && (warp & 3) == 0 && wg < 2) TR(4 + wg, lc, 2);
+                if (lane == 0 && (warp & 3) == 0 && wg < 2) TRL(4 + wg, lc, 2);
                 tc::mbar_wait(acc_full, (lc - 1) & 1);
-                if (lane == 0 && (warp & 3) == 0 && wg < 2) TR(4 + wg, lc, 3);
+                if (lane == 0 && (warp & 3) == 0 && wg < 2) TRL(4 + wg, lc, 3);
                 tc::tc_fence_after_sync();
                 const uint32_t taddr = tmem_base + lane_base + (((lc - 1) & 1) ? 128u : 0u);
                 float* yrow = p.y + (row0 + row) * p.ldy;
@@ -735,9 +775,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                     }
                     if (row < nrows) {
                         if (p.has_post) {
+                            const float4 s0 = *reinterpret_cast<const float4*>(post_sc + 8 * jb), s1 = *reinterpret_cast<const float4*>(post_sc + 8 * jb + 4);
+                            const float4 h0 = *reinterpret_cast<const float4*>(post_sh + 8 * jb), h1 = *reinterpret_cast<const float4*>(post_sh + 8 * jb + 4);
+                            v[0] = fmaf(v[0], s0.x, h0.x); v[1] = fmaf(v[1], s0.y, h0.y); v[2] = fmaf(v[2], s0.z, h0.z); v[3] = fmaf(v[3], s0.w, h0.w);
+                            v[4] = fmaf(v[4], s1.x, h1.x); v[5] = fmaf(v[5], s1.y, h1.y); v[6] = fmaf(v[6], s1.z, h1.z); v[7] = fmaf(v[7], s1.w, h1.w);
+                            if (p.post.act == KAGNN_ACT_SILU) {
 #pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                if (8 * jb + i < L.N) v[i] = apply_affine(p.post, 8 * jb + i, v[i]);
+                                for (int i = 0; i < 8; ++i) v[i] = silu_f(v[i]);
+                            }
                         }
                         if (p.y_vec && 8 * jb + 8 <= L.N) {
                             *reinterpret_cast<float4*>(yrow + 8 * jb) = make_float4(v[0], v[1], v[2], v[3]);
@@ -750,7 +795,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                     }
                 }
                 tc::tc_fence_before_sync();
-                if (lane == 0 && (warp & 3) == 0 && wg < 2) TR(4 + wg, lc, 4);
+                if (lane == 0 && (warp & 3) == 0 && wg < 2) TRL(4 + wg, lc, 4);
             }
         }
     } else if (warp < NPW + NGW) {
@@ -769,9 +814,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
             const long long row0 = (long long)tile * BM;
             for (int ub = 0; ub < p.units_per_tile; ++ub, ++uc) {
                 const int u = (int)(uc % (uint32_t)p.n_units);
-                if (lane == 0 && gw == 0) TR(6, uc, 0);
-                tc::mbar_wait(&xs_empty[u], ((uc / (uint32_t)p.n_units) & 1u) ^ 1u);
-                if (lane == 0 && gw == 0) TR(6, uc, 1);
+                if (lane == 0 && gw == 0) TRL(6, uc, 0);
+                tc::mbar_wait_relaxed(&xs_empty[u], ((uc / (uint32_t)p.n_units) & 1u) ^ 1u);
+                if (lane == 0 && gw == 0) TRL(6, uc, 1);
                 float* xsu = xs + (size_t)u * p.unit_floats;
                 const int c0 = ub * p.uw, ucols = min(p.uw, F_pad - c0);
                 if (vec) {
@@ -785,7 +830,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                 }
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&xs_full[u]);
-                if (lane == 0 && gw == 0) TR(6, uc, 2);
+                if (lane == 0 && gw == 0) TRL(6, uc, 2);
             }
         }
     } else if (warp == WARP_MMA) {
@@ -807,16 +852,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                 const uint32_t lbo_b = (uint32_t)L.N_pad * 32u;          // k-core slab = hi rows + lo rows
                 const uint32_t lo_off = (uint32_t)L.N_pad;               // (N_pad * 16 bytes) >> 4: hi -> lo rows of a slab
                 const uint32_t kk_step = (2u * lbo_b) >> 4;              // two slabs per MMA
-                for (int q = 0; q < n_chunks; ++q, ++cq) {
-                    const ChunkInfo c = chunk_info(L, q);
-                    if (lane == 0) TR(2, cq, 0);
+                ChunkCursor c(L.F_pad);
+                for (int q = 0; q < n_chunks; ++q, ++cq, c.next()) {
+                    if (lane == 0) TRC(2, cq, 0);
                     tc::mbar_wait(&full[s], par);
-                    if (lane == 0) TR(2, cq, 2);
+                    if (lane == 0) TRC(2, cq, 2);
                     tc::tc_fence_after_sync();
                     if (tc::elect_one()) {
                         const uint32_t a_hi = tmem_base + TMEM_A0 + 64u * s, a_lo = a_hi + 32u;
                         const uint64_t d0 = tc::smem_desc(tc::smem_u32(bst + (size_t)s * p.bstage_bytes), lbo_b, 128);
-                        const int nkk = c.nk >> 1;
+                        const int nkk = c.nk() >> 1;
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk) {
                             if (kk < nkk) {
@@ -836,7 +881,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                         if (q == n_chunks - 1) tc::umma_commit(acc_full);
                     }
                     __syncwarp();
-                    if (lane == 0) TR(2, cq, 3);
+                    if (lane == 0) TRC(2, cq, 3);
                     if (++s == p.ns) { s = 0; par ^= 1u; }
                 }
             }
@@ -845,18 +890,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
         // ========================================== W LOADER (+ two idle warps) ================================
         if (NPW == 16) tc::reg_dec<40>();
         if (warp == WARP_LOAD && lane == 0) {
-            uint32_t cq = 0;
+            uint32_t cq = 0, par = 1;
+            int s = 0;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
                 for (int l = 0; l < p.n_layers; ++l) {
                     const LayerT2& L = p.layers[l];
-                    for (int q = 0; q < L.n_chunks; ++q, ++cq) {
-                        const int s = (int)(cq % (uint32_t)p.ns);
-                        const ChunkInfo c = chunk_info(L, q);
-                        TR(3, cq, 0);
-                        tc::mbar_wait(&empty[s], ((cq / (uint32_t)p.ns) & 1u) ^ 1u);
-                        TR(3, cq, 1);
-                        tc::mbar_arrive_expect_tx(&full[s], c.b_bytes);
-                        tc::bulk_g2s(bst + (size_t)s * p.bstage_bytes, L.wtc + c.b_off, c.b_bytes, &full[s]);
+                    ChunkCursor c(L.F_pad);
+                    for (int q = 0; q < L.n_chunks; ++q, ++cq, c.next()) {
+                        TRC(3, cq, 0);
+                        tc::mbar_wait_relaxed(&empty[s], par);
+                        TRC(3, cq, 1);
+#ifdef KAGNN_EXP_HALFW   // timing experiment only (wrong results): how much of the time is W streaming from L2?
+                        const uint32_t bytes = c.b_bytes(L.N_pad) / KAGNN_EXP_HALFW;
+#else
+                        const uint32_t bytes = c.b_bytes(L.N_pad);
+#endif
+                        tc::mbar_arrive_expect_tx(&full[s], bytes);
+                        tc::bulk_g2s(bst + (size_t)s * p.bstage_bytes, L.wtc + c.b_off(L.N_pad), bytes, &full[s]);
+                        if (++s == p.ns) { s = 0; par ^= 1u; }
                     }
                 }
             }
@@ -923,11 +974,12 @@ int kagnn_fused_fwd_tc2(const KagnnAggregate* agg, int64_t num_rows, const Kagnn
 
     const int F_pad0 = p.layers[0].F_pad;
     p.uw = F_pad0 > 64 ? 128 : 64;
+    p.uw_shift = F_pad0 > 64 ? 7 : 6;
     p.xld = p.uw + 4;                                   // (xld / 4) odd: conflict-free float4 reads with thread = row
     p.unit_floats = BM * p.xld;
     p.units_per_tile = (F_pad0 + p.uw - 1) / p.uw;
     p.bstage_bytes = 256 * n_max;
-    const int tail = KAGNN_MAX_LAYERS * LUT_ROWS * 16 + (2 * MAX_UNITS + 2 * MAX_STAGE + 2) * 8;
+    const int tail = KAGNN_MAX_LAYERS * LUT_ROWS * 16 + (2 * MAX_UNITS + 2 * MAX_STAGE + 2) * 8 + 2 * 128 * 4;
     const int unit_bytes = p.unit_floats * (int)sizeof(float);
     // ring depths: at least 2 x-units and 2 stages; prefer deeper stages, then more units
     int best_units = 0, best_ns = 0;

@@ -81,6 +81,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// Wait of a warp that is not on the critical path (it is ahead of whoever it waits for): back off with nanosleep between
+// probes so that the probe loop does not take issue slots from the warps that are working.
+#ifndef KAGNN_MBAR_SLEEP_NS
+#define KAGNN_MBAR_SLEEP_NS 96
+#endif
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    uint32_t tries = 0;
+    do {
+        __nanosleep(KAGNN_MBAR_SLEEP_NS);
+        if (++tries > (1u << 24)) __trap();
+    } while (!mbar_try_wait(bar, parity));
+}
+
 // ---- proxies / fences ---------------------------------------------------------------------------------
 // generic-proxy st.shared -> visible to the async proxy (UMMA operand fetch, bulk copies)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

@@ -60,8 +60,9 @@ for tile in range(min(ntiles, 3)):
         k = base + q
         def d(r, a, b):
             return int(rel[r, k, b] - rel[r, k, a]) if rel[r, k, a] >= 0 and rel[r, k, b] >= 0 else 0
-        print(f" {q:5d} | {d(0,0,1):8d} {d(0,2,3):8d} {d(0,3,4):8d} | {d(1,0,1):8d} {d(1,2,3):8d} {d(1,3,4):8d} |"
-              f" {d(2,0,2):8d} {0:6d} {d(2,2,3):6d} | {d(3,0,1):8d} | {int(rel[2,k,3])}")
+        print(f" {q:5d} | [cmp {d(0,3,5)} st {d(0,5,6)} stwait {d(0,6,7)} arr {d(0,7,4)}] {d(0,0,1):8d} {d(0,2,3):8d} {d(0,3,4):8d} | {d(1,0,1):8d} {d(1,2,3):8d} {d(1,3,4):8d} |"
+              f" {d(2,0,2):8d} {0:6d} {d(2,2,3):6d} | {d(3,0,1):8d} | {int(rel[2,k,3])}"
+              f" | A-ready {int(rel[0,k,4])} W-issued {int(rel[3,k,1])} MMA-go {int(rel[2,k,2])}  (go-A {int(rel[2,k,2]-rel[0,k,4])}, go-Wissue {int(rel[2,k,2]-rel[3,k,1])})")
     for l in range(len(nch)):
         lc = tile * len(nch) + l
         for r in (4, 5):
@@ -84,3 +85,23 @@ M = rel[2]
 valid = M[:, 3] >= 0
 print("MMA totals: wait", int((M[valid, 2] - M[valid, 0]).sum()), "issue",
       int((M[valid, 3] - M[valid, 2]).sum()))
+# tile-level view (valid in the light trace build, KAGNN_TRACE=1)
+print("--- tile-level (wg0 warp 0): t_start_wait_x, x_wait, [acc waits per later layer], epi_acc_wait, epi_body, t_end | gather unit: wait, work")
+nl = len(nch)
+prev_end = 0
+upt = 3 if which == "layout" else 1
+for tile in range(int((rel[4, :, 4] >= 0).sum())):
+    k0 = tile * per_tile
+    xs0, xs1 = int(rel[0, k0, 0]), int(rel[0, k0, 1])
+    accw = [int(rel[4, tile * nl + l, 1] - rel[4, tile * nl + l, 0]) for l in range(1, nl)]
+    e = rel[4, tile * nl + nl]
+    g = rel[6, tile * upt]
+    print(f" tile {tile}: start {xs0} (+{xs0 - prev_end} after prev end) x_wait {xs1 - xs0} acc_waits {accw} epi_wait {int(e[3]-e[2])} epi_body {int(e[4]-e[3])} end {int(e[4])}"
+          f" | gather wait {int(g[1]-g[0])} work {int(g[2]-g[1])} done_at {int(g[2])}")
+    prev_end = int(e[4])
+print("--- gather warp 0, second tile of CTA 0, per sub-batch of U loads: t_start, addresses+loads issued (+), first data used (+), consumed (+)")
+for b in range(12):
+    r = rel[7, b]
+    if r[0] < 0:
+        break
+    print(f"   sub-batch {b}: start {int(r[0])} issued +{int(r[1]-r[0])} first-data +{int(r[2]-r[1])} consumed +{int(r[3]-r[2])}")
