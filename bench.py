@@ -32,6 +32,8 @@ import torch  # noqa: E402
 
 N_NODES, N_EDGES, N_FEAT, HIDDEN, N_CLASSES, MP_LAYERS, KAN_DEPTH, GRID, ORDER = 169_343, 1_166_243, 128, 64, 40, 3, 2, 5, 3
 METRIC = "KAGNN-layer forward nodes/sec"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture (profiles/README.md)
+NCU_TRAFFIC_BYTES = {"agg1[128]->64->64": 222_804_480, "agg1[64]->64->64": 65_161_216, "agg0[320]->40": 235_834_624}
 WORKLOAD = "ogbn-arxiv-shaped KAGIN (GKAN_Nodes gin, 3 layers, hidden 64, grid 5, order 3, KAN depth 2), fp32, eval"
 
 
@@ -66,44 +68,74 @@ def model_state(seed=12345):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    """SM clock / throttle reasons DURING the timed region: an NVML polling thread (2 ms period; the timed region of this
+    bench is tens of milliseconds, too short for `nvidia-smi -lms`), falling back to the nvidia-smi query of
+    B200_PROFILING.md when NVML cannot be loaded."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.lines, self.proc = [], None
+        self.samples, self.stop_flag, self.proc, self.nvml = [], False, None, None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nvml
+        names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
+        while not self.stop_flag:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                self.samples.append((time.perf_counter(), mhz, self.max, [n for n, b in names if mask & b]))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append((time.perf_counter(), ln.strip()))
-
-    def stop(self, t0=None, t1=None):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        sm, mx, reasons = [], None, set()
-        for ts, ln in self.lines:
-            if t0 is not None and not (t0 <= ts <= t1 + 0.15):
-                continue
-            parts = [p.strip() for p in ln.split(",")]
+            parts = [q.strip() for q in ln.split(",")]
             if len(parts) < 7:
                 continue
             try:
-                sm.append(float(parts[0]))
-                mx = float(parts[1])
+                mhz, mx = float(parts[0]), float(parts[1])
             except ValueError:
                 continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+            rs = [n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7])
+                  if v.lower().startswith("active")]
+            self.samples.append((time.perf_counter(), mhz, mx, rs))
+
+    def stop(self, t0=None, t1=None):
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+        if self.nvml is None and self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"], "samples": 0}
+        time.sleep(0.01)
+        sel = [q for q in self.samples if t0 is None or (t0 <= q[0] <= t1)]
+        if not sel:                                       # region shorter than one period: nearest sample
+            sel = sorted(self.samples, key=lambda q: abs(q[0] - (t0 or 0)))[:1]
+        reasons = sorted({r for q in sel for r in q[3]})
+        return {"sm_mhz": statistics.median([q[1] for q in sel]) if sel else None, "sm_max_mhz": sel[0][2] if sel else None,
+                "reasons": reasons, "samples": len(sel), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def layer_algorithmic_bytes(n, e_agg, f_in, f_out, params, self_rows=True, per_edge_scalar=False):
@@ -256,27 +288,52 @@ def main():
         kernels = [{"launch": k[0], "label": k[1], "ms": round(m_, 4)} for m_, k in kern]
 
         # ---- e2e: pinned host buffers in, logits out, through the module API ----------------------------
-        e2e = None
-        if not dist_on:
-            def e2e_step():
+        # Per step, inside the timed region: H2D of edge_index (int64 COO) and of x from pinned host memory, CSR build
+        # (kagnn_b200.graph.get_graph; it overlaps the x copy, which runs on a second stream), halo plan + exchanges when
+        # sharded, the model forward, and D2H of the logits into a pinned host buffer.
+        from kagnn_b200.graph import get_graph
+        copy_stream = torch.cuda.Stream(device=dev)
+        y_host = torch.empty(n_local, N_CLASSES, dtype=torch.float32).pin_memory()
+
+        def e2e_step():
+            cur = torch.cuda.current_stream()
+            copy_stream.wait_stream(cur)
+            with torch.cuda.stream(copy_stream):
                 xd = x_host.to(dev, non_blocking=True)
-                ed = ei_host.to(dev, non_blocking=True)
-                return model(xd, ed).to("cpu")
-            for _ in range(3):
-                flush.zero_()
-                y_host = e2e_step()
+            ed = ei_host.to(dev, non_blocking=True)
+            if dist_on:
+                ed[1] += rank * n_local
+                pl = runner.prepare(ed)                  # halo plan (index all-to-all) + shard CSR
+                cur.wait_stream(copy_stream)
+                xd.record_stream(cur)
+                y = runner.forward(xd, pl)
+            else:
+                get_graph(ed, n_local)                   # COO -> CSR on the compute stream while x is still in flight
+                cur.wait_stream(copy_stream)
+                xd.record_stream(cur)
+                y = model(xd, ed)
+            y_host.copy_(y, non_blocking=True)
+
+        for _ in range(3):
+            flush.zero_()
+            e2e_step()
+        barrier()
+        ts = []
+        for _ in range(max(5, min(args.steps, 20))):
+            flush.zero_()
+            barrier()
+            t0 = time.perf_counter()
+            e2e_step()
             torch.cuda.synchronize()
-            ts = []
-            for _ in range(max(5, min(args.steps, 20))):
-                flush.zero_()
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                y_host = e2e_step()
-                torch.cuda.synchronize()
-                ts.append(time.perf_counter() - t0)
-            e2e_s = statistics.mean(ts)
-            e2e = {"value": n_local / e2e_s, "unit": "nodes/s", "ms_per_step": 1e3 * e2e_s,
-                   "h2d_bytes_per_step": x_host.numel() * 4 + ei_host.numel() * 8, "d2h_bytes_per_step": y_host.numel() * 4}
+            ts.append(time.perf_counter() - t0)
+        e2e_s = statistics.mean(ts)
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        if dist_on:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+        e2e = {"value": n_local * world / e2e_s, "unit": "nodes/s", "ms_per_step": 1e3 * e2e_s,
+               "h2d_bytes_per_step": (x_host.numel() * 4 + ei_host.numel() * 8) * world, "d2h_bytes_per_step": y_host.numel() * 4 * world,
+               "includes": "H2D x + edge_index (pinned), CSR build" + (", halo plan" if dist_on else "") + ", forward, D2H logits (pinned)"}
 
     if rank != 0:
         if dist_on:
@@ -299,10 +356,21 @@ def main():
             width = N_FEAT + MP_LAYERS * HIDDEN
             bytes_ = 4 * width * n_local + 4 * N_CLASSES * n_local + 4 * kan_params([width, N_CLASSES], S)
         ach = bytes_ / (top["ms"] * 1e-3) / 1e9
+        # tensor work of the same launch: dense flops 2*N*sum(in*out*(1+S)), issued as 3 bf16 products (hi/lo split)
+        if li < MP_LAYERS:
+            f_in = N_FEAT if li == 0 else HIDDEN
+            dense = 2.0 * n_local * (f_in * HIDDEN + HIDDEN * HIDDEN) * (1 + S)
+        else:
+            dense = 2.0 * n_local * (N_FEAT + MP_LAYERS * HIDDEN) * N_CLASSES * (1 + S)
+        tf = 3.0 * dense / (top["ms"] * 1e-3) / 1e12
         roofline = {"bound": "hbm", "kernel": top["label"], "launch_ms": top["ms"], "algorithmic_bytes": bytes_,
                     "achieved": ach, "peak": pk["hbm_gbs"], "peak_source": pk_src, "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-                    "traffic": None,
-                    "note": "fp32 CUDA-core contraction: FMA-bound, see DESIGN.md; L2-resident feature matrix (87 MB < 126 MB L2)"}
+                    "traffic": NCU_TRAFFIC_BYTES.get(top["label"]),
+                    "tensor": {"achieved_tflops_bf16x3": tf, "peak_tflops": pk["bf16_tflops"], "frac": tf / pk["bf16_tflops"],
+                               "dense_fp32_equiv_flops": dense},
+                    "note": "no-reuse gather model (SURVEY 8d); feature matrix (87 MB) is L2-resident after first touch, so DRAM "
+                            "traffic < algorithmic bytes; contraction on tcgen05 (bf16 hi/lo x3, fp32 accumulate in TMEM); "
+                            "traffic = ncu dram bytes of the same launch (profiles/, null if that launch was not captured)"}
 
     cpu = None
     if not args.no_cpu_baseline:
