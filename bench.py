@@ -201,6 +201,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dist-mode", default="auto", choices=["auto", "peer", "halo"],
+                    help="N > 1: 'peer' = in-kernel NVLink gather from symmetric memory, 'halo' = NCCL all-to-all per layer")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -231,7 +233,7 @@ def main():
 
     if dist_on:
         from kagnn_b200 import dist as kdist
-        runner = kdist.ShardedNodeModel(model, rank, world, n_local)
+        runner = kdist.ShardedNodeModel(model, rank, world, n_local, mode=args.dist_mode)
         ei_glob = ei_host.to(dev)
         ei_glob[1] += rank * n_local                                     # targets: this rank's node range, global ids
         plan = runner.prepare(ei_glob)
@@ -385,7 +387,10 @@ def main():
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "nodes_per_gpu": n_local, "edges_per_gpu": N_EDGES, "features": N_FEAT,
                    "l2": "flushed between iterations (512 MB memset)", "csr": "cached across steps (static graph)",
-                   "parallelism": f"node-range shards x{world}, one halo all-to-all per layer" if dist_on else "single GPU"},
+                   "parallelism": (f"node-range shards x{world}, " + ("remote rows gathered in-kernel over NVLink (symmetric memory), "
+                                   "one device barrier per layer" if runner.mode == "peer" else "one NCCL halo all-to-all per layer"))
+                   if dist_on else "single GPU",
+                   "graph": "uniform random edges over all shards: (N-1)/N of the edges are cut" if dist_on else "uniform random edges"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "kernels": kernels, "roofline": roofline, "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)

@@ -103,6 +103,17 @@ typedef struct KagnnAggregate {
     const float* x_halo;
     int64_t ld_halo;
     int64_t num_local_src;
+    /* Node-sharded graphs, in-kernel NVLink gather (alternative to x_halo): `col` holds GLOBAL source ids and source row j lives
+     * on rank j / rows_per_rank at peer_x[rank] + (j % rows_per_rank) * ldx, where peer_x is a DEVICE array of num_ranks
+     * peer-mapped base pointers (same column slice and leading dimension on every rank; peer_x[my rank] == x).  The gather
+     * warps of the fused kernel load remote rows directly over NVLink while the tensor-core pipeline works on the previous
+     * tile: no pack kernel, no all-to-all, no halo matrix.  The caller orders layers across ranks (a barrier between the
+     * producer launch of a matrix and the launches that read it remotely).  peer_x == NULL: not used.
+     * Implemented by the pipelined tcgen05 kernel (128-bit path); other kernels return KAGNN_EUNSUPPORTED.                 */
+    const float* const* peer_x;
+    int64_t rows_per_rank;
+    int32_t num_ranks;
+    int32_t _pad2;
 } KagnnAggregate;
 
 /* ---- library ------------------------------------------------------------------------------------ */

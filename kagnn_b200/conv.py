@@ -118,8 +118,10 @@ class GINConv(_MessagePassing):
             self._eps_host = (key, float(self.eps.detach().cpu()))
         return self._eps_host[1]
 
-    def _agg_spec(self, x: Tensor, g: GraphCSR, x_halo: Optional[Tensor] = None) -> ops.AggSpec:
-        return ops.AggSpec(L.AGG_GIN, x, g.rowptr, g.col, self_scale=1.0 + self.eps_value(), x_halo=x_halo)
+    def _agg_spec(self, x: Tensor, g: GraphCSR, x_halo: Optional[Tensor] = None, peer_x: Optional[Tensor] = None,
+                  rows_per_rank: int = 0) -> ops.AggSpec:
+        return ops.AggSpec(L.AGG_GIN, x, g.rowptr, g.col, self_scale=1.0 + self.eps_value(), x_halo=x_halo, peer_x=peer_x,
+                           rows_per_rank=rows_per_rank)
 
     def forward(self, x: Tensor, edge_index, size=None, out: Optional[Tensor] = None,
                 post: Optional[ops.Affine] = None, **agg_kw) -> Tensor:

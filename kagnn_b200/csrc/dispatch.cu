@@ -26,6 +26,8 @@ int kagnn_validate_fused_args(const KagnnAggregate* agg, int64_t num_rows, const
     if (agg_out && ld_agg_out < agg->num_cols) return KAGNN_EINVAL;
     if (agg->x_halo && (agg->ld_halo < agg->num_cols || agg->num_local_src < 0)) return KAGNN_EINVAL;
     if (agg->x_halo && (agg->mode == KAGNN_AGG_NONE || agg->src_index)) return KAGNN_EINVAL;
+    if (agg->peer_x && (agg->x_halo || agg->src_index || agg->rows_per_rank <= 0 || agg->num_ranks <= 0)) return KAGNN_EINVAL;
+    if (agg->peer_x && agg->mode != KAGNN_AGG_GIN && agg->mode != KAGNN_AGG_WEIGHTED) return KAGNN_EINVAL;
     if (num_rows > (int64_t)INT32_MAX * 32) return KAGNN_EUNSUPPORTED;
 
     return KAGNN_OK;
@@ -74,6 +76,7 @@ extern "C" int kagnn_fused_layer_fwd(const KagnnAggregate* agg, int64_t num_rows
                 }
                 if (rc != KAGNN_EUNSUPPORTED) return rc;
             }
+            if (agg->peer_x) return KAGNN_EUNSUPPORTED;   // in-kernel peer gather exists in the pipelined kernel only
             rc = kagnn_fused_fwd_tc(agg, num_rows, pre, agg_out, ld_agg_out, n_layers, layers, post, y, ldy, stream);
             if (rc == KAGNN_OK) {
                 g_count_tc.fetch_add(1);
@@ -86,6 +89,7 @@ extern "C" int kagnn_fused_layer_fwd(const KagnnAggregate* agg, int64_t num_rows
     } else if (mode == KAGNN_PATH_TC && n_layers >= 1 && num_rows > 0) {
         return KAGNN_EUNSUPPORTED;
     }
+    if (agg->peer_x) return KAGNN_EUNSUPPORTED;
     int rc = kagnn_fused_fwd_fp32(agg, num_rows, pre, agg_out, ld_agg_out, n_layers, layers, post, y, ldy, stream);
     if (rc == KAGNN_OK && num_rows > 0) g_count_fp32.fetch_add(1);
     return rc;

@@ -484,7 +484,14 @@ __device__ __forceinline__ void gather_unit_fast(const Tc2Params& p, long long r
             } else {
                 int j = m.col;
                 if (a.src_index) j = __ldg(a.src_index + j);
-                my_row = src_row(a, j);
+                if (a.peer_x) {
+                    // node-sharded graph, global source id: the row is read in place from its owner over NVLink
+                    const int owner = j / (int)a.rows_per_rank;
+                    my_row = reinterpret_cast<const float*>(__ldg(reinterpret_cast<const unsigned long long*>(a.peer_x) + owner)) +
+                             (long long)(j - owner * (int)a.rows_per_rank) * a.ldx;
+                } else {
+                    my_row = src_row(a, j);
+                }
                 my_w = m.w;
             }
         }
@@ -970,6 +977,10 @@ int kagnn_fused_fwd_tc2(const KagnnAggregate* agg, int64_t num_rows, const Kagnn
     }
     if (ldy < width) return KAGNN_EINVAL;
     if (agg->num_cols > 4096) return KAGNN_EUNSUPPORTED;   // g_zero_row covers 4096 columns
+    if (agg->peer_x) {                                     // served by gather_unit_fast only (128-bit loads)
+        if (agg->num_cols % 4 != 0 || !aligned16(agg->x) || agg->ldx % 4 != 0) return KAGNN_EUNSUPPORTED;
+        if (agg->rows_per_rank * (int64_t)agg->num_ranks > (int64_t)INT32_MAX) return KAGNN_EUNSUPPORTED;
+    }
     p.y_vec = aligned16(y) && (ldy % 4 == 0);
 
     const int F_pad0 = p.layers[0].F_pad;

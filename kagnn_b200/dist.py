@@ -126,22 +126,120 @@ class ShardGraph(GraphCSR):
         return self._gcn[0], self._gcn[1]
 
 
+@dataclass
+class PeerPlan:
+    """Plan of the in-kernel NVLink gather: just the shard's CSR over GLOBAL source ids (no halo numbering, no send lists)."""
+    graph: GraphCSR
+    n_local: int
+    world: int
+
+
 class ShardedNodeModel:
     """Runs a ``GKAN_Nodes`` / ``GFASTKAN_Nodes`` (eval mode, weights replicated on every rank) on this rank's node
-    range: the fused plan of ``models_node._NodeModel.forward`` with one halo exchange in front of each aggregation."""
+    range: the fused plan of ``models_node._NodeModel.forward`` with the remote source rows of each aggregation fetched
 
-    def __init__(self, model, rank: int, world: int, n_local: int, group=None):
+    * ``mode="halo"``: by one NCCL ``all_to_all_single`` of the distinct remote rows in front of the layer (works for every
+      model flavour, any backend; the CPU tests run it over gloo);
+    * ``mode="peer"``: by the gather warps of the fused kernel themselves, straight from the owners' memory over NVLink
+      (``KagnnAggregate.peer_x``): every rank keeps its skip-concat buffer in ``torch.distributed._symmetric_memory``, the
+      kernel receives the table of peer-mapped base pointers, and the only cross-rank traffic besides the row loads is one
+      device-side barrier between layers.  The transfer overlaps the tensor-core pipeline tile by tile.  Available for the
+      GIN flavour with ``skip=True`` and B-spline chains (what the pipelined kernel runs); ``mode="auto"`` picks it when it
+      applies and falls back to ``"halo"`` otherwise."""
+
+    def __init__(self, model, rank: int, world: int, n_local: int, group=None, mode: str = "halo"):
+        if mode not in ("halo", "peer", "auto"):
+            raise ValueError("mode must be 'halo', 'peer' or 'auto'")
         self.model, self.rank, self.world, self.n_local, self.group = model, rank, world, n_local, group
+        self._symm = {}
+        if mode == "auto":
+            mode = "peer" if self.peer_supported() else "halo"
+        elif mode == "peer" and not self.peer_supported():
+            raise NotImplementedError("mode='peer' needs a GIN-flavour GKAN_Nodes with skip=True, spline_order <= 3, G + k <= 8, "
+                                      "widths <= 128 and feature widths that are multiples of 4")
+        self.mode = mode
 
-    def prepare(self, edge_index_global: Tensor) -> HaloPlan:
+    def peer_supported(self) -> bool:
+        from .conv import GINConv, GINEConv
+        from .ekan import KAN
+        m = self.model
+        if not (getattr(m, "skip", False) and len(m.convs) and all(isinstance(c, GINConv) and not isinstance(c, GINEConv) for c in m.convs)):
+            return False
+        for c in m.convs:
+            if not isinstance(c.nn, KAN):
+                return False
+            for lay in c.nn.layers:
+                if lay.spline_order > 3 or lay.grid_size + lay.spline_order > 8 or lay.out_features > 128 or lay.in_features % 4:
+                    return False
+        try:
+            import torch.distributed._symmetric_memory  # noqa: F401
+        except Exception:
+            return False
+        return True
+
+    def prepare(self, edge_index_global: Tensor):
+        if self.mode == "peer":
+            lo = self.rank * self.n_local
+            dst = edge_index_global[1] - lo
+            ei = torch.stack([edge_index_global[0], dst])
+            g = GraphCSR(ei, self.n_local, self.n_local * self.world)       # range check of both rows happens in the build
+            return PeerPlan(g, self.n_local, self.world)
         plan = build_halo_plan(edge_index_global, self.rank, self.world, self.n_local, self.group)
         plan.exchange = HaloExchange(plan, self.group)
         return plan
 
+    def _symm_buffer(self, n: int, width: int, dev):
+        """Skip-concat buffer in symmetric memory + one device table of peer base pointers per column offset (cached)."""
+        key = (n, width, dev.index)
+        if key not in self._symm:
+            import torch.distributed._symmetric_memory as symm_mem
+            grp = self.group if self.group is not None else dist.group.WORLD
+            if hasattr(symm_mem, "enable_symm_mem_for_group"):
+                try:
+                    symm_mem.enable_symm_mem_for_group(grp.group_name)
+                except Exception:
+                    pass
+            buf = symm_mem.empty((n, width), dtype=torch.float32, device=dev)
+            hdl = symm_mem.rendezvous(buf, grp)
+            self._symm[key] = (buf, hdl, [int(q) for q in hdl.buffer_ptrs], {})
+        return self._symm[key]
+
     @torch.no_grad()
-    def forward(self, x: Tensor, plan: HaloPlan) -> Tensor:
+    def _forward_peer(self, x: Tensor, plan: PeerPlan) -> Tensor:
+        m = self.model
+        n, f = x.shape
+        n_mp = len(m.convs)
+        hid = m.bns[0].num_features
+        buf, hdl, ptrs, tables = self._symm_buffer(n, f + n_mp * hid, x.device)
+
+        def table(col_off: int) -> Tensor:
+            if col_off not in tables:
+                tables[col_off] = torch.tensor([q + 4 * col_off for q in ptrs], dtype=torch.int64, device=x.device)
+            return tables[col_off]
+
+        hdl.barrier()                                     # every rank is done reading the previous step's buffer
+        ops.gather_rows(x, None, out=buf[:, :f])
+        col = 0
+        cur = buf[:, :f]
+        for l, (conv, bn) in enumerate(zip(m.convs, m.bns)):
+            hdl.barrier()                                 # the slice read below is complete on every rank
+            dst = buf[:, f + l * hid: f + (l + 1) * hid]
+            conv(cur, plan.graph, out=dst, post=m._folds[l].get(bn), peer_x=table(col), rows_per_rank=self.n_local)
+            col = f + l * hid
+            cur = dst
+        return m.lay_out(buf)
+
+    @torch.no_grad()
+    def forward(self, x: Tensor, plan) -> Tensor:
         from .conv import GCNConv
         m = self.model
+        if self.mode == "peer":
+            if not m._fusable():
+                raise NotImplementedError("the sharded forward implements the eval-mode plan (BatchNorm folded)")
+            x = x.to(torch.float32)
+            if x.size(0) != self.n_local:
+                raise ValueError("x must hold exactly the rows this rank owns")
+            return self._forward_peer(x, plan)
         if not m._fusable():
             raise NotImplementedError("the sharded forward implements the eval-mode plan (BatchNorm folded)")
         x = x.to(torch.float32)

@@ -288,6 +288,8 @@ class AggSpec:
     edge_row: Optional[Tensor] = None
     src_index: Optional[Tensor] = None
     x_halo: Optional[Tensor] = None       # node-sharded graphs: source rows >= x.size(0) live here (dist.py)
+    peer_x: Optional[Tensor] = None       # node-sharded graphs, in-kernel NVLink gather: (world,) int64 peer base pointers
+    rows_per_rank: int = 0
 
     def struct(self) -> L.KagnnAggregate:
         ldx = _rows(self.x, "x")
@@ -314,6 +316,13 @@ class AggSpec:
             s.ld_halo = _rows(self.x_halo, "x_halo")
             s.x_halo = _addr(self.x_halo)
             s.num_local_src = self.x.size(0)
+        if self.peer_x is not None:
+            _need_cuda(self.peer_x, "peer_x", torch.int64)
+            if self.rows_per_rank <= 0:
+                raise ValueError("peer_x needs rows_per_rank")
+            s.peer_x = _addr(self.peer_x)
+            s.rows_per_rank = int(self.rows_per_rank)
+            s.num_ranks = int(self.peer_x.numel())
         return s
 
 

@@ -15,9 +15,10 @@ n = B.N_NODES
 x, ei = B.synth_graph(n, B.N_EDGES, B.N_FEAT, 12345 + rank, n_src=n * world)
 x, ei = x.to(dev), ei.to(dev)
 ei[1] += rank * n
-runner = kd.ShardedNodeModel(model, rank, world, n)
+mode = sys.argv[1] if len(sys.argv) > 1 else 'halo'
+runner = kd.ShardedNodeModel(model, rank, world, n, mode=mode)
 plan = runner.prepare(ei)
-print(f"rank {rank}: n_halo {plan.n_halo} send rows {sum(plan.send_splits)}", flush=True)
+print(f"rank {rank}: mode {runner.mode}", flush=True)
 orig_call = kd.HaloExchange.__call__
 rec = []
 def timed_call(self, x_local, out=None):
