@@ -201,7 +201,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--dist-mode", default="auto", choices=["auto", "peer", "halo"],
+    ap.add_argument("--dist-mode", default="auto", choices=["auto", "peer", "pull", "halo"],
                     help="N > 1: 'peer' = in-kernel NVLink gather from symmetric memory, 'halo' = NCCL all-to-all per layer")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -388,7 +388,8 @@ def main():
         "config": {"workload": WORKLOAD, "nodes_per_gpu": n_local, "edges_per_gpu": N_EDGES, "features": N_FEAT,
                    "l2": "flushed between iterations (512 MB memset)", "csr": "cached across steps (static graph)",
                    "parallelism": (f"node-range shards x{world}, " + ("remote rows gathered in-kernel over NVLink (symmetric memory), "
-                                   "one device barrier per layer" if runner.mode == "peer" else "one NCCL halo all-to-all per layer"))
+                                   "one device barrier per layer" if runner.mode == "peer" else ("distinct remote rows pulled over NVLink from symmetric memory "
+                                   "by one copy kernel per layer" if runner.mode == "pull" else "one NCCL halo all-to-all per layer")))
                    if dist_on else "single GPU",
                    "graph": "uniform random edges over all shards: (N-1)/N of the edges are cut" if dist_on else "uniform random edges"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "kernels": kernels, "roofline": roofline, "cpu_baseline": cpu,

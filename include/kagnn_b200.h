@@ -201,6 +201,12 @@ int kagnn_tc_selftest(const float* A, const float* B, int32_t N, int32_t K, floa
 int kagnn_gather_rows(const float* x, int64_t ldx, const int32_t* index, int64_t num_rows, int32_t num_cols,
                       float* out, int64_t ld_out, void* stream);
 
+/* Halo pull over NVLink (node-sharded graphs): out[r,:] = row (ids[r] % rows_per_rank) of rank (ids[r] / rows_per_rank)'s
+ * matrix, read in place through peer_x, a DEVICE array of peer-mapped base pointers (see KagnnAggregate.peer_x).  Replaces
+ * pack + all-to-all: only the distinct remote rows cross the link, no send lists, no NCCL.  16-byte aligned, cols % 4 == 0. */
+int kagnn_gather_rows_peer(const float* const* peer_x, int64_t ldx, int64_t rows_per_rank, const int32_t* ids,
+                           int64_t num_rows, int32_t num_cols, float* out, int64_t ld_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

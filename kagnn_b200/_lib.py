@@ -81,6 +81,8 @@ _SIGNATURES = {
     "kagnn_tc_selftest_workspace": (C.c_size_t, [C.c_int32, C.c_int32]),
     "kagnn_tc_selftest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t,
                                     C.c_void_p]),
+    "kagnn_gather_rows_peer": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64,
+                                         C.c_void_p]),
     "kagnn_gather_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
 }
 

@@ -110,6 +110,22 @@ __global__ void gather_rows_kernel(const float* __restrict__ x, int64_t ldx, con
     }
 }
 
+// Halo pull for node-sharded graphs: out[r, :] = row (ids[r] % rows_per_rank) of the matrix of rank ids[r] / rows_per_rank,
+// read in place from the owner over NVLink through a table of peer-mapped base pointers (warp per row, 128-bit loads).
+__global__ void gather_rows_peer_kernel(const float* const* __restrict__ peer_x, int64_t ldx, int64_t rows_per_rank,
+                                        const int32_t* __restrict__ ids, int64_t rows, int cols, float* __restrict__ out,
+                                        int64_t ld_out) {
+    int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    const int32_t gid = ids[r];
+    const int owner = (int)(gid / rows_per_rank);
+    const float* src = peer_x[owner] + (gid - owner * rows_per_rank) * ldx;
+    float* dst = out + r * ld_out;
+    for (int c = lane * 4; c < cols; c += 128)
+        *reinterpret_cast<float4*>(dst + c) = __ldg(reinterpret_cast<const float4*>(src + c));
+}
+
 inline int bits_for(int64_t n) {
     int b = 1;
     while (b < 31 && ((int64_t)1 << b) < n) ++b;
@@ -230,6 +246,18 @@ extern "C" int kagnn_gather_rows(const float* x, int64_t ldx, const int32_t* ind
     bool vec = aligned16(x) && aligned16(out) && (ldx % 4 == 0) && (ld_out % 4 == 0) && (cols % 4 == 0);
     if (vec) gather_rows_kernel<true><<<blocks, kThreads, 0, stream>>>(x, ldx, index, rows, cols, out, ld_out);
     else gather_rows_kernel<false><<<blocks, kThreads, 0, stream>>>(x, ldx, index, rows, cols, out, ld_out);
+    KAGNN_LAUNCH_CHECK();
+    return KAGNN_OK;
+}
+
+extern "C" int kagnn_gather_rows_peer(const float* const* peer_x, int64_t ldx, int64_t rows_per_rank, const int32_t* ids,
+                                      int64_t rows, int32_t cols, float* out, int64_t ld_out, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (rows < 0 || cols < 0 || rows_per_rank <= 0 || (rows > 0 && (!peer_x || !ids || !out))) return KAGNN_EINVAL;
+    if (rows == 0 || cols == 0) return KAGNN_OK;
+    if (!aligned16(out) || (ldx % 4) || (ld_out % 4) || (cols % 4)) return KAGNN_EALIGN;
+    unsigned blocks = (unsigned)ceil_div64(rows * 32, kThreads);
+    gather_rows_peer_kernel<<<blocks, kThreads, 0, stream>>>(peer_x, ldx, rows_per_rank, ids, rows, cols, out, ld_out);
     KAGNN_LAUNCH_CHECK();
     return KAGNN_OK;
 }

@@ -172,6 +172,21 @@ def gather_rows(x: Tensor, index: Optional[Tensor], out: Optional[Tensor] = None
     return out
 
 
+def gather_rows_peer(peer_x: Tensor, ldx: int, rows_per_rank: int, ids: Tensor, num_cols: int, out: Optional[Tensor] = None) -> Tensor:
+    """out[r] = row ids[r] % rows_per_rank of rank ids[r] // rows_per_rank, pulled over NVLink (kagnn_gather_rows_peer)."""
+    global launch_count
+    _need_cuda(peer_x, "peer_x", torch.int64)
+    _need_cuda(ids, "ids", torch.int32)
+    if out is None:
+        out = torch.empty(ids.numel(), num_cols, dtype=torch.float32, device=ids.device)
+    if ids.numel() == 0:
+        return out
+    L.check(L.lib().kagnn_gather_rows_peer(_p(peer_x), ldx, rows_per_rank, _p(ids), ids.numel(), num_cols, _p(out), _rows(out, "out"),
+                                           _stream()), "gather_rows_peer")
+    launch_count += 1
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------
 # weights
 # ---------------------------------------------------------------------------------------------------

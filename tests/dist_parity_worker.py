@@ -68,18 +68,19 @@ def main():
         assert e2 <= 1e-4, (conv_type, fast, e2)
         if conv_type == "gin" and not fast:
             # in-kernel NVLink gather (KagnnAggregate.peer_x): same numbers without pack / all-to-all / halo matrix
-            peer = kd.ShardedNodeModel(m, rank, world, n_local, mode="peer")
-            pplan = peer.prepare(ei[:, mine].to(dev))
-            for rep in range(3):                      # repeated steps exercise the cross-step buffer reuse barriers
-                y_peer = peer.forward(x[rank * n_local:(rank + 1) * n_local].to(dev), pplan)
-            ys = [torch.empty_like(y_peer) for _ in range(world)]
-            dist.all_gather(ys, y_peer)
-            y_peer_all = torch.cat(ys).cpu()
-            e3, e4 = K.rel_err(y_peer_all, y_single), K.rel_err(y_peer_all, y_ref)
-            worst = max(worst, e3, e4)
-            if rank == 0:
-                print(f"kan/gin peer gather: vs single {e3:.2e}, vs oracle {e4:.2e}", flush=True)
-            assert e3 <= 1e-5 and e4 <= 1e-4, (e3, e4)
+            for pmode in ("peer", "pull"):
+                peer = kd.ShardedNodeModel(m, rank, world, n_local, mode=pmode)
+                pplan = peer.prepare(ei[:, mine].to(dev))
+                for rep in range(3):                  # repeated steps exercise the cross-step buffer reuse barriers
+                    y_peer = peer.forward(x[rank * n_local:(rank + 1) * n_local].to(dev), pplan)
+                ys = [torch.empty_like(y_peer) for _ in range(world)]
+                dist.all_gather(ys, y_peer)
+                y_peer_all = torch.cat(ys).cpu()
+                e3, e4 = K.rel_err(y_peer_all, y_single), K.rel_err(y_peer_all, y_ref)
+                worst = max(worst, e3, e4)
+                if rank == 0:
+                    print(f"kan/gin {pmode}: vs single {e3:.2e}, vs oracle {e4:.2e}", flush=True)
+                assert e3 <= 1e-5 and e4 <= 1e-4, (pmode, e3, e4)
     if rank == 0:
         print(f"DIST_PARITY_OK world={world} worst={worst:.2e}", flush=True)
     dist.destroy_process_group()

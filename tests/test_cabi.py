@@ -37,11 +37,27 @@ def test_host_only_queries_need_no_gpu():
     assert _lib.lib().kagnn_packed_weight_elems(5, 7, 3) == 5 * 4 * 8        # out padded to 4
 
 
-def test_struct_layouts_match_the_header():
+def test_struct_layouts_match_the_header(tmp_path):
+    """sizeof / offsetof of every struct as gcc lays the header out == the ctypes mirror in kagnn_b200/_lib.py."""
+    import subprocess
     from kagnn_b200 import _lib
-    assert ctypes.sizeof(_lib.KagnnAffine) == 24
-    assert ctypes.sizeof(_lib.KagnnKanLayer) == 72
-    assert ctypes.sizeof(_lib.KagnnAggregate) == 120
+    structs = {"KagnnAffine": _lib.KagnnAffine, "KagnnKanLayer": _lib.KagnnKanLayer, "KagnnAggregate": _lib.KagnnAggregate}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "kagnn_b200.h")}"', "int main(void) {"]
+    for name, cls in structs.items():
+        lines.append(f'printf("{name} %zu\\n", sizeof({name}));')
+        for field, _ in cls._fields_:
+            lines.append(f'printf("{name}.{field} %zu\\n", offsetof({name}, {field}));')
+    lines += ["return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-o", str(exe), str(src)], check=True)
+    got = dict(ln.split() for ln in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for name, cls in structs.items():
+        assert int(got[name]) == ctypes.sizeof(cls), name
+        for field, _ in cls._fields_:
+            assert int(got[f"{name}.{field}"]) == getattr(cls, field).offset, (name, field)
+    assert ctypes.sizeof(_lib.KagnnAggregate) == 144
 
 
 def test_no_cpu_fallback():
