@@ -113,7 +113,13 @@ typedef struct KagnnAggregate {
     const float* const* peer_x;
     int64_t rows_per_rank;
     int32_t num_ranks;
-    int32_t _pad2;
+    /* Two-part rows for KAGNN_AGG_NONE (the skip concat of nc/models.py:196-201 without the copy of x): logical row r is
+     * [x_head[r, 0:num_head_cols] | x[r, 0:num_cols - num_head_cols]].  num_head_cols == 0: not used.  Implemented by the
+     * pipelined tcgen05 kernel when num_head_cols is a multiple of 128; otherwise KAGNN_EUNSUPPORTED (the host side then
+     * materialises the concatenation).                                                                                    */
+    int32_t num_head_cols;
+    const float* x_head;
+    int64_t ld_head;
 } KagnnAggregate;
 
 /* ---- library ------------------------------------------------------------------------------------ */

@@ -44,7 +44,8 @@ class KagnnAggregate(C.Structure):
         ("self_scale", C.c_float), ("_pad", C.c_int32),
         ("edge_feat", C.c_void_p), ("ld_edge", C.c_int64), ("edge_row", C.c_void_p),
         ("x_halo", C.c_void_p), ("ld_halo", C.c_int64), ("num_local_src", C.c_int64),
-        ("peer_x", C.c_void_p), ("rows_per_rank", C.c_int64), ("num_ranks", C.c_int32), ("_pad2", C.c_int32),
+        ("peer_x", C.c_void_p), ("rows_per_rank", C.c_int64), ("num_ranks", C.c_int32), ("num_head_cols", C.c_int32),
+        ("x_head", C.c_void_p), ("ld_head", C.c_int64),
     ]
 
 

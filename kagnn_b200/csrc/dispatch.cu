@@ -17,7 +17,7 @@ int kagnn_validate_fused_args(const KagnnAggregate* agg, int64_t num_rows, const
     if (n_layers > 0 && (!layers || !y)) return KAGNN_EINVAL;
     if (n_layers == 0 && !agg_out) return KAGNN_EINVAL;
     if (agg->mode < KAGNN_AGG_NONE || agg->mode > KAGNN_AGG_SEGMENT_MEAN) return KAGNN_EINVAL;
-    if (agg->num_cols <= 0 || !agg->x || agg->ldx < agg->num_cols) return KAGNN_EINVAL;
+    if (agg->num_cols <= 0 || !agg->x || agg->ldx < agg->num_cols - (agg->num_head_cols > 0 ? agg->num_head_cols : 0)) return KAGNN_EINVAL;
     if (agg->mode != KAGNN_AGG_NONE && !agg->rowptr) return KAGNN_EINVAL;
     const bool segment = agg->mode == KAGNN_AGG_SEGMENT_SUM || agg->mode == KAGNN_AGG_SEGMENT_MEAN;
     if (agg->mode != KAGNN_AGG_NONE && !segment && !agg->col) return KAGNN_EINVAL;
@@ -26,6 +26,9 @@ int kagnn_validate_fused_args(const KagnnAggregate* agg, int64_t num_rows, const
     if (agg_out && ld_agg_out < agg->num_cols) return KAGNN_EINVAL;
     if (agg->x_halo && (agg->ld_halo < agg->num_cols || agg->num_local_src < 0)) return KAGNN_EINVAL;
     if (agg->x_halo && (agg->mode == KAGNN_AGG_NONE || agg->src_index)) return KAGNN_EINVAL;
+    if (agg->num_head_cols < 0 || (agg->num_head_cols > 0 && agg->num_head_cols >= agg->num_cols)) return KAGNN_EINVAL;
+    if (agg->num_head_cols > 0 && (agg->mode != KAGNN_AGG_NONE || !agg->x_head || agg->ld_head < agg->num_head_cols || agg->src_index))
+        return KAGNN_EINVAL;
     if (agg->peer_x && (agg->x_halo || agg->src_index || agg->rows_per_rank <= 0 || agg->num_ranks <= 0)) return KAGNN_EINVAL;
     if (agg->peer_x && agg->mode != KAGNN_AGG_GIN && agg->mode != KAGNN_AGG_WEIGHTED) return KAGNN_EINVAL;
     if (num_rows > (int64_t)INT32_MAX * 32) return KAGNN_EUNSUPPORTED;
@@ -76,7 +79,7 @@ extern "C" int kagnn_fused_layer_fwd(const KagnnAggregate* agg, int64_t num_rows
                 }
                 if (rc != KAGNN_EUNSUPPORTED) return rc;
             }
-            if (agg->peer_x) return KAGNN_EUNSUPPORTED;   // in-kernel peer gather exists in the pipelined kernel only
+            if (agg->peer_x || agg->num_head_cols) return KAGNN_EUNSUPPORTED;   // peer gather / two-part rows: pipelined kernel only
             rc = kagnn_fused_fwd_tc(agg, num_rows, pre, agg_out, ld_agg_out, n_layers, layers, post, y, ldy, stream);
             if (rc == KAGNN_OK) {
                 g_count_tc.fetch_add(1);
@@ -89,7 +92,7 @@ extern "C" int kagnn_fused_layer_fwd(const KagnnAggregate* agg, int64_t num_rows
     } else if (mode == KAGNN_PATH_TC && n_layers >= 1 && num_rows > 0) {
         return KAGNN_EUNSUPPORTED;
     }
-    if (agg->peer_x) return KAGNN_EUNSUPPORTED;
+    if (agg->peer_x || agg->num_head_cols) return KAGNN_EUNSUPPORTED;
     int rc = kagnn_fused_fwd_fp32(agg, num_rows, pre, agg_out, ld_agg_out, n_layers, layers, post, y, ldy, stream);
     if (rc == KAGNN_OK && num_rows > 0) g_count_fp32.fetch_add(1);
     return rc;

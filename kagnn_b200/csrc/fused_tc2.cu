@@ -236,10 +236,16 @@ __device__ __forceinline__ void gather_unit(const Tc2Params& p, long long row0, 
         for (int rb = 0; rb < RPW; rb += 8) {
             float v[8][4];
 #pragma unroll
+            // two-part rows: units below num_head_cols come from x_head, the others from x (unit-aligned split)
+            const bool head = c0 < a.num_head_cols;
+            const float* src = head ? a.x_head : a.x;
+            const long long ld = head ? a.ld_head : a.ldx;
+            const int cb = head ? cbase : cbase - a.num_head_cols;
+#pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const long long r = row0 + rl0 + rb + u;
                 const bool on = r < p.num_rows;
-                ldp4<VEC>(a.x + (on ? r : 0) * a.ldx + cbase, on, v[u], cv);
+                ldp4<VEC>(src + (on ? r : 0) * ld + cb, on, v[u], cv);
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
@@ -814,6 +820,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                          (p.agg.mode != KAGNN_AGG_GINE ||
                           (((reinterpret_cast<uintptr_t>(p.agg.edge_feat) & 15u) == 0) && (p.agg.ld_edge % 4 == 0)));
         const bool gine = p.agg.mode == KAGNN_AGG_GINE;
+        const bool head_ok = !p.agg.num_head_cols || (((reinterpret_cast<uintptr_t>(p.agg.x_head) & 15u) == 0) && (p.agg.ld_head % 4 == 0));
         const bool plain_copy = p.agg.mode == KAGNN_AGG_NONE && !p.has_pre && !p.agg_out && !p.agg.src_index;
         const int F_pad = p.layers[0].F_pad;
         uint32_t uc = 0;
@@ -826,7 +833,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                 if (lane == 0 && gw == 0) TRL(6, uc, 1);
                 float* xsu = xs + (size_t)u * p.unit_floats;
                 const int c0 = ub * p.uw, ucols = min(p.uw, F_pad - c0);
-                if (vec) {
+                if (vec && head_ok) {
                     if (gine) gather_unit<true, true>(p, row0, c0, ucols, xsu, gw, lane);
                     else if (plain_copy) gather_unit<true, false>(p, row0, c0, ucols, xsu, gw, lane);
                     else if (p.agg.mode == KAGNN_AGG_WEIGHTED) gather_unit_fast<true>(p, row0, c0, ucols, xsu, gw, lane);
@@ -977,6 +984,10 @@ int kagnn_fused_fwd_tc2(const KagnnAggregate* agg, int64_t num_rows, const Kagnn
     }
     if (ldy < width) return KAGNN_EINVAL;
     if (agg->num_cols > 4096) return KAGNN_EUNSUPPORTED;   // g_zero_row covers 4096 columns
+    if (agg->num_head_cols) {                              // two-part rows: plain-copy path, split on a unit boundary
+        if (agg->mode != KAGNN_AGG_NONE || pre || agg_out || agg->src_index) return KAGNN_EUNSUPPORTED;
+        if (agg->num_head_cols % 128 != 0 || agg->num_cols - agg->num_head_cols <= 0) return KAGNN_EUNSUPPORTED;
+    }
     if (agg->peer_x) {                                     // served by gather_unit_fast only (128-bit loads)
         if (agg->num_cols % 4 != 0 || !aligned16(agg->x) || agg->ldx % 4 != 0) return KAGNN_EUNSUPPORTED;
         if (agg->rows_per_rank * (int64_t)agg->num_ranks > (int64_t)INT32_MAX) return KAGNN_EUNSUPPORTED;

@@ -114,10 +114,14 @@ __global__ void gather_rows_kernel(const float* __restrict__ x, int64_t ldx, con
 // read in place from the owner over NVLink through a table of peer-mapped base pointers (warp per row, 128-bit loads).
 __global__ void gather_rows_peer_kernel(const float* const* __restrict__ peer_x, int64_t ldx, int64_t rows_per_rank,
                                         const int32_t* __restrict__ ids, int64_t rows, int cols, float* __restrict__ out,
-                                        int64_t ld_out) {
-    int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+                                        int64_t ld_out, int nseg) {
+    // ids are sorted by owner: consecutive warps take rows `seg` apart (a transposed walk over `nseg` segments), so the
+    // warps in flight at any moment read from ALL peers instead of queueing on one NVLink egress port at a time
+    const int64_t v = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
-    if (r >= rows) return;
+    const int64_t seg = (rows + nseg - 1) / nseg;
+    const int64_t r = (v % nseg) * seg + v / nseg;
+    if (v >= seg * nseg || r >= rows) return;
     const int32_t gid = ids[r];
     const int owner = (int)(gid / rows_per_rank);
     const float* src = peer_x[owner] + (gid - owner * rows_per_rank) * ldx;
@@ -256,8 +260,10 @@ extern "C" int kagnn_gather_rows_peer(const float* const* peer_x, int64_t ldx, i
     if (rows < 0 || cols < 0 || rows_per_rank <= 0 || (rows > 0 && (!peer_x || !ids || !out))) return KAGNN_EINVAL;
     if (rows == 0 || cols == 0) return KAGNN_OK;
     if (!aligned16(out) || (ldx % 4) || (ld_out % 4) || (cols % 4)) return KAGNN_EALIGN;
-    unsigned blocks = (unsigned)ceil_div64(rows * 32, kThreads);
-    gather_rows_peer_kernel<<<blocks, kThreads, 0, stream>>>(peer_x, ldx, rows_per_rank, ids, rows, cols, out, ld_out);
+    const int nseg = 16;
+    const int64_t seg = ceil_div64(rows, nseg);
+    unsigned blocks = (unsigned)ceil_div64(seg * nseg * 32, kThreads);
+    gather_rows_peer_kernel<<<blocks, kThreads, 0, stream>>>(peer_x, ldx, rows_per_rank, ids, rows, cols, out, ld_out, nseg);
     KAGNN_LAUNCH_CHECK();
     return KAGNN_OK;
 }

@@ -78,18 +78,14 @@ class _NodeModel(nn.Module):
         n_mp = len(self.convs)
         if not self._fusable():
             return self._forward_unfused(x, g)
-        width = f + n_mp * hid
-        if self.skip:
-            buf = torch.empty(n, width, dtype=torch.float32, device=x.device)
-            buf[:, :f].copy_(x)
-            cur = buf[:, :f]
-        else:
-            buf = None
-            cur = x
+        # skip concat (models.py:196-201) without any copy: every layer writes its column slice of the hidden buffer and
+        # lay_out reads two-part rows [x | h_1 .. h_L] (KagnnAggregate.x_head)
+        buf = torch.empty(n, n_mp * hid, dtype=torch.float32, device=x.device) if self.skip else None
+        cur = x
         is_gcn = isinstance(self.convs[0], GCNConv)
         t = self.convs[0].transform(cur) if is_gcn else None
         for l, (conv, bn) in enumerate(zip(self.convs, self.bns)):
-            dst = buf[:, f + l * hid: f + (l + 1) * hid] if self.skip else torch.empty(n, hid, dtype=torch.float32, device=x.device)
+            dst = buf[:, l * hid: (l + 1) * hid] if self.skip else torch.empty(n, hid, dtype=torch.float32, device=x.device)
             if is_gcn:
                 pre = self._folds[l].get(bn, conv.bias.detach() if conv.bias is not None else None)
                 nxt = self.convs[l + 1].lin.kernel_specs() if l + 1 < n_mp else []
@@ -99,7 +95,11 @@ class _NodeModel(nn.Module):
             else:
                 conv(cur, g, out=dst, post=self._folds[l].get(bn))
             cur = dst
-        return self.lay_out(buf if self.skip else cur)
+        if not self.skip:
+            return self.lay_out(cur)
+        if n_mp == 0:
+            return self.lay_out(x)
+        return ops.fused_layer(ops.AggSpec(L.AGG_NONE, buf, x_head=x), n, self.lay_out.kernel_specs())
 
     def _forward_unfused(self, x: Tensor, g) -> Tensor:
         feats = [x]

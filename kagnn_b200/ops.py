@@ -305,11 +305,19 @@ class AggSpec:
     x_halo: Optional[Tensor] = None       # node-sharded graphs: source rows >= x.size(0) live here (dist.py)
     peer_x: Optional[Tensor] = None       # node-sharded graphs, in-kernel NVLink gather: (world,) int64 peer base pointers
     rows_per_rank: int = 0
+    x_head: Optional[Tensor] = None       # AGG_NONE two-part rows: logical row = [x_head[r] | x[r]] (skip concat without the copy)
 
     def struct(self) -> L.KagnnAggregate:
         ldx = _rows(self.x, "x")
         s = L.KagnnAggregate()
         s.mode, s.num_cols = self.mode, self.x.size(1)
+        if self.x_head is not None:
+            if self.x_head.size(0) != self.x.size(0):
+                raise ValueError("x_head must have as many rows as x")
+            s.ld_head = _rows(self.x_head, "x_head")
+            s.x_head = _addr(self.x_head)
+            s.num_head_cols = self.x_head.size(1)
+            s.num_cols = self.x_head.size(1) + self.x.size(1)
         s.x, s.ldx = _addr(self.x), ldx
         for name in ("src_index", "rowptr", "col", "edge_row"):
             t = getattr(self, name)
@@ -343,7 +351,7 @@ class AggSpec:
 
 def _launch_fused(agg: AggSpec, num_rows: int, layers: Sequence[KanLayerSpec], pre, post, agg_out, y) -> int:
     if fused_timing is not None:
-        label = "agg%d[%d]%s" % (agg.mode, agg.x.size(1), "".join("->%d" % sp.out_features for sp in layers))
+        label = "agg%d[%d]%s" % (agg.mode, agg.x.size(1) + (agg.x_head.size(1) if agg.x_head is not None else 0), "".join("->%d" % sp.out_features for sp in layers))
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         code = _launch_fused_raw(agg, num_rows, layers, pre, post, agg_out, y)
@@ -383,6 +391,14 @@ def fused_layer(agg: AggSpec, num_rows: int, layers: Sequence[KanLayerSpec], pre
         return out if layers else agg_out
     code = _launch_fused(agg, num_rows, layers, pre, post, agg_out, out)
     launch_count += 1
+    if code == L.E_UNSUPPORTED and agg.x_head is not None:
+        # two-part rows not available for this shape / kernel: materialise the concatenation (two strided row copies)
+        cat = torch.empty(agg.x.size(0), agg.x_head.size(1) + agg.x.size(1), dtype=torch.float32, device=dev)
+        gather_rows(agg.x_head, None, out=cat[:, :agg.x_head.size(1)])
+        gather_rows(agg.x, None, out=cat[:, agg.x_head.size(1):])
+        agg = AggSpec(agg.mode, cat)
+        code = _launch_fused(agg, num_rows, layers, pre, post, agg_out, out)
+        launch_count += 1
     if code == L.E_UNSUPPORTED and layers and (agg.mode != L.AGG_NONE or pre is not None or agg.src_index is not None):
         # the aggregated tile is too wide for shared memory: aggregate to HBM, then stream the chain
         tmp = agg_out if agg_out is not None else torch.empty(num_rows, agg.x.size(1), dtype=torch.float32, device=dev)
