@@ -58,7 +58,18 @@ constexpr int BM = 128;
 #endif
 constexpr int NPW = KAGNN_TC2_NPW;           // producer warps: 2 or 4 warpgroups, each expands 8 / NWG features of every chunk
 constexpr int NWG = NPW / 4;
-constexpr int FPW = 8 / NWG;                 // features per warpgroup per spline chunk
+#ifndef KAGNN_TC2_OWN
+#define KAGNN_TC2_OWN 0
+#endif
+// OWN = 1: chunk c of the running sequence is expanded entirely by warpgroup c % NWG (per-chunk fixed costs -- barrier round,
+//          fences, address setup -- are paid once per warpgroup per NWG chunks; the warpgroups work on different ring stages);
+// OWN = 0: every warpgroup expands 8 / NWG features of EVERY chunk (lowest latency per chunk, NWG times the fixed costs).
+// Measured on the bench (B200): OWN = 1 is 3-8 % slower on the GIN layers and 5 % faster on lay_out, so 0 is the default.
+// OWN = 1 needs ring depth >= NWG (a warpgroup must never be two mbarrier phases ahead of its stage); the launcher declines
+// shapes whose W stages do not fit that often.
+constexpr bool OWN = KAGNN_TC2_OWN != 0;
+constexpr int FPW = OWN ? 8 : 8 / NWG;       // features per warpgroup per spline chunk it works on
+constexpr int FULL_ARRIVALS = (OWN ? 128 : NPW * 32) + 1;   // producer threads of one chunk + the W loader's expect_tx
 constexpr int NGW = 8;                       // gather warps
 constexpr int NPROD = NPW * 32;
 constexpr int NTHREADS = (NPW + NGW + 4) * 32;   // + MMA, W loader and two idle warps (whole warpgroups for setmaxnreg)
@@ -603,7 +614,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
             tc::mbar_init(&xs_empty[s], NPW);
         }
         for (int s = 0; s < MAX_STAGE; ++s) {
-            tc::mbar_init(&full[s], NPROD + 1);
+            tc::mbar_init(&full[s], FULL_ARRIVALS);
             tc::mbar_init(&empty[s], 1);
         }
         tc::mbar_init(acc_full, 1);
@@ -669,9 +680,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                 }
                 int s = (int)(cq % (uint32_t)p.ns);
                 uint32_t par = ((cq / (uint32_t)p.ns) & 1u) ^ 1u;
+                bool unit_ready = false;
                 ChunkCursor c(L.F_pad);
                 for (int q = 0; q < n_chunks; ++q, c.next()) {
                     if (l == 0 && c.j == 0) {
+                        // x-tile ring bookkeeping (every warp walks every chunk): leaving a unit releases it
                         const int ul = (64 * c.group) >> p.uw_shift;
                         if (ul != cur_unit) {
                             if (cur_unit >= 0) {
@@ -679,86 +692,96 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                                 if (lane == 0) tc::mbar_arrive(&xs_empty[(uc0 + cur_unit) % p.n_units]);
                             }
                             cur_unit = ul;
+                            unit_ready = false;
                             const uint32_t un = uc0 + ul;
-                            if (lane == 0 && (warp & 3) == 0 && wg < 2) TRL(wg, cq + q, 0);
-                            tc::mbar_wait_relaxed(&xs_full[un % p.n_units], (un / p.n_units) & 1);
-                            if (lane == 0 && (warp & 3) == 0 && wg < 2) TRL(wg, cq + q, 1);
                             xrow = xs + (size_t)(un % p.n_units) * p.unit_floats + (size_t)row * p.xld - (size_t)ul * p.uw;
                         }
                     }
-                    if (lane == 0 && (warp & 3) == 0 && wg < 2) TRC(wg, cq + q, 2);
-                    tc::mbar_wait_relaxed(&empty[s], par);
-                    if (lane == 0 && (warp & 3) == 0 && wg < 2) TRC(wg, cq + q, 3);
-                    tc::tc_fence_after_sync();
-                    const uint32_t a_t = tmem_base + lane_base + TMEM_A0 + 64u * s;
-                    if (!c.base()) {
-                        const int f0 = 64 * c.group + 8 * c.j + FPW * wg;
-                        float v[FPW];
-                        if (l == 0) {
-                            if (FPW == 4) {
-                                const float4 t = *reinterpret_cast<const float4*>(xrow + f0);
-                                v[0] = t.x; v[1] = t.y; v[FPW - 2] = t.z; v[FPW - 1] = t.w;
-                            } else {
-                                const float2 t = *reinterpret_cast<const float2*>(xrow + f0);
-                                v[0] = t.x; v[1] = t.y;
-                            }
-                        } else {
-                            tc::tmem_ldn<FPW>(src_t + (uint32_t)f0, v);
-                            if (src_lo) {
-                                float v2[FPW];
-                                tc::tmem_ldn<FPW>(src_t + src_lo + (uint32_t)f0, v2);
-#pragma unroll
-                                for (int i = 0; i < FPW; ++i) v[i] += v2[i];
-                            }
+                    const bool mine = !OWN || (int)((cq + (uint32_t)q) & (uint32_t)(NWG - 1)) == wg;
+                    if (mine) {
+                        if (l == 0 && !unit_ready) {
+                            const uint32_t un = uc0 + (uint32_t)cur_unit;
+                            if (lane == 0 && (warp & 3) == 0 && wg < 2) TRL(wg, cq + q, 0);
+                            tc::mbar_wait_relaxed(&xs_full[un % p.n_units], (un / p.n_units) & 1);
+                            if (lane == 0 && (warp & 3) == 0 && wg < 2) TRL(wg, cq + q, 1);
+                            unit_ready = true;
                         }
-                        uint32_t hi[FPW / 2][8], lo[FPW / 2][8];
-#pragma unroll
-                        for (int i = 0; i < FPW; i += 2) {
-                            bspline_slots<K>(inv_h, c0f, limp, lutL, v[i], hi[i / 2], lo[i / 2]);
-                            bspline_slots<K>(inv_h, c0f, limp, lutL, v[i + 1], hi[i / 2] + 4, lo[i / 2] + 4);
-                        }
-                        if (lane == 0 && (warp & 3) == 0 && wg < 2) TRC(wg, cq + q, 5);
-#pragma unroll
-                        for (int i = 0; i < FPW; i += 2) {
-                            tc::tmem_st8(a_t + 4u * (uint32_t)(FPW * wg + i), hi[i / 2]);
-                            tc::tmem_st8(a_t + 32u + 4u * (uint32_t)(FPW * wg + i), lo[i / 2]);
-                        }
-                    } else {
-#pragma unroll 1
-                        for (int jj = wg; jj < c.n_oct; jj += NWG) {
-                            const int f0 = 64 * c.group + 8 * jj;
-                            float v[8];
+                        if (lane == 0 && (warp & 3) == 0 && wg < 2) TRC(wg, cq + q, 2);
+                        tc::mbar_wait_relaxed(&empty[s], par);
+                        if (lane == 0 && (warp & 3) == 0 && wg < 2) TRC(wg, cq + q, 3);
+                        tc::tc_fence_after_sync();
+                        const uint32_t a_t = tmem_base + lane_base + TMEM_A0 + 64u * s;
+                        if (!c.base()) {
+                            const int fsh = OWN ? 0 : FPW * wg;               // first feature of this warpgroup inside the chunk
+                            const int f0 = 64 * c.group + 8 * c.j + fsh;
+                            float v[FPW];
                             if (l == 0) {
-                                const float4 t0 = *reinterpret_cast<const float4*>(xrow + f0);
-                                const float4 t1 = *reinterpret_cast<const float4*>(xrow + f0 + 4);
-                                v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w; v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
+                                if (FPW == 8) {
+                                    const float4 t0 = *reinterpret_cast<const float4*>(xrow + f0);
+                                    const float4 t1 = *reinterpret_cast<const float4*>(xrow + f0 + 4);
+                                    v[0] = t0.x; v[1] = t0.y; v[2 % FPW] = t0.z; v[3 % FPW] = t0.w;
+                                    v[4 % FPW] = t1.x; v[5 % FPW] = t1.y; v[6 % FPW] = t1.z; v[7 % FPW] = t1.w;
+                                } else if (FPW == 4) {
+                                    const float4 t = *reinterpret_cast<const float4*>(xrow + f0);
+                                    v[0] = t.x; v[1] = t.y; v[2 % FPW] = t.z; v[3 % FPW] = t.w;
+                                } else {
+                                    const float2 t = *reinterpret_cast<const float2*>(xrow + f0);
+                                    v[0] = t.x; v[1] = t.y;
+                                }
                             } else {
-                                tc::tmem_ld8(src_t + (uint32_t)f0, v);
+                                tc::tmem_ldn<FPW>(src_t + (uint32_t)f0, v);
                                 if (src_lo) {
-                                    float v2[8];
-                                    tc::tmem_ld8(src_t + src_lo + (uint32_t)f0, v2);
+                                    float v2[FPW];
+                                    tc::tmem_ldn<FPW>(src_t + src_lo + (uint32_t)f0, v2);
 #pragma unroll
-                                    for (int i = 0; i < 8; ++i) v[i] += v2[i];
+                                    for (int i = 0; i < FPW; ++i) v[i] += v2[i];
                                 }
                             }
-                            float r[8];
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                v[i] = silu_nan(v[i]);
-                                r[i] = trunc_residual(v[i]);
+                            for (int i = 0; i < FPW; i += 2) {
+                                uint32_t hi[8], lo[8];
+                                bspline_slots<K>(inv_h, c0f, limp, lutL, v[i], hi, lo);
+                                bspline_slots<K>(inv_h, c0f, limp, lutL, v[i + 1], hi + 4, lo + 4);
+                                tc::tmem_st8(a_t + 4u * (uint32_t)(fsh + i), hi);
+                                tc::tmem_st8(a_t + 32u + 4u * (uint32_t)(fsh + i), lo);
                             }
-                            tc::tmem_st4(a_t + 4u * jj, pack_trunc(v[0], v[1]), pack_trunc(v[2], v[3]), pack_trunc(v[4], v[5]),
-                                         pack_trunc(v[6], v[7]));
-                            tc::tmem_st4(a_t + 32u + 4u * jj, pack_rn(r[0], r[1]), pack_rn(r[2], r[3]), pack_rn(r[4], r[5]),
-                                         pack_rn(r[6], r[7]));
+                        } else {
+#pragma unroll 1
+                            for (int jj = OWN ? 0 : wg; jj < c.n_oct; jj += OWN ? 1 : NWG) {
+                                const int f0 = 64 * c.group + 8 * jj;
+                                float v[8];
+                                if (l == 0) {
+                                    const float4 t0 = *reinterpret_cast<const float4*>(xrow + f0);
+                                    const float4 t1 = *reinterpret_cast<const float4*>(xrow + f0 + 4);
+                                    v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w; v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
+                                } else {
+                                    tc::tmem_ld8(src_t + (uint32_t)f0, v);
+                                    if (src_lo) {
+                                        float v2[8];
+                                        tc::tmem_ld8(src_t + src_lo + (uint32_t)f0, v2);
+#pragma unroll
+                                        for (int i = 0; i < 8; ++i) v[i] += v2[i];
+                                    }
+                                }
+                                float r[8];
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    v[i] = silu_nan(v[i]);
+                                    r[i] = trunc_residual(v[i]);
+                                }
+                                tc::tmem_st4(a_t + 4u * jj, pack_trunc(v[0], v[1]), pack_trunc(v[2], v[3]), pack_trunc(v[4], v[5]),
+                                             pack_trunc(v[6], v[7]));
+                                tc::tmem_st4(a_t + 32u + 4u * jj, pack_rn(r[0], r[1]), pack_rn(r[2], r[3]), pack_rn(r[4], r[5]),
+                                             pack_rn(r[6], r[7]));
+                            }
                         }
+                        if (lane == 0 && (warp & 3) == 0 && wg < 2) TRC(wg, cq + q, 6);
+                        tc::tmem_st_wait();
+                        if (lane == 0 && (warp & 3) == 0 && wg < 2) TRC(wg, cq + q, 7);
+                        tc::tc_fence_before_sync();
+                        tc::mbar_arrive(&full[s]);
+                        if (lane == 0 && (warp & 3) == 0 && wg < 2) TRC(wg, cq + q, 4);
                     }
-                    if (lane == 0 && (warp & 3) == 0 && wg < 2) TRC(wg, cq + q, 6);
-                    tc::tmem_st_wait();
-                    if (lane == 0 && (warp & 3) == 0 && wg < 2) TRC(wg, cq + q, 7);
-                    tc::tc_fence_before_sync();
-                    tc::mbar_arrive(&full[s]);
-                    if (lane == 0 && (warp & 3) == 0 && wg < 2) TRC(wg, cq + q, 4);
                     if (++s == p.ns) { s = 0; par ^= 1u; }
                 }
                 cq += (uint32_t)n_chunks;
@@ -1016,6 +1039,7 @@ int kagnn_fused_fwd_tc2(const KagnnAggregate* agg, int64_t num_rows, const Kagnn
     if (best_units == 0) return KAGNN_EUNSUPPORTED;
     p.n_units = best_units;
     p.ns = best_ns;
+    if (OWN && p.ns < NWG) return KAGNN_EUNSUPPORTED;
     const size_t smem = (size_t)p.n_units * unit_bytes + (size_t)p.ns * p.bstage_bytes + tail;
 
     void (*kern)(Tc2Params) = k == 3 ? fused_tc2_kernel<3> : (k == 2 ? fused_tc2_kernel<2> : fused_tc2_kernel<1>);

@@ -153,6 +153,8 @@ template <>
 __device__ __forceinline__ void tmem_ldn<2>(uint32_t taddr, float (&v)[2]) { tmem_ld2(taddr, v); }
 template <>
 __device__ __forceinline__ void tmem_ldn<4>(uint32_t taddr, float (&v)[4]) { tmem_ld4(taddr, v); }
+template <>
+__device__ __forceinline__ void tmem_ldn<8>(uint32_t taddr, float (&v)[8]) { tmem_ld8(taddr, v); }
 __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
