@@ -213,6 +213,18 @@ int kagnn_gather_rows(const float* x, int64_t ldx, const int32_t* index, int64_t
 int kagnn_gather_rows_peer(const float* const* peer_x, int64_t ldx, int64_t rows_per_rank, const int32_t* ids,
                            int64_t num_rows, int32_t num_cols, float* out, int64_t ld_out, void* stream);
 
+/* ---- small epilogues of the models (so that no step of a forward runs as framework math) ---------------------------- */
+/* y[r,:] = log_softmax(x[r,:]) (gc/models.py:119,194). */
+int kagnn_log_softmax_rows(const float* x, int64_t ldx, int64_t num_rows, int32_t num_cols, float* y, int64_t ldy, void* stream);
+/* Training-mode BatchNorm1d forward (nc/models.py:197 under model.train(), also the no_grad validation pass of
+ * nc/utils.py:172): batch mean / biased variance over all rows, y = act((x - mean) * rsqrt(var + eps) * weight + bias);
+ * running_mean / running_var (may be NULL) get the momentum update with the unbiased variance.  x and y may alias. */
+size_t kagnn_batchnorm_train_workspace(int32_t num_cols);
+int kagnn_batchnorm_train_fwd(const float* x, int64_t ldx, int64_t num_rows, int32_t num_cols, const float* weight_or_null,
+                              const float* bias_or_null, float eps, float momentum, float* running_mean_or_null,
+                              float* running_var_or_null, int32_t act, float* y, int64_t ldy, void* workspace,
+                              size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

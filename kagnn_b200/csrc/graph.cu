@@ -267,3 +267,94 @@ extern "C" int kagnn_gather_rows_peer(const float* const* peer_x, int64_t ldx, i
     KAGNN_LAUNCH_CHECK();
     return KAGNN_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Row-wise log_softmax of the class logits (graph_classification/models.py:119,194) and training-mode
+// BatchNorm1d (node_classification_clean/models.py:197 with model.train(): batch statistics over all
+// rows, biased variance for the normalisation, unbiased for the running estimate, momentum update).
+// Small HBM-bound helpers so that no step of a product forward runs as framework math.
+// ---------------------------------------------------------------------------------------------------
+namespace {
+__global__ void log_softmax_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int cols, float* __restrict__ y,
+                                   int64_t ldy) {
+    const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    const float* xr = x + r * ldx;
+    float m = -INFINITY;
+    for (int c = lane; c < cols; c += 32) m = fmaxf(m, xr[c]);
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.f;
+    for (int c = lane; c < cols; c += 32) s += expf(xr[c] - m);
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float lse = m + logf(s);
+    for (int c = lane; c < cols; c += 32) y[r * ldy + c] = xr[c] - lse;
+}
+
+// column sums and sums of squares: each block owns a slab of rows, threads stride over columns (coalesced), fp64 partials
+__global__ void bn_stats_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int cols, int64_t rows_per_block,
+                                double* __restrict__ sums) {
+    const int64_t r0 = blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+        double s = 0.0, q = 0.0;
+        for (int64_t r = r0; r < r1; ++r) {
+            const double v = (double)x[r * ldx + c];
+            s += v;
+            q += v * v;
+        }
+        atomicAdd(&sums[c], s);
+        atomicAdd(&sums[cols + c], q);
+    }
+}
+
+__global__ void bn_apply_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int cols, const double* __restrict__ sums,
+                                const float* __restrict__ weight, const float* __restrict__ bias, float eps, float momentum,
+                                float* __restrict__ running_mean, float* __restrict__ running_var, int act, float* __restrict__ y,
+                                int64_t ldy) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int c = (int)(idx % cols);
+    const int64_t r = idx / cols;
+    if (r >= rows) return;
+    const double mean = sums[c] / (double)rows;
+    const double var = fmax(sums[cols + c] / (double)rows - mean * mean, 0.0);
+    const float inv = (float)(1.0 / sqrt(var + (double)eps));
+    float v = (x[r * ldx + c] - (float)mean) * inv;
+    if (weight) v *= weight[c];
+    if (bias) v += bias[c];
+    if (act == KAGNN_ACT_SILU) v = v / (1.0f + expf(-v));
+    y[r * ldy + c] = v;
+    if (r == 0 && running_mean && running_var) {
+        const double unbiased = rows > 1 ? var * (double)rows / (double)(rows - 1) : var;
+        running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * (float)mean;
+        running_var[c] = (1.0f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+}
+}  // namespace
+
+extern "C" int kagnn_log_softmax_rows(const float* x, int64_t ldx, int64_t rows, int32_t cols, float* y, int64_t ldy, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (rows < 0 || cols <= 0 || (rows > 0 && (!x || !y)) || ldx < cols || ldy < cols) return KAGNN_EINVAL;
+    if (rows == 0) return KAGNN_OK;
+    log_softmax_kernel<<<(unsigned)ceil_div64(rows * 32, kThreads), kThreads, 0, stream>>>(x, ldx, rows, cols, y, ldy);
+    KAGNN_LAUNCH_CHECK();
+    return KAGNN_OK;
+}
+
+extern "C" size_t kagnn_batchnorm_train_workspace(int32_t cols) { return cols > 0 ? (size_t)cols * 2 * sizeof(double) : 0; }
+
+extern "C" int kagnn_batchnorm_train_fwd(const float* x, int64_t ldx, int64_t rows, int32_t cols, const float* weight,
+                                         const float* bias, float eps, float momentum, float* running_mean, float* running_var,
+                                         int32_t act, float* y, int64_t ldy, void* workspace, size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (rows <= 0 || cols <= 0 || !x || !y || ldx < cols || ldy < cols) return KAGNN_EINVAL;
+    if (!workspace || workspace_bytes < kagnn_batchnorm_train_workspace(cols)) return KAGNN_EWORKSPACE;
+    double* sums = static_cast<double*>(workspace);
+    KAGNN_CUDA_TRY(cudaMemsetAsync(sums, 0, (size_t)cols * 2 * sizeof(double), stream));
+    const int64_t rows_per_block = 256;
+    bn_stats_kernel<<<(unsigned)ceil_div64(rows, rows_per_block), 128, 0, stream>>>(x, ldx, rows, cols, rows_per_block, sums);
+    KAGNN_LAUNCH_CHECK();
+    bn_apply_kernel<<<(unsigned)ceil_div64(rows * (int64_t)cols, kThreads), kThreads, 0, stream>>>(
+        x, ldx, rows, cols, sums, weight, bias, eps, momentum, running_mean, running_var, act, y, ldy);
+    KAGNN_LAUNCH_CHECK();
+    return KAGNN_OK;
+}

@@ -43,6 +43,11 @@ def pooled_readout(x: Tensor, batch: Tensor, num_graphs: int, readout: nn.Module
     return out
 
 
+def _bn_unfused(x: Tensor, bn: nn.BatchNorm1d) -> Tensor:
+    from .models_node import _bn_eval
+    return ops.batchnorm_forward(x, bn) if (bn.training or bn.running_mean is None) else _bn_eval(x, bn)
+
+
 class _GINGraphModel(nn.Module):
     """conv -> bn -> dropout, xL; add-pool; KAN readout (shared by KAGIN / FASTKAGIN here and in models_regr)."""
     log_softmax = True
@@ -65,7 +70,7 @@ class _GINGraphModel(nn.Module):
             if fus:
                 x = self._conv(i, x, g, self._folds[i].get(self.bn[i]), extra)
             else:
-                x = self.dropout(self.bn[i](self._conv(i, x, g, None, extra)))
+                x = self.dropout(_bn_unfused(self._conv(i, x, g, None, extra), self.bn[i]))
         return x
 
     def forward(self, data) -> Tensor:
@@ -75,7 +80,7 @@ class _GINGraphModel(nn.Module):
         g = get_graph(data.edge_index, x.size(0))
         x = self._message_passing(x, g)
         x = pooled_readout(x, data.batch, _num_graphs(data), self.kan, mean=False)
-        return F.log_softmax(x, dim=1) if self.log_softmax else x
+        return ops.log_softmax(x) if self.log_softmax else x
 
 
 class KAGIN(_GINGraphModel):
@@ -108,7 +113,9 @@ class _GCNGraphModel(nn.Module):
         drop_off = (not self.training) or self.dropout.p == 0.0
         if not drop_off:
             for i in range(self.n_layers):
-                x = self.dropout(F.silu(self.conv[i](x, g)))
+                c = self.conv[i]
+                act = ops.Affine(shift=None if c.bias is None else c.bias.detach(), act=L.ACT_SILU)
+                x = self.dropout(c.aggregate_transformed(c.transform(x).to(torch.float32), g, extra=act))
             return x
         w, sw = g.gcn_weights()
         t = self.conv[0].transform(x)
@@ -130,7 +137,7 @@ class _GCNGraphModel(nn.Module):
         g = get_graph(data.edge_index, x.size(0))
         x = self._message_passing(x, g)
         x = pooled_readout(x, data.batch, _num_graphs(data), self.readout, mean=self.mean_pool)
-        return F.log_softmax(x, dim=1) if self.log_softmax else x
+        return ops.log_softmax(x) if self.log_softmax else x
 
     def _encode(self, x: Tensor) -> Tensor:
         return x.to(torch.float32)

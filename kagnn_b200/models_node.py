@@ -55,6 +55,13 @@ def bn_is_foldable(bn: nn.BatchNorm1d) -> bool:
     return (not bn.training) and bn.track_running_stats and bn.running_mean is not None
 
 
+def _bn_eval(x: Tensor, bn: nn.BatchNorm1d) -> Tensor:
+    """Eval-mode BatchNorm outside a fused launch (only reached when dropout is active in training mode of a model whose
+    BatchNorm layers are individually in eval mode): y = x * scale + shift through the aggregation-free fused launch."""
+    fold = _BNFold().get(bn)
+    return ops.fused_layer(ops.AggSpec(L.AGG_NONE, x), x.size(0), [], pre=fold)
+
+
 class _NodeModel(nn.Module):
     """Shared forward of GKAN_Nodes / GFASTKAN_Nodes."""
     convs: nn.ModuleList
@@ -105,7 +112,7 @@ class _NodeModel(nn.Module):
         feats = [x]
         for conv, bn in zip(self.convs, self.bns):
             x = conv(x, g)
-            x = bn(x)
+            x = ops.batchnorm_forward(x, bn) if (bn.training or bn.running_mean is None) else _bn_eval(x, bn)
             x = self.dropout(x)
             feats.append(x)
         if self.skip:

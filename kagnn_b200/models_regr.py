@@ -17,7 +17,7 @@ from . import ops
 from .conv import FASTKAGCN_Layer, GINEConv, KAGCN_Layer, make_fastkan, make_kan
 from .ekan import _module_backend_guard
 from .graph import get_graph
-from .models_graph import _GCNGraphModel, _GINGraphModel, _num_graphs, pooled_readout
+from .models_graph import _GCNGraphModel, _GINGraphModel, _bn_unfused, _num_graphs, pooled_readout
 
 Tensor = torch.Tensor
 
@@ -107,7 +107,7 @@ class _GINERegression(_GINGraphModel):
             else:
                 h = conv(h, g, edge_feat, post=post, edge_row=edge_row)
             if not fus:
-                h = self.dropout(self.bn[i](h))
+                h = self.dropout(_bn_unfused(h, self.bn[i]))
         return pooled_readout(h, data.batch, _num_graphs(data), self.kan, mean=False)
 
 

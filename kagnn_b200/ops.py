@@ -172,6 +172,47 @@ def gather_rows(x: Tensor, index: Optional[Tensor], out: Optional[Tensor] = None
     return out
 
 
+def log_softmax(x: Tensor) -> Tensor:
+    """Row-wise log_softmax of (rows, classes) logits (kagnn_log_softmax_rows)."""
+    global launch_count
+    ldx = _rows(x, "x")
+    y = torch.empty(x.size(0), x.size(1), dtype=torch.float32, device=x.device)
+    if x.numel():
+        L.check(L.lib().kagnn_log_softmax_rows(_p(x), ldx, x.size(0), x.size(1), _p(y), _rows(y, "y"), _stream()), "log_softmax")
+        launch_count += 1
+    return y
+
+
+def batchnorm_forward(x: Tensor, bn, act: int = L.ACT_NONE) -> Tensor:
+    """``bn(x)`` of a ``torch.nn.BatchNorm1d`` in training mode (or without running statistics): batch statistics, running
+    estimates updated like torch does (kagnn_batchnorm_train_fwd).  Eval mode with running statistics is folded into the
+    fused kernels' affine epilogue by the models and never comes here."""
+    global launch_count
+    ldx = _rows(x, "x")
+    n, c = x.shape
+    if n == 0:
+        return x.clone()
+    use_batch = bn.training or bn.running_mean is None
+    if not use_batch:
+        raise RuntimeError("eval-mode BatchNorm is folded into the fused layer (models_node._BNFold)")
+    if bn.momentum is None and bn.track_running_stats and bn.running_mean is not None:
+        momentum = 1.0 / float(int(bn.num_batches_tracked) + 1)          # cumulative moving average
+    else:
+        momentum = 0.0 if bn.momentum is None else float(bn.momentum)
+    track = bn.training and bn.track_running_stats and bn.running_mean is not None
+    y = torch.empty(n, c, dtype=torch.float32, device=x.device)
+    wbytes = L.lib().kagnn_batchnorm_train_workspace(c)
+    ws = torch.empty(wbytes, dtype=torch.uint8, device=x.device)
+    L.check(L.lib().kagnn_batchnorm_train_fwd(
+        _p(x), ldx, n, c, _p(bn.weight.detach()) if bn.weight is not None else None, _p(bn.bias.detach()) if bn.bias is not None else None,
+        float(bn.eps), momentum, _p(bn.running_mean) if track else None, _p(bn.running_var) if track else None, act,
+        _p(y), _rows(y, "y"), _p(ws), wbytes, _stream()), "batchnorm_train_fwd")
+    if track:
+        bn.num_batches_tracked += 1
+    launch_count += 3
+    return y
+
+
 def gather_rows_peer(peer_x: Tensor, ldx: int, rows_per_rank: int, ids: Tensor, num_cols: int, out: Optional[Tensor] = None) -> Tensor:
     """out[r] = row ids[r] % rows_per_rank of rank ids[r] // rows_per_rank, pulled over NVLink (kagnn_gather_rows_peer)."""
     global launch_count

@@ -275,3 +275,39 @@ def test_arxiv_scale_model_against_oracle():
     torch.set_num_threads(max(1, torch.get_num_threads()))
     y_ref = K.node_model_forward(_sd_cpu(m), "gin", x, ei, True)
     assert K.rel_err(y, y_ref) <= TOL
+
+
+@pytest.mark.parametrize("rows,cols", [(1, 2), (37, 7), (4096, 40), (5, 300)])
+def test_log_softmax_rows(rows, cols):
+    from kagnn_b200 import ops
+    torch.manual_seed(rows)
+    x = torch.randn(rows, cols) * 5
+    y = ops.log_softmax(x.cuda()).cpu()
+    assert torch.allclose(y, torch.log_softmax(x, dim=1), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("rows,cols,affine", [(2, 3, True), (1000, 64, True), (50_000, 32, False), (777, 130, True)])
+def test_batchnorm_training_forward_matches_torch(rows, cols, affine):
+    """Training-mode BatchNorm1d (node_classification_clean/models.py:197 under model.train()): output, running statistics
+    and num_batches_tracked against torch.nn.BatchNorm1d on the CPU."""
+    from kagnn_b200 import ops
+    torch.manual_seed(cols)
+    x = torch.randn(rows, cols) * 2 + 0.5
+    ref = torch.nn.BatchNorm1d(cols, affine=affine)
+    if affine:
+        with torch.no_grad():
+            ref.weight.uniform_(0.5, 1.5)
+            ref.bias.normal_()
+    mine = torch.nn.BatchNorm1d(cols, affine=affine)
+    mine.load_state_dict(ref.state_dict())
+    mine = mine.cuda()
+    ref.train()
+    mine.train()
+    for _ in range(2):
+        with torch.no_grad():
+            y_ref = ref(x)
+            y = ops.batchnorm_forward(x.cuda(), mine).cpu()
+    assert K.rel_err(y, y_ref) <= TOL
+    assert torch.allclose(mine.running_mean.cpu(), ref.running_mean, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(mine.running_var.cpu(), ref.running_var, rtol=1e-5, atol=1e-6)
+    assert int(mine.num_batches_tracked) == int(ref.num_batches_tracked) == 2
