@@ -53,6 +53,11 @@ constexpr int BM = 128;
 #ifndef KAGNN_TC2_GATHER_U
 #define KAGNN_TC2_GATHER_U 16           // 128-bit row loads in flight per gather warp
 #endif
+#ifndef KAGNN_TC2_PREFETCH_DIST
+#define KAGNN_TC2_PREFETCH_DIST 0        // tiles an L2 prefetch warp may run ahead of the gather; 0 = off (default: measured on the
+                                         // bench, distance 3 makes the GIN layers 8 % SLOWER -- the extra requests cost more than the
+                                         // DRAM latency they hide; through cp.async.bulk.prefetch they also delay the W loader, 1.7x)
+#endif
 #ifndef KAGNN_TC2_NPW
 #define KAGNN_TC2_NPW 16
 #endif
@@ -605,6 +610,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
     float* post_sc = reinterpret_cast<float*>(tmem_slot + 2);     // post-affine of the last layer (<= 128 columns each)
     float* post_sh = post_sc + 128;
+    volatile int* gather_progress = reinterpret_cast<volatile int*>(post_sh + 128);   // tiles the gather warps have started
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (warp == WARP_MMA) tc::tmem_alloc(tmem_slot, 512);
@@ -620,6 +626,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
         tc::mbar_init(acc_full, 1);
         tc::mbar_fence_init();
     }
+    if (tid == 0) *gather_progress = 0;
     if (tid >= 128 && tid < 256) {
         const int c = tid - 128;
         const bool on = p.has_post && c < p.layers[p.n_layers - 1].N;
@@ -847,8 +854,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
         const bool plain_copy = p.agg.mode == KAGNN_AGG_NONE && !p.has_pre && !p.agg_out && !p.agg.src_index;
         const int F_pad = p.layers[0].F_pad;
         uint32_t uc = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
             const long long row0 = (long long)tile * BM;
+            if (gw == 0 && lane == 0) *gather_progress = it;          // paces the L2 prefetch warp
             for (int ub = 0; ub < p.units_per_tile; ++ub, ++uc) {
                 const int u = (int)(uc % (uint32_t)p.n_units);
                 if (lane == 0 && gw == 0) TRL(6, uc, 0);
@@ -926,6 +935,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
     } else {
         // ========================================== W LOADER (+ two idle warps) ================================
         if (NPW == 16) tc::reg_dec<40>();
+        if (warp == WARP_LOAD + 1 && KAGNN_TC2_PREFETCH_DIST > 0) {
+            // ------------------------------------ L2 PREFETCHER ------------------------------------------------
+            // One otherwise idle warp walks the CSR a few tiles ahead of the gather warps and asks L2 for the self and
+            // neighbour rows (cp.async.bulk.prefetch.L2, one instruction per row), so that the gather's loads of a cold
+            // feature matrix (first touch after the previous layer / an L2 flush) hit L2 instead of paying DRAM latency.
+            const KagnnAggregate& a = p.agg;
+            const bool csr = a.mode == KAGNN_AGG_GIN || a.mode == KAGNN_AGG_WEIGHTED || a.mode == KAGNN_AGG_GINE;
+            const uint32_t row_bytes = (uint32_t)a.num_cols * 4u;
+            const bool ok = csr && !a.peer_x && !a.src_index && (a.num_cols % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.x) & 15u) == 0) &&
+                            (a.ldx % 4 == 0) && (!a.x_halo || (((reinterpret_cast<uintptr_t>(a.x_halo) & 15u) == 0) && (a.ld_halo % 4 == 0)));
+            if (ok) {
+                int it = 0;
+                for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+                    uint32_t naps = 0;
+                    while (it > *gather_progress + KAGNN_TC2_PREFETCH_DIST && ++naps < (1u << 20)) __nanosleep(256);
+                    const long long row0 = (long long)tile * BM;
+                    const long long row1 = min(row0 + (long long)BM, p.num_rows);
+                    for (long long r = row0 + lane; r < row1; r += 32) tc::prefetch_l2(a.x + r * a.ldx, row_bytes);
+                    const int beg = __ldg(a.rowptr + row0), end = __ldg(a.rowptr + row1);
+                    for (int e = beg + lane; e < end; e += 32) tc::prefetch_l2(src_row(a, __ldg(a.col + e)), row_bytes);
+                }
+            }
+        }
         if (warp == WARP_LOAD && lane == 0) {
             uint32_t cq = 0, par = 1;
             int s = 0;
@@ -1024,7 +1056,7 @@ int kagnn_fused_fwd_tc2(const KagnnAggregate* agg, int64_t num_rows, const Kagnn
     p.unit_floats = BM * p.xld;
     p.units_per_tile = (F_pad0 + p.uw - 1) / p.uw;
     p.bstage_bytes = 256 * n_max;
-    const int tail = KAGNN_MAX_LAYERS * LUT_ROWS * 16 + (2 * MAX_UNITS + 2 * MAX_STAGE + 2) * 8 + 2 * 128 * 4;
+    const int tail = KAGNN_MAX_LAYERS * LUT_ROWS * 16 + (2 * MAX_UNITS + 2 * MAX_STAGE + 2) * 8 + 2 * 128 * 4 + 16;
     const int unit_bytes = p.unit_floats * (int)sizeof(float);
     // ring depths: at least 2 x-units and 2 stages; prefer deeper stages, then more units
     int best_units = 0, best_ns = 0;
