@@ -58,6 +58,9 @@ constexpr int BM = 128;
                                          // bench, distance 3 makes the GIN layers 8 % SLOWER -- the extra requests cost more than the
                                          // DRAM latency they hide; through cp.async.bulk.prefetch they also delay the W loader, 1.7x)
 #endif
+#ifndef KAGNN_TC2_BAL
+#define KAGNN_TC2_BAL 1
+#endif
 #ifndef KAGNN_TC2_NPW
 #define KAGNN_TC2_NPW 16
 #endif
@@ -187,9 +190,22 @@ __device__ __forceinline__ void bspline_slots(float inv_h, float c0, float limp,
     // every value is >= 0, so hi = truncation to bf16 and lo = bf16(b - hi) are >= 0 too: their sign bits are 0, which
     // lets the byte-permute synthesise the zero slots by sign replication (selector nibble 9)
     const uint32_t h01 = pack_trunc(b0, b1), h23 = pack_trunc(b2, b3);
+#if KAGNN_TC2_BAL
+    // residuals from the packed hi words: the even element's hi is a left shift (fma pipe), the odd one's a mask (alu pipe);
+    // the LUT row address is one multiply-add on the float's bit pattern -- both move work off the busier alu pipe
+    const uint32_t l01 = pack_rn(b0 - __uint_as_float(h01 << 16), b1 - __uint_as_float(h01 & 0xffff0000u));
+    const uint32_t l23 = (K >= 2) ? pack_rn(b2 - __uint_as_float(h23 << 16), b3 - __uint_as_float(h23 & 0xffff0000u)) : 0u;
+    uint4 sel;
+    {
+        const uint32_t addr = __float_as_uint(t) * 16u + (tc::smem_u32(lut) - (uint32_t)((0x4B400000u - 1u) * 16u));
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(sel.x), "=r"(sel.y), "=r"(sel.z), "=r"(sel.w) : "r"(addr));
+        (void)idx;
+    }
+#else
     const uint32_t l01 = pack_rn(trunc_residual(b0), trunc_residual(b1));
     const uint32_t l23 = (K >= 2) ? pack_rn(trunc_residual(b2), trunc_residual(b3)) : 0u;
     const uint4 sel = lut[idx];
+#endif
     hi[0] = prmt(h01, h23, sel.x);
     hi[1] = prmt(h01, h23, sel.y);
     hi[2] = prmt(h01, h23, sel.z);
@@ -607,8 +623,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
     uint64_t* full = bars + 2 * MAX_UNITS;        // A stage written by all producers AND W chunk landed (one wait for the MMA)
     uint64_t* empty = full + MAX_STAGE;
     uint64_t* acc_full = empty + MAX_STAGE;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
-    float* post_sc = reinterpret_cast<float*>(tmem_slot + 2);     // post-affine of the last layer (<= 128 columns each)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 2);       // acc_full[region]: one barrier per accumulator region
+    float* post_sc = reinterpret_cast<float*>(tmem_slot + 4);     // post-affine of the last layer (<= 128 columns each; 16-byte aligned)
     float* post_sh = post_sc + 128;
     volatile int* gather_progress = reinterpret_cast<volatile int*>(post_sh + 128);   // tiles the gather warps have started
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -623,7 +639,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
             tc::mbar_init(&full[s], FULL_ARRIVALS);
             tc::mbar_init(&empty[s], 1);
         }
-        tc::mbar_init(acc_full, 1);
+        tc::mbar_init(&acc_full[0], 1);
+        tc::mbar_init(&acc_full[1], 1);
         tc::mbar_fence_init();
     }
     if (tid == 0) *gather_progress = 0;
@@ -666,9 +683,56 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
         const int row = tid & 127;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         uint32_t cq = 0, lc = 0, uc0 = 0;                  // running chunk / layer / unit counters
+        // ---- epilogue of a tile's last layer: TMEM -> registers -> post-affine -> y.  Software-pipelined: it runs AFTER the
+        // basis production of the NEXT tile's first layer (which writes the other accumulator region), so the wait for the
+        // last MMAs, the TMEM reads and the stores overlap the tensor-core work already queued for the next tile.
+        auto epilogue = [&](long long e_row0, uint32_t e_lc) {
+            const LayerT2& L = p.layers[p.n_layers - 1];
+            const int nrows = (int)min((long long)BM, p.num_rows - e_row0);
+            if (lane == 0 && (warp & 3) == 0 && wg < 2) TRL(4 + wg, e_lc, 2);
+            tc::mbar_wait(&acc_full[(e_lc - 1) & 1], ((e_lc - 1) >> 1) & 1);
+            if (lane == 0 && (warp & 3) == 0 && wg < 2) TRL(4 + wg, e_lc, 3);
+            tc::tc_fence_after_sync();
+            const uint32_t taddr = tmem_base + lane_base + (((e_lc - 1) & 1) ? 128u : 0u);
+            float* yrow = p.y + (e_row0 + row) * p.ldy;
+            for (int jb = wg; jb < L.N_pad / 8; jb += NWG) {
+                float v[8];
+                tc::tmem_ld8(taddr + (uint32_t)(8 * jb), v);
+                if (L.stack) {
+                    float v2[8];
+                    tc::tmem_ld8(taddr + (uint32_t)(L.N_pad + 8 * jb), v2);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] += v2[i];
+                }
+                if (row < nrows) {
+                    if (p.has_post) {
+                        const float4 s0 = *reinterpret_cast<const float4*>(post_sc + 8 * jb), s1 = *reinterpret_cast<const float4*>(post_sc + 8 * jb + 4);
+                        const float4 h0 = *reinterpret_cast<const float4*>(post_sh + 8 * jb), h1 = *reinterpret_cast<const float4*>(post_sh + 8 * jb + 4);
+                        v[0] = fmaf(v[0], s0.x, h0.x); v[1] = fmaf(v[1], s0.y, h0.y); v[2] = fmaf(v[2], s0.z, h0.z); v[3] = fmaf(v[3], s0.w, h0.w);
+                        v[4] = fmaf(v[4], s1.x, h1.x); v[5] = fmaf(v[5], s1.y, h1.y); v[6] = fmaf(v[6], s1.z, h1.z); v[7] = fmaf(v[7], s1.w, h1.w);
+                        if (p.post.act == KAGNN_ACT_SILU) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[i] = silu_f(v[i]);
+                        }
+                    }
+                    if (p.y_vec && 8 * jb + 8 <= L.N) {
+                        *reinterpret_cast<float4*>(yrow + 8 * jb) = make_float4(v[0], v[1], v[2], v[3]);
+                        *reinterpret_cast<float4*>(yrow + 8 * jb + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            if (8 * jb + i < L.N) yrow[8 * jb + i] = v[i];
+                    }
+                }
+            }
+            tc::tc_fence_before_sync();
+            if (lane == 0 && (warp & 3) == 0 && wg < 2) TRL(4 + wg, e_lc, 4);
+        };
+        long long pend_row0 = 0;
+        uint32_t pend_lc = 0;
+        bool have_pend = false;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             const long long row0 = (long long)tile * BM;
-            const int nrows = (int)min((long long)BM, p.num_rows - row0);
             for (int l = 0; l < p.n_layers; ++l, ++lc) {
                 const LayerT2& L = p.layers[l];
                 const float inv_h = L.inv_h, c0f = L.c0, limp = L.lim + 0.5f;
@@ -679,7 +743,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                 const float* xrow = nullptr;
                 if (l > 0) {
                     if (lane == 0 && (warp & 3) == 0 && wg < 2) TRL(4 + wg, lc, 0);
-                    tc::mbar_wait(acc_full, (lc - 1) & 1);
+                    tc::mbar_wait(&acc_full[(lc - 1) & 1], ((lc - 1) >> 1) & 1);
                     if (lane == 0 && (warp & 3) == 0 && wg < 2) TRL(4 + wg, lc, 1);
                     tc::tc_fence_after_sync();
                     src_t = tmem_base + lane_base + (((lc - 1) & 1) ? 128u : 0u);
@@ -688,6 +752,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                 int s = (int)(cq % (uint32_t)p.ns);
                 uint32_t par = ((cq / (uint32_t)p.ns) & 1u) ^ 1u;
                 bool unit_ready = false;
+                // Deferred hand-over: the arrive on full[] of a chunk is issued only after the NEXT chunk's basis math, so the
+                // latency of the tcgen05.st stores (tcgen05.wait::st) hides behind useful work instead of ending every chunk.
+                int pending = -1;
+                auto flush_pending = [&]() {
+                    if (pending >= 0) {
+                        tc::tmem_st_wait();
+                        tc::tc_fence_before_sync();
+                        tc::mbar_arrive(&full[pending]);
+                        pending = -1;
+                    }
+                };
                 ChunkCursor c(L.F_pad);
                 for (int q = 0; q < n_chunks; ++q, c.next()) {
                     if (l == 0 && c.j == 0) {
@@ -749,10 +824,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                                 uint32_t hi[8], lo[8];
                                 bspline_slots<K>(inv_h, c0f, limp, lutL, v[i], hi, lo);
                                 bspline_slots<K>(inv_h, c0f, limp, lutL, v[i + 1], hi + 4, lo + 4);
+                                if (i == 0) flush_pending();          // the previous chunk's TMEM stores drained behind this math
                                 tc::tmem_st8(a_t + 4u * (uint32_t)(fsh + i), hi);
                                 tc::tmem_st8(a_t + 32u + 4u * (uint32_t)(fsh + i), lo);
                             }
                         } else {
+                            flush_pending();
 #pragma unroll 1
                             for (int jj = OWN ? 0 : wg; jj < c.n_oct; jj += OWN ? 1 : NWG) {
                                 const int f0 = 64 * c.group + 8 * jj;
@@ -782,65 +859,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                                              pack_rn(r[6], r[7]));
                             }
                         }
-                        if (lane == 0 && (warp & 3) == 0 && wg < 2) TRC(wg, cq + q, 6);
-                        tc::tmem_st_wait();
-                        if (lane == 0 && (warp & 3) == 0 && wg < 2) TRC(wg, cq + q, 7);
-                        tc::tc_fence_before_sync();
-                        tc::mbar_arrive(&full[s]);
+                        pending = s;                              // arrive on full[s] once these stores have drained
+                        if (OWN) flush_pending();                 // (a warpgroup's next own chunk may depend on this one)
                         if (lane == 0 && (warp & 3) == 0 && wg < 2) TRC(wg, cq + q, 4);
                     }
                     if (++s == p.ns) { s = 0; par ^= 1u; }
                 }
+                flush_pending();
                 cq += (uint32_t)n_chunks;
                 if (l == 0) {
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(&xs_empty[(uc0 + cur_unit) % p.n_units]);
                     uc0 += (uint32_t)p.units_per_tile;
-                }
-            }
-            // ---- epilogue of the last layer: TMEM -> registers -> post-affine -> y -------------------------------
-            {
-                const LayerT2& L = p.layers[p.n_layers - 1];
-                if (lane == 0 && (warp & 3) == 0 && wg < 2) TRL(4 + wg, lc, 2);
-                tc::mbar_wait(acc_full, (lc - 1) & 1);
-                if (lane == 0 && (warp & 3) == 0 && wg < 2) TRL(4 + wg, lc, 3);
-                tc::tc_fence_after_sync();
-                const uint32_t taddr = tmem_base + lane_base + (((lc - 1) & 1) ? 128u : 0u);
-                float* yrow = p.y + (row0 + row) * p.ldy;
-                for (int jb = wg; jb < L.N_pad / 8; jb += NWG) {
-                    float v[8];
-                    tc::tmem_ld8(taddr + (uint32_t)(8 * jb), v);
-                    if (L.stack) {
-                        float v2[8];
-                        tc::tmem_ld8(taddr + (uint32_t)(L.N_pad + 8 * jb), v2);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) v[i] += v2[i];
-                    }
-                    if (row < nrows) {
-                        if (p.has_post) {
-                            const float4 s0 = *reinterpret_cast<const float4*>(post_sc + 8 * jb), s1 = *reinterpret_cast<const float4*>(post_sc + 8 * jb + 4);
-                            const float4 h0 = *reinterpret_cast<const float4*>(post_sh + 8 * jb), h1 = *reinterpret_cast<const float4*>(post_sh + 8 * jb + 4);
-                            v[0] = fmaf(v[0], s0.x, h0.x); v[1] = fmaf(v[1], s0.y, h0.y); v[2] = fmaf(v[2], s0.z, h0.z); v[3] = fmaf(v[3], s0.w, h0.w);
-                            v[4] = fmaf(v[4], s1.x, h1.x); v[5] = fmaf(v[5], s1.y, h1.y); v[6] = fmaf(v[6], s1.z, h1.z); v[7] = fmaf(v[7], s1.w, h1.w);
-                            if (p.post.act == KAGNN_ACT_SILU) {
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) v[i] = silu_f(v[i]);
-                            }
-                        }
-                        if (p.y_vec && 8 * jb + 8 <= L.N) {
-                            *reinterpret_cast<float4*>(yrow + 8 * jb) = make_float4(v[0], v[1], v[2], v[3]);
-                            *reinterpret_cast<float4*>(yrow + 8 * jb + 4) = make_float4(v[4], v[5], v[6], v[7]);
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                if (8 * jb + i < L.N) yrow[8 * jb + i] = v[i];
-                        }
+                    if (have_pend) {                       // previous tile's epilogue, behind this tile's first layer
+                        epilogue(pend_row0, pend_lc);
+                        have_pend = false;
                     }
                 }
-                tc::tc_fence_before_sync();
-                if (lane == 0 && (warp & 3) == 0 && wg < 2) TRL(4 + wg, lc, 4);
             }
+            pend_row0 = row0;
+            pend_lc = lc;
+            have_pend = true;
         }
+        if (have_pend) epilogue(pend_row0, pend_lc);
     } else if (warp < NPW + NGW) {
         // ========================================= GATHER ======================================================
         if (NPW == 16) tc::reg_inc<104>();
@@ -924,7 +965,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                             }
                         }
                         tc::umma_commit(&empty[s]);
-                        if (q == n_chunks - 1) tc::umma_commit(acc_full);
+                        if (q == n_chunks - 1) tc::umma_commit(&acc_full[lc & 1]);
                     }
                     __syncwarp();
                     if (lane == 0) TRC(2, cq, 3);
@@ -1056,7 +1097,8 @@ int kagnn_fused_fwd_tc2(const KagnnAggregate* agg, int64_t num_rows, const Kagnn
     p.unit_floats = BM * p.xld;
     p.units_per_tile = (F_pad0 + p.uw - 1) / p.uw;
     p.bstage_bytes = 256 * n_max;
-    const int tail = KAGNN_MAX_LAYERS * LUT_ROWS * 16 + (2 * MAX_UNITS + 2 * MAX_STAGE + 2) * 8 + 2 * 128 * 4 + 16;
+    // LUTs | mbarriers (x ring full/empty, stage full/empty, 2 accumulator) | tmem slot (16 B) | post scale/shift | progress word
+    const int tail = KAGNN_MAX_LAYERS * LUT_ROWS * 16 + (2 * MAX_UNITS + 2 * MAX_STAGE + 2) * 8 + 16 + 2 * 128 * 4 + 16;
     const int unit_bytes = p.unit_floats * (int)sizeof(float);
     // ring depths: at least 2 x-units and 2 stages; prefer deeper stages, then more units
     int best_units = 0, best_ns = 0;
