@@ -7,7 +7,7 @@
 
 namespace {
 std::atomic<int> g_path_mode{KAGNN_PATH_AUTO};
-std::atomic<long long> g_count_tc{0}, g_count_fp32{0}, g_count_tc2{0};
+std::atomic<long long> g_count_tc{0}, g_count_fp32{0}, g_count_tc2{0}, g_count_agg{0};
 std::atomic<int> g_tc_variant{0};   // 0 = auto, 1 = only the shared-memory-A kernel (fused_tc.cu); tests/benchmarks
 }  // namespace
 
@@ -91,6 +91,15 @@ extern "C" int kagnn_fused_layer_fwd(const KagnnAggregate* agg, int64_t num_rows
         }
     } else if (mode == KAGNN_PATH_TC && n_layers >= 1 && num_rows > 0) {
         return KAGNN_EUNSUPPORTED;
+    }
+    if (n_layers == 0 && num_rows > 0 && mode != KAGNN_PATH_FP32) {
+        // aggregation only: the high-MLP flattened-list gather (fused_tc2.cu) when the shape allows, else the general kernel
+        int rc = kagnn_aggregate_only_tc2(agg, num_rows, pre, agg_out, ld_agg_out, stream);
+        if (rc == KAGNN_OK) {
+            g_count_agg.fetch_add(1);
+            return rc;
+        }
+        if (rc != KAGNN_EUNSUPPORTED) return rc;
     }
     if (agg->peer_x || agg->num_head_cols) return KAGNN_EUNSUPPORTED;
     int rc = kagnn_fused_fwd_fp32(agg, num_rows, pre, agg_out, ld_agg_out, n_layers, layers, post, y, ldy, stream);

@@ -436,7 +436,7 @@ __device__ float g_zero_row[4096];
 //   * the column index / edge weight of the NEXT batch of 32 entries are fetched before the current batch is consumed;
 //   * a finished row is parked raw (one STS.128); mean scale, pre-affine and the agg_out store run in a post-pass over
 //     the warp's 16 rows only when the layer has any of them (a plain GIN layer has none).
-template <bool WEIGHTED>
+template <bool WEIGHTED, bool GOUT = false>      // GOUT: rows are parked in GLOBAL memory (aggregation-only launch): bounds-checked
 __device__ __forceinline__ void gather_unit_fast(const Tc2Params& p, long long row0, int c0, int ucols, float* __restrict__ xsu,
                                                  int gw, int lane) {
     constexpr int U = KAGNN_TC2_GATHER_U;
@@ -462,9 +462,9 @@ __device__ __forceinline__ void gather_unit_fast(const Tc2Params& p, long long r
     float* const dst0 = xsu + rl0 * xld + cl;
 
     auto finish_row = [&]() {
-        if (cin0) {
+        if (GOUT ? (cv0 && row0 + rl0 + cur < p.num_rows) : cin0) {
             const float4 o = cv0 ? make_float4(acc[0], acc[1], acc[2], acc[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
-            *reinterpret_cast<float4*>(dst0 + cur * xld) = o;
+            *reinterpret_cast<float4*>(dst0 + (long long)cur * xld) = o;
         }
         acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
         ++cur;
@@ -566,7 +566,7 @@ __device__ __forceinline__ void gather_unit_fast(const Tc2Params& p, long long r
     while (cur < RPW) finish_row();
 
     const bool pre_silu = p.has_pre && p.pre.act == KAGNN_ACT_SILU;
-    if (p.has_pre || p.agg_out || mode == KAGNN_AGG_SEGMENT_MEAN) {
+    if (p.has_pre || (!GOUT && p.agg_out) || mode == KAGNN_AGG_SEGMENT_MEAN) {
         // post-pass: every lane revisits the values it parked itself (no synchronisation needed)
         float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.has_pre && cv0) {
@@ -588,8 +588,8 @@ __device__ __forceinline__ void gather_unit_fast(const Tc2Params& p, long long r
             float os = 1.0f;
             if (mode == KAGNN_AGG_SEGMENT_MEAN)
                 os = 1.0f / (float)max(__shfl_sync(0xffffffffu, rp, rr + 1) - __shfl_sync(0xffffffffu, rp, rr), 1);
-            if (!cin0) continue;
-            float4 t = *reinterpret_cast<const float4*>(dst0 + rr * xld);
+            if (GOUT ? !(cv0 && rv) : !cin0) continue;
+            float4 t = *reinterpret_cast<const float4*>(dst0 + (long long)rr * xld);
             float o[4] = {t.x * os, t.y * os, t.z * os, t.w * os};
             const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
 #pragma unroll
@@ -600,8 +600,8 @@ __device__ __forceinline__ void gather_unit_fast(const Tc2Params& p, long long r
                 }
                 if (!(cv0 && rv)) o[i] = 0.f;
             }
-            *reinterpret_cast<float4*>(dst0 + rr * xld) = make_float4(o[0], o[1], o[2], o[3]);
-            if (p.agg_out && rv && cv0) {
+            *reinterpret_cast<float4*>(dst0 + (long long)rr * xld) = make_float4(o[0], o[1], o[2], o[3]);
+            if (!GOUT && p.agg_out && rv && cv0) {
                 float* g = p.agg_out + r * p.ld_agg_out + c0 + cl;
                 if (out_vec) *reinterpret_cast<float4*>(g) = make_float4(o[0], o[1], o[2], o[3]);
                 else { g[0] = o[0]; g[1] = o[1]; g[2] = o[2]; g[3] = o[3]; }
@@ -1028,9 +1028,54 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
     if (warp == WARP_MMA) tc::tmem_dealloc(tmem_base, 512);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Aggregation-only launch (n_layers == 0: the last layer of a GCN-flavour model, a stand-alone GCNConv after its KAN, pooling
+// without a readout): the same flattened-list gather, one warp per 16 destination rows, result (after mean scale / pre-affine)
+// written straight to agg_out.  HBM-bound: 16 independent 128-bit row loads in flight per warp, grid = all row groups.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int AGG_WARPS = 8;
+__global__ void __launch_bounds__(AGG_WARPS * 32) aggregate_only_kernel(const __grid_constant__ Tc2Params p) {
+    const int lane = threadIdx.x & 31;
+    const long long group = (long long)blockIdx.x * AGG_WARPS + (threadIdx.x >> 5);      // 16 rows each
+    const long long row0 = group * RPW;
+    if (row0 >= p.num_rows) return;
+    const int F = p.agg.num_cols;
+    for (int c0 = 0; c0 < F; c0 += 128) {
+        float* out = p.agg_out + row0 * p.ld_agg_out + c0;
+        const int ucols = min(128, F - c0);
+        if (p.agg.mode == KAGNN_AGG_WEIGHTED) gather_unit_fast<true, true>(p, row0, c0, ucols, out, 0, lane);
+        else gather_unit_fast<false, true>(p, row0, c0, ucols, out, 0, lane);
+    }
+}
+
 inline int ceil16(int v) { return (v + 15) & ~15; }
 
 }  // namespace
+
+int kagnn_aggregate_only_tc2(const KagnnAggregate* agg, int64_t num_rows, const KagnnAffine* pre, float* agg_out,
+                             int64_t ld_agg_out, cudaStream_t stream) {
+    // shapes the 128-bit flattened-list gather serves; everything else stays on the general kernel
+    if (!agg_out || agg->mode == KAGNN_AGG_GINE || agg->num_head_cols || agg->num_cols > 4096) return KAGNN_EUNSUPPORTED;
+    if (agg->num_cols % 4 != 0 || !aligned16(agg->x) || agg->ldx % 4 != 0 || !aligned16(agg_out) || ld_agg_out % 4 != 0)
+        return KAGNN_EUNSUPPORTED;
+    if (agg->x_halo && (!aligned16(agg->x_halo) || agg->ld_halo % 4 != 0)) return KAGNN_EUNSUPPORTED;
+    if (agg->peer_x && agg->rows_per_rank * (int64_t)agg->num_ranks > (int64_t)INT32_MAX) return KAGNN_EUNSUPPORTED;
+    if (agg->mode == KAGNN_AGG_NONE && !pre && !agg->src_index) return KAGNN_EUNSUPPORTED;      // a plain copy: not worth a gather
+    Tc2Params p{};
+    p.agg = *agg;
+    p.has_pre = pre != nullptr;
+    if (pre) p.pre = *pre;
+    p.num_rows = num_rows;
+    p.agg_out = agg_out;
+    p.ld_agg_out = ld_agg_out;
+    p.xld = (int)ld_agg_out;
+    if (ld_agg_out > (int64_t)INT32_MAX) return KAGNN_EUNSUPPORTED;
+    const long long groups = ceil_div64(num_rows, RPW);
+    const unsigned blocks = (unsigned)ceil_div64(groups, AGG_WARPS);
+    aggregate_only_kernel<<<blocks, AGG_WARPS * 32, 0, stream>>>(p);
+    KAGNN_LAUNCH_CHECK();
+    return KAGNN_OK;
+}
 
 int kagnn_fused_fwd_tc2(const KagnnAggregate* agg, int64_t num_rows, const KagnnAffine* pre, float* agg_out,
                         int64_t ld_agg_out, int32_t n_layers, const KagnnKanLayer* layers, const KagnnAffine* post, float* y,
