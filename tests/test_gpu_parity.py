@@ -311,3 +311,53 @@ def test_batchnorm_training_forward_matches_torch(rows, cols, affine):
     assert torch.allclose(mine.running_mean.cpu(), ref.running_mean, rtol=1e-5, atol=1e-6)
     assert torch.allclose(mine.running_var.cpu(), ref.running_var, rtol=1e-5, atol=1e-6)
     assert int(mine.num_batches_tracked) == int(ref.num_batches_tracked) == 2
+
+
+@pytest.mark.parametrize("head,tail,out_f", [(128, 192, 40), (256, 64, 16), (100, 60, 8), (128, 3, 5)])
+def test_two_part_rows_match_concatenation(head, tail, out_f):
+    """KagnnAggregate.x_head: lay_out over [x | hidden] without materialising the concat (and the host-side fallback when
+    the split is not on a 128-column boundary) == the oracle on torch.cat."""
+    import kagnn_b200 as kb
+    from kagnn_b200 import ops, _lib as L
+    torch.manual_seed(head + tail)
+    n = 777
+    a, b = torch.randn(n, head) * 0.7, torch.randn(n, tail) * 0.7
+    m = kb.KANLinear(head + tail, out_f, grid_size=5, spline_order=3)
+    y_ref = K._kan_layer_from_sd(_sd_cpu(m), "", torch.cat([a, b], 1))
+    m = m.cuda()
+    big = torch.zeros(n, tail + 5).cuda()                 # b as a column slice (leading dimension > width)
+    big[:, :tail] = b.cuda()
+    with torch.no_grad():
+        y = ops.fused_layer(ops.AggSpec(L.AGG_NONE, big[:, :tail], x_head=a.cuda()), n, m.kernel_specs()).cpu()
+    assert K.rel_err(y, y_ref) <= TOL
+
+
+@pytest.mark.parametrize("n,e,f", [(1000, 7000, 128), (333, 900, 64), (50, 0, 32), (4097, 30000, 36), (200, 1500, 30)])
+def test_aggregation_only_launches(n, e, f):
+    """n_layers == 0: GIN sum, GCN-weighted sum with bias + SiLU, mean pooling -- 128-bit gather kernel for aligned shapes,
+    general kernel otherwise (f = 30) -- against plain index arithmetic on the CPU."""
+    from kagnn_b200 import ops, _lib as L
+    from kagnn_b200.graph import get_graph
+    torch.manual_seed(n + f)
+    x = torch.randn(n, f)
+    ei = torch.randint(0, n, (2, e))
+    g = get_graph(ei.cuda(), n)
+    xd = x.cuda()
+    # GIN: (1 + eps) x_i + sum_j x_j
+    y = ops.fused_layer(ops.AggSpec(L.AGG_GIN, xd, g.rowptr, g.col, self_scale=1.25), n, []).cpu()
+    ref = 1.25 * x + torch.zeros(n, f).index_add_(0, ei[1], x[ei[0]])
+    assert K.rel_err(y, ref) <= 1e-5
+    # GCN: normalised sum + bias, SiLU
+    w, sw = g.gcn_weights()
+    bias = torch.randn(f)
+    y = ops.fused_layer(ops.AggSpec(L.AGG_WEIGHTED, xd, g.rowptr, g.col, edge_weight=w, self_weight=sw), n, [],
+                        pre=ops.Affine(shift=bias.cuda(), act=L.ACT_SILU)).cpu()
+    ref = torch.nn.functional.silu(K.gcn_conv(x, ei, lambda t: t, bias))
+    assert K.rel_err(y, ref) <= 1e-5
+    # mean pooling over sorted segments (some empty)
+    nb = 17
+    batch = torch.sort(torch.randint(0, nb, (n,)))[0]
+    ptr = ops.segment_ptr(batch.cuda(), nb)
+    y = ops.fused_layer(ops.AggSpec(L.AGG_SEGMENT_MEAN, xd, rowptr=ptr), nb, []).cpu()
+    ref = torch.zeros(nb, f).index_add_(0, batch, x) / torch.bincount(batch, minlength=nb).clamp(min=1).unsqueeze(1)
+    assert K.rel_err(y, ref) <= 1e-5
