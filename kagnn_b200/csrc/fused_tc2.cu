@@ -429,6 +429,16 @@ __device__ __forceinline__ void gather_unit(const Tc2Params& p, long long row0, 
 // point here, so every load of a sub-batch is unconditional and the U loads are all in flight together.
 __device__ float g_zero_row[4096];
 
+// Degree skew (R-MAT hubs): a destination row with more than HUB_T incoming entries would serialise on the one warp that owns
+// it.  Such rows are left out of the owner's flattened list (only the self term is parked) and are then summed COOPERATIVELY:
+// each of the NGW gather warps of the tile takes a contiguous 1/NGW slice of the row's CSR entries, the partial sums meet in
+// this shared scratch, and the owner adds them in warp order (deterministic, no atomics).
+constexpr int HUB_T = 512;
+struct HubScratch {
+    float part[NGW][128];
+};
+__device__ __forceinline__ void gather_warps_barrier() { asm volatile("bar.sync 2, %0;" ::"n"(NGW * 32) : "memory"); }
+
 // Fast gather (128-bit path, no edge features): same flattened list as gather_unit, restructured for memory-level
 // parallelism and a short instruction stream:
 //   * every entry of a sub-batch is loaded unconditionally from a valid address (missing entries -> g_zero_row with
@@ -438,7 +448,7 @@ __device__ float g_zero_row[4096];
 //     the warp's 16 rows only when the layer has any of them (a plain GIN layer has none).
 template <bool WEIGHTED, bool GOUT = false>      // GOUT: rows are parked in GLOBAL memory (aggregation-only launch): bounds-checked
 __device__ __forceinline__ void gather_unit_fast(const Tc2Params& p, long long row0, int c0, int ucols, float* __restrict__ xsu,
-                                                 int gw, int lane) {
+                                                 int gw, int lane, HubScratch* hub = nullptr) {
     constexpr int U = KAGNN_TC2_GATHER_U;
     const KagnnAggregate& a = p.agg;
     const int F = a.num_cols, mode = a.mode, xld = p.xld;
@@ -455,11 +465,49 @@ __device__ __forceinline__ void gather_unit_fast(const Tc2Params& p, long long r
         if (r > p.num_rows) r = p.num_rows;
         rp = __ldg(a.rowptr + r);
     }
-    const int vs = rp + self1 * min(lane, RPW);
-    const int v_beg = __shfl_sync(0xffffffffu, vs, 0), v_end = __shfl_sync(0xffffffffu, vs, RPW);
+    // hub rows of the whole 128-row tile (every gather warp computes the same four ballots, so no communication is needed to
+    // agree on them); my own hub rows contribute only their self entry to the flattened list
+    uint32_t tile_hub[4] = {0u, 0u, 0u, 0u};
+    bool any_hub = false;
+    if (hub != nullptr && !segment && mode != KAGNN_AGG_NONE) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const long long r = row0 + 32 * k + lane;
+            int d = 0;
+            if (r < p.num_rows) d = __ldg(a.rowptr + r + 1) - __ldg(a.rowptr + r);
+            tile_hub[k] = __ballot_sync(0xffffffffu, d > HUB_T);
+            any_hub = any_hub || tile_hub[k] != 0u;
+        }
+    }
+    const uint32_t my_hub = any_hub ? ((tile_hub[rl0 >> 5] >> (rl0 & 31)) & 0xffffu) : 0u;
+    // virtual start of every row = exclusive prefix sum of the rows' list lengths (self entry + the CSR entries it keeps)
+    int vs;
+    {
+        const int rp_next = __shfl_down_sync(0xffffffffu, rp, 1);
+        int len = 0;
+        if (lane < RPW) len = self1 + (((my_hub >> lane) & 1u) ? 0 : (rp_next - rp));
+        int incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        vs = incl - len;                                   // lane RPW holds the total
+    }
+    const int v_beg = 0, v_end = __shfl_sync(0xffffffffu, vs, RPW);
     int cur = 0, cur_vend = __shfl_sync(0xffffffffu, vs, 1);
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     float* const dst0 = xsu + rl0 * xld + cl;
+    // pointer of source row j (owned / halo matrix, or the owner's memory over NVLink)
+    auto entry_row = [&](int j) -> const float* {
+        if (a.src_index) j = __ldg(a.src_index + j);
+        if (a.peer_x) {
+            const int owner = j / (int)a.rows_per_rank;
+            return reinterpret_cast<const float*>(__ldg(reinterpret_cast<const unsigned long long*>(a.peer_x) + owner)) +
+                   (long long)(j - owner * (int)a.rows_per_rank) * a.ldx;
+        }
+        return src_row(a, j);
+    };
 
     auto finish_row = [&]() {
         if (GOUT ? (cv0 && row0 + rl0 + cur < p.num_rows) : cin0) {
@@ -520,16 +568,7 @@ __device__ __forceinline__ void gather_unit_fast(const Tc2Params& p, long long r
                     if (WEIGHTED && a.self_weight) my_w = __ldg(a.self_weight + rg);
                 }
             } else {
-                int j = m.col;
-                if (a.src_index) j = __ldg(a.src_index + j);
-                if (a.peer_x) {
-                    // node-sharded graph, global source id: the row is read in place from its owner over NVLink
-                    const int owner = j / (int)a.rows_per_rank;
-                    my_row = reinterpret_cast<const float*>(__ldg(reinterpret_cast<const unsigned long long*>(a.peer_x) + owner)) +
-                             (long long)(j - owner * (int)a.rows_per_rank) * a.ldx;
-                } else {
-                    my_row = src_row(a, j);
-                }
+                my_row = entry_row(m.col);
                 my_w = m.w;
             }
         }
@@ -564,6 +603,62 @@ __device__ __forceinline__ void gather_unit_fast(const Tc2Params& p, long long r
         }
     }
     while (cur < RPW) finish_row();
+
+    if (any_hub) {
+        // ---- cooperative pass over the tile's hub rows (uniform across the NGW gather warps) ------------------------------
+#pragma unroll 1
+        for (int k = 0; k < 4; ++k) {
+            uint32_t bits = tile_hub[k];
+#pragma unroll 1
+            while (bits) {
+                const int h = 32 * k + (__ffs(bits) - 1);           // row of the tile
+                bits &= bits - 1;
+                const int beg = __ldg(a.rowptr + row0 + h), end = __ldg(a.rowptr + row0 + h + 1);
+                const int per = (end - beg + NGW - 1) / NGW;
+                const int s_beg = min(end, beg + gw * per), s_end = min(end, s_beg + per);
+                float ph[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+                for (int eb = s_beg; eb < s_end; eb += 32) {
+                    const int e = eb + lane;
+                    const float* my_row = g_zero_row;
+                    float my_w = 0.0f;
+                    if (e < s_end) {
+                        my_row = entry_row(a.col ? __ldg(a.col + e) : e);
+                        my_w = WEIGHTED ? __ldg(a.edge_weight + e) : 1.0f;
+                    }
+                    const int cnt = min(32, s_end - eb);
+#pragma unroll 1
+                    for (int t0 = 0; t0 < cnt; t0 += U) {
+                        float4 v[U];
+#pragma unroll
+                        for (int u = 0; u < U; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(shfl_ptr(my_row, t0 + u) + cload));
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            const float w = __shfl_sync(0xffffffffu, my_w, t0 + u);
+                            ph[0] = fmaf(w, v[u].x, ph[0]);
+                            ph[1] = fmaf(w, v[u].y, ph[1]);
+                            ph[2] = fmaf(w, v[u].z, ph[2]);
+                            ph[3] = fmaf(w, v[u].w, ph[3]);
+                        }
+                    }
+                }
+                if (cin0) *reinterpret_cast<float4*>(&hub->part[gw][cl]) = make_float4(ph[0], ph[1], ph[2], ph[3]);
+                gather_warps_barrier();
+                if (h >= rl0 && h < rl0 + RPW && (GOUT ? (cv0 && row0 + h < p.num_rows) : cin0)) {
+                    float* d = dst0 + (long long)(h - rl0) * xld;
+                    float4 t = *reinterpret_cast<const float4*>(d);
+#pragma unroll
+                    for (int w8 = 0; w8 < NGW; ++w8) {
+                        const float4 q = *reinterpret_cast<const float4*>(&hub->part[w8][cl]);
+                        t.x += q.x; t.y += q.y; t.z += q.z; t.w += q.w;
+                    }
+                    if (!cv0) t = make_float4(0.f, 0.f, 0.f, 0.f);
+                    *reinterpret_cast<float4*>(d) = t;
+                }
+                gather_warps_barrier();
+            }
+        }
+    }
 
     const bool pre_silu = p.has_pre && p.pre.act == KAGNN_ACT_SILU;
     if (p.has_pre || (!GOUT && p.agg_out) || mode == KAGNN_AGG_SEGMENT_MEAN) {
@@ -627,6 +722,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
     float* post_sc = reinterpret_cast<float*>(tmem_slot + 4);     // post-affine of the last layer (<= 128 columns each; 16-byte aligned)
     float* post_sh = post_sc + 128;
     volatile int* gather_progress = reinterpret_cast<volatile int*>(post_sh + 128);   // tiles the gather warps have started
+    HubScratch* hub_scratch = reinterpret_cast<HubScratch*>(post_sh + 128 + 4);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (warp == WARP_MMA) tc::tmem_alloc(tmem_slot, 512);
@@ -909,8 +1005,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                 if (vec && head_ok) {
                     if (gine) gather_unit<true, true>(p, row0, c0, ucols, xsu, gw, lane);
                     else if (plain_copy) gather_unit<true, false>(p, row0, c0, ucols, xsu, gw, lane);
-                    else if (p.agg.mode == KAGNN_AGG_WEIGHTED) gather_unit_fast<true>(p, row0, c0, ucols, xsu, gw, lane);
-                    else gather_unit_fast<false>(p, row0, c0, ucols, xsu, gw, lane);
+                    else if (p.agg.mode == KAGNN_AGG_WEIGHTED) gather_unit_fast<true>(p, row0, c0, ucols, xsu, gw, lane, hub_scratch);
+                    else gather_unit_fast<false>(p, row0, c0, ucols, xsu, gw, lane, hub_scratch);
                 } else {
                     if (gine) gather_unit<false, true>(p, row0, c0, ucols, xsu, gw, lane);
                     else gather_unit<false, false>(p, row0, c0, ucols, xsu, gw, lane);
@@ -1035,16 +1131,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int AGG_WARPS = 8;
 __global__ void __launch_bounds__(AGG_WARPS * 32) aggregate_only_kernel(const __grid_constant__ Tc2Params p) {
-    const int lane = threadIdx.x & 31;
-    const long long group = (long long)blockIdx.x * AGG_WARPS + (threadIdx.x >> 5);      // 16 rows each
-    const long long row0 = group * RPW;
-    if (row0 >= p.num_rows) return;
+    __shared__ HubScratch hub;
+    const int lane = threadIdx.x & 31, gw = threadIdx.x >> 5;
+    const long long row0 = (long long)blockIdx.x * BM;                     // block = one 128-row tile, warp gw = rows 16 gw ..
     const int F = p.agg.num_cols;
     for (int c0 = 0; c0 < F; c0 += 128) {
         float* out = p.agg_out + row0 * p.ld_agg_out + c0;
         const int ucols = min(128, F - c0);
-        if (p.agg.mode == KAGNN_AGG_WEIGHTED) gather_unit_fast<true, true>(p, row0, c0, ucols, out, 0, lane);
-        else gather_unit_fast<false, true>(p, row0, c0, ucols, out, 0, lane);
+        if (p.agg.mode == KAGNN_AGG_WEIGHTED) gather_unit_fast<true, true>(p, row0, c0, ucols, out, gw, lane, &hub);
+        else gather_unit_fast<false, true>(p, row0, c0, ucols, out, gw, lane, &hub);
     }
 }
 
@@ -1070,8 +1165,8 @@ int kagnn_aggregate_only_tc2(const KagnnAggregate* agg, int64_t num_rows, const 
     p.ld_agg_out = ld_agg_out;
     p.xld = (int)ld_agg_out;
     if (ld_agg_out > (int64_t)INT32_MAX) return KAGNN_EUNSUPPORTED;
-    const long long groups = ceil_div64(num_rows, RPW);
-    const unsigned blocks = (unsigned)ceil_div64(groups, AGG_WARPS);
+    static_assert(AGG_WARPS == NGW && AGG_WARPS * RPW == BM, "aggregate_only_kernel: one block = one 128-row tile of NGW warps");
+    const unsigned blocks = (unsigned)ceil_div64(num_rows, BM);
     aggregate_only_kernel<<<blocks, AGG_WARPS * 32, 0, stream>>>(p);
     KAGNN_LAUNCH_CHECK();
     return KAGNN_OK;
@@ -1143,7 +1238,7 @@ int kagnn_fused_fwd_tc2(const KagnnAggregate* agg, int64_t num_rows, const Kagnn
     p.units_per_tile = (F_pad0 + p.uw - 1) / p.uw;
     p.bstage_bytes = 256 * n_max;
     // LUTs | mbarriers (x ring full/empty, stage full/empty, 2 accumulator) | tmem slot (16 B) | post scale/shift | progress word
-    const int tail = KAGNN_MAX_LAYERS * LUT_ROWS * 16 + (2 * MAX_UNITS + 2 * MAX_STAGE + 2) * 8 + 16 + 2 * 128 * 4 + 16;
+    const int tail = KAGNN_MAX_LAYERS * LUT_ROWS * 16 + (2 * MAX_UNITS + 2 * MAX_STAGE + 2) * 8 + 16 + 2 * 128 * 4 + 16 + (int)sizeof(HubScratch);
     const int unit_bytes = p.unit_floats * (int)sizeof(float);
     // ring depths: at least 2 x-units and 2 stages; prefer deeper stages, then more units
     int best_units = 0, best_ns = 0;
