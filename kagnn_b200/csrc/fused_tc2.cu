@@ -79,7 +79,6 @@ constexpr bool OWN = KAGNN_TC2_OWN != 0;
 constexpr int FPW = OWN ? 8 : 8 / NWG;       // features per warpgroup per spline chunk it works on
 constexpr int FULL_ARRIVALS = (OWN ? 128 : NPW * 32) + 1;   // producer threads of one chunk + the W loader's expect_tx
 constexpr int NGW = 8;                       // gather warps
-constexpr int NPROD = NPW * 32;
 constexpr int NTHREADS = (NPW + NGW + 4) * 32;   // + MMA, W loader and two idle warps (whole warpgroups for setmaxnreg)
 constexpr int WARP_MMA = NPW + NGW;
 constexpr int WARP_LOAD = NPW + NGW + 1;
@@ -94,7 +93,9 @@ constexpr float kMagic = 12582912.0f;        // 1.5 * 2^23: u + kMagic (round do
 struct LayerT2 {
     int F, F_pad, N, N_pad, n_chunks;
     int stack;                               // 1: [W_hi | W_lo] is one B operand (N_pad <= 64): accumulator = [hi.hi + lo.hi | hi.lo]
-    float c0, inv_h, lim;                    // u = x * inv_h + c0 (= (x - t0)/h); valid iff 0 <= u < lim = G + 2k
+    float c0, inv_h, lim;                    // B-spline: u = x * inv_h + c0 (= (x - t0)/h); valid iff 0 <= u < lim = G + 2k
+    float rc0, rstep, rk;                    // RBF: centres rc0 + g * rstep, k = sqrt(log2 e) / denominator: phi = 2^-((z - c) k)^2
+    const float *bias, *lnw, *lnb;           // RBF: base_linear.bias, LayerNorm weight / bias (NULL = none)
     const uint8_t* wtc;
 };
 
@@ -216,6 +217,22 @@ __device__ __forceinline__ void bspline_slots(float inv_h, float c0, float limp,
     lo[3] = prmt(l01, l23, sel.w);
 }
 
+// FastKAN: the 8 Gaussians exp(-((z - c_g)/den)^2) of one layer-normalised input (fastkan.py:46-47) as bf16 hi / lo slot words.
+// All 8 slots are dense (no placement); slots past num_grids meet zero weights.
+__device__ __forceinline__ void rbf_slots(float rc0, float rstep, float rk, float z, uint32_t* hi, uint32_t* lo) {
+    float v[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        const float d = (z - (rc0 + (float)g * rstep)) * rk;
+        v[g] = ex2_approx(-d * d);
+    }
+#pragma unroll
+    for (int g = 0; g < 8; g += 2) {
+        hi[g / 2] = pack_trunc(v[g], v[g + 1]);
+        lo[g / 2] = pack_rn(trunc_residual(v[g]), trunc_residual(v[g + 1]));
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // GATHER: one warp aggregates RPW destination rows of one unit (column block [c0, c0 + ucols)) into the ring slot.
 // ---------------------------------------------------------------------------------------------------------------------
@@ -267,7 +284,6 @@ __device__ __forceinline__ void gather_unit(const Tc2Params& p, long long row0, 
 #pragma unroll 1
         for (int rb = 0; rb < RPW; rb += 8) {
             float v[8][4];
-#pragma unroll
             // two-part rows: units below num_head_cols come from x_head, the others from x (unit-aligned split)
             const bool head = c0 < a.num_head_cols;
             const float* src = head ? a.x_head : a.x;
@@ -723,6 +739,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
     float* post_sh = post_sc + 128;
     volatile int* gather_progress = reinterpret_cast<volatile int*>(post_sh + 128);   // tiles the gather warps have started
     HubScratch* hub_scratch = reinterpret_cast<HubScratch*>(post_sh + 128 + 4);
+    float2* ln_part = reinterpret_cast<float2*>(hub_scratch + 1);       // [2][NWG][128]: FastKAN LayerNorm partial sums
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (warp == WARP_MMA) tc::tmem_alloc(tmem_slot, 512);
@@ -742,9 +759,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
     if (tid == 0) *gather_progress = 0;
     if (tid >= 128 && tid < 256) {
         const int c = tid - 128;
-        const bool on = p.has_post && c < p.layers[p.n_layers - 1].N;
-        post_sc[c] = (on && p.post.scale) ? __ldg(p.post.scale + c) : 1.0f;
-        post_sh[c] = (on && p.post.shift) ? __ldg(p.post.shift + c) : 0.0f;
+        const LayerT2& LL = p.layers[p.n_layers - 1];
+        const bool on = p.has_post && c < LL.N;
+        const float sc = (on && p.post.scale) ? __ldg(p.post.scale + c) : 1.0f;
+        const float sh = (on && p.post.shift) ? __ldg(p.post.shift + c) : 0.0f;
+        const float bb = (K == 0 && LL.bias && c < LL.N) ? __ldg(LL.bias + c) : 0.0f;     // FastKAN base_linear.bias
+        post_sc[c] = sc;
+        post_sh[c] = fmaf(bb, sc, sh);
     }
     if (tid < p.n_layers * LUT_ROWS) {
         // per layer, row q <-> knot interval j = q - 1.  A valid interval (0 <= j < G + 2k) puts its first non-zero basis
@@ -801,7 +822,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                     for (int i = 0; i < 8; ++i) v[i] += v2[i];
                 }
                 if (row < nrows) {
-                    if (p.has_post) {
+                    if (p.has_post || (K == 0 && L.bias)) {
                         const float4 s0 = *reinterpret_cast<const float4*>(post_sc + 8 * jb), s1 = *reinterpret_cast<const float4*>(post_sc + 8 * jb + 4);
                         const float4 h0 = *reinterpret_cast<const float4*>(post_sh + 8 * jb), h1 = *reinterpret_cast<const float4*>(post_sh + 8 * jb + 4);
                         v[0] = fmaf(v[0], s0.x, h0.x); v[1] = fmaf(v[1], s0.y, h0.y); v[2] = fmaf(v[2], s0.z, h0.z); v[3] = fmaf(v[3], s0.w, h0.w);
@@ -848,6 +869,67 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                 int s = (int)(cq % (uint32_t)p.ns);
                 uint32_t par = ((cq / (uint32_t)p.ns) & 1u) ^ 1u;
                 bool unit_ready = false;
+                // ---- FastKAN (K == 0): previous layer's base bias rides on the values read back from TMEM; LayerNorm statistics
+                // of this thread's row (fastkan.py:66,78: biased variance, eps 1e-5), shifted one-pass sums split over the warpgroups
+                const float* pbias = (K == 0 && l > 0) ? p.layers[l - 1].bias : nullptr;
+                const float rc0 = L.rc0, rstep = L.rstep, rk = L.rk;
+                float ln_mean = 0.f, ln_rstd = 1.f;
+                if (K == 0) {
+                    if (l == 0) {                                     // the launcher guarantees one x unit per tile for FastKAN
+                        cur_unit = 0;
+                        xrow = xs + (size_t)(uc0 % p.n_units) * p.unit_floats + (size_t)row * p.xld;
+                        tc::mbar_wait_relaxed(&xs_full[uc0 % p.n_units], (uc0 / p.n_units) & 1);
+                        unit_ready = true;
+                    }
+                    if (L.lnw) {
+                        auto load8 = [&](int f0, float (&v)[8]) {
+                            if (l == 0) {
+                                const float4 t0 = *reinterpret_cast<const float4*>(xrow + f0);
+                                const float4 t1 = *reinterpret_cast<const float4*>(xrow + f0 + 4);
+                                v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w; v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
+                            } else {
+                                tc::tmem_ld8(src_t + (uint32_t)f0, v);
+                                if (src_lo) {
+                                    float v2[8];
+                                    tc::tmem_ld8(src_t + src_lo + (uint32_t)f0, v2);
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) v[i] += v2[i];
+                                }
+                                if (pbias) {
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) v[i] += __ldg(pbias + min(f0 + i, L.F - 1));
+                                }
+                            }
+                        };
+                        float v[8];
+                        load8(0, v);
+                        const float x0 = v[0];
+                        float sd = 0.f, sq = 0.f;
+                        for (int f0 = 8 * wg; f0 < L.F_pad; f0 += 8 * NWG) {
+                            load8(f0, v);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float d = (f0 + i < L.F) ? v[i] - x0 : 0.f;
+                                sd += d;
+                                sq = fmaf(d, d, sq);
+                            }
+                        }
+                        float2* part = ln_part + (size_t)(lc & 1u) * NWG * 128;
+                        part[wg * 128 + row] = make_float2(sd, sq);
+                        asm volatile("bar.sync 3, %0;" ::"n"(NPW * 32) : "memory");
+                        sd = 0.f;
+                        sq = 0.f;
+#pragma unroll
+                        for (int w = 0; w < NWG; ++w) {
+                            const float2 t = part[w * 128 + row];
+                            sd += t.x;
+                            sq += t.y;
+                        }
+                        const float inv_f = 1.0f / (float)L.F, md = sd * inv_f;
+                        ln_mean = x0 + md;
+                        ln_rstd = rsqrtf(fmaxf(fmaf(sq, inv_f, -md * md), 0.f) + 1e-5f);
+                    }
+                }
                 // Deferred hand-over: the arrive on full[] of a chunk is issued only after the NEXT chunk's basis math, so the
                 // latency of the tcgen05.st stores (tcgen05.wait::st) hides behind useful work instead of ending every chunk.
                 int pending = -1;
@@ -914,12 +996,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
 #pragma unroll
                                     for (int i = 0; i < FPW; ++i) v[i] += v2[i];
                                 }
+                                if (pbias) {
+#pragma unroll
+                                    for (int i = 0; i < FPW; ++i) v[i] += __ldg(pbias + min(f0 + i, L.F - 1));
+                                }
+                            }
+                            if (K == 0 && L.lnw) {
+#pragma unroll
+                                for (int i = 0; i < FPW; ++i) {
+                                    const int f = min(f0 + i, L.F - 1);
+                                    v[i] = fmaf((v[i] - ln_mean) * ln_rstd, __ldg(L.lnw + f), L.lnb ? __ldg(L.lnb + f) : 0.f);
+                                }
                             }
 #pragma unroll
                             for (int i = 0; i < FPW; i += 2) {
                                 uint32_t hi[8], lo[8];
-                                bspline_slots<K>(inv_h, c0f, limp, lutL, v[i], hi, lo);
-                                bspline_slots<K>(inv_h, c0f, limp, lutL, v[i + 1], hi + 4, lo + 4);
+                                if (K == 0) {
+                                    rbf_slots(rc0, rstep, rk, v[i], hi, lo);
+                                    rbf_slots(rc0, rstep, rk, v[i + 1], hi + 4, lo + 4);
+                                } else {
+                                    bspline_slots<(K == 0 ? 1 : K)>(inv_h, c0f, limp, lutL, v[i], hi, lo);
+                                    bspline_slots<(K == 0 ? 1 : K)>(inv_h, c0f, limp, lutL, v[i + 1], hi + 4, lo + 4);
+                                }
                                 if (i == 0) flush_pending();          // the previous chunk's TMEM stores drained behind this math
                                 tc::tmem_st8(a_t + 4u * (uint32_t)(fsh + i), hi);
                                 tc::tmem_st8(a_t + 32u + 4u * (uint32_t)(fsh + i), lo);
@@ -942,11 +1040,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
 #pragma unroll
                                         for (int i = 0; i < 8; ++i) v[i] += v2[i];
                                     }
+                                    if (pbias) {
+#pragma unroll
+                                        for (int i = 0; i < 8; ++i) v[i] += __ldg(pbias + min(f0 + i, L.F - 1));
+                                    }
                                 }
                                 float r[8];
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) {
-                                    v[i] = silu_nan(v[i]);
+                                    v[i] = (K == 0) ? __fdividef(v[i], 1.0f + ex2_approx(-kLog2e * v[i])) : silu_nan(v[i]);
                                     r[i] = trunc_residual(v[i]);
                                 }
                                 tc::tmem_st4(a_t + 4u * jj, pack_trunc(v[0], v[1]), pack_trunc(v[2], v[3]), pack_trunc(v[4], v[5]),
@@ -1195,15 +1297,21 @@ int kagnn_fused_fwd_tc2(const KagnnAggregate* agg, int64_t num_rows, const Kagnn
     p.n_layers = n_layers;
     p.n_tiles = (int)ceil_div64(num_rows, BM);
 
-    const int k = layers[0].spline_order;
+    const bool rbf = layers[0].basis == KAGNN_BASIS_RBF;
+    const int k = rbf ? 0 : layers[0].spline_order;
     int width = agg->num_cols, n_max = 0;
     for (int l = 0; l < n_layers; ++l) {
         const KagnnKanLayer& s = layers[l];
         LayerT2& d = p.layers[l];
-        if (s.basis != KAGNN_BASIS_BSPLINE || !s.packed_w_tc || s.in_features != width) return KAGNN_EUNSUPPORTED;
-        if (s.spline_order != k || k < 1 || k > 3 || s.grid_size < 1 || s.grid_size + k > 8) return KAGNN_EUNSUPPORTED;
+        if (s.basis != layers[0].basis || !s.packed_w_tc || s.in_features != width) return KAGNN_EUNSUPPORTED;
+        if (rbf) {
+            if (s.grid_size < 1 || s.grid_size > 8 || OWN) return KAGNN_EUNSUPPORTED;
+        } else {
+            if (s.basis != KAGNN_BASIS_BSPLINE) return KAGNN_EINVAL;
+            if (s.spline_order != k || k < 1 || k > 3 || s.grid_size < 1 || s.grid_size + k > 8) return KAGNN_EUNSUPPORTED;
+            if (!(s.h > 0.f)) return KAGNN_EINVAL;
+        }
         if (s.out_features <= 0 || s.out_features > 128) return KAGNN_EUNSUPPORTED;
-        if (!(s.h > 0.f)) return KAGNN_EINVAL;
         if (!aligned16(s.packed_w_tc)) return KAGNN_EALIGN;
         d.F = s.in_features;
         d.F_pad = ceil16(s.in_features);
@@ -1211,9 +1319,18 @@ int kagnn_fused_fwd_tc2(const KagnnAggregate* agg, int64_t num_rows, const Kagnn
         d.N_pad = ceil16(s.out_features);
         d.n_chunks = d.F_pad / 8 + (d.F_pad + 63) / 64;
         d.stack = d.N_pad <= 64 ? 1 : 0;
-        d.inv_h = 1.0f / s.h;
-        d.c0 = -s.t0 * d.inv_h;
-        d.lim = (float)(s.grid_size + 2 * k);
+        if (rbf) {
+            d.rc0 = s.t0;
+            d.rstep = s.h;
+            d.rk = s.inv_denominator * 1.2011224087864498f;          // sqrt(log2 e): exp(-d^2) = 2^-(d sqrt(log2 e))^2
+            d.bias = s.base_bias;
+            d.lnw = s.ln_weight;
+            d.lnb = s.ln_bias;
+        } else {
+            d.inv_h = 1.0f / s.h;
+            d.c0 = -s.t0 * d.inv_h;
+            d.lim = (float)(s.grid_size + 2 * k);
+        }
         d.wtc = static_cast<const uint8_t*>(s.packed_w_tc);
         if (d.N_pad > n_max) n_max = d.N_pad;
         width = s.out_features;
@@ -1238,7 +1355,7 @@ int kagnn_fused_fwd_tc2(const KagnnAggregate* agg, int64_t num_rows, const Kagnn
     p.units_per_tile = (F_pad0 + p.uw - 1) / p.uw;
     p.bstage_bytes = 256 * n_max;
     // LUTs | mbarriers (x ring full/empty, stage full/empty, 2 accumulator) | tmem slot (16 B) | post scale/shift | progress word
-    const int tail = KAGNN_MAX_LAYERS * LUT_ROWS * 16 + (2 * MAX_UNITS + 2 * MAX_STAGE + 2) * 8 + 16 + 2 * 128 * 4 + 16 + (int)sizeof(HubScratch);
+    const int tail = KAGNN_MAX_LAYERS * LUT_ROWS * 16 + (2 * MAX_UNITS + 2 * MAX_STAGE + 2) * 8 + 16 + 2 * 128 * 4 + 16 + (int)sizeof(HubScratch) + 2 * NWG * 128 * 8;
     const int unit_bytes = p.unit_floats * (int)sizeof(float);
     // ring depths: at least 2 x-units and 2 stages; prefer deeper stages, then more units
     int best_units = 0, best_ns = 0;
@@ -1256,7 +1373,8 @@ int kagnn_fused_fwd_tc2(const KagnnAggregate* agg, int64_t num_rows, const Kagnn
     if (OWN && p.ns < NWG) return KAGNN_EUNSUPPORTED;
     const size_t smem = (size_t)p.n_units * unit_bytes + (size_t)p.ns * p.bstage_bytes + tail;
 
-    void (*kern)(Tc2Params) = k == 3 ? fused_tc2_kernel<3> : (k == 2 ? fused_tc2_kernel<2> : fused_tc2_kernel<1>);
+    if (rbf && p.units_per_tile != 1) return KAGNN_EUNSUPPORTED;      // LayerNorm needs the whole input row in one x unit
+    void (*kern)(Tc2Params) = k == 3 ? fused_tc2_kernel<3> : (k == 2 ? fused_tc2_kernel<2> : (k == 1 ? fused_tc2_kernel<1> : fused_tc2_kernel<0>));
     KAGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)props.max_smem));
     const int grid = p.n_tiles < props.num_sms ? p.n_tiles : props.num_sms;
     kern<<<(unsigned)grid, NTHREADS, smem, stream>>>(p);

@@ -175,3 +175,45 @@ def test_node_model_auto_path_uses_tc_and_matches():
         c1 = ops.launch_counters()
         assert c1["tc"] - c0["tc"] >= 4, (c0, c1)
         assert K.rel_err(y, y_ref) <= TOL, conv
+
+
+@pytest.mark.parametrize("sizes,G,n,ln", [([128, 128, 128], 8, 1000, True), ([7, 64, 64], 8, 300, True), ([64, 32, 16, 8, 4], 5, 129, True),
+                                          ([100, 128], 6, 515, False), ([16, 16], 2, 128, True), ([128, 40], 8, 4097, True)])
+def test_fastkan_pipelined_kernel(sizes, G, n, ln):
+    """FastKAN chains up to 128 wide run in the pipelined kernel (RBF basis + LayerNorm statistics in the producers, base bias
+    folded into the TMEM read-back / epilogue); result against the oracle."""
+    import kagnn_b200 as kb
+    from kagnn_b200 import ops
+    torch.manual_seed(sum(sizes) + G)
+    m = kb.FastKAN(sizes, num_grids=G)
+    if not ln:
+        for lay in m.layers:
+            lay.layernorm = None
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.dim() == 1 and p.requires_grad:
+                p.add_(torch.randn_like(p) * 0.1)
+    x = torch.randn(n, sizes[0]) * 1.5 + 0.3
+    y_ref = K.fastkan_chain(_sd_cpu(m), "layers.", x)
+    c0 = ops.launch_counters()["tc2"]
+    with torch.no_grad():
+        y = m.cuda()(x.cuda()).cpu()
+    assert ops.launch_counters()["tc2"] == c0 + 1
+    assert K.rel_err(y, y_ref) <= TOL
+
+
+def test_fastkan_gin_layer_pipelined():
+    import kagnn_b200 as kb
+    from kagnn_b200 import ops
+    torch.manual_seed(9)
+    n, e, f = 3000, 20000, 128
+    ei = _rand_graph(n, e, 5)
+    x = torch.randn(n, f) * 0.4
+    conv = kb.GIFASTKANLayer(f, 64, 8, 64, 2)
+    sd = _sd_cpu(conv)
+    c0 = ops.launch_counters()["tc2"]
+    with torch.no_grad():
+        y = conv.cuda()(x.cuda(), ei.cuda()).cpu()
+    assert ops.launch_counters()["tc2"] == c0 + 1
+    ref = K.gin_conv(x, ei, lambda t: K.fastkan_chain(sd, "nn.layers.", t))
+    assert K.rel_err(y, ref) <= TOL
