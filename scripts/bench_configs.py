@@ -81,6 +81,17 @@ def main():
     ms = timeit(lambda: mm(dm))
     out.append({"config": "4: FastKAN KAGIN hidden 256 grid 8 batch 4096 (fp32)", "nodes": nn_, "graphs": 4096, "ms": ms,
                 "nodes_per_s": nn_ / ms * 1e3, "graphs_per_s": 4096 / ms * 1e3})
+    # FastKAN inside the Optuna ranges of the reference (hidden <= 128): arxiv-shaped GFASTKAN_Nodes, pipelined vs general kernel
+    n, e = 169_343, 1_166_243
+    ei = torch.randint(0, n, (2, e), generator=gen).to(dev)
+    xa = (torch.randn(n, 128, generator=gen) * 0.3).to(dev)
+    mf = kb.GFASTKAN_Nodes("gin", 3, 128, 64, 40, skip=True, grid_size=8, hidden_layers=2).eval().to(dev)
+    for variant, tag in ((0, "pipelined kernel"), (1, "general tcgen05 kernel")):
+        ops.set_tc_variant(variant)
+        ms = timeit(lambda: mf(xa, ei))
+        out.append({"config": f"arxiv-shaped GFASTKAN_Nodes gin 3 layers hidden 64 grid 8 ({tag})", "nodes": n, "ms": ms,
+                    "nodes_per_s": n / ms * 1e3})
+    ops.set_tc_variant(0)
     # config 3 (one shard's worth): RMAT-like skewed graph, KAGCN layer hidden 128 -- 1/8 of 10 M nodes / 100 M edges
     n, e = 1_250_000, 12_500_000
     src = (torch.rand(e, generator=gen) ** 3 * n).long()           # heavy-tailed source popularity
