@@ -109,6 +109,7 @@ struct Tc2Params {
     float* y;
     long long ldy;
     int n_layers, n_tiles, y_vec;
+    int defer;                                            // deferred full[] arrive: throughput-bound launches only
     int uw, uw_shift, xld, n_units, units_per_tile, unit_floats;   // x-tile ring geometry (uw = 1 << uw_shift = 64 or 128)
     int ns, bstage_bytes;                                 // A/B stage ring depth, bytes of one B stage
     LayerT2 layers[KAGNN_MAX_LAYERS];
@@ -1058,7 +1059,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                             }
                         }
                         pending = s;                              // arrive on full[s] once these stores have drained
-                        if (OWN) flush_pending();                 // (a warpgroup's next own chunk may depend on this one)
+                        if (OWN || !p.defer) flush_pending();     // (OWN: a warpgroup's next own chunk may depend on this one)
                         if (lane == 0 && (warp & 3) == 0 && wg < 2) TRC(wg, cq + q, 4);
                     }
                     if (++s == p.ns) { s = 0; par ^= 1u; }
@@ -1377,6 +1378,9 @@ int kagnn_fused_fwd_tc2(const KagnnAggregate* agg, int64_t num_rows, const Kagnn
     void (*kern)(Tc2Params) = k == 3 ? fused_tc2_kernel<3> : (k == 2 ? fused_tc2_kernel<2> : (k == 1 ? fused_tc2_kernel<1> : fused_tc2_kernel<0>));
     KAGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)props.max_smem));
     const int grid = p.n_tiles < props.num_sms ? p.n_tiles : props.num_sms;
+    // hiding the tcgen05.st latency behind the next chunk's math adds one chunk of latency per layer: worth it only when every CTA
+    // streams many tiles (bench: +1..3 %), harmful for small batches (ZINC batch 1024: 0.50 -> 0.58 ms)
+    p.defer = p.n_tiles >= 4 * grid ? 1 : 0;
     kern<<<(unsigned)grid, NTHREADS, smem, stream>>>(p);
     KAGNN_LAUNCH_CHECK();
     return KAGNN_OK;
