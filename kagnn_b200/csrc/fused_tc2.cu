@@ -58,6 +58,12 @@ constexpr int BM = 128;
                                          // bench, distance 3 makes the GIN layers 8 % SLOWER -- the extra requests cost more than the
                                          // DRAM latency they hide; through cp.async.bulk.prefetch they also delay the W loader, 1.7x)
 #endif
+#ifndef KAGNN_TC2_HUB
+#define KAGNN_TC2_HUB 1
+#endif
+#ifndef KAGNN_TC2_PIPE_EPI
+#define KAGNN_TC2_PIPE_EPI 1
+#endif
 #ifndef KAGNN_TC2_BAL
 #define KAGNN_TC2_BAL 1
 #endif
@@ -498,8 +504,8 @@ __device__ __forceinline__ void gather_unit_fast(const Tc2Params& p, long long r
     }
     const uint32_t my_hub = any_hub ? ((tile_hub[rl0 >> 5] >> (rl0 & 31)) & 0xffffu) : 0u;
     // virtual start of every row = exclusive prefix sum of the rows' list lengths (self entry + the CSR entries it keeps)
-    int vs;
-    {
+    int vs = rp + self1 * min(lane, RPW);                  // no hub in the tile: list positions follow the CSR directly
+    if (any_hub) {
         const int rp_next = __shfl_down_sync(0xffffffffu, rp, 1);
         int len = 0;
         if (lane < RPW) len = self1 + (((my_hub >> lane) & 1u) ? 0 : (rp_next - rp));
@@ -511,7 +517,7 @@ __device__ __forceinline__ void gather_unit_fast(const Tc2Params& p, long long r
         }
         vs = incl - len;                                   // lane RPW holds the total
     }
-    const int v_beg = 0, v_end = __shfl_sync(0xffffffffu, vs, RPW);
+    const int v_beg = __shfl_sync(0xffffffffu, vs, 0), v_end = __shfl_sync(0xffffffffu, vs, RPW);
     int cur = 0, cur_vend = __shfl_sync(0xffffffffu, vs, 1);
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     float* const dst0 = xsu + rl0 * xld + cl;
@@ -1079,6 +1085,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
             pend_row0 = row0;
             pend_lc = lc;
             have_pend = true;
+            if (!KAGNN_TC2_PIPE_EPI) {
+                epilogue(pend_row0, pend_lc);
+                have_pend = false;
+            }
         }
         if (have_pend) epilogue(pend_row0, pend_lc);
     } else if (warp < NPW + NGW) {
@@ -1108,8 +1118,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                 if (vec && head_ok) {
                     if (gine) gather_unit<true, true>(p, row0, c0, ucols, xsu, gw, lane);
                     else if (plain_copy) gather_unit<true, false>(p, row0, c0, ucols, xsu, gw, lane);
-                    else if (p.agg.mode == KAGNN_AGG_WEIGHTED) gather_unit_fast<true>(p, row0, c0, ucols, xsu, gw, lane, hub_scratch);
-                    else gather_unit_fast<false>(p, row0, c0, ucols, xsu, gw, lane, hub_scratch);
+                    else if (p.agg.mode == KAGNN_AGG_WEIGHTED) gather_unit_fast<true>(p, row0, c0, ucols, xsu, gw, lane, KAGNN_TC2_HUB ? hub_scratch : nullptr);
+                    else gather_unit_fast<false>(p, row0, c0, ucols, xsu, gw, lane, KAGNN_TC2_HUB ? hub_scratch : nullptr);
                 } else {
                     if (gine) gather_unit<false, true>(p, row0, c0, ucols, xsu, gw, lane);
                     else gather_unit<false, false>(p, row0, c0, ucols, xsu, gw, lane);
