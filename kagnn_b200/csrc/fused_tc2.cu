@@ -72,18 +72,10 @@ constexpr int BM = 128;
 #endif
 constexpr int NPW = KAGNN_TC2_NPW;           // producer warps: 2 or 4 warpgroups, each expands 8 / NWG features of every chunk
 constexpr int NWG = NPW / 4;
-#ifndef KAGNN_TC2_OWN
-#define KAGNN_TC2_OWN 0
-#endif
-// OWN = 1: chunk c of the running sequence is expanded entirely by warpgroup c % NWG (per-chunk fixed costs -- barrier round,
-//          fences, address setup -- are paid once per warpgroup per NWG chunks; the warpgroups work on different ring stages);
-// OWN = 0: every warpgroup expands 8 / NWG features of EVERY chunk (lowest latency per chunk, NWG times the fixed costs).
-// Measured on the bench (B200): OWN = 1 is 3-8 % slower on the GIN layers and 5 % faster on lay_out, so 0 is the default.
-// OWN = 1 needs ring depth >= NWG (a warpgroup must never be two mbarrier phases ahead of its stage); the launcher declines
-// shapes whose W stages do not fit that often.
-constexpr bool OWN = KAGNN_TC2_OWN != 0;
-constexpr int FPW = OWN ? 8 : 8 / NWG;       // features per warpgroup per spline chunk it works on
-constexpr int FULL_ARRIVALS = (OWN ? 128 : NPW * 32) + 1;   // producer threads of one chunk + the W loader's expect_tx
+// Every warpgroup expands 8 / NWG features of EVERY chunk (lowest latency per chunk; the alternative -- whole chunks handed round
+// robin to the warpgroups -- was measured 3-8 % slower on the GIN layers and needs ring depth >= NWG).
+constexpr int FPW = 8 / NWG;                 // features per warpgroup per spline chunk
+constexpr int FULL_ARRIVALS = NPW * 32 + 1;  // every producer thread + the W loader's expect_tx
 constexpr int NGW = 8;                       // gather warps
 constexpr int NTHREADS = (NPW + NGW + 4) * 32;   // + MMA, W loader and two idle warps (whole warpgroups for setmaxnreg)
 constexpr int WARP_MMA = NPW + NGW;
@@ -115,7 +107,6 @@ struct Tc2Params {
     float* y;
     long long ldy;
     int n_layers, n_tiles, y_vec;
-    int defer;                                            // deferred full[] arrive: throughput-bound launches only
     int uw, uw_shift, xld, n_units, units_per_tile, unit_floats;   // x-tile ring geometry (uw = 1 << uw_shift = 64 or 128)
     int ns, bstage_bytes;                                 // A/B stage ring depth, bytes of one B stage
     LayerT2 layers[KAGNN_MAX_LAYERS];
@@ -806,7 +797,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
         const int wg = warp >> 2;
         const int row = tid & 127;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-        uint32_t cq = 0, lc = 0, uc0 = 0;                  // running chunk / layer / unit counters
+        uint32_t cq = 0, lc = 0;                           // running chunk / layer counters
+        int u_slot = 0;                                    // x-tile ring: slot and phase parity of the unit being consumed
+        uint32_t u_par = 0;
         // ---- epilogue of a tile's last layer: TMEM -> registers -> post-affine -> y.  Software-pipelined: it runs AFTER the
         // basis production of the NEXT tile's first layer (which writes the other accumulator region), so the wait for the
         // last MMAs, the TMEM reads and the stores overlap the tensor-core work already queued for the next tile.
@@ -875,7 +868,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                 }
                 int s = (int)(cq % (uint32_t)p.ns);
                 uint32_t par = ((cq / (uint32_t)p.ns) & 1u) ^ 1u;
-                bool unit_ready = false;
                 // ---- FastKAN (K == 0): previous layer's base bias rides on the values read back from TMEM; LayerNorm statistics
                 // of this thread's row (fastkan.py:66,78: biased variance, eps 1e-5), shifted one-pass sums split over the warpgroups
                 const float* pbias = (K == 0 && l > 0) ? p.layers[l - 1].bias : nullptr;
@@ -884,9 +876,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                 if (K == 0) {
                     if (l == 0) {                                     // the launcher guarantees one x unit per tile for FastKAN
                         cur_unit = 0;
-                        xrow = xs + (size_t)(uc0 % p.n_units) * p.unit_floats + (size_t)row * p.xld;
-                        tc::mbar_wait_relaxed(&xs_full[uc0 % p.n_units], (uc0 / p.n_units) & 1);
-                        unit_ready = true;
+                        xrow = xs + (size_t)u_slot * p.unit_floats + (size_t)row * p.xld;
+                        tc::mbar_wait_relaxed(&xs_full[u_slot], u_par);
                     }
                     if (L.lnw) {
                         auto load8 = [&](int f0, float (&v)[8]) {
@@ -937,49 +928,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                         ln_rstd = rsqrtf(fmaxf(fmaf(sq, inv_f, -md * md), 0.f) + 1e-5f);
                     }
                 }
-                // Deferred hand-over: the arrive on full[] of a chunk is issued only after the NEXT chunk's basis math, so the
-                // latency of the tcgen05.st stores (tcgen05.wait::st) hides behind useful work instead of ending every chunk.
-                int pending = -1;
-                auto flush_pending = [&]() {
-                    if (pending >= 0) {
-                        tc::tmem_st_wait();
-                        tc::tc_fence_before_sync();
-                        tc::mbar_arrive(&full[pending]);
-                        pending = -1;
-                    }
-                };
                 ChunkCursor c(L.F_pad);
                 for (int q = 0; q < n_chunks; ++q, c.next()) {
                     if (l == 0 && c.j == 0) {
-                        // x-tile ring bookkeeping (every warp walks every chunk): leaving a unit releases it
+                        // x-tile ring: entering a new unit releases the previous one and waits for the gather warps
                         const int ul = (64 * c.group) >> p.uw_shift;
                         if (ul != cur_unit) {
                             if (cur_unit >= 0) {
                                 __syncwarp();
-                                if (lane == 0) tc::mbar_arrive(&xs_empty[(uc0 + cur_unit) % p.n_units]);
+                                if (lane == 0) tc::mbar_arrive(&xs_empty[u_slot]);
+                                if (++u_slot == p.n_units) { u_slot = 0; u_par ^= 1u; }
                             }
                             cur_unit = ul;
-                            unit_ready = false;
-                            const uint32_t un = uc0 + ul;
-                            xrow = xs + (size_t)(un % p.n_units) * p.unit_floats + (size_t)row * p.xld - (size_t)ul * p.uw;
+                            if (lane == 0 && (warp & 3) == 0 && wg < 2) TRL(wg, cq + q, 0);
+                            tc::mbar_wait_relaxed(&xs_full[u_slot], u_par);
+                            if (lane == 0 && (warp & 3) == 0 && wg < 2) TRL(wg, cq + q, 1);
+                            xrow = xs + (size_t)u_slot * p.unit_floats + (size_t)row * p.xld - (size_t)ul * p.uw;
                         }
                     }
-                    const bool mine = !OWN || (int)((cq + (uint32_t)q) & (uint32_t)(NWG - 1)) == wg;
-                    if (mine) {
-                        if (l == 0 && !unit_ready) {
-                            const uint32_t un = uc0 + (uint32_t)cur_unit;
-                            if (lane == 0 && (warp & 3) == 0 && wg < 2) TRL(wg, cq + q, 0);
-                            tc::mbar_wait_relaxed(&xs_full[un % p.n_units], (un / p.n_units) & 1);
-                            if (lane == 0 && (warp & 3) == 0 && wg < 2) TRL(wg, cq + q, 1);
-                            unit_ready = true;
-                        }
+                    {
                         if (lane == 0 && (warp & 3) == 0 && wg < 2) TRC(wg, cq + q, 2);
                         tc::mbar_wait_relaxed(&empty[s], par);
                         if (lane == 0 && (warp & 3) == 0 && wg < 2) TRC(wg, cq + q, 3);
                         tc::tc_fence_after_sync();
                         const uint32_t a_t = tmem_base + lane_base + TMEM_A0 + 64u * s;
                         if (!c.base()) {
-                            const int fsh = OWN ? 0 : FPW * wg;               // first feature of this warpgroup inside the chunk
+                            const int fsh = FPW * wg;                         // first feature of this warpgroup inside the chunk
                             const int f0 = 64 * c.group + 8 * c.j + fsh;
                             float v[FPW];
                             if (l == 0) {
@@ -1025,14 +999,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                                     bspline_slots<(K == 0 ? 1 : K)>(inv_h, c0f, limp, lutL, v[i], hi, lo);
                                     bspline_slots<(K == 0 ? 1 : K)>(inv_h, c0f, limp, lutL, v[i + 1], hi + 4, lo + 4);
                                 }
-                                if (i == 0) flush_pending();          // the previous chunk's TMEM stores drained behind this math
                                 tc::tmem_st8(a_t + 4u * (uint32_t)(fsh + i), hi);
                                 tc::tmem_st8(a_t + 32u + 4u * (uint32_t)(fsh + i), lo);
                             }
                         } else {
-                            flush_pending();
 #pragma unroll 1
-                            for (int jj = OWN ? 0 : wg; jj < c.n_oct; jj += OWN ? 1 : NWG) {
+                            for (int jj = wg; jj < c.n_oct; jj += NWG) {
                                 const int f0 = 64 * c.group + 8 * jj;
                                 float v[8];
                                 if (l == 0) {
@@ -1064,18 +1036,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                                              pack_rn(r[6], r[7]));
                             }
                         }
-                        pending = s;                              // arrive on full[s] once these stores have drained
-                        if (OWN || !p.defer) flush_pending();     // (OWN: a warpgroup's next own chunk may depend on this one)
+                        tc::tmem_st_wait();
+                        tc::tc_fence_before_sync();
+                        tc::mbar_arrive(&full[s]);
                         if (lane == 0 && (warp & 3) == 0 && wg < 2) TRC(wg, cq + q, 4);
                     }
                     if (++s == p.ns) { s = 0; par ^= 1u; }
                 }
-                flush_pending();
                 cq += (uint32_t)n_chunks;
                 if (l == 0) {
                     __syncwarp();
-                    if (lane == 0) tc::mbar_arrive(&xs_empty[(uc0 + cur_unit) % p.n_units]);
-                    uc0 += (uint32_t)p.units_per_tile;
+                    if (lane == 0) tc::mbar_arrive(&xs_empty[u_slot]);
+                    if (++u_slot == p.n_units) { u_slot = 0; u_par ^= 1u; }
                     if (have_pend) {                       // previous tile's epilogue, behind this tile's first layer
                         epilogue(pend_row0, pend_lc);
                         have_pend = false;
@@ -1316,7 +1288,7 @@ int kagnn_fused_fwd_tc2(const KagnnAggregate* agg, int64_t num_rows, const Kagnn
         LayerT2& d = p.layers[l];
         if (s.basis != layers[0].basis || !s.packed_w_tc || s.in_features != width) return KAGNN_EUNSUPPORTED;
         if (rbf) {
-            if (s.grid_size < 1 || s.grid_size > 8 || OWN) return KAGNN_EUNSUPPORTED;
+            if (s.grid_size < 1 || s.grid_size > 8) return KAGNN_EUNSUPPORTED;
         } else {
             if (s.basis != KAGNN_BASIS_BSPLINE) return KAGNN_EINVAL;
             if (s.spline_order != k || k < 1 || k > 3 || s.grid_size < 1 || s.grid_size + k > 8) return KAGNN_EUNSUPPORTED;
@@ -1381,16 +1353,12 @@ int kagnn_fused_fwd_tc2(const KagnnAggregate* agg, int64_t num_rows, const Kagnn
     if (best_units == 0) return KAGNN_EUNSUPPORTED;
     p.n_units = best_units;
     p.ns = best_ns;
-    if (OWN && p.ns < NWG) return KAGNN_EUNSUPPORTED;
     const size_t smem = (size_t)p.n_units * unit_bytes + (size_t)p.ns * p.bstage_bytes + tail;
 
     if (rbf && p.units_per_tile != 1) return KAGNN_EUNSUPPORTED;      // LayerNorm needs the whole input row in one x unit
     void (*kern)(Tc2Params) = k == 3 ? fused_tc2_kernel<3> : (k == 2 ? fused_tc2_kernel<2> : (k == 1 ? fused_tc2_kernel<1> : fused_tc2_kernel<0>));
     KAGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)props.max_smem));
     const int grid = p.n_tiles < props.num_sms ? p.n_tiles : props.num_sms;
-    // hiding the tcgen05.st latency behind the next chunk's math adds one chunk of latency per layer: worth it only when every CTA
-    // streams many tiles (bench: +1..3 %), harmful for small batches (ZINC batch 1024: 0.50 -> 0.58 ms)
-    p.defer = p.n_tiles >= 4 * grid ? 1 : 0;
     kern<<<(unsigned)grid, NTHREADS, smem, stream>>>(p);
     KAGNN_LAUNCH_CHECK();
     return KAGNN_OK;
