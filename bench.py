@@ -33,7 +33,7 @@ import torch  # noqa: E402
 N_NODES, N_EDGES, N_FEAT, HIDDEN, N_CLASSES, MP_LAYERS, KAN_DEPTH, GRID, ORDER = 169_343, 1_166_243, 128, 64, 40, 3, 2, 5, 3
 METRIC = "KAGNN-layer forward nodes/sec"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture (profiles/README.md)
-NCU_TRAFFIC_BYTES = {"agg1[128]->64->64": 216_651_776, "agg1[64]->64->64": 65_238_272, "agg0[320]->40": 235_025_408}
+NCU_TRAFFIC_BYTES = {"agg1[128]->64->64": 214_118_656, "agg1[64]->64->64": 64_955_648, "agg0[320]->40": 232_909_824}
 WORKLOAD = "ogbn-arxiv-shaped KAGIN (GKAN_Nodes gin, 3 layers, hidden 64, grid 5, order 3, KAN depth 2), fp32, eval"
 
 

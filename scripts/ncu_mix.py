@@ -35,7 +35,8 @@ src = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "kagnn
 def find(s):
     return next(i + 1 for i, l in enumerate(src) if s in l)
 L_GATHER_FN0, L_KERNEL = find("__device__ __forceinline__ void ldp4("), find("fused_tc2_kernel(const __grid_constant__")
-L_PROD, L_EPI, L_GATHER, L_MMA, L_LOAD = (find(s) for s in ("BASIS PRODUCERS / EPILOGUE", "epilogue of the last layer", "= GATHER =", "MMA ISSUER", "W LOADER"))
+L_PROD, L_GATHER, L_MMA, L_LOAD = (find(s) for s in ("BASIS PRODUCERS / EPILOGUE", "= GATHER =", "MMA ISSUER", "W LOADER"))
+L_EPI0, L_EPI1 = find("auto epilogue = [&]"), find("long long pend_row0")      # the epilogue lambda sits inside the producer section
 cat = collections.Counter()
 samp = collections.Counter()
 role = "setup"
@@ -49,7 +50,7 @@ for r in data:
         if ln >= L_LOAD: role = "loader"
         elif ln >= L_MMA: role = "mma"
         elif ln >= L_GATHER: role = "gather"
-        elif ln >= L_EPI: role = "epilogue"
+        elif L_EPI0 <= ln < L_EPI1: role = "epilogue"
         elif ln >= L_PROD: role = "producer"
         elif ln >= L_KERNEL: role = "setup"
         elif ln >= L_GATHER_FN0: role = "gather"
