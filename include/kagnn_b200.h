@@ -79,6 +79,9 @@ typedef struct KagnnKanLayer {
     const float* ln_weight; /* RBF LayerNorm weight (in) or NULL = no LayerNorm                              */
     const float* ln_bias;   /* RBF LayerNorm bias (in) or NULL                                               */
     const void* packed_w_tc;/* optional: weights packed by kagnn_pack_kan_weights_tc() -> enables the tcgen05 path   */
+    const float* ln_stats;  /* RBF, optional, FIRST layer of a launch in mode KAGNN_AGG_NONE only: per-row (mean, rstd) of
+                             * its LayerNorm from kagnn_layernorm_stats(); lets the pipelined kernel take inputs wider than
+                             * one 128-column tile unit (e.g. the skip-concat read-out).  NULL = computed in the kernel.   */
 } KagnnKanLayer;
 
 /* Input side of the fused layer: where rows come from and how they are aggregated. */
@@ -212,6 +215,11 @@ int kagnn_gather_rows(const float* x, int64_t ldx, const int32_t* index, int64_t
  * pack + all-to-all: only the distinct remote rows cross the link, no send lists, no NCCL.  16-byte aligned, cols % 4 == 0. */
 int kagnn_gather_rows_peer(const float* const* peer_x, int64_t ldx, int64_t rows_per_rank, const int32_t* ids,
                            int64_t num_rows, int32_t num_cols, float* out, int64_t ld_out, void* stream);
+
+/* LayerNorm row statistics (fastkan.py:66,78: biased variance, eps 1e-5) of two-part rows [x_head | x] (x_head may be NULL):
+ * stats[2r] = mean, stats[2r+1] = 1/sqrt(var + eps).  See KagnnKanLayer.ln_stats. */
+int kagnn_layernorm_stats(const float* x, int64_t ldx, int32_t num_cols, const float* x_head_or_null, int64_t ld_head,
+                          int32_t num_head_cols, int64_t num_rows, float eps, float* stats, void* stream);
 
 /* ---- small epilogues of the models (so that no step of a forward runs as framework math) ---------------------------- */
 /* y[r,:] = log_softmax(x[r,:]) (gc/models.py:119,194). */

@@ -31,7 +31,7 @@ class KagnnKanLayer(C.Structure):
         ("grid_size", C.c_int32), ("spline_order", C.c_int32),
         ("t0", C.c_float), ("h", C.c_float), ("inv_denominator", C.c_float),
         ("packed_w", C.c_void_p), ("base_bias", C.c_void_p), ("ln_weight", C.c_void_p), ("ln_bias", C.c_void_p),
-        ("packed_w_tc", C.c_void_p),
+        ("packed_w_tc", C.c_void_p), ("ln_stats", C.c_void_p),
     ]
 
 
@@ -82,6 +82,8 @@ _SIGNATURES = {
     "kagnn_tc_selftest_workspace": (C.c_size_t, [C.c_int32, C.c_int32]),
     "kagnn_tc_selftest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t,
                                     C.c_void_p]),
+    "kagnn_layernorm_stats": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_float,
+                                        C.c_void_p, C.c_void_p]),
     "kagnn_log_softmax_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
     "kagnn_batchnorm_train_workspace": (C.c_size_t, [C.c_int32]),
     "kagnn_batchnorm_train_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_float, C.c_float,

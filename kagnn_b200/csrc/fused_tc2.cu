@@ -94,6 +94,7 @@ struct LayerT2 {
     float c0, inv_h, lim;                    // B-spline: u = x * inv_h + c0 (= (x - t0)/h); valid iff 0 <= u < lim = G + 2k
     float rc0, rstep, rk;                    // RBF: centres rc0 + g * rstep, k = sqrt(log2 e) / denominator: phi = 2^-((z - c) k)^2
     const float *bias, *lnw, *lnb;           // RBF: base_linear.bias, LayerNorm weight / bias (NULL = none)
+    const float* ln_stats;                   // RBF, layer 0: precomputed per-row (mean, rstd) or NULL (computed here)
     const uint8_t* wtc;
 };
 
@@ -873,8 +874,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                 const float* pbias = (K == 0 && l > 0) ? p.layers[l - 1].bias : nullptr;
                 const float rc0 = L.rc0, rstep = L.rstep, rk = L.rk;
                 float ln_mean = 0.f, ln_rstd = 1.f;
-                if (K == 0) {
-                    if (l == 0) {                                     // the launcher guarantees one x unit per tile for FastKAN
+                if (K == 0 && L.lnw && l == 0 && L.ln_stats) {
+                    // statistics from the pre-pass (rows wider than one x unit)
+                    const long long r = min(row0 + row, p.num_rows - 1);
+                    const float2 st = __ldg(reinterpret_cast<const float2*>(L.ln_stats) + r);
+                    ln_mean = st.x;
+                    ln_rstd = st.y;
+                } else if (K == 0) {
+                    if (l == 0 && L.lnw) {                            // the launcher guarantees one x unit per tile in this case
                         cur_unit = 0;
                         xrow = xs + (size_t)u_slot * p.unit_floats + (size_t)row * p.xld;
                         tc::mbar_wait_relaxed(&xs_full[u_slot], u_par);
@@ -1309,6 +1316,7 @@ int kagnn_fused_fwd_tc2(const KagnnAggregate* agg, int64_t num_rows, const Kagnn
             d.bias = s.base_bias;
             d.lnw = s.ln_weight;
             d.lnb = s.ln_bias;
+            d.ln_stats = (l == 0 && agg->mode == KAGNN_AGG_NONE && !pre) ? s.ln_stats : nullptr;
         } else {
             d.inv_h = 1.0f / s.h;
             d.c0 = -s.t0 * d.inv_h;
@@ -1355,7 +1363,8 @@ int kagnn_fused_fwd_tc2(const KagnnAggregate* agg, int64_t num_rows, const Kagnn
     p.ns = best_ns;
     const size_t smem = (size_t)p.n_units * unit_bytes + (size_t)p.ns * p.bstage_bytes + tail;
 
-    if (rbf && p.units_per_tile != 1) return KAGNN_EUNSUPPORTED;      // LayerNorm needs the whole input row in one x unit
+    // in-kernel LayerNorm statistics need the whole input row in one x unit; wider rows need the pre-pass (ln_stats)
+    if (rbf && p.units_per_tile != 1 && p.layers[0].lnw && !p.layers[0].ln_stats) return KAGNN_EUNSUPPORTED;
     void (*kern)(Tc2Params) = k == 3 ? fused_tc2_kernel<3> : (k == 2 ? fused_tc2_kernel<2> : (k == 1 ? fused_tc2_kernel<1> : fused_tc2_kernel<0>));
     KAGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)props.max_smem));
     const int grid = p.n_tiles < props.num_sms ? p.n_tiles : props.num_sms;

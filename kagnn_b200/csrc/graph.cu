@@ -358,3 +358,41 @@ extern "C" int kagnn_batchnorm_train_fwd(const float* x, int64_t ldx, int64_t ro
     KAGNN_LAUNCH_CHECK();
     return KAGNN_OK;
 }
+
+namespace {
+// warp per row, two passes (the second one hits L1): exact two-pass variance like torch.nn.functional.layer_norm
+__global__ void layernorm_stats_kernel(const float* __restrict__ x, int64_t ldx, int cols, const float* __restrict__ xh, int64_t ldh,
+                                       int hcols, int64_t rows, float eps, float* __restrict__ stats) {
+    const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    const float* a = xh ? xh + r * ldh : nullptr;
+    const float* b = x + r * ldx;
+    const int total = hcols + cols;
+    float s = 0.f;
+    for (int c = lane; c < total; c += 32) s += c < hcols ? a[c] : b[c - hcols];
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)total;
+    float q = 0.f;
+    for (int c = lane; c < total; c += 32) {
+        const float d = (c < hcols ? a[c] : b[c - hcols]) - mean;
+        q = fmaf(d, d, q);
+    }
+    for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    if (lane == 0) {
+        stats[2 * r] = mean;
+        stats[2 * r + 1] = 1.0f / sqrtf(q / (float)total + eps);
+    }
+}
+}  // namespace
+
+extern "C" int kagnn_layernorm_stats(const float* x, int64_t ldx, int32_t cols, const float* x_head, int64_t ld_head, int32_t hcols,
+                                     int64_t rows, float eps, float* stats, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (rows < 0 || cols <= 0 || hcols < 0 || !x || !stats || ldx < cols || (hcols > 0 && (!x_head || ld_head < hcols))) return KAGNN_EINVAL;
+    if (rows == 0) return KAGNN_OK;
+    layernorm_stats_kernel<<<(unsigned)ceil_div64(rows * 32, kThreads), kThreads, 0, stream>>>(x, ldx, cols, hcols > 0 ? x_head : nullptr,
+                                                                                                ld_head, hcols, rows, eps, stats);
+    KAGNN_LAUNCH_CHECK();
+    return KAGNN_OK;
+}

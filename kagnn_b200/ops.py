@@ -172,6 +172,20 @@ def gather_rows(x: Tensor, index: Optional[Tensor], out: Optional[Tensor] = None
     return out
 
 
+def layernorm_stats(x: Tensor, x_head: Optional[Tensor] = None, eps: float = 1e-5) -> Tensor:
+    """(rows, 2) per-row (mean, rstd) of LayerNorm over the two-part rows [x_head | x] (kagnn_layernorm_stats)."""
+    global launch_count
+    ldx = _rows(x, "x")
+    stats = torch.empty(x.size(0), 2, dtype=torch.float32, device=x.device)
+    if x.size(0):
+        L.check(L.lib().kagnn_layernorm_stats(_p(x), ldx, x.size(1), _p(x_head) if x_head is not None else None,
+                                              _rows(x_head, "x_head") if x_head is not None else 0,
+                                              x_head.size(1) if x_head is not None else 0, x.size(0), eps, _p(stats), _stream()),
+                "layernorm_stats")
+        launch_count += 1
+    return stats
+
+
 def log_softmax(x: Tensor) -> Tensor:
     """Row-wise log_softmax of (rows, classes) logits (kagnn_log_softmax_rows)."""
     global launch_count
@@ -303,6 +317,7 @@ class KanLayerSpec:
     ln_weight: Optional[Tensor] = None
     ln_bias: Optional[Tensor] = None
     packed_w_tc: Optional[Tensor] = None
+    ln_stats: Optional[Tensor] = None     # per-row (mean, rstd) of the first layer's LayerNorm (layernorm_stats); per call
 
     def fill(self, s: L.KagnnKanLayer) -> None:
         s.basis, s.in_features, s.out_features = self.basis, self.in_features, self.out_features
@@ -313,6 +328,7 @@ class KanLayerSpec:
         s.ln_weight = None if self.ln_weight is None else self.ln_weight.data_ptr()
         s.ln_bias = None if self.ln_bias is None else self.ln_bias.data_ptr()
         s.packed_w_tc = None if self.packed_w_tc is None else self.packed_w_tc.data_ptr()
+        s.ln_stats = None if self.ln_stats is None else self.ln_stats.data_ptr()
 
 
 @dataclass
@@ -430,6 +446,14 @@ def fused_layer(agg: AggSpec, num_rows: int, layers: Sequence[KanLayerSpec], pre
         agg_out = torch.empty(num_rows, agg.x.size(1), dtype=torch.float32, device=dev)
     if num_rows == 0:
         return out if layers else agg_out
+    if (layers and layers[0].basis == L.BASIS_RBF and layers[0].ln_weight is not None and layers[0].ln_stats is None
+            and agg.mode == L.AGG_NONE and pre is None and agg.src_index is None and layers[0].packed_w_tc is not None
+            and layers[0].in_features > 128 and all(sp.out_features <= 128 for sp in layers)):
+        # FastKAN over rows wider than one tile unit (the skip-concat read-out): LayerNorm statistics by a small pre-pass so
+        # that the pipelined kernel can stream the row unit by unit
+        import dataclasses
+        stats = layernorm_stats(agg.x, agg.x_head)
+        layers = [dataclasses.replace(layers[0], ln_stats=stats)] + list(layers[1:])
     code = _launch_fused(agg, num_rows, layers, pre, post, agg_out, out)
     launch_count += 1
     if code == L.E_UNSUPPORTED and agg.x_head is not None:

@@ -217,3 +217,29 @@ def test_fastkan_gin_layer_pipelined():
     assert ops.launch_counters()["tc2"] == c0 + 1
     ref = K.gin_conv(x, ei, lambda t: K.fastkan_chain(sd, "nn.layers.", t))
     assert K.rel_err(y, ref) <= TOL
+
+
+@pytest.mark.parametrize("fin,fout,n,split", [(320, 40, 1500, 128), (300, 64, 500, 0), (1433, 16, 200, 0), (256, 128, 777, 128)])
+def test_fastkan_wide_input_uses_layernorm_prepass(fin, fout, n, split):
+    """FastKAN layers whose input is wider than one 128-column tile unit (the skip-concat read-out): LayerNorm statistics from
+    the kagnn_layernorm_stats pre-pass, the layer itself in the pipelined kernel (optionally over two-part rows)."""
+    import kagnn_b200 as kb
+    from kagnn_b200 import ops, _lib as L
+    torch.manual_seed(fin + fout)
+    m = kb.FastKANLayer(fin, fout, num_grids=8)
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.dim() == 1 and p.requires_grad:
+                p.add_(torch.randn_like(p) * 0.1)
+    x = torch.randn(n, fin) * 1.3 - 0.2
+    y_ref = K._fastkan_layer_from_sd(_sd_cpu(m), "", x)
+    m = m.cuda()
+    c0 = ops.launch_counters()["tc2"]
+    with torch.no_grad():
+        if split:
+            xd = x.cuda()
+            y = ops.fused_layer(ops.AggSpec(L.AGG_NONE, xd[:, split:], x_head=xd[:, :split].contiguous()), n, m.kernel_specs()).cpu()
+        else:
+            y = m(x.cuda()).cpu()
+    assert ops.launch_counters()["tc2"] == c0 + 1
+    assert K.rel_err(y, y_ref) <= TOL
