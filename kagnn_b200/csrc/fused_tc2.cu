@@ -1198,11 +1198,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                         TRC(3, cq, 0);
                         tc::mbar_wait_relaxed(&empty[s], par);
                         TRC(3, cq, 1);
-#ifdef KAGNN_EXP_HALFW   // timing experiment only (wrong results): how much of the time is W streaming from L2?
-                        const uint32_t bytes = c.b_bytes(L.N_pad) / KAGNN_EXP_HALFW;
-#else
                         const uint32_t bytes = c.b_bytes(L.N_pad);
-#endif
                         tc::mbar_arrive_expect_tx(&full[s], bytes);
                         tc::bulk_g2s(bst + (size_t)s * p.bstage_bytes, L.wtc + c.b_off(L.N_pad), bytes, &full[s]);
                         if (++s == p.ns) { s = 0; par ^= 1u; }

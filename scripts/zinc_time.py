@@ -1,5 +1,7 @@
+"""Forward time of the ZINC-shaped GINE-KAGIN batch (development aid; KAGNN_LIB selects the library variant)."""
 import sys, os, json
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/scripts")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "scripts"))
 import torch
 import bench_configs as B
 from kagnn_b200 import models_regr
