@@ -210,7 +210,7 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank)
         return
-    assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
+    args.warmup = max(args.warmup, 3)            # timing rules: at least 3 warm-up steps (the line reports what was run)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the kagnn_b200 path has no CPU fallback")
     import kagnn_b200 as kb

@@ -154,6 +154,8 @@ class ShardedNodeModel:
             raise ValueError("mode must be 'halo', 'peer', 'pull' or 'auto'")
         self.model, self.rank, self.world, self.n_local, self.group = model, rank, world, n_local, group
         self._symm = {}
+        if mode == "auto" and self.peer_supported() and not self._probe_symmetric_memory():
+            mode = "halo"                                   # NVLink peer memory not available here: NCCL transport
         if mode == "auto":
             # "pull" moves only the DISTINCT remote rows (measured 1.28 vs 1.47 ms/step against "peer" on 2 x B200 for the
             # arxiv-shaped bench, where every remote row is referenced ~3.6 times); "peer" needs no halo matrix at all
@@ -163,6 +165,24 @@ class ShardedNodeModel:
             raise NotImplementedError("mode='peer' needs a GIN-flavour GKAN_Nodes with skip=True, spline_order <= 3, G + k <= 8, "
                                       "widths <= 128 and feature widths that are multiples of 4")
         self.mode = mode
+
+    def _probe_symmetric_memory(self) -> bool:
+        """Collective: can every rank allocate and rendezvous symmetric memory?  (False -> the NCCL halo transport.)"""
+        ok = 1
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            grp = self.group if self.group is not None else dist.group.WORLD
+            dev = torch.device("cuda", torch.cuda.current_device())
+            t = symm_mem.empty((64,), dtype=torch.float32, device=dev)
+            symm_mem.rendezvous(t, grp).barrier()
+        except Exception:
+            ok = 0
+        try:
+            flag = torch.tensor([ok], dtype=torch.int32, device=torch.device("cuda", torch.cuda.current_device()))
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            return bool(int(flag.item()))
+        except Exception:
+            return False
 
     def peer_supported(self) -> bool:
         from .conv import GINConv, GINEConv
