@@ -64,6 +64,21 @@ def main():
     l0 = ops.launch_count
     ms = timeit(lambda: m(x, ei))
     out.append({"config": "0: Cora-shaped KAGCN 2 layers hidden 32 grid 5", "nodes": n, "ms": ms, "nodes_per_s": n / ms * 1e3})
+    # the same forward captured in a CUDA graph (launch-latency-bound problem: replay removes the host side of 6 launches)
+    try:
+        with torch.no_grad():
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                m(x, ei)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                m(x, ei)
+        ms = timeit(graph.replay)
+        out.append({"config": "0: Cora-shaped KAGCN, CUDA-graph replay", "nodes": n, "ms": ms, "nodes_per_s": n / ms * 1e3})
+    except Exception as exc:  # pragma: no cover
+        out.append({"config": "0: Cora-shaped KAGCN, CUDA-graph replay", "error": repr(exc)[:200]})
     # config 2: ZINC-shaped KAGIN (GINE), batch 1024
     nn_, batch, ei = batch_of_graphs(1024, 23.15, 50, gen)
     xz = torch.randint(0, 28, (nn_, 1), generator=gen)
