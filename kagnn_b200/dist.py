@@ -271,6 +271,8 @@ class ShardedNodeModel:
     def forward(self, x: Tensor, plan) -> Tensor:
         from .conv import GCNConv
         m = self.model
+        if len(m.convs) == 0:                               # no message passing: nothing to exchange
+            return m(x, torch.zeros(2, 0, dtype=torch.int64, device=x.device))
         if self.mode in ("peer", "pull"):
             if not m._fusable():
                 raise NotImplementedError("the sharded forward implements the eval-mode plan (BatchNorm folded)")

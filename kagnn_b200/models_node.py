@@ -9,8 +9,9 @@ Execution plan in eval mode (BatchNorm folded to an affine, dropout is the ident
   shifted half a layer: launch 0 = KAN_1(x); launch l = [aggregate(A_hat, t_l) + b_l -> BN_l -> store h_l into the
   concat buffer -> KAN_{l+1}(h_l)]; the last launch has no KAN; then ``lay_out``.
 
-In training mode (batch-statistics BatchNorm, dropout) each conv still runs fused, BN/dropout run as torch modules
-between launches (SURVEY.md section 8f rank 2 is the fused training epilogue)."""
+In training mode (batch-statistics BatchNorm, dropout) each conv still runs fused; BatchNorm runs as its own launches
+(``ops.batchnorm_forward``) and dropout, being random, stays ``nn.Dropout`` between launches (SURVEY.md section 8f rank 2 is
+the fused training epilogue with a Philox mask)."""
 from __future__ import annotations
 
 from typing import List, Optional
@@ -81,8 +82,10 @@ class _NodeModel(nn.Module):
         x = x.to(torch.float32)
         n, f = x.shape
         g = get_graph(edge_index, n)
-        hid = self.bns[0].num_features if len(self.bns) else 0
         n_mp = len(self.convs)
+        if n_mp == 0:
+            return self.lay_out(x)
+        hid = self.bns[0].num_features
         if not self._fusable():
             return self._forward_unfused(x, g)
         # skip concat (models.py:196-201) without any copy: every layer writes its column slice of the hidden buffer and
@@ -104,8 +107,6 @@ class _NodeModel(nn.Module):
             cur = dst
         if not self.skip:
             return self.lay_out(cur)
-        if n_mp == 0:
-            return self.lay_out(x)
         return ops.fused_layer(ops.AggSpec(L.AGG_NONE, buf, x_head=x), n, self.lay_out.kernel_specs())
 
     def _forward_unfused(self, x: Tensor, g) -> Tensor:

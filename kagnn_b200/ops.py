@@ -364,6 +364,14 @@ class AggSpec:
     rows_per_rank: int = 0
     x_head: Optional[Tensor] = None       # AGG_NONE two-part rows: logical row = [x_head[r] | x[r]] (skip concat without the copy)
 
+    def __post_init__(self) -> None:
+        # the C ABI takes row-major matrices with a leading dimension: a transposed / column-strided view (which the
+        # reference's ATen ops accept) is made row-major here -- a copy, no arithmetic
+        for name in ("x", "x_head", "x_halo", "edge_feat"):
+            t = getattr(self, name)
+            if isinstance(t, torch.Tensor) and t.dim() == 2 and t.size(1) > 1 and t.stride(1) != 1:
+                setattr(self, name, t.contiguous())
+
     def struct(self) -> L.KagnnAggregate:
         ldx = _rows(self.x, "x")
         s = L.KagnnAggregate()

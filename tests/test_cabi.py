@@ -100,3 +100,12 @@ def test_init_matches_reference_recipe_statistics():
     ref = K.bspline_bases(x, lay.grid, 3)
     assert torch.allclose(mine, ref, atol=2e-6)
     assert lay.spline_weight.abs().max() < 1.0 and lay.spline_weight.abs().max() > 0
+
+
+def test_aggspec_makes_column_strided_views_row_major():
+    from kagnn_b200 import ops, _lib as L
+    base = torch.randn(6, 10)
+    spec = ops.AggSpec(L.AGG_NONE, base.t())
+    assert spec.x.stride(1) == 1 and torch.equal(spec.x, base.t())
+    sliced = base[:, 2:7]                              # unit column stride: kept as a view (the kernels take a leading dimension)
+    assert ops.AggSpec(L.AGG_NONE, sliced).x.data_ptr() == sliced.data_ptr()

@@ -361,3 +361,38 @@ def test_aggregation_only_launches(n, e, f):
     y = ops.fused_layer(ops.AggSpec(L.AGG_SEGMENT_MEAN, xd, rowptr=ptr), nb, []).cpu()
     ref = torch.zeros(nb, f).index_add_(0, batch, x) / torch.bincount(batch, minlength=nb).clamp(min=1).unsqueeze(1)
     assert K.rel_err(y, ref) <= 1e-5
+
+
+def test_strided_inputs_are_accepted():
+    """Transposed and column-sliced views (which the reference's ATen ops accept) give the same result as a fresh copy."""
+    import kagnn_b200 as kb
+    torch.manual_seed(9)
+    lay = kb.KANLinear(48, 24).cuda()
+    conv = kb.GIKANLayer(48, 24, 5, 3, 32, 2).cuda()
+    ei = torch.randint(0, 500, (2, 3000)).cuda()
+    base = (torch.randn(48, 500) * 0.4).cuda()
+    wide = (torch.randn(500, 100) * 0.4).cuda()
+    with torch.no_grad():
+        xt = base.t()                                  # column stride 500
+        assert torch.equal(lay(xt), lay(xt.contiguous()))
+        assert torch.equal(conv(xt, ei), conv(xt.contiguous(), ei))
+        xs = wide[:, 3:51]                             # row stride 100, misaligned start
+        assert torch.equal(lay(xs), lay(xs.contiguous()))
+        assert torch.equal(conv(xs, ei), conv(xs.contiguous(), ei))
+        xe = wide[:, ::2][:, :48]                      # column stride 2
+        assert torch.equal(lay(xe), lay(xe.contiguous()))
+
+
+@pytest.mark.parametrize("fast", [False, True])
+def test_node_model_without_message_passing_layers(fast):
+    """mp_layers = 0 with skip: the model is lay_out(x) (node_classification_clean/models.py:192-203 with an empty loop)."""
+    import kagnn_b200 as kb
+    torch.manual_seed(3)
+    cls = kb.GFASTKAN_Nodes if fast else kb.GKAN_Nodes
+    m = cls("gin", 0, 12, 8, 3, skip=True).eval()
+    sd = _sd_cpu(m)
+    x = torch.randn(50, 12) * 0.5
+    ei = torch.randint(0, 50, (2, 100))
+    with torch.no_grad():
+        y = m.cuda()(x.cuda(), ei.cuda()).cpu()
+    assert K.rel_err(y, K.node_model_forward(sd, "gin", x, ei, True)) <= TOL
