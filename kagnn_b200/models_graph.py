@@ -4,14 +4,11 @@ graph_classification/models.py:95-265.  ``data`` is duck-typed: ``.x``, ``.edge_
 graph id per node) and optionally ``.num_graphs``.
 
 Eval-mode plan: GIN = one launch per layer (gather -> KAN chain -> BN affine); GCN = KAN_1, then per layer
-[aggregate + bias -> SiLU -> KAN_{l+1}]; readout = one launch [segment pool -> KAN chain]; ``log_softmax`` over the
-(graphs x classes) result is left to torch."""
+[aggregate + bias -> SiLU -> KAN_{l+1}]; readout = one launch [segment pool -> KAN chain]; then one ``log_softmax`` launch over
+the (graphs x classes) result."""
 from __future__ import annotations
 
-from typing import Optional
-
 import torch
-import torch.nn.functional as F
 from torch import nn
 
 from . import _lib as L
@@ -110,6 +107,8 @@ class _GCNGraphModel(nn.Module):
 
     def _message_passing(self, x: Tensor, g) -> Tensor:
         n = x.size(0)
+        if self.n_layers == 0:
+            return x
         drop_off = (not self.training) or self.dropout.p == 0.0
         if not drop_off:
             for i in range(self.n_layers):

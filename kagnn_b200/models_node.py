@@ -14,14 +14,14 @@ In training mode (batch-statistics BatchNorm, dropout) each conv still runs fuse
 the fused training epilogue with a Philox mask)."""
 from __future__ import annotations
 
-from typing import List, Optional
+from typing import Optional
 
 import torch
 from torch import nn
 
 from . import _lib as L
 from . import ops
-from .conv import (FASTKAGCNConv, GIFASTKANLayer, GIKANLayer, KAGCNConv, GCNConv, GINConv)
+from .conv import FASTKAGCNConv, GIFASTKANLayer, GIKANLayer, KAGCNConv, GCNConv
 from .ekan import KANLinear, _module_backend_guard
 from .fastkan import FastKANLayer
 from .graph import get_graph

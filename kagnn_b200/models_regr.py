@@ -9,7 +9,6 @@ through an index (``src_index`` / ``edge_row``), which keeps the per-edge operan
 from __future__ import annotations
 
 import torch
-import torch.nn.functional as F
 from torch import nn
 
 from . import _lib as L

@@ -5,8 +5,8 @@ Nothing here falls back to torch math: a CPU tensor or a missing library raises.
 from __future__ import annotations
 
 import ctypes as C
-from dataclasses import dataclass, field
-from typing import List, Optional, Sequence
+from dataclasses import dataclass
+from typing import Optional, Sequence
 
 import torch
 

@@ -36,8 +36,7 @@ tighter comparisons).
 """
 from __future__ import annotations
 
-import math
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, Optional
 
 import torch
 import torch.nn.functional as F
