@@ -233,6 +233,45 @@ int kagnn_batchnorm_train_fwd(const float* x, int64_t ldx, int64_t num_rows, int
                               float* running_var_or_null, int32_t act, float* y, int64_t ldy, void* workspace,
                               size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * Backward: what `loss.backward()` needs from the modules so that the reference's training
+ * loops run (node_classification_clean/utils.py:125-132, graph_classification/graph_classification_utils.py:44-54).
+ * B-spline layers only; the aggregation backward is kagnn_fused_layer_fwd with n_layers = 0 on the TRANSPOSED CSR.
+ * ------------------------------------------------------------------------------------------------------------------- */
+
+/* dx[n,i] = silu'(x) sum_o dy[n,o] Wb[o,i] + sum_s B_s'(x) sum_o dy[n,o] Ws[o,i,s] sc[o,i]: the input gradient of
+ * KANLinear.forward (ekan.py:154-162) as autograd computes it through b_splines (ekan.py:79-112).  Reads layer->packed_w. */
+int kagnn_kan_bwd_input(const KagnnKanLayer* layer, const float* x, int64_t ldx, const float* dy, int64_t ld_dy,
+                        int64_t num_rows, float* dx, int64_t ld_dx, void* stream);
+
+/* Gradient of the packed weights, same [in][slots+1][out_pad4] layout as kagnn_pack_kan_weights writes (slot `slots` = base
+ * weight).  d_packed (kagnn_packed_weight_elems floats) is zeroed by the call; row sums use float atomics. */
+int kagnn_kan_bwd_weights(const KagnnKanLayer* layer, const float* x, int64_t ldx, const float* dy, int64_t ld_dy,
+                          int64_t num_rows, float* d_packed, void* stream);
+
+/* Chain rule through scaled_spline_weight (ekan.py:146-152): d_packed -> d base_weight (out,in), d spline_weight (out,in,slots),
+ * d spline_scaler (out,in).  d_base_w / d_scaler may be NULL. */
+int kagnn_kan_unpack_weight_grads(const float* d_packed, const float* spline_w, const float* scaler_or_null, int32_t in_f,
+                                  int32_t out_f, int32_t slots, float* d_base_w_or_null, float* d_spline_w,
+                                  float* d_scaler_or_null, void* stream);
+
+/* Backward of training-mode nn.BatchNorm1d (batch statistics recomputed from x in fp64). */
+size_t kagnn_batchnorm_bwd_workspace(int32_t num_cols);
+int kagnn_batchnorm_train_bwd(const float* x, int64_t ldx, const float* dy, int64_t ld_dy, int64_t num_rows, int32_t num_cols,
+                              const float* weight_or_null, float eps, float* dx, int64_t ld_dx, float* d_weight_or_null,
+                              float* d_bias_or_null, void* workspace, size_t workspace_bytes, void* stream);
+
+/* out[c] = sum_r x[r,c] (GCNConv bias gradient); out is zeroed by the call. */
+int kagnn_column_sums(const float* x, int64_t ldx, int64_t num_rows, int32_t num_cols, float* out, void* stream);
+
+/* y = log_softmax(x) row-wise: dx = dy - exp(y) * sum_c dy. */
+int kagnn_log_softmax_bwd(const float* y, int64_t ldy, const float* dy, int64_t ld_dy, int64_t rows, int32_t cols, float* dx,
+                          int64_t ld_dx, void* stream);
+
+/* global_add_pool / global_mean_pool backward: dx[n,:] = d_pooled[batch[n],:] (divided by the segment length when mean != 0). */
+int kagnn_segment_pool_bwd(const float* d_pooled, int64_t ld_dp, const int32_t* segment_ptr, const int64_t* batch,
+                           int64_t num_rows, int32_t num_cols, int32_t mean, float* dx, int64_t ld_dx, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,15 @@
+// Kernel-launch seam of backward.cu.
+//
+// Product build (nvcc, the only thing libkagnn_b200.so is ever made from): KAGNN_LAUNCH is an ordinary <<< >>> launch.
+//
+// KAGNN_HOST_CHECK (defined only by tests/emul/build_emul.py, g++, output under tests/emul/_build/): the kernels of backward.cu
+// use no shared memory, no barriers and no warp intrinsics, so running their threads one after another on the host is a valid
+// schedule.  The CPU test-suite uses that to check the index arithmetic of those kernels in a container without a GPU.  It is
+// test infrastructure: nothing under kagnn_b200/ loads it, and the product has no CPU path.
+#pragma once
+#ifdef KAGNN_HOST_CHECK
+#include "host_check.h"            // tests/emul/host_check.h
+#else
+#include "common.cuh"
+#define KAGNN_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#endif

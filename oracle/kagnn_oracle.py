@@ -346,6 +346,6 @@ def to_dtype(sd: Dict[str, Tensor], dtype) -> Dict[str, Tensor]:
 
 def rel_err(y: Tensor, ref: Tensor) -> float:
     """The parity metric used everywhere: max|y - ref| / max|ref|."""
-    ref = ref.double()
+    ref = ref.detach().double()
     denom = float(ref.abs().max())
-    return float((y.double() - ref).abs().max()) / (denom if denom > 0 else 1.0)
+    return float((y.detach().double() - ref).abs().max()) / (denom if denom > 0 else 1.0)

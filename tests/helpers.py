@@ -42,7 +42,7 @@ def oracle_run(meta, inputs, sd, dtype=torch.float32):
     data = K.Batch(x, inputs["edge_index"], inputs["batch"], ea)
     fam = meta["family"]
     if kind == "gc":
-        return K.gc_kagin_forward(sd, data) if fam.endswith("GIN") else K.gc_kagcn_forward(sd, data)
+        return (K.gc_kagin_forward(sd, data, meta.get("training", False)) if fam.endswith("GIN") else K.gc_kagcn_forward(sd, data))
     if kind == "gr":
         return K.gr_kagin_forward(sd, data, dtype=dtype) if fam.endswith("GIN") else K.gr_kagcn_forward(sd, data, dtype=dtype)
     raise ValueError(kind)
@@ -92,3 +92,40 @@ def product_run(meta, inputs, model, device="cuda"):
         if meta["kind"] == "node":
             return model(inp["x"], inp["edge_index"])
         return model(K.Batch(inp["x"], inp["edge_index"], inp["batch"], inp.get("edge_attr")))
+
+
+# ---- gradient fixtures (tests/golden/grad/, produced by oracle/make_golden_grad.py) -----------------------------------
+def grad_golden_names(prefix=""):
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "grad", prefix + "*.npz")))
+
+
+def load_grad_golden(name):
+    """-> meta, inputs (x, dy[, edge_index, batch]), state_dict, y, grads ('__x' = d loss / d x, else parameter names)."""
+    z = np.load(os.path.join(GOLDEN, "grad", name + ".npz"))
+    meta = json.loads(str(z["meta"]))
+    pick = lambda pre: {k[len(pre):]: torch.from_numpy(z[k]) for k in z.files if k.startswith(pre)}
+    return meta, pick("in/"), pick("sd/"), torch.from_numpy(z["out/y"]), pick("grad/")
+
+
+def oracle_grads(meta, inputs, sd):
+    """Autograd through the oracle: the same quantities the fixture holds."""
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not k.endswith(("grid", "running_mean", "running_var"))
+              else v.clone()) for k, v in sd.items()}
+    x = inputs["x"].clone().requires_grad_(True)
+    ins = dict(inputs, x=x)
+    y = oracle_run(meta, ins, sd)
+    y.backward(inputs["dy"])
+    grads = {k: v.grad for k, v in sd.items() if isinstance(v, torch.Tensor) and v.requires_grad and v.grad is not None}
+    grads["__x"] = x.grad
+    return y, grads
+
+
+def grad_err(g, g_ref, scale):
+    """max|g - g_ref| relative to max|g_ref|, floored at 5 % of the largest parameter gradient of the case: a gradient that is
+    analytically zero (a bias in front of a train-mode BatchNorm) is rounding noise in the reference itself."""
+    denom = max(float(g_ref.abs().max()), 0.05 * scale)
+    return float((g.double() - g_ref.double()).abs().max()) / denom
+
+
+def grad_scale(g_ref):
+    return max(float(v.abs().max()) for k, v in g_ref.items() if k != "__x")

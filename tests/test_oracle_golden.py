@@ -62,3 +62,18 @@ def test_gin_gine_pool_small_known_answers():
     batch = torch.tensor([0, 0, 2])
     assert torch.allclose(K.global_add_pool(x, batch), torch.stack([x[0] + x[1], torch.zeros(2), x[2]]))
     assert torch.allclose(K.global_mean_pool(x, batch), torch.stack([(x[0] + x[1]) / 2, torch.zeros(2), x[2]]))
+
+
+# ---- gradients: the oracle differentiated by autograd == the reference's own modules differentiated by autograd ----------
+from tests.helpers import grad_err, grad_golden_names, grad_scale, load_grad_golden, oracle_grads
+
+
+@pytest.mark.parametrize("name", grad_golden_names())
+def test_oracle_gradients_match_reference(name):
+    meta, inputs, sd, y_ref, g_ref = load_grad_golden(name)
+    y, g = oracle_grads(meta, inputs, sd)
+    assert K.rel_err(y.detach(), y_ref) <= 2e-6
+    assert set(g) == set(g_ref), (sorted(set(g) ^ set(g_ref)))
+    scale = grad_scale(g_ref)
+    for k in g_ref:
+        assert grad_err(g[k].detach(), g_ref[k], scale) <= 1e-5, (name, k)
