@@ -268,6 +268,12 @@ int kagnn_column_sums(const float* x, int64_t ldx, int64_t num_rows, int32_t num
 int kagnn_log_softmax_bwd(const float* y, int64_t ldy, const float* dy, int64_t ld_dy, int64_t rows, int32_t cols, float* dx,
                           int64_t ld_dx, void* stream);
 
+/* y = silu(x), kept as its own launch when it must be differentiated (the activation between the GCN layers of
+ * graph_classification/models.py:190), and dx = dy * silu'(x). */
+int kagnn_silu_fwd(const float* x, int64_t ldx, int64_t rows, int32_t cols, float* y, int64_t ldy, void* stream);
+int kagnn_silu_bwd(const float* x, int64_t ldx, const float* dy, int64_t ld_dy, int64_t rows, int32_t cols, float* dx,
+                   int64_t ld_dx, void* stream);
+
 /* global_add_pool / global_mean_pool backward: dx[n,:] = d_pooled[batch[n],:] (divided by the segment length when mean != 0). */
 int kagnn_segment_pool_bwd(const float* d_pooled, int64_t ld_dp, const int32_t* segment_ptr, const int64_t* batch,
                            int64_t num_rows, int32_t num_cols, int32_t mean, float* dx, int64_t ld_dx, void* stream);

@@ -1,0 +1,187 @@
+"""``torch.autograd.Function`` wrappers that give the modules a backward, so that the
+reference's untouched training loops -- ``loss.backward()`` at node_classification_clean/utils.py:130 and
+graph_classification/graph_classification_utils.py:52 -- run on them.
+
+Every forward below is the same library launch the inference path uses; every backward is a library launch too
+(``kagnn_kan_bwd_*``, ``kagnn_batchnorm_train_bwd``, ... in include/kagnn_b200.h, or the forward aggregation kernel on the
+TRANSPOSED CSR).  torch contributes the autograd tape, ``torch.cat`` of the skip connection and ``nn.Dropout``'s mask.
+Scope of this first backward: B-spline KAN layers, GIN / GCN aggregation, BatchNorm1d, SiLU, add / mean pooling,
+log_softmax.  FastKAN layers and the GINE message raise ``NotImplementedError`` under autograd."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+from . import ops
+
+Tensor = torch.Tensor
+
+
+def grad_needed(x: Tensor, params) -> bool:
+    return torch.is_grad_enabled() and ((isinstance(x, torch.Tensor) and x.requires_grad) or any(p.requires_grad for p in params))
+
+
+def _rowmajor(t: Tensor) -> Tensor:
+    t = t.to(torch.float32)
+    return t if t.dim() == 2 and (t.size(1) <= 1 or t.stride(1) == 1) else t.contiguous()
+
+
+class _KanLinearFn(torch.autograd.Function):
+    """y = KANLinear(x) (ekan.py:154-162)."""
+
+    @staticmethod
+    def forward(ctx, x, base_w, spline_w, scaler, layer):
+        spec = layer.kernel_spec()
+        x = _rowmajor(x)
+        y = ops.fused_layer(ops.AggSpec(L.AGG_NONE, x), x.size(0), [spec])
+        ctx.spec = spec                      # keeps the packed weights of THIS forward alive
+        ctx.has_scaler = scaler is not None
+        ctx.save_for_backward(x, spline_w, scaler if scaler is not None else spline_w)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, spline_w, scaler = ctx.saved_tensors
+        scaler = scaler if ctx.has_scaler else None
+        dy = _rowmajor(dy)
+        dx = ops.kan_bwd_input(ctx.spec, x, dy) if ctx.needs_input_grad[0] else None
+        d_base = d_spline = d_scaler = None
+        if any(ctx.needs_input_grad[1:4]):
+            d_packed = ops.kan_bwd_weights(ctx.spec, x, dy)
+            d_base, d_spline, d_scaler = ops.kan_unpack_weight_grads(d_packed, spline_w, scaler)
+        return dx, d_base, d_spline, d_scaler, None
+
+
+def kan_linear(layer, x: Tensor) -> Tensor:
+    scaler = layer.spline_scaler if layer.enable_standalone_scale_spline else None
+    return _KanLinearFn.apply(x, layer.base_weight, layer.spline_weight, scaler, layer)
+
+
+class _GinAggFn(torch.autograd.Function):
+    """a_i = self_scale * x_i + sum_{j -> i} x_j; backward = the same sum over the reversed edges."""
+
+    @staticmethod
+    def forward(ctx, x, graph, self_scale):
+        x = _rowmajor(x)
+        ctx.graph, ctx.self_scale = graph, float(self_scale)
+        agg = ops.AggSpec(L.AGG_GIN, x, graph.rowptr, graph.col, self_scale=ctx.self_scale)
+        return ops.fused_layer(agg, graph.num_nodes, [])
+
+    @staticmethod
+    def backward(ctx, da):
+        gt = ctx.graph.transposed()
+        agg = ops.AggSpec(L.AGG_GIN, _rowmajor(da), gt.rowptr, gt.col, self_scale=ctx.self_scale)
+        return ops.fused_layer(agg, gt.num_nodes, []), None, None
+
+
+def gin_aggregate(x: Tensor, graph, self_scale: float) -> Tensor:
+    return _GinAggFn.apply(x, graph, self_scale)
+
+
+class _GcnAggFn(torch.autograd.Function):
+    """out = A_hat h + b with A_hat = D^-1/2 (A + I) D^-1/2 (PyG GCNConv.propagate + bias); dh = A_hat^T d_out."""
+
+    @staticmethod
+    def forward(ctx, h, bias, graph):
+        h = _rowmajor(h)
+        ctx.graph, ctx.has_bias = graph, bias is not None
+        w, sw = graph.gcn_weights()
+        agg = ops.AggSpec(L.AGG_WEIGHTED, h, graph.rowptr, graph.col, edge_weight=w, self_weight=sw)
+        pre = ops.Affine(shift=bias.detach()) if bias is not None else None
+        return ops.fused_layer(agg, graph.num_nodes, [], pre=pre)
+
+    @staticmethod
+    def backward(ctx, dout):
+        dout = _rowmajor(dout)
+        dh = db = None
+        if ctx.needs_input_grad[0]:
+            gt = ctx.graph.transposed()
+            w, sw = ctx.graph.gcn_weights_transposed()
+            agg = ops.AggSpec(L.AGG_WEIGHTED, dout, gt.rowptr, gt.col, edge_weight=w, self_weight=sw)
+            dh = ops.fused_layer(agg, gt.num_nodes, [])
+        if ctx.has_bias and ctx.needs_input_grad[1]:
+            db = ops.column_sums(dout)
+        return dh, db, None
+
+
+def gcn_aggregate(h: Tensor, bias: Optional[Tensor], graph) -> Tensor:
+    return _GcnAggFn.apply(h, bias, graph)
+
+
+class _BatchNormFn(torch.autograd.Function):
+    """Training-mode BatchNorm1d (batch statistics; running estimates updated by the forward launch)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, bn):
+        x = _rowmajor(x)
+        y = ops.batchnorm_forward(x, bn)
+        ctx.eps = float(bn.eps)
+        ctx.has_affine = weight is not None
+        ctx.save_for_backward(x, weight if weight is not None else x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dx, dw, db = ops.batchnorm_backward(x, _rowmajor(dy), weight if ctx.has_affine else None, ctx.eps)
+        return dx, (dw if ctx.has_affine else None), (db if ctx.has_affine else None), None
+
+
+def batch_norm_train(x: Tensor, bn) -> Tensor:
+    return _BatchNormFn.apply(x, bn.weight, bn.bias, bn)
+
+
+class _SiluFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _rowmajor(x)
+        ctx.save_for_backward(x)
+        return ops.silu_forward(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        return ops.silu_backward(x, _rowmajor(dy))
+
+
+def silu(x: Tensor) -> Tensor:
+    return _SiluFn.apply(x)
+
+
+class _PoolFn(torch.autograd.Function):
+    """global_add_pool / global_mean_pool."""
+
+    @staticmethod
+    def forward(ctx, x, batch, num_graphs, mean):
+        x = _rowmajor(x)
+        ptr = ops.segment_ptr(batch, num_graphs)
+        ctx.ptr, ctx.batch, ctx.n, ctx.mean = ptr, batch, x.size(0), bool(mean)
+        agg = ops.AggSpec(L.AGG_SEGMENT_MEAN if mean else L.AGG_SEGMENT_SUM, x, rowptr=ptr)
+        return ops.fused_layer(agg, num_graphs, [])
+
+    @staticmethod
+    def backward(ctx, dp):
+        return ops.segment_pool_backward(_rowmajor(dp), ctx.ptr, ctx.batch, ctx.n, ctx.mean), None, None, None
+
+
+def pool(x: Tensor, batch: Tensor, num_graphs: int, mean: bool) -> Tensor:
+    return _PoolFn.apply(x, batch, num_graphs, mean)
+
+
+class _LogSoftmaxFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        y = ops.log_softmax(_rowmajor(x))
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        return ops.log_softmax_backward(y, _rowmajor(dy))
+
+
+def log_softmax(x: Tensor) -> Tensor:
+    return _LogSoftmaxFn.apply(x)

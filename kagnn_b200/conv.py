@@ -24,7 +24,7 @@ import torch
 from torch import nn
 
 from . import _lib as L
-from . import ops
+from . import autograd, ops
 from .ekan import KAN, KANLinear, _module_backend_guard
 from .fastkan import FastKAN, FastKANLayer
 from .graph import GraphCSR, get_graph
@@ -90,8 +90,12 @@ class GCNConv(_MessagePassing):
         return ops.fused_layer(agg, graph.num_nodes, [], pre=pre, agg_out=out)
 
     def forward(self, x: Tensor, edge_index, edge_weight: Optional[Tensor] = None) -> Tensor:
-        _module_backend_guard(x, list(self.parameters()))
+        needs_grad = _module_backend_guard(x, list(self.parameters()), grad_ok=True)
         g = self._graph(x, edge_index)
+        if needs_grad:
+            if edge_weight is not None:
+                raise NotImplementedError("the backward of GCNConv with user edge weights is not implemented")
+            return autograd.gcn_aggregate(self.transform(x), self.bias, g)
         return self.aggregate_transformed(self.transform(x).to(torch.float32), g, edge_weight)
 
 
@@ -125,8 +129,14 @@ class GINConv(_MessagePassing):
 
     def forward(self, x: Tensor, edge_index, size=None, out: Optional[Tensor] = None,
                 post: Optional[ops.Affine] = None, **agg_kw) -> Tensor:
-        _module_backend_guard(x, list(self.parameters()))
+        needs_grad = _module_backend_guard(x, list(self.parameters()), grad_ok=not isinstance(self, GINEConv))
         g = self._graph(x, edge_index)
+        if needs_grad:
+            if post is not None or out is not None or agg_kw:
+                raise NotImplementedError("fused epilogues / sharded inputs are inference-only")
+            if self.eps.requires_grad:
+                raise NotImplementedError("train_eps=True has no backward yet (the reference models keep eps fixed)")
+            return self.nn(autograd.gin_aggregate(x, g, 1.0 + self.eps_value()))
         agg = self._agg_spec(x.to(torch.float32), g, **agg_kw)
         if _is_kan(self.nn):
             specs = self.nn.kernel_specs()

@@ -56,14 +56,14 @@ __device__ __forceinline__ void local_bases(int k, float fr, float* b, float* m)
 
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
 
-// thread = (row n, input feature i), consecutive threads = consecutive features
+// block = 256 rows x ONE input feature i (blockIdx.y), thread = row: the weight rows of feature i are shared by the whole block
+// (a warp touches at most G + k distinct ones), every thread streams its own dy row
 __global__ void kan_bwd_input_kernel(KanGeom g, const float* __restrict__ w, const float* __restrict__ x, long long ldx,
                                      const float* __restrict__ dy, long long ld_dy, long long n_rows, float* __restrict__ dx,
                                      long long ld_dx) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n_rows * g.in_f) return;
-    const int i = (int)(idx % g.in_f);
-    const long long n = idx / g.in_f;
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = (int)blockIdx.y;
+    if (n >= n_rows) return;
     const float xv = x[n * ldx + i];
     int cell;
     float fr;
@@ -227,6 +227,28 @@ __global__ void segment_pool_bwd_kernel(const float* __restrict__ dp, long long 
     dx[r * ld_dx + c] = v;
 }
 
+// y = silu(x):  dx = dy * sigmoid(x) * (1 + x * (1 - sigmoid(x)))
+__global__ void silu_bwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ dy, long long ld_dy,
+                                long long rows, int cols, float* __restrict__ dx, long long ld_dx) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * cols) return;
+    const int c = (int)(idx % cols);
+    const long long r = idx / cols;
+    const float xv = x[r * ldx + c];
+    const float s = sigmoid_f(xv);
+    dx[r * ld_dx + c] = dy[r * ld_dy + c] * (s * (1.0f + xv * (1.0f - s)));
+}
+
+__global__ void silu_fwd_kernel(const float* __restrict__ x, long long ldx, long long rows, int cols, float* __restrict__ y,
+                                long long ldy) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * cols) return;
+    const int c = (int)(idx % cols);
+    const long long r = idx / cols;
+    const float xv = x[r * ldx + c];
+    y[r * ldy + c] = xv * sigmoid_f(xv);
+}
+
 int geometry(const KagnnKanLayer* L, KanGeom* g) {
     if (!L || !L->packed_w) return KAGNN_EINVAL;
     if (L->basis != KAGNN_BASIS_BSPLINE) return KAGNN_EUNSUPPORTED;           // FastKAN backward: not built yet
@@ -253,9 +275,10 @@ extern "C" int kagnn_kan_bwd_input(const KagnnKanLayer* layer, const float* x, i
     if (rc != KAGNN_OK) return rc;
     if (num_rows < 0 || (num_rows > 0 && (!x || !dy || !dx)) || ldx < g.in_f || ld_dy < g.out_f || ld_dx < g.in_f) return KAGNN_EINVAL;
     if (num_rows == 0) return KAGNN_OK;
-    const int64_t total = num_rows * g.in_f;
-    KAGNN_LAUNCH(kan_bwd_input_kernel, (unsigned)ceil_div64(total, kBwdThreads), kBwdThreads, stream, g, layer->packed_w, x,
-                 (long long)ldx, dy, (long long)ld_dy, (long long)num_rows, dx, (long long)ld_dx);
+    if (g.in_f > 65535) return KAGNN_EUNSUPPORTED;                                  // gridDim.y
+    KAGNN_LAUNCH(kan_bwd_input_kernel, dim3((unsigned)ceil_div64(num_rows, kBwdThreads), (unsigned)g.in_f, 1),
+                 dim3((unsigned)kBwdThreads, 1, 1), stream, g, layer->packed_w, x, (long long)ldx, dy, (long long)ld_dy,
+                 (long long)num_rows, dx, (long long)ld_dx);
     KAGNN_LAUNCH_CHECK();
     return KAGNN_OK;
 }
@@ -347,6 +370,27 @@ extern "C" int kagnn_segment_pool_bwd(const float* d_pooled, int64_t ld_dp, cons
     if (!d_pooled || !segment_ptr || !batch || !dx) return KAGNN_EINVAL;
     KAGNN_LAUNCH(segment_pool_bwd_kernel, (unsigned)ceil_div64(num_rows * (int64_t)num_cols, kBwdThreads), kBwdThreads, stream,
                  d_pooled, (long long)ld_dp, segment_ptr, batch, (long long)num_rows, (int)num_cols, (int)mean, dx, (long long)ld_dx);
+    KAGNN_LAUNCH_CHECK();
+    return KAGNN_OK;
+}
+
+extern "C" int kagnn_silu_bwd(const float* x, int64_t ldx, const float* dy, int64_t ld_dy, int64_t rows, int32_t cols, float* dx,
+                              int64_t ld_dx, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (rows < 0 || cols <= 0 || (rows > 0 && (!x || !dy || !dx)) || ldx < cols || ld_dy < cols || ld_dx < cols) return KAGNN_EINVAL;
+    if (rows == 0) return KAGNN_OK;
+    KAGNN_LAUNCH(silu_bwd_kernel, (unsigned)ceil_div64(rows * (int64_t)cols, kBwdThreads), kBwdThreads, stream, x, (long long)ldx, dy,
+                 (long long)ld_dy, (long long)rows, (int)cols, dx, (long long)ld_dx);
+    KAGNN_LAUNCH_CHECK();
+    return KAGNN_OK;
+}
+
+extern "C" int kagnn_silu_fwd(const float* x, int64_t ldx, int64_t rows, int32_t cols, float* y, int64_t ldy, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (rows < 0 || cols <= 0 || (rows > 0 && (!x || !y)) || ldx < cols || ldy < cols) return KAGNN_EINVAL;
+    if (rows == 0) return KAGNN_OK;
+    KAGNN_LAUNCH(silu_fwd_kernel, (unsigned)ceil_div64(rows * (int64_t)cols, kBwdThreads), kBwdThreads, stream, x, (long long)ldx,
+                 (long long)rows, (int)cols, y, (long long)ldy);
     KAGNN_LAUNCH_CHECK();
     return KAGNN_OK;
 }

@@ -19,7 +19,7 @@ import torch
 from torch import nn
 
 from . import _lib as L
-from . import ops
+from . import autograd, ops
 
 Tensor = torch.Tensor
 
@@ -53,13 +53,18 @@ def _uniform_bspline_design(x: Tensor, t0: float, h: float, grid_size: int, orde
     return out
 
 
-def _module_backend_guard(x: Tensor, params: Sequence[Tensor]) -> None:
+def _module_backend_guard(x: Tensor, params: Sequence[Tensor], grad_ok: bool = False) -> bool:
+    """Raises for CPU inputs (no fallback).  Returns True when autograd must record this call: modules that have a backward
+    (``grad_ok``) then take their ``kagnn_b200.autograd`` path; the others (FastKAN, GINE) raise."""
     if not x.is_cuda:
         raise RuntimeError("kagnn_b200 modules run on the B200 only: move the module and its inputs to a CUDA device "
                            "(there is deliberately no CPU fallback)")
     if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params)):
-        raise NotImplementedError("kagnn_b200 implements the forward path; call it under torch.no_grad() / "
-                                  "torch.inference_mode() (backward kernels are the next item of SURVEY.md section 8f)")
+        if not grad_ok:
+            raise NotImplementedError("this kagnn_b200 module has no backward yet (FastKAN layers, GINE messages): call it under "
+                                      "torch.no_grad() / torch.inference_mode()")
+        return True
+    return False
 
 
 class KANLinear(nn.Module):
@@ -158,7 +163,8 @@ class KANLinear(nn.Module):
 
     def forward(self, x: Tensor) -> Tensor:
         assert x.dim() == 2 and x.size(1) == self.in_features
-        _module_backend_guard(x, self._params())
+        if _module_backend_guard(x, self._params(), grad_ok=True):
+            return autograd.kan_linear(self, x)
         return ops.fused_layer(ops.AggSpec(L.AGG_NONE, x.to(torch.float32)), x.size(0), [self.kernel_spec()])
 
 
@@ -180,7 +186,10 @@ class KAN(nn.Module):
     def forward(self, x: Tensor, update_grid: bool = False) -> Tensor:
         if update_grid:
             raise NotImplementedError("update_grid is never used by the reference drivers and is not implemented")
-        _module_backend_guard(x, list(self.parameters()))
+        if _module_backend_guard(x, list(self.parameters()), grad_ok=True):
+            for layer in self.layers:               # one launch per layer: every layer's input is kept for its backward
+                x = layer(x)
+            return x
         return chain_forward(self, x)
 
 

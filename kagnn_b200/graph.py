@@ -24,6 +24,10 @@ class GraphCSR:
         self.csr = ops.csr_build(edge_index, num_nodes, num_src_nodes)
         self.num_nodes = num_nodes
         self._gcn: Optional[Tuple[Tensor, Tensor, Tensor]] = None
+        self._edge_index = edge_index
+        self._square = num_src_nodes is None or num_src_nodes == num_nodes
+        self._transposed: Optional["GraphCSR"] = None
+        self._gcn_t: Optional[Tuple[Tensor, Tensor]] = None
 
     rowptr = property(lambda self: self.csr.rowptr)
     col = property(lambda self: self.csr.col)
@@ -38,6 +42,27 @@ class GraphCSR:
         if self._gcn is None:
             self._gcn = ops.gcn_norm(self.csr)
         return self._gcn[0], self._gcn[1]
+
+
+    # -- backward: the adjoint of an aggregation is the same aggregation over the reversed edges --------------------
+    def transposed(self) -> "GraphCSR":
+        """CSR of the reversed edges (built on first use, i.e. only when something is differentiated)."""
+        if self._transposed is None:
+            if not self._square:
+                raise NotImplementedError("the backward of a sharded (rectangular) graph is not implemented")
+            self._transposed = GraphCSR(self._edge_index.flip(0), self.num_nodes)
+        return self._transposed
+
+    def gcn_weights_transposed(self) -> Tuple[Tensor, Tensor]:
+        """gcn_norm edge weights in the entry order of ``transposed()`` (an edge keeps its weight) + the self weights."""
+        if self._gcn_t is None:
+            w, sw = self.gcn_weights()
+            gt = self.transposed()
+            by_edge = torch.empty_like(w)
+            by_edge[self.csr.perm.long()] = w                       # forward CSR order -> original edge order (a permutation)
+            w_t = ops.gather_rows(by_edge.view(-1, 1), gt.csr.perm).view(-1) if w.numel() else w
+            self._gcn_t = (w_t, sw)
+        return self._gcn_t
 
 
 _CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()

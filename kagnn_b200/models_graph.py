@@ -12,11 +12,11 @@ import torch
 from torch import nn
 
 from . import _lib as L
-from . import ops
+from . import autograd, ops
 from .conv import FASTKAGCN_Layer, GINConv, KAGCN_Layer, make_fastkan, make_kan
 from .ekan import _module_backend_guard
 from .graph import get_graph
-from .models_node import _BNFold, bn_is_foldable
+from .models_node import _BNFold, bn_is_foldable, bn_unfused
 
 Tensor = torch.Tensor
 
@@ -28,8 +28,10 @@ def _num_graphs(data) -> int:
     return int(data.batch.max()) + 1 if data.batch.numel() else 0
 
 
-def pooled_readout(x: Tensor, batch: Tensor, num_graphs: int, readout: nn.Module, mean: bool) -> Tensor:
+def pooled_readout(x: Tensor, batch: Tensor, num_graphs: int, readout: nn.Module, mean: bool, needs_grad: bool = False) -> Tensor:
     """global_add_pool / global_mean_pool (graph_classification/models.py:117,192) fused with the readout KAN."""
+    if needs_grad:
+        return readout(autograd.pool(x, batch, num_graphs, mean))
     ptr = ops.segment_ptr(batch, num_graphs)
     agg = ops.AggSpec(L.AGG_SEGMENT_MEAN if mean else L.AGG_SEGMENT_SUM, x, rowptr=ptr)
     specs = readout.kernel_specs()
@@ -41,8 +43,13 @@ def pooled_readout(x: Tensor, batch: Tensor, num_graphs: int, readout: nn.Module
 
 
 def _bn_unfused(x: Tensor, bn: nn.BatchNorm1d) -> Tensor:
-    from .models_node import _bn_eval
-    return ops.batchnorm_forward(x, bn) if (bn.training or bn.running_mean is None) else _bn_eval(x, bn)
+    return bn_unfused(x, bn)
+
+
+def _eval_without_no_grad(model: nn.Module, data) -> Tensor:
+    """model.eval() with autograd enabled (graph_classification_utils.py:57-72): inference plan, result detached."""
+    with torch.no_grad():
+        return model.forward(data)
 
 
 class _GINGraphModel(nn.Module):
@@ -61,23 +68,27 @@ class _GINGraphModel(nn.Module):
     def _conv(self, i: int, x: Tensor, g, post, extra):
         return self.conv[i](x, g, post=post)
 
-    def _message_passing(self, x: Tensor, g, extra=None) -> Tensor:
-        fus = self._fusable()
+    def _message_passing(self, x: Tensor, g, extra=None, needs_grad: bool = False) -> Tensor:
+        fus = self._fusable() and not needs_grad
         for i in range(self.n_layers):
             if fus:
                 x = self._conv(i, x, g, self._folds[i].get(self.bn[i]), extra)
             else:
-                x = self.dropout(_bn_unfused(self._conv(i, x, g, None, extra), self.bn[i]))
+                x = self.dropout(bn_unfused(self._conv(i, x, g, None, extra), self.bn[i], needs_grad))
         return x
 
     def forward(self, data) -> Tensor:
         x = data.x
-        _module_backend_guard(x, list(self.parameters()))
+        needs_grad = _module_backend_guard(x, list(self.parameters()), grad_ok=True)
+        if needs_grad and not self.training:
+            return _eval_without_no_grad(self, data)
         x = x.to(torch.float32)
         g = get_graph(data.edge_index, x.size(0))
-        x = self._message_passing(x, g)
-        x = pooled_readout(x, data.batch, _num_graphs(data), self.kan, mean=False)
-        return ops.log_softmax(x) if self.log_softmax else x
+        x = self._message_passing(x, g, needs_grad=needs_grad)
+        x = pooled_readout(x, data.batch, _num_graphs(data), self.kan, mean=False, needs_grad=needs_grad)
+        if not self.log_softmax:
+            return x
+        return autograd.log_softmax(x) if needs_grad else ops.log_softmax(x)
 
 
 class KAGIN(_GINGraphModel):
@@ -105,9 +116,14 @@ class _GCNGraphModel(nn.Module):
     log_softmax = True
     mean_pool = True
 
-    def _message_passing(self, x: Tensor, g) -> Tensor:
+    def _message_passing(self, x: Tensor, g, needs_grad: bool = False) -> Tensor:
         n = x.size(0)
         if self.n_layers == 0:
+            return x
+        if needs_grad:
+            for i in range(self.n_layers):
+                c = self.conv[i]
+                x = self.dropout(autograd.silu(autograd.gcn_aggregate(c.transform(x), c.bias, g)))
             return x
         drop_off = (not self.training) or self.dropout.p == 0.0
         if not drop_off:
@@ -131,12 +147,16 @@ class _GCNGraphModel(nn.Module):
 
     def forward(self, data) -> Tensor:
         x = data.x
-        _module_backend_guard(x, list(self.parameters()))
+        needs_grad = _module_backend_guard(x, list(self.parameters()), grad_ok=True)
+        if needs_grad and not self.training:
+            return _eval_without_no_grad(self, data)
         x = self._encode(x)
         g = get_graph(data.edge_index, x.size(0))
-        x = self._message_passing(x, g)
-        x = pooled_readout(x, data.batch, _num_graphs(data), self.readout, mean=self.mean_pool)
-        return ops.log_softmax(x) if self.log_softmax else x
+        x = self._message_passing(x, g, needs_grad=needs_grad)
+        x = pooled_readout(x, data.batch, _num_graphs(data), self.readout, mean=self.mean_pool, needs_grad=needs_grad)
+        if not self.log_softmax:
+            return x
+        return autograd.log_softmax(x) if needs_grad else ops.log_softmax(x)
 
     def _encode(self, x: Tensor) -> Tensor:
         return x.to(torch.float32)

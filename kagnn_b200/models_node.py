@@ -20,7 +20,7 @@ import torch
 from torch import nn
 
 from . import _lib as L
-from . import ops
+from . import autograd, ops
 from .conv import FASTKAGCNConv, GIFASTKANLayer, GIKANLayer, KAGCNConv, GCNConv
 from .ekan import KANLinear, _module_backend_guard
 from .fastkan import FastKANLayer
@@ -63,6 +63,16 @@ def _bn_eval(x: Tensor, bn: nn.BatchNorm1d) -> Tensor:
     return ops.fused_layer(ops.AggSpec(L.AGG_NONE, x), x.size(0), [], pre=fold)
 
 
+def bn_unfused(x: Tensor, bn: nn.BatchNorm1d, needs_grad: bool = False) -> Tensor:
+    """BatchNorm1d as its own launches: batch statistics (training) or the folded affine (eval)."""
+    batch_stats = bn.training or bn.running_mean is None
+    if needs_grad:
+        if not batch_stats:
+            raise NotImplementedError("an eval-mode BatchNorm1d inside a differentiated forward has no backward here")
+        return autograd.batch_norm_train(x, bn)
+    return ops.batchnorm_forward(x, bn) if batch_stats else _bn_eval(x, bn)
+
+
 class _NodeModel(nn.Module):
     """Shared forward of GKAN_Nodes / GFASTKAN_Nodes."""
     convs: nn.ModuleList
@@ -78,7 +88,12 @@ class _NodeModel(nn.Module):
         return drop_off and all(bn_is_foldable(bn) for bn in self.bns)
 
     def forward(self, x: Tensor, edge_index: Tensor) -> Tensor:
-        _module_backend_guard(x, list(self.parameters()))
+        needs_grad = _module_backend_guard(x, list(self.parameters()), grad_ok=True)
+        if needs_grad and not self.training:
+            # model.eval() without torch.no_grad() (the reference's val()/test() loops of graph_classification_utils.py:57-72 do
+            # that): the fused inference plan, result detached from autograd
+            with torch.no_grad():
+                return self.forward(x, edge_index)
         x = x.to(torch.float32)
         n, f = x.shape
         g = get_graph(edge_index, n)
@@ -86,8 +101,8 @@ class _NodeModel(nn.Module):
         if n_mp == 0:
             return self.lay_out(x)
         hid = self.bns[0].num_features
-        if not self._fusable():
-            return self._forward_unfused(x, g)
+        if needs_grad or not self._fusable():
+            return self._forward_unfused(x, g, needs_grad)
         # skip concat (models.py:196-201) without any copy: every layer writes its column slice of the hidden buffer and
         # lay_out reads two-part rows [x | h_1 .. h_L] (KagnnAggregate.x_head)
         buf = torch.empty(n, n_mp * hid, dtype=torch.float32, device=x.device) if self.skip else None
@@ -109,11 +124,12 @@ class _NodeModel(nn.Module):
             return self.lay_out(cur)
         return ops.fused_layer(ops.AggSpec(L.AGG_NONE, buf, x_head=x), n, self.lay_out.kernel_specs())
 
-    def _forward_unfused(self, x: Tensor, g) -> Tensor:
+    def _forward_unfused(self, x: Tensor, g, needs_grad: bool = False) -> Tensor:
+        """Layer by layer; with ``needs_grad`` every step is an autograd.Function whose backward is a library launch."""
         feats = [x]
         for conv, bn in zip(self.convs, self.bns):
             x = conv(x, g)
-            x = ops.batchnorm_forward(x, bn) if (bn.training or bn.running_mean is None) else _bn_eval(x, bn)
+            x = bn_unfused(x, bn, needs_grad)
             x = self.dropout(x)
             feats.append(x)
         if self.skip:

@@ -82,7 +82,11 @@ class _GINERegression(_GINGraphModel):
 
     def forward(self, data) -> Tensor:
         x, edge_attr = data.x, data.edge_attr
-        _module_backend_guard(x, list(self.parameters()))
+        if _module_backend_guard(x, list(self.parameters()), grad_ok=not self.training):
+            # eval() without no_grad (graph_regression/optuna_zinc.py:68-86): inference plan, result detached.  Training the
+            # GINE models needs the backward of the relu(x_j + e_ji) message, which is not built yet (grad_ok=False raises).
+            with torch.no_grad():
+                return self.forward(data)
         if edge_attr.dim() == 1:
             edge_attr = edge_attr.unsqueeze(1)
         n = x.size(0)

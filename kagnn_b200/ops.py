@@ -497,3 +497,120 @@ def tc_selftest(a: Tensor, b: Tensor, nprod: int = 3) -> Tensor:
     L.check(L.lib().kagnn_tc_selftest(_p(a), _p(b), n, k, _p(d), nprod, _p(ws), wb, _stream()), "tc_selftest")
     launch_count += 2
     return d
+
+
+# ---------------------------------------------------------------------------------------------------
+# backward (include/kagnn_b200.h "Backward"; used by kagnn_b200/autograd.py)
+# ---------------------------------------------------------------------------------------------------
+def _layer_struct(spec: KanLayerSpec) -> L.KagnnKanLayer:
+    s = L.KagnnKanLayer()
+    spec.fill(s)
+    return s
+
+
+def kan_bwd_input(spec: KanLayerSpec, x: Tensor, dy: Tensor) -> Tensor:
+    """d loss / d x of one B-spline KAN layer (kagnn_kan_bwd_input)."""
+    global launch_count
+    ldx, ld_dy = _rows(x, "x"), _rows(dy, "dy")
+    dx = torch.empty(x.size(0), spec.in_features, dtype=torch.float32, device=x.device)
+    s = _layer_struct(spec)
+    L.check(L.lib().kagnn_kan_bwd_input(C.byref(s), _p(x), ldx, _p(dy), ld_dy, x.size(0), _p(dx), _rows(dx, "dx"), _stream()),
+            "kan_bwd_input")
+    launch_count += 1
+    return dx
+
+
+def kan_bwd_weights(spec: KanLayerSpec, x: Tensor, dy: Tensor) -> Tensor:
+    """Gradient of the packed fp32 weights [in][slots+1][out_pad4] (kagnn_kan_bwd_weights)."""
+    global launch_count
+    ldx, ld_dy = _rows(x, "x"), _rows(dy, "dy")
+    d_packed = torch.empty_like(spec.packed_w)
+    s = _layer_struct(spec)
+    L.check(L.lib().kagnn_kan_bwd_weights(C.byref(s), _p(x), ldx, _p(dy), ld_dy, x.size(0), _p(d_packed), _stream()),
+            "kan_bwd_weights")
+    launch_count += 1
+    return d_packed
+
+
+def kan_unpack_weight_grads(d_packed: Tensor, spline_w: Tensor, scaler: Optional[Tensor], need_base: bool = True):
+    """d_packed -> (d base_weight | None, d spline_weight, d spline_scaler | None) (kagnn_kan_unpack_weight_grads)."""
+    global launch_count
+    out_f, in_f, slots = spline_w.shape
+    sw = spline_w.detach().contiguous()
+    sc = None if scaler is None else scaler.detach().contiguous()
+    dev = spline_w.device
+    d_base = torch.empty(out_f, in_f, dtype=torch.float32, device=dev) if need_base else None
+    d_spline = torch.empty(out_f, in_f, slots, dtype=torch.float32, device=dev)
+    d_scaler = torch.empty(out_f, in_f, dtype=torch.float32, device=dev) if sc is not None else None
+    L.check(L.lib().kagnn_kan_unpack_weight_grads(_p(d_packed), _p(sw), _p(sc), in_f, out_f, slots, _p(d_base), _p(d_spline),
+                                                  _p(d_scaler), _stream()), "kan_unpack_weight_grads")
+    launch_count += 1
+    return d_base, d_spline, d_scaler
+
+
+def batchnorm_backward(x: Tensor, dy: Tensor, weight: Optional[Tensor], eps: float):
+    """Backward of training-mode BatchNorm1d -> (dx, d weight, d bias) (kagnn_batchnorm_train_bwd)."""
+    global launch_count
+    ldx, ld_dy = _rows(x, "x"), _rows(dy, "dy")
+    n, c = x.shape
+    dx = torch.empty(n, c, dtype=torch.float32, device=x.device)
+    dw = torch.empty(c, dtype=torch.float32, device=x.device)
+    db = torch.empty(c, dtype=torch.float32, device=x.device)
+    wbytes = L.lib().kagnn_batchnorm_bwd_workspace(c)
+    ws = torch.empty(wbytes, dtype=torch.uint8, device=x.device)
+    L.check(L.lib().kagnn_batchnorm_train_bwd(_p(x), ldx, _p(dy), ld_dy, n, c, _p(weight.detach()) if weight is not None else None,
+                                              float(eps), _p(dx), _rows(dx, "dx"), _p(dw), _p(db), _p(ws), wbytes, _stream()),
+            "batchnorm_train_bwd")
+    launch_count += 2
+    return dx, dw, db
+
+
+def column_sums(x: Tensor) -> Tensor:
+    global launch_count
+    ldx = _rows(x, "x")
+    out = torch.empty(x.size(1), dtype=torch.float32, device=x.device)
+    L.check(L.lib().kagnn_column_sums(_p(x), ldx, x.size(0), x.size(1), _p(out), _stream()), "column_sums")
+    launch_count += 1
+    return out
+
+
+def log_softmax_backward(y: Tensor, dy: Tensor) -> Tensor:
+    global launch_count
+    dx = torch.empty(y.size(0), y.size(1), dtype=torch.float32, device=y.device)
+    if y.numel():
+        L.check(L.lib().kagnn_log_softmax_bwd(_p(y), _rows(y, "y"), _p(dy), _rows(dy, "dy"), y.size(0), y.size(1), _p(dx),
+                                              _rows(dx, "dx"), _stream()), "log_softmax_bwd")
+        launch_count += 1
+    return dx
+
+
+def silu_forward(x: Tensor) -> Tensor:
+    global launch_count
+    y = torch.empty(x.size(0), x.size(1), dtype=torch.float32, device=x.device)
+    if x.numel():
+        L.check(L.lib().kagnn_silu_fwd(_p(x), _rows(x, "x"), x.size(0), x.size(1), _p(y), _rows(y, "y"), _stream()), "silu_fwd")
+        launch_count += 1
+    return y
+
+
+def silu_backward(x: Tensor, dy: Tensor) -> Tensor:
+    global launch_count
+    dx = torch.empty(x.size(0), x.size(1), dtype=torch.float32, device=x.device)
+    if x.numel():
+        L.check(L.lib().kagnn_silu_bwd(_p(x), _rows(x, "x"), _p(dy), _rows(dy, "dy"), x.size(0), x.size(1), _p(dx), _rows(dx, "dx"),
+                                       _stream()), "silu_bwd")
+        launch_count += 1
+    return dx
+
+
+def segment_pool_backward(d_pooled: Tensor, ptr: Tensor, batch: Tensor, num_rows: int, mean: bool) -> Tensor:
+    global launch_count
+    _need_cuda(ptr, "segment_ptr", torch.int32)
+    _need_cuda(batch, "batch", torch.int64)
+    cols = d_pooled.size(1)
+    dx = torch.empty(num_rows, cols, dtype=torch.float32, device=d_pooled.device)
+    if num_rows:
+        L.check(L.lib().kagnn_segment_pool_bwd(_p(d_pooled), _rows(d_pooled, "d_pooled"), _p(ptr), _p(batch.contiguous()), num_rows, cols,
+                                               1 if mean else 0, _p(dx), _rows(dx, "dx"), _stream()), "segment_pool_bwd")
+        launch_count += 1
+    return dx

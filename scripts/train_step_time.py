@@ -1,0 +1,70 @@
+"""Time of one TRAINING step (forward + backward + Adam) of the arxiv-shaped GKAN_Nodes (gin, 3 layers, hidden 64, grid 5) on
+one B200 -- the first, untuned backward path (kagnn_b200/csrc/backward.cu).  CUDA events, 3 warm-ups, median of 10.
+
+    python scripts/train_step_time.py > gpurun_out/train_step.json
+"""
+import json
+import os
+import statistics
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import kagnn_b200 as kb
+from kagnn_b200 import ops
+
+
+def main():
+    dev = torch.device("cuda")
+    gen = torch.Generator().manual_seed(12345)
+    n, e, f, c = 169_343, 1_166_243, 128, 40
+    ei = torch.randint(0, n, (2, e), generator=gen).to(dev)
+    x = (torch.randn(n, f, generator=gen) * 0.3).to(dev)
+    y = torch.randint(0, c, (n,), generator=gen).to(dev)
+    torch.manual_seed(0)
+    model = kb.GKAN_Nodes("gin", 3, f, 64, c, skip=True, grid_size=5, spline_order=3, hidden_layers=2, dropout=0.0).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+
+    def step():
+        model.train()
+        opt.zero_grad(set_to_none=True)
+        loss = torch.nn.functional.cross_entropy(model(x, ei), y)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def fwd_only():
+        model.train()
+        with torch.no_grad():
+            return model(x, ei)
+
+    def timed(fn, steps=10, warmup=3):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(steps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return statistics.median(ts)
+
+    l0 = float(step())
+    t_step = timed(step)
+    l1 = float(step())
+    t_fwd = timed(fwd_only)
+    c0 = ops.launch_count
+    step()
+    launches = ops.launch_count - c0
+    print(json.dumps({"config": "arxiv-shaped GKAN_Nodes gin 3x64 grid 5, training step (fwd + bwd + Adam), batch-statistics BatchNorm",
+                      "nodes": n, "edges": e, "train_step_ms": t_step, "train_mode_forward_ms": t_fwd,
+                      "nodes_per_s_training": n / t_step * 1e3, "library_launches_per_step": launches,
+                      "loss_first": l0, "loss_after_14_steps": l1,
+                      "max_memory_gb": torch.cuda.max_memory_allocated() / 2**30}))
+
+
+if __name__ == "__main__":
+    main()

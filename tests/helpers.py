@@ -109,7 +109,7 @@ def load_grad_golden(name):
 
 def oracle_grads(meta, inputs, sd):
     """Autograd through the oracle: the same quantities the fixture holds."""
-    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not k.endswith(("grid", "running_mean", "running_var"))
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not k.endswith(("grid", "running_mean", "running_var", "eps"))
               else v.clone()) for k, v in sd.items()}
     x = inputs["x"].clone().requires_grad_(True)
     ins = dict(inputs, x=x)

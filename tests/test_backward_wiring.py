@@ -1,0 +1,73 @@
+"""CPU dry run of the autograd wiring (kagnn_b200/autograd.py and the modules' training paths): forward launches replaced
+by torch-CPU stand-ins, backward launches served by the host-check build of backward.cu (tests/emul/cpu_double.py -- test
+infrastructure).  Checked against gradients computed by the reference's own modules (tests/golden/grad/).  The same
+scenarios run against the real library on the B200 in tests/test_gpu_backward.py."""
+import pytest
+import torch
+
+from oracle import kagnn_oracle as K
+from tests.emul.cpu_double import cpu_double
+from tests.helpers import build_product_model, grad_err, grad_golden_names, grad_scale, load_grad_golden
+
+TOL = 1e-4
+
+
+def run_product_grads(meta, inputs, sd, device):
+    model = build_product_model(meta, sd, device=device)
+    model.train(bool(meta.get("training", True)))
+    inp = {k: v.to(device) for k, v in inputs.items()}
+    x = inp["x"].clone().requires_grad_(True)
+    if meta["kind"] in ("kan_linear", "kan_chain"):
+        y = model(x)
+    elif meta["kind"] == "node":
+        y = model(x, inp["edge_index"])
+    else:
+        y = model(K.Batch(x, inp["edge_index"], inp["batch"]))
+    y.backward(inp["dy"])
+    grads = {n: p.grad for n, p in model.named_parameters() if p.grad is not None}
+    grads["__x"] = x.grad
+    return y.detach(), grads, model
+
+
+def check_against_fixture(name, device):
+    meta, inputs, sd, y_ref, g_ref = load_grad_golden(name)
+    y, g, model = run_product_grads(meta, inputs, sd, device)
+    assert K.rel_err(y.cpu(), y_ref) <= TOL
+    assert set(g) == set(g_ref), sorted(set(g) ^ set(g_ref))
+    scale = grad_scale(g_ref)
+    for k in g_ref:
+        assert g[k].shape == g_ref[k].shape, k
+        assert grad_err(g[k].cpu(), g_ref[k], scale) <= TOL, (name, k)
+    return model
+
+
+@pytest.mark.parametrize("name", grad_golden_names())
+def test_module_gradients_match_reference_dry_run(name):
+    with cpu_double():
+        check_against_fixture(name, "cpu")
+
+
+def test_eval_mode_with_autograd_enabled_takes_the_inference_plan():
+    """graph_classification_utils.py:57-72 evaluates with model.eval() but without torch.no_grad()."""
+    import kagnn_b200 as kb
+    with cpu_double():
+        m = kb.GKAN_Nodes("gin", 2, 6, 8, 3).eval()
+        x = torch.randn(20, 6)
+        ei = torch.randint(0, 20, (2, 50))
+        y = m(x, ei)
+        assert not y.requires_grad
+        with torch.no_grad():
+            assert torch.equal(y, m(x, ei))
+
+
+def test_modules_without_backward_raise_under_autograd():
+    import kagnn_b200 as kb
+    with cpu_double():
+        x = torch.randn(10, 4)
+        with pytest.raises(NotImplementedError):
+            kb.FastKANLayer(4, 3)(x)
+        with pytest.raises(NotImplementedError):
+            kb.GFASTKAN_Nodes("gin", 1, 4, 4, 2).train()(x, torch.randint(0, 10, (2, 20)))
+        conv = kb.GINEConv(kb.make_kan(4, 4, 4, 1, 5, 3))
+        with pytest.raises(NotImplementedError):
+            conv(x, torch.randint(0, 10, (2, 20)), torch.randn(20, 4))

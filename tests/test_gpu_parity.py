@@ -248,14 +248,16 @@ def test_results_are_deterministic():
     assert torch.equal(a, b)                           # CSR reduction order is fixed: bitwise reproducible
 
 
-def test_requires_no_grad_and_cuda():
+def test_requires_cuda_and_modules_without_backward_raise_under_autograd():
     import kagnn_b200 as kb
-    m = kb.KANLinear(4, 4).cuda()
-    with pytest.raises(NotImplementedError):
+    m = kb.FastKANLayer(4, 4).cuda()
+    with pytest.raises(NotImplementedError):              # FastKAN has no backward yet: loud, not silent
         m(torch.randn(3, 4).cuda())
+    y = kb.KANLinear(4, 4).cuda()(torch.randn(3, 4).cuda())
+    assert y.requires_grad                                # B-spline layers record themselves for autograd
     with pytest.raises(RuntimeError):
         with torch.no_grad():
-            m(torch.randn(3, 4))
+            kb.KANLinear(4, 4).cuda()(torch.randn(3, 4))
 
 
 def test_arxiv_scale_model_against_oracle():
