@@ -9,7 +9,7 @@ Inside ``with cpu_double():``
 * the "CUDA tensors only" guards are lifted.
 
 Nothing here is reachable from the product: the patches are applied by the tests and undone on exit.  The GPU tests
-(tests/test_gpu_backward.py) run the same scenarios against the real library."""
+(tests/test_gpu_train_backward.py) run the same scenarios against the real library."""
 import contextlib
 import ctypes as C
 

@@ -1,7 +1,7 @@
 """CPU check of the backward kernels' index arithmetic: kagnn_b200/csrc/backward.cu compiled as serial host code
 (tests/emul/build_emul.py -- test infrastructure, never loaded by the product) against torch autograd through the oracle
 (the reference's own forward restated, node_classification_clean/ekan.py:79-162).  The real CUDA build of the same source is
-checked on the B200 by tests/test_gpu_backward.py."""
+checked on the B200 by tests/test_gpu_train_backward.py."""
 import ctypes as C
 
 import pytest
