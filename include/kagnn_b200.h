@@ -278,6 +278,23 @@ int kagnn_silu_bwd(const float* x, int64_t ldx, const float* dy, int64_t ld_dy, 
 int kagnn_segment_pool_bwd(const float* d_pooled, int64_t ld_dp, const int32_t* segment_ptr, const int64_t* batch,
                            int64_t num_rows, int32_t num_cols, int32_t mean, float* dx, int64_t ld_dx, void* stream);
 
+/* FastKAN layer (fastkan.py:76-85), z = LayerNorm(x):
+ *   dz[n,i] = sum_g phi_g'(z) sum_o dy[n,o] Ws[o,i*G+g]      dx_base[n,i] = silu'(x) sum_o dy[n,o] Wb[o,i]
+ * ln_stats = per-row (mean, rstd) from kagnn_layernorm_stats (NULL for a layer without LayerNorm: then dz receives the complete
+ * input gradient dz + dx_base and dx_base is ignored).  Reads layer->packed_w, ln_weight, ln_bias. */
+int kagnn_rbf_bwd_input(const KagnnKanLayer* layer, const float* x, int64_t ldx, const float* ln_stats_or_null, const float* dy,
+                        int64_t ld_dy, int64_t num_rows, float* dz, int64_t ld_dz, float* dx_base, int64_t ld_dxb, void* stream);
+
+/* Gradient of the packed FastKAN weights [in][G+1][out_pad4] (slot G = base_linear.weight); zeroed by the call. */
+int kagnn_rbf_bwd_weights(const KagnnKanLayer* layer, const float* x, int64_t ldx, const float* ln_stats_or_null, const float* dy,
+                          int64_t ld_dy, int64_t num_rows, float* d_packed, void* stream);
+
+/* LayerNorm backward: dx = rstd (dz w - mean_i(dz w) - xhat mean_i(dz w xhat)) [+ dx_base]; d_weight = sum_n dz xhat,
+ * d_bias = sum_n dz (either may be NULL; zeroed by the call). */
+int kagnn_layernorm_bwd(const float* x, int64_t ldx, const float* ln_stats, const float* ln_weight_or_null, const float* dz,
+                        int64_t ld_dz, const float* dx_base_or_null, int64_t ld_dxb, int64_t num_rows, int32_t num_cols, float* dx,
+                        int64_t ld_dx, float* d_weight_or_null, float* d_bias_or_null, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -106,6 +106,12 @@ _SIGNATURES = {
     "kagnn_silu_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
     "kagnn_segment_pool_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
                                          C.c_int64, C.c_void_p]),
+    "kagnn_rbf_bwd_input": (C.c_int, [C.POINTER(KagnnKanLayer), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                      C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
+    "kagnn_rbf_bwd_weights": (C.c_int, [C.POINTER(KagnnKanLayer), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                        C.c_void_p, C.c_void_p]),
+    "kagnn_layernorm_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                      C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "kagnn_gather_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
 }
 

@@ -5,8 +5,8 @@ graph_classification/graph_classification_utils.py:52 -- run on them.
 Every forward below is the same library launch the inference path uses; every backward is a library launch too
 (``kagnn_kan_bwd_*``, ``kagnn_batchnorm_train_bwd``, ... in include/kagnn_b200.h, or the forward aggregation kernel on the
 TRANSPOSED CSR).  torch contributes the autograd tape, ``torch.cat`` of the skip connection and ``nn.Dropout``'s mask.
-Scope of this first backward: B-spline KAN layers, GIN / GCN aggregation, BatchNorm1d, SiLU, add / mean pooling,
-log_softmax.  FastKAN layers and the GINE message raise ``NotImplementedError`` under autograd."""
+Scope of this first backward: B-spline and FastKAN layers, GIN / GCN aggregation, BatchNorm1d, SiLU, add / mean pooling,
+log_softmax.  The GINE message raises ``NotImplementedError`` under autograd."""
 from __future__ import annotations
 
 from typing import Optional
@@ -57,6 +57,50 @@ class _KanLinearFn(torch.autograd.Function):
 def kan_linear(layer, x: Tensor) -> Tensor:
     scaler = layer.spline_scaler if layer.enable_standalone_scale_spline else None
     return _KanLinearFn.apply(x, layer.base_weight, layer.spline_weight, scaler, layer)
+
+
+class _FastKanLayerFn(torch.autograd.Function):
+    """y = FastKANLayer(x) (fastkan.py:76-85): spline_linear(rbf(layernorm(x))) + base_linear(silu(x))."""
+
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, spline_w, base_w, base_b, layer):
+        spec = layer.kernel_spec()
+        x = _rowmajor(x)
+        y = ops.fused_layer(ops.AggSpec(L.AGG_NONE, x), x.size(0), [spec])
+        ctx.spec, ctx.layer = spec, layer
+        ctx.has_ln, ctx.ln_affine, ctx.has_base = layer.layernorm is not None, ln_w is not None, base_w is not None
+        ctx.save_for_backward(x, spline_w, ln_w if ln_w is not None else spline_w)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, spline_w, ln_w = ctx.saved_tensors
+        ln_w = ln_w if ctx.ln_affine else None
+        dy = _rowmajor(dy)
+        spec, lay = ctx.spec, ctx.layer
+        stats = ops.layernorm_stats(x) if ctx.has_ln else None          # recomputed, not kept: (rows, 2)
+        dx = d_lnw = d_lnb = d_spline = d_base = d_bb = None
+        if ctx.needs_input_grad[0] or (ctx.has_ln and any(ctx.needs_input_grad[1:3])):
+            dz, dxb = ops.rbf_bwd_input(spec, x, stats, dy)
+            if ctx.has_ln:
+                dx, d_lnw, d_lnb = ops.layernorm_backward(x, stats, ln_w, dz, dxb, ctx.ln_affine)
+            else:
+                dx = dz
+        if ctx.needs_input_grad[3] or (ctx.has_base and ctx.needs_input_grad[4]):
+            d_packed = ops.rbf_bwd_weights(spec, x, stats, dy)
+            sw3 = spline_w.detach().view(lay.output_dim, lay.input_dim, -1)
+            d_base, d_spline3, _ = ops.kan_unpack_weight_grads(d_packed, sw3, None, need_base=ctx.has_base)
+            d_spline = d_spline3.view_as(spline_w)
+        if ctx.has_base and ctx.needs_input_grad[5]:
+            d_bb = ops.column_sums(dy)
+        return dx, d_lnw, d_lnb, d_spline, d_base, d_bb, None
+
+
+def fastkan_layer(layer, x: Tensor) -> Tensor:
+    ln = layer.layernorm
+    base = layer.base_linear if layer.use_base_update else None
+    return _FastKanLayerFn.apply(x, None if ln is None else ln.weight, None if ln is None else ln.bias, layer.spline_linear.weight,
+                                 None if base is None else base.weight, None if base is None else base.bias, layer)
 
 
 class _GinAggFn(torch.autograd.Function):

@@ -394,3 +394,214 @@ extern "C" int kagnn_silu_fwd(const float* x, int64_t ldx, int64_t rows, int32_t
     KAGNN_LAUNCH_CHECK();
     return KAGNN_OK;
 }
+
+// =====================================================================================================================
+// FastKAN layer (fastkan.py:76-85):  z = LayerNorm(x),  y = sum_i sum_g phi_g(z_i) Ws[o, i*G+g] + sum_i silu(x_i) Wb[o,i] + bb[o],
+// phi_g(z) = exp(-((z - c_g) / den)^2).  Gradients:
+//   dz[n,i]  = sum_g phi_g'(z) sum_o dy[n,o] Ws[o,i,g],   phi_g' = -2 (z - c_g) / den^2 * phi_g
+//   dxb[n,i] = silu'(x) sum_o dy[n,o] Wb[o,i]                                (the base branch sees the RAW x)
+//   dP[i][g][o] = sum_n dy[n,o] phi_g(z[n,i]),  dP[i][G][o] = sum_n dy[n,o] silu(x[n,i])      (packed layout, no scaler)
+//   LayerNorm: xhat = (x - mean) rstd, z = xhat gamma + beta;  dgamma = sum_n dz xhat, dbeta = sum_n dz,
+//              dx = rstd (dz gamma - mean_i(dz gamma) - xhat mean_i(dz gamma xhat)) + dxb
+// =====================================================================================================================
+namespace {
+constexpr int kMaxGrids = 32;
+
+struct RbfGeom {
+    int in_f, out_f, out_pad, G;
+    float c0, step, inv_den;
+    const float* ln_w;      // NULL = no LayerNorm
+    const float* ln_b;
+};
+
+__device__ __forceinline__ float rbf_input(const RbfGeom& g, const float* __restrict__ stats, long long n, int i, float xv) {
+    if (!stats) return xv;
+    float z = (xv - stats[2 * n]) * stats[2 * n + 1];
+    if (g.ln_w) z *= g.ln_w[i];
+    if (g.ln_b) z += g.ln_b[i];
+    return z;
+}
+
+// block = 256 rows x one input feature (blockIdx.y), thread = row
+__global__ void rbf_bwd_input_kernel(RbfGeom g, const float* __restrict__ w, const float* __restrict__ x, long long ldx,
+                                     const float* __restrict__ stats, const float* __restrict__ dy, long long ld_dy,
+                                     long long n_rows, float* __restrict__ dz, long long ld_dz, float* __restrict__ dxb,
+                                     long long ld_dxb) {
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = (int)blockIdx.y;
+    if (n >= n_rows) return;
+    const float xv = x[n * ldx + i];
+    const float z = rbf_input(g, stats, n, i, xv);
+    const float* wi = w + (long long)i * (g.G + 1) * g.out_pad;
+    const float* wb = wi + (long long)g.G * g.out_pad;
+    const float* dyr = dy + n * ld_dy;
+    float gs[kMaxGrids];
+    for (int q = 0; q < g.G; ++q) gs[q] = 0.f;
+    float gb = 0.f;
+    for (int o = 0; o < g.out_f; ++o) {
+        const float d = dyr[o];
+        gb = fmaf(d, wb[o], gb);
+        for (int q = 0; q < g.G; ++q) gs[q] = fmaf(d, wi[(long long)q * g.out_pad + o], gs[q]);
+    }
+    float acc = 0.f;
+    for (int q = 0; q < g.G; ++q) {
+        const float t = (z - (g.c0 + (float)q * g.step)) * g.inv_den;
+        acc = fmaf(-2.0f * t * g.inv_den * expf(-t * t), gs[q], acc);
+    }
+    const float s = sigmoid_f(xv);
+    const float base = gb * (s * (1.0f + xv * (1.0f - s)));
+    if (dxb) {
+        dz[n * ld_dz + i] = acc;
+        dxb[n * ld_dxb + i] = base;
+    } else {
+        dz[n * ld_dz + i] = acc + base;          // no LayerNorm: this is the complete input gradient
+    }
+}
+
+// block = one input feature x one slab of rows, thread = output column
+__global__ void rbf_bwd_weights_kernel(RbfGeom g, const float* __restrict__ x, long long ldx, const float* __restrict__ stats,
+                                       const float* __restrict__ dy, long long ld_dy, long long n_rows, long long rows_per_block,
+                                       float* __restrict__ dP) {
+    const int i = (int)(blockIdx.x % g.in_f);
+    const int o = (int)(blockIdx.x / g.in_f) * (int)blockDim.x + (int)threadIdx.x;
+    if (o >= g.out_f) return;
+    const long long r0 = (long long)blockIdx.y * rows_per_block;
+    const long long r1 = min(n_rows, r0 + rows_per_block);
+    float acc[kMaxGrids + 1];
+    for (int q = 0; q <= g.G; ++q) acc[q] = 0.f;
+    for (long long n = r0; n < r1; ++n) {
+        const float xv = x[n * ldx + i];
+        const float z = rbf_input(g, stats, n, i, xv);
+        const float d = dy[n * ld_dy + o];
+        for (int q = 0; q < g.G; ++q) {
+            const float t = (z - (g.c0 + (float)q * g.step)) * g.inv_den;
+            acc[q] = fmaf(d, expf(-t * t), acc[q]);
+        }
+        acc[g.G] = fmaf(d, xv * sigmoid_f(xv), acc[g.G]);
+    }
+    float* out = dP + (long long)i * (g.G + 1) * g.out_pad + o;
+    for (int q = 0; q <= g.G; ++q)
+        if (acc[q] != 0.f) atomicAdd(out + (long long)q * g.out_pad, acc[q]);
+}
+
+// thread = row: dx = rstd (dz gamma - mean(dz gamma) - xhat mean(dz gamma xhat)) + dxb
+__global__ void layernorm_bwd_rows_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ stats,
+                                          const float* __restrict__ ln_w, const float* __restrict__ dz, long long ld_dz,
+                                          const float* __restrict__ dxb, long long ld_dxb, long long n_rows, int cols,
+                                          float* __restrict__ dx, long long ld_dx) {
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_rows) return;
+    const float mean = stats[2 * n], rstd = stats[2 * n + 1];
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = 0; i < cols; ++i) {
+        const float gz = dz[n * ld_dz + i] * (ln_w ? ln_w[i] : 1.0f);
+        const float xh = (x[n * ldx + i] - mean) * rstd;
+        s1 += gz;
+        s2 = fmaf(gz, xh, s2);
+    }
+    const float inv_f = 1.0f / (float)cols;
+    for (int i = 0; i < cols; ++i) {
+        const float gz = dz[n * ld_dz + i] * (ln_w ? ln_w[i] : 1.0f);
+        const float xh = (x[n * ldx + i] - mean) * rstd;
+        float v = rstd * (gz - s1 * inv_f - xh * s2 * inv_f);
+        if (dxb) v += dxb[n * ld_dxb + i];
+        dx[n * ld_dx + i] = v;
+    }
+}
+
+// dgamma[i] += sum over a slab of rows dz xhat, dbeta[i] += sum dz     (thread = column)
+__global__ void layernorm_bwd_params_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ stats,
+                                            const float* __restrict__ dz, long long ld_dz, long long n_rows, int cols,
+                                            long long rows_per_block, float* __restrict__ d_w, float* __restrict__ d_b) {
+    const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(n_rows, r0 + rows_per_block);
+    for (int c = (int)threadIdx.x; c < cols; c += (int)blockDim.x) {
+        double sw = 0.0, sb = 0.0;
+        for (long long r = r0; r < r1; ++r) {
+            const double d = (double)dz[r * ld_dz + c];
+            sw += d * (double)((x[r * ldx + c] - stats[2 * r]) * stats[2 * r + 1]);
+            sb += d;
+        }
+        if (d_w) atomicAdd(&d_w[c], (float)sw);
+        if (d_b) atomicAdd(&d_b[c], (float)sb);
+    }
+}
+
+int rbf_geometry(const KagnnKanLayer* L, const float* stats, RbfGeom* g) {
+    if (!L || !L->packed_w) return KAGNN_EINVAL;
+    if (L->basis != KAGNN_BASIS_RBF) return KAGNN_EINVAL;
+    if (L->in_features <= 0 || L->out_features <= 0 || L->grid_size < 1) return KAGNN_EINVAL;
+    if (L->grid_size > kMaxGrids) return KAGNN_EUNSUPPORTED;
+    if ((L->ln_weight || L->ln_bias) && !stats) return KAGNN_EINVAL;          // a LayerNorm layer needs its row statistics
+    g->in_f = L->in_features;
+    g->out_f = L->out_features;
+    g->out_pad = pad4(L->out_features);
+    g->G = L->grid_size;
+    g->c0 = L->t0;
+    g->step = L->h;
+    g->inv_den = L->inv_denominator;
+    g->ln_w = stats ? L->ln_weight : nullptr;
+    g->ln_b = stats ? L->ln_bias : nullptr;
+    return KAGNN_OK;
+}
+}  // namespace
+
+extern "C" int kagnn_rbf_bwd_input(const KagnnKanLayer* layer, const float* x, int64_t ldx, const float* ln_stats, const float* dy,
+                                   int64_t ld_dy, int64_t num_rows, float* dz, int64_t ld_dz, float* dx_base, int64_t ld_dxb,
+                                   void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    RbfGeom g;
+    const int rc = rbf_geometry(layer, ln_stats, &g);
+    if (rc != KAGNN_OK) return rc;
+    if (num_rows < 0 || (num_rows > 0 && (!x || !dy || !dz)) || ldx < g.in_f || ld_dy < g.out_f || ld_dz < g.in_f) return KAGNN_EINVAL;
+    if (ln_stats && (!dx_base || ld_dxb < g.in_f)) return KAGNN_EINVAL;       // with a LayerNorm the two branches stay separate
+    if (g.in_f > 65535) return KAGNN_EUNSUPPORTED;
+    if (num_rows == 0) return KAGNN_OK;
+    KAGNN_LAUNCH(rbf_bwd_input_kernel, dim3((unsigned)ceil_div64(num_rows, kBwdThreads), (unsigned)g.in_f, 1),
+                 dim3((unsigned)kBwdThreads, 1, 1), stream, g, layer->packed_w, x, (long long)ldx, ln_stats, dy, (long long)ld_dy,
+                 (long long)num_rows, dz, (long long)ld_dz, ln_stats ? dx_base : (float*)nullptr, (long long)ld_dxb);
+    KAGNN_LAUNCH_CHECK();
+    return KAGNN_OK;
+}
+
+extern "C" int kagnn_rbf_bwd_weights(const KagnnKanLayer* layer, const float* x, int64_t ldx, const float* ln_stats, const float* dy,
+                                     int64_t ld_dy, int64_t num_rows, float* d_packed, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    RbfGeom g;
+    const int rc = rbf_geometry(layer, ln_stats, &g);
+    if (rc != KAGNN_OK) return rc;
+    if (num_rows < 0 || !d_packed || (num_rows > 0 && (!x || !dy)) || ldx < g.in_f || ld_dy < g.out_f) return KAGNN_EINVAL;
+    KAGNN_CUDA_TRY(cudaMemsetAsync(d_packed, 0, sizeof(float) * (size_t)g.in_f * (size_t)(g.G + 1) * (size_t)g.out_pad, stream));
+    if (num_rows == 0) return KAGNN_OK;
+    const int threads = g.out_f >= 256 ? 256 : ((g.out_f + 31) / 32) * 32;
+    const int o_blocks = (g.out_f + threads - 1) / threads;
+    int64_t slabs = ceil_div64(num_rows, 512);
+    if (slabs > 64) slabs = 64;
+    const int64_t rows_per_block = ceil_div64(num_rows, slabs);
+    slabs = ceil_div64(num_rows, rows_per_block);
+    KAGNN_LAUNCH(rbf_bwd_weights_kernel, dim3((unsigned)(g.in_f * o_blocks), (unsigned)slabs, 1), dim3((unsigned)threads, 1, 1), stream,
+                 g, x, (long long)ldx, ln_stats, dy, (long long)ld_dy, (long long)num_rows, (long long)rows_per_block, d_packed);
+    KAGNN_LAUNCH_CHECK();
+    return KAGNN_OK;
+}
+
+extern "C" int kagnn_layernorm_bwd(const float* x, int64_t ldx, const float* ln_stats, const float* ln_weight, const float* dz,
+                                   int64_t ld_dz, const float* dx_base, int64_t ld_dxb, int64_t num_rows, int32_t num_cols,
+                                   float* dx, int64_t ld_dx, float* d_weight, float* d_bias, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (num_rows < 0 || num_cols <= 0 || ldx < num_cols || ld_dz < num_cols || ld_dx < num_cols) return KAGNN_EINVAL;
+    if (dx_base && ld_dxb < num_cols) return KAGNN_EINVAL;
+    if (d_weight) KAGNN_CUDA_TRY(cudaMemsetAsync(d_weight, 0, (size_t)num_cols * sizeof(float), stream));
+    if (d_bias) KAGNN_CUDA_TRY(cudaMemsetAsync(d_bias, 0, (size_t)num_cols * sizeof(float), stream));
+    if (num_rows == 0) return KAGNN_OK;
+    if (!x || !ln_stats || !dz || !dx) return KAGNN_EINVAL;
+    KAGNN_LAUNCH(layernorm_bwd_rows_kernel, (unsigned)ceil_div64(num_rows, 128), 128, stream, x, (long long)ldx, ln_stats, ln_weight,
+                 dz, (long long)ld_dz, dx_base, (long long)ld_dxb, (long long)num_rows, (int)num_cols, dx, (long long)ld_dx);
+    KAGNN_LAUNCH_CHECK();
+    if (d_weight || d_bias) {
+        const int64_t rows_per_block = 256;
+        KAGNN_LAUNCH(layernorm_bwd_params_kernel, (unsigned)ceil_div64(num_rows, rows_per_block), 128, stream, x, (long long)ldx,
+                     ln_stats, dz, (long long)ld_dz, (long long)num_rows, (int)num_cols, (long long)rows_per_block, d_weight, d_bias);
+        KAGNN_LAUNCH_CHECK();
+    }
+    return KAGNN_OK;
+}

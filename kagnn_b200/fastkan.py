@@ -13,7 +13,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import _lib as L
-from . import ops
+from . import autograd, ops
 from .ekan import _module_backend_guard, chain_forward
 
 Tensor = torch.Tensor
@@ -105,8 +105,9 @@ class FastKANLayer(nn.Module):
     def forward(self, x: Tensor, use_layernorm: bool = True) -> Tensor:
         if not use_layernorm and self.layernorm is not None:
             raise NotImplementedError("use_layernorm=False at call time is never used by the reference models")
-        _module_backend_guard(x, list(self.parameters()))
         lead = x.shape[:-1]
+        if _module_backend_guard(x, list(self.parameters()), grad_ok=True):
+            return autograd.fastkan_layer(self, x.reshape(-1, self.input_dim)).view(*lead, self.output_dim)
         y = ops.fused_layer(ops.AggSpec(L.AGG_NONE, x.reshape(-1, self.input_dim).to(torch.float32)),
                             x.numel() // self.input_dim, [self.kernel_spec()])
         return y.view(*lead, self.output_dim)
@@ -127,5 +128,8 @@ class FastKAN(nn.Module):
         return [lay.kernel_spec() for lay in self.layers]
 
     def forward(self, x: Tensor) -> Tensor:
-        _module_backend_guard(x, list(self.parameters()))
+        if _module_backend_guard(x, list(self.parameters()), grad_ok=True):
+            for layer in self.layers:               # one launch per layer: every layer's input is kept for its backward
+                x = layer(x)
+            return x
         return chain_forward(self, x)

@@ -614,3 +614,41 @@ def segment_pool_backward(d_pooled: Tensor, ptr: Tensor, batch: Tensor, num_rows
                                                1 if mean else 0, _p(dx), _rows(dx, "dx"), _stream()), "segment_pool_bwd")
         launch_count += 1
     return dx
+
+
+def rbf_bwd_input(spec: KanLayerSpec, x: Tensor, stats: Optional[Tensor], dy: Tensor):
+    """FastKAN layer: (dz, dx_base) with a LayerNorm (stats given), else (complete dx, None) (kagnn_rbf_bwd_input)."""
+    global launch_count
+    n = x.size(0)
+    dz = torch.empty(n, spec.in_features, dtype=torch.float32, device=x.device)
+    dxb = torch.empty(n, spec.in_features, dtype=torch.float32, device=x.device) if stats is not None else None
+    s = _layer_struct(spec)
+    L.check(L.lib().kagnn_rbf_bwd_input(C.byref(s), _p(x), _rows(x, "x"), _p(stats), _p(dy), _rows(dy, "dy"), n, _p(dz), _rows(dz, "dz"),
+                                        _p(dxb), _rows(dxb, "dxb") if dxb is not None else 0, _stream()), "rbf_bwd_input")
+    launch_count += 1
+    return dz, dxb
+
+
+def rbf_bwd_weights(spec: KanLayerSpec, x: Tensor, stats: Optional[Tensor], dy: Tensor) -> Tensor:
+    """Gradient of the packed FastKAN weights [in][G+1][out_pad4] (kagnn_rbf_bwd_weights)."""
+    global launch_count
+    d_packed = torch.empty_like(spec.packed_w)
+    s = _layer_struct(spec)
+    L.check(L.lib().kagnn_rbf_bwd_weights(C.byref(s), _p(x), _rows(x, "x"), _p(stats), _p(dy), _rows(dy, "dy"), x.size(0), _p(d_packed),
+                                          _stream()), "rbf_bwd_weights")
+    launch_count += 1
+    return d_packed
+
+
+def layernorm_backward(x: Tensor, stats: Tensor, ln_weight: Optional[Tensor], dz: Tensor, dx_base: Optional[Tensor], affine: bool):
+    """LayerNorm backward -> (dx, d weight | None, d bias | None) (kagnn_layernorm_bwd)."""
+    global launch_count
+    n, c = x.shape
+    dx = torch.empty(n, c, dtype=torch.float32, device=x.device)
+    dw = torch.empty(c, dtype=torch.float32, device=x.device) if affine else None
+    db = torch.empty(c, dtype=torch.float32, device=x.device) if affine else None
+    L.check(L.lib().kagnn_layernorm_bwd(_p(x), _rows(x, "x"), _p(stats), _p(ln_weight.detach()) if ln_weight is not None else None,
+                                        _p(dz), _rows(dz, "dz"), _p(dx_base), _rows(dx_base, "dx_base") if dx_base is not None else 0,
+                                        n, c, _p(dx), _rows(dx, "dx"), _p(dw), _p(db), _stream()), "layernorm_bwd")
+    launch_count += 2 if affine else 1
+    return dx, dw, db

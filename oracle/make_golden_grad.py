@@ -94,5 +94,47 @@ def main() -> None:
         _save(name, dict(kind="gc", training=True, **meta), dict(x=x, edge_index=ei, batch=batch, dy=dy), sd0, y, grads)
 
 
+def main_fastkan() -> None:
+    """FastKAN cases, own seed (added after the B-spline fixtures were validated on the GPU: those files stay byte-identical)."""
+    from . import pyg_shim
+    pyg_shim.install()
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(4242)
+    gen = torch.Generator().manual_seed(4242)
+    fastkan = _load(os.path.join(NC, "fastkan.py"), "ref_nc_fastkan")
+    for sizes, g in [([7, 32], 8), ([33, 5], 4), ([16, 16, 4], 8), ([5, 6, 7], 32)]:
+        net = fastkan.FastKAN(sizes, num_grids=g)
+        _randomise(net, gen)
+        x = torch.randn(40, sizes[0], generator=gen) * 1.5
+        sd0, y, dy, grads = _backprop(net, net, x, gen)
+        _save("grad_fastkan_" + "_".join(map(str, sizes)) + f"_g{g}", dict(kind="fastkan_chain", G=g), dict(x=x, dy=dy), sd0, y, grads)
+
+    ncm = _load(os.path.join(NC, "models.py"), "ref_nc_models")
+    n, e, f, c = 70, 260, 19, 5
+    ei = small_graph(n, e, gen)
+    x = torch.randn(n, f, generator=gen) * 0.7
+    for conv in ("gcn", "gin"):
+        m = ncm.GFASTKAN_Nodes(conv, 2, f, 10, c, skip=True, grid_size=6, hidden_layers=2, dropout=0.0).train()
+        _randomise(m, gen)
+        sd0, y, dy, grads = _backprop(m, lambda t: m(t, ei), x, gen)
+        _save(f"grad_nc_gfastkan_{conv}", dict(kind="node", conv_type=conv, skip=True, fast=True, training=True, mp_layers=2,
+              num_features=f, hidden=10, classes=c, G=6, hidden_layers=2), dict(x=x, edge_index=ei, dy=dy), sd0, y, grads)
+
+    gcm = _load(os.path.join(GC, "models.py"), "ref_gc_models")
+    ei, batch, n = batched_graphs(9, gen)
+    x = torch.randn(n, 7, generator=gen)
+    for name, mk, meta in [
+        ("grad_gc_fastkagin", lambda: gcm.FASTKAGIN(2, 7, 16, 2, 2, 8, 0.0), dict(family="FASTKAGIN", args=[2, 7, 16, 2, 2, 8, 0.0])),
+        ("grad_gc_fastkagcn", lambda: gcm.FASTKAGCN(2, 7, 12, 3, 5, 0.0), dict(family="FASTKAGCN", args=[2, 7, 12, 3, 5, 0.0])),
+    ]:
+        m = mk().train()
+        _randomise(m, gen)
+        sd0, y, dy, grads = _backprop(m, lambda t: m(K.Batch(t, ei, batch)), x, gen)
+        _save(name, dict(kind="gc", training=True, **meta), dict(x=x, edge_index=ei, batch=batch, dy=dy), sd0, y, grads)
+
+
 if __name__ == "__main__":
-    main()
+    import sys
+    if "--fastkan-only" not in sys.argv:
+        main()
+    main_fastkan()

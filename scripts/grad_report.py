@@ -8,7 +8,8 @@ from oracle import kagnn_oracle as K
 from tests.helpers import grad_err, grad_golden_names, grad_scale, load_grad_golden
 from tests.test_backward_wiring import run_product_grads
 
-for name in grad_golden_names():
+only = sys.argv[1] if len(sys.argv) > 1 else ""
+for name in [n for n in grad_golden_names() if only in n]:
     meta, inputs, sd, y_ref, g_ref = load_grad_golden(name)
     try:
         y, g, _ = run_product_grads(meta, inputs, sd, "cuda")

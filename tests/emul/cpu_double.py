@@ -22,7 +22,7 @@ from kagnn_b200 import graph as kgraph
 from tests.emul import build_emul
 
 _BACKWARD = ("kagnn_kan_bwd_input", "kagnn_kan_bwd_weights", "kagnn_kan_unpack_weight_grads", "kagnn_batchnorm_bwd_workspace",
-             "kagnn_batchnorm_train_bwd", "kagnn_column_sums", "kagnn_log_softmax_bwd", "kagnn_silu_fwd", "kagnn_silu_bwd", "kagnn_segment_pool_bwd")
+             "kagnn_batchnorm_train_bwd", "kagnn_column_sums", "kagnn_log_softmax_bwd", "kagnn_silu_fwd", "kagnn_silu_bwd", "kagnn_segment_pool_bwd", "kagnn_rbf_bwd_input", "kagnn_rbf_bwd_weights", "kagnn_layernorm_bwd")
 
 
 class _HostLib:
@@ -100,8 +100,23 @@ def _affine(a, v):
     return F.silu(v) if a.act == L.ACT_SILU else v
 
 
+def _layernorm_stats(x, x_head=None, eps=1e-5):
+    assert x_head is None
+    mean = x.mean(1)
+    return torch.stack([mean, (x.var(1, unbiased=False) + eps).rsqrt()], dim=1).contiguous()
+
+
 def _kan_layer(spec, x):
-    assert spec.basis == L.BASIS_BSPLINE, "the CPU double covers B-spline layers only"
+    if spec.basis == L.BASIS_RBF:
+        G = spec.grid_size
+        z = x
+        if spec.ln_weight is not None:
+            z = F.layer_norm(x, (x.size(1),), spec.ln_weight, spec.ln_bias, 1e-5)
+        centres = spec.t0 + spec.h * torch.arange(G)
+        phi = torch.exp(-((z.unsqueeze(-1) - centres) * spec.inv_denominator) ** 2)
+        w = spec.packed_w.view(spec.in_features, G + 1, -1)[:, :, :spec.out_features]
+        y = torch.einsum("nig,igo->no", phi, w[:, :G]) + F.silu(x) @ w[:, G]
+        return y if spec.base_bias is None else y + spec.base_bias
     S = spec.grid_size + spec.spline_order
     bases = ekan._uniform_bspline_design(x, spec.t0, spec.h, spec.grid_size, spec.spline_order)      # (n, in, S)
     w = spec.packed_w.view(spec.in_features, S + 1, -1)[:, :, :spec.out_features]
@@ -172,7 +187,7 @@ def cpu_double():
     patch(ops, "tc_supported", lambda *a: False)
     for name, fn in (("csr_build", _csr_build), ("gcn_norm", _gcn_norm), ("gather_rows", _gather_rows), ("segment_ptr", _segment_ptr),
                      ("pack_kan_weights", _pack), ("fused_layer", _fused_layer), ("batchnorm_forward", _batchnorm_forward),
-                     ("log_softmax", lambda x: torch.log_softmax(x, dim=1))):
+                     ("log_softmax", lambda x: torch.log_softmax(x, dim=1)), ("layernorm_stats", _layernorm_stats)):
         patch(ops, name, fn)
     for mod in (ekan, fastkan, conv, models_node, models_graph, models_regr):
         patch(mod, "_module_backend_guard", guard)

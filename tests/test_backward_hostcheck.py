@@ -164,3 +164,54 @@ def test_small_epilogue_backwards(lib):
         dh = torch.empty(11, 5)
         assert lib.kagnn_segment_pool_bwd(p(dp), C.c_int64(5), p(ptr), p(batch), C.c_int64(11), 5, mean, p(dh), C.c_int64(5), None) == 0
         assert K.rel_err(dh, h.grad) <= 1e-6
+
+
+@pytest.mark.parametrize("G,fin,fout,n,ln", [(8, 7, 5, 120, True), (4, 16, 3, 77, False), (32, 3, 9, 40, True), (1, 2, 2, 10, False),
+                                            (6, 5, 260, 30, True)])
+def test_fastkan_layer_gradients(lib, G, fin, fout, n, ln):
+    """rbf_bwd_input / rbf_bwd_weights / layernorm_bwd against autograd through the oracle's fastkan_layer (fastkan.py:76-85)."""
+    torch.manual_seed(G * 10 + fin)
+    grid = torch.linspace(-2.0, 2.0, G) if G > 1 else torch.tensor([-2.0])
+    den = 4.0 / (G - 1) if G > 1 else 1.0
+    x = (torch.randn(n, fin) * 1.3).requires_grad_(True)
+    lw = (1.0 + 0.3 * torch.randn(fin)).requires_grad_(True) if ln else None
+    lb = (0.2 * torch.randn(fin)).requires_grad_(True) if ln else None
+    sw = (torch.randn(fout, fin * G) * 0.3).requires_grad_(True)
+    bw = (torch.randn(fout, fin) * 0.3).requires_grad_(True)
+    bb = torch.randn(fout).requires_grad_(True)
+    dy = torch.randn(n, fout)
+    K.fastkan_layer(x, lw, lb, grid, sw, bw, bb, den).backward(dy)
+
+    packed = pack(bw.detach(), sw.detach().view(fout, fin, G), torch.ones(fout, fin))
+    lay = Layer(1, fin, fout, G, 0, -2.0, (4.0 / (G - 1)) if G > 1 else 1.0, 1.0 / den, packed.data_ptr(), None,
+                lw.data_ptr() if ln else None, lb.data_ptr() if ln else None, None, None)
+    xd = x.detach()
+    stats = None
+    if ln:
+        stats = torch.stack([xd.mean(1), (xd.var(1, unbiased=False) + 1e-5).rsqrt()], dim=1).contiguous()
+    dz = torch.empty(n, fin + 2)
+    dxb = torch.empty(n, fin + 1) if ln else None
+    lib.kagnn_rbf_bwd_input.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
+                                        C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
+    assert lib.kagnn_rbf_bwd_input(C.byref(lay), p(xd), fin, p(stats) if ln else None, p(dy), fout, n, p(dz), fin + 2,
+                                   p(dxb) if ln else None, fin + 1 if ln else 0, None) == 0
+    if ln:
+        dx = torch.empty(n, fin)
+        d_lw, d_lb = torch.empty(fin), torch.empty(fin)
+        lib.kagnn_layernorm_bwd.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                            C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        assert lib.kagnn_layernorm_bwd(p(xd), fin, p(stats), p(lw.detach()), p(dz), fin + 2, p(dxb), fin + 1, n, fin, p(dx), fin,
+                                       p(d_lw), p(d_lb), None) == 0
+        assert K.rel_err(d_lw, lw.grad) <= TOL and K.rel_err(d_lb, lb.grad) <= TOL
+    else:
+        dx = dz[:, :fin]
+    assert K.rel_err(dx, x.grad) <= TOL
+
+    dP = torch.full_like(packed, 9.0)
+    lib.kagnn_rbf_bwd_weights.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
+                                          C.c_void_p]
+    assert lib.kagnn_rbf_bwd_weights(C.byref(lay), p(xd), fin, p(stats) if ln else None, p(dy), fout, n, p(dP), None) == 0
+    d_base, d_spline = torch.empty(fout, fin), torch.empty(fout, fin, G)
+    assert lib.kagnn_kan_unpack_weight_grads(p(dP), p(sw.detach()), None, fin, fout, G, p(d_base), p(d_spline), None, None) == 0
+    assert K.rel_err(d_base, bw.grad) <= TOL
+    assert K.rel_err(d_spline.view(fout, fin * G), sw.grad) <= TOL

@@ -17,7 +17,7 @@ def run_product_grads(meta, inputs, sd, device):
     model.train(bool(meta.get("training", True)))
     inp = {k: v.to(device) for k, v in inputs.items()}
     x = inp["x"].clone().requires_grad_(True)
-    if meta["kind"] in ("kan_linear", "kan_chain"):
+    if meta["kind"] in ("kan_linear", "kan_chain", "fastkan_chain"):
         y = model(x)
     elif meta["kind"] == "node":
         y = model(x, inp["edge_index"])
@@ -64,10 +64,9 @@ def test_modules_without_backward_raise_under_autograd():
     import kagnn_b200 as kb
     with cpu_double():
         x = torch.randn(10, 4)
-        with pytest.raises(NotImplementedError):
-            kb.FastKANLayer(4, 3)(x)
-        with pytest.raises(NotImplementedError):
-            kb.GFASTKAN_Nodes("gin", 1, 4, 4, 2).train()(x, torch.randint(0, 10, (2, 20)))
         conv = kb.GINEConv(kb.make_kan(4, 4, 4, 1, 5, 3))
         with pytest.raises(NotImplementedError):
             conv(x, torch.randint(0, 10, (2, 20)), torch.randn(20, 4))
+        gin = kb.GINConv(kb.make_kan(4, 4, 4, 1, 5, 3), train_eps=True)
+        with pytest.raises(NotImplementedError):
+            gin(x, torch.randint(0, 10, (2, 20)))
