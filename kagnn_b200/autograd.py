@@ -24,8 +24,10 @@ def grad_needed(x: Tensor, params) -> bool:
 
 
 def _rowmajor(t: Tensor) -> Tensor:
+    """fp32, unit column stride, rows at least one row apart (the cotangent of ``y.sum()`` is an expanded, stride-0 tensor)."""
     t = t.to(torch.float32)
-    return t if t.dim() == 2 and (t.size(1) <= 1 or t.stride(1) == 1) else t.contiguous()
+    ok = t.dim() == 2 and (t.size(1) <= 1 or t.stride(1) == 1) and (t.size(0) <= 1 or t.stride(0) >= t.size(1))
+    return t if ok else t.contiguous()
 
 
 class _KanLinearFn(torch.autograd.Function):

@@ -70,3 +70,31 @@ def test_modules_without_backward_raise_under_autograd():
         gin = kb.GINConv(kb.make_kan(4, 4, 4, 1, 5, 3), train_eps=True)
         with pytest.raises(NotImplementedError):
             gin(x, torch.randint(0, 10, (2, 20)))
+
+
+@pytest.mark.parametrize("family,args", [("KAGCN", (1, 2, 16, 5, 3, 1, 0.0, True)), ("FASTKAGCN", (1, 2, 16, 4, 1, 0.0, True))])
+def test_graph_regression_gcn_models_train(family, args):
+    """graph_regression KAGCN / FASTKAGCN (OGB atom encoder -> GCN layers -> add pool -> read-out, one output column) with the
+    loss ``y.sum()``, whose cotangent is an expanded stride-0 tensor."""
+    from kagnn_b200 import models_regr
+    with cpu_double():
+        g = torch.Generator().manual_seed(0)
+        n = 30
+        x = torch.randint(0, 28, (n, 1), generator=g)
+        ei = torch.randint(0, n, (2, 80), generator=g)
+        batch = torch.sort(torch.randint(0, 4, (n,), generator=g))[0]
+        torch.manual_seed(1)
+        m = getattr(models_regr, family)(*args).train()
+        sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+        y = m(K.Batch(x, ei, batch))
+        y.sum().backward()
+        ref_sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not k.endswith("grid") else v) for k, v in sd.items()}
+        yr = K.gr_kagcn_forward(ref_sd, K.Batch(x, ei, batch))
+        yr.sum().backward()
+        assert K.rel_err(y, yr) <= 1e-5
+        g_ref = {k: v.grad for k, v in ref_sd.items() if isinstance(v, torch.Tensor) and v.requires_grad and v.grad is not None}
+        scale = grad_scale(g_ref)
+        got = {nm: p.grad for nm, p in m.named_parameters() if p.grad is not None}
+        assert set(got) == set(g_ref)
+        for k in g_ref:
+            assert grad_err(got[k], g_ref[k], scale) <= TOL, k
