@@ -295,6 +295,13 @@ int kagnn_layernorm_bwd(const float* x, int64_t ldx, const float* ln_stats, cons
                         int64_t ld_dz, const float* dx_base_or_null, int64_t ld_dxb, int64_t num_rows, int32_t num_cols, float* dx,
                         int64_t ld_dx, float* d_weight_or_null, float* d_bias_or_null, void* stream);
 
+/* Backward of the GINE aggregation a_i = self_scale x_i + sum_{e: dst_e = i} relu(x_{src_e} + ef_e) (PyG GINEConv,
+ * graph_regression/models.py:98) on the COO edge list: edge_index is the contiguous (2, E) int64 tensor, edge_feat has one row
+ * per edge in the same order.  dx (num_nodes x num_cols) is overwritten; d_edge_feat (E x num_cols) may be NULL. */
+int kagnn_gine_bwd(const float* x, int64_t ldx, const float* edge_feat, int64_t ld_edge, const int64_t* edge_index,
+                   int64_t num_edges, int64_t num_nodes, int32_t num_cols, const float* da, int64_t ld_da, float self_scale,
+                   float* dx, int64_t ld_dx, float* d_edge_feat_or_null, int64_t ld_de, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,8 +5,8 @@ graph_classification/graph_classification_utils.py:52 -- run on them.
 Every forward below is the same library launch the inference path uses; every backward is a library launch too
 (``kagnn_kan_bwd_*``, ``kagnn_batchnorm_train_bwd``, ... in include/kagnn_b200.h, or the forward aggregation kernel on the
 TRANSPOSED CSR).  torch contributes the autograd tape, ``torch.cat`` of the skip connection and ``nn.Dropout``'s mask.
-Scope of this first backward: B-spline and FastKAN layers, GIN / GCN aggregation, BatchNorm1d, SiLU, add / mean pooling,
-log_softmax.  The GINE message raises ``NotImplementedError`` under autograd."""
+Scope of this first backward: B-spline and FastKAN layers, GIN / GINE / GCN aggregation, BatchNorm1d, SiLU, add / mean
+pooling, log_softmax."""
 from __future__ import annotations
 
 from typing import Optional
@@ -124,6 +124,28 @@ class _GinAggFn(torch.autograd.Function):
 
 def gin_aggregate(x: Tensor, graph, self_scale: float) -> Tensor:
     return _GinAggFn.apply(x, graph, self_scale)
+
+
+class _GineAggFn(torch.autograd.Function):
+    """a_i = self_scale * x_i + sum_{j -> i} relu(x_j + e_ji) (PyG GINEConv); edge features in COO order, one row per edge."""
+
+    @staticmethod
+    def forward(ctx, x, edge_feat, graph, self_scale):
+        x, edge_feat = _rowmajor(x), _rowmajor(edge_feat)
+        ctx.graph, ctx.self_scale = graph, float(self_scale)
+        ctx.save_for_backward(x, edge_feat)
+        agg = ops.AggSpec(L.AGG_GINE, x, graph.rowptr, graph.col, self_scale=ctx.self_scale, edge_feat=edge_feat, edge_row=graph.perm)
+        return ops.fused_layer(agg, graph.num_nodes, [])
+
+    @staticmethod
+    def backward(ctx, da):
+        x, edge_feat = ctx.saved_tensors
+        dx, de = ops.gine_backward(x, edge_feat, ctx.graph.edge_index, _rowmajor(da), ctx.self_scale, ctx.needs_input_grad[1])
+        return dx, de, None, None
+
+
+def gine_aggregate(x: Tensor, edge_feat: Tensor, graph, self_scale: float) -> Tensor:
+    return _GineAggFn.apply(x, edge_feat, graph, self_scale)
 
 
 class _GcnAggFn(torch.autograd.Function):

@@ -18,6 +18,7 @@ additionally fuse across layer boundaries (models_*.py).
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -129,7 +130,7 @@ class GINConv(_MessagePassing):
 
     def forward(self, x: Tensor, edge_index, size=None, out: Optional[Tensor] = None,
                 post: Optional[ops.Affine] = None, **agg_kw) -> Tensor:
-        needs_grad = _module_backend_guard(x, list(self.parameters()), grad_ok=not isinstance(self, GINEConv))
+        needs_grad = _module_backend_guard(x, list(self.parameters()), grad_ok=True)
         g = self._graph(x, edge_index)
         if needs_grad:
             if post is not None or out is not None or agg_kw:
@@ -167,6 +168,18 @@ class GINEConv(GINConv):
         if edge_attr is None:
             raise ValueError("GINEConv needs edge_attr")
         g = self._graph(x, edge_index)
+        params = list(self.parameters())
+        if autograd.grad_needed(x, params) or (torch.is_grad_enabled() and edge_attr.requires_grad):
+            # Host-checked and dry-run on the CPU against the reference's gradients (tests/test_backward_wiring.py), but not yet
+            # run on a GPU: opt-in until it has been (the B-spline / FastKAN / GIN / GCN backward has).
+            _module_backend_guard(x, params, grad_ok=os.environ.get("KAGNN_EXPERIMENTAL_GINE_BACKWARD") == "1")
+            if edge_row is not None or out is not None or post is not None:
+                raise NotImplementedError("edge-feature tables / fused epilogues are inference-only")
+            if self.eps.requires_grad:
+                raise NotImplementedError("train_eps=True has no backward yet (the reference models keep eps fixed)")
+            if edge_attr.dim() != 2 or edge_attr.size(0) != g.csr.nnz or edge_attr.size(1) != x.size(1):
+                raise ValueError("Node and edge feature dimensionalities do not match")
+            return self.nn(autograd.gine_aggregate(x, edge_attr, g, 1.0 + self.eps_value()))
         if edge_row is None:
             if edge_attr.size(0) != g.csr.nnz or edge_attr.size(-1) != x.size(-1):
                 raise ValueError("Node and edge feature dimensionalities do not match")

@@ -605,3 +605,55 @@ extern "C" int kagnn_layernorm_bwd(const float* x, int64_t ldx, const float* ln_
     }
     return KAGNN_OK;
 }
+
+// =====================================================================================================================
+// GINE aggregation (PyG GINEConv as used at graph_regression/models.py:98):
+//   a_i = self_scale x_i + sum_{e: dst_e = i} relu(x_{src_e} + ef_e)
+//   dx_j = self_scale da_j + sum_{e: src_e = j} [x_j + ef_e > 0] da_{dst_e},      d ef_e = [x_{src_e} + ef_e > 0] da_{dst_e}
+// Works on the COO edge list (edge features in COO order, one row per edge); float atomics into dx.
+// =====================================================================================================================
+namespace {
+__global__ void scale_rows_kernel(const float* __restrict__ a, long long lda, long long rows, int cols, float s, float* __restrict__ y,
+                                  long long ldy) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * cols) return;
+    const int c = (int)(idx % cols);
+    const long long r = idx / cols;
+    y[r * ldy + c] = s * a[r * lda + c];
+}
+
+// thread = (edge e, column c)
+__global__ void gine_bwd_edges_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ ef, long long ld_e,
+                                      const int64_t* __restrict__ src, const int64_t* __restrict__ dst, long long n_edges, int cols,
+                                      const float* __restrict__ da, long long ld_da, float* __restrict__ dx, long long ld_dx,
+                                      float* __restrict__ d_ef, long long ld_de) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_edges * cols) return;
+    const int c = (int)(idx % cols);
+    const long long e = idx / cols;
+    const long long j = src[e], i = dst[e];
+    const float m = x[j * ldx + c] + ef[e * ld_e + c];
+    const float g = m > 0.f ? da[i * ld_da + c] : 0.f;
+    if (d_ef) d_ef[e * ld_de + c] = g;
+    if (g != 0.f) atomicAdd(&dx[j * ld_dx + c], g);
+}
+}  // namespace
+
+extern "C" int kagnn_gine_bwd(const float* x, int64_t ldx, const float* edge_feat, int64_t ld_edge, const int64_t* edge_index,
+                              int64_t num_edges, int64_t num_nodes, int32_t num_cols, const float* da, int64_t ld_da,
+                              float self_scale, float* dx, int64_t ld_dx, float* d_edge_feat, int64_t ld_de, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (num_nodes < 0 || num_edges < 0 || num_cols <= 0 || ldx < num_cols || ld_da < num_cols || ld_dx < num_cols) return KAGNN_EINVAL;
+    if (num_nodes > 0 && (!x || !da || !dx)) return KAGNN_EINVAL;
+    if (num_edges > 0 && (!edge_feat || !edge_index || ld_edge < num_cols || (d_edge_feat && ld_de < num_cols))) return KAGNN_EINVAL;
+    if (num_nodes == 0) return KAGNN_OK;
+    KAGNN_LAUNCH(scale_rows_kernel, (unsigned)ceil_div64(num_nodes * (int64_t)num_cols, kBwdThreads), kBwdThreads, stream, da,
+                 (long long)ld_da, (long long)num_nodes, (int)num_cols, self_scale, dx, (long long)ld_dx);
+    KAGNN_LAUNCH_CHECK();
+    if (num_edges == 0) return KAGNN_OK;
+    KAGNN_LAUNCH(gine_bwd_edges_kernel, (unsigned)ceil_div64(num_edges * (int64_t)num_cols, kBwdThreads), kBwdThreads, stream, x,
+                 (long long)ldx, edge_feat, (long long)ld_edge, edge_index, edge_index + num_edges, (long long)num_edges, (int)num_cols,
+                 da, (long long)ld_da, dx, (long long)ld_dx, d_edge_feat, (long long)ld_de);
+    KAGNN_LAUNCH_CHECK();
+    return KAGNN_OK;
+}

@@ -55,13 +55,13 @@ def _uniform_bspline_design(x: Tensor, t0: float, h: float, grid_size: int, orde
 
 def _module_backend_guard(x: Tensor, params: Sequence[Tensor], grad_ok: bool = False) -> bool:
     """Raises for CPU inputs (no fallback).  Returns True when autograd must record this call: modules that have a backward
-    (``grad_ok``) then take their ``kagnn_b200.autograd`` path; the others (the GINE message) raise."""
+    (``grad_ok``) then take their ``kagnn_b200.autograd`` path; a caller that cannot be differentiated passes False and raises."""
     if not x.is_cuda:
         raise RuntimeError("kagnn_b200 modules run on the B200 only: move the module and its inputs to a CUDA device "
                            "(there is deliberately no CPU fallback)")
     if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params)):
         if not grad_ok:
-            raise NotImplementedError("this kagnn_b200 module has no backward yet (GINE messages): call it under "
+            raise NotImplementedError("this kagnn_b200 call has no backward: use it under "
                                       "torch.no_grad() / torch.inference_mode()")
         return True
     return False

@@ -29,6 +29,7 @@ class GraphCSR:
         self._transposed: Optional["GraphCSR"] = None
         self._gcn_t: Optional[Tuple[Tensor, Tensor]] = None
 
+    edge_index = property(lambda self: self._edge_index)          # the COO tensor the CSR was built from
     rowptr = property(lambda self: self.csr.rowptr)
     col = property(lambda self: self.csr.col)
     perm = property(lambda self: self.csr.perm)

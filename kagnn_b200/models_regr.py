@@ -17,6 +17,7 @@ from .conv import FASTKAGCN_Layer, GINEConv, KAGCN_Layer, make_fastkan, make_kan
 from .ekan import _module_backend_guard
 from .graph import get_graph
 from .models_graph import _GCNGraphModel, _GINGraphModel, _bn_unfused, _num_graphs, pooled_readout
+from .models_node import bn_unfused
 
 Tensor = torch.Tensor
 
@@ -82,11 +83,13 @@ class _GINERegression(_GINGraphModel):
 
     def forward(self, data) -> Tensor:
         x, edge_attr = data.x, data.edge_attr
-        if _module_backend_guard(x, list(self.parameters()), grad_ok=not self.training):
-            # eval() without no_grad (graph_regression/optuna_zinc.py:68-86): inference plan, result detached.  Training the
-            # GINE models needs the backward of the relu(x_j + e_ji) message, which is not built yet (grad_ok=False raises).
+        needs_grad = _module_backend_guard(x, list(self.parameters()), grad_ok=True)
+        if needs_grad and not self.training:
+            # eval() without no_grad (graph_regression/optuna_zinc.py:68-86): inference plan, result detached
             with torch.no_grad():
                 return self.forward(data)
+        if needs_grad:
+            return self._forward_train(data)
         if edge_attr.dim() == 1:
             edge_attr = edge_attr.unsqueeze(1)
         n = x.size(0)
@@ -112,6 +115,20 @@ class _GINERegression(_GINGraphModel):
             if not fus:
                 h = self.dropout(_bn_unfused(h, self.bn[i]))
         return pooled_readout(h, data.batch, _num_graphs(data), self.kan, mean=False)
+
+
+    def _forward_train(self, data) -> Tensor:
+        """Differentiated forward: the encoders are torch modules (their tables / weights get their gradients from torch), every
+        GINE layer is aggregation -> KAN chain -> BatchNorm -> dropout as autograd.Functions over library launches."""
+        x, edge_attr = data.x, data.edge_attr
+        if edge_attr.dim() == 1:
+            edge_attr = edge_attr.unsqueeze(1)
+        g = get_graph(data.edge_index, x.size(0))
+        h = self.atom_encoder(x).to(torch.float32)
+        ef = self.bond_encoder(edge_attr).to(torch.float32)
+        for i in range(self.n_layers):
+            h = self.dropout(bn_unfused(self.conv[i](h, g, ef), self.bn[i], True))
+        return pooled_readout(h, data.batch, _num_graphs(data), self.kan, mean=False, needs_grad=True)
 
 
 class KAGIN(_GINERegression):

@@ -652,3 +652,20 @@ def layernorm_backward(x: Tensor, stats: Tensor, ln_weight: Optional[Tensor], dz
                                         n, c, _p(dx), _rows(dx, "dx"), _p(dw), _p(db), _stream()), "layernorm_bwd")
     launch_count += 2 if affine else 1
     return dx, dw, db
+
+
+def gine_backward(x: Tensor, edge_feat: Tensor, edge_index: Tensor, da: Tensor, self_scale: float, need_edge_grad: bool = True):
+    """Backward of the GINE aggregation on the COO edge list -> (dx, d edge_feat | None) (kagnn_gine_bwd)."""
+    global launch_count
+    _need_cuda(edge_index, "edge_index", torch.int64)
+    ei = edge_index.contiguous()
+    n, c = x.shape
+    e = ei.size(1)
+    dx = torch.empty(n, c, dtype=torch.float32, device=x.device)
+    de = torch.empty(e, c, dtype=torch.float32, device=x.device) if need_edge_grad else None
+    L.check(L.lib().kagnn_gine_bwd(_p(x), _rows(x, "x"), _p(edge_feat) if e else None, _rows(edge_feat, "edge_feat") if e else c,
+                                   _p(ei) if e else None, e, n, c, _p(da), _rows(da, "da"), float(self_scale), _p(dx), _rows(dx, "dx"),
+                                   _p(de) if (de is not None and e) else None, _rows(de, "d_edge") if (de is not None and e) else c,
+                                   _stream()), "gine_bwd")
+    launch_count += 2 if e else 1
+    return dx, de

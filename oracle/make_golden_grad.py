@@ -133,8 +133,46 @@ def main_fastkan() -> None:
         _save(name, dict(kind="gc", training=True, **meta), dict(x=x, edge_index=ei, batch=batch, dy=dy), sd0, y, grads)
 
 
+def main_gine() -> None:
+    """graph_regression GINE models (ZINC-style OGB encoders and QM9-style linear encoders), own seed."""
+    from . import pyg_shim
+    from .make_golden import GR
+    pyg_shim.install()
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(999)
+    gen = torch.Generator().manual_seed(999)
+    grm = _load(os.path.join(GR, "models.py"), "ref_gr_models", extra_path=(NC,))
+    ei, batch, n = batched_graphs(8, gen)
+    xz = torch.randint(0, 28, (n, 1), generator=gen)
+    ea = torch.randint(1, 4, (ei.size(1),), generator=gen)
+    xq = torch.randn(n, 11, generator=gen)
+    eq = torch.randn(ei.size(1), 4, generator=gen)
+    for name, mk, args, x, e_attr in [
+        ("grad_gr_kagin", grm.KAGIN, [1, 1, 3, 16, 2, 5, 3, 1, 0.0, True], xz, ea),
+        ("grad_gr_fastkagin", grm.FASTKAGIN, [1, 1, 2, 16, 2, 6, 1, 0.0, True], xz, ea),
+        ("grad_gr_kagin_linear_enc", grm.KAGIN, [11, 4, 2, 16, 2, 4, 3, 3, 0.0, False], xq, eq),
+    ]:
+        m = mk(*args).train()
+        _randomise(m, gen)
+        sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+        xin = x.clone().requires_grad_(True) if x.is_floating_point() else x
+        y = m(K.Batch(xin, ei, batch, e_attr))
+        dy = torch.randn(y.shape, generator=gen)
+        y.backward(dy)
+        grads = {nm: p.grad for nm, p in m.named_parameters() if p.grad is not None}
+        grads["__x"] = xin.grad if x.is_floating_point() else torch.zeros(1)
+        fam = "KAGIN" if mk is grm.KAGIN else "FASTKAGIN"
+        _save(name, dict(kind="gr", family=fam, args=args, training=True), dict(x=x, edge_index=ei, batch=batch, edge_attr=e_attr, dy=dy),
+              sd0, y, grads)
+
+
 if __name__ == "__main__":
     import sys
-    if "--fastkan-only" not in sys.argv:
+    if "--gine-only" in sys.argv:
+        main_gine()
+    elif "--fastkan-only" in sys.argv:
+        main_fastkan()
+    else:
         main()
-    main_fastkan()
+        main_fastkan()
+        main_gine()

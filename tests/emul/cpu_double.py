@@ -22,7 +22,7 @@ from kagnn_b200 import graph as kgraph
 from tests.emul import build_emul
 
 _BACKWARD = ("kagnn_kan_bwd_input", "kagnn_kan_bwd_weights", "kagnn_kan_unpack_weight_grads", "kagnn_batchnorm_bwd_workspace",
-             "kagnn_batchnorm_train_bwd", "kagnn_column_sums", "kagnn_log_softmax_bwd", "kagnn_silu_fwd", "kagnn_silu_bwd", "kagnn_segment_pool_bwd", "kagnn_rbf_bwd_input", "kagnn_rbf_bwd_weights", "kagnn_layernorm_bwd")
+             "kagnn_batchnorm_train_bwd", "kagnn_column_sums", "kagnn_log_softmax_bwd", "kagnn_silu_fwd", "kagnn_silu_bwd", "kagnn_segment_pool_bwd", "kagnn_rbf_bwd_input", "kagnn_rbf_bwd_weights", "kagnn_layernorm_bwd", "kagnn_gine_bwd")
 
 
 class _HostLib:
@@ -140,6 +140,9 @@ def _fused_layer(agg, num_rows, layers, pre=None, post=None, agg_out=None, out=N
         if agg.mode == L.AGG_WEIGHTED:
             msg = msg * agg.edge_weight.unsqueeze(1)
             t = x[:num_rows] * agg.self_weight.unsqueeze(1)
+        elif agg.mode == L.AGG_GINE:
+            msg = (msg + agg.edge_feat[agg.edge_row.long()]).relu()
+            t = x[:num_rows] * agg.self_scale
         else:
             assert agg.mode == L.AGG_GIN
             t = x[:num_rows] * agg.self_scale

@@ -44,7 +44,8 @@ def oracle_run(meta, inputs, sd, dtype=torch.float32):
     if kind == "gc":
         return (K.gc_kagin_forward(sd, data, meta.get("training", False)) if fam.endswith("GIN") else K.gc_kagcn_forward(sd, data))
     if kind == "gr":
-        return K.gr_kagin_forward(sd, data, dtype=dtype) if fam.endswith("GIN") else K.gr_kagcn_forward(sd, data, dtype=dtype)
+        return (K.gr_kagin_forward(sd, data, meta.get("training", False), dtype=dtype) if fam.endswith("GIN")
+                else K.gr_kagcn_forward(sd, data, dtype=dtype))
     raise ValueError(kind)
 
 
@@ -111,12 +112,14 @@ def oracle_grads(meta, inputs, sd):
     """Autograd through the oracle: the same quantities the fixture holds."""
     sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not k.endswith(("grid", "running_mean", "running_var", "eps"))
               else v.clone()) for k, v in sd.items()}
-    x = inputs["x"].clone().requires_grad_(True)
+    x = inputs["x"].clone()
+    if x.is_floating_point():
+        x.requires_grad_(True)
     ins = dict(inputs, x=x)
     y = oracle_run(meta, ins, sd)
     y.backward(inputs["dy"])
     grads = {k: v.grad for k, v in sd.items() if isinstance(v, torch.Tensor) and v.requires_grad and v.grad is not None}
-    grads["__x"] = x.grad
+    grads["__x"] = x.grad if x.is_floating_point() else torch.zeros(1)          # integer atom codes: no input gradient
     return y, grads
 
 

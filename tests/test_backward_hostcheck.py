@@ -215,3 +215,23 @@ def test_fastkan_layer_gradients(lib, G, fin, fout, n, ln):
     assert lib.kagnn_kan_unpack_weight_grads(p(dP), p(sw.detach()), None, fin, fout, G, p(d_base), p(d_spline), None, None) == 0
     assert K.rel_err(d_base, bw.grad) <= TOL
     assert K.rel_err(d_spline.view(fout, fin * G), sw.grad) <= TOL
+
+
+@pytest.mark.parametrize("n,e,h", [(20, 90, 6), (5, 0, 3), (64, 400, 17)])
+def test_gine_aggregation_gradients(lib, n, e, h):
+    torch.manual_seed(n + e)
+    x = torch.randn(n, h, requires_grad=True)
+    ef = torch.randn(e, h, requires_grad=True)
+    ei = torch.randint(0, n, (2, e))
+    da = torch.randn(n, h)
+    K.gine_conv(x, ei, ef, lambda t: t, eps=0.25).backward(da)
+    dx = torch.full((n, h + 2), 4.0)
+    de = torch.full((max(e, 1), h + 1), 4.0)
+    lib.kagnn_gine_bwd.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p,
+                                   C.c_int64, C.c_float, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
+    rc = lib.kagnn_gine_bwd(p(x.detach()), h, p(ef.detach()) if e else None, h, p(ei.contiguous()) if e else None, e, n, h, p(da), h,
+                            1.25, p(dx), h + 2, p(de) if e else None, h + 1, None)
+    assert rc == 0
+    assert K.rel_err(dx[:, :h], x.grad) <= 1e-6 and torch.all(dx[:, h:] == 4.0)
+    if e:
+        assert K.rel_err(de[:, :h], ef.grad) <= 1e-6 and torch.all(de[:, h:] == 4.0)
