@@ -6,12 +6,14 @@ Every forward below is the same library launch the inference path uses; every ba
 (``kagnn_kan_bwd_*``, ``kagnn_batchnorm_train_bwd``, ... in include/kagnn_b200.h, or the forward aggregation kernel on the
 TRANSPOSED CSR).  torch contributes the autograd tape, ``torch.cat`` of the skip connection and ``nn.Dropout``'s mask.
 Scope of this first backward: B-spline and FastKAN layers, GIN / GINE / GCN aggregation, BatchNorm1d, SiLU, add / mean
-pooling, log_softmax."""
+pooling, log_softmax.  First derivatives only (``once_differentiable``): ``create_graph=True`` raises instead of returning a
+graph-less result."""
 from __future__ import annotations
 
 from typing import Optional
 
 import torch
+from torch.autograd.function import once_differentiable
 
 from . import _lib as L
 from . import ops
@@ -44,6 +46,7 @@ class _KanLinearFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, dy):
         x, spline_w, scaler = ctx.saved_tensors
         scaler = scaler if ctx.has_scaler else None
@@ -75,6 +78,7 @@ class _FastKanLayerFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, dy):
         x, spline_w, ln_w = ctx.saved_tensors
         ln_w = ln_w if ctx.ln_affine else None
@@ -116,6 +120,7 @@ class _GinAggFn(torch.autograd.Function):
         return ops.fused_layer(agg, graph.num_nodes, [])
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, da):
         gt = ctx.graph.transposed()
         agg = ops.AggSpec(L.AGG_GIN, _rowmajor(da), gt.rowptr, gt.col, self_scale=ctx.self_scale)
@@ -138,6 +143,7 @@ class _GineAggFn(torch.autograd.Function):
         return ops.fused_layer(agg, graph.num_nodes, [])
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, da):
         x, edge_feat = ctx.saved_tensors
         dx, de = ops.gine_backward(x, edge_feat, ctx.graph.edge_index, _rowmajor(da), ctx.self_scale, ctx.needs_input_grad[1])
@@ -161,6 +167,7 @@ class _GcnAggFn(torch.autograd.Function):
         return ops.fused_layer(agg, graph.num_nodes, [], pre=pre)
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, dout):
         dout = _rowmajor(dout)
         dh = db = None
@@ -191,6 +198,7 @@ class _BatchNormFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, dy):
         x, weight = ctx.saved_tensors
         dx, dw, db = ops.batchnorm_backward(x, _rowmajor(dy), weight if ctx.has_affine else None, ctx.eps)
@@ -209,6 +217,7 @@ class _SiluFn(torch.autograd.Function):
         return ops.silu_forward(x)
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, dy):
         (x,) = ctx.saved_tensors
         return ops.silu_backward(x, _rowmajor(dy))
@@ -230,6 +239,7 @@ class _PoolFn(torch.autograd.Function):
         return ops.fused_layer(agg, num_graphs, [])
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, dp):
         return ops.segment_pool_backward(_rowmajor(dp), ctx.ptr, ctx.batch, ctx.n, ctx.mean), None, None, None
 
@@ -246,6 +256,7 @@ class _LogSoftmaxFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, dy):
         (y,) = ctx.saved_tensors
         return ops.log_softmax_backward(y, _rowmajor(dy))
