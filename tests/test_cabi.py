@@ -109,3 +109,23 @@ def test_aggspec_makes_column_strided_views_row_major():
     assert spec.x.stride(1) == 1 and torch.equal(spec.x, base.t())
     sliced = base[:, 2:7]                              # unit column stride: kept as a view (the kernels take a leading dimension)
     assert ops.AggSpec(L.AGG_NONE, sliced).x.data_ptr() == sliced.data_ptr()
+
+
+def test_host_check_seam_is_not_part_of_the_product():
+    """kagnn_b200/csrc/launch.cuh lets the CPU suite compile backward.cu as serial host code (tests/emul/).  That build is test
+    infrastructure: the product's Python never refers to it, the product build never defines the macro, and the only source
+    that mentions the macro is the seam header itself."""
+    from kagnn_b200 import build
+    pkg = os.path.join(ROOT, "kagnn_b200")
+    for f in os.listdir(pkg):
+        if f.endswith(".py"):
+            with open(os.path.join(pkg, f)) as fh:
+                src = fh.read()
+            assert "emul" not in src and "host_check" not in src.lower() and "HOST_CHECK" not in src, f
+    assert not any("HOST_CHECK" in flag for flag in build.NVCC_FLAGS)
+    users = []
+    for f in os.listdir(os.path.join(pkg, "csrc")):
+        with open(os.path.join(pkg, "csrc", f)) as fh:
+            if "KAGNN_HOST_CHECK" in fh.read():
+                users.append(f)
+    assert users == ["launch.cuh"]
