@@ -65,6 +65,20 @@ def _gcn_norm(csr, edge_weight_csr=None):
     return dinv[col] * dinv[row] * keep, dinv * dinv, dinv
 
 
+def _gcn_degree(csr, edge_weight_csr=None):
+    assert edge_weight_csr is None
+    row, col = _row_of_entry(csr), csr.col.long()
+    deg = 1.0 + torch.zeros(csr.num_rows).index_add_(0, row, (row != col).float())
+    dinv = deg.rsqrt()
+    return dinv * dinv, dinv
+
+
+def _gcn_edge_weight(csr, dinv_src, dinv_dst, edge_weight_csr=None):
+    assert edge_weight_csr is None
+    row, col = _row_of_entry(csr), csr.col.long()
+    return dinv_src[col] * dinv_dst[row] * (row != col).float()
+
+
 def _gather_rows(x, index, out=None, num_rows=None):
     res = x[index.long()] if index is not None else x[: (x.size(0) if num_rows is None else num_rows)]
     if out is None:
@@ -125,6 +139,10 @@ def _kan_layer(spec, x):
 
 def _fused_layer(agg, num_rows, layers, pre=None, post=None, agg_out=None, out=None):
     x = agg.x if agg.x_head is None else torch.cat([agg.x_head, agg.x], dim=1)
+    if agg.x_halo is not None:
+        x = torch.cat([x, agg.x_halo], dim=0)                # halo rows follow the owned rows in the local numbering
+    if agg.src_index is not None:
+        x = x[agg.src_index.long()]                          # rows of a small table addressed through an index
     if agg.mode == L.AGG_NONE:
         t = x[:num_rows]
     elif agg.mode in (L.AGG_SEGMENT_SUM, L.AGG_SEGMENT_MEAN):
@@ -188,7 +206,7 @@ def cpu_double():
     patch(ops, "_need_cuda", lambda t, name, dtype=None: None)
     patch(ops, "_stream", lambda: None)
     patch(ops, "tc_supported", lambda *a: False)
-    for name, fn in (("csr_build", _csr_build), ("gcn_norm", _gcn_norm), ("gather_rows", _gather_rows), ("segment_ptr", _segment_ptr),
+    for name, fn in (("csr_build", _csr_build), ("gcn_norm", _gcn_norm), ("gcn_degree", _gcn_degree), ("gcn_edge_weight", _gcn_edge_weight), ("gather_rows", _gather_rows), ("segment_ptr", _segment_ptr),
                      ("pack_kan_weights", _pack), ("fused_layer", _fused_layer), ("batchnorm_forward", _batchnorm_forward),
                      ("log_softmax", lambda x: torch.log_softmax(x, dim=1)), ("layernorm_stats", _layernorm_stats)):
         patch(ops, name, fn)

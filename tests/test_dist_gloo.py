@@ -120,3 +120,57 @@ def test_shard_batch_by_graph():
         seen |= mask
         assert set(batch[mask].tolist()) == set(range(g0, g1))
     assert seen.all()
+
+
+# ---- the whole sharded forward (ShardedNodeModel, mode="halo") over gloo, library launches replaced by the CPU stand-ins --------
+def _model_worker(rank, world, port, conv_type, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import kagnn_b200 as kb
+        from kagnn_b200 import dist as kd
+        from tests.emul.cpu_double import cpu_double
+        n_local, f, c = 30, 8, 3
+        x, eis = _global_problem(world, n_local, 120, f, seed=3)
+        ei_all = torch.cat(eis, dim=1)
+        torch.manual_seed(11)                                         # same replicated weights on every rank
+        model = kb.GKAN_Nodes(conv_type, 2, f, 12, c, skip=True, grid_size=5, spline_order=3, hidden_layers=2).eval()
+        with torch.no_grad():
+            for bn in model.bns:                                      # non-trivial eval BatchNorm
+                bn.running_mean.uniform_(-0.3, 0.3)
+                bn.running_var.uniform_(0.5, 1.5)
+        sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        lo = rank * n_local
+        with cpu_double(), torch.no_grad():
+            runner = kd.ShardedNodeModel(model, rank, world, n_local, mode="halo")
+            plan = runner.prepare(eis[rank])
+            y_shard = runner.forward(x[lo:lo + n_local].contiguous(), plan)
+            y_shard2 = runner.forward(x[lo:lo + n_local].contiguous(), plan)          # the plan is reusable
+            y_single = model(x, ei_all)                                               # the un-sharded plan, same stand-ins
+        y_ref = K.node_model_forward(sd, conv_type, x, ei_all, True)
+        assert torch.equal(y_shard, y_shard2)
+        assert K.rel_err(y_shard, y_ref[lo:lo + n_local]) <= 1e-5
+        assert K.rel_err(y_single, y_ref) <= 1e-5
+        out.put((rank, "ok"))
+    except Exception as exc:  # pragma: no cover - reported to the parent
+        import traceback
+        out.put((rank, f"{type(exc).__name__}: {exc}\\n{traceback.format_exc()}"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("conv_type", ["gin", "gcn"])
+def test_sharded_model_forward_gloo(conv_type):
+    """world_size 2: every rank's rows of the sharded forward == the oracle on the global graph."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_model_worker, args=(r, world, port, conv_type, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [out.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(results) == [(r, "ok") for r in range(world)], results
