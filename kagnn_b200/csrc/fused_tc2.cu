@@ -24,6 +24,7 @@
 #include "common.cuh"
 #include "stage.cuh"
 #include "tc_common.cuh"
+#include <cstdlib>
 
 // Optional timeline trace of CTA 0 (development builds only: KAGNN_NVCC_EXTRA="-DKAGNN_TRACE=1"): clock stamps per role,
 // event counter and event kind into a caller-provided buffer (scripts/trace_tc2.py).
@@ -51,7 +52,7 @@ namespace {
 
 constexpr int BM = 128;
 #ifndef KAGNN_TC2_GATHER_U
-#define KAGNN_TC2_GATHER_U 16           // 128-bit row loads in flight per gather warp
+#define KAGNN_TC2_GATHER_U 8            // 128-bit row loads in flight per gather warp (register gather; the asynchronous gather is the default path)
 #endif
 #ifndef KAGNN_TC2_PREFETCH_DIST
 #define KAGNN_TC2_PREFETCH_DIST 0        // tiles an L2 prefetch warp may run ahead of the gather; 0 = off (default: measured on the
@@ -74,8 +75,30 @@ constexpr int NPW = KAGNN_TC2_NPW;           // producer warps: 2 or 4 warpgroup
 constexpr int NWG = NPW / 4;
 // Every warpgroup expands 8 / NWG features of EVERY chunk (lowest latency per chunk; the alternative -- whole chunks handed round
 // robin to the warpgroups -- was measured 3-8 % slower on the GIN layers and needs ring depth >= NWG).
-constexpr int FPW = 8 / NWG;                 // features per warpgroup per spline chunk
-constexpr int FULL_ARRIVALS = NPW * 32 + 1;  // every producer thread + the W loader's expect_tx
+#ifndef KAGNN_TC2_CPR
+#define KAGNN_TC2_CPR 2
+#endif
+// CPR = chunks produced concurrently: the NWG warpgroups form CPR teams, chunk number c (counted over the whole launch) belongs to
+// team c % CPR, and the NWG / CPR warpgroups of a team split its 8 features.  CPR = 1: every warpgroup on every chunk (lowest
+// latency per chunk, one barrier round per 8 / NWG features of a thread); CPR = 2: two chunks in flight, half as many barrier
+// rounds per thread (each covers 4 features), needs two stages per team to keep the tensor pipe fed.
+constexpr int CPR = (NWG >= 2 * KAGNN_TC2_CPR || KAGNN_TC2_CPR == 1) ? KAGNN_TC2_CPR : 1;
+constexpr int WGT = NWG / CPR;               // warpgroups per team
+constexpr int FPW = 8 / WGT;                 // features per warpgroup per spline chunk
+#ifndef KAGNN_TC2_ELECT_ARRIVE
+#define KAGNN_TC2_ELECT_ARRIVE 0
+#endif
+#ifndef KAGNN_TC2_WDIV
+#define KAGNN_TC2_WDIV 1
+#endif
+#ifndef KAGNN_TC2_X2
+#define KAGNN_TC2_X2 1                       // packed-pair (f32x2) polynomial evaluation in the basis producers
+#endif
+#ifndef KAGNN_TC2_NOMATH
+#define KAGNN_TC2_NOMATH 0                   // development probe: producers skip the basis expansion (results are wrong)
+#endif
+// arrivals on full[s]: every producer thread (or one elected lane per producer warp) + the W loader's expect_tx
+constexpr int FULL_ARRIVALS = (KAGNN_TC2_ELECT_ARRIVE ? NPW / CPR : NPW / CPR * 32) + 1;
 constexpr int NGW = 8;                       // gather warps
 constexpr int NTHREADS = (NPW + NGW + 4) * 32;   // + MMA, W loader and two idle warps (whole warpgroups for setmaxnreg)
 constexpr int WARP_MMA = NPW + NGW;
@@ -110,6 +133,7 @@ struct Tc2Params {
     int n_layers, n_tiles, y_vec;
     int uw, uw_shift, xld, n_units, units_per_tile, unit_floats;   // x-tile ring geometry (uw = 1 << uw_shift = 64 or 128)
     int ns, bstage_bytes;                                 // A/B stage ring depth, bytes of one B stage
+    int ag;                                               // 1: asynchronous (cp.async ring) gather, 64-column units
     LayerT2 layers[KAGNN_MAX_LAYERS];
 };
 
@@ -214,6 +238,87 @@ __device__ __forceinline__ void bspline_slots(float inv_h, float c0, float limp,
     lo[1] = prmt(l01, l23, sel.y);
     lo[2] = prmt(l01, l23, sel.z);
     lo[3] = prmt(l01, l23, sel.w);
+}
+
+// ---- packed fp32 pairs (FFMA2 / FMUL2 / FADD2 of sm_100): the same IEEE operations on two values per issue slot ----------------
+__device__ __forceinline__ unsigned long long f2_bits(float2 v) { return *reinterpret_cast<unsigned long long*>(&v); }
+__device__ __forceinline__ float2 bits_f2(unsigned long long b) { return *reinterpret_cast<float2*>(&b); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)), "l"(f2_bits(c)));
+    return bits_f2(d);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return bits_f2(d);
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return bits_f2(d);
+}
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return bits_f2(d);
+}
+__device__ __forceinline__ float2 add2_rm(float2 a, float2 b) {
+    unsigned long long d;
+    asm("add.rm.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return bits_f2(d);
+}
+__device__ __forceinline__ float2 splat(float v) { return make_float2(v, v); }
+
+// Two input values (two features of one row) -> their slot words, bit-identical to two bspline_slots calls: the polynomial part
+// runs as packed pairs (element .x = first feature, .y = second), which halves its issue slots.
+template <int K>
+__device__ __forceinline__ void bspline_slots2(float inv_h, float c0, float limp, const uint4* __restrict__ lut, float xa, float xb,
+                                               uint32_t* hi, uint32_t* lo) {
+    float2 u = fma2(make_float2(xa, xb), splat(inv_h), splat(c0));
+    u.x = fminf(fmaxf(u.x, -0.5f), limp);
+    u.y = fminf(fmaxf(u.y, -0.5f), limp);
+    const float2 t = add2_rm(u, splat(kMagic));
+    const float2 fr = sub2(u, sub2(t, splat(kMagic)));
+    float2 b0, b1, b2 = splat(0.f), b3 = splat(0.f);
+    if (K == 3) {
+        const float2 omf = sub2(splat(1.0f), fr), f2 = mul2(fr, fr);
+        b0 = mul2(mul2(omf, omf), mul2(omf, splat(1.0f / 6.0f)));
+        b3 = mul2(f2, mul2(fr, splat(1.0f / 6.0f)));
+        b1 = fma2(f2, fma2(fr, splat(0.5f), splat(-1.0f)), splat(2.0f / 3.0f));
+        b2 = fma2(fr, fma2(fr, fma2(fr, splat(-0.5f), splat(0.5f)), splat(0.5f)), splat(1.0f / 6.0f));
+    } else if (K == 2) {
+        const float2 omf = sub2(splat(1.0f), fr);
+        b0 = mul2(mul2(splat(0.5f), omf), omf);
+        b2 = mul2(mul2(splat(0.5f), fr), fr);
+        b1 = fma2(fr, omf, splat(0.5f));
+    } else {
+        b0 = sub2(splat(1.0f), fr);
+        b1 = fr;
+    }
+    const uint32_t h01a = pack_trunc(b0.x, b1.x), h23a = pack_trunc(b2.x, b3.x);
+    const uint32_t h01b = pack_trunc(b0.y, b1.y), h23b = pack_trunc(b2.y, b3.y);
+    const float2 r0 = sub2(b0, make_float2(__uint_as_float(h01a << 16), __uint_as_float(h01b << 16)));
+    const float2 r1 = sub2(b1, make_float2(__uint_as_float(h01a & 0xffff0000u), __uint_as_float(h01b & 0xffff0000u)));
+    uint32_t l23a = 0u, l23b = 0u;
+    if (K >= 2) {
+        const float2 r2 = sub2(b2, make_float2(__uint_as_float(h23a << 16), __uint_as_float(h23b << 16)));
+        const float2 r3 = sub2(b3, make_float2(__uint_as_float(h23a & 0xffff0000u), __uint_as_float(h23b & 0xffff0000u)));
+        l23a = pack_rn(r2.x, r3.x);
+        l23b = pack_rn(r2.y, r3.y);
+    }
+    const uint32_t l01a = pack_rn(r0.x, r1.x), l01b = pack_rn(r0.y, r1.y);
+    uint4 sa, sb;
+    {
+        const uint32_t lbase = tc::smem_u32(lut) - (uint32_t)((0x4B400000u - 1u) * 16u);
+        const uint32_t aa = __float_as_uint(t.x) * 16u + lbase, ab = __float_as_uint(t.y) * 16u + lbase;
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(sa.x), "=r"(sa.y), "=r"(sa.z), "=r"(sa.w) : "r"(aa));
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(sb.x), "=r"(sb.y), "=r"(sb.z), "=r"(sb.w) : "r"(ab));
+    }
+    hi[0] = prmt(h01a, h23a, sa.x); hi[1] = prmt(h01a, h23a, sa.y); hi[2] = prmt(h01a, h23a, sa.z); hi[3] = prmt(h01a, h23a, sa.w);
+    lo[0] = prmt(l01a, l23a, sa.x); lo[1] = prmt(l01a, l23a, sa.y); lo[2] = prmt(l01a, l23a, sa.z); lo[3] = prmt(l01a, l23a, sa.w);
+    hi[4] = prmt(h01b, h23b, sb.x); hi[5] = prmt(h01b, h23b, sb.y); hi[6] = prmt(h01b, h23b, sb.z); hi[7] = prmt(h01b, h23b, sb.w);
+    lo[4] = prmt(l01b, l23b, sb.x); lo[5] = prmt(l01b, l23b, sb.y); lo[6] = prmt(l01b, l23b, sb.z); lo[7] = prmt(l01b, l23b, sb.w);
 }
 
 // FastKAN: the 8 Gaussians exp(-((z - c_g)/den)^2) of one layer-normalised input (fastkan.py:46-47) as bf16 hi / lo slot words.
@@ -721,6 +826,189 @@ __device__ __forceinline__ void gather_unit_fast(const Tc2Params& p, long long r
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Asynchronous gather (the default for GIN / GCN layers whose width is a multiple of 64): neighbour rows travel
+// global -> shared memory with cp.async (LDGSTS, 16 bytes per lane, L2 -> shared without a register or L1 stop-over) into a
+// small ring of row slots, and are summed from there.  What this buys over the register gathers above:
+//   * memory-level parallelism no longer costs registers or warps: every half-warp keeps AG_D row copies in flight all the time
+//     (issue of entry t and summation of entry t - AG_D alternate), instead of batches of loads that drain before the next batch;
+//   * a lane only ever reads the 16 bytes it copied itself, so the only synchronisation is cp.async.wait_group -- no barrier, no
+//     fence, no shuffled 64-bit pointers;
+//   * a unit is 64 columns wide, so ONE instruction moves two rows (one per half-warp): half h owns destination rows 8h .. 8h+7
+//     of the warp's 16 and walks their entries as one flattened list [self_0, nbrs_0 ..., self_1, ...] (balanced inside the half).
+// Per list entry: ~1 shuffle + address + LDGSTS to issue, 1 shuffle + LDS.128 + 4 FMA + row-end test to sum.
+// ---------------------------------------------------------------------------------------------------------------------
+#ifndef KAGNN_TC2_AG
+#define KAGNN_TC2_AG 0
+#endif
+#ifndef KAGNN_TC2_AG_DEPTH
+#define KAGNN_TC2_AG_DEPTH 8
+#endif
+constexpr int AG_D = KAGNN_TC2_AG_DEPTH;          // row copies in flight per half-warp (<= 16: two metadata batches are kept)
+constexpr int AG_R = AG_D + 2;                    // ring slots per half-warp
+constexpr int AG_ROW_BYTES = 256;                 // one row of a 64-column unit
+constexpr int AG_WARP_BYTES = 2 * AG_R * AG_ROW_BYTES;
+constexpr int AG_BYTES = NGW * AG_WARP_BYTES;
+static_assert(AG_D >= 1 && AG_D <= 16, "AG_DEPTH");
+
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+template <bool WEIGHTED>
+__device__ __forceinline__ void gather_unit_ag(const Tc2Params& p, long long row0, int c0, float* __restrict__ xsu, int gw, int lane,
+                                               uint32_t stage_warp) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const KagnnAggregate& a = p.agg;
+    const int mode = a.mode, xld = p.xld;
+    const int half = lane >> 4, l16 = lane & 15;
+    const int rh0 = gw * RPW + 8 * half;                   // first tile-local row of this half-warp
+    const long long grow0 = row0 + rh0;
+    const int nvalid = (int)max(0LL, min(8LL, p.num_rows - grow0));      // rows of this half that exist
+    const int li = min(min(l16, 8), nvalid);
+    int rp = 0;
+    if (mode != KAGNN_AGG_NONE) rp = __ldg(a.rowptr + min(grow0 + li, p.num_rows));
+    const int rp0 = __shfl_sync(FULL, rp, 0, 16);
+    const int vs = (rp - rp0) + li;                        // list position where row l16 starts (one self entry per existing row)
+    const int L = __shfl_sync(FULL, vs, 8, 16);            // length of this half's list
+    const int T = max(L, __shfl_xor_sync(FULL, L, 16));    // steps of the warp (both halves run in lockstep)
+    const float* const xcol = a.x + c0 + 4 * l16;          // column offset folded into the base pointers
+    const uint32_t stage_half = stage_warp + (uint32_t)(half * AG_R * AG_ROW_BYTES + 16 * l16);
+
+    // source row of list code j (bit 30 = self entry, always an owned row)
+    auto src_ptr = [&](int code) -> const float* {
+        int j = code & 0x3fffffff;
+        if (code & 0x40000000) {
+            if (a.src_index) j = __ldg(a.src_index + j);
+            return xcol + (long long)j * a.ldx;
+        }
+        if (a.src_index) j = __ldg(a.src_index + j);
+        if (a.peer_x) {
+            const int owner = j / (int)a.rows_per_rank;
+            return reinterpret_cast<const float*>(__ldg(reinterpret_cast<const unsigned long long*>(a.peer_x) + owner)) +
+                   (long long)(j - owner * (int)a.rows_per_rank) * a.ldx + (c0 + 4 * l16);
+        }
+        if (a.x_halo != nullptr && j >= a.num_local_src) return a.x_halo + (long long)(j - a.num_local_src) * a.ld_halo + (c0 + 4 * l16);
+        return xcol + (long long)j * a.ldx;
+    };
+    // lane-parallel description of list position pb + l16: code = source id | self << 30 | last-entry-of-its-row << 31
+    struct Meta {
+        int code;
+        float w;
+    };
+    auto prep = [&](int pb) {
+        Meta m;
+        m.code = 0;
+        m.w = 0.f;
+        const int pos = pb + l16;
+        int r = 0;
+#pragma unroll
+        for (int step = 4; step >= 1; step >>= 1) {
+            const int t = __shfl_sync(FULL, vs, r + step, 16);
+            r += (t <= pos) ? step : 0;
+        }
+        const int vs_r = __shfl_sync(FULL, vs, r, 16), vs_n = __shfl_sync(FULL, vs, r + 1, 16), rp_r = __shfl_sync(FULL, rp, r, 16);
+        if (pos < L) {
+            const int lastbit = (pos + 1 == vs_n) ? (int)0x80000000 : 0;
+            if (pos == vs_r) {
+                const long long rg = grow0 + r;
+                m.code = (int)rg | 0x40000000 | lastbit;
+                m.w = (mode == KAGNN_AGG_NONE) ? 1.0f : a.self_scale;
+                if (mode == KAGNN_AGG_WEIGHTED && a.self_weight) m.w = __ldg(a.self_weight + rg);
+            } else {
+                const int e = rp_r + (pos - vs_r) - 1;
+                m.code = (a.col ? __ldg(a.col + e) : e) | lastbit;
+                m.w = (mode == KAGNN_AGG_WEIGHTED) ? __ldg(a.edge_weight + e) : 1.0f;
+            }
+        }
+        return m;
+    };
+
+    Meta prv, cur, nxt = prep(0);
+    prv.code = cur.code = 0;
+    prv.w = cur.w = 0.f;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float* drow = xsu + (long long)rh0 * xld + 4 * l16;    // destination of the row being summed
+    uint32_t wslot = 0, rslot = 0;
+#pragma unroll 1
+    for (int t = 0; t < T + AG_D; ++t) {
+        if ((t & 15) == 0) {
+            prv = cur;
+            cur = nxt;
+            if (t + 16 < T) nxt = prep(t + 16);
+        }
+        // ---- issue: the copy of list entry t ------------------------------------------------------------------------------
+        {
+            const int code = __shfl_sync(FULL, cur.code, t & 15, 16);
+            if (t < L) cp_async16(stage_half + wslot * AG_ROW_BYTES, src_ptr(code));
+            cp_async_commit();
+            wslot = (wslot + 1 == AG_R) ? 0u : wslot + 1;
+        }
+        // ---- sum: list entry u = t - AG_D, whose copy has landed once at most AG_D newer groups are pending --------------------
+        const int u = t - AG_D;
+        if (u >= 0) {
+            cp_async_wait<AG_D>();
+            const bool in_cur = (u >> 4) == (t >> 4);
+            const int code = __shfl_sync(FULL, in_cur ? cur.code : prv.code, u & 15, 16);
+            const float w = WEIGHTED ? __shfl_sync(FULL, in_cur ? cur.w : prv.w, u & 15, 16) : 1.0f;
+            if (u < L) {
+                const float4 v = lds128(stage_half + rslot * AG_ROW_BYTES);
+                acc.x = fmaf(w, v.x, acc.x);
+                acc.y = fmaf(w, v.y, acc.y);
+                acc.z = fmaf(w, v.z, acc.z);
+                acc.w = fmaf(w, v.w, acc.w);
+                if (code < 0) {                            // last entry of its destination row: park the sum
+                    *reinterpret_cast<float4*>(drow) = acc;
+                    acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    drow += xld;
+                }
+            }
+            rslot = (rslot + 1 == AG_R) ? 0u : rslot + 1;
+        }
+    }
+    // rows past the end of the graph (last tile): zeros for the basis producers
+    for (int r = nvalid; r < 8; ++r) *reinterpret_cast<float4*>(xsu + (long long)(rh0 + r) * xld + 4 * l16) = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    if (p.has_pre || p.agg_out) {
+        // post-pass over the values this lane parked itself: pre-affine (GCNConv bias / eval BatchNorm / SiLU) and the agg_out copy
+        const bool pre_silu = p.has_pre && p.pre.act == KAGNN_ACT_SILU;
+        const int c = c0 + 4 * l16;
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.has_pre) {
+            if (p.pre.scale) sc = make_float4(__ldg(p.pre.scale + c), __ldg(p.pre.scale + c + 1), __ldg(p.pre.scale + c + 2), __ldg(p.pre.scale + c + 3));
+            if (p.pre.shift) sh = make_float4(__ldg(p.pre.shift + c), __ldg(p.pre.shift + c + 1), __ldg(p.pre.shift + c + 2), __ldg(p.pre.shift + c + 3));
+        }
+        const bool out_vec = p.agg_out && ((reinterpret_cast<uintptr_t>(p.agg_out) & 15u) == 0) && (p.ld_agg_out % 4 == 0);
+#pragma unroll 1
+        for (int r = 0; r < nvalid; ++r) {
+            float* d = xsu + (long long)(rh0 + r) * xld + 4 * l16;
+            const float4 t = *reinterpret_cast<const float4*>(d);
+            float o[4] = {t.x, t.y, t.z, t.w};
+            if (p.has_pre) {
+                o[0] = fmaf(o[0], sc.x, sh.x); o[1] = fmaf(o[1], sc.y, sh.y); o[2] = fmaf(o[2], sc.z, sh.z); o[3] = fmaf(o[3], sc.w, sh.w);
+                if (pre_silu) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) o[q] = __fdividef(o[q], 1.0f + ex2_approx(-kLog2e * o[q]));
+                }
+                *reinterpret_cast<float4*>(d) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+            if (p.agg_out) {
+                float* g = p.agg_out + (grow0 + r) * p.ld_agg_out + c;
+                if (out_vec) *reinterpret_cast<float4*>(g) = make_float4(o[0], o[1], o[2], o[3]);
+                else { g[0] = o[0]; g[1] = o[1]; g[2] = o[2]; g[3] = o[3]; }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 template <int K>
 __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_constant__ Tc2Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -739,6 +1027,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
     volatile int* gather_progress = reinterpret_cast<volatile int*>(post_sh + 128);   // tiles the gather warps have started
     HubScratch* hub_scratch = reinterpret_cast<HubScratch*>(post_sh + 128 + 4);
     float2* ln_part = reinterpret_cast<float2*>(hub_scratch + 1);       // [2][NWG][128]: FastKAN LayerNorm partial sums
+    uint8_t* ag_stage = reinterpret_cast<uint8_t*>(ln_part + 2 * NWG * 128);   // [NGW][2][AG_R][256 B]: row slots of the asynchronous gather
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (warp == WARP_MMA) tc::tmem_alloc(tmem_slot, 512);
@@ -791,7 +1080,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < NPW) {
-        if (NPW == 16) tc::reg_dec<64>();
+        // register budget (launch: 72 per thread): producers keep 72, the MMA / loader / idle warpgroup drops to 40 and hands its
+        // 32 x 128 registers to the gather warps (72 -> 88)
         // ============================== BASIS PRODUCERS / EPILOGUE =============================================
         // Every warpgroup works on EVERY chunk: warpgroup wg expands FPW features of a spline chunk (every NWG-th octet of a
         // SiLU chunk), so the parts of a chunk are produced concurrently and the groups stay balanced.
@@ -953,14 +1243,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                             xrow = xs + (size_t)u_slot * p.unit_floats + (size_t)row * p.xld - (size_t)ul * p.uw;
                         }
                     }
-                    {
+                    if (CPR == 1 || ((cq + (uint32_t)q) % CPR) == (uint32_t)(wg / WGT)) {
+                        const int wsub = wg % WGT;                            // this warpgroup's share inside its team
                         if (lane == 0 && (warp & 3) == 0 && wg < 2) TRC(wg, cq + q, 2);
                         tc::mbar_wait_relaxed(&empty[s], par);
                         if (lane == 0 && (warp & 3) == 0 && wg < 2) TRC(wg, cq + q, 3);
                         tc::tc_fence_after_sync();
                         const uint32_t a_t = tmem_base + lane_base + TMEM_A0 + 64u * s;
-                        if (!c.base()) {
-                            const int fsh = FPW * wg;                         // first feature of this warpgroup inside the chunk
+                        if (KAGNN_TC2_NOMATH) {
+                        } else if (!c.base()) {
+                            const int fsh = FPW * wsub;                       // first feature of this warpgroup inside the chunk
                             const int f0 = 64 * c.group + 8 * c.j + fsh;
                             float v[FPW];
                             if (l == 0) {
@@ -1002,6 +1294,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                                 if (K == 0) {
                                     rbf_slots(rc0, rstep, rk, v[i], hi, lo);
                                     rbf_slots(rc0, rstep, rk, v[i + 1], hi + 4, lo + 4);
+                                } else if (KAGNN_TC2_X2) {
+                                    bspline_slots2<(K == 0 ? 1 : K)>(inv_h, c0f, limp, lutL, v[i], v[i + 1], hi, lo);
                                 } else {
                                     bspline_slots<(K == 0 ? 1 : K)>(inv_h, c0f, limp, lutL, v[i], hi, lo);
                                     bspline_slots<(K == 0 ? 1 : K)>(inv_h, c0f, limp, lutL, v[i + 1], hi + 4, lo + 4);
@@ -1011,7 +1305,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                             }
                         } else {
 #pragma unroll 1
-                            for (int jj = wg; jj < c.n_oct; jj += NWG) {
+                            for (int jj = wsub; jj < c.n_oct; jj += WGT) {
                                 const int f0 = 64 * c.group + 8 * jj;
                                 float v[8];
                                 if (l == 0) {
@@ -1045,7 +1339,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                         }
                         tc::tmem_st_wait();
                         tc::tc_fence_before_sync();
+#if KAGNN_TC2_ELECT_ARRIVE
+                        __syncwarp();
+                        if (lane == 0) tc::mbar_arrive(&full[s]);
+#else
                         tc::mbar_arrive(&full[s]);
+#endif
                         if (lane == 0 && (warp & 3) == 0 && wg < 2) TRC(wg, cq + q, 4);
                     }
                     if (++s == p.ns) { s = 0; par ^= 1u; }
@@ -1058,6 +1357,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                     if (have_pend) {                       // previous tile's epilogue, behind this tile's first layer
                         epilogue(pend_row0, pend_lc);
                         have_pend = false;
+                        // The accumulator region just read is the one this tile's NEXT layer (or, for one-layer chains, the next
+                        // tile) overwrites.  With every warpgroup on every chunk that MMA cannot start before all warps have left
+                        // the epilogue; with teams (CPR > 1) a team could hand over its chunk while the other team still reads.
+                        if (CPR > 1) asm volatile("bar.sync 4, %0;" ::"n"(NPW * 32) : "memory");
                     }
                 }
             }
@@ -1072,7 +1375,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
         if (have_pend) epilogue(pend_row0, pend_lc);
     } else if (warp < NPW + NGW) {
         // ========================================= GATHER ======================================================
-        if (NPW == 16) tc::reg_inc<104>();
+        if (NPW == 16) tc::reg_inc<88>();
         const int gw = warp - NPW;
         const bool vec = (p.agg.num_cols % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.agg.x) & 15u) == 0) && (p.agg.ldx % 4 == 0) &&
                          (!p.agg.x_halo || (((reinterpret_cast<uintptr_t>(p.agg.x_halo) & 15u) == 0) && (p.agg.ld_halo % 4 == 0))) &&
@@ -1094,7 +1397,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                 if (lane == 0 && gw == 0) TRL(6, uc, 1);
                 float* xsu = xs + (size_t)u * p.unit_floats;
                 const int c0 = ub * p.uw, ucols = min(p.uw, F_pad - c0);
-                if (vec && head_ok) {
+                // asynchronous gather: 64-column units of a GIN / GCN layer (p.ag, decided by the launcher), unless the tile holds a
+                // hub row (more than HUB_T entries), which the register gather sums cooperatively
+                bool gpr = false;
+                if (KAGNN_TC2_AG && p.ag) {
+                    gpr = true;
+                    if (KAGNN_TC2_HUB) {
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4) {
+                            const long long rr = row0 + 32 * k4 + lane;
+                            int d = 0;
+                            if (rr < p.num_rows) d = __ldg(p.agg.rowptr + rr + 1) - __ldg(p.agg.rowptr + rr);
+                            if (__any_sync(0xffffffffu, d > HUB_T)) gpr = false;          // tile-uniform
+                        }
+                    }
+                    if (gpr) {
+                        const uint32_t st = tc::smem_u32(ag_stage) + (uint32_t)(gw * AG_WARP_BYTES);
+                        if (p.agg.mode == KAGNN_AGG_WEIGHTED || p.agg.self_scale != 1.0f) gather_unit_ag<true>(p, row0, c0, xsu, gw, lane, st);
+                        else gather_unit_ag<false>(p, row0, c0, xsu, gw, lane, st);
+                    }
+                }
+                if (gpr) {
+                } else if (vec && head_ok) {
                     if (gine) gather_unit<true, true>(p, row0, c0, ucols, xsu, gw, lane);
                     else if (plain_copy) gather_unit<true, false>(p, row0, c0, ucols, xsu, gw, lane);
                     else if (p.agg.mode == KAGNN_AGG_WEIGHTED) gather_unit_fast<true>(p, row0, c0, ucols, xsu, gw, lane, KAGNN_TC2_HUB ? hub_scratch : nullptr);
@@ -1198,7 +1522,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                         TRC(3, cq, 0);
                         tc::mbar_wait_relaxed(&empty[s], par);
                         TRC(3, cq, 1);
-                        const uint32_t bytes = c.b_bytes(L.N_pad);
+                        const uint32_t bytes = c.b_bytes(L.N_pad) / KAGNN_TC2_WDIV;   // WDIV > 1: development probe (results are wrong)
                         tc::mbar_arrive_expect_tx(&full[s], bytes);
                         tc::bulk_g2s(bst + (size_t)s * p.bstage_bytes, L.wtc + c.b_off(L.N_pad), bytes, &full[s]);
                         if (++s == p.ns) { s = 0; par ^= 1u; }
@@ -1221,13 +1545,15 @@ constexpr int AGG_WARPS = 8;
 __global__ void __launch_bounds__(AGG_WARPS * 32) aggregate_only_kernel(const __grid_constant__ Tc2Params p) {
     __shared__ HubScratch hub;
     const int lane = threadIdx.x & 31, gw = threadIdx.x >> 5;
-    const long long row0 = (long long)blockIdx.x * BM;                     // block = one 128-row tile, warp gw = rows 16 gw ..
     const int F = p.agg.num_cols;
-    for (int c0 = 0; c0 < F; c0 += 128) {
-        float* out = p.agg_out + row0 * p.ld_agg_out + c0;
-        const int ucols = min(128, F - c0);
-        if (p.agg.mode == KAGNN_AGG_WEIGHTED) gather_unit_fast<true, true>(p, row0, c0, ucols, out, gw, lane, &hub);
-        else gather_unit_fast<false, true>(p, row0, c0, ucols, out, gw, lane, &hub);
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {     // block = one 128-row tile at a time, warp gw = rows 16 gw ..
+        const long long row0 = (long long)tile * BM;
+        for (int c0 = 0; c0 < F; c0 += 128) {
+            float* out = p.agg_out + row0 * p.ld_agg_out + c0;
+            const int ucols = min(128, F - c0);
+            if (p.agg.mode == KAGNN_AGG_WEIGHTED) gather_unit_fast<true, true>(p, row0, c0, ucols, out, gw, lane, &hub);
+            else gather_unit_fast<false, true>(p, row0, c0, ucols, out, gw, lane, &hub);
+        }
     }
 }
 
@@ -1254,8 +1580,17 @@ int kagnn_aggregate_only_tc2(const KagnnAggregate* agg, int64_t num_rows, const 
     p.xld = (int)ld_agg_out;
     if (ld_agg_out > (int64_t)INT32_MAX) return KAGNN_EUNSUPPORTED;
     static_assert(AGG_WARPS == NGW && AGG_WARPS * RPW == BM, "aggregate_only_kernel: one block = one 128-row tile of NGW warps");
-    const unsigned blocks = (unsigned)ceil_div64(num_rows, BM);
-    aggregate_only_kernel<<<blocks, AGG_WARPS * 32, 0, stream>>>(p);
+    unsigned blocks = (unsigned)ceil_div64(num_rows, BM);
+    p.n_tiles = (int)blocks;
+    size_t dbg_smem = 0;
+#ifdef KAGNN_DEBUG_KNOBS
+    if (const char* e = getenv("KAGNN_DEBUG_AGG_GRID")) blocks = (unsigned)atoi(e);
+    if (const char* e = getenv("KAGNN_DEBUG_AGG_SMEM")) {
+        dbg_smem = (size_t)atoi(e);
+        cudaFuncSetAttribute(aggregate_only_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dbg_smem);
+    }
+#endif
+    aggregate_only_kernel<<<blocks, AGG_WARPS * 32, dbg_smem, stream>>>(p);
     KAGNN_LAUNCH_CHECK();
     return KAGNN_OK;
 }
@@ -1335,14 +1670,21 @@ int kagnn_fused_fwd_tc2(const KagnnAggregate* agg, int64_t num_rows, const Kagnn
     p.y_vec = aligned16(y) && (ldy % 4 == 0);
 
     const int F_pad0 = p.layers[0].F_pad;
-    p.uw = F_pad0 > 64 ? 128 : 64;
-    p.uw_shift = F_pad0 > 64 ? 7 : 6;
+    // asynchronous gather: GIN / GCN aggregation of rows whose width is a multiple of 64 columns, 128-bit aligned operands
+    p.ag = KAGNN_TC2_AG && (agg->mode == KAGNN_AGG_GIN || agg->mode == KAGNN_AGG_WEIGHTED) && agg->num_cols % 64 == 0 &&
+           aligned16(agg->x) && agg->ldx % 4 == 0 && (!agg->x_halo || (aligned16(agg->x_halo) && agg->ld_halo % 4 == 0)) &&
+           num_rows < (1LL << 30) && (!agg->peer_x || agg->rows_per_rank * (int64_t)agg->num_ranks < (1LL << 30)) &&
+           (!agg->x_halo || agg->num_local_src < (1LL << 29)) &&
+           !(rbf && layers[0].ln_weight && F_pad0 > 64);          // in-kernel LayerNorm statistics need the row in ONE unit
+    p.uw = (F_pad0 > 64 && !p.ag) ? 128 : 64;
+    p.uw_shift = p.uw == 128 ? 7 : 6;
     p.xld = p.uw + 4;                                   // (xld / 4) odd: conflict-free float4 reads with thread = row
     p.unit_floats = BM * p.xld;
     p.units_per_tile = (F_pad0 + p.uw - 1) / p.uw;
     p.bstage_bytes = 256 * n_max;
     // LUTs | mbarriers (x ring full/empty, stage full/empty, 2 accumulator) | tmem slot (16 B) | post scale/shift | progress word
-    const int tail = KAGNN_MAX_LAYERS * LUT_ROWS * 16 + (2 * MAX_UNITS + 2 * MAX_STAGE + 2) * 8 + 16 + 2 * 128 * 4 + 16 + (int)sizeof(HubScratch) + 2 * NWG * 128 * 8;
+    const int tail = KAGNN_MAX_LAYERS * LUT_ROWS * 16 + (2 * MAX_UNITS + 2 * MAX_STAGE + 2) * 8 + 16 + 2 * 128 * 4 + 16 + (int)sizeof(HubScratch) + 2 * NWG * 128 * 8 +
+                     (p.ag ? AG_BYTES : 0);
     const int unit_bytes = p.unit_floats * (int)sizeof(float);
     // ring depths: at least 2 x-units and 2 stages; prefer deeper stages, then more units
     int best_units = 0, best_ns = 0;

@@ -7,6 +7,7 @@ destination-sorted int32 CSR (deterministic reduction order, no atomics), the GC
 per graph, and both are kept in a small identity-keyed cache."""
 from __future__ import annotations
 
+import os
 from collections import OrderedDict
 from typing import Optional, Tuple
 
@@ -22,6 +23,7 @@ class GraphCSR:
 
     def __init__(self, edge_index: Tensor, num_nodes: int, num_src_nodes: Optional[int] = None):
         self.csr = ops.csr_build(edge_index, num_nodes, num_src_nodes)
+        _watch_index_flag(self.csr)
         self.num_nodes = num_nodes
         self._gcn: Optional[Tuple[Tensor, Tensor, Tensor]] = None
         self._edge_index = edge_index
@@ -66,6 +68,44 @@ class GraphCSR:
         return self._gcn_t
 
 
+# ---- deferred range check of edge_index -------------------------------------------------------------------------------
+# kagnn_csr_build never synchronises: it clamps an out-of-range node id to 0 and raises a device-side flag.  PyG / ATen would
+# raise (or device-assert) on such an edge_index, so the flag must not go unread: its 4 bytes are copied to pinned host memory
+# behind the build and examined -- without blocking -- whenever a later graph call finds the copy complete, which raises
+# IndexError then (like any asynchronous CUDA error surfaces at a later call).  KAGNN_CHECK_INDICES=1 checks synchronously.
+_PENDING: list = []
+
+
+def _watch_index_flag(csr) -> None:
+    if csr.err_flag is None or not csr.err_flag.is_cuda or torch.cuda.is_current_stream_capturing():
+        return
+    host = torch.empty(1, dtype=torch.int32).pin_memory()
+    host.copy_(csr.err_flag, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    _PENDING.append((ev, host, csr.num_rows))
+    if os.environ.get("KAGNN_CHECK_INDICES") == "1":
+        ev.synchronize()
+    poll_index_flags()
+
+
+def poll_index_flags(block: bool = False) -> None:
+    """Raise IndexError if a finished CSR build saw node ids outside [0, num_nodes); ``block=True`` waits for every build."""
+    if not _PENDING or torch.cuda.is_current_stream_capturing():
+        return
+    bad = None
+    for item in list(_PENDING):
+        ev, host, n = item
+        if block:
+            ev.synchronize()
+        if ev.query():
+            _PENDING.remove(item)
+            if int(host[0]) != 0:
+                bad = n
+    if bad is not None:
+        raise IndexError(f"kagnn_b200: edge_index contains node ids outside [0, {bad}) (detected by an earlier CSR build)")
+
+
 _CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
 _CACHE_SIZE = 4
 
@@ -81,6 +121,7 @@ def get_graph(edge_index: Tensor, num_nodes: int) -> GraphCSR:
         raise RuntimeError("kagnn_b200: edge_index must be a CUDA tensor (no CPU fallback)")
     key = (edge_index.data_ptr(), tuple(edge_index.shape), tuple(edge_index.stride()), edge_index._version,
            int(num_nodes), edge_index.device.index)
+    poll_index_flags()
     hit = _CACHE.get(key)
     if hit is not None:
         _CACHE.move_to_end(key)

@@ -5,6 +5,8 @@ Nothing here falls back to torch math: a CPU tensor or a missing library raises.
 from __future__ import annotations
 
 import ctypes as C
+import dataclasses
+import functools
 from dataclasses import dataclass
 from typing import Optional, Sequence
 
@@ -21,7 +23,53 @@ fused_timing = None
 
 
 def _stream() -> C.c_void_p:
+    """Current stream of the current device; every public op below runs under ``_on_device``, which makes the device of
+    its tensor arguments the current one first (the library launches on cudaGetDevice and never switches devices itself)."""
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _devices_of(obj, found: set) -> None:
+    """Devices of the tensors of a launch argument.  Records (AggSpec, KanLayerSpec, Affine, CSR) name the tensors that stand
+    for them in ``_anchors`` -- enough to catch inputs / weights / outputs on different devices without walking every field on
+    every launch."""
+    if obj is None:
+        return
+    if isinstance(obj, torch.Tensor):
+        if obj.is_cuda:
+            found.add(obj.device.index)
+    elif isinstance(obj, (list, tuple)):
+        for o in obj:
+            _devices_of(o, found)
+    elif hasattr(obj, "_anchors"):
+        d = obj.__dict__
+        for n in obj._anchors:
+            v = d[n]
+            if v is not None and v.is_cuda:
+                found.add(v.device.index)
+    elif isinstance(obj, torch.nn.Module):
+        for t in obj._parameters.values():
+            _devices_of(t, found)
+        for t in obj._buffers.values():
+            _devices_of(t, found)
+
+
+def _on_device(fn):
+    """Device guard of a launch wrapper (what ATen ops do implicitly): all CUDA tensor arguments -- also inside the AggSpec /
+    KanLayerSpec / Affine / CSR records and BatchNorm modules -- must live on ONE device, and that device is made current for
+    the call, so the kernels, workspaces and the stream handed to the library belong to the tensors and not to whatever device
+    happened to be current."""
+    @functools.wraps(fn)
+    def guarded(*args, **kwargs):
+        found: set = set()
+        _devices_of(args, found)
+        _devices_of(tuple(kwargs.values()), found)
+        if len(found) > 1:
+            raise RuntimeError(f"kagnn_b200.{fn.__name__}: tensor arguments live on different CUDA devices {sorted(found)}")
+        if not found or next(iter(found)) == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(next(iter(found))):
+            return fn(*args, **kwargs)
+    return guarded
 
 
 def _p(t: Optional[Tensor]) -> Optional[C.c_void_p]:
@@ -68,6 +116,7 @@ class CSR:
     num_rows: int
     num_src: int
     err_flag: Tensor      # int32 scalar: non-zero if an index was out of range
+    _anchors = ("rowptr",)
 
     @property
     def nnz(self) -> int:
@@ -79,6 +128,7 @@ class CSR:
             raise IndexError("kagnn_b200: edge_index contains node ids outside [0, num_nodes)")
 
 
+@_on_device
 def csr_build(edge_index: Tensor, num_nodes: int, num_src_nodes: Optional[int] = None) -> CSR:
     global launch_count
     _need_cuda(edge_index, "edge_index", torch.int64)
@@ -96,9 +146,12 @@ def csr_build(edge_index: Tensor, num_nodes: int, num_src_nodes: Optional[int] =
     L.check(L.lib().kagnn_csr_build(_p(ei), E, num_nodes, nsrc, _p(rowptr), _p(col), _p(perm), _p(ws), wbytes, _stream()),
             "csr_build")
     launch_count += 5 if E else 0
-    return CSR(rowptr, col, perm, num_nodes, nsrc, ws[:4].view(torch.int32))
+    # the range-check flag is the first word of the workspace: keep a 4-byte copy so the workspace (16 B per edge + sort
+    # scratch) is released as soon as the build has run instead of living as long as the cached graph
+    return CSR(rowptr, col, perm, num_nodes, nsrc, ws[:4].view(torch.int32).clone())
 
 
+@_on_device
 def segment_ptr(batch: Tensor, num_graphs: int) -> Tensor:
     global launch_count
     _need_cuda(batch, "batch", torch.int64)
@@ -109,6 +162,7 @@ def segment_ptr(batch: Tensor, num_graphs: int) -> Tensor:
     return ptr
 
 
+@_on_device
 def gcn_norm(csr: CSR, edge_weight_csr: Optional[Tensor] = None):
     """PyG gcn_norm on the CSR -> (edge_weight (nnz), self_weight (N), dinv (N))."""
     global launch_count
@@ -126,6 +180,7 @@ def gcn_norm(csr: CSR, edge_weight_csr: Optional[Tensor] = None):
     return w, sw, dinv
 
 
+@_on_device
 def gcn_degree(csr: CSR, edge_weight_csr: Optional[Tensor] = None):
     """First half of gcn_norm: (self_weight (N), dinv (N)) of the destination rows."""
     global launch_count
@@ -138,6 +193,7 @@ def gcn_degree(csr: CSR, edge_weight_csr: Optional[Tensor] = None):
     return sw, dinv
 
 
+@_on_device
 def gcn_edge_weight(csr: CSR, dinv_src: Tensor, dinv_dst: Tensor, edge_weight_csr: Optional[Tensor] = None) -> Tensor:
     """Second half of gcn_norm: w_e = dinv_src[col_e] * w_e * dinv_dst[row]; dinv_src covers halo rows too."""
     global launch_count
@@ -153,6 +209,7 @@ def gcn_edge_weight(csr: CSR, dinv_src: Tensor, dinv_dst: Tensor, edge_weight_cs
     return w
 
 
+@_on_device
 def gather_rows(x: Tensor, index: Optional[Tensor], out: Optional[Tensor] = None, num_rows: Optional[int] = None) -> Tensor:
     """out[r] = x[index[r]] (halo send-buffer packing); ``index=None`` copies the first ``num_rows`` rows."""
     global launch_count
@@ -172,6 +229,7 @@ def gather_rows(x: Tensor, index: Optional[Tensor], out: Optional[Tensor] = None
     return out
 
 
+@_on_device
 def layernorm_stats(x: Tensor, x_head: Optional[Tensor] = None, eps: float = 1e-5) -> Tensor:
     """(rows, 2) per-row (mean, rstd) of LayerNorm over the two-part rows [x_head | x] (kagnn_layernorm_stats)."""
     global launch_count
@@ -186,6 +244,7 @@ def layernorm_stats(x: Tensor, x_head: Optional[Tensor] = None, eps: float = 1e-
     return stats
 
 
+@_on_device
 def log_softmax(x: Tensor) -> Tensor:
     """Row-wise log_softmax of (rows, classes) logits (kagnn_log_softmax_rows)."""
     global launch_count
@@ -197,6 +256,7 @@ def log_softmax(x: Tensor) -> Tensor:
     return y
 
 
+@_on_device
 def batchnorm_forward(x: Tensor, bn, act: int = L.ACT_NONE) -> Tensor:
     """``bn(x)`` of a ``torch.nn.BatchNorm1d`` in training mode (or without running statistics): batch statistics, running
     estimates updated like torch does (kagnn_batchnorm_train_fwd).  Eval mode with running statistics is folded into the
@@ -223,10 +283,15 @@ def batchnorm_forward(x: Tensor, bn, act: int = L.ACT_NONE) -> Tensor:
         _p(y), _rows(y, "y"), _p(ws), wbytes, _stream()), "batchnorm_train_fwd")
     if track:
         bn.num_batches_tracked += 1
+        # the kernel updated the running statistics through raw pointers: bump their version counters like an in-place ATen
+        # op would, so that caches keyed on them (models_node._BNFold) see the change
+        torch.autograd.graph.increment_version(bn.running_mean)
+        torch.autograd.graph.increment_version(bn.running_var)
     launch_count += 3
     return y
 
 
+@_on_device
 def gather_rows_peer(peer_x: Tensor, ldx: int, rows_per_rank: int, ids: Tensor, num_cols: int, out: Optional[Tensor] = None) -> Tensor:
     """out[r] = row ids[r] % rows_per_rank of rank ids[r] // rows_per_rank, pulled over NVLink (kagnn_gather_rows_peer)."""
     global launch_count
@@ -245,6 +310,7 @@ def gather_rows_peer(peer_x: Tensor, ldx: int, rows_per_rank: int, ids: Tensor, 
 # ---------------------------------------------------------------------------------------------------
 # weights
 # ---------------------------------------------------------------------------------------------------
+@_on_device
 def pack_kan_weights(base_w: Optional[Tensor], spline_w: Tensor, scaler: Optional[Tensor], in_f: int, out_f: int,
                      slots: int) -> Tensor:
     global launch_count
@@ -268,6 +334,7 @@ def tc_supported(basis: int, grid_size: int, spline_order: int, out_features: in
     return 1 <= grid_size <= 8
 
 
+@_on_device
 def pack_kan_weights_tc(base_w: Optional[Tensor], spline_w: Tensor, scaler: Optional[Tensor], in_f: int, out_f: int,
                         slots: int) -> Tensor:
     """bf16 hi/lo weights in the UMMA canonical layout, chunked for the tcgen05 kernel."""
@@ -318,6 +385,7 @@ class KanLayerSpec:
     ln_bias: Optional[Tensor] = None
     packed_w_tc: Optional[Tensor] = None
     ln_stats: Optional[Tensor] = None     # per-row (mean, rstd) of the first layer's LayerNorm (layernorm_stats); per call
+    _anchors = ("packed_w",)
 
     def fill(self, s: L.KagnnKanLayer) -> None:
         s.basis, s.in_features, s.out_features = self.basis, self.in_features, self.out_features
@@ -336,6 +404,7 @@ class Affine:
     scale: Optional[Tensor] = None
     shift: Optional[Tensor] = None
     act: int = L.ACT_NONE
+    _anchors = ("scale", "shift")
 
     def struct(self) -> L.KagnnAffine:
         for t, n in ((self.scale, "scale"), (self.shift, "shift")):
@@ -363,6 +432,7 @@ class AggSpec:
     peer_x: Optional[Tensor] = None       # node-sharded graphs, in-kernel NVLink gather: (world,) int64 peer base pointers
     rows_per_rank: int = 0
     x_head: Optional[Tensor] = None       # AGG_NONE two-part rows: logical row = [x_head[r] | x[r]] (skip concat without the copy)
+    _anchors = ("x", "rowptr", "x_head", "x_halo", "edge_feat")
 
     def __post_init__(self) -> None:
         # the C ABI takes row-major matrices with a leading dimension: a transposed / column-strided view (which the
@@ -440,6 +510,7 @@ def _launch_fused_raw(agg: AggSpec, num_rows: int, layers: Sequence[KanLayerSpec
         _p(y), _rows(y, "y") if y is not None else 0, _stream())
 
 
+@_on_device
 def fused_layer(agg: AggSpec, num_rows: int, layers: Sequence[KanLayerSpec], pre: Optional[Affine] = None,
                 post: Optional[Affine] = None, agg_out: Optional[Tensor] = None, out: Optional[Tensor] = None) -> Optional[Tensor]:
     """tile = aggregate(x) -> pre -> [agg_out] -> KAN chain -> post -> out, in one launch
@@ -459,7 +530,6 @@ def fused_layer(agg: AggSpec, num_rows: int, layers: Sequence[KanLayerSpec], pre
             and layers[0].in_features > 128 and all(sp.out_features <= 128 for sp in layers)):
         # FastKAN over rows wider than one tile unit (the skip-concat read-out): LayerNorm statistics by a small pre-pass so
         # that the pipelined kernel can stream the row unit by unit
-        import dataclasses
         stats = layernorm_stats(agg.x, agg.x_head)
         layers = [dataclasses.replace(layers[0], ln_stats=stats)] + list(layers[1:])
     code = _launch_fused(agg, num_rows, layers, pre, post, agg_out, out)
@@ -482,6 +552,7 @@ def fused_layer(agg: AggSpec, num_rows: int, layers: Sequence[KanLayerSpec], pre
     return out if layers else agg_out
 
 
+@_on_device
 def tc_selftest(a: Tensor, b: Tensor, nprod: int = 3) -> Tensor:
     """D = A @ B^T for one 128-row tile through the tcgen05 path (kagnn_tc_selftest); tests only."""
     global launch_count
@@ -508,6 +579,7 @@ def _layer_struct(spec: KanLayerSpec) -> L.KagnnKanLayer:
     return s
 
 
+@_on_device
 def kan_bwd_input(spec: KanLayerSpec, x: Tensor, dy: Tensor) -> Tensor:
     """d loss / d x of one B-spline KAN layer (kagnn_kan_bwd_input)."""
     global launch_count
@@ -520,6 +592,7 @@ def kan_bwd_input(spec: KanLayerSpec, x: Tensor, dy: Tensor) -> Tensor:
     return dx
 
 
+@_on_device
 def kan_bwd_weights(spec: KanLayerSpec, x: Tensor, dy: Tensor) -> Tensor:
     """Gradient of the packed fp32 weights [in][slots+1][out_pad4] (kagnn_kan_bwd_weights)."""
     global launch_count
@@ -532,6 +605,7 @@ def kan_bwd_weights(spec: KanLayerSpec, x: Tensor, dy: Tensor) -> Tensor:
     return d_packed
 
 
+@_on_device
 def kan_unpack_weight_grads(d_packed: Tensor, spline_w: Tensor, scaler: Optional[Tensor], need_base: bool = True):
     """d_packed -> (d base_weight | None, d spline_weight, d spline_scaler | None) (kagnn_kan_unpack_weight_grads)."""
     global launch_count
@@ -548,6 +622,7 @@ def kan_unpack_weight_grads(d_packed: Tensor, spline_w: Tensor, scaler: Optional
     return d_base, d_spline, d_scaler
 
 
+@_on_device
 def batchnorm_backward(x: Tensor, dy: Tensor, weight: Optional[Tensor], eps: float):
     """Backward of training-mode BatchNorm1d -> (dx, d weight, d bias) (kagnn_batchnorm_train_bwd)."""
     global launch_count
@@ -565,6 +640,7 @@ def batchnorm_backward(x: Tensor, dy: Tensor, weight: Optional[Tensor], eps: flo
     return dx, dw, db
 
 
+@_on_device
 def column_sums(x: Tensor) -> Tensor:
     global launch_count
     ldx = _rows(x, "x")
@@ -574,6 +650,7 @@ def column_sums(x: Tensor) -> Tensor:
     return out
 
 
+@_on_device
 def log_softmax_backward(y: Tensor, dy: Tensor) -> Tensor:
     global launch_count
     dx = torch.empty(y.size(0), y.size(1), dtype=torch.float32, device=y.device)
@@ -584,6 +661,7 @@ def log_softmax_backward(y: Tensor, dy: Tensor) -> Tensor:
     return dx
 
 
+@_on_device
 def silu_forward(x: Tensor) -> Tensor:
     global launch_count
     y = torch.empty(x.size(0), x.size(1), dtype=torch.float32, device=x.device)
@@ -593,6 +671,7 @@ def silu_forward(x: Tensor) -> Tensor:
     return y
 
 
+@_on_device
 def silu_backward(x: Tensor, dy: Tensor) -> Tensor:
     global launch_count
     dx = torch.empty(x.size(0), x.size(1), dtype=torch.float32, device=x.device)
@@ -603,6 +682,7 @@ def silu_backward(x: Tensor, dy: Tensor) -> Tensor:
     return dx
 
 
+@_on_device
 def segment_pool_backward(d_pooled: Tensor, ptr: Tensor, batch: Tensor, num_rows: int, mean: bool) -> Tensor:
     global launch_count
     _need_cuda(ptr, "segment_ptr", torch.int32)
@@ -616,6 +696,7 @@ def segment_pool_backward(d_pooled: Tensor, ptr: Tensor, batch: Tensor, num_rows
     return dx
 
 
+@_on_device
 def rbf_bwd_input(spec: KanLayerSpec, x: Tensor, stats: Optional[Tensor], dy: Tensor):
     """FastKAN layer: (dz, dx_base) with a LayerNorm (stats given), else (complete dx, None) (kagnn_rbf_bwd_input)."""
     global launch_count
@@ -629,6 +710,7 @@ def rbf_bwd_input(spec: KanLayerSpec, x: Tensor, stats: Optional[Tensor], dy: Te
     return dz, dxb
 
 
+@_on_device
 def rbf_bwd_weights(spec: KanLayerSpec, x: Tensor, stats: Optional[Tensor], dy: Tensor) -> Tensor:
     """Gradient of the packed FastKAN weights [in][G+1][out_pad4] (kagnn_rbf_bwd_weights)."""
     global launch_count
@@ -640,6 +722,7 @@ def rbf_bwd_weights(spec: KanLayerSpec, x: Tensor, stats: Optional[Tensor], dy: 
     return d_packed
 
 
+@_on_device
 def layernorm_backward(x: Tensor, stats: Tensor, ln_weight: Optional[Tensor], dz: Tensor, dx_base: Optional[Tensor], affine: bool):
     """LayerNorm backward -> (dx, d weight | None, d bias | None) (kagnn_layernorm_bwd)."""
     global launch_count
@@ -654,6 +737,7 @@ def layernorm_backward(x: Tensor, stats: Tensor, ln_weight: Optional[Tensor], dz
     return dx, dw, db
 
 
+@_on_device
 def gine_backward(x: Tensor, edge_feat: Tensor, edge_index: Tensor, da: Tensor, self_scale: float, need_edge_grad: bool = True):
     """Backward of the GINE aggregation on the COO edge list -> (dx, d edge_feat | None) (kagnn_gine_bwd)."""
     global launch_count

@@ -1,0 +1,101 @@
+"""The three transports of the node-sharded forward (kagnn_b200/dist.py: NCCL halo matrix, NVLink pull, in-kernel NVLink gather)
+exercised on ONE GPU: the ranks are simulated inside one process -- every "rank" owns a separately allocated block of rows, the
+peer table (KagnnAggregate.peer_x) holds the base pointers of all blocks, and the halo matrix is filled by the same pull kernel
+(kagnn_gather_rows_peer) the multi-GPU run uses.  The kernels cannot tell a peer-mapped pointer from a local one, so this checks
+exactly the device code of `mode="peer"` / `mode="pull"` / `mode="halo"` (x_halo) on the single-GPU test box; the process-group
+side (symmetric memory rendezvous, barriers, all-to-all) is covered by tests/test_gpu_dist.py (>= 2 GPUs) and tests/test_dist_gloo.py.
+Reference: the single-GPU forward of the same layer and the oracle (PyG GINConv / GCNConv semantics, nc/models.py:31-56)."""
+import pytest
+import torch
+
+from oracle import kagnn_oracle as K
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _setup(world, n_local, f, e, seed):
+    g = torch.Generator().manual_seed(seed)
+    n = world * n_local
+    x = torch.randn(n, f, generator=g) * 0.5
+    ei = torch.randint(0, n, (2, e), generator=g)
+    return n, x, ei
+
+
+@pytest.mark.parametrize("fast", [False, True])
+@pytest.mark.parametrize("world,f", [(2, 64), (4, 128), (3, 48)])
+def test_gin_layer_peer_and_pull_transports_single_gpu(world, f, fast):
+    import kagnn_b200 as kb
+    from kagnn_b200 import dist as kd
+    from kagnn_b200 import ops
+    from kagnn_b200.graph import GraphCSR
+    torch.manual_seed(1)
+    n_local = 1111                                                # not a multiple of the 128-row tile
+    n, x, ei = _setup(world, n_local, f, 9 * world * n_local, seed=world * 100 + f)
+    conv = (kb.GIFASTKANLayer(f, 32, 5, 32, 2) if fast else kb.GIKANLayer(f, 32, 5, 3, 32, 2))
+    sd = {k: v.detach().clone() for k, v in conv.state_dict().items()}
+    conv = conv.cuda()
+    dev = torch.device("cuda")
+    with torch.no_grad():
+        y_single = conv(x.to(dev), ei.to(dev)).cpu()
+    chain = (lambda t: K.fastkan_chain(sd, "nn.layers.", t)) if fast else (lambda t: K.kan_chain(sd, "nn.layers.", t))
+    ref = K.gin_conv(x, ei, chain)
+    assert K.rel_err(y_single, ref) <= TOL
+    blocks = [x[r * n_local:(r + 1) * n_local].to(dev).clone() for r in range(world)]       # one allocation per "rank"
+    table = torch.tensor([b.data_ptr() for b in blocks], dtype=torch.int64, device=dev)
+    y_peer, y_pull = [], []
+    with torch.no_grad():
+        for r in range(world):
+            lo = r * n_local
+            mine = (ei[1] >= lo) & (ei[1] < lo + n_local)
+            ei_r = ei[:, mine].to(dev)
+            # in-kernel gather: CSR over GLOBAL source ids, rows read through the peer table
+            g_peer = GraphCSR(torch.stack([ei_r[0], ei_r[1] - lo]), n_local, n)
+            y_peer.append(conv(blocks[r], g_peer, peer_x=table, rows_per_rank=n_local).cpu())
+            # pull: distinct remote rows copied by the pull kernel into a halo matrix, CSR over the local + halo numbering
+            ei_local, halo_global, _ = kd.relabel_edges(ei_r, r, world, n_local)
+            halo = ops.gather_rows_peer(table, blocks[r].stride(0), n_local, halo_global.to(torch.int32), f)
+            assert torch.equal(halo.cpu(), x[halo_global.cpu()])
+            g_pull = GraphCSR(ei_local, n_local, n_local + int(halo_global.numel()))
+            y_pull.append(conv(blocks[r], g_pull, x_halo=halo).cpu())
+    for name, ys in (("peer", y_peer), ("pull", y_pull)):
+        y = torch.cat(ys)
+        assert K.rel_err(y, y_single) <= 2e-6, name              # same kernels; only the order of equal-valued row sources may differ
+        assert K.rel_err(y, ref) <= TOL, name
+
+
+def test_gcn_layer_halo_matrix_single_gpu():
+    """GCN flavour over a halo matrix (the transport `auto` keeps for GCN / non-skip models): h = KAN(x) of the remote sources
+    arrives in x_halo, gcn_norm weights come from the degrees of the whole graph."""
+    import kagnn_b200 as kb
+    from kagnn_b200 import _lib as L
+    from kagnn_b200 import dist as kd
+    from kagnn_b200 import ops
+    from kagnn_b200.graph import GraphCSR
+    torch.manual_seed(2)
+    world, n_local, f = 2, 1500, 64
+    n, x, ei = _setup(world, n_local, f, 14_000, seed=5)
+    conv = kb.KAGCNConv(f, 32, 5, 3)
+    with torch.no_grad():
+        conv.bias.normal_(0, 0.1)
+    sd = {k: v.detach().clone() for k, v in conv.state_dict().items()}
+    conv = conv.cuda()
+    dev = torch.device("cuda")
+    ref = K.gcn_conv(x, ei, lambda t: K._kan_layer_from_sd(sd, "lin.", t), sd["bias"])
+    with torch.no_grad():
+        h = conv.transform(x.to(dev))                              # KAN(x) of every node (each rank computes its own rows)
+        full = GraphCSR(ei.to(dev), n)
+        _, dinv_all = ops.gcn_degree(full.csr)
+        ys = []
+        for r in range(world):
+            lo = r * n_local
+            mine = (ei[1] >= lo) & (ei[1] < lo + n_local)
+            ei_local, halo_global, _ = kd.relabel_edges(ei[:, mine].to(dev), r, world, n_local)
+            g = GraphCSR(ei_local, n_local, n_local + int(halo_global.numel()))
+            sw, dinv = ops.gcn_degree(g.csr)
+            assert torch.allclose(dinv, dinv_all[lo:lo + n_local])
+            w = ops.gcn_edge_weight(g.csr, torch.cat([dinv, dinv_all[halo_global]]), dinv)
+            agg = ops.AggSpec(L.AGG_WEIGHTED, h[lo:lo + n_local], g.rowptr, g.col, edge_weight=w, self_weight=sw,
+                              x_halo=h[halo_global].contiguous())
+            ys.append(ops.fused_layer(agg, n_local, [], pre=ops.Affine(shift=conv.bias.detach())).cpu())
+    assert K.rel_err(torch.cat(ys), ref) <= TOL
