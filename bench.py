@@ -208,6 +208,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary configurations (key 'extra' of the line)")
+    ap.add_argument("--config", default="arxiv", choices=["arxiv", "cora", "zinc", "mutag", "rmat"],
+                    help="arxiv = the headline workload (BASELINE configs[1]); the others print the secondary measurement of that "
+                         "configuration alone (scripts/bench_extras.py) as one JSON line")
     ap.add_argument("--dist-mode", default="auto", choices=["auto", "peer", "pull", "halo"],
                     help="N > 1: 'peer' = in-kernel NVLink gather from symmetric memory, 'halo' = NCCL all-to-all per layer")
     args = ap.parse_args()
@@ -220,6 +224,17 @@ def main():
     args.warmup = max(args.warmup, 3)            # timing rules: at least 3 warm-up steps (the line reports what was run)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the kagnn_b200 path has no CPU fallback")
+    if args.config != "arxiv":
+        if rank == 0:
+            sys.path.insert(0, os.path.join(ROOT, "scripts"))
+            import bench_extras as BX
+            torch.cuda.set_device(local_rank)
+            dev = torch.device("cuda", local_rank)
+            flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+            fn = getattr(BX, args.config)
+            res = fn(dev, flush) if args.config == "rmat" else fn(dev, flush, with_cpu=not args.no_cpu_baseline)
+            print(json.dumps({"config": args.config, **res}), flush=True)
+        return
     import kagnn_b200 as kb
     from kagnn_b200 import ops
 
@@ -374,7 +389,9 @@ def main():
         tf = 3.0 * dense / (top["ms"] * 1e-3) / 1e12
         roofline = {"bound": "hbm", "kernel": top["label"], "launch_ms": top["ms"], "algorithmic_bytes": bytes_,
                     "achieved": ach, "peak": pk["hbm_gbs"], "peak_source": pk_src, "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-                    "traffic": NCU_TRAFFIC_BYTES.get(top["label"]),
+                    "traffic": NCU_TRAFFIC_BYTES.get(top["label"]) if not dist_on else None,
+                    "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of the same launch at N=1 (profiles/, not re-measured "
+                                      "in this run); null for N>1, where the gather also reads peer memory over NVLink",
                     "tensor": {"achieved_tflops_bf16x3": tf, "peak_tflops": pk["bf16_tflops"], "frac": tf / pk["bf16_tflops"],
                                "dense_fp32_equiv_flops": dense},
                     "note": "no-reuse gather model (SURVEY 8d); feature matrix (87 MB) is L2-resident after first touch, so DRAM "
@@ -387,6 +404,40 @@ def main():
         cpu = {"value": n_s / min(ts), "unit": "nodes/s", "cores": threads, "kind": "port",
                "sample": f"oracle forward of the full model on the full {n_s}-node / {e_s}-edge workload graph, best of 2 (1 warm-up)"}
 
+    # ---- NVLink side of the sharded run: bytes this rank pulls from its peers per step against the measured peer-copy rate ----
+    if roofline is not None and dist_on:
+        widths = N_FEAT + (MP_LAYERS - 1) * HIDDEN                       # row widths gathered by the three GIN layers: 128 + 64 + 64
+        if runner.mode == "pull":
+            rows, what = int(plan.n_halo), "distinct remote rows (pulled once per layer)"
+        elif runner.mode == "peer":
+            col = plan.graph.col.long()
+            rows = int(((col < rank * n_local) | (col >= (rank + 1) * n_local)).sum())
+            what = "every referenced remote row (in-kernel gather, no de-duplication)"
+        else:
+            rows, what = int(plan.n_halo), "distinct remote rows (NCCL all-to-all per layer)"
+        nv_bytes = rows * widths * 4
+        roofline["nvlink"] = {"bytes_per_step_per_gpu": nv_bytes, "rows": rows, "what": what,
+                              "achieved_gbs_over_step": nv_bytes / (ms_step * 1e-3) / 1e9, "peak_gbs": 770.0,
+                              "peak_source": "measured peer copy per direction per GPU (B200_PROFILING.md)",
+                              "frac_over_step": nv_bytes / (ms_step * 1e-3) / 1e9 / 770.0,
+                              "note": "rank 0's ingress; achieved = bytes / whole step time, so 1.0 would mean the step is nothing but NVLink transfer"}
+
+    # ---- the other BASELINE configurations on this GPU (secondary numbers; N = 1 only) ----------------------------------
+    extra = None
+    if not dist_on and not args.no_extras:
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        import bench_extras as BX
+        extra = {}
+        del x_dev, ei_dev
+        torch.cuda.empty_cache()
+        for name in ("cora", "zinc", "mutag", "rmat"):
+            try:
+                fn = getattr(BX, name)
+                extra[name] = fn(dev, flush, hbm_gbs=pk["hbm_gbs"]) if name == "rmat" else fn(dev, flush, with_cpu=not args.no_cpu_baseline)
+            except Exception as exc:  # a secondary number must never cost the headline
+                extra[name] = {"error": repr(exc)[:300]}
+            torch.cuda.empty_cache()
+
     line = {
         "metric": METRIC, "value": value, "unit": "nodes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -395,10 +446,11 @@ def main():
                    "l2": "flushed between iterations (512 MB memset)", "csr": "cached across steps (static graph)",
                    "parallelism": (f"node-range shards x{world}, " + ("remote rows gathered in-kernel over NVLink (symmetric memory), "
                                    "one device barrier per layer" if runner.mode == "peer" else ("distinct remote rows pulled over NVLink from symmetric memory "
-                                   "by one copy kernel per layer" if runner.mode == "pull" else "one NCCL halo all-to-all per layer")))
+                                   "by a copy kernel that runs concurrently with the layer (first-use order, progress flags; no collective)" if runner.mode == "pull" else "one NCCL halo all-to-all per layer")))
                    if dist_on else "single GPU",
                    "graph": "uniform random edges over all shards: (N-1)/N of the edges are cut" if dist_on else "uniform random edges"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "kernels": kernels, "roofline": roofline, "cpu_baseline": cpu,
+        "extra": extra,
     }
     print(json.dumps(line), flush=True)
     if dist_on:

@@ -123,6 +123,16 @@ typedef struct KagnnAggregate {
     int32_t num_head_cols;
     const float* x_head;
     int64_t ld_head;
+    /* Node-sharded graphs, halo rows that arrive WHILE the layer runs (kagnn_gather_rows_peer_ordered on a second stream): the
+     * halo matrix is filled in the order the destination tiles first use its rows; halo_need[t] (one entry per 128-row tile) =
+     * number of leading halo rows that tiles 0..t reference, halo_flags[c] == halo_epoch <=> halo rows [256 c, 256 c + 256) have
+     * landed.  The gather warps of the pipelined kernel wait for the flags of their tile's prefix before they read x_halo, so the
+     * NVLink transfer overlaps the tensor-core pipeline tile by tile instead of preceding it.  reserve_sms: SMs the launch leaves
+     * free (for the concurrently running pull kernel).  halo_flags == NULL: not used (x_halo must be complete at launch).     */
+    const int32_t* halo_need;
+    const int32_t* halo_flags;
+    int32_t halo_epoch;
+    int32_t reserve_sms;
 } KagnnAggregate;
 
 /* ---- library ------------------------------------------------------------------------------------ */
@@ -192,6 +202,14 @@ int kagnn_fused_layer_fwd(const KagnnAggregate* agg, int64_t num_rows,
 enum { KAGNN_PATH_AUTO = 0, KAGNN_PATH_FP32 = 1, KAGNN_PATH_TC = 2 };
 int kagnn_set_path(int mode);
 int kagnn_get_launch_counters(int64_t* tc_launches, int64_t* fp32_launches);
+/* Arithmetic of the tensor-core path.  KAGNN_PREC_FP32 (default): every product is formed from bf16 hi/lo pairs (three
+ * tcgen05.mma per K step, fp32 accumulate) and matches the reference's fp32 forward within 1e-4.  KAGNN_PREC_BF16: operands are
+ * rounded to bf16 once (ONE product per K step, fp32 accumulate) -- BASELINE config C5 ("fastkan ... hidden=256 grid=8 bf16");
+ * about 2e-3 relative to the fp32 result per layer.  Applies to the pipelined kernel; the other kernels stay fp32. */
+enum { KAGNN_PREC_FP32 = 0, KAGNN_PREC_BF16 = 1 };
+int kagnn_set_precision(int mode);
+int kagnn_get_precision(void);
+
 /* The tensor-core path has two kernels: the pipelined one (A operand in tensor memory, fused_tc2.cu; B-spline chains up
  * to 128 wide) and the general one (A in shared memory, fused_tc.cu).  variant 0 = pipelined first (default),
  * 1 = general only.  kagnn_get_tc2_launches counts launches of the pipelined kernel. */
@@ -215,6 +233,13 @@ int kagnn_gather_rows(const float* x, int64_t ldx, const int32_t* index, int64_t
  * pack + all-to-all: only the distinct remote rows cross the link, no send lists, no NCCL.  16-byte aligned, cols % 4 == 0. */
 int kagnn_gather_rows_peer(const float* const* peer_x, int64_t ldx, int64_t rows_per_rank, const int32_t* ids,
                            int64_t num_rows, int32_t num_cols, float* out, int64_t ld_out, void* stream);
+
+/* The same pull in first-use order with progress flags (see KagnnAggregate.halo_flags): a persistent kernel of num_ctas blocks
+ * copies halo rows [256 c, 256 c + 256) chunk by chunk (block b takes chunks b, b + num_ctas, ...) and then stores `epoch` into
+ * chunk_flags[c] with release semantics.  Launch it on a second stream BEFORE the fused layer that consumes the flags. */
+int kagnn_gather_rows_peer_ordered(const float* const* peer_x, int64_t ldx, int64_t rows_per_rank, const int32_t* ids,
+                                   int64_t num_rows, int32_t num_cols, float* out, int64_t ld_out, int32_t* chunk_flags,
+                                   int32_t epoch, int32_t num_ctas, void* stream);
 
 /* LayerNorm row statistics (fastkan.py:66,78: biased variance, eps 1e-5) of two-part rows [x_head | x] (x_head may be NULL):
  * stats[2r] = mean, stats[2r+1] = 1/sqrt(var + eps).  See KagnnKanLayer.ln_stats. */

@@ -16,5 +16,6 @@ from .conv import (GCNConv, GINConv, GINEConv, KANLayer, FKANLayer, KAGCNConv, F
                    GIFASTKANLayer, KAGCN_Layer, FASTKAGCN_Layer, make_kan, make_fastkan)
 from .models_node import GKAN_Nodes, GFASTKAN_Nodes
 from . import models_graph, models_regr
+from .ops import set_precision, get_precision
 
 __version__ = "0.1.0"

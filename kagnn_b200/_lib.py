@@ -15,6 +15,7 @@ BASIS_BSPLINE, BASIS_RBF = 0, 1
 AGG_NONE, AGG_GIN, AGG_GINE, AGG_WEIGHTED, AGG_SEGMENT_SUM, AGG_SEGMENT_MEAN = range(6)
 ACT_NONE, ACT_SILU = 0, 1
 PATH_AUTO, PATH_FP32, PATH_TC = 0, 1, 2
+PREC_FP32, PREC_BF16 = 0, 1
 MAX_LAYERS = 8
 
 _ERRORS = {-1: ValueError, -2: NotImplementedError, -3: ValueError, -4: RuntimeError, -5: RuntimeError, -6: IndexError}
@@ -46,6 +47,7 @@ class KagnnAggregate(C.Structure):
         ("x_halo", C.c_void_p), ("ld_halo", C.c_int64), ("num_local_src", C.c_int64),
         ("peer_x", C.c_void_p), ("rows_per_rank", C.c_int64), ("num_ranks", C.c_int32), ("num_head_cols", C.c_int32),
         ("x_head", C.c_void_p), ("ld_head", C.c_int64),
+        ("halo_need", C.c_void_p), ("halo_flags", C.c_void_p), ("halo_epoch", C.c_int32), ("reserve_sms", C.c_int32),
     ]
 
 
@@ -78,6 +80,8 @@ _SIGNATURES = {
     "kagnn_set_path": (C.c_int, [C.c_int]),
     "kagnn_get_launch_counters": (C.c_int, [C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "kagnn_set_tc_variant": (C.c_int, [C.c_int]),
+    "kagnn_set_precision": (C.c_int, [C.c_int]),
+    "kagnn_get_precision": (C.c_int, []),
     "kagnn_get_tc2_launches": (C.c_int64, []),
     "kagnn_tc_selftest_workspace": (C.c_size_t, [C.c_int32, C.c_int32]),
     "kagnn_tc_selftest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t,
@@ -90,6 +94,8 @@ _SIGNATURES = {
                                             C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]),
     "kagnn_gather_rows_peer": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64,
                                          C.c_void_p]),
+    "kagnn_gather_rows_peer_ordered": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64,
+                                                 C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "kagnn_kan_bwd_input": (C.c_int, [C.POINTER(KagnnKanLayer), C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
                                       C.c_int64, C.c_void_p]),
     "kagnn_kan_bwd_weights": (C.c_int, [C.POINTER(KagnnKanLayer), C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,

@@ -8,6 +8,7 @@
 namespace {
 std::atomic<int> g_path_mode{KAGNN_PATH_AUTO};
 std::atomic<long long> g_count_tc{0}, g_count_fp32{0}, g_count_tc2{0}, g_count_agg{0};
+std::atomic<int> g_precision{KAGNN_PREC_FP32};
 std::atomic<int> g_tc_variant{0};   // 0 = auto, 1 = only the shared-memory-A kernel (fused_tc.cu); tests/benchmarks
 }  // namespace
 
@@ -41,6 +42,14 @@ extern "C" int kagnn_set_path(int mode) {
     g_path_mode.store(mode);
     return KAGNN_OK;
 }
+
+extern "C" int kagnn_set_precision(int mode) {
+    if (mode != KAGNN_PREC_FP32 && mode != KAGNN_PREC_BF16) return KAGNN_EINVAL;
+    g_precision.store(mode);
+    return KAGNN_OK;
+}
+
+extern "C" int kagnn_get_precision(void) { return g_precision.load(); }
 
 extern "C" int kagnn_set_tc_variant(int variant) {
     if (variant != 0 && variant != 1) return KAGNN_EINVAL;
@@ -79,7 +88,7 @@ extern "C" int kagnn_fused_layer_fwd(const KagnnAggregate* agg, int64_t num_rows
                 }
                 if (rc != KAGNN_EUNSUPPORTED) return rc;
             }
-            if (agg->peer_x || agg->num_head_cols) return KAGNN_EUNSUPPORTED;   // peer gather / two-part rows: pipelined kernel only
+            if (agg->peer_x || agg->num_head_cols || agg->halo_flags) return KAGNN_EUNSUPPORTED;   // peer gather / two-part rows / in-flight halo: pipelined kernel only
             rc = kagnn_fused_fwd_tc(agg, num_rows, pre, agg_out, ld_agg_out, n_layers, layers, post, y, ldy, stream);
             if (rc == KAGNN_OK) {
                 g_count_tc.fetch_add(1);
@@ -101,7 +110,7 @@ extern "C" int kagnn_fused_layer_fwd(const KagnnAggregate* agg, int64_t num_rows
         }
         if (rc != KAGNN_EUNSUPPORTED) return rc;
     }
-    if (agg->peer_x || agg->num_head_cols) return KAGNN_EUNSUPPORTED;
+    if (agg->peer_x || agg->num_head_cols || agg->halo_flags) return KAGNN_EUNSUPPORTED;
     int rc = kagnn_fused_fwd_fp32(agg, num_rows, pre, agg_out, ld_agg_out, n_layers, layers, post, y, ldy, stream);
     if (rc == KAGNN_OK && num_rows > 0) g_count_fp32.fetch_add(1);
     return rc;

@@ -94,6 +94,9 @@ constexpr int FPW = 8 / WGT;                 // features per warpgroup per splin
 #ifndef KAGNN_TC2_X2
 #define KAGNN_TC2_X2 1                       // packed-pair (f32x2) polynomial evaluation in the basis producers
 #endif
+#ifndef KAGNN_TC2_NOMMA
+#define KAGNN_TC2_NOMMA 0                    // development probe: the MMA warp only commits (results are wrong)
+#endif
 #ifndef KAGNN_TC2_NOMATH
 #define KAGNN_TC2_NOMATH 0                   // development probe: producers skip the basis expansion (results are wrong)
 #endif
@@ -134,6 +137,8 @@ struct Tc2Params {
     int uw, uw_shift, xld, n_units, units_per_tile, unit_floats;   // x-tile ring geometry (uw = 1 << uw_shift = 64 or 128)
     int ns, bstage_bytes;                                 // A/B stage ring depth, bytes of one B stage
     int ag;                                               // 1: asynchronous (cp.async ring) gather, 64-column units
+    int wide;                                             // 1: one layer up to 256 outputs wide: a single 256-column accumulator region
+    int bf16;                                             // 1: single bf16 product (A_hi . W_hi), kagnn_set_precision(KAGNN_PREC_BF16)
     LayerT2 layers[KAGNN_MAX_LAYERS];
 };
 
@@ -272,7 +277,7 @@ __device__ __forceinline__ float2 splat(float v) { return make_float2(v, v); }
 
 // Two input values (two features of one row) -> their slot words, bit-identical to two bspline_slots calls: the polynomial part
 // runs as packed pairs (element .x = first feature, .y = second), which halves its issue slots.
-template <int K>
+template <int K, bool BF16 = false>
 __device__ __forceinline__ void bspline_slots2(float inv_h, float c0, float limp, const uint4* __restrict__ lut, float xa, float xb,
                                                uint32_t* hi, uint32_t* lo) {
     float2 u = fma2(make_float2(xa, xb), splat(inv_h), splat(c0));
@@ -295,6 +300,18 @@ __device__ __forceinline__ void bspline_slots2(float inv_h, float c0, float limp
     } else {
         b0 = sub2(splat(1.0f), fr);
         b1 = fr;
+    }
+    if (BF16) {
+        // single-product precision: round the bases to bf16 (nearest), no residual words
+        const uint32_t g01a = pack_rn(b0.x, b1.x), g23a = pack_rn(b2.x, b3.x), g01b = pack_rn(b0.y, b1.y), g23b = pack_rn(b2.y, b3.y);
+        const uint32_t lbase = tc::smem_u32(lut) - (uint32_t)((0x4B400000u - 1u) * 16u);
+        const uint32_t aa = __float_as_uint(t.x) * 16u + lbase, ab = __float_as_uint(t.y) * 16u + lbase;
+        uint4 sa, sb;
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(sa.x), "=r"(sa.y), "=r"(sa.z), "=r"(sa.w) : "r"(aa));
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(sb.x), "=r"(sb.y), "=r"(sb.z), "=r"(sb.w) : "r"(ab));
+        hi[0] = prmt(g01a, g23a, sa.x); hi[1] = prmt(g01a, g23a, sa.y); hi[2] = prmt(g01a, g23a, sa.z); hi[3] = prmt(g01a, g23a, sa.w);
+        hi[4] = prmt(g01b, g23b, sb.x); hi[5] = prmt(g01b, g23b, sb.y); hi[6] = prmt(g01b, g23b, sb.z); hi[7] = prmt(g01b, g23b, sb.w);
+        return;
     }
     const uint32_t h01a = pack_trunc(b0.x, b1.x), h23a = pack_trunc(b2.x, b3.x);
     const uint32_t h01b = pack_trunc(b0.y, b1.y), h23b = pack_trunc(b2.y, b3.y);
@@ -323,6 +340,7 @@ __device__ __forceinline__ void bspline_slots2(float inv_h, float c0, float limp
 
 // FastKAN: the 8 Gaussians exp(-((z - c_g)/den)^2) of one layer-normalised input (fastkan.py:46-47) as bf16 hi / lo slot words.
 // All 8 slots are dense (no placement); slots past num_grids meet zero weights.
+template <bool BF16 = false>
 __device__ __forceinline__ void rbf_slots(float rc0, float rstep, float rk, float z, uint32_t* hi, uint32_t* lo) {
     float v[8];
 #pragma unroll
@@ -332,8 +350,12 @@ __device__ __forceinline__ void rbf_slots(float rc0, float rstep, float rk, floa
     }
 #pragma unroll
     for (int g = 0; g < 8; g += 2) {
-        hi[g / 2] = pack_trunc(v[g], v[g + 1]);
-        lo[g / 2] = pack_rn(trunc_residual(v[g]), trunc_residual(v[g + 1]));
+        if (BF16) {
+            hi[g / 2] = pack_rn(v[g], v[g + 1]);
+        } else {
+            hi[g / 2] = pack_trunc(v[g], v[g + 1]);
+            lo[g / 2] = pack_rn(trunc_residual(v[g]), trunc_residual(v[g + 1]));
+        }
     }
 }
 
@@ -566,10 +588,10 @@ __device__ __forceinline__ void gather_warps_barrier() { asm volatile("bar.sync 
 //   * the column index / edge weight of the NEXT batch of 32 entries are fetched before the current batch is consumed;
 //   * a finished row is parked raw (one STS.128); mean scale, pre-affine and the agg_out store run in a post-pass over
 //     the warp's 16 rows only when the layer has any of them (a plain GIN layer has none).
-template <bool WEIGHTED, bool GOUT = false>      // GOUT: rows are parked in GLOBAL memory (aggregation-only launch): bounds-checked
+template <bool WEIGHTED, bool GOUT = false, int U_ = KAGNN_TC2_GATHER_U>      // GOUT: rows are parked in GLOBAL memory (aggregation-only launch): bounds-checked
 __device__ __forceinline__ void gather_unit_fast(const Tc2Params& p, long long row0, int c0, int ucols, float* __restrict__ xsu,
                                                  int gw, int lane, HubScratch* hub = nullptr) {
-    constexpr int U = KAGNN_TC2_GATHER_U;
+    constexpr int U = U_;
     const KagnnAggregate& a = p.agg;
     const int F = a.num_cols, mode = a.mode, xld = p.xld;
     const bool segment = (mode == KAGNN_AGG_SEGMENT_SUM) || (mode == KAGNN_AGG_SEGMENT_MEAN);
@@ -1009,7 +1031,7 @@ __device__ __forceinline__ void gather_unit_ag(const Tc2Params& p, long long row
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-template <int K>
+template <int K, bool BF16>
 __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_constant__ Tc2Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
     float* xs = reinterpret_cast<float*>(smem);
@@ -1022,10 +1044,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
     uint64_t* empty = full + MAX_STAGE;
     uint64_t* acc_full = empty + MAX_STAGE;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 2);       // acc_full[region]: one barrier per accumulator region
-    float* post_sc = reinterpret_cast<float*>(tmem_slot + 4);     // post-affine of the last layer (<= 128 columns each; 16-byte aligned)
-    float* post_sh = post_sc + 128;
-    volatile int* gather_progress = reinterpret_cast<volatile int*>(post_sh + 128);   // tiles the gather warps have started
-    HubScratch* hub_scratch = reinterpret_cast<HubScratch*>(post_sh + 128 + 4);
+    float* post_sc = reinterpret_cast<float*>(tmem_slot + 4);     // post-affine of the last layer (<= 256 columns each; 16-byte aligned)
+    float* post_sh = post_sc + 256;
+    volatile int* gather_progress = reinterpret_cast<volatile int*>(post_sh + 256);   // tiles the gather warps have started
+    HubScratch* hub_scratch = reinterpret_cast<HubScratch*>(post_sh + 256 + 4);
     float2* ln_part = reinterpret_cast<float2*>(hub_scratch + 1);       // [2][NWG][128]: FastKAN LayerNorm partial sums
     uint8_t* ag_stage = reinterpret_cast<uint8_t*>(ln_part + 2 * NWG * 128);   // [NGW][2][AG_R][256 B]: row slots of the asynchronous gather
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -1045,7 +1067,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
         tc::mbar_fence_init();
     }
     if (tid == 0) *gather_progress = 0;
-    if (tid >= 128 && tid < 256) {
+    if (tid >= 128 && tid < 384) {
         const int c = tid - 128;
         const LayerT2& LL = p.layers[p.n_layers - 1];
         const bool on = p.has_post && c < LL.N;
@@ -1101,7 +1123,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
             tc::mbar_wait(&acc_full[(e_lc - 1) & 1], ((e_lc - 1) >> 1) & 1);
             if (lane == 0 && (warp & 3) == 0 && wg < 2) TRL(4 + wg, e_lc, 3);
             tc::tc_fence_after_sync();
-            const uint32_t taddr = tmem_base + lane_base + (((e_lc - 1) & 1) ? 128u : 0u);
+            const uint32_t taddr = tmem_base + lane_base + ((((e_lc - 1) & 1) && !p.wide) ? 128u : 0u);
             float* yrow = p.y + (e_row0 + row) * p.ldy;
             for (int jb = wg; jb < L.N_pad / 8; jb += NWG) {
                 float v[8];
@@ -1292,16 +1314,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                             for (int i = 0; i < FPW; i += 2) {
                                 uint32_t hi[8], lo[8];
                                 if (K == 0) {
-                                    rbf_slots(rc0, rstep, rk, v[i], hi, lo);
-                                    rbf_slots(rc0, rstep, rk, v[i + 1], hi + 4, lo + 4);
-                                } else if (KAGNN_TC2_X2) {
-                                    bspline_slots2<(K == 0 ? 1 : K)>(inv_h, c0f, limp, lutL, v[i], v[i + 1], hi, lo);
+                                    rbf_slots<BF16>(rc0, rstep, rk, v[i], hi, lo);
+                                    rbf_slots<BF16>(rc0, rstep, rk, v[i + 1], hi + 4, lo + 4);
+                                } else if (KAGNN_TC2_X2 || BF16) {
+                                    bspline_slots2<(K == 0 ? 1 : K), BF16>(inv_h, c0f, limp, lutL, v[i], v[i + 1], hi, lo);
                                 } else {
                                     bspline_slots<(K == 0 ? 1 : K)>(inv_h, c0f, limp, lutL, v[i], hi, lo);
                                     bspline_slots<(K == 0 ? 1 : K)>(inv_h, c0f, limp, lutL, v[i + 1], hi + 4, lo + 4);
                                 }
                                 tc::tmem_st8(a_t + 4u * (uint32_t)(fsh + i), hi);
-                                tc::tmem_st8(a_t + 32u + 4u * (uint32_t)(fsh + i), lo);
+                                if (!BF16) tc::tmem_st8(a_t + 32u + 4u * (uint32_t)(fsh + i), lo);
                             }
                         } else {
 #pragma unroll 1
@@ -1331,10 +1353,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                                     v[i] = (K == 0) ? __fdividef(v[i], 1.0f + ex2_approx(-kLog2e * v[i])) : silu_nan(v[i]);
                                     r[i] = trunc_residual(v[i]);
                                 }
-                                tc::tmem_st4(a_t + 4u * jj, pack_trunc(v[0], v[1]), pack_trunc(v[2], v[3]), pack_trunc(v[4], v[5]),
-                                             pack_trunc(v[6], v[7]));
-                                tc::tmem_st4(a_t + 32u + 4u * jj, pack_rn(r[0], r[1]), pack_rn(r[2], r[3]), pack_rn(r[4], r[5]),
-                                             pack_rn(r[6], r[7]));
+                                if (BF16) {
+                                    tc::tmem_st4(a_t + 4u * jj, pack_rn(v[0], v[1]), pack_rn(v[2], v[3]), pack_rn(v[4], v[5]), pack_rn(v[6], v[7]));
+                                } else {
+                                    tc::tmem_st4(a_t + 4u * jj, pack_trunc(v[0], v[1]), pack_trunc(v[2], v[3]), pack_trunc(v[4], v[5]),
+                                                 pack_trunc(v[6], v[7]));
+                                    tc::tmem_st4(a_t + 32u + 4u * jj, pack_rn(r[0], r[1]), pack_rn(r[2], r[3]), pack_rn(r[4], r[5]),
+                                                 pack_rn(r[6], r[7]));
+                                }
                             }
                         }
                         tc::tmem_st_wait();
@@ -1367,9 +1393,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
             pend_row0 = row0;
             pend_lc = lc;
             have_pend = true;
-            if (!KAGNN_TC2_PIPE_EPI) {
+            if (!KAGNN_TC2_PIPE_EPI || p.wide) {
+                // one accumulator region only (wide layers): read it out before the next tile's first chunk can be handed over
                 epilogue(pend_row0, pend_lc);
                 have_pend = false;
+                if (CPR > 1) asm volatile("bar.sync 4, %0;" ::"n"(NPW * 32) : "memory");
             }
         }
         if (have_pend) epilogue(pend_row0, pend_lc);
@@ -1387,9 +1415,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
         const int F_pad = p.layers[0].F_pad;
         uint32_t uc = 0;
         int it = 0;
+        int halo_done = 0;                                            // leading chunks of 256 halo rows known to have landed
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
             const long long row0 = (long long)tile * BM;
             if (gw == 0 && lane == 0) *gather_progress = it;          // paces the L2 prefetch warp
+            if (p.agg.halo_flags) {
+                // halo rows are being pulled over NVLink while this kernel runs (kagnn_gather_rows_peer_ordered): wait until
+                // the prefix that tiles 0..tile reference has landed
+                const int nchunk = (__ldg(p.agg.halo_need + tile) + 255) >> 8;
+                uint32_t tries = 0;
+                while (halo_done < nchunk) {
+                    int v;
+                    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p.agg.halo_flags + halo_done) : "memory");
+                    if (v == p.agg.halo_epoch) {
+                        ++halo_done;
+                    } else {
+                        __nanosleep(200);
+                        if (++tries > (1u << 24)) __trap();          // the pull never came: fail the launch instead of hanging
+                    }
+                }
+            }
             for (int ub = 0; ub < p.units_per_tile; ++ub, ++uc) {
                 const int u = (int)(uc % (uint32_t)p.n_units);
                 if (lane == 0 && gw == 0) TRL(6, uc, 0);
@@ -1447,8 +1492,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                 const int n_chunks = L.n_chunks, stack = L.stack;
                 const uint32_t idesc_n = tc::idesc_bf16_f32(BM, L.N_pad);
                 const uint32_t idesc_2n = tc::idesc_bf16_f32(BM, 2 * L.N_pad);
-                const uint32_t d_tmem = tmem_base + ((lc & 1) ? 128u : 0u);
-                const uint32_t lbo_b = (uint32_t)L.N_pad * 32u;          // k-core slab = hi rows + lo rows
+                const uint32_t d_tmem = tmem_base + (((lc & 1) && !p.wide) ? 128u : 0u);
+                const uint32_t lbo_b = (uint32_t)L.N_pad * (BF16 ? 16u : 32u);   // k-core slab = hi rows + lo rows (bf16 mode: hi rows only)
                 const uint32_t lo_off = (uint32_t)L.N_pad;               // (N_pad * 16 bytes) >> 4: hi -> lo rows of a slab
                 const uint32_t kk_step = (2u * lbo_b) >> 4;              // two slabs per MMA
                 ChunkCursor c(L.F_pad);
@@ -1463,10 +1508,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                         const int nkk = c.nk() >> 1;
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk) {
-                            if (kk < nkk) {
+                            if (kk < nkk && !KAGNN_TC2_NOMMA) {
                                 const uint64_t dbh = d0 + (uint64_t)(kk * kk_step);
                                 const uint32_t acc = (q | kk) != 0 ? 1u : 0u;
-                                if (stack) {
+                                if (BF16) {
+                                    tc::umma_bf16_ts(d_tmem, a_hi + 8u * kk, dbh, idesc_n, acc);
+                                } else if (stack) {
                                     tc::umma_bf16_ts(d_tmem, a_hi + 8u * kk, dbh, idesc_2n, acc);
                                     tc::umma_bf16_ts(d_tmem, a_lo + 8u * kk, dbh, idesc_n, 1u);
                                 } else {
@@ -1522,9 +1569,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                         TRC(3, cq, 0);
                         tc::mbar_wait_relaxed(&empty[s], par);
                         TRC(3, cq, 1);
-                        const uint32_t bytes = c.b_bytes(L.N_pad) / KAGNN_TC2_WDIV;   // WDIV > 1: development probe (results are wrong)
-                        tc::mbar_arrive_expect_tx(&full[s], bytes);
-                        tc::bulk_g2s(bst + (size_t)s * p.bstage_bytes, L.wtc + c.b_off(L.N_pad), bytes, &full[s]);
+                        if (BF16) {
+                            // hi rows only: one bulk copy per k-core slab (the packed layout interleaves hi and lo rows), dense in the stage
+                            const uint32_t slab = 16u * (uint32_t)L.N_pad;
+                            const int nk = c.nk();
+                            tc::mbar_arrive_expect_tx(&full[s], slab * (uint32_t)nk);
+                            for (int i = 0; i < nk; ++i)
+                                tc::bulk_g2s(bst + (size_t)s * p.bstage_bytes + (size_t)i * slab, L.wtc + c.b_off(L.N_pad) + (size_t)i * 2u * slab, slab,
+                                             &full[s]);
+                        } else {
+                            const uint32_t bytes = c.b_bytes(L.N_pad) / KAGNN_TC2_WDIV;   // WDIV > 1: development probe (results are wrong)
+                            tc::mbar_arrive_expect_tx(&full[s], bytes);
+                            tc::bulk_g2s(bst + (size_t)s * p.bstage_bytes, L.wtc + c.b_off(L.N_pad), bytes, &full[s]);
+                        }
                         if (++s == p.ns) { s = 0; par ^= 1u; }
                     }
                 }
@@ -1542,7 +1599,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
 // written straight to agg_out.  HBM-bound: 16 independent 128-bit row loads in flight per warp, grid = all row groups.
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int AGG_WARPS = 8;
-__global__ void __launch_bounds__(AGG_WARPS * 32) aggregate_only_kernel(const __grid_constant__ Tc2Params p) {
+// Occupancy of the aggregation-only kernel: its limiter on a graph that does not fit L2 (R-MAT 10 M nodes) is memory-level
+// parallelism, and skewed degrees leave warps of a block idle behind its heaviest one, so more resident blocks with fewer loads
+// each win (measured on the 10 M-node / 100 M-edge R-MAT KAGCN layer: 11.5 ms at 3 blocks x 8 loads -> 10.0 ms at 5 x 4).
+#ifndef KAGNN_AGG_MINB
+#define KAGNN_AGG_MINB 5
+#endif
+#ifndef KAGNN_AGG_U
+#define KAGNN_AGG_U 4
+#endif
+__global__ void __launch_bounds__(AGG_WARPS * 32, KAGNN_AGG_MINB) aggregate_only_kernel(const __grid_constant__ Tc2Params p) {
     __shared__ HubScratch hub;
     const int lane = threadIdx.x & 31, gw = threadIdx.x >> 5;
     const int F = p.agg.num_cols;
@@ -1551,8 +1617,8 @@ __global__ void __launch_bounds__(AGG_WARPS * 32) aggregate_only_kernel(const __
         for (int c0 = 0; c0 < F; c0 += 128) {
             float* out = p.agg_out + row0 * p.ld_agg_out + c0;
             const int ucols = min(128, F - c0);
-            if (p.agg.mode == KAGNN_AGG_WEIGHTED) gather_unit_fast<true, true>(p, row0, c0, ucols, out, gw, lane, &hub);
-            else gather_unit_fast<false, true>(p, row0, c0, ucols, out, gw, lane, &hub);
+            if (p.agg.mode == KAGNN_AGG_WEIGHTED) gather_unit_fast<true, true, KAGNN_AGG_U>(p, row0, c0, ucols, out, gw, lane, &hub);
+            else gather_unit_fast<false, true, KAGNN_AGG_U>(p, row0, c0, ucols, out, gw, lane, &hub);
         }
     }
 }
@@ -1620,6 +1686,7 @@ int kagnn_fused_fwd_tc2(const KagnnAggregate* agg, int64_t num_rows, const Kagnn
 
     const bool rbf = layers[0].basis == KAGNN_BASIS_RBF;
     const int k = rbf ? 0 : layers[0].spline_order;
+    const bool bf16 = kagnn_get_precision() == KAGNN_PREC_BF16;
     int width = agg->num_cols, n_max = 0;
     for (int l = 0; l < n_layers; ++l) {
         const KagnnKanLayer& s = layers[l];
@@ -1632,14 +1699,16 @@ int kagnn_fused_fwd_tc2(const KagnnAggregate* agg, int64_t num_rows, const Kagnn
             if (s.spline_order != k || k < 1 || k > 3 || s.grid_size < 1 || s.grid_size + k > 8) return KAGNN_EUNSUPPORTED;
             if (!(s.h > 0.f)) return KAGNN_EINVAL;
         }
-        if (s.out_features <= 0 || s.out_features > 128) return KAGNN_EUNSUPPORTED;
+        // up to 128 outputs per layer in a chain (two accumulator regions of 128 columns ping-pong between chained layers);
+        // a single layer may be up to 256 wide (one region of 256 columns, epilogue not overlapped with the next tile)
+        if (s.out_features <= 0 || s.out_features > (n_layers == 1 ? 256 : 128)) return KAGNN_EUNSUPPORTED;
         if (!aligned16(s.packed_w_tc)) return KAGNN_EALIGN;
         d.F = s.in_features;
         d.F_pad = ceil16(s.in_features);
         d.N = s.out_features;
         d.N_pad = ceil16(s.out_features);
         d.n_chunks = d.F_pad / 8 + (d.F_pad + 63) / 64;
-        d.stack = d.N_pad <= 64 ? 1 : 0;
+        d.stack = (d.N_pad <= 64 && !bf16) ? 1 : 0;
         if (rbf) {
             d.rc0 = s.t0;
             d.rstep = s.h;
@@ -1676,36 +1745,52 @@ int kagnn_fused_fwd_tc2(const KagnnAggregate* agg, int64_t num_rows, const Kagnn
            num_rows < (1LL << 30) && (!agg->peer_x || agg->rows_per_rank * (int64_t)agg->num_ranks < (1LL << 30)) &&
            (!agg->x_halo || agg->num_local_src < (1LL << 29)) &&
            !(rbf && layers[0].ln_weight && F_pad0 > 64);          // in-kernel LayerNorm statistics need the row in ONE unit
-    p.uw = (F_pad0 > 64 && !p.ag) ? 128 : 64;
+    p.wide = n_max > 128;
+    p.bf16 = bf16 ? 1 : 0;
+    p.bstage_bytes = 256 * n_max;
+    // LUTs | mbarriers (x ring full/empty, stage full/empty, 2 accumulator) | tmem slot (16 B) | post scale/shift | progress word
+    const int tail = KAGNN_MAX_LAYERS * LUT_ROWS * 16 + (2 * MAX_UNITS + 2 * MAX_STAGE + 2) * 8 + 16 + 2 * 128 * 4 + 16 + (int)sizeof(HubScratch) + 2 * NWG * 128 * 8 + 2 * 128 * 4 +
+                     (p.ag ? AG_BYTES : 0);
+    // x-ring geometry: units of 128 or 64 columns.  128 (one unit per tile up to 128 inputs) is the default; 64-column units are
+    // forced by the asynchronous gather and by wide layers (64 KB W stages), and preferred for plain row tiles (no gather) when
+    // they buy a deeper W / A stage ring.  Ring depths: at least 2 units and 2 stages; deeper stages first, then more units.
+    int best_units = 0, best_ns = 0, best_uw = 0;
+    for (int uw = 128; uw >= 64; uw >>= 1) {
+        if (uw == 128 && (F_pad0 <= 64 || p.ag || p.wide)) continue;
+        if (uw == 64 && best_units != 0 && !(agg->mode == KAGNN_AGG_NONE && !pre && !agg->src_index)) break;
+        // in-kernel LayerNorm statistics need the whole input row in ONE unit
+        if (uw == 64 && best_units != 0 && rbf && layers[0].ln_weight && !p.layers[0].ln_stats) break;
+        const int unit_bytes_c = BM * (uw + 4) * (int)sizeof(float);
+        for (int nu = 2; nu <= MAX_UNITS; ++nu) {
+            const int left = (int)props.max_smem - tail - nu * unit_bytes_c;
+            int ns = left / p.bstage_bytes;
+            if (ns > MAX_STAGE) ns = MAX_STAGE;
+            if (ns < 2) break;
+            if (best_units == 0 || ns > best_ns || (ns == best_ns && uw == best_uw)) { best_units = nu; best_ns = ns; best_uw = uw; }
+            else break;
+        }
+    }
+    if (best_units == 0) return KAGNN_EUNSUPPORTED;
+    p.uw = best_uw;
     p.uw_shift = p.uw == 128 ? 7 : 6;
     p.xld = p.uw + 4;                                   // (xld / 4) odd: conflict-free float4 reads with thread = row
     p.unit_floats = BM * p.xld;
     p.units_per_tile = (F_pad0 + p.uw - 1) / p.uw;
-    p.bstage_bytes = 256 * n_max;
-    // LUTs | mbarriers (x ring full/empty, stage full/empty, 2 accumulator) | tmem slot (16 B) | post scale/shift | progress word
-    const int tail = KAGNN_MAX_LAYERS * LUT_ROWS * 16 + (2 * MAX_UNITS + 2 * MAX_STAGE + 2) * 8 + 16 + 2 * 128 * 4 + 16 + (int)sizeof(HubScratch) + 2 * NWG * 128 * 8 +
-                     (p.ag ? AG_BYTES : 0);
     const int unit_bytes = p.unit_floats * (int)sizeof(float);
-    // ring depths: at least 2 x-units and 2 stages; prefer deeper stages, then more units
-    int best_units = 0, best_ns = 0;
-    for (int nu = 2; nu <= MAX_UNITS; ++nu) {
-        const int left = (int)props.max_smem - tail - nu * unit_bytes;
-        int ns = left / p.bstage_bytes;
-        if (ns > MAX_STAGE) ns = MAX_STAGE;
-        if (ns < 2) break;
-        if (best_units == 0 || ns >= best_ns) { best_units = nu; best_ns = ns; }
-        else break;
-    }
-    if (best_units == 0) return KAGNN_EUNSUPPORTED;
     p.n_units = best_units;
     p.ns = best_ns;
     const size_t smem = (size_t)p.n_units * unit_bytes + (size_t)p.ns * p.bstage_bytes + tail;
 
     // in-kernel LayerNorm statistics need the whole input row in one x unit; wider rows need the pre-pass (ln_stats)
     if (rbf && p.units_per_tile != 1 && p.layers[0].lnw && !p.layers[0].ln_stats) return KAGNN_EUNSUPPORTED;
-    void (*kern)(Tc2Params) = k == 3 ? fused_tc2_kernel<3> : (k == 2 ? fused_tc2_kernel<2> : (k == 1 ? fused_tc2_kernel<1> : fused_tc2_kernel<0>));
+    void (*kern)(Tc2Params);
+    if (bf16) kern = k == 3 ? fused_tc2_kernel<3, true> : (k == 2 ? fused_tc2_kernel<2, true> : (k == 1 ? fused_tc2_kernel<1, true> : fused_tc2_kernel<0, true>));
+    else kern = k == 3 ? fused_tc2_kernel<3, false> : (k == 2 ? fused_tc2_kernel<2, false> : (k == 1 ? fused_tc2_kernel<1, false> : fused_tc2_kernel<0, false>));
     KAGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)props.max_smem));
-    const int grid = p.n_tiles < props.num_sms ? p.n_tiles : props.num_sms;
+    if (agg->halo_flags && (!agg->x_halo || !agg->halo_need)) return KAGNN_EINVAL;
+    int sms = props.num_sms - (agg->reserve_sms > 0 ? agg->reserve_sms : 0);
+    if (sms < 1) sms = 1;
+    const int grid = p.n_tiles < sms ? p.n_tiles : sms;
     kern<<<(unsigned)grid, NTHREADS, smem, stream>>>(p);
     KAGNN_LAUNCH_CHECK();
     return KAGNN_OK;

@@ -130,6 +130,49 @@ __global__ void gather_rows_peer_kernel(const float* const* __restrict__ peer_x,
         *reinterpret_cast<float4*>(dst + c) = __ldg(reinterpret_cast<const float4*>(src + c));
 }
 
+// The same pull as a persistent kernel that publishes its progress: rows are copied in the given order, 256 at a time per block
+// (block b: chunks b, b + gridDim.x, ...), and a finished chunk stores `epoch` into its flag with release semantics.  The fused
+// layer that runs concurrently (fused_tc2.cu, KagnnAggregate.halo_flags) waits on the flags of the prefix its tile needs.
+constexpr int kHaloChunk = 256;
+__global__ void __launch_bounds__(256) gather_rows_peer_ordered_kernel(const float* const* __restrict__ peer_x, int64_t ldx,
+                                                                       int64_t rows_per_rank, const int32_t* __restrict__ ids,
+                                                                       int64_t rows, int cols, float* __restrict__ out, int64_t ld_out,
+                                                                       int32_t* __restrict__ flags, int32_t epoch) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t n_chunks = (rows + kHaloChunk - 1) / kHaloChunk;
+    for (int64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        const int64_t r0 = c * kHaloChunk;
+        // warp w copies rows r0 + w, r0 + w + 8, ...: four rows in flight per warp (each lane 16 bytes per 128 columns)
+        for (int64_t rb = r0 + warp; rb < min(rows, r0 + (int64_t)kHaloChunk); rb += 32) {
+            const float* src[4];
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t r = rb + 8 * u;
+                src[u] = nullptr;
+                if (r < min(rows, r0 + (int64_t)kHaloChunk)) {
+                    const int32_t gid = ids[r];
+                    const int owner = (int)(gid / rows_per_rank);
+                    src[u] = peer_x[owner] + (gid - owner * rows_per_rank) * ldx;
+                }
+            }
+            for (int cc = lane * 4; cc < cols; cc += 128) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (src[u]) v[u] = __ldg(reinterpret_cast<const float4*>(src[u] + cc));
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (src[u]) *reinterpret_cast<float4*>(out + (rb + 8 * u) * ld_out + cc) = v[u];
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flags + c), "r"(epoch) : "memory");
+        }
+    }
+}
+
 inline int bits_for(int64_t n) {
     int b = 1;
     while (b < 31 && ((int64_t)1 << b) < n) ++b;
@@ -264,6 +307,22 @@ extern "C" int kagnn_gather_rows_peer(const float* const* peer_x, int64_t ldx, i
     const int64_t seg = ceil_div64(rows, nseg);
     unsigned blocks = (unsigned)ceil_div64(seg * nseg * 32, kThreads);
     gather_rows_peer_kernel<<<blocks, kThreads, 0, stream>>>(peer_x, ldx, rows_per_rank, ids, rows, cols, out, ld_out, nseg);
+    KAGNN_LAUNCH_CHECK();
+    return KAGNN_OK;
+}
+
+extern "C" int kagnn_gather_rows_peer_ordered(const float* const* peer_x, int64_t ldx, int64_t rows_per_rank, const int32_t* ids,
+                                              int64_t rows, int32_t cols, float* out, int64_t ld_out, int32_t* chunk_flags,
+                                              int32_t epoch, int32_t num_ctas, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (rows < 0 || cols < 0 || rows_per_rank <= 0 || num_ctas <= 0 || (rows > 0 && (!peer_x || !ids || !out || !chunk_flags)))
+        return KAGNN_EINVAL;
+    if (rows == 0 || cols == 0) return KAGNN_OK;
+    if (!aligned16(out) || (ldx % 4) || (ld_out % 4) || (cols % 4)) return KAGNN_EALIGN;
+    const int64_t n_chunks = ceil_div64(rows, kHaloChunk);
+    const unsigned blocks = (unsigned)(n_chunks < num_ctas ? n_chunks : num_ctas);
+    gather_rows_peer_ordered_kernel<<<blocks, 256, 0, stream>>>(peer_x, ldx, rows_per_rank, ids, rows, cols, out, ld_out, chunk_flags,
+                                                                epoch);
     KAGNN_LAUNCH_CHECK();
     return KAGNN_OK;
 }

@@ -64,6 +64,35 @@ def relabel_edges(edge_index: Tensor, rank: int, world: int, n_local: int):
     return torch.stack([src_local, dst - lo]), halo_global, recv_counts
 
 
+def relabel_edges_first_use(edge_index: Tensor, rank: int, world: int, n_local: int, tile: int = 128):
+    """Halo numbering for the OVERLAPPED pull (mode "pull"): the distinct remote sources are numbered in the order in which the
+    128-row destination tiles first use them, so that a pull which copies halo rows 0, 1, 2, ... delivers what tile t needs before
+    what tile t + 1 needs.  Returns (edge_index_local, halo_global, need): ``need[t]`` = number of leading halo rows referenced by
+    tiles 0..t (int32, one entry per tile).  Index arithmetic only, no communication; one host synchronisation (the halo count)."""
+    src, dst = edge_index[0], edge_index[1]
+    lo = rank * n_local
+    dev = edge_index.device
+    n_tiles = (n_local + tile - 1) // tile
+    remote = (src < lo) | (src >= lo + n_local)
+    rs = src[remote]
+    rt = torch.div(dst[remote] - lo, tile, rounding_mode="floor")
+    if rs.numel() == 0:
+        return (torch.stack([src - lo, dst - lo]), torch.zeros(0, dtype=torch.int64, device=dev),
+                torch.zeros(n_tiles, dtype=torch.int32, device=dev))
+    key = torch.sort(rs * n_tiles + rt).values                       # by source id, then by tile: first entry of a source = first use
+    ks = torch.div(key, n_tiles, rounding_mode="floor")
+    uniq, counts = torch.unique_consecutive(ks, return_counts=True)
+    first_tile = key[torch.cumsum(counts, 0) - counts] - uniq * n_tiles
+    order = torch.argsort(first_tile * (world * n_local) + uniq)     # first-use tile, then id
+    halo_global = uniq[order]
+    pos_of_uniq = torch.empty_like(order)
+    pos_of_uniq[order] = torch.arange(order.numel(), device=dev)
+    need = torch.searchsorted(first_tile[order].contiguous(), torch.arange(n_tiles, device=dev), right=True).to(torch.int32)
+    pos = pos_of_uniq[torch.searchsorted(uniq, src.contiguous()).clamp(max=uniq.numel() - 1)]
+    src_local = torch.where(remote, pos + n_local, src - lo)
+    return torch.stack([src_local, dst - lo]), halo_global, need
+
+
 def build_halo_plan(edge_index: Tensor, rank: int, world: int, n_local: int, group=None, build_csr: bool = True) -> HaloPlan:
     """Collective: every rank of ``group`` must call it with its own target-sharded ``edge_index`` (global ids)."""
     ei_local, halo_global, recv_counts = relabel_edges(edge_index, rank, world, n_local)
@@ -154,6 +183,10 @@ class ShardedNodeModel:
             raise ValueError("mode must be 'halo', 'peer', 'pull' or 'auto'")
         self.model, self.rank, self.world, self.n_local, self.group = model, rank, world, n_local, group
         self._symm = {}
+        self._side = {}
+        # overlapped pull: SMs left to the pull kernel and its persistent blocks (4 per reserved SM keep ~1 MB of loads in flight)
+        self.pull_sms = 12
+        self.pull_ctas = 48
         if mode == "auto" and self.peer_supported() and not self._probe_symmetric_memory():
             mode = "halo"                                   # NVLink peer memory not available here: NCCL transport
         if mode == "auto":
@@ -162,8 +195,9 @@ class ShardedNodeModel:
             # on 8 ranks the in-kernel gather measured 2.20 ms/step (NCCL halo 2.90) and is the measured choice there
             mode = ("peer" if world >= 8 else "pull") if self.peer_supported() else "halo"
         elif mode in ("peer", "pull") and not self.peer_supported():
-            raise NotImplementedError("mode='peer' needs a GIN-flavour GKAN_Nodes with skip=True, spline_order <= 3, G + k <= 8, "
-                                      "widths <= 128 and feature widths that are multiples of 4")
+            raise NotImplementedError("modes 'peer' / 'pull' need a GIN-flavour GKAN_Nodes / GFASTKAN_Nodes with skip=True, "
+                                      "spline_order <= 3, G + k <= 8 (FastKAN: <= 8 centres), widths <= 128 and feature widths that "
+                                      "are multiples of 4; GCN flavours and skip=False use mode='halo'")
         self.mode = mode
 
     def _probe_symmetric_memory(self) -> bool:
@@ -187,15 +221,23 @@ class ShardedNodeModel:
     def peer_supported(self) -> bool:
         from .conv import GINConv, GINEConv
         from .ekan import KAN
+        from .fastkan import FastKAN
         m = self.model
         if not (getattr(m, "skip", False) and len(m.convs) and all(isinstance(c, GINConv) and not isinstance(c, GINEConv) for c in m.convs)):
             return False
         for c in m.convs:
-            if not isinstance(c.nn, KAN):
+            if isinstance(c.nn, KAN):
+                for lay in c.nn.layers:
+                    if lay.spline_order > 3 or lay.grid_size + lay.spline_order > 8 or lay.out_features > 128 or lay.in_features % 4:
+                        return False
+            elif isinstance(c.nn, FastKAN):
+                # what the pipelined kernel runs for RBF chains: <= 8 centres, widths <= 128 (LayerNorm statistics of the gathered
+                # row are taken in the kernel, which needs the row in one 128-column unit)
+                for lay in c.nn.layers:
+                    if lay.rbf.num_grids > 8 or lay.output_dim > 128 or lay.input_dim > 128 or lay.input_dim % 4:
+                        return False
+            else:
                 return False
-            for lay in c.nn.layers:
-                if lay.spline_order > 3 or lay.grid_size + lay.spline_order > 8 or lay.out_features > 128 or lay.in_features % 4:
-                    return False
         try:
             import torch.distributed._symmetric_memory  # noqa: F401
         except Exception:
@@ -204,12 +246,16 @@ class ShardedNodeModel:
 
     def prepare(self, edge_index_global: Tensor):
         if self.mode == "pull":
-            # local index arithmetic only (no communication): distinct remote sources -> halo numbering
-            ei_local, halo_global, _ = relabel_edges(edge_index_global, self.rank, self.world, self.n_local)
+            # local index arithmetic only (no communication): distinct remote sources -> halo numbering in first-use order
+            ei_local, halo_global, need = relabel_edges_first_use(edge_index_global, self.rank, self.world, self.n_local)
             n_halo = int(halo_global.numel())
             plan = PeerPlan(GraphCSR(ei_local, self.n_local, self.n_local + n_halo), self.n_local, self.world)
             plan.halo_ids = halo_global.to(torch.int32)
             plan.n_halo = n_halo
+            plan.need = need
+            plan.flags = torch.zeros(max(1, (n_halo + ops.HALO_CHUNK - 1) // ops.HALO_CHUNK), dtype=torch.int32, device=need.device)
+            plan.epoch = 0
+            plan.halo_buf = {}
             return plan
         if self.mode == "peer":
             lo = self.rank * self.n_local
@@ -220,6 +266,11 @@ class ShardedNodeModel:
         plan = build_halo_plan(edge_index_global, self.rank, self.world, self.n_local, self.group)
         plan.exchange = HaloExchange(plan, self.group)
         return plan
+
+    def _side_stream(self, dev):
+        if dev.index not in self._side:
+            self._side[dev.index] = torch.cuda.Stream(device=dev)
+        return self._side[dev.index]
 
     def _symm_buffer(self, n: int, width: int, dev):
         """Skip-concat buffer in symmetric memory + one device table of peer base pointers per column offset (cached)."""
@@ -258,9 +309,23 @@ class ShardedNodeModel:
             hdl.barrier()                                 # the slice read below is complete on every rank
             dst = buf[:, f + l * hid: f + (l + 1) * hid]
             if self.mode == "pull":
-                # the distinct remote rows, copied once from their owners by a pull kernel, then the ordinary halo layer
-                halo = ops.gather_rows_peer(table(col), buf.stride(0), self.n_local, plan.halo_ids, cur.size(1))
-                conv(cur, plan.graph, out=dst, post=m._folds[l].get(bn), x_halo=halo)
+                # the distinct remote rows, pulled from their owners WHILE the layer runs: the pull kernel (side stream, a few SMs)
+                # copies them in first-use order and raises one flag per 256 rows; the gather warps of the fused kernel wait for the
+                # prefix their tile needs (KagnnAggregate.halo_flags), so NVLink time hides behind the tensor-core pipeline
+                width = cur.size(1)
+                if width not in plan.halo_buf:
+                    plan.halo_buf[width] = torch.empty(max(plan.n_halo, 1), width, dtype=torch.float32, device=x.device)
+                halo = plan.halo_buf[width]
+                plan.epoch += 1
+                main = torch.cuda.current_stream()
+                side = self._side_stream(x.device)
+                side.wait_stream(main)                     # the barrier above and the previous layer
+                with torch.cuda.stream(side):
+                    ops.gather_rows_peer_ordered(table(col), buf.stride(0), self.n_local, plan.halo_ids, width, halo, plan.flags,
+                                                 plan.epoch, self.pull_ctas)
+                conv(cur, plan.graph, out=dst, post=m._folds[l].get(bn), x_halo=halo, halo_need=plan.need, halo_flags=plan.flags,
+                     halo_epoch=plan.epoch, reserve_sms=self.pull_sms)
+                main.wait_stream(side)
             else:
                 conv(cur, plan.graph, out=dst, post=m._folds[l].get(bn), peer_x=table(col), rows_per_rank=self.n_local)
             col = f + l * hid

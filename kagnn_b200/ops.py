@@ -307,6 +307,28 @@ def gather_rows_peer(peer_x: Tensor, ldx: int, rows_per_rank: int, ids: Tensor, 
     return out
 
 
+HALO_CHUNK = 256          # rows per progress flag of gather_rows_peer_ordered (kHaloChunk in csrc/graph.cu)
+
+
+@_on_device
+def gather_rows_peer_ordered(peer_x: Tensor, ldx: int, rows_per_rank: int, ids: Tensor, num_cols: int, out: Tensor, flags: Tensor,
+                             epoch: int, num_ctas: int) -> Tensor:
+    """The pull of gather_rows_peer as a persistent kernel on the CURRENT stream that publishes per-chunk progress flags
+    (kagnn_gather_rows_peer_ordered); meant to run on a side stream next to the fused layer that reads ``out`` as x_halo."""
+    global launch_count
+    _need_cuda(peer_x, "peer_x", torch.int64)
+    _need_cuda(ids, "ids", torch.int32)
+    _need_cuda(flags, "flags", torch.int32)
+    if flags.numel() * HALO_CHUNK < ids.numel():
+        raise ValueError("one flag per 256 halo rows")
+    if ids.numel() == 0:
+        return out
+    L.check(L.lib().kagnn_gather_rows_peer_ordered(_p(peer_x), ldx, rows_per_rank, _p(ids), ids.numel(), num_cols, _p(out), _rows(out, "out"),
+                                                   _p(flags), int(epoch), int(num_ctas), _stream()), "gather_rows_peer_ordered")
+    launch_count += 1
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------
 # weights
 # ---------------------------------------------------------------------------------------------------
@@ -355,9 +377,22 @@ def set_path(mode: int) -> None:
     L.check(L.lib().kagnn_set_path(mode), "set_path")
 
 
+def set_precision(mode) -> None:
+    """``"fp32"`` (default: bf16 hi/lo split, three products per K step, matches the reference's fp32 forward within 1e-4) or
+    ``"bf16"`` (one bf16 product per K step, fp32 accumulate: BASELINE config C5) -- see kagnn_set_precision."""
+    code = {"fp32": L.PREC_FP32, "bf16": L.PREC_BF16}.get(mode, mode)
+    L.check(L.lib().kagnn_set_precision(int(code)), "set_precision")
+
+
+def get_precision() -> str:
+    return "bf16" if L.lib().kagnn_get_precision() == L.PREC_BF16 else "fp32"
+
+
 def set_tc_variant(variant: int) -> None:
     """0 = pipelined tcgen05 kernel first (default), 1 = only the shared-memory-A tcgen05 kernel."""
+    global _tc_variant
     L.check(L.lib().kagnn_set_tc_variant(variant), "set_tc_variant")
+    _tc_variant = variant
 
 
 def launch_counters():
@@ -432,6 +467,10 @@ class AggSpec:
     peer_x: Optional[Tensor] = None       # node-sharded graphs, in-kernel NVLink gather: (world,) int64 peer base pointers
     rows_per_rank: int = 0
     x_head: Optional[Tensor] = None       # AGG_NONE two-part rows: logical row = [x_head[r] | x[r]] (skip concat without the copy)
+    halo_need: Optional[Tensor] = None    # x_halo filled while the layer runs (gather_rows_peer_ordered): per tile, halo rows needed so far
+    halo_flags: Optional[Tensor] = None   # ... per chunk of 256 halo rows: == halo_epoch once the chunk has landed
+    halo_epoch: int = 0
+    reserve_sms: int = 0
     _anchors = ("x", "rowptr", "x_head", "x_halo", "edge_feat")
 
     def __post_init__(self) -> None:
@@ -474,6 +513,13 @@ class AggSpec:
             s.ld_halo = _rows(self.x_halo, "x_halo")
             s.x_halo = _addr(self.x_halo)
             s.num_local_src = self.x.size(0)
+        if self.halo_flags is not None:
+            if self.x_halo is None or self.halo_need is None:
+                raise ValueError("halo_flags needs x_halo and halo_need")
+            _need_cuda(self.halo_flags, "halo_flags", torch.int32)
+            _need_cuda(self.halo_need, "halo_need", torch.int32)
+            s.halo_flags, s.halo_need = _addr(self.halo_flags), _addr(self.halo_need)
+            s.halo_epoch, s.reserve_sms = int(self.halo_epoch), int(self.reserve_sms)
         if self.peer_x is not None:
             _need_cuda(self.peer_x, "peer_x", torch.int64)
             if self.rows_per_rank <= 0:
@@ -525,11 +571,15 @@ def fused_layer(agg: AggSpec, num_rows: int, layers: Sequence[KanLayerSpec], pre
         agg_out = torch.empty(num_rows, agg.x.size(1), dtype=torch.float32, device=dev)
     if num_rows == 0:
         return out if layers else agg_out
+    if len(layers) > 1 and any(sp.out_features > 128 for sp in layers) and all(sp.packed_w_tc is not None for sp in layers) \
+            and _tc_variant_is_pipelined():
+        return _wide_chain(agg, num_rows, layers, pre, post, agg_out, out)
+    wide_single = len(layers) == 1 and layers[0].out_features > 128
     if (layers and layers[0].basis == L.BASIS_RBF and layers[0].ln_weight is not None and layers[0].ln_stats is None
             and agg.mode == L.AGG_NONE and pre is None and agg.src_index is None and layers[0].packed_w_tc is not None
-            and layers[0].in_features > 128 and all(sp.out_features <= 128 for sp in layers)):
-        # FastKAN over rows wider than one tile unit (the skip-concat read-out): LayerNorm statistics by a small pre-pass so
-        # that the pipelined kernel can stream the row unit by unit
+            and layers[0].in_features > (64 if wide_single else 128) and (wide_single or all(sp.out_features <= 128 for sp in layers))):
+        # FastKAN over rows wider than one tile unit (the skip-concat read-out; every input of a wide layer, whose units are 64
+        # columns): LayerNorm statistics by a small pre-pass so that the pipelined kernel can stream the row unit by unit
         stats = layernorm_stats(agg.x, agg.x_head)
         layers = [dataclasses.replace(layers[0], ln_stats=stats)] + list(layers[1:])
     code = _launch_fused(agg, num_rows, layers, pre, post, agg_out, out)
@@ -550,6 +600,37 @@ def fused_layer(agg: AggSpec, num_rows: int, layers: Sequence[KanLayerSpec], pre
         launch_count += 1
     L.check(code, "fused_layer")
     return out if layers else agg_out
+
+
+_tc_variant = 0
+
+
+def _tc_variant_is_pipelined() -> bool:
+    return _tc_variant == 0
+
+
+def _wide_chain(agg: AggSpec, num_rows: int, layers, pre, post, agg_out, out):
+    """KAN / FastKAN chains with a layer wider than 128 outputs (BASELINE config C5: hidden 256).  The pipelined kernel keeps
+    chained activations in tensor memory, which holds two 128-column accumulators or ONE of 256: such a chain runs as one launch
+    per layer with the (rows x width) activations passing through HBM in between -- a few tens of MB against hundreds of GFLOP.
+    An aggregation in front of a layer that needs whole-row LayerNorm statistics (FastKAN, inputs wider than one 64-column tile
+    unit) becomes its own launch too, so that the statistics pre-pass sees the aggregated rows."""
+    dev = agg.x.device
+    first = layers[0]
+    needs_stats = first.basis == L.BASIS_RBF and first.ln_weight is not None and first.in_features > 64
+    cur_agg, cur_pre = agg, pre
+    if needs_stats and (agg.mode != L.AGG_NONE or pre is not None or agg.src_index is not None or agg.x_head is not None):
+        tmp = agg_out if agg_out is not None else torch.empty(num_rows, first.in_features, dtype=torch.float32, device=dev)
+        fused_layer(agg, num_rows, [], pre=pre, agg_out=tmp)
+        cur_agg, cur_pre, agg_out = AggSpec(L.AGG_NONE, tmp), None, None
+    x = None
+    for i, sp in enumerate(layers):
+        last = i == len(layers) - 1
+        a = cur_agg if i == 0 else AggSpec(L.AGG_NONE, x)
+        y = out if last else torch.empty(num_rows, sp.out_features, dtype=torch.float32, device=dev)
+        x = fused_layer(a, num_rows, [sp], pre=cur_pre if i == 0 else None, post=post if last else None,
+                        agg_out=agg_out if i == 0 else None, out=y)
+    return x
 
 
 @_on_device

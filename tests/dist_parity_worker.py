@@ -48,6 +48,8 @@ def main():
         sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
         m = m.to(dev)
         runner = kd.ShardedNodeModel(m, rank, world, n_local)
+        auto = kd.ShardedNodeModel(m, rank, world, n_local, mode="auto")
+        assert auto.mode in (("peer", "pull", "halo") if conv_type == "gin" else ("halo",)), (conv_type, fast, auto.mode)
         plan = runner.prepare(ei[:, mine].to(dev))
         y_local = runner.forward(x[rank * n_local:(rank + 1) * n_local].to(dev), plan)
         ys = [torch.empty_like(y_local) for _ in range(world)]
@@ -66,8 +68,9 @@ def main():
                   f"halo rows {plan.n_halo}", flush=True)
         assert e1 <= 1e-5, (conv_type, fast, e1)     # same kernels, same reduction order per row
         assert e2 <= 1e-4, (conv_type, fast, e2)
-        if conv_type == "gin" and not fast:
-            # in-kernel NVLink gather (KagnnAggregate.peer_x): same numbers without pack / all-to-all / halo matrix
+        if conv_type == "gin":
+            # in-kernel NVLink gather (KagnnAggregate.peer_x) and the overlapped pull: same numbers without pack / all-to-all
+            # (B-spline and FastKAN flavours; GCN flavours stay on the NCCL halo transport, which `auto` picks for them)
             for pmode in ("peer", "pull"):
                 peer = kd.ShardedNodeModel(m, rank, world, n_local, mode=pmode)
                 pplan = peer.prepare(ei[:, mine].to(dev))
@@ -79,7 +82,7 @@ def main():
                 e3, e4 = K.rel_err(y_peer_all, y_single), K.rel_err(y_peer_all, y_ref)
                 worst = max(worst, e3, e4)
                 if rank == 0:
-                    print(f"kan/gin {pmode}: vs single {e3:.2e}, vs oracle {e4:.2e}", flush=True)
+                    print(f"{'fastkan' if fast else 'kan'}/gin {pmode}: vs single {e3:.2e}, vs oracle {e4:.2e}", flush=True)
                 assert e3 <= 1e-5 and e4 <= 1e-4, (pmode, e3, e4)
     if rank == 0:
         print(f"DIST_PARITY_OK world={world} worst={worst:.2e}", flush=True)

@@ -99,3 +99,48 @@ def test_gcn_layer_halo_matrix_single_gpu():
                               x_halo=h[halo_global].contiguous())
             ys.append(ops.fused_layer(agg, n_local, [], pre=ops.Affine(shift=conv.bias.detach())).cpu())
     assert K.rel_err(torch.cat(ys), ref) <= TOL
+
+
+@pytest.mark.parametrize("fast", [False, True])
+def test_overlapped_pull_with_progress_flags_single_gpu(fast):
+    """mode="pull" as the multi-GPU run executes it: halo rows numbered in first-use order, pulled by the persistent copy kernel
+    on a SECOND stream while the fused layer runs on a reduced grid and waits on the per-chunk flags (KagnnAggregate.halo_flags)."""
+    import kagnn_b200 as kb
+    from kagnn_b200 import dist as kd
+    from kagnn_b200 import ops
+    from kagnn_b200.graph import GraphCSR
+    torch.manual_seed(3)
+    world, n_local, f = 2, 20_000, 64
+    n, x, ei = _setup(world, n_local, f, 10 * world * n_local, seed=77)
+    conv = (kb.GIFASTKANLayer(f, 32, 5, 32, 2) if fast else kb.GIKANLayer(f, 32, 5, 3, 32, 2)).cuda()
+    dev = torch.device("cuda")
+    with torch.no_grad():
+        y_single = conv(x.to(dev), ei.to(dev)).cpu()
+    blocks = [x[r * n_local:(r + 1) * n_local].to(dev).clone() for r in range(world)]
+    table = torch.tensor([b.data_ptr() for b in blocks], dtype=torch.int64, device=dev)
+    side = torch.cuda.Stream()
+    ys = []
+    with torch.no_grad():
+        for r in range(world):
+            lo = r * n_local
+            mine = (ei[1] >= lo) & (ei[1] < lo + n_local)
+            ei_local, halo_global, need = kd.relabel_edges_first_use(ei[:, mine].to(dev), r, world, n_local)
+            n_halo = int(halo_global.numel())
+            assert n_halo > 10 * ops.HALO_CHUNK                       # several chunks, several tiles per chunk
+            g = GraphCSR(ei_local, n_local, n_local + n_halo)
+            flags = torch.zeros((n_halo + ops.HALO_CHUNK - 1) // ops.HALO_CHUNK, dtype=torch.int32, device=dev)
+            halo = torch.full((n_halo, f), float("nan"), device=dev)     # a row read before it landed would poison the result
+            for epoch in (1, 2):                                         # the flags are reused with a new epoch, never reset
+                halo.fill_(float("nan"))
+                main = torch.cuda.current_stream()
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    torch.cuda._sleep(2_000_000)                         # the pull starts ~1 ms late: the layer really has to wait
+                    ops.gather_rows_peer_ordered(table, blocks[r].stride(0), n_local, halo_global.to(torch.int32), f, halo, flags,
+                                                 epoch, 8)
+                y = conv(blocks[r], g, x_halo=halo, halo_need=need, halo_flags=flags, halo_epoch=epoch, reserve_sms=8)
+                main.wait_stream(side)
+            ys.append(y.cpu())
+    y = torch.cat(ys)
+    assert torch.isfinite(y).all()
+    assert K.rel_err(y, y_single) <= 2e-6
