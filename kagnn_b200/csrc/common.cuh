@@ -41,5 +41,10 @@ int kagnn_fused_fwd_tc2(const KagnnAggregate* agg, int64_t num_rows, const Kagnn
                         int64_t ldy, cudaStream_t stream);
 int kagnn_aggregate_only_tc2(const KagnnAggregate* agg, int64_t num_rows, const KagnnAffine* pre, float* agg_out,
                              int64_t ld_agg_out, cudaStream_t stream);
+// shared-memory-tiled B-spline backward (backward_tiled.cu); KAGNN_EUNSUPPORTED -> the general kernels of backward.cu
+int kagnn_kan_bwd_weights_tiled(const KagnnKanLayer* layer, const float* x, int64_t ldx, const float* dy, int64_t ld_dy, int64_t num_rows,
+                                float* d_packed, cudaStream_t stream);
+int kagnn_kan_bwd_input_tiled(const KagnnKanLayer* layer, const float* x, int64_t ldx, const float* dy, int64_t ld_dy, int64_t num_rows,
+                              float* dx, int64_t ld_dx, cudaStream_t stream);
 int kagnn_validate_fused_args(const KagnnAggregate* agg, int64_t num_rows, const float* agg_out, int64_t ld_agg_out,
                               int32_t n_layers, const KagnnKanLayer* layers, const float* y);

@@ -97,6 +97,9 @@ constexpr int FPW = 8 / WGT;                 // features per warpgroup per splin
 #ifndef KAGNN_TC2_NOMMA
 #define KAGNN_TC2_NOMMA 0                    // development probe: the MMA warp only commits (results are wrong)
 #endif
+#ifndef KAGNN_TC2_STACK4
+#define KAGNN_TC2_STACK4 1
+#endif
 #ifndef KAGNN_TC2_NOMATH
 #define KAGNN_TC2_NOMATH 0                   // development probe: producers skip the basis expansion (results are wrong)
 #endif
@@ -1427,7 +1430,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                 while (halo_done < nchunk) {
                     int v;
                     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p.agg.halo_flags + halo_done) : "memory");
-                    if (v == p.agg.halo_epoch) {
+                    if (v >= 32 * p.agg.halo_epoch) {            // all 32 warps of the pull block have stored their rows of this chunk
                         ++halo_done;
                     } else {
                         __nanosleep(200);
@@ -1514,8 +1517,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                                 if (BF16) {
                                     tc::umma_bf16_ts(d_tmem, a_hi + 8u * kk, dbh, idesc_n, acc);
                                 } else if (stack) {
+                                    // [W_hi | W_lo] is one B operand: A_hi gives hi.hi | hi.lo; A_lo gives lo.hi (and, with
+                                    // KAGNN_TC2_STACK4, lo.lo as well: the full product, relative error ~2^-24 instead of ~2^-17,
+                                    // for 128 instead of 96 tensor cycles per K step on layers whose tensor pipe is ~30 % busy)
                                     tc::umma_bf16_ts(d_tmem, a_hi + 8u * kk, dbh, idesc_2n, acc);
-                                    tc::umma_bf16_ts(d_tmem, a_lo + 8u * kk, dbh, idesc_n, 1u);
+                                    tc::umma_bf16_ts(d_tmem, a_lo + 8u * kk, dbh, KAGNN_TC2_STACK4 ? idesc_2n : idesc_n, 1u);
                                 } else {
                                     tc::umma_bf16_ts(d_tmem, a_hi + 8u * kk, dbh, idesc_n, acc);
                                     tc::umma_bf16_ts(d_tmem, a_hi + 8u * kk, dbh + lo_off, idesc_n, 1u);

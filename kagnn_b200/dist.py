@@ -19,6 +19,7 @@ exchange at all: every rank simply runs the ordinary model on its slice of the b
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Callable, List, Optional
 
@@ -185,8 +186,8 @@ class ShardedNodeModel:
         self._symm = {}
         self._side = {}
         # overlapped pull: SMs left to the pull kernel and its persistent blocks (4 per reserved SM keep ~1 MB of loads in flight)
-        self.pull_sms = 12
-        self.pull_ctas = 48
+        self.pull_sms = int(os.environ.get("KAGNN_PULL_SMS", "16"))
+        self.pull_ctas = self.pull_sms                 # whole-SM blocks (1024 threads): one per reserved SM
         if mode == "auto" and self.peer_supported() and not self._probe_symmetric_memory():
             mode = "halo"                                   # NVLink peer memory not available here: NCCL transport
         if mode == "auto":
