@@ -275,12 +275,7 @@ extern "C" int kagnn_kan_bwd_input(const KagnnKanLayer* layer, const float* x, i
     if (rc != KAGNN_OK) return rc;
     if (num_rows < 0 || (num_rows > 0 && (!x || !dy || !dx)) || ldx < g.in_f || ld_dy < g.out_f || ld_dx < g.in_f) return KAGNN_EINVAL;
     if (num_rows == 0) return KAGNN_OK;
-#ifndef KAGNN_HOST_CHECK
-    {   // product build: the shared-memory-tiled kernel (backward_tiled.cu) where its shape limits allow
-        const int trc = kagnn_kan_bwd_input_tiled(layer, x, ldx, dy, ld_dy, num_rows, dx, ld_dx, stream);
-        if (trc != KAGNN_EUNSUPPORTED) return trc;
-    }
-#endif
+    KAGNN_TRY_TILED(kagnn_kan_bwd_input_tiled(layer, x, ldx, dy, ld_dy, num_rows, dx, ld_dx, stream));
     if (g.in_f > 65535) return KAGNN_EUNSUPPORTED;                                  // gridDim.y
     KAGNN_LAUNCH(kan_bwd_input_kernel, dim3((unsigned)ceil_div64(num_rows, kBwdThreads), (unsigned)g.in_f, 1),
                  dim3((unsigned)kBwdThreads, 1, 1), stream, g, layer->packed_w, x, (long long)ldx, dy, (long long)ld_dy,
@@ -296,12 +291,7 @@ extern "C" int kagnn_kan_bwd_weights(const KagnnKanLayer* layer, const float* x,
     const int rc = geometry(layer, &g);
     if (rc != KAGNN_OK) return rc;
     if (num_rows < 0 || !d_packed || (num_rows > 0 && (!x || !dy)) || ldx < g.in_f || ld_dy < g.out_f) return KAGNN_EINVAL;
-#ifndef KAGNN_HOST_CHECK
-    if (num_rows > 0) {
-        const int trc = kagnn_kan_bwd_weights_tiled(layer, x, ldx, dy, ld_dy, num_rows, d_packed, stream);
-        if (trc != KAGNN_EUNSUPPORTED) return trc;
-    }
-#endif
+    if (num_rows > 0) KAGNN_TRY_TILED(kagnn_kan_bwd_weights_tiled(layer, x, ldx, dy, ld_dy, num_rows, d_packed, stream));
     KAGNN_CUDA_TRY(cudaMemsetAsync(d_packed, 0, sizeof(float) * (size_t)g.in_f * (size_t)(g.S + 1) * (size_t)g.out_pad, stream));
     if (num_rows == 0) return KAGNN_OK;
     const int threads = g.out_f >= 256 ? 256 : ((g.out_f + 31) / 32) * 32;

@@ -12,4 +12,13 @@
 #else
 #include "common.cuh"
 #define KAGNN_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+// product build: try the shared-memory-tiled kernel (backward_tiled.cu) first; it declines shapes outside its limits
+#define KAGNN_TRY_TILED(call)                              \
+    do {                                                   \
+        const int _trc = (call);                           \
+        if (_trc != KAGNN_EUNSUPPORTED) return _trc;       \
+    } while (0)
+#endif
+#ifndef KAGNN_TRY_TILED
+#define KAGNN_TRY_TILED(call) do { } while (0)            // the serial host build checks the general kernels only
 #endif
