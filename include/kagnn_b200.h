@@ -125,8 +125,8 @@ typedef struct KagnnAggregate {
     int64_t ld_head;
     /* Node-sharded graphs, halo rows that arrive WHILE the layer runs (kagnn_gather_rows_peer_ordered on a second stream): the
      * halo matrix is filled in the order the destination tiles first use its rows; halo_need[t] (one entry per 128-row tile) =
-     * number of leading halo rows that tiles 0..t reference, halo_flags[c] >= 32 * halo_epoch <=> halo rows [256 c, 256 c + 256)
-     * have landed (cumulative arrival counters of the pull kernel's 32 warps; epoch = 1, 2, ... per use, never reset).  The gather warps of the pipelined kernel wait for the flags of their tile's prefix before they read x_halo, so the
+     * number of leading halo rows that tiles 0..t reference, halo_flags[c] >= 16 * halo_epoch <=> halo rows [256 c, 256 c + 256)
+     * have landed (cumulative arrival counters of the pull kernel's 16 warps; epoch = 1, 2, ... per use, never reset).  The gather warps of the pipelined kernel wait for the flags of their tile's prefix before they read x_halo, so the
      * NVLink transfer overlaps the tensor-core pipeline tile by tile instead of preceding it.  reserve_sms: SMs the launch leaves
      * free (for the concurrently running pull kernel).  halo_flags == NULL: not used (x_halo must be complete at launch).     */
     const int32_t* halo_need;
@@ -235,9 +235,9 @@ int kagnn_gather_rows_peer(const float* const* peer_x, int64_t ldx, int64_t rows
                            int64_t num_rows, int32_t num_cols, float* out, int64_t ld_out, void* stream);
 
 /* The same pull in first-use order with progress flags (see KagnnAggregate.halo_flags): a persistent kernel of num_ctas blocks
- * copies halo rows [256 c, 256 c + 256) chunk by chunk (block b takes chunks b, b + num_ctas, ...); each of its 32 warps adds 1
- * to chunk_flags[c] (release) when its rows are stored, so a chunk of the epoch-th use is complete at 32 * epoch.  chunk_flags
- * must be zero before the first use.  Blocks are 1024 threads (one per SM): num_ctas = the SMs given to the pull.  Launch it on
+ * copies halo rows [256 c, 256 c + 256) chunk by chunk (block b takes chunks b, b + num_ctas, ...); each of its 16 warps adds 1
+ * to chunk_flags[c] (release) when its rows are stored, so a chunk of the epoch-th use is complete at 16 * epoch.  chunk_flags
+ * must be zero before the first use.  Blocks claim a whole SM each: num_ctas = the SMs given to the pull.  Launch it on
  * a second stream BEFORE the fused layer that consumes the flags. */
 int kagnn_gather_rows_peer_ordered(const float* const* peer_x, int64_t ldx, int64_t rows_per_rank, const int32_t* ids,
                                    int64_t num_rows, int32_t num_cols, float* out, int64_t ld_out, int32_t* chunk_flags,

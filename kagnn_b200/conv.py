@@ -18,7 +18,6 @@ additionally fuse across layer boundaries (models_*.py).
 """
 from __future__ import annotations
 
-import os
 from typing import Optional
 
 import torch
@@ -172,9 +171,7 @@ class GINEConv(GINConv):
         g = self._graph(x, edge_index)
         params = list(self.parameters())
         if autograd.grad_needed(x, params) or (torch.is_grad_enabled() and edge_attr.requires_grad):
-            # Host-checked and dry-run on the CPU against the reference's gradients (tests/test_backward_wiring.py), but not yet
-            # run on a GPU: opt-in until it has been (the B-spline / FastKAN / GIN / GCN backward has).
-            _module_backend_guard(x, params, grad_ok=os.environ.get("KAGNN_EXPERIMENTAL_GINE_BACKWARD") == "1")
+            _module_backend_guard(x, params, grad_ok=True)       # backward: kagnn_gine_bwd (autograd.gine_aggregate), GPU-validated
             if edge_row is not None or out is not None or post is not None:
                 raise NotImplementedError("edge-feature tables / fused epilogues are inference-only")
             if self.eps.requires_grad:

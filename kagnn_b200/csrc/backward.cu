@@ -628,12 +628,16 @@ __global__ void scale_rows_kernel(const float* __restrict__ a, long long lda, lo
 __global__ void gine_bwd_edges_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ ef, long long ld_e,
                                       const int64_t* __restrict__ src, const int64_t* __restrict__ dst, long long n_edges, int cols,
                                       const float* __restrict__ da, long long ld_da, float* __restrict__ dx, long long ld_dx,
-                                      float* __restrict__ d_ef, long long ld_de) {
+                                      float* __restrict__ d_ef, long long ld_de, long long n_nodes) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_edges * cols) return;
     const int c = (int)(idx % cols);
     const long long e = idx / cols;
     const long long j = src[e], i = dst[e];
+    if (j < 0 || j >= n_nodes || i < 0 || i >= n_nodes) {     // the forward's CSR build has flagged this edge_index (IndexError): no stray access
+        if (d_ef) d_ef[e * ld_de + c] = 0.f;
+        return;
+    }
     const float m = x[j * ldx + c] + ef[e * ld_e + c];
     const float g = m > 0.f ? da[i * ld_da + c] : 0.f;
     if (d_ef) d_ef[e * ld_de + c] = g;
@@ -655,7 +659,7 @@ extern "C" int kagnn_gine_bwd(const float* x, int64_t ldx, const float* edge_fea
     if (num_edges == 0) return KAGNN_OK;
     KAGNN_LAUNCH(gine_bwd_edges_kernel, (unsigned)ceil_div64(num_edges * (int64_t)num_cols, kBwdThreads), kBwdThreads, stream, x,
                  (long long)ldx, edge_feat, (long long)ld_edge, edge_index, edge_index + num_edges, (long long)num_edges, (int)num_cols,
-                 da, (long long)ld_da, dx, (long long)ld_dx, d_edge_feat, (long long)ld_de);
+                 da, (long long)ld_da, dx, (long long)ld_dx, d_edge_feat, (long long)ld_de, (long long)num_nodes);
     KAGNN_LAUNCH_CHECK();
     return KAGNN_OK;
 }

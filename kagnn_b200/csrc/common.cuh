@@ -5,6 +5,7 @@
 #include "../../include/kagnn_b200.h"
 
 #define KAGNN_MAX_LAYERS 8
+#define KAGNN_PULL_WARPS 16       // warps of a kagnn_gather_rows_peer_ordered block: arrivals per chunk counter and use (graph.cu, fused_tc2.cu)
 
 #define KAGNN_CUDA_TRY(expr)                         \
     do {                                             \

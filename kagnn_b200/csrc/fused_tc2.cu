@@ -1430,7 +1430,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                 while (halo_done < nchunk) {
                     int v;
                     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p.agg.halo_flags + halo_done) : "memory");
-                    if (v >= 32 * p.agg.halo_epoch) {            // all 32 warps of the pull block have stored their rows of this chunk
+                    if (v >= KAGNN_PULL_WARPS * p.agg.halo_epoch) {   // every warp of the pull block has stored its rows of this chunk
                         ++halo_done;
                     } else {
                         __nanosleep(200);

@@ -134,49 +134,62 @@ __global__ void gather_rows_peer_kernel(const float* const* __restrict__ peer_x,
 // (block b: chunks b, b + gridDim.x, ...), and a finished chunk stores `epoch` into its flag with release semantics.  The fused
 // layer that runs concurrently (fused_tc2.cu, KagnnAggregate.halo_flags) waits on the flags of the prefix its tile needs.
 constexpr int kHaloChunk = 256;
-constexpr int kPullU = 8;                               // rows in flight per warp
-constexpr int kPullWarps = 32;                          // one block = 1024 threads = a whole SM (see below)
+constexpr int kPullU = 16;                              // rows in flight per warp
+constexpr int kPullWarps = KAGNN_PULL_WARPS;            // 16 warps x 16 rows = one chunk; the block also claims a whole SM (see below)
+constexpr int kPullSmem = 180 * 1024;                   // dynamic shared memory requested only to keep other blocks off the SM
 // Why whole-SM blocks: the fused layer that runs next to this kernel needs an entire SM per block (register file and shared
-// memory), and the hardware spreads the blocks of a small kernel one per SM.  Pull blocks that each fill an SM occupy exactly
-// gridDim.x SMs and leave the others to the layer (KagnnAggregate.reserve_sms); light blocks would be scattered over 4x as many
-// SMs and push a third of the layer's blocks into a second wave.  32 warps x 8 rows x 512 B per block keep ~2 MB in flight on 16
-// SMs -- the NVLink latency-bandwidth product.  No block-wide barrier: every warp adds 1 to its chunk's counter (release) when its
-// 8 rows are stored, so warps run ahead into later chunks; a chunk is complete when its counter reaches 32 * epoch.
+// memory), and the hardware spreads the blocks of a small kernel one per SM.  Pull blocks that each claim an SM (180 KB of shared
+// memory they never touch) occupy exactly gridDim.x SMs and leave the others to the layer (KagnnAggregate.reserve_sms); light
+// blocks would be scattered over 4x as many SMs and push a third of the layer's blocks into a second wave.  16 warps x 16 rows
+// x 512 B per block keep ~2 MB in flight on 16 SMs -- the NVLink latency-bandwidth product.  No block-wide barrier: every warp
+// adds 1 to its chunk's counter (release) when its rows are stored, so warps run ahead into later chunks; a chunk is complete
+// when its counter reaches KAGNN_PULL_WARPS * epoch.
 __global__ void __launch_bounds__(kPullWarps * 32, 1) gather_rows_peer_ordered_kernel(const float* const* __restrict__ peer_x, int64_t ldx,
                                                                                       int64_t rows_per_rank, const int32_t* __restrict__ ids,
                                                                                       int64_t rows, int cols, float* __restrict__ out,
                                                                                       int64_t ld_out, int32_t* __restrict__ flags) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t n_chunks = (rows + kHaloChunk - 1) / kHaloChunk;
-    for (int64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+    // Software pipeline per warp: the row ids of the NEXT chunk are fetched while the current chunk's rows are in flight, and a
+    // chunk is published (release add on its counter) one iteration late, just before the next batch of loads is issued -- by
+    // then its stores have long been acknowledged, so an iteration costs about one NVLink round trip and nothing else.
+    int32_t gid[kPullU];
+    auto fetch_ids = [&](int64_t c) {
         const int64_t r0 = c * kHaloChunk, r1 = min(rows, r0 + (int64_t)kHaloChunk);
-        // warp w copies rows r0 + w, r0 + w + 32, ... of the chunk (each lane 16 bytes per 128 columns), all kPullU in flight
-        const float* src[kPullU];
 #pragma unroll
         for (int u = 0; u < kPullU; ++u) {
             const int64_t r = r0 + warp + kPullWarps * u;
+            gid[u] = (r < r1) ? ids[r] : -1;
+        }
+    };
+    int64_t c = blockIdx.x, prev = -1;
+    if (c < n_chunks) fetch_ids(c);
+    for (; c < n_chunks; c += gridDim.x) {
+        const int64_t r0 = c * kHaloChunk;
+        const float* src[kPullU];
+#pragma unroll
+        for (int u = 0; u < kPullU; ++u) {
             src[u] = nullptr;
-            if (r < r1) {
-                const int32_t gid = ids[r];
-                const int owner = (int)(gid / rows_per_rank);
-                src[u] = peer_x[owner] + (gid - owner * rows_per_rank) * ldx;
+            if (gid[u] >= 0) {
+                const int owner = (int)(gid[u] / rows_per_rank);
+                src[u] = peer_x[owner] + (gid[u] - owner * rows_per_rank) * ldx;
             }
         }
+        if (prev >= 0 && lane == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(flags + prev) : "memory");
         for (int cc = lane * 4; cc < cols; cc += 128) {
             float4 v[kPullU];
 #pragma unroll
             for (int u = 0; u < kPullU; ++u)
                 if (src[u]) v[u] = __ldg(reinterpret_cast<const float4*>(src[u] + cc));
+            if (cc == lane * 4 && c + gridDim.x < n_chunks) fetch_ids(c + gridDim.x);      // overlaps the row loads above
 #pragma unroll
             for (int u = 0; u < kPullU; ++u)
                 if (src[u]) *reinterpret_cast<float4*>(out + (r0 + warp + kPullWarps * u) * ld_out + cc) = v[u];
         }
-        __syncwarp();
-        if (lane == 0) {
-            __threadfence();
-            asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(flags + c) : "memory");
-        }
+        __syncwarp();                                   // the warp's stores are ordered before lane 0's release below / next iteration
+        prev = c;
     }
+    if (prev >= 0 && lane == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(flags + prev) : "memory");
 }
 
 inline int bits_for(int64_t n) {
@@ -325,11 +338,12 @@ extern "C" int kagnn_gather_rows_peer_ordered(const float* const* peer_x, int64_
         return KAGNN_EINVAL;
     if (rows == 0 || cols == 0) return KAGNN_OK;
     if (!aligned16(out) || (ldx % 4) || (ld_out % 4) || (cols % 4)) return KAGNN_EALIGN;
-    (void)epoch;                                        // the counters are cumulative: a chunk of use `epoch` is complete at 32 * epoch
+    (void)epoch;                                        // the counters are cumulative: a chunk of use `epoch` is complete at KAGNN_PULL_WARPS * epoch
     const int64_t n_chunks = ceil_div64(rows, kHaloChunk);
     const unsigned blocks = (unsigned)(n_chunks < num_ctas ? n_chunks : num_ctas);
-    gather_rows_peer_ordered_kernel<<<blocks, kPullWarps * 32, 0, stream>>>(peer_x, ldx, rows_per_rank, ids, rows, cols, out, ld_out,
-                                                                            chunk_flags);
+    KAGNN_CUDA_TRY(cudaFuncSetAttribute(gather_rows_peer_ordered_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPullSmem));
+    gather_rows_peer_ordered_kernel<<<blocks, kPullWarps * 32, kPullSmem, stream>>>(peer_x, ldx, rows_per_rank, ids, rows, cols, out,
+                                                                                    ld_out, chunk_flags);
     KAGNN_LAUNCH_CHECK();
     return KAGNN_OK;
 }

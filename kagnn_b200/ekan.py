@@ -67,6 +67,26 @@ def _module_backend_guard(x: Tensor, params: Sequence[Tensor], grad_ok: bool = F
     return False
 
 
+_warned_eval_detach = False
+
+
+def eval_mode_detach_notice(x: Tensor) -> None:
+    """model.eval() with autograd enabled: the models take the fused inference plan and return a result that is DETACHED from
+    autograd (the reference's val() / test() loops run exactly like that and never call backward on it).  Anything that does need
+    gradients through an eval-mode model must not get a silently detached tensor: input gradients raise, and the first detached
+    call warns once."""
+    global _warned_eval_detach
+    if x.is_floating_point() and x.requires_grad:
+        raise NotImplementedError("kagnn_b200: gradients with respect to the input of a model in eval() mode are not implemented "
+                                  "(the eval-mode forward is the fused inference plan); call model.train() -- with BatchNorm / "
+                                  "Dropout modules individually in eval() if their statistics must stay frozen -- or detach the input")
+    if not _warned_eval_detach:
+        _warned_eval_detach = True
+        import warnings
+        warnings.warn("kagnn_b200: a model in eval() mode was called with autograd enabled; its output is computed by the fused "
+                      "inference plan and is detached from autograd (wrap evaluation in torch.no_grad() to silence this)", stacklevel=3)
+
+
 class KANLinear(nn.Module):
     """Drop-in for ``ekan.KANLinear``: y = silu(x) @ base_weight^T + B(x) @ (spline_weight * spline_scaler)^T."""
 

@@ -14,7 +14,7 @@ from torch import nn
 from . import _lib as L
 from . import autograd, ops
 from .conv import FASTKAGCN_Layer, GINConv, KAGCN_Layer, make_fastkan, make_kan
-from .ekan import _module_backend_guard
+from .ekan import _module_backend_guard, eval_mode_detach_notice
 from .graph import get_graph
 from .models_node import _BNFold, bn_is_foldable, bn_unfused
 
@@ -48,6 +48,7 @@ def _bn_unfused(x: Tensor, bn: nn.BatchNorm1d) -> Tensor:
 
 def _eval_without_no_grad(model: nn.Module, data) -> Tensor:
     """model.eval() with autograd enabled (graph_classification_utils.py:57-72): inference plan, result detached."""
+    eval_mode_detach_notice(data.x)
     with torch.no_grad():
         return model.forward(data)
 

@@ -22,7 +22,7 @@ from torch import nn
 from . import _lib as L
 from . import autograd, ops
 from .conv import FASTKAGCNConv, GIFASTKANLayer, GIKANLayer, KAGCNConv, GCNConv
-from .ekan import KANLinear, _module_backend_guard
+from .ekan import KANLinear, _module_backend_guard, eval_mode_detach_notice
 from .fastkan import FastKANLayer
 from .graph import get_graph
 
@@ -92,6 +92,7 @@ class _NodeModel(nn.Module):
         if needs_grad and not self.training:
             # model.eval() without torch.no_grad() (the reference's val()/test() loops of graph_classification_utils.py:57-72 do
             # that): the fused inference plan, result detached from autograd
+            eval_mode_detach_notice(x)
             with torch.no_grad():
                 return self.forward(x, edge_index)
         x = x.to(torch.float32)

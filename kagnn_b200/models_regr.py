@@ -14,7 +14,7 @@ from torch import nn
 from . import _lib as L
 from . import ops
 from .conv import FASTKAGCN_Layer, GINEConv, KAGCN_Layer, make_fastkan, make_kan
-from .ekan import _module_backend_guard
+from .ekan import _module_backend_guard, eval_mode_detach_notice
 from .graph import get_graph
 from .models_graph import _GCNGraphModel, _GINGraphModel, _bn_unfused, _num_graphs, pooled_readout
 from .models_node import bn_unfused
@@ -86,6 +86,7 @@ class _GINERegression(_GINGraphModel):
         needs_grad = _module_backend_guard(x, list(self.parameters()), grad_ok=True)
         if needs_grad and not self.training:
             # eval() without no_grad (graph_regression/optuna_zinc.py:68-86): inference plan, result detached
+            eval_mode_detach_notice(x)
             with torch.no_grad():
                 return self.forward(data)
         if needs_grad:

@@ -43,13 +43,8 @@ def check_against_fixture(name, device, grad_tol=TOL):
     return model
 
 
-GINE_FIXTURES = grad_golden_names("grad_gr_")          # graph_regression GINE models: backward is opt-in until GPU-validated
-
-
 @pytest.mark.parametrize("name", grad_golden_names())
-def test_module_gradients_match_reference_dry_run(name, monkeypatch):
-    if name in GINE_FIXTURES:
-        monkeypatch.setenv("KAGNN_EXPERIMENTAL_GINE_BACKWARD", "1")
+def test_module_gradients_match_reference_dry_run(name):
     with cpu_double():
         check_against_fixture(name, "cpu")
 
@@ -71,9 +66,6 @@ def test_modules_without_backward_raise_under_autograd():
     import kagnn_b200 as kb
     with cpu_double():
         x = torch.randn(10, 4)
-        conv = kb.GINEConv(kb.make_kan(4, 4, 4, 1, 5, 3))
-        with pytest.raises(NotImplementedError):              # opt-in (KAGNN_EXPERIMENTAL_GINE_BACKWARD) until GPU-validated
-            conv(x, torch.randint(0, 10, (2, 20)), torch.randn(20, 4))
         gin = kb.GINConv(kb.make_kan(4, 4, 4, 1, 5, 3), train_eps=True)
         with pytest.raises(NotImplementedError):
             gin(x, torch.randint(0, 10, (2, 20)))

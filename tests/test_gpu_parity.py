@@ -252,9 +252,9 @@ def test_requires_cuda_and_modules_without_backward_raise_under_autograd():
     import kagnn_b200 as kb
     x = torch.randn(10, 4).cuda()
     ei = torch.randint(0, 10, (2, 20)).cuda()
-    conv = kb.GINEConv(kb.make_kan(4, 4, 4, 1, 5, 3)).cuda()
-    with pytest.raises(NotImplementedError):              # the GINE message has no backward yet: loud, not silent
-        conv(x, ei, torch.randn(20, 4).cuda())
+    gin = kb.GINConv(kb.make_kan(4, 4, 4, 1, 5, 3), train_eps=True).cuda()
+    with pytest.raises(NotImplementedError):              # a trainable eps has no backward here: loud, not silent
+        gin(x, ei)
     y = kb.KANLinear(4, 4).cuda()(torch.randn(3, 4).cuda())
     assert y.requires_grad                                # KAN layers record themselves for autograd
     with pytest.raises(RuntimeError):

@@ -104,8 +104,6 @@ def test_backward_at_arxiv_width_against_oracle_rows():
         assert grad_err(p.grad.cpu(), g_ref[name], scale) <= GRAD_TOL, name
 
 
-@pytest.mark.skipif(os.environ.get("KAGNN_EXPERIMENTAL_GINE_BACKWARD") != "1",
-                    reason="GINE backward is host-checked and dry-run on the CPU only so far; opt in with KAGNN_EXPERIMENTAL_GINE_BACKWARD=1")
 @pytest.mark.parametrize("name", GINE_FIXTURES)
 def test_gine_model_gradients_match_reference(name):
     check_against_fixture(name, "cuda", grad_tol=GRAD_TOL)
