@@ -212,7 +212,7 @@ def main():
     ap.add_argument("--config", default="arxiv", choices=["arxiv", "cora", "zinc", "mutag", "rmat"],
                     help="arxiv = the headline workload (BASELINE configs[1]); the others print the secondary measurement of that "
                          "configuration alone (scripts/bench_extras.py) as one JSON line")
-    ap.add_argument("--dist-mode", default="auto", choices=["auto", "peer", "pull", "halo"],
+    ap.add_argument("--dist-mode", default="auto", choices=["auto", "peer", "pull", "pull_overlap", "halo"],
                     help="N > 1: 'peer' = in-kernel NVLink gather from symmetric memory, 'halo' = NCCL all-to-all per layer")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -407,7 +407,7 @@ def main():
     # ---- NVLink side of the sharded run: bytes this rank pulls from its peers per step against the measured peer-copy rate ----
     if roofline is not None and dist_on:
         widths = N_FEAT + (MP_LAYERS - 1) * HIDDEN                       # row widths gathered by the three GIN layers: 128 + 64 + 64
-        if runner.mode == "pull":
+        if runner.mode in ("pull", "pull_overlap"):
             rows, what = int(plan.n_halo), "distinct remote rows (pulled once per layer)"
         elif runner.mode == "peer":
             col = plan.graph.col.long()
@@ -446,7 +446,7 @@ def main():
                    "l2": "flushed between iterations (512 MB memset)", "csr": "cached across steps (static graph)",
                    "parallelism": (f"node-range shards x{world}, " + ("remote rows gathered in-kernel over NVLink (symmetric memory), "
                                    "one device barrier per layer" if runner.mode == "peer" else ("distinct remote rows pulled over NVLink from symmetric memory "
-                                   "by a copy kernel that runs concurrently with the layer (first-use order, progress flags; no collective)" if runner.mode == "pull" else "one NCCL halo all-to-all per layer")))
+                                   "by one copy kernel per layer (no collective)" if runner.mode == "pull" else ("distinct remote rows pulled over NVLink by a copy kernel that runs concurrently with the layer (first-use order, progress counters)" if runner.mode == "pull_overlap" else "one NCCL halo all-to-all per layer"))))
                    if dist_on else "single GPU",
                    "graph": "uniform random edges over all shards: (N-1)/N of the edges are cut" if dist_on else "uniform random edges"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "kernels": kernels, "roofline": roofline, "cpu_baseline": cpu,

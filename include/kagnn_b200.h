@@ -248,6 +248,18 @@ int kagnn_gather_rows_peer_ordered(const float* const* peer_x, int64_t ldx, int6
 int kagnn_layernorm_stats(const float* x, int64_t ldx, int32_t num_cols, const float* x_head_or_null, int64_t ld_head,
                           int32_t num_head_cols, int64_t num_rows, float eps, float* stats, void* stream);
 
+/* ---- GAT attention (PyG GATConv with the KAN as its shared projection: nc/models.py:39-46,76-83; gc/models.py:165-172,236-243) --
+ * h = lin(x) is (num_rows, heads * channels).  kagnn_gat_scores: a_src / a_dst (num_rows, heads) = per-head dot products of h with
+ * att_src / att_dst (heads * channels, PyG's (1, heads, channels) parameter flattened).  kagnn_gat_edge_softmax: PyG's attention
+ * coefficients alpha = softmax_i(leaky_relu(a_src[j] + a_dst[i])) over the incoming CSR entries of i with existing self loops
+ * removed and one self loop appended, written as edge_weight [heads][nnz] (CSR order, 0 for a removed loop) and self_weight
+ * [heads][num_rows]: head by head the operands of kagnn_fused_layer_fwd in mode KAGNN_AGG_WEIGHTED on the head's column slice. */
+int kagnn_gat_scores(const float* h, int64_t ldh, int64_t num_rows, int32_t heads, int32_t channels, const float* att_src,
+                     const float* att_dst, float* a_src, float* a_dst, void* stream);
+int kagnn_gat_edge_softmax(const int32_t* rowptr, const int32_t* col, int64_t num_rows, int64_t nnz, int32_t heads,
+                           const float* a_src, const float* a_dst, float negative_slope, float* edge_weight, float* self_weight,
+                           void* stream);
+
 /* ---- small epilogues of the models (so that no step of a forward runs as framework math) ---------------------------- */
 /* y[r,:] = log_softmax(x[r,:]) (gc/models.py:119,194). */
 int kagnn_log_softmax_rows(const float* x, int64_t ldx, int64_t num_rows, int32_t num_cols, float* y, int64_t ldy, void* stream);

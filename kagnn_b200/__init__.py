@@ -12,8 +12,9 @@ Layout
 from . import _lib, ops, graph
 from .ekan import KAN, KANLinear
 from .fastkan import FastKAN, FastKANLayer, RadialBasisFunction, SplineLinear
-from .conv import (GCNConv, GINConv, GINEConv, KANLayer, FKANLayer, KAGCNConv, FASTKAGCNConv, GIKANLayer,
-                   GIFASTKANLayer, KAGCN_Layer, FASTKAGCN_Layer, make_kan, make_fastkan)
+from .conv import (GCNConv, GINConv, GINEConv, GATConv, KANLayer, FKANLayer, KAGCNConv, FASTKAGCNConv, GIKANLayer,
+                   GIFASTKANLayer, KAGCN_Layer, FASTKAGCN_Layer, KAGATConv, FASTKAGATConv, KAGAT_Layer, FASTKAGAT_Layer,
+                   make_kan, make_fastkan)
 from .models_node import GKAN_Nodes, GFASTKAN_Nodes
 from . import models_graph, models_regr
 from .ops import set_precision, get_precision

@@ -96,6 +96,10 @@ _SIGNATURES = {
                                          C.c_void_p]),
     "kagnn_gather_rows_peer_ordered": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64,
                                                  C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "kagnn_gat_scores": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p]),
+    "kagnn_gat_edge_softmax": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_float,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]),
     "kagnn_kan_bwd_input": (C.c_int, [C.POINTER(KagnnKanLayer), C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
                                       C.c_int64, C.c_void_p]),
     "kagnn_kan_bwd_weights": (C.c_int, [C.POINTER(KagnnKanLayer), C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,

@@ -230,11 +230,75 @@ KAGCN_Layer = KAGCNConv
 FASTKAGCN_Layer = FASTKAGCNConv
 
 
-class KAGATConv(nn.Module):
-    """GAT variants are outside the hot path."""
+class GATConv(_MessagePassing):
+    """PyG ``GATConv`` with the options the reference uses (``GATConv(in, out, heads)``: concat=True, negative_slope=0.2,
+    dropout=0, add_self_loops=True, bias=True, edge_dim=None) and PyG 2.5's parameter names: one shared projection ``lin``
+    (which the KAN-ised subclasses replace), ``att_src`` / ``att_dst`` (1, heads, out_channels), ``bias`` (heads * out_channels).
+    Forward = projection launch, attention launches (``ops.gat_attention``), one WEIGHTED aggregation launch per head on the
+    head's column slice.  Inference only: the edge-softmax has no backward here."""
 
-    def __init__(self, *a, **kw):
-        raise NotImplementedError("GAT-based KAN layers are out of scope of the B200 hot path")
+    def __init__(self, in_channels: int, out_channels: int, heads: int = 1, concat: bool = True, negative_slope: float = 0.2,
+                 dropout: float = 0.0, add_self_loops: bool = True, edge_dim=None, fill_value="mean", bias: bool = True, **kwargs):
+        super().__init__()
+        if not concat or dropout != 0.0 or not add_self_loops or edge_dim is not None or not bias or kwargs:
+            raise NotImplementedError("only GATConv's default options (as the reference uses them) are implemented")
+        self.in_channels, self.out_channels, self.heads, self.negative_slope = in_channels, out_channels, heads, negative_slope
+        self.lin = nn.Linear(in_channels, heads * out_channels, bias=False)
+        self.att_src = nn.Parameter(torch.empty(1, heads, out_channels))
+        self.att_dst = nn.Parameter(torch.empty(1, heads, out_channels))
+        self.bias = nn.Parameter(torch.zeros(heads * out_channels))
+        nn.init.xavier_uniform_(self.att_src)
+        nn.init.xavier_uniform_(self.att_dst)
+
+    def reset_parameters(self):
+        if hasattr(self.lin, "reset_parameters"):
+            self.lin.reset_parameters()
+        nn.init.xavier_uniform_(self.att_src)
+        nn.init.xavier_uniform_(self.att_dst)
+        nn.init.zeros_(self.bias)
+
+    def attend_and_aggregate(self, h: Tensor, graph: GraphCSR, out: Optional[Tensor] = None,
+                             extra: Optional[ops.Affine] = None) -> Tensor:
+        """``extra``: per-column affine / activation applied after the aggregation INSTEAD of the plain bias (the models fold
+        bias + eval BatchNorm or bias + SiLU into it); None = ``+ bias``."""
+        n, hc = h.shape
+        hd, c = self.heads, self.out_channels
+        w, sw = ops.gat_attention(h, graph.csr, self.att_src, self.att_dst, hd, self.negative_slope)
+        if out is None:
+            out = torch.empty(n, hc, dtype=torch.float32, device=h.device)
+        pre = extra if extra is not None else ops.Affine(shift=self.bias.detach())
+        for k in range(hd):
+            sl = slice(k * c, (k + 1) * c)
+            pre_k = ops.Affine(None if pre.scale is None else pre.scale[sl], None if pre.shift is None else pre.shift[sl], pre.act)
+            agg = ops.AggSpec(L.AGG_WEIGHTED, h[:, sl], graph.rowptr, graph.col, edge_weight=w[k], self_weight=sw[k])
+            ops.fused_layer(agg, n, [], pre=pre_k, agg_out=out[:, sl])
+        return out
+
+    def forward(self, x: Tensor, edge_index, edge_attr=None, size=None, out: Optional[Tensor] = None,
+                extra: Optional[ops.Affine] = None) -> Tensor:
+        if edge_attr is not None:
+            raise NotImplementedError("edge_dim is never used by the reference")
+        _module_backend_guard(x, list(self.parameters()), grad_ok=False)
+        g = self._graph(x, edge_index)
+        return self.attend_and_aggregate(self.lin(x).to(torch.float32), g, out=out, extra=extra)
 
 
-FASTKAGATConv = KAGAT_Layer = FASTKAGAT_Layer = KAGATConv
+class KAGATConv(GATConv):
+    """node_classification_clean/models.py:39-46, graph_classification/models.py:165-172 (``KAGAT_Layer``)."""
+
+    def __init__(self, in_feat: int, out_feat: int, heads: int, grid_size: int = 4, spline_order: int = 3):
+        super().__init__(in_feat, out_feat, heads)
+        self.lin = KANLayer(in_feat, out_feat * heads, grid_size, spline_order)
+
+
+class FASTKAGATConv(GATConv):
+    """node_classification_clean/models.py:76-83, graph_classification/models.py:236-243 (``FASTKAGAT_Layer``)."""
+
+    def __init__(self, in_feat: int, out_feat: int, heads: int, grid_size: int = 4):
+        super().__init__(in_feat, out_feat, heads)
+        self.grid_size = grid_size
+        self.lin = FKANLayer(in_feat, out_feat * heads, grid_size)
+
+
+KAGAT_Layer = KAGATConv
+FASTKAGAT_Layer = FASTKAGATConv

@@ -349,6 +349,102 @@ extern "C" int kagnn_gather_rows_peer_ordered(const float* const* peer_x, int64_
 }
 
 // ---------------------------------------------------------------------------------------------------
+// GAT attention (PyG GATConv with the KAN as shared projection: node_classification_clean/models.py:39-46,
+// graph_classification/models.py:165-172).  h = lin(x) has heads * C columns.
+//   gat_scores:        a_src[n,hd] = sum_c h[n, hd C + c] att_src[hd C + c], a_dst likewise                 (warp per row)
+//   gat_edge_softmax:  per destination row i and head: e = leaky_relu(a_src[j] + a_dst[i]) over the CSR entries j != i and the
+//                      one self loop PyG appends (existing self loops are removed first), alpha = exp(e - max) / (sum + 1e-16);
+//                      written as edge weights [head][nnz] (0 for a removed self loop) and self weights [head][N], i.e. exactly
+//                      the operands of the WEIGHTED aggregation (kagnn_fused_layer_fwd), which then runs once per head on the
+//                      head's column slice of h.
+// ---------------------------------------------------------------------------------------------------
+namespace {
+__global__ void gat_scores_kernel(const float* __restrict__ h, int64_t ldh, int64_t rows, int heads, int C,
+                                  const float* __restrict__ att_src, const float* __restrict__ att_dst, float* __restrict__ a_src,
+                                  float* __restrict__ a_dst) {
+    const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    const float* hr = h + r * ldh;
+    for (int hd = 0; hd < heads; ++hd) {
+        float s = 0.f, d = 0.f;
+        for (int c = lane; c < C; c += 32) {
+            const float v = hr[hd * C + c];
+            s = fmaf(v, att_src[hd * C + c], s);
+            d = fmaf(v, att_dst[hd * C + c], d);
+        }
+        for (int o = 16; o; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            d += __shfl_xor_sync(0xffffffffu, d, o);
+        }
+        if (lane == 0) {
+            a_src[r * heads + hd] = s;
+            a_dst[r * heads + hd] = d;
+        }
+    }
+}
+
+__device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
+
+__global__ void gat_edge_softmax_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t rows, int heads,
+                                        const float* __restrict__ a_src, const float* __restrict__ a_dst, float slope,
+                                        float* __restrict__ edge_w, int64_t nnz, float* __restrict__ self_w) {
+    const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (i >= rows) return;
+    const int beg = rowptr[i], end = rowptr[i + 1];
+    for (int hd = 0; hd < heads; ++hd) {
+        const float ad = a_dst[i * heads + hd];
+        const float e_self = lrelu(a_src[i * heads + hd] + ad, slope);
+        float m = e_self;
+        for (int e = beg + lane; e < end; e += 32) {
+            const int j = col[e];
+            if (j != (int)i) m = fmaxf(m, lrelu(a_src[(int64_t)j * heads + hd] + ad, slope));
+        }
+        for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        float sum = 0.f;
+        for (int e = beg + lane; e < end; e += 32) {
+            const int j = col[e];
+            if (j != (int)i) sum += expf(lrelu(a_src[(int64_t)j * heads + hd] + ad, slope) - m);
+        }
+        for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float x_self = expf(e_self - m);
+        const float inv = 1.0f / (sum + x_self + 1e-16f);
+        for (int e = beg + lane; e < end; e += 32) {
+            const int j = col[e];
+            edge_w[(int64_t)hd * nnz + e] = (j != (int)i) ? expf(lrelu(a_src[(int64_t)j * heads + hd] + ad, slope) - m) * inv : 0.f;
+        }
+        if (lane == 0) self_w[(int64_t)hd * rows + i] = x_self * inv;
+    }
+}
+}  // namespace
+
+extern "C" int kagnn_gat_scores(const float* h, int64_t ldh, int64_t num_rows, int32_t heads, int32_t channels, const float* att_src,
+                                const float* att_dst, float* a_src, float* a_dst, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (num_rows < 0 || heads <= 0 || channels <= 0 || ldh < (int64_t)heads * channels) return KAGNN_EINVAL;
+    if (num_rows > 0 && (!h || !att_src || !att_dst || !a_src || !a_dst)) return KAGNN_EINVAL;
+    if (num_rows == 0) return KAGNN_OK;
+    gat_scores_kernel<<<(unsigned)ceil_div64(num_rows * 32, kThreads), kThreads, 0, stream>>>(h, ldh, num_rows, heads, channels, att_src,
+                                                                                              att_dst, a_src, a_dst);
+    KAGNN_LAUNCH_CHECK();
+    return KAGNN_OK;
+}
+
+extern "C" int kagnn_gat_edge_softmax(const int32_t* rowptr, const int32_t* col, int64_t num_rows, int64_t nnz, int32_t heads,
+                                      const float* a_src, const float* a_dst, float negative_slope, float* edge_weight,
+                                      float* self_weight, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (num_rows < 0 || nnz < 0 || heads <= 0) return KAGNN_EINVAL;
+    if (num_rows > 0 && (!rowptr || !a_src || !a_dst || !self_weight || (nnz > 0 && (!col || !edge_weight)))) return KAGNN_EINVAL;
+    if (num_rows == 0) return KAGNN_OK;
+    gat_edge_softmax_kernel<<<(unsigned)ceil_div64(num_rows * 32, kThreads), kThreads, 0, stream>>>(
+        rowptr, col, num_rows, heads, a_src, a_dst, negative_slope, edge_weight, nnz, self_weight);
+    KAGNN_LAUNCH_CHECK();
+    return KAGNN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Row-wise log_softmax of the class logits (graph_classification/models.py:119,194) and training-mode
 // BatchNorm1d (node_classification_clean/models.py:197 with model.train(): batch statistics over all
 // rows, biased variance for the normalisation, unbiased for the running estimate, momentum update).

@@ -172,6 +172,11 @@ class ShardedNodeModel:
       model flavour, any backend; the CPU tests run it over gloo);
     * ``mode="pull"``: like "halo", but the distinct remote rows are pulled from their owners' symmetric memory by one copy
       kernel over NVLink (``kagnn_gather_rows_peer``): no pack, no send lists, no NCCL, plan built without communication;
+    * ``mode="pull_overlap"``: the same pull running CONCURRENTLY with the layer on a few reserved SMs: halo rows numbered in the
+      order the destination tiles first use them, per-chunk progress counters, the gather warps of the fused kernel wait for the
+      prefix their tile needs (``kagnn_gather_rows_peer_ordered``, ``KagnnAggregate.halo_flags``).  Measured on two B200s it does
+      NOT pay yet: an SM sustains only ~15 GB/s of peer loads, so the 16 SMs it may take from the layer pull at 240 GB/s where the
+      all-SM kernel reaches 680 GB/s (profiles/README.md); it stays available for experiments and is parity-tested;
     * ``mode="peer"``: by the gather warps of the fused kernel themselves, straight from the owners' memory over NVLink
       (``KagnnAggregate.peer_x``): every rank keeps its skip-concat buffer in ``torch.distributed._symmetric_memory``, the
       kernel receives the table of peer-mapped base pointers, and the only cross-rank traffic besides the row loads is one
@@ -180,8 +185,8 @@ class ShardedNodeModel:
       applies and falls back to ``"halo"`` otherwise."""
 
     def __init__(self, model, rank: int, world: int, n_local: int, group=None, mode: str = "halo"):
-        if mode not in ("halo", "peer", "pull", "auto"):
-            raise ValueError("mode must be 'halo', 'peer', 'pull' or 'auto'")
+        if mode not in ("halo", "peer", "pull", "pull_overlap", "auto"):
+            raise ValueError("mode must be 'halo', 'peer', 'pull', 'pull_overlap' or 'auto'")
         self.model, self.rank, self.world, self.n_local, self.group = model, rank, world, n_local, group
         self._symm = {}
         self._side = {}
@@ -195,7 +200,7 @@ class ShardedNodeModel:
             # arxiv-shaped bench, where every remote row is referenced ~3.6 times); "peer" needs no halo matrix at all
             # on 8 ranks the in-kernel gather measured 2.20 ms/step (NCCL halo 2.90) and is the measured choice there
             mode = ("peer" if world >= 8 else "pull") if self.peer_supported() else "halo"
-        elif mode in ("peer", "pull") and not self.peer_supported():
+        elif mode in ("peer", "pull", "pull_overlap") and not self.peer_supported():
             raise NotImplementedError("modes 'peer' / 'pull' need a GIN-flavour GKAN_Nodes / GFASTKAN_Nodes with skip=True, "
                                       "spline_order <= 3, G + k <= 8 (FastKAN: <= 8 centres), widths <= 128 and feature widths that "
                                       "are multiples of 4; GCN flavours and skip=False use mode='halo'")
@@ -247,7 +252,15 @@ class ShardedNodeModel:
 
     def prepare(self, edge_index_global: Tensor):
         if self.mode == "pull":
-            # local index arithmetic only (no communication): distinct remote sources -> halo numbering in first-use order
+            # local index arithmetic only (no communication): distinct remote sources -> halo numbering
+            ei_local, halo_global, _ = relabel_edges(edge_index_global, self.rank, self.world, self.n_local)
+            n_halo = int(halo_global.numel())
+            plan = PeerPlan(GraphCSR(ei_local, self.n_local, self.n_local + n_halo), self.n_local, self.world)
+            plan.halo_ids = halo_global.to(torch.int32)
+            plan.n_halo = n_halo
+            return plan
+        if self.mode == "pull_overlap":
+            # the same, numbered in first-use order for the pull that runs concurrently with the layer
             ei_local, halo_global, need = relabel_edges_first_use(edge_index_global, self.rank, self.world, self.n_local)
             n_halo = int(halo_global.numel())
             plan = PeerPlan(GraphCSR(ei_local, self.n_local, self.n_local + n_halo), self.n_local, self.world)
@@ -310,6 +323,11 @@ class ShardedNodeModel:
             hdl.barrier()                                 # the slice read below is complete on every rank
             dst = buf[:, f + l * hid: f + (l + 1) * hid]
             if self.mode == "pull":
+                # the distinct remote rows, copied once from their owners by a pull kernel on all SMs (678 GB/s measured on two
+                # B200s), then the ordinary halo layer
+                halo = ops.gather_rows_peer(table(col), buf.stride(0), self.n_local, plan.halo_ids, cur.size(1))
+                conv(cur, plan.graph, out=dst, post=m._folds[l].get(bn), x_halo=halo)
+            elif self.mode == "pull_overlap":
                 # the distinct remote rows, pulled from their owners WHILE the layer runs: the pull kernel (side stream, a few SMs)
                 # copies them in first-use order and raises one flag per 256 rows; the gather warps of the fused kernel wait for the
                 # prefix their tile needs (KagnnAggregate.halo_flags), so NVLink time hides behind the tensor-core pipeline
@@ -339,7 +357,7 @@ class ShardedNodeModel:
         m = self.model
         if len(m.convs) == 0:                               # no message passing: nothing to exchange
             return m(x, torch.zeros(2, 0, dtype=torch.int64, device=x.device))
-        if self.mode in ("peer", "pull"):
+        if self.mode in ("peer", "pull", "pull_overlap"):
             if not m._fusable():
                 raise NotImplementedError("the sharded forward implements the eval-mode plan (BatchNorm folded)")
             x = x.to(torch.float32)

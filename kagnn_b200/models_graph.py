@@ -13,7 +13,7 @@ from torch import nn
 
 from . import _lib as L
 from . import autograd, ops
-from .conv import FASTKAGCN_Layer, GINConv, KAGCN_Layer, make_fastkan, make_kan
+from .conv import FASTKAGAT_Layer, FASTKAGCN_Layer, GINConv, KAGAT_Layer, KAGCN_Layer, make_fastkan, make_kan
 from .ekan import _module_backend_guard, eval_mode_detach_notice
 from .graph import get_graph
 from .models_node import _BNFold, bn_is_foldable, bn_unfused
@@ -180,4 +180,40 @@ class FASTKAGCN(_GCNGraphModel):
         self.conv = nn.ModuleList(
             FASTKAGCN_Layer(num_features if i == 0 else hidden_dim, hidden_dim, grid_size) for i in range(gnn_layers))
         self.readout = make_fastkan(hidden_dim, hidden_dim, num_classes, 1, grid_size)
+        self.dropout = nn.Dropout(p=dropout)
+
+
+class _GATGraphModel(_GCNGraphModel):
+    """(GAT conv -> silu -> dropout) xL; ADD pool; 1-layer KAN read-out (graph_classification/models.py:194-216, 266-288)."""
+    mean_pool = False
+
+    def _message_passing(self, x: Tensor, g, needs_grad: bool = False) -> Tensor:
+        if needs_grad:
+            raise NotImplementedError("the GAT flavour has no backward here (inference / evaluation only)")
+        for i in range(self.n_layers):
+            c = self.conv[i]
+            x = c(x, g, extra=ops.Affine(shift=c.bias.detach(), act=L.ACT_SILU))
+            if self.training and self.dropout.p > 0.0:
+                x = self.dropout(x)
+        return x
+
+
+class KAGAT(_GATGraphModel):
+    def __init__(self, gnn_layers, num_features, hidden_dim, num_classes, grid_size, spline_order, dropout, heads):
+        super().__init__()
+        self.n_layers = gnn_layers
+        self.conv = nn.ModuleList(
+            KAGAT_Layer(num_features if i == 0 else hidden_dim * heads, hidden_dim, heads, grid_size, spline_order) for i in range(gnn_layers))
+        self.readout = make_kan(hidden_dim * heads, hidden_dim, num_classes, 1, grid_size, spline_order)
+        self.dropout = nn.Dropout(p=dropout)
+
+
+class FASTKAGAT(_GATGraphModel):
+    def __init__(self, gnn_layers, num_features, hidden_dim, num_classes, grid_size, dropout, heads):
+        super().__init__()
+        self.n_layers = gnn_layers
+        self.heads = heads
+        self.conv = nn.ModuleList(
+            FASTKAGAT_Layer(num_features if i == 0 else hidden_dim * heads, hidden_dim, heads=heads, grid_size=grid_size) for i in range(gnn_layers))
+        self.readout = make_fastkan(hidden_dim * heads, hidden_dim, num_classes, 1, grid_size)
         self.dropout = nn.Dropout(p=dropout)

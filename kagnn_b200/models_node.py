@@ -21,7 +21,7 @@ from torch import nn
 
 from . import _lib as L
 from . import autograd, ops
-from .conv import FASTKAGCNConv, GIFASTKANLayer, GIKANLayer, KAGCNConv, GCNConv
+from .conv import FASTKAGATConv, FASTKAGCNConv, GATConv, GIFASTKANLayer, GIKANLayer, KAGATConv, KAGCNConv, GCNConv
 from .ekan import KANLinear, _module_backend_guard, eval_mode_detach_notice
 from .fastkan import FastKANLayer
 from .graph import get_graph
@@ -109,10 +109,14 @@ class _NodeModel(nn.Module):
         buf = torch.empty(n, n_mp * hid, dtype=torch.float32, device=x.device) if self.skip else None
         cur = x
         is_gcn = isinstance(self.convs[0], GCNConv)
+        is_gat = isinstance(self.convs[0], GATConv)
         t = self.convs[0].transform(cur) if is_gcn else None
         for l, (conv, bn) in enumerate(zip(self.convs, self.bns)):
             dst = buf[:, l * hid: (l + 1) * hid] if self.skip else torch.empty(n, hid, dtype=torch.float32, device=x.device)
-            if is_gcn:
+            if is_gat:
+                # projection (KAN launch) -> attention -> one weighted aggregation per head; bias + eval BatchNorm folded into it
+                conv(cur, g, out=dst, extra=self._folds[l].get(bn, conv.bias.detach()))
+            elif is_gcn:
                 pre = self._folds[l].get(bn, conv.bias.detach() if conv.bias is not None else None)
                 nxt = self.convs[l + 1].lin.kernel_specs() if l + 1 < n_mp else []
                 w, sw = g.gcn_weights()
@@ -143,20 +147,22 @@ class GKAN_Nodes(_NodeModel):
                  skip: bool = True, grid_size: int = 4, spline_order: int = 3, hidden_layers: int = 2, dropout: float = 0.,
                  heads=4):
         super().__init__()
-        if conv_type == "gat":
-            raise NotImplementedError("GAT variants are out of scope of the B200 hot path (SURVEY.md section 2)")
-        if conv_type not in ("gcn", "gin"):
+        if conv_type not in ("gcn", "gin", "gat"):
             raise ValueError("unknown conv_type")
+        if conv_type != "gat":
+            heads = 1
         self.convs = nn.ModuleList()
         self.bns = nn.ModuleList()
         for i in range(mp_layers):
-            fin = num_features if i == 0 else hidden_channels
+            fin = num_features if i == 0 else hidden_channels * heads
             if conv_type == "gcn":
                 self.convs.append(KAGCNConv(fin, hidden_channels, grid_size, spline_order))
+            elif conv_type == "gat":
+                self.convs.append(KAGATConv(fin, hidden_channels, heads, grid_size, spline_order))
             else:
                 self.convs.append(GIKANLayer(fin, hidden_channels, grid_size, spline_order, hidden_channels, hidden_layers))
-            self.bns.append(nn.BatchNorm1d(hidden_channels))
-        dim_out = num_features + mp_layers * hidden_channels if skip else hidden_channels
+            self.bns.append(nn.BatchNorm1d(hidden_channels * heads))
+        dim_out = num_features + mp_layers * hidden_channels * heads if skip else hidden_channels * heads
         self.lay_out = KANLinear(dim_out, num_classes, grid_size=grid_size, spline_order=spline_order)
         self._init_common(skip, dropout)
 
@@ -165,19 +171,21 @@ class GFASTKAN_Nodes(_NodeModel):
     def __init__(self, conv_type: str, mp_layers: int, num_features: int, hidden_channels: int, num_classes: int,
                  skip: bool = True, grid_size: int = 4, hidden_layers: int = 2, dropout: float = 0., heads=4):
         super().__init__()
-        if conv_type == "gat":
-            raise NotImplementedError("GAT variants are out of scope of the B200 hot path (SURVEY.md section 2)")
-        if conv_type not in ("gcn", "gin"):
+        if conv_type not in ("gcn", "gin", "gat"):
             raise ValueError("unknown conv_type")
+        if conv_type != "gat":
+            heads = 1
         self.convs = nn.ModuleList()
         self.bns = nn.ModuleList()
         for i in range(mp_layers):
-            fin = num_features if i == 0 else hidden_channels
+            fin = num_features if i == 0 else hidden_channels * heads
             if conv_type == "gcn":
                 self.convs.append(FASTKAGCNConv(fin, hidden_channels, grid_size))
+            elif conv_type == "gat":
+                self.convs.append(FASTKAGATConv(fin, hidden_channels, heads, grid_size))
             else:
                 self.convs.append(GIFASTKANLayer(fin, hidden_channels, grid_size, hidden_channels, hidden_layers))
-            self.bns.append(nn.BatchNorm1d(hidden_channels))
-        dim_out = num_features + mp_layers * hidden_channels if skip else hidden_channels
+            self.bns.append(nn.BatchNorm1d(hidden_channels * heads))
+        dim_out = num_features + mp_layers * hidden_channels * heads if skip else hidden_channels * heads
         self.lay_out = FastKANLayer(dim_out, num_classes, num_grids=grid_size)
         self._init_common(skip, dropout)

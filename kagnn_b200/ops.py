@@ -307,6 +307,30 @@ def gather_rows_peer(peer_x: Tensor, ldx: int, rows_per_rank: int, ids: Tensor, 
     return out
 
 
+@_on_device
+def gat_attention(h: Tensor, csr: CSR, att_src: Tensor, att_dst: Tensor, heads: int, negative_slope: float = 0.2):
+    """PyG GATConv's attention coefficients for h = lin(x) of shape (N, heads * C) on a destination-sorted CSR:
+    returns (edge_weight (heads, nnz), self_weight (heads, N)) -- per head the operands of the WEIGHTED aggregation
+    (kagnn_gat_scores + kagnn_gat_edge_softmax)."""
+    global launch_count
+    ldh = _rows(h, "h")
+    n, hc = h.shape
+    c = hc // heads
+    dev = h.device
+    a_s = torch.empty(n, heads, dtype=torch.float32, device=dev)
+    a_d = torch.empty(n, heads, dtype=torch.float32, device=dev)
+    ats, atd = att_src.detach().reshape(-1).contiguous(), att_dst.detach().reshape(-1).contiguous()
+    _need_cuda(ats, "att_src", torch.float32)
+    _need_cuda(atd, "att_dst", torch.float32)
+    L.check(L.lib().kagnn_gat_scores(_p(h), ldh, n, heads, c, _p(ats), _p(atd), _p(a_s), _p(a_d), _stream()), "gat_scores")
+    w = torch.empty(heads, max(csr.nnz, 1), dtype=torch.float32, device=dev)
+    sw = torch.empty(heads, n, dtype=torch.float32, device=dev)
+    L.check(L.lib().kagnn_gat_edge_softmax(_p(csr.rowptr), C.c_void_p(_addr(csr.col)), n, csr.nnz, heads, _p(a_s), _p(a_d),
+                                           float(negative_slope), _p(w), _p(sw), _stream()), "gat_edge_softmax")
+    launch_count += 2
+    return w[:, :csr.nnz] if csr.nnz else w[:, :0], sw
+
+
 HALO_CHUNK = 256          # rows per progress flag of gather_rows_peer_ordered (kHaloChunk in csrc/graph.cu)
 
 

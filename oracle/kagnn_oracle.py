@@ -199,6 +199,36 @@ def gine_conv(x: Tensor, edge_index: Tensor, edge_attr: Tensor, nn_fn, eps: floa
     return nn_fn(agg + (1.0 + eps) * x)
 
 
+def gat_conv(x: Tensor, edge_index: Tensor, lin, att_src: Tensor, att_dst: Tensor, bias: Optional[Tensor],
+             heads: int, negative_slope: float = 0.2, concat: bool = True) -> Tensor:
+    """PyG 2.5 ``GATConv.forward`` for an int ``in_channels`` (one shared projection ``self.lin``, which KAGATConv replaces by a
+    KAN: node_classification_clean/models.py:39-46), ``edge_dim=None``, ``dropout=0``, ``add_self_loops=True``:
+        h = lin(x).view(N, H, C);  a_src = (h * att_src).sum(-1);  a_dst = (h * att_dst).sum(-1)
+        edges: existing self loops removed, one loop per node appended (remove_self_loops + add_self_loops)
+        e_ji = leaky_relu(a_src[j] + a_dst[i], 0.2);  alpha = softmax over the incoming edges of i (PyG softmax: exp(e - max) /
+        (sum + 1e-16));  out_i = sum_j alpha_ji h_j;  heads concatenated (or averaged), + bias.
+    ``lin`` is a callable.  Parity unpinned like the rest of the PyG half (torch_geometric is not installable here)."""
+    n = x.size(0)
+    h = lin(x)
+    c = h.size(1) // heads
+    h = h.view(n, heads, c)
+    a_s = (h * att_src.view(1, heads, c).to(h.dtype)).sum(-1)
+    a_d = (h * att_dst.view(1, heads, c).to(h.dtype)).sum(-1)
+    row, col = edge_index[0], edge_index[1]
+    keep = row != col
+    loops = torch.arange(n, dtype=row.dtype)
+    row2, col2 = torch.cat([row[keep], loops]), torch.cat([col[keep], loops])
+    e = F.leaky_relu(a_s[row2] + a_d[col2], negative_slope)                                     # (E', H)
+    idx = col2.unsqueeze(1).expand(-1, heads)
+    m = torch.full((n, heads), float("-inf"), dtype=h.dtype).scatter_reduce(0, idx, e, reduce="amax", include_self=True)
+    ex = (e - m[col2]).exp()
+    den = torch.zeros(n, heads, dtype=h.dtype).index_add_(0, col2, ex) + 1e-16
+    alpha = ex / den[col2]
+    out = torch.zeros(n, heads, c, dtype=h.dtype).index_add_(0, col2, alpha.unsqueeze(-1) * h[row2])
+    out = out.reshape(n, heads * c) if concat else out.mean(1)
+    return out if bias is None else out + bias.to(out.dtype)
+
+
 def global_add_pool(x: Tensor, batch: Tensor, num_graphs: Optional[int] = None) -> Tensor:
     """scatter(x, batch, dim=0, reduce='sum'), dim_size = batch.max()+1."""
     if num_graphs is None:
@@ -254,7 +284,7 @@ def _kan_or_fast_layer(sd, prefix, x):
 def node_model_forward(sd: Dict[str, Tensor], conv_type: str, x: Tensor, edge_index: Tensor,
                        skip: bool = True, training: bool = False) -> Tensor:
     """``GKAN_Nodes.forward`` / ``GFASTKAN_Nodes.forward`` (node_classification_clean/models.py:192-203,
-    :246-257) for conv_type in {'gcn','gin'}; dropout p=0."""
+    :246-257) for conv_type in {'gcn','gin','gat'}; dropout p=0."""
     feats = [x]
     n_mp = _count_layers(sd, "bns.", "weight")
     for l in range(n_mp):
@@ -263,6 +293,10 @@ def node_model_forward(sd: Dict[str, Tensor], conv_type: str, x: Tensor, edge_in
             x = gcn_conv(x, edge_index, lambda t: _kan_or_fast_layer(sd, p + "lin.", t), sd[p + "bias"].to(x.dtype))
         elif conv_type == "gin":
             x = gin_conv(x, edge_index, lambda t: _kan_or_fast_chain(sd, p + "nn.layers.", t), float(sd[p + "eps"]))
+        elif conv_type == "gat":
+            heads = sd[p + "att_src"].shape[1]
+            x = gat_conv(x, edge_index, lambda t: _kan_or_fast_layer(sd, p + "lin.", t), sd[p + "att_src"], sd[p + "att_dst"],
+                         sd[p + "bias"], heads)
         else:
             raise ValueError("unknown conv_type")
         x = batch_norm(sd, f"bns.{l}.", x, training)
@@ -298,6 +332,19 @@ def gc_kagcn_forward(sd: Dict[str, Tensor], data) -> Tensor:
         p = f"conv.{l}."
         x = F.silu(gcn_conv(x, data.edge_index, lambda t: _kan_or_fast_layer(sd, p + "lin.", t), sd[p + "bias"].to(x.dtype)))
     x = global_mean_pool(x, data.batch)
+    return F.log_softmax(_kan_or_fast_chain(sd, "readout.layers.", x), dim=1)
+
+
+def gc_kagat_forward(sd: Dict[str, Tensor], data) -> Tensor:
+    """graph_classification ``KAGAT.forward`` / ``FASTKAGAT.forward`` (models.py:205-216, :277-288):
+    (GAT conv -> silu) xL -> ADD pool -> 1-layer KAN -> log_softmax."""
+    x = data.x
+    for l in range(_count_layers(sd, "conv.", "bias")):
+        p = f"conv.{l}."
+        heads = sd[p + "att_src"].shape[1]
+        x = F.silu(gat_conv(x, data.edge_index, lambda t: _kan_or_fast_layer(sd, p + "lin.", t), sd[p + "att_src"], sd[p + "att_dst"],
+                            sd[p + "bias"], heads))
+    x = global_add_pool(x, data.batch)
     return F.log_softmax(_kan_or_fast_chain(sd, "readout.layers.", x), dim=1)
 
 

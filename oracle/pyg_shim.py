@@ -56,14 +56,22 @@ class GINEConv(GINConv):
 
 
 class GATConv(nn.Module):
-    """Out of scope; exists so that ``class KAGATConv(GATConv)`` can be defined."""
+    """PyG 2.5 GATConv with the defaults the reference uses (concat=True, negative_slope=0.2, dropout=0, add_self_loops=True,
+    bias=True, edge_dim=None): one shared projection ``lin`` (which KAGATConv / KAGAT_Layer replace by a KAN), ``att_src`` /
+    ``att_dst`` of shape (1, heads, out_channels), ``bias`` of heads * out_channels."""
 
     def __init__(self, in_channels, out_channels, heads=1, **kw):
         super().__init__()
-        self.lin = None
+        self.in_channels, self.out_channels, self.heads = in_channels, out_channels, heads
+        self.lin = nn.Linear(in_channels, heads * out_channels, bias=False)
+        self.att_src = nn.Parameter(torch.empty(1, heads, out_channels))
+        self.att_dst = nn.Parameter(torch.empty(1, heads, out_channels))
+        self.bias = nn.Parameter(torch.zeros(heads * out_channels))
+        nn.init.xavier_uniform_(self.att_src)
+        nn.init.xavier_uniform_(self.att_dst)
 
-    def forward(self, *a, **kw):
-        raise NotImplementedError("GAT variants are out of scope")
+    def forward(self, x, edge_index, edge_attr=None, size=None):
+        return K.gat_conv(x, edge_index, self.lin, self.att_src, self.att_dst, self.bias, self.heads)
 
 
 global_add_pool = K.global_add_pool

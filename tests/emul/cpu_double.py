@@ -79,6 +79,25 @@ def _gcn_edge_weight(csr, dinv_src, dinv_dst, edge_weight_csr=None):
     return dinv_src[col] * dinv_dst[row] * (row != col).float()
 
 
+def _gat_attention(h, csr, att_src, att_dst, heads, negative_slope=0.2):
+    # PyG GATConv coefficients on the CSR: existing self loops dropped (weight 0), one appended self loop per node
+    n = h.size(0)
+    c = h.size(1) // heads
+    hv = h.view(n, heads, c)
+    a_s = (hv * att_src.detach().view(1, heads, c)).sum(-1)
+    a_d = (hv * att_dst.detach().view(1, heads, c)).sum(-1)
+    row, col = _row_of_entry(csr), csr.col.long()
+    keep = row != col
+    e = F.leaky_relu(a_s[col] + a_d[row], negative_slope)                      # (nnz, H)
+    e_self = F.leaky_relu(a_s + a_d, negative_slope)                            # (n, H)
+    m = e_self.clone()
+    m = m.scatter_reduce(0, row[keep].unsqueeze(1).expand(-1, heads), e[keep], reduce="amax", include_self=True)
+    ex = torch.where(keep.unsqueeze(1), (e - m[row]).exp(), torch.zeros_like(e))
+    xs = (e_self - m).exp()
+    den = xs + torch.zeros(n, heads).index_add_(0, row, ex) + 1e-16
+    return (ex / den[row]).t().contiguous(), (xs / den).t().contiguous()
+
+
 def _gather_rows(x, index, out=None, num_rows=None):
     res = x[index.long()] if index is not None else x[: (x.size(0) if num_rows is None else num_rows)]
     if out is None:
@@ -208,7 +227,8 @@ def cpu_double():
     patch(ops, "tc_supported", lambda *a: False)
     for name, fn in (("csr_build", _csr_build), ("gcn_norm", _gcn_norm), ("gcn_degree", _gcn_degree), ("gcn_edge_weight", _gcn_edge_weight), ("gather_rows", _gather_rows), ("segment_ptr", _segment_ptr),
                      ("pack_kan_weights", _pack), ("fused_layer", _fused_layer), ("batchnorm_forward", _batchnorm_forward),
-                     ("log_softmax", lambda x: torch.log_softmax(x, dim=1)), ("layernorm_stats", _layernorm_stats)):
+                     ("log_softmax", lambda x: torch.log_softmax(x, dim=1)), ("layernorm_stats", _layernorm_stats),
+                     ("gat_attention", _gat_attention)):
         patch(ops, name, fn)
     for mod in (ekan, fastkan, conv, models_node, models_graph, models_regr):
         patch(mod, "_module_backend_guard", guard)

@@ -42,6 +42,8 @@ def oracle_run(meta, inputs, sd, dtype=torch.float32):
     data = K.Batch(x, inputs["edge_index"], inputs["batch"], ea)
     fam = meta["family"]
     if kind == "gc":
+        if fam.endswith("GAT"):
+            return K.gc_kagat_forward(sd, data)
         return (K.gc_kagin_forward(sd, data, meta.get("training", False)) if fam.endswith("GIN") else K.gc_kagcn_forward(sd, data))
     if kind == "gr":
         return (K.gr_kagin_forward(sd, data, meta.get("training", False), dtype=dtype) if fam.endswith("GIN")
@@ -69,10 +71,11 @@ def build_product_model(meta, sd, device="cuda"):
     elif kind == "node":
         if meta["fast"]:
             m = kb.GFASTKAN_Nodes(meta["conv_type"], meta["mp_layers"], meta["num_features"], meta["hidden"], meta["classes"],
-                                  skip=meta["skip"], grid_size=meta["G"], hidden_layers=meta["hidden_layers"])
+                                  skip=meta["skip"], grid_size=meta["G"], hidden_layers=meta["hidden_layers"], heads=meta.get("heads", 4))
         else:
             m = kb.GKAN_Nodes(meta["conv_type"], meta["mp_layers"], meta["num_features"], meta["hidden"], meta["classes"],
-                              skip=meta["skip"], grid_size=meta["G"], spline_order=meta["k"], hidden_layers=meta["hidden_layers"])
+                              skip=meta["skip"], grid_size=meta["G"], spline_order=meta["k"], hidden_layers=meta["hidden_layers"],
+                              heads=meta.get("heads", 4))
     elif kind == "gc":
         m = getattr(kb.models_graph, meta["family"])(*meta["args"])
     elif kind == "gr":

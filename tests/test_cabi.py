@@ -73,8 +73,10 @@ def test_unknown_and_out_of_scope_configurations_raise():
     import kagnn_b200 as kb
     with pytest.raises(ValueError, match="unknown conv_type"):
         kb.GKAN_Nodes("sage", 1, 3, 4, 2)
+    m = kb.GKAN_Nodes("gat", 1, 3, 4, 2, heads=2)               # the GAT flavour exists (inference); its non-default options do not
+    assert m.bns[0].num_features == 8 and m.lay_out.in_features == 3 + 8
     with pytest.raises(NotImplementedError):
-        kb.GKAN_Nodes("gat", 1, 3, 4, 2)
+        kb.GATConv(3, 4, heads=2, concat=False)
 
 
 def test_product_never_imports_the_oracle():
