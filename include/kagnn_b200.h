@@ -272,6 +272,19 @@ int kagnn_batchnorm_train_fwd(const float* x, int64_t ldx, int64_t num_rows, int
                               float* running_var_or_null, int32_t act, float* y, int64_t ldy, void* workspace,
                               size_t workspace_bytes, void* stream);
 
+/* Fused training-mode epilogue of a message-passing layer: y = dropout(bn(x)) of nc/models.py:196-198
+ * with batch statistics -- column statistics, then ONE pass that normalises, applies the affine, updates the running estimates
+ * and applies a Philox4x32-10 dropout mask keyed by (seed, element index); the mask is never stored, the backward regenerates it.
+ * p_drop in [0, 1).  Workspace: kagnn_bn_dropout_train_workspace(cols) bytes for either direction. */
+size_t kagnn_bn_dropout_train_workspace(int32_t num_cols);
+int kagnn_bn_dropout_train_fwd(const float* x, int64_t ldx, int64_t num_rows, int32_t num_cols, const float* weight_or_null,
+                               const float* bias_or_null, float eps, float momentum, float* running_mean_or_null,
+                               float* running_var_or_null, float p_drop, uint64_t seed, float* y, int64_t ldy, void* workspace,
+                               size_t workspace_bytes, void* stream);
+int kagnn_bn_dropout_train_bwd(const float* x, int64_t ldx, const float* dy, int64_t ld_dy, int64_t num_rows, int32_t num_cols,
+                               const float* weight_or_null, float eps, float p_drop, uint64_t seed, float* dx, int64_t ld_dx,
+                               float* d_weight_or_null, float* d_bias_or_null, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------------
  * Backward: what `loss.backward()` needs from the modules so that the reference's training
  * loops run (node_classification_clean/utils.py:125-132, graph_classification/graph_classification_utils.py:44-54).

@@ -96,6 +96,13 @@ _SIGNATURES = {
                                          C.c_void_p]),
     "kagnn_gather_rows_peer_ordered": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64,
                                                  C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "kagnn_bn_dropout_train_workspace": (C.c_size_t, [C.c_int32]),
+    "kagnn_bn_dropout_train_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
+                                             C.c_void_p, C.c_void_p, C.c_float, C.c_uint64, C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t,
+                                             C.c_void_p]),
+    "kagnn_bn_dropout_train_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_float,
+                                             C.c_float, C.c_uint64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                             C.c_void_p]),
     "kagnn_gat_scores": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p]),
     "kagnn_gat_edge_softmax": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_float,

@@ -209,6 +209,38 @@ def batch_norm_train(x: Tensor, bn) -> Tensor:
     return _BatchNormFn.apply(x, bn.weight, bn.bias, bn)
 
 
+class _BatchNormDropoutFn(torch.autograd.Function):
+    """dropout(bn(x)) with batch statistics as one fused epilogue; the Philox mask is a function of the seed, not a saved tensor."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, bn, p, seed):
+        x = _rowmajor(x)
+        y = ops.batchnorm_dropout_forward(x, bn, p, seed)
+        ctx.save_for_backward(x, weight if weight is not None else x.new_empty(0))
+        ctx.has_affine, ctx.eps, ctx.p, ctx.seed = weight is not None, bn.eps, p, seed
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dx, dw, db = ops.batchnorm_dropout_backward(x, _rowmajor(dy), weight if ctx.has_affine else None, ctx.eps, ctx.p, ctx.seed)
+        return dx, (dw if ctx.has_affine else None), (db if ctx.has_affine else None), None, None, None
+
+
+def new_dropout_seed() -> int:
+    """A 63-bit seed drawn from torch's CPU generator: reproducible under torch.manual_seed, no device synchronisation."""
+    return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+
+
+def batch_norm_dropout_train(x: Tensor, bn, p: float, needs_grad: bool = True) -> Tensor:
+    """``dropout(bn(x), p)`` in training mode (nc/models.py:197-198) through kagnn_bn_dropout_train_fwd / _bwd."""
+    seed = new_dropout_seed()
+    if needs_grad:
+        return _BatchNormDropoutFn.apply(x, bn.weight, bn.bias, bn, float(p), seed)
+    return ops.batchnorm_dropout_forward(x, bn, float(p), seed)
+
+
 class _SiluFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):

@@ -16,7 +16,7 @@ from . import autograd, ops
 from .conv import FASTKAGAT_Layer, FASTKAGCN_Layer, GINConv, KAGAT_Layer, KAGCN_Layer, make_fastkan, make_kan
 from .ekan import _module_backend_guard, eval_mode_detach_notice
 from .graph import get_graph
-from .models_node import _BNFold, bn_is_foldable, bn_unfused
+from .models_node import _BNFold, bn_is_foldable, bn_unfused, bn_dropout
 
 Tensor = torch.Tensor
 
@@ -75,7 +75,7 @@ class _GINGraphModel(nn.Module):
             if fus:
                 x = self._conv(i, x, g, self._folds[i].get(self.bn[i]), extra)
             else:
-                x = self.dropout(bn_unfused(self._conv(i, x, g, None, extra), self.bn[i], needs_grad))
+                x = bn_dropout(self._conv(i, x, g, None, extra), self.bn[i], self.dropout, needs_grad)
         return x
 
     def forward(self, data) -> Tensor:

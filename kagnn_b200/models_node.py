@@ -63,6 +63,14 @@ def _bn_eval(x: Tensor, bn: nn.BatchNorm1d) -> Tensor:
     return ops.fused_layer(ops.AggSpec(L.AGG_NONE, x), x.size(0), [], pre=fold)
 
 
+def bn_dropout(x: Tensor, bn: nn.BatchNorm1d, dropout: nn.Dropout, needs_grad: bool = False) -> Tensor:
+    """``dropout(bn(x))`` of the training loops (nc/models.py:197-198).  Batch-statistics BatchNorm followed by an active dropout
+    runs as the fused epilogue (kagnn_bn_dropout_train_fwd: Philox mask, never stored); every other combination as before."""
+    if dropout.training and dropout.p > 0.0 and (bn.training or bn.running_mean is None) and dropout.p < 1.0:
+        return autograd.batch_norm_dropout_train(x, bn, dropout.p, needs_grad)
+    return dropout(bn_unfused(x, bn, needs_grad))
+
+
 def bn_unfused(x: Tensor, bn: nn.BatchNorm1d, needs_grad: bool = False) -> Tensor:
     """BatchNorm1d as its own launches: batch statistics (training) or the folded affine (eval)."""
     batch_stats = bn.training or bn.running_mean is None
@@ -134,8 +142,7 @@ class _NodeModel(nn.Module):
         feats = [x]
         for conv, bn in zip(self.convs, self.bns):
             x = conv(x, g)
-            x = bn_unfused(x, bn, needs_grad)
-            x = self.dropout(x)
+            x = bn_dropout(x, bn, self.dropout, needs_grad)
             feats.append(x)
         if self.skip:
             x = torch.cat(feats, dim=1)

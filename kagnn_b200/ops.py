@@ -291,6 +291,54 @@ def batchnorm_forward(x: Tensor, bn, act: int = L.ACT_NONE) -> Tensor:
     return y
 
 
+def _bn_momentum(bn) -> float:
+    if bn.momentum is None and bn.track_running_stats and bn.running_mean is not None:
+        return 1.0 / float(int(bn.num_batches_tracked) + 1)                  # cumulative moving average
+    return 0.0 if bn.momentum is None else float(bn.momentum)
+
+
+@_on_device
+def batchnorm_dropout_forward(x: Tensor, bn, p: float, seed: int) -> Tensor:
+    """``dropout(bn(x), p)`` in training mode as two launches (kagnn_bn_dropout_train_fwd): batch statistics, running estimates
+    updated like torch does, Philox mask keyed by ``seed`` (regenerated by ``batchnorm_dropout_backward``)."""
+    global launch_count
+    ldx = _rows(x, "x")
+    n, c = x.shape
+    if n == 0:
+        return x.clone()
+    track = bn.training and bn.track_running_stats and bn.running_mean is not None
+    y = torch.empty(n, c, dtype=torch.float32, device=x.device)
+    wbytes = L.lib().kagnn_bn_dropout_train_workspace(c)
+    ws = torch.empty(wbytes, dtype=torch.uint8, device=x.device)
+    L.check(L.lib().kagnn_bn_dropout_train_fwd(
+        _p(x), ldx, n, c, _p(bn.weight.detach()) if bn.weight is not None else None, _p(bn.bias.detach()) if bn.bias is not None else None,
+        float(bn.eps), _bn_momentum(bn), _p(bn.running_mean) if track else None, _p(bn.running_var) if track else None, float(p),
+        int(seed) & 0xFFFFFFFFFFFFFFFF, _p(y), _rows(y, "y"), _p(ws), wbytes, _stream()), "bn_dropout_train_fwd")
+    if track:
+        bn.num_batches_tracked += 1
+        torch.autograd.graph.increment_version(bn.running_mean)
+        torch.autograd.graph.increment_version(bn.running_var)
+    launch_count += 3
+    return y
+
+
+@_on_device
+def batchnorm_dropout_backward(x: Tensor, dy: Tensor, weight: Optional[Tensor], eps: float, p: float, seed: int):
+    """Backward of ``batchnorm_dropout_forward`` -> (dx, d weight, d bias) (kagnn_bn_dropout_train_bwd)."""
+    global launch_count
+    n, c = x.shape
+    dx = torch.empty(n, c, dtype=torch.float32, device=x.device)
+    dw = torch.empty(c, dtype=torch.float32, device=x.device)
+    db = torch.empty(c, dtype=torch.float32, device=x.device)
+    wbytes = L.lib().kagnn_bn_dropout_train_workspace(c)
+    ws = torch.empty(wbytes, dtype=torch.uint8, device=x.device)
+    L.check(L.lib().kagnn_bn_dropout_train_bwd(_p(x), _rows(x, "x"), _p(dy), _rows(dy, "dy"), n, c, _p(weight.detach()) if weight is not None else None,
+                                               float(eps), float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, _p(dx), _rows(dx, "dx"), _p(dw), _p(db),
+                                               _p(ws), wbytes, _stream()), "bn_dropout_train_bwd")
+    launch_count += 3
+    return dx, dw, db
+
+
 @_on_device
 def gather_rows_peer(peer_x: Tensor, ldx: int, rows_per_rank: int, ids: Tensor, num_cols: int, out: Optional[Tensor] = None) -> Tensor:
     """out[r] = row ids[r] % rows_per_rank of rank ids[r] // rows_per_rank, pulled over NVLink (kagnn_gather_rows_peer)."""
