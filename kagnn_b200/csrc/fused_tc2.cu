@@ -100,12 +100,22 @@ constexpr int FPW = 8 / WGT;                 // features per warpgroup per splin
 #ifndef KAGNN_TC2_STACK4
 #define KAGNN_TC2_STACK4 1
 #endif
+#ifndef KAGNN_TC2_HALF
+#define KAGNN_TC2_HALF 1                     // two rows per load for units of at most 64 columns (gather_unit_half)
+#endif
 #ifndef KAGNN_TC2_NOMATH
 #define KAGNN_TC2_NOMATH 0                   // development probe: producers skip the basis expansion (results are wrong)
 #endif
 // arrivals on full[s]: every producer thread (or one elected lane per producer warp) + the W loader's expect_tx
 constexpr int FULL_ARRIVALS = (KAGNN_TC2_ELECT_ARRIVE ? NPW / CPR : NPW / CPR * 32) + 1;
-constexpr int NGW = 8;                       // gather warps
+#ifndef KAGNN_TC2_NGW
+#define KAGNN_TC2_NGW 8
+#endif
+constexpr int NGW = KAGNN_TC2_NGW;           // gather warps (8 or 16; NPW + NGW = 24: six warpgroups + the MMA / loader warpgroup)
+static_assert(NPW + NGW == 24 && (NGW == 8 || NGW == 16), "role split");
+// registers after setmaxnreg (launch: 72 per thread, 896 threads): 16 producer + 8 gather warps -> producers 72, gather 88;
+// 8 producer + 16 gather warps -> producers 80, gather 80; the MMA / loader warpgroup gives up the difference either way
+constexpr int REGS_PROD = NPW == 16 ? 72 : 80, REGS_GATHER = NGW == 8 ? 88 : 80, REGS_AUX = NPW == 16 ? 40 : 24;
 constexpr int NTHREADS = (NPW + NGW + 4) * 32;   // + MMA, W loader and two idle warps (whole warpgroups for setmaxnreg)
 constexpr int WARP_MMA = NPW + NGW;
 constexpr int WARP_LOAD = NPW + NGW + 1;
@@ -624,7 +634,7 @@ __device__ __forceinline__ void gather_unit_fast(const Tc2Params& p, long long r
             any_hub = any_hub || tile_hub[k] != 0u;
         }
     }
-    const uint32_t my_hub = any_hub ? ((tile_hub[rl0 >> 5] >> (rl0 & 31)) & 0xffffu) : 0u;
+    const uint32_t my_hub = any_hub ? ((tile_hub[rl0 >> 5] >> (rl0 & 31)) & ((1u << RPW) - 1u)) : 0u;
     // virtual start of every row = exclusive prefix sum of the rows' list lengths (self entry + the CSR entries it keeps)
     int vs = rp + self1 * min(lane, RPW);                  // no hub in the tile: list positions follow the CSR directly
     if (any_hub) {
@@ -830,6 +840,185 @@ __device__ __forceinline__ void gather_unit_fast(const Tc2Params& p, long long r
                 os = 1.0f / (float)max(__shfl_sync(0xffffffffu, rp, rr + 1) - __shfl_sync(0xffffffffu, rp, rr), 1);
             if (GOUT ? !(cv0 && rv) : !cin0) continue;
             float4 t = *reinterpret_cast<const float4*>(dst0 + (long long)rr * xld);
+            float o[4] = {t.x * os, t.y * os, t.z * os, t.w * os};
+            const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (p.has_pre) {
+                    o[i] = fmaf(o[i], scv[i], shv[i]);
+                    if (pre_silu) o[i] = __fdividef(o[i], 1.0f + ex2_approx(-kLog2e * o[i]));
+                }
+                if (!(cv0 && rv)) o[i] = 0.f;
+            }
+            *reinterpret_cast<float4*>(dst0 + (long long)rr * xld) = make_float4(o[0], o[1], o[2], o[3]);
+            if (!GOUT && p.agg_out && rv && cv0) {
+                float* g = p.agg_out + r * p.ld_agg_out + c0 + cl;
+                if (out_vec) *reinterpret_cast<float4*>(g) = make_float4(o[0], o[1], o[2], o[3]);
+                else { g[0] = o[0]; g[1] = o[1]; g[2] = o[2]; g[3] = o[3]; }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Two rows per load (units of at most 64 columns).  gather_unit_fast gives every lane 4 columns of ONE source row, so a 64-column
+// unit (hidden width 64: two of the three GIN layers of the arxiv-shaped model) keeps half the warp idle in every 128-bit load.
+// Here the flattened list is a list of entry PAIRS: lanes 0..15 read the pair's first row, lanes 16..31 its second, the two halves
+// accumulate separately and meet (one shuffle-add per register) when the destination row is finished.  A row's list
+// [self, nbr_0, nbr_1, ...] is padded to an even length with a zero row, so a pair never straddles two destination rows and the
+// bookkeeping of the flattened list carries over with "entry" read as "pair".  Metadata: lane L describes slot (L & 1) of pair
+// (L >> 1) of the current batch of 16 pairs, so one pointer shuffle per lane fetches "my half's" row of pair j from lane
+// 2 j + (lane >> 4).  Tiles with hub rows (cooperative pass) stay on gather_unit_fast.
+// ---------------------------------------------------------------------------------------------------------------------
+template <bool WEIGHTED, bool GOUT = false, int U_ = KAGNN_TC2_GATHER_U>
+__device__ __forceinline__ void gather_unit_half(const Tc2Params& p, long long row0, int c0, int ucols, float* __restrict__ xsu, int gw,
+                                                 int lane) {
+    constexpr int U = U_;
+    constexpr unsigned FULL = 0xffffffffu;
+    const KagnnAggregate& a = p.agg;
+    const int F = a.num_cols, mode = a.mode, xld = p.xld;
+    const bool segment = (mode == KAGNN_AGG_SEGMENT_SUM) || (mode == KAGNN_AGG_SEGMENT_MEAN);
+    const int rl0 = gw * RPW;
+    const int half = lane >> 4, cl = 4 * (lane & 15);
+    const bool cin0 = cl < ucols;
+    const bool cv0 = cin0 && (c0 + cl) < F;
+    const int cload = cv0 ? (c0 + cl) : 0;
+    const bool storer = half == 0;                         // after the halves have met, lanes 0..15 hold (and park) the row
+    const int self1 = segment ? 0 : 1;
+    int rp = 0;
+    if (mode != KAGNN_AGG_NONE) {
+        long long r = row0 + rl0 + min(lane, RPW);
+        if (r > p.num_rows) r = p.num_rows;
+        rp = __ldg(a.rowptr + r);
+    }
+    // pairs per row and their exclusive prefix sum (lane RPW holds the total)
+    const int rp_next = __shfl_down_sync(FULL, rp, 1);
+    int len = 0;
+    if (lane < RPW) len = (self1 + (rp_next - rp) + 1) >> 1;
+    int incl = len;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const int vs = incl - len;
+    const int v_end = __shfl_sync(FULL, vs, RPW);
+    int cur = 0, cur_vend = __shfl_sync(FULL, vs, 1);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float* const dst0 = xsu + rl0 * xld + cl;
+    auto entry_row = [&](int j) -> const float* {
+        if (a.src_index) j = __ldg(a.src_index + j);
+        if (a.peer_x) {
+            const int owner = j / (int)a.rows_per_rank;
+            return reinterpret_cast<const float*>(__ldg(reinterpret_cast<const unsigned long long*>(a.peer_x) + owner)) +
+                   (long long)(j - owner * (int)a.rows_per_rank) * a.ldx;
+        }
+        return src_row(a, j);
+    };
+    auto finish_row = [&]() {
+        acc[0] += __shfl_xor_sync(FULL, acc[0], 16);
+        acc[1] += __shfl_xor_sync(FULL, acc[1], 16);
+        acc[2] += __shfl_xor_sync(FULL, acc[2], 16);
+        acc[3] += __shfl_xor_sync(FULL, acc[3], 16);
+        if (storer && (GOUT ? (cv0 && row0 + rl0 + cur < p.num_rows) : cin0)) {
+            const float4 o = cv0 ? make_float4(acc[0], acc[1], acc[2], acc[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(dst0 + (long long)cur * xld) = o;
+        }
+        acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+        ++cur;
+        cur_vend = (cur < RPW) ? __shfl_sync(FULL, vs, min(cur + 1, RPW)) : 0x7fffffff;
+    };
+    // lane L <-> slot (L & 1) of pair vbase + (L >> 1): source-row pointer and weight of that list entry (zero row, weight 0 for
+    // the pad slot of an odd list and past the end); index / weight loads are issued one batch ahead
+    struct Meta {
+        int r, k, col;
+        float w;
+        bool on, self_;
+    };
+    auto prep = [&](int vbase) {
+        Meta m;
+        const int ve = vbase + (lane >> 1);
+        int r = 0;
+#pragma unroll
+        for (int step = RPW / 2; step >= 1; step >>= 1) {
+            const int t = __shfl_sync(FULL, vs, r + step);
+            r += (t <= ve) ? step : 0;
+        }
+        const int vs_r = __shfl_sync(FULL, vs, r), rp_r = __shfl_sync(FULL, rp, r), rp_n = __shfl_sync(FULL, rp, r + 1);
+        m.r = r;
+        m.k = 2 * (ve - vs_r) + (lane & 1);                // position in the row's list [self, nbr_0, ...]
+        m.on = ve < v_end && m.k < self1 + (rp_n - rp_r);
+        m.self_ = (self1 != 0) && m.k == 0;
+        m.col = rp_r + m.k - self1;                        // CSR entry id (also the row id in the SEGMENT modes)
+        m.w = 1.0f;
+        if (m.on && !m.self_) {
+            const int e = m.col;
+            if (a.col) m.col = __ldg(a.col + e);
+            if (WEIGHTED) m.w = __ldg(a.edge_weight + e);
+        }
+        return m;
+    };
+
+    Meta nxt = prep(0);
+#pragma unroll 1
+    for (int vbase = 0; vbase < v_end; vbase += 16) {
+        const Meta m = nxt;
+        if (vbase + 16 < v_end) nxt = prep(vbase + 16);
+        const float* my_row = g_zero_row;
+        float my_w = 0.0f;
+        if (m.on) {
+            if (m.self_) {
+                const long long rg = row0 + rl0 + m.r;
+                if (rg < p.num_rows) {
+                    const long long sr = a.src_index ? (long long)__ldg(a.src_index + rg) : rg;
+                    my_row = a.x + sr * a.ldx;
+                    my_w = (mode == KAGNN_AGG_NONE) ? 1.0f : a.self_scale;
+                    if (WEIGHTED && a.self_weight) my_w = __ldg(a.self_weight + rg);
+                }
+            } else {
+                my_row = entry_row(m.col);
+                my_w = m.w;
+            }
+        }
+        const int cnt = min(16, v_end - vbase);
+#pragma unroll 1
+        for (int t0 = 0; t0 < cnt; t0 += U) {
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(shfl_ptr(my_row, min(2 * (t0 + u), 30) + half) + cload));
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = vbase + t0 + u;
+                float w = __shfl_sync(FULL, my_w, min(2 * (t0 + u), 30) + half);
+                if (t0 + u >= cnt) w = 0.f;                // pairs past the end of the list (their rows were loaded from valid lanes)
+                while (e >= cur_vend && cur < RPW) finish_row();
+                acc[0] = fmaf(w, v[u].x, acc[0]);
+                acc[1] = fmaf(w, v[u].y, acc[1]);
+                acc[2] = fmaf(w, v[u].z, acc[2]);
+                acc[3] = fmaf(w, v[u].w, acc[3]);
+            }
+        }
+    }
+    while (cur < RPW) finish_row();
+
+    const bool pre_silu = p.has_pre && p.pre.act == KAGNN_ACT_SILU;
+    if (storer && (p.has_pre || (!GOUT && p.agg_out) || mode == KAGNN_AGG_SEGMENT_MEAN)) {
+        // post-pass: lanes 0..15 revisit the values they parked themselves (no synchronisation needed)
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.has_pre && cv0) {
+            const int c = c0 + cl;
+            if (p.pre.scale) sc = make_float4(__ldg(p.pre.scale + c), __ldg(p.pre.scale + c + 1), __ldg(p.pre.scale + c + 2), __ldg(p.pre.scale + c + 3));
+            if (p.pre.shift) sh = make_float4(__ldg(p.pre.shift + c), __ldg(p.pre.shift + c + 1), __ldg(p.pre.shift + c + 2), __ldg(p.pre.shift + c + 3));
+        }
+        const bool out_vec = p.agg_out && ((reinterpret_cast<uintptr_t>(p.agg_out) & 15u) == 0) && (p.ld_agg_out % 4 == 0);
+#pragma unroll 1
+        for (int rr = 0; rr < RPW; ++rr) {
+            const long long r = row0 + rl0 + rr;
+            const bool rv = r < p.num_rows;
+            float os = 1.0f;
+            if (mode == KAGNN_AGG_SEGMENT_MEAN && rv) os = 1.0f / (float)max(__ldg(a.rowptr + r + 1) - __ldg(a.rowptr + r), 1);
+            if (GOUT ? !(cv0 && rv) : !cin0) continue;
+            const float4 t = *reinterpret_cast<const float4*>(dst0 + (long long)rr * xld);
             float o[4] = {t.x * os, t.y * os, t.z * os, t.w * os};
             const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
 #pragma unroll
@@ -1105,8 +1294,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < NPW) {
-        // register budget (launch: 72 per thread): producers keep 72, the MMA / loader / idle warpgroup drops to 40 and hands its
-        // 32 x 128 registers to the gather warps (72 -> 88)
+        // register budget (launch: 72 per thread): see REGS_PROD / REGS_GATHER / REGS_AUX
+        if (REGS_PROD > 72) tc::reg_inc<REGS_PROD>();
         // ============================== BASIS PRODUCERS / EPILOGUE =============================================
         // Every warpgroup works on EVERY chunk: warpgroup wg expands FPW features of a spline chunk (every NWG-th octet of a
         // SiLU chunk), so the parts of a chunk are produced concurrently and the groups stay balanced.
@@ -1406,7 +1595,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
         if (have_pend) epilogue(pend_row0, pend_lc);
     } else if (warp < NPW + NGW) {
         // ========================================= GATHER ======================================================
-        if (NPW == 16) tc::reg_inc<88>();
+        if (REGS_GATHER > 72) tc::reg_inc<REGS_GATHER>();
         const int gw = warp - NPW;
         const bool vec = (p.agg.num_cols % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.agg.x) & 15u) == 0) && (p.agg.ldx % 4 == 0) &&
                          (!p.agg.x_halo || (((reinterpret_cast<uintptr_t>(p.agg.x_halo) & 15u) == 0) && (p.agg.ld_halo % 4 == 0))) &&
@@ -1445,25 +1634,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                 if (lane == 0 && gw == 0) TRL(6, uc, 1);
                 float* xsu = xs + (size_t)u * p.unit_floats;
                 const int c0 = ub * p.uw, ucols = min(p.uw, F_pad - c0);
-                // asynchronous gather: 64-column units of a GIN / GCN layer (p.ag, decided by the launcher), unless the tile holds a
-                // hub row (more than HUB_T entries), which the register gather sums cooperatively
-                bool gpr = false;
-                if (KAGNN_TC2_AG && p.ag) {
-                    gpr = true;
-                    if (KAGNN_TC2_HUB) {
+                // does the tile hold a hub row (more than HUB_T entries)?  Those are summed cooperatively by gather_unit_fast; the
+                // decision is tile-uniform (every gather warp evaluates the same four ballots)
+                const bool csr_mode = p.agg.mode == KAGNN_AGG_GIN || p.agg.mode == KAGNN_AGG_WEIGHTED;
+                const bool half_ok = KAGNN_TC2_HALF && vec && head_ok && !gine && !plain_copy && ucols <= 64;
+                bool tile_has_hub = false;
+                if (KAGNN_TC2_HUB && csr_mode && ((KAGNN_TC2_AG && p.ag) || half_ok)) {
 #pragma unroll
-                        for (int k4 = 0; k4 < 4; ++k4) {
-                            const long long rr = row0 + 32 * k4 + lane;
-                            int d = 0;
-                            if (rr < p.num_rows) d = __ldg(p.agg.rowptr + rr + 1) - __ldg(p.agg.rowptr + rr);
-                            if (__any_sync(0xffffffffu, d > HUB_T)) gpr = false;          // tile-uniform
-                        }
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        const long long rr = row0 + 32 * k4 + lane;
+                        int d = 0;
+                        if (rr < p.num_rows) d = __ldg(p.agg.rowptr + rr + 1) - __ldg(p.agg.rowptr + rr);
+                        if (__any_sync(0xffffffffu, d > HUB_T)) tile_has_hub = true;
                     }
-                    if (gpr) {
-                        const uint32_t st = tc::smem_u32(ag_stage) + (uint32_t)(gw * AG_WARP_BYTES);
-                        if (p.agg.mode == KAGNN_AGG_WEIGHTED || p.agg.self_scale != 1.0f) gather_unit_ag<true>(p, row0, c0, xsu, gw, lane, st);
-                        else gather_unit_ag<false>(p, row0, c0, xsu, gw, lane, st);
-                    }
+                }
+                bool gpr = false;
+                if (KAGNN_TC2_AG && p.ag && !tile_has_hub) {
+                    // asynchronous (cp.async ring) gather: 64-column units of a GIN / GCN layer (compiled out by default)
+                    gpr = true;
+                    const uint32_t st = tc::smem_u32(ag_stage) + (uint32_t)(gw * AG_WARP_BYTES);
+                    if (p.agg.mode == KAGNN_AGG_WEIGHTED || p.agg.self_scale != 1.0f) gather_unit_ag<true>(p, row0, c0, xsu, gw, lane, st);
+                    else gather_unit_ag<false>(p, row0, c0, xsu, gw, lane, st);
+                } else if (half_ok && !tile_has_hub) {
+                    // units of at most 64 columns: two source rows per 128-bit load instruction
+                    gpr = true;
+                    if (p.agg.mode == KAGNN_AGG_WEIGHTED) gather_unit_half<true>(p, row0, c0, ucols, xsu, gw, lane);
+                    else gather_unit_half<false>(p, row0, c0, ucols, xsu, gw, lane);
                 }
                 if (gpr) {
                 } else if (vec && head_ok) {
@@ -1481,7 +1677,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
             }
         }
     } else if (warp == WARP_MMA) {
-        if (NPW == 16) tc::reg_dec<40>();
+        tc::reg_dec<REGS_AUX>();
         // ========================================= MMA ISSUER ==================================================
         // The whole warp walks the loops (uniform control flow, descriptor arithmetic on the uniform datapath); one elected
         // lane issues.  Per K = 16 step: stacked layers (N_pad <= 64) issue A_hi.[W_hi | W_lo] (N = 2 N_pad) + A_lo.W_hi,
@@ -1540,7 +1736,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
         }
     } else {
         // ========================================== W LOADER (+ two idle warps) ================================
-        if (NPW == 16) tc::reg_dec<40>();
+        tc::reg_dec<REGS_AUX>();
         if (warp == WARP_LOAD + 1 && KAGNN_TC2_PREFETCH_DIST > 0) {
             // ------------------------------------ L2 PREFETCHER ------------------------------------------------
             // One otherwise idle warp walks the CSR a few tiles ahead of the gather warps and asks L2 for the self and
@@ -1604,7 +1800,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
 // without a readout): the same flattened-list gather, one warp per 16 destination rows, result (after mean scale / pre-affine)
 // written straight to agg_out.  HBM-bound: 16 independent 128-bit row loads in flight per warp, grid = all row groups.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int AGG_WARPS = 8;
+constexpr int AGG_WARPS = NGW;
 // Occupancy of the aggregation-only kernel: its limiter on a graph that does not fit L2 (R-MAT 10 M nodes) is memory-level
 // parallelism, and skewed degrees leave warps of a block idle behind its heaviest one, so more resident blocks with fewer loads
 // each win (measured on the 10 M-node / 100 M-edge R-MAT KAGCN layer: 11.5 ms at 3 blocks x 8 loads -> 10.0 ms at 5 x 4).
@@ -1614,7 +1810,7 @@ constexpr int AGG_WARPS = 8;
 #ifndef KAGNN_AGG_U
 #define KAGNN_AGG_U 4
 #endif
-__global__ void __launch_bounds__(AGG_WARPS * 32, KAGNN_AGG_MINB) aggregate_only_kernel(const __grid_constant__ Tc2Params p) {
+__global__ void __launch_bounds__(AGG_WARPS * 32, AGG_WARPS == 8 ? KAGNN_AGG_MINB : 2) aggregate_only_kernel(const __grid_constant__ Tc2Params p) {
     __shared__ HubScratch hub;
     const int lane = threadIdx.x & 31, gw = threadIdx.x >> 5;
     const int F = p.agg.num_cols;
@@ -1623,7 +1819,20 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, KAGNN_AGG_MINB) aggregate_only
         for (int c0 = 0; c0 < F; c0 += 128) {
             float* out = p.agg_out + row0 * p.ld_agg_out + c0;
             const int ucols = min(128, F - c0);
-            if (p.agg.mode == KAGNN_AGG_WEIGHTED) gather_unit_fast<true, true, KAGNN_AGG_U>(p, row0, c0, ucols, out, gw, lane, &hub);
+            bool half = KAGNN_TC2_HALF && ucols <= 64;
+            if (half && KAGNN_TC2_HUB && (p.agg.mode == KAGNN_AGG_GIN || p.agg.mode == KAGNN_AGG_WEIGHTED)) {
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {
+                    const long long rr = row0 + 32 * k4 + lane;
+                    int d = 0;
+                    if (rr < p.num_rows) d = __ldg(p.agg.rowptr + rr + 1) - __ldg(p.agg.rowptr + rr);
+                    if (__any_sync(0xffffffffu, d > HUB_T)) half = false;       // block-uniform: the cooperative hub pass needs every warp
+                }
+            }
+            if (half) {
+                if (p.agg.mode == KAGNN_AGG_WEIGHTED) gather_unit_half<true, true, KAGNN_AGG_U>(p, row0, c0, ucols, out, gw, lane);
+                else gather_unit_half<false, true, KAGNN_AGG_U>(p, row0, c0, ucols, out, gw, lane);
+            } else if (p.agg.mode == KAGNN_AGG_WEIGHTED) gather_unit_fast<true, true, KAGNN_AGG_U>(p, row0, c0, ucols, out, gw, lane, &hub);
             else gather_unit_fast<false, true, KAGNN_AGG_U>(p, row0, c0, ucols, out, gw, lane, &hub);
         }
     }

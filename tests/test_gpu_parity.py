@@ -382,7 +382,9 @@ def test_strided_inputs_are_accepted():
         assert torch.equal(conv(xt, ei), conv(xt.contiguous(), ei))
         xs = wide[:, 3:51]                             # row stride 100, misaligned start
         assert torch.equal(lay(xs), lay(xs.contiguous()))
-        assert torch.equal(conv(xs, ei), conv(xs.contiguous(), ei))
+        # the aligned copy takes the 128-bit gather (pairs of rows per load, the halves' partial sums meet at the row end), the
+        # misaligned view the scalar one: the same neighbours summed in a different, equally deterministic order
+        assert K.rel_err(conv(xs, ei).cpu(), conv(xs.contiguous(), ei).cpu()) <= 2e-5
         xe = wide[:, ::2][:, :48]                      # column stride 2
         assert torch.equal(lay(xe), lay(xe.contiguous()))
 
