@@ -40,6 +40,9 @@ int kagnn_fused_fwd_tc(const KagnnAggregate* agg, int64_t num_rows, const KagnnA
 int kagnn_fused_fwd_tc2(const KagnnAggregate* agg, int64_t num_rows, const KagnnAffine* pre, float* agg_out,
                         int64_t ld_agg_out, int32_t n_layers, const KagnnKanLayer* layers, const KagnnAffine* post, float* y,
                         int64_t ldy, cudaStream_t stream);
+int kagnn_fused_fwd_tc2_g16(const KagnnAggregate* agg, int64_t num_rows, const KagnnAffine* pre, float* agg_out,
+                            int64_t ld_agg_out, int32_t n_layers, const KagnnKanLayer* layers, const KagnnAffine* post, float* y,
+                            int64_t ldy, cudaStream_t stream);
 int kagnn_aggregate_only_tc2(const KagnnAggregate* agg, int64_t num_rows, const KagnnAffine* pre, float* agg_out,
                              int64_t ld_agg_out, cudaStream_t stream);
 // shared-memory-tiled B-spline backward (backward_tiled.cu); KAGNN_EUNSUPPORTED -> the general kernels of backward.cu

@@ -28,7 +28,7 @@
 
 // Optional timeline trace of CTA 0 (development builds only: KAGNN_NVCC_EXTRA="-DKAGNN_TRACE=1"): clock stamps per role,
 // event counter and event kind into a caller-provided buffer (scripts/trace_tc2.py).
-#ifdef KAGNN_TRACE
+#if defined(KAGNN_TRACE) && !defined(KAGNN_TC2_VARIANT_G16)
 __device__ unsigned long long* g_trace = nullptr;
 #define TR(role, k, evt)                                                                                           \
     do {                                                                                                             \
@@ -102,6 +102,9 @@ constexpr int FPW = 8 / WGT;                 // features per warpgroup per splin
 #endif
 #ifndef KAGNN_TC2_HALF
 #define KAGNN_TC2_HALF 1                     // two rows per load for units of at most 64 columns (gather_unit_half)
+#endif
+#ifndef KAGNN_TC2_USE_G16
+#define KAGNN_TC2_USE_G16 1                  // launches with a CSR gather run the 8-producer / 16-gather-warp build (fused_tc2_g16.cu)
 #endif
 #ifndef KAGNN_TC2_NOMATH
 #define KAGNN_TC2_NOMATH 0                   // development probe: producers skip the basis expansion (results are wrong)
@@ -1800,6 +1803,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
 // without a readout): the same flattened-list gather, one warp per 16 destination rows, result (after mean scale / pre-affine)
 // written straight to agg_out.  HBM-bound: 16 independent 128-bit row loads in flight per warp, grid = all row groups.
 // ---------------------------------------------------------------------------------------------------------------------
+#ifndef KAGNN_TC2_VARIANT_G16
 constexpr int AGG_WARPS = NGW;
 // Occupancy of the aggregation-only kernel: its limiter on a graph that does not fit L2 (R-MAT 10 M nodes) is memory-level
 // parallelism, and skewed degrees leave warps of a block idle behind its heaviest one, so more resident blocks with fewer loads
@@ -1838,10 +1842,13 @@ __global__ void __launch_bounds__(AGG_WARPS * 32, AGG_WARPS == 8 ? KAGNN_AGG_MIN
     }
 }
 
+#endif  // !KAGNN_TC2_VARIANT_G16
+
 inline int ceil16(int v) { return (v + 15) & ~15; }
 
 }  // namespace
 
+#ifndef KAGNN_TC2_VARIANT_G16
 int kagnn_aggregate_only_tc2(const KagnnAggregate* agg, int64_t num_rows, const KagnnAffine* pre, float* agg_out,
                              int64_t ld_agg_out, cudaStream_t stream) {
     // shapes the 128-bit flattened-list gather serves; everything else stays on the general kernel
@@ -1876,10 +1883,26 @@ int kagnn_aggregate_only_tc2(const KagnnAggregate* agg, int64_t num_rows, const 
     return KAGNN_OK;
 }
 
-int kagnn_fused_fwd_tc2(const KagnnAggregate* agg, int64_t num_rows, const KagnnAffine* pre, float* agg_out,
-                        int64_t ld_agg_out, int32_t n_layers, const KagnnKanLayer* layers, const KagnnAffine* post, float* y,
-                        int64_t ldy, cudaStream_t stream) {
+#endif  // !KAGNN_TC2_VARIANT_G16
+
+// This file is compiled twice (fused_tc2_g16.cu includes it with the other role split): 16 basis-producer + 8 gather warps for
+// launches without a neighbour gather (bare KAN chains, the read-out: producer-bound), 8 producer + 16 gather warps for the
+// launches that gather over a CSR (GIN / GCN / GINE: bound by the memory-level parallelism of the gather).  Measured on the
+// arxiv-shaped layers: gather layers 0.249 -> 0.226 ms (128 wide) and 0.185 -> 0.167 ms (64 wide) with 16 gather warps, plain
+// layers 0.157 -> 0.179 ms and the read-out 0.226 -> 0.267 ms -- hence one variant each.
+#ifdef KAGNN_TC2_VARIANT_G16
+#define KAGNN_TC2_ENTRY kagnn_fused_fwd_tc2_g16
+#else
+#define KAGNN_TC2_ENTRY kagnn_fused_fwd_tc2
+#endif
+int KAGNN_TC2_ENTRY(const KagnnAggregate* agg, int64_t num_rows, const KagnnAffine* pre, float* agg_out,
+                    int64_t ld_agg_out, int32_t n_layers, const KagnnKanLayer* layers, const KagnnAffine* post, float* y,
+                    int64_t ldy, cudaStream_t stream) {
     if (n_layers < 1 || n_layers > KAGNN_MAX_LAYERS) return KAGNN_EUNSUPPORTED;
+#if !defined(KAGNN_TC2_VARIANT_G16) && KAGNN_TC2_USE_G16
+    if (agg->mode == KAGNN_AGG_GIN || agg->mode == KAGNN_AGG_WEIGHTED || agg->mode == KAGNN_AGG_GINE)
+        return kagnn_fused_fwd_tc2_g16(agg, num_rows, pre, agg_out, ld_agg_out, n_layers, layers, post, y, ldy, stream);
+#endif
     DeviceProps props{};
     int rc = kagnn_get_props(&props);
     if (rc != KAGNN_OK) return rc;
