@@ -32,8 +32,9 @@ import torch  # noqa: E402
 
 N_NODES, N_EDGES, N_FEAT, HIDDEN, N_CLASSES, MP_LAYERS, KAN_DEPTH, GRID, ORDER = 169_343, 1_166_243, 128, 64, 40, 3, 2, 5, 3
 METRIC = "KAGNN-layer forward nodes/sec"
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture (profiles/README.md)
-NCU_TRAFFIC_BYTES = {"agg1[128]->64->64": 214_118_656, "agg1[64]->64->64": 64_955_648, "agg0[320]->40": 232_909_824}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+# (profiles/r2_ncu_full_summary.csv: 186.43+28.46 MB, 50.56+8.02 MB, 217.40+15.70 MB)
+NCU_TRAFFIC_BYTES = {"agg1[128]->64->64": 214_891_776, "agg1[64]->64->64": 58_577_664, "agg0[320]->40": 233_096_960}
 WORKLOAD = "ogbn-arxiv-shaped KAGIN (GKAN_Nodes gin, 3 layers, hidden 64, grid 5, order 3, KAN depth 2), fp32, eval"
 
 
@@ -212,7 +213,7 @@ def main():
     ap.add_argument("--config", default="arxiv", choices=["arxiv", "cora", "zinc", "mutag", "rmat"],
                     help="arxiv = the headline workload (BASELINE configs[1]); the others print the secondary measurement of that "
                          "configuration alone (scripts/bench_extras.py) as one JSON line")
-    ap.add_argument("--dist-mode", default="auto", choices=["auto", "peer", "pull", "pull_overlap", "halo"],
+    ap.add_argument("--dist-mode", default="auto", choices=["auto", "peer", "pull", "pull_overlap", "push", "halo"],
                     help="N > 1: 'peer' = in-kernel NVLink gather from symmetric memory, 'halo' = NCCL all-to-all per layer")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -409,6 +410,9 @@ def main():
         widths = N_FEAT + (MP_LAYERS - 1) * HIDDEN                       # row widths gathered by the three GIN layers: 128 + 64 + 64
         if runner.mode in ("pull", "pull_overlap"):
             rows, what = int(plan.n_halo), "distinct remote rows (pulled once per layer)"
+        elif runner.mode == "push":
+            rows, what = int(plan.n_halo), ("distinct remote rows: x pulled before layer 0, hidden rows pushed by their producer layer "
+                                            "(masked to the ranks that reference them)")
         elif runner.mode == "peer":
             col = plan.graph.col.long()
             rows = int(((col < rank * n_local) | (col >= (rank + 1) * n_local)).sum())
@@ -446,7 +450,7 @@ def main():
                    "l2": "flushed between iterations (512 MB memset)", "csr": "cached across steps (static graph)",
                    "parallelism": (f"node-range shards x{world}, " + ("remote rows gathered in-kernel over NVLink (symmetric memory), "
                                    "one device barrier per layer" if runner.mode == "peer" else ("distinct remote rows pulled over NVLink from symmetric memory "
-                                   "by one copy kernel per layer (no collective)" if runner.mode == "pull" else ("distinct remote rows pulled over NVLink by a copy kernel that runs concurrently with the layer (first-use order, progress counters)" if runner.mode == "pull_overlap" else "one NCCL halo all-to-all per layer"))))
+                                   "by one copy kernel per layer (no collective)" if runner.mode == "pull" else ("x halo pulled over NVLink before layer 0; hidden rows pushed into the peers' replicas by a relay warp of the producing layer's kernel (bulk copies, masked per row), one device barrier per layer" if runner.mode == "push" else ("distinct remote rows pulled over NVLink by a copy kernel that runs concurrently with the layer (first-use order, progress counters)" if runner.mode == "pull_overlap" else "one NCCL halo all-to-all per layer")))))
                    if dist_on else "single GPU",
                    "graph": "uniform random edges over all shards: (N-1)/N of the edges are cut" if dist_on else "uniform random edges"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "kernels": kernels, "roofline": roofline, "cpu_baseline": cpu,

@@ -133,6 +133,20 @@ typedef struct KagnnAggregate {
     const int32_t* halo_flags;
     int32_t halo_epoch;
     int32_t reserve_sms;
+    /* Node-sharded graphs, output rows PUSHED to the other ranks while the layer runs: besides y, every finished 128-row tile
+     * is copied row by row into push_y[i] + row * ld_push for the num_push peer-mapped destinations (DEVICE array of pointers to
+     * row 0 of THIS launch's rows inside each peer's replica of the layer output), by one otherwise idle warp per CTA that
+     * relays the rows through shared memory with bulk copies (posted NVLink writes: no round trip, so the transfer rides
+     * behind the tensor-core pipeline of the following tiles).  push_mask: optional, one byte per row, bit i set <=> peer i
+     * needs the row (NULL: every row goes to every peer).  The caller orders the ranks (a barrier between this launch and the
+     * peers' launches that read the replica).  Implemented by the pipelined tcgen05 kernel for outputs whose width is a multiple
+     * of 4 columns and at most 128, 16-byte aligned y / ldy / destinations; other kernels return KAGNN_EUNSUPPORTED.
+     * num_push == 0: not used.                                                                                              */
+    float* const* push_y;
+    const uint8_t* push_mask;
+    int64_t ld_push;
+    int32_t num_push;
+    int32_t _pad2;
 } KagnnAggregate;
 
 /* ---- library ------------------------------------------------------------------------------------ */

@@ -48,6 +48,7 @@ class KagnnAggregate(C.Structure):
         ("peer_x", C.c_void_p), ("rows_per_rank", C.c_int64), ("num_ranks", C.c_int32), ("num_head_cols", C.c_int32),
         ("x_head", C.c_void_p), ("ld_head", C.c_int64),
         ("halo_need", C.c_void_p), ("halo_flags", C.c_void_p), ("halo_epoch", C.c_int32), ("reserve_sms", C.c_int32),
+        ("push_y", C.c_void_p), ("push_mask", C.c_void_p), ("ld_push", C.c_int64), ("num_push", C.c_int32), ("_pad2", C.c_int32),
     ]
 
 

@@ -124,10 +124,11 @@ class GINConv(_MessagePassing):
 
     def _agg_spec(self, x: Tensor, g: GraphCSR, x_halo: Optional[Tensor] = None, peer_x: Optional[Tensor] = None,
                   rows_per_rank: int = 0, halo_need: Optional[Tensor] = None, halo_flags: Optional[Tensor] = None,
-                  halo_epoch: int = 0, reserve_sms: int = 0) -> ops.AggSpec:
+                  halo_epoch: int = 0, reserve_sms: int = 0, push_y: Optional[Tensor] = None, push_ld: int = 0,
+                  push_mask: Optional[Tensor] = None) -> ops.AggSpec:
         return ops.AggSpec(L.AGG_GIN, x, g.rowptr, g.col, self_scale=1.0 + self.eps_value(), x_halo=x_halo, peer_x=peer_x,
                            rows_per_rank=rows_per_rank, halo_need=halo_need, halo_flags=halo_flags, halo_epoch=halo_epoch,
-                           reserve_sms=reserve_sms)
+                           reserve_sms=reserve_sms, push_y=push_y, push_ld=push_ld, push_mask=push_mask)
 
     def forward(self, x: Tensor, edge_index, size=None, out: Optional[Tensor] = None,
                 post: Optional[ops.Affine] = None, **agg_kw) -> Tensor:

@@ -17,6 +17,7 @@ int kagnn_validate_fused_args(const KagnnAggregate* agg, int64_t num_rows, const
     if (!agg || num_rows < 0 || n_layers < 0 || n_layers > KAGNN_MAX_LAYERS) return KAGNN_EINVAL;
     if (n_layers > 0 && (!layers || !y)) return KAGNN_EINVAL;
     if (n_layers == 0 && !agg_out) return KAGNN_EINVAL;
+    if (agg->num_push && (n_layers == 0 || !agg->push_y || agg->num_push < 0 || agg->num_push > 8)) return KAGNN_EINVAL;   // the pushed rows are those of y
     if (agg->mode < KAGNN_AGG_NONE || agg->mode > KAGNN_AGG_SEGMENT_MEAN) return KAGNN_EINVAL;
     if (agg->num_cols <= 0 || !agg->x || agg->ldx < agg->num_cols - (agg->num_head_cols > 0 ? agg->num_head_cols : 0)) return KAGNN_EINVAL;
     if (agg->mode != KAGNN_AGG_NONE && !agg->rowptr) return KAGNN_EINVAL;
@@ -88,7 +89,7 @@ extern "C" int kagnn_fused_layer_fwd(const KagnnAggregate* agg, int64_t num_rows
                 }
                 if (rc != KAGNN_EUNSUPPORTED) return rc;
             }
-            if (agg->peer_x || agg->num_head_cols || agg->halo_flags) return KAGNN_EUNSUPPORTED;   // peer gather / two-part rows / in-flight halo: pipelined kernel only
+            if (agg->peer_x || agg->num_head_cols || agg->halo_flags || agg->num_push) return KAGNN_EUNSUPPORTED;   // peer gather / two-part rows / in-flight halo / pushed output: pipelined kernel only
             rc = kagnn_fused_fwd_tc(agg, num_rows, pre, agg_out, ld_agg_out, n_layers, layers, post, y, ldy, stream);
             if (rc == KAGNN_OK) {
                 g_count_tc.fetch_add(1);
@@ -110,7 +111,7 @@ extern "C" int kagnn_fused_layer_fwd(const KagnnAggregate* agg, int64_t num_rows
         }
         if (rc != KAGNN_EUNSUPPORTED) return rc;
     }
-    if (agg->peer_x || agg->num_head_cols || agg->halo_flags) return KAGNN_EUNSUPPORTED;
+    if (agg->peer_x || agg->num_head_cols || agg->halo_flags || agg->num_push) return KAGNN_EUNSUPPORTED;
     int rc = kagnn_fused_fwd_fp32(agg, num_rows, pre, agg_out, ld_agg_out, n_layers, layers, post, y, ldy, stream);
     if (rc == KAGNN_OK && num_rows > 0) g_count_fp32.fetch_add(1);
     return rc;

@@ -122,6 +122,9 @@ constexpr int REGS_PROD = NPW == 16 ? 72 : 80, REGS_GATHER = NGW == 8 ? 88 : 80,
 constexpr int NTHREADS = (NPW + NGW + 4) * 32;   // + MMA, W loader and two idle warps (whole warpgroups for setmaxnreg)
 constexpr int WARP_MMA = NPW + NGW;
 constexpr int WARP_LOAD = NPW + NGW + 1;
+constexpr int WARP_PUSH = NPW + NGW + 3;             // relays finished output tiles to the peers (KagnnAggregate.push_y)
+constexpr int RELAY_BYTES = 8192;                    // shared-memory relay of the push warp: 32 rows of 64 columns, 16 of 128
+constexpr int RELAY_TAIL = RELAY_BYTES + 128 + 128;  // + mbarrier / tile counter block + alignment slack
 constexpr int RPW = BM / NGW;                // rows per gather warp
 constexpr int MAX_STAGE = 4;                 // A stages in TMEM (64 columns each) / B stages in shared memory
 constexpr int MAX_UNITS = 4;                 // x-tile ring slots
@@ -1226,7 +1229,7 @@ __device__ __forceinline__ void gather_unit_ag(const Tc2Params& p, long long row
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-template <int K, bool BF16>
+template <int K, bool BF16, bool PUSH>
 __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_constant__ Tc2Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
     float* xs = reinterpret_cast<float*>(smem);
@@ -1245,6 +1248,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
     HubScratch* hub_scratch = reinterpret_cast<HubScratch*>(post_sh + 256 + 4);
     float2* ln_part = reinterpret_cast<float2*>(hub_scratch + 1);       // [2][NWG][128]: FastKAN LayerNorm partial sums
     uint8_t* ag_stage = reinterpret_cast<uint8_t*>(ln_part + 2 * NWG * 128);   // [NGW][2][AG_R][256 B]: row slots of the asynchronous gather
+    // pushed output (KagnnAggregate.push_y): [mbarrier | tiles stored so far | pad to 128 B | RELAY_BYTES of row slots]
+    // (addresses are derived where they are used: keeping them live across the role dispatch costs every role registers)
+    auto relay_block = [&]() -> uint8_t* {
+        return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ag_stage + ((KAGNN_TC2_AG && p.ag) ? AG_BYTES : 0)) + 127u) & ~(uintptr_t)127u);
+    };
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (warp == WARP_MMA) tc::tmem_alloc(tmem_slot, 512);
@@ -1259,6 +1267,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
         }
         tc::mbar_init(&acc_full[0], 1);
         tc::mbar_init(&acc_full[1], 1);
+        if (PUSH) {
+            tc::mbar_init(reinterpret_cast<uint64_t*>(relay_block()), 1);
+            *reinterpret_cast<uint32_t*>(relay_block() + 8) = 0u;
+        }
         tc::mbar_fence_init();
     }
     if (tid == 0) *gather_progress = 0;
@@ -1351,7 +1363,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                 }
             }
             tc::tc_fence_before_sync();
+            if (PUSH) tc::fence_proxy_async_global();   // the push warp reads these rows back with bulk copies
             if (lane == 0 && (warp & 3) == 0 && wg < 2) TRL(4 + wg, e_lc, 4);
+        };
+        // After an epilogue.  (1) The accumulator region just read is the one this tile's NEXT layer (or, for one-layer chains,
+        // the next tile) overwrites: with every warpgroup on every chunk that MMA cannot start before all warps have left the
+        // epilogue; with teams (CPR > 1) a team could hand over its chunk while the other team still reads -> barrier.
+        // (2) Pushed output: every row of the tile is stored -> publish the count to the push warp.
+        auto tile_stored = [&]() {
+            if (CPR > 1 || PUSH) asm volatile("bar.sync 4, %0;" ::"n"(NPW * 32) : "memory");
+            if (PUSH && tid == 0) {                     // the only writer: the count lives in shared memory, not in a register
+                const uint32_t a = tc::smem_u32(relay_block() + 8);
+                uint32_t v;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+                asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(a), "r"(v + 1u) : "memory");
+            }
         };
         long long pend_row0 = 0;
         uint32_t pend_lc = 0;
@@ -1578,10 +1604,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                     if (have_pend) {                       // previous tile's epilogue, behind this tile's first layer
                         epilogue(pend_row0, pend_lc);
                         have_pend = false;
-                        // The accumulator region just read is the one this tile's NEXT layer (or, for one-layer chains, the next
-                        // tile) overwrites.  With every warpgroup on every chunk that MMA cannot start before all warps have left
-                        // the epilogue; with teams (CPR > 1) a team could hand over its chunk while the other team still reads.
-                        if (CPR > 1) asm volatile("bar.sync 4, %0;" ::"n"(NPW * 32) : "memory");
+                        tile_stored();
                     }
                 }
             }
@@ -1592,10 +1615,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                 // one accumulator region only (wide layers): read it out before the next tile's first chunk can be handed over
                 epilogue(pend_row0, pend_lc);
                 have_pend = false;
-                if (CPR > 1) asm volatile("bar.sync 4, %0;" ::"n"(NPW * 32) : "memory");
+                tile_stored();
             }
         }
-        if (have_pend) epilogue(pend_row0, pend_lc);
+        if (have_pend) {
+            epilogue(pend_row0, pend_lc);
+            if (PUSH) tile_stored();
+        }
     } else if (warp < NPW + NGW) {
         // ========================================= GATHER ======================================================
         if (REGS_GATHER > 72) tc::reg_inc<REGS_GATHER>();
@@ -1762,6 +1788,51 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                     for (int e = beg + lane; e < end; e += 32) tc::prefetch_l2(src_row(a, __ldg(a.col + e)), row_bytes);
                 }
             }
+        }
+        if (PUSH && warp == WARP_PUSH) {
+            // ------------------------------------ OUTPUT PUSH ---------------------------------------------------
+            // Node-sharded graphs: the rows of every finished tile also go to the other ranks' replicas of this layer's output
+            // (KagnnAggregate.push_y).  NVLink WRITES are posted, so a single warp relaying rows through shared memory with bulk
+            // copies (global -> shared -> peer global) keeps up with the tile rate; measured in isolation 16 such CTAs already
+            // saturate the link (profiles/r2_nvlink_push.jsonl), where peer LOADS need every SM of the GPU.
+            const uint32_t rb = (uint32_t)p.layers[p.n_layers - 1].N * 4u;          // bytes of one output row (multiple of 16)
+            const int S = min(32, RELAY_BYTES / (int)rb);                           // rows per relay batch
+            uint64_t* relay_bar = reinterpret_cast<uint64_t*>(relay_block());
+            const uint32_t tiles_stored = tc::smem_u32(relay_block() + 8);
+            uint8_t* slot = relay_block() + 128 + (size_t)lane * rb;
+            float* const* dsts = p.agg.push_y;
+            uint32_t ph = 0, want = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                ++want;
+                uint32_t have, tries = 0;
+                for (;;) {
+                    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(have) : "r"(tiles_stored) : "memory");
+                    if (have >= want) break;
+                    __nanosleep(256);
+                    if (++tries > (1u << 24)) __trap();
+                }
+                const long long row0 = (long long)tile * BM;
+                const int nrows = (int)min((long long)BM, p.num_rows - row0);
+                for (int r0 = 0; r0 < nrows; r0 += S) {
+                    const int cnt = min(S, nrows - r0);
+                    tc::bulk_wait_read_all();                                       // the previous batch left the slots
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive_expect_tx(relay_bar, (uint32_t)cnt * rb);
+                    __syncwarp();
+                    const long long row = row0 + r0 + lane;
+                    if (lane < cnt) tc::bulk_g2s(slot, p.y + row * p.ldy, rb, relay_bar);
+                    tc::mbar_wait(relay_bar, ph);
+                    ph ^= 1u;
+                    if (lane < cnt) {
+                        const uint32_t m = p.agg.push_mask ? (uint32_t)__ldg(p.agg.push_mask + row) : 0xffu;
+                        for (int i = 0; i < p.agg.num_push; ++i)
+                            if ((m >> i) & 1u) tc::bulk_s2g(dsts[i] + row * p.agg.ld_push, slot, rb);
+                        tc::bulk_commit();
+                    }
+                }
+            }
+            tc::bulk_wait_all();
+            __threadfence_system();
         }
         if (warp == WARP_LOAD && lane == 0) {
             uint32_t cq = 0, par = 1;
@@ -1975,6 +2046,10 @@ int KAGNN_TC2_ENTRY(const KagnnAggregate* agg, int64_t num_rows, const KagnnAffi
         if (agg->rows_per_rank * (int64_t)agg->num_ranks > (int64_t)INT32_MAX) return KAGNN_EUNSUPPORTED;
     }
     p.y_vec = aligned16(y) && (ldy % 4 == 0);
+    if (agg->num_push > 0) {                               // pushed output: whole rows move as bulk copies (16-byte granules)
+        if (!agg->push_y || agg->num_push > 8) return KAGNN_EINVAL;
+        if (!p.y_vec || width % 4 != 0 || width > 128 || agg->ld_push % 4 != 0 || agg->ld_push < width) return KAGNN_EUNSUPPORTED;
+    }
 
     const int F_pad0 = p.layers[0].F_pad;
     // asynchronous gather: GIN / GCN aggregation of rows whose width is a multiple of 64 columns, 128-bit aligned operands
@@ -1988,7 +2063,7 @@ int KAGNN_TC2_ENTRY(const KagnnAggregate* agg, int64_t num_rows, const KagnnAffi
     p.bstage_bytes = 256 * n_max;
     // LUTs | mbarriers (x ring full/empty, stage full/empty, 2 accumulator) | tmem slot (16 B) | post scale/shift | progress word
     const int tail = KAGNN_MAX_LAYERS * LUT_ROWS * 16 + (2 * MAX_UNITS + 2 * MAX_STAGE + 2) * 8 + 16 + 2 * 128 * 4 + 16 + (int)sizeof(HubScratch) + 2 * NWG * 128 * 8 + 2 * 128 * 4 +
-                     (p.ag ? AG_BYTES : 0);
+                     (p.ag ? AG_BYTES : 0) + (agg->num_push > 0 ? RELAY_TAIL : 0);
     // x-ring geometry: units of 128 or 64 columns.  128 (one unit per tile up to 128 inputs) is the default; 64-column units are
     // forced by the asynchronous gather and by wide layers (64 KB W stages), and preferred for plain row tiles (no gather) when
     // they buy a deeper W / A stage ring.  Ring depths: at least 2 units and 2 stages; deeper stages first, then more units.
@@ -2022,8 +2097,15 @@ int KAGNN_TC2_ENTRY(const KagnnAggregate* agg, int64_t num_rows, const KagnnAffi
     // in-kernel LayerNorm statistics need the whole input row in one x unit; wider rows need the pre-pass (ln_stats)
     if (rbf && p.units_per_tile != 1 && p.layers[0].lnw && !p.layers[0].ln_stats) return KAGNN_EUNSUPPORTED;
     void (*kern)(Tc2Params);
-    if (bf16) kern = k == 3 ? fused_tc2_kernel<3, true> : (k == 2 ? fused_tc2_kernel<2, true> : (k == 1 ? fused_tc2_kernel<1, true> : fused_tc2_kernel<0, true>));
-    else kern = k == 3 ? fused_tc2_kernel<3, false> : (k == 2 ? fused_tc2_kernel<2, false> : (k == 1 ? fused_tc2_kernel<1, false> : fused_tc2_kernel<0, false>));
+    // the pushed-output variant is a separate instantiation: its relay warp and the extra barrier cost the other launches
+    // registers in the producer loop (measured 3 % of the step when it was a run-time switch)
+    if (agg->num_push > 0 && bf16) return KAGNN_EUNSUPPORTED;
+    if (agg->num_push > 0)
+        kern = k == 3 ? fused_tc2_kernel<3, false, true> : (k == 2 ? fused_tc2_kernel<2, false, true> : (k == 1 ? fused_tc2_kernel<1, false, true> : fused_tc2_kernel<0, false, true>));
+    else if (bf16)
+        kern = k == 3 ? fused_tc2_kernel<3, true, false> : (k == 2 ? fused_tc2_kernel<2, true, false> : (k == 1 ? fused_tc2_kernel<1, true, false> : fused_tc2_kernel<0, true, false>));
+    else
+        kern = k == 3 ? fused_tc2_kernel<3, false, false> : (k == 2 ? fused_tc2_kernel<2, false, false> : (k == 1 ? fused_tc2_kernel<1, false, false> : fused_tc2_kernel<0, false, false>));
     KAGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)props.max_smem));
     if (agg->halo_flags && (!agg->x_halo || !agg->halo_need)) return KAGNN_EINVAL;
     int sms = props.num_sms - (agg->reserve_sms > 0 ? agg->reserve_sms : 0);

@@ -109,6 +109,19 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  : "memory");
 }
 
+// ---- bulk TMA: shared -> global (also peer-mapped global: posted NVLink writes), tracked by bulk async-groups ----------
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the source shared memory of every committed group of this thread has been read (the slots may be overwritten)
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// every committed group of this thread is complete (the writes are performed)
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy st.global -> visible to bulk copies (async proxy) that read the same global memory afterwards
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+
 // fire-and-forget request to bring `bytes` of global memory into L2, one 128-byte line per instruction through the LSU path
 // (cp.async.bulk.prefetch.L2 would queue behind the W loader's bulk copies in the TMA unit: measured 1.7x slower layers)
 __device__ __forceinline__ void prefetch_l2(const void* src_gmem, uint32_t bytes) {

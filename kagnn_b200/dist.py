@@ -177,6 +177,13 @@ class ShardedNodeModel:
       prefix their tile needs (``kagnn_gather_rows_peer_ordered``, ``KagnnAggregate.halo_flags``).  Measured on two B200s it does
       NOT pay yet: an SM sustains only ~15 GB/s of peer loads, so the 16 SMs it may take from the layer pull at 240 GB/s where the
       all-SM kernel reaches 680 GB/s (profiles/README.md); it stays available for experiments and is parity-tested;
+    * ``mode="push"``: the layer that PRODUCES a hidden matrix sends it: every rank keeps a replica of each hidden matrix (all
+      ranks' rows) in symmetric memory, and one warp per CTA of the fused kernel copies every finished output tile into the
+      peers' replicas with bulk copies while the following tiles are computed (``KagnnAggregate.push_y``; a per-row byte mask
+      restricts the copies to the ranks that reference the row).  NVLink writes are posted, so -- unlike peer loads, which
+      need every SM of the GPU to fill the link -- the transfer costs no SMs and hides behind the tensor-core pipeline; the
+      next layer reads the replica as an ordinary halo matrix after one device barrier.  The input features of the first layer
+      are still pulled (``kagnn_gather_rows_peer``): nothing runs before them that could hide the transfer;
     * ``mode="peer"``: by the gather warps of the fused kernel themselves, straight from the owners' memory over NVLink
       (``KagnnAggregate.peer_x``): every rank keeps its skip-concat buffer in ``torch.distributed._symmetric_memory``, the
       kernel receives the table of peer-mapped base pointers, and the only cross-rank traffic besides the row loads is one
@@ -185,8 +192,8 @@ class ShardedNodeModel:
       applies and falls back to ``"halo"`` otherwise."""
 
     def __init__(self, model, rank: int, world: int, n_local: int, group=None, mode: str = "halo"):
-        if mode not in ("halo", "peer", "pull", "pull_overlap", "auto"):
-            raise ValueError("mode must be 'halo', 'peer', 'pull', 'pull_overlap' or 'auto'")
+        if mode not in ("halo", "peer", "pull", "pull_overlap", "push", "auto"):
+            raise ValueError("mode must be 'halo', 'peer', 'pull', 'pull_overlap', 'push' or 'auto'")
         self.model, self.rank, self.world, self.n_local, self.group = model, rank, world, n_local, group
         self._symm = {}
         self._side = {}
@@ -200,7 +207,7 @@ class ShardedNodeModel:
             # arxiv-shaped bench, where every remote row is referenced ~3.6 times); "peer" needs no halo matrix at all
             # on 8 ranks the in-kernel gather measured 2.20 ms/step (NCCL halo 2.90) and is the measured choice there
             mode = ("peer" if world >= 8 else "pull") if self.peer_supported() else "halo"
-        elif mode in ("peer", "pull", "pull_overlap") and not self.peer_supported():
+        elif mode in ("peer", "pull", "pull_overlap", "push") and not self.peer_supported():
             raise NotImplementedError("modes 'peer' / 'pull' need a GIN-flavour GKAN_Nodes / GFASTKAN_Nodes with skip=True, "
                                       "spline_order <= 3, G + k <= 8 (FastKAN: <= 8 centres), widths <= 128 and feature widths that "
                                       "are multiples of 4; GCN flavours and skip=False use mode='halo'")
@@ -259,6 +266,21 @@ class ShardedNodeModel:
             plan.halo_ids = halo_global.to(torch.int32)
             plan.n_halo = n_halo
             return plan
+        if self.mode == "push":
+            # layer 0 reads x through the compact halo numbering of "pull"; the later layers read the replicas of the hidden
+            # matrices, where the row of global node j is row j (source id n_local + j in the two-matrix addressing of x_halo)
+            lo, dev = self.rank * self.n_local, edge_index_global.device
+            ei_local, halo_global, _ = relabel_edges(edge_index_global, self.rank, self.world, self.n_local)
+            n_halo = int(halo_global.numel())
+            plan = PeerPlan(GraphCSR(ei_local, self.n_local, self.n_local + n_halo), self.n_local, self.world)
+            plan.halo_ids = halo_global.to(torch.int32)
+            plan.n_halo = n_halo
+            src, dst = edge_index_global[0], edge_index_global[1] - lo
+            mine = (src >= lo) & (src < lo + self.n_local)
+            src_rep = torch.where(mine, src - lo, src + self.n_local)
+            plan.graph_rep = GraphCSR(torch.stack([src_rep, dst]), self.n_local, self.n_local * (self.world + 1))
+            plan.push_mask = self._push_mask(halo_global, dev)
+            return plan
         if self.mode == "pull_overlap":
             # the same, numbered in first-use order for the pull that runs concurrently with the layer
             ei_local, halo_global, need = relabel_edges_first_use(edge_index_global, self.rank, self.world, self.n_local)
@@ -281,14 +303,40 @@ class ShardedNodeModel:
         plan.exchange = HaloExchange(plan, self.group)
         return plan
 
+    def push_peers(self):
+        """The ranks this one pushes to, in the bit order of the push mask / the order of the destination table."""
+        return [q for q in range(self.world) if q != self.rank]
+
+    def _push_mask(self, halo_global: Tensor, dev) -> Optional[Tensor]:
+        """Collective (plan time): byte r has bit i set <=> rank push_peers()[i] references row r of this rank.  None when
+        (nearly) every row goes everywhere -- then the kernel skips the mask load."""
+        grp = self.group
+        cnt = torch.tensor([int(halo_global.numel())], dtype=torch.int64, device=dev)
+        cnts = [torch.zeros_like(cnt) for _ in range(self.world)]
+        dist.all_gather(cnts, cnt, group=grp)
+        mx = max(1, max(int(c.item()) for c in cnts))
+        pad = torch.full((mx,), -1, dtype=torch.int64, device=dev)
+        pad[: halo_global.numel()] = halo_global
+        lists = [torch.empty_like(pad) for _ in range(self.world)]
+        dist.all_gather(lists, pad, group=grp)
+        lo = self.rank * self.n_local
+        mask = torch.zeros(self.n_local, dtype=torch.uint8, device=dev)
+        for i, q in enumerate(self.push_peers()):
+            ids = lists[q][: int(cnts[q].item())]
+            ids = ids[(ids >= lo) & (ids < lo + self.n_local)] - lo
+            mask[ids] |= (1 << i)
+        full = (1 << (self.world - 1)) - 1
+        dense = float((mask == full).float().mean().item()) if self.n_local else 1.0
+        return None if dense > 0.9 else mask
+
     def _side_stream(self, dev):
         if dev.index not in self._side:
             self._side[dev.index] = torch.cuda.Stream(device=dev)
         return self._side[dev.index]
 
-    def _symm_buffer(self, n: int, width: int, dev):
+    def _symm_buffer(self, n: int, width: int, dev, tag: int = 0):
         """Skip-concat buffer in symmetric memory + one device table of peer base pointers per column offset (cached)."""
-        key = (n, width, dev.index)
+        key = (n, width, dev.index, tag)
         if key not in self._symm:
             import torch.distributed._symmetric_memory as symm_mem
             grp = self.group if self.group is not None else dist.group.WORLD
@@ -315,6 +363,15 @@ class ShardedNodeModel:
                 tables[col_off] = torch.tensor([q + 4 * col_off for q in ptrs], dtype=torch.int64, device=x.device)
             return tables[col_off]
 
+        reps = []
+        if self.mode == "push":
+            # replicas of the hidden matrices that a later layer aggregates (all but the last one) + my destination tables
+            for l in range(n_mp - 1):
+                rbuf, _, rptrs, rtab = self._symm_buffer(self.world * n, hid, x.device, tag=1 + l)
+                if "push" not in rtab:
+                    rtab["push"] = torch.tensor([rptrs[q] + 4 * self.rank * n * hid for q in self.push_peers()], dtype=torch.int64,
+                                                device=x.device)
+                reps.append((rbuf, rtab["push"]))
         hdl.barrier()                                     # every rank is done reading the previous step's buffer
         ops.gather_rows(x, None, out=buf[:, :f])
         col = 0
@@ -322,7 +379,14 @@ class ShardedNodeModel:
         for l, (conv, bn) in enumerate(zip(m.convs, m.bns)):
             hdl.barrier()                                 # the slice read below is complete on every rank
             dst = buf[:, f + l * hid: f + (l + 1) * hid]
-            if self.mode == "pull":
+            if self.mode == "push":
+                push = dict(push_y=reps[l][1], push_ld=hid, push_mask=plan.push_mask) if l < n_mp - 1 else {}
+                if l == 0:
+                    halo = ops.gather_rows_peer(table(col), buf.stride(0), self.n_local, plan.halo_ids, cur.size(1))
+                    conv(cur, plan.graph, out=dst, post=m._folds[l].get(bn), x_halo=halo, **push)
+                else:
+                    conv(cur, plan.graph_rep, out=dst, post=m._folds[l].get(bn), x_halo=reps[l - 1][0], **push)
+            elif self.mode == "pull":
                 # the distinct remote rows, copied once from their owners by a pull kernel on all SMs (678 GB/s measured on two
                 # B200s), then the ordinary halo layer
                 halo = ops.gather_rows_peer(table(col), buf.stride(0), self.n_local, plan.halo_ids, cur.size(1))
@@ -357,7 +421,7 @@ class ShardedNodeModel:
         m = self.model
         if len(m.convs) == 0:                               # no message passing: nothing to exchange
             return m(x, torch.zeros(2, 0, dtype=torch.int64, device=x.device))
-        if self.mode in ("peer", "pull", "pull_overlap"):
+        if self.mode in ("peer", "pull", "pull_overlap", "push"):
             if not m._fusable():
                 raise NotImplementedError("the sharded forward implements the eval-mode plan (BatchNorm folded)")
             x = x.to(torch.float32)

@@ -543,6 +543,9 @@ class AggSpec:
     halo_flags: Optional[Tensor] = None   # ... per chunk of 256 halo rows: == halo_epoch once the chunk has landed
     halo_epoch: int = 0
     reserve_sms: int = 0
+    push_y: Optional[Tensor] = None       # output rows pushed to the peers while the layer runs: (num_push,) int64 destination pointers
+    push_ld: int = 0                      # ... leading dimension of the destinations (floats)
+    push_mask: Optional[Tensor] = None    # ... optional (num_rows,) uint8: bit i set <=> destination i needs the row
     _anchors = ("x", "rowptr", "x_head", "x_halo", "edge_feat")
 
     def __post_init__(self) -> None:
@@ -592,6 +595,14 @@ class AggSpec:
             _need_cuda(self.halo_need, "halo_need", torch.int32)
             s.halo_flags, s.halo_need = _addr(self.halo_flags), _addr(self.halo_need)
             s.halo_epoch, s.reserve_sms = int(self.halo_epoch), int(self.reserve_sms)
+        if self.push_y is not None and self.push_y.numel():
+            _need_cuda(self.push_y, "push_y", torch.int64)
+            if self.push_ld <= 0 or self.push_y.numel() > 8:
+                raise ValueError("push_y needs push_ld and at most 8 destinations")
+            s.push_y, s.ld_push, s.num_push = _addr(self.push_y), int(self.push_ld), int(self.push_y.numel())
+            if self.push_mask is not None:
+                _need_cuda(self.push_mask, "push_mask", torch.uint8)
+                s.push_mask = _addr(self.push_mask)
         if self.peer_x is not None:
             _need_cuda(self.peer_x, "peer_x", torch.int64)
             if self.rows_per_rank <= 0:

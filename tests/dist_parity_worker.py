@@ -71,7 +71,7 @@ def main():
         if conv_type == "gin":
             # in-kernel NVLink gather (KagnnAggregate.peer_x) and the overlapped pull: same numbers without pack / all-to-all
             # (B-spline and FastKAN flavours; GCN flavours stay on the NCCL halo transport, which `auto` picks for them)
-            for pmode in ("peer", "pull", "pull_overlap"):
+            for pmode in ("peer", "pull", "pull_overlap", "push"):
                 peer = kd.ShardedNodeModel(m, rank, world, n_local, mode=pmode)
                 pplan = peer.prepare(ei[:, mine].to(dev))
                 for rep in range(3):                  # repeated steps exercise the cross-step buffer reuse barriers

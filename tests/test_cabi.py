@@ -57,7 +57,7 @@ def test_struct_layouts_match_the_header(tmp_path):
         assert int(got[name]) == ctypes.sizeof(cls), name
         for field, _ in cls._fields_:
             assert int(got[f"{name}.{field}"]) == getattr(cls, field).offset, (name, field)
-    assert ctypes.sizeof(_lib.KagnnAggregate) == 184
+    assert ctypes.sizeof(_lib.KagnnAggregate) == 216
 
 
 def test_no_cpu_fallback():

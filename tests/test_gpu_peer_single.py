@@ -144,3 +144,74 @@ def test_overlapped_pull_with_progress_flags_single_gpu(fast):
     y = torch.cat(ys)
     assert torch.isfinite(y).all()
     assert K.rel_err(y, y_single) <= 2e-6
+
+
+@pytest.mark.parametrize("fast,hid,masked", [(False, 64, False), (False, 64, True), (True, 32, True), (False, 128, True)])
+def test_pushed_layer_output_single_gpu(fast, hid, masked):
+    """mode="push": the layer that produces a hidden matrix also copies every finished tile into the other ranks' replicas
+    (KagnnAggregate.push_y, one relay warp per CTA, bulk copies), optionally restricted by the per-row byte mask; the next layer
+    then aggregates over [own rows | replica].  Three "ranks" on one GPU, every replica a separate allocation."""
+    import kagnn_b200 as kb
+    from kagnn_b200 import ops
+    from kagnn_b200.graph import GraphCSR
+    torch.manual_seed(4)
+    world, n_local, f = 3, 5_003, 64                              # many tiles per CTA would need > 148 * 128 rows: see the second size
+    if hid == 128:
+        n_local = 40_001                                         # 313 tiles: every CTA relays several tiles
+    n, x, ei = _setup(world, n_local, f, 8 * world * n_local, seed=11 + hid)
+    mk = (lambda a, b: kb.GIFASTKANLayer(a, hid, 5, b, 2)) if fast else (lambda a, b: kb.GIKANLayer(a, hid, 5, 3, b, 2))
+    conv0, conv1 = mk(f, hid).cuda(), mk(hid, 24).cuda()
+    dev = torch.device("cuda")
+    xd, eid = x.to(dev), ei.to(dev)
+    with torch.no_grad():
+        h_single = conv0(xd, eid)
+        y_single = conv1(h_single, eid).cpu()
+    # per "rank": replica of the hidden matrix (all ranks' rows), poisoned so that a missing push shows
+    reps = [torch.full((n, hid), float("nan"), device=dev) for _ in range(world)]
+    h_local = [torch.empty(n_local, hid, device=dev) for _ in range(world)]
+    need = torch.zeros(world, n, dtype=torch.bool)               # need[q, j]: rank q references global row j
+    for q in range(world):
+        mine = (ei[1] >= q * n_local) & (ei[1] < (q + 1) * n_local)
+        need[q, ei[0][mine]] = True
+    with torch.no_grad():
+        for r in range(world):
+            lo = r * n_local
+            mine = (ei[1] >= lo) & (ei[1] < lo + n_local)
+            peers = [q for q in range(world) if q != r]
+            table = torch.tensor([reps[q][lo:].data_ptr() for q in peers], dtype=torch.int64, device=dev)
+            mask = None
+            if masked:
+                mask = torch.zeros(n_local, dtype=torch.uint8)
+                for i, q in enumerate(peers):
+                    mask |= need[q, lo:lo + n_local].to(torch.uint8) << i
+                mask = mask.to(dev)
+            # x of the whole graph as [own rows | everything]: source ids >= n_local address the second matrix
+            conv0(xd[lo:lo + n_local], _rep_graph(ei[:, mine], lo, n_local, n, dev), out=h_local[r], x_halo=xd, push_y=table, push_ld=hid,
+                  push_mask=mask)
+        torch.cuda.synchronize()
+        ys = []
+        for r in range(world):
+            lo = r * n_local
+            mine = (ei[1] >= lo) & (ei[1] < lo + n_local)
+            assert torch.equal(h_local[r], h_single[lo:lo + n_local]) or K.rel_err(h_local[r].cpu(), h_single[lo:lo + n_local].cpu()) <= 2e-6
+            got = reps[r].clone()
+            for q in range(world):                                   # what rank r received from rank q
+                if q == r:
+                    continue
+                rows = torch.arange(q * n_local, (q + 1) * n_local)
+                sent = need[r, rows] if masked else torch.ones(n_local, dtype=torch.bool)
+                assert torch.equal(got[rows[sent].to(dev)], h_local[q][sent.to(dev)]), (r, q)
+                assert torch.isnan(got[rows[~sent].to(dev)]).all()   # rows nobody asked for were not sent
+            ys.append(conv1(h_local[r], _rep_graph(ei[:, mine], lo, n_local, n, dev), x_halo=reps[r]).cpu())
+    y = torch.cat(ys)
+    assert torch.isfinite(y).all()
+    assert K.rel_err(y, y_single) <= 2e-6
+
+
+def _rep_graph(ei_mine, lo, n_local, n, dev):
+    """CSR of one rank's destination rows over [own rows | replica of all rows]: local source j -> j - lo, remote -> n_local + j."""
+    from kagnn_b200.graph import GraphCSR
+    src, dst = ei_mine[0], ei_mine[1] - lo
+    local = (src >= lo) & (src < lo + n_local)
+    src = torch.where(local, src - lo, src + n_local)
+    return GraphCSR(torch.stack([src, dst]).to(dev), n_local, n_local + n)
