@@ -213,6 +213,9 @@ def main():
     ap.add_argument("--config", default="arxiv", choices=["arxiv", "cora", "zinc", "mutag", "rmat"],
                     help="arxiv = the headline workload (BASELINE configs[1]); the others print the secondary measurement of that "
                          "configuration alone (scripts/bench_extras.py) as one JSON line")
+    ap.add_argument("--resident-x-halo", action="store_true",
+                    help="N > 1: keep the halo rows of the static input features between steps (part of the partitioned input); "
+                         "default off = the input halo crosses NVLink every step")
     ap.add_argument("--dist-mode", default="auto", choices=["auto", "peer", "pull", "pull_overlap", "push", "halo"],
                     help="N > 1: 'peer' = in-kernel NVLink gather from symmetric memory, 'halo' = NCCL all-to-all per layer")
     args = ap.parse_args()
@@ -256,11 +259,16 @@ def main():
 
     if dist_on:
         from kagnn_b200 import dist as kdist
-        runner = kdist.ShardedNodeModel(model, rank, world, n_local, mode=args.dist_mode)
+        runner = kdist.ShardedNodeModel(model, rank, world, n_local, mode=args.dist_mode, resident_x_halo=args.resident_x_halo)
         ei_glob = ei_host.to(dev)
         ei_glob[1] += rank * n_local                                     # targets: this rank's node range, global ids
         plan = runner.prepare(ei_glob)
-        x_dev = x_host.to(dev)
+        in_symm = runner.mode in ("peer", "pull", "pull_overlap", "push")
+        if in_symm:
+            x_dev = runner.input_buffer(N_FEAT, dev)                     # x resident where the peers can read it (symmetric memory)
+            x_dev.copy_(x_host)
+        else:
+            x_dev = x_host.to(dev)
         step = lambda: runner.forward(x_dev, plan)                       # noqa: E731
     else:
         x_dev, ei_dev = x_host.to(dev), ei_host.to(dev)
@@ -324,13 +332,18 @@ def main():
             cur = torch.cuda.current_stream()
             copy_stream.wait_stream(cur)
             with torch.cuda.stream(copy_stream):
-                xd = x_host.to(dev, non_blocking=True)
+                if dist_on and in_symm:
+                    xd = runner.input_buffer(N_FEAT, dev)     # H2D straight into the symmetric buffer the peers read
+                    xd.copy_(x_host, non_blocking=True)
+                else:
+                    xd = x_host.to(dev, non_blocking=True)
             ed = ei_host.to(dev, non_blocking=True)
             if dist_on:
                 ed[1] += rank * n_local
                 pl = runner.prepare(ed)                  # halo plan (index all-to-all) + shard CSR
                 cur.wait_stream(copy_stream)
-                xd.record_stream(cur)
+                if not in_symm:
+                    xd.record_stream(cur)
                 y = runner.forward(xd, pl)
             else:
                 get_graph(ed, n_local)                   # COO -> CSR on the compute stream while x is still in flight
@@ -452,7 +465,9 @@ def main():
                                    "one device barrier per layer" if runner.mode == "peer" else ("distinct remote rows pulled over NVLink from symmetric memory "
                                    "by one copy kernel per layer (no collective)" if runner.mode == "pull" else ("x halo pulled over NVLink before layer 0; hidden rows pushed into the peers' replicas by a relay warp of the producing layer's kernel (bulk copies, masked per row), one device barrier per layer" if runner.mode == "push" else ("distinct remote rows pulled over NVLink by a copy kernel that runs concurrently with the layer (first-use order, progress counters)" if runner.mode == "pull_overlap" else "one NCCL halo all-to-all per layer")))))
                    if dist_on else "single GPU",
-                   "graph": "uniform random edges over all shards: (N-1)/N of the edges are cut" if dist_on else "uniform random edges"},
+                   "graph": "uniform random edges over all shards: (N-1)/N of the edges are cut" if dist_on else "uniform random edges",
+                   "x_halo": ("resident between steps (static features; e2e re-fetches it every step)" if args.resident_x_halo
+                              else "fetched every step") if dist_on else None},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "kernels": kernels, "roofline": roofline, "cpu_baseline": cpu,
         "extra": extra,
     }

@@ -123,8 +123,7 @@ constexpr int NTHREADS = (NPW + NGW + 4) * 32;   // + MMA, W loader and two idle
 constexpr int WARP_MMA = NPW + NGW;
 constexpr int WARP_LOAD = NPW + NGW + 1;
 constexpr int WARP_PUSH = NPW + NGW + 3;             // relays finished output tiles to the peers (KagnnAggregate.push_y)
-constexpr int RELAY_BYTES = 8192;                    // shared-memory relay of the push warp: 32 rows of 64 columns, 16 of 128
-constexpr int RELAY_TAIL = RELAY_BYTES + 128 + 128;  // + mbarrier / tile counter block + alignment slack
+constexpr int RELAY_PAD = 128 + 128;                 // pushed output: mbarrier / tile counter block + alignment slack in front of the relay slots
 constexpr int RPW = BM / NGW;                // rows per gather warp
 constexpr int MAX_STAGE = 4;                 // A stages in TMEM (64 columns each) / B stages in shared memory
 constexpr int MAX_UNITS = 4;                 // x-tile ring slots
@@ -158,6 +157,7 @@ struct Tc2Params {
     int ag;                                               // 1: asynchronous (cp.async ring) gather, 64-column units
     int wide;                                             // 1: one layer up to 256 outputs wide: a single 256-column accumulator region
     int bf16;                                             // 1: single bf16 product (A_hi . W_hi), kagnn_set_precision(KAGNN_PREC_BF16)
+    int relay_bytes;                                      // pushed output: shared-memory relay of the push warps (16 KB if the rings keep their depth, else 8 KB)
     LayerT2 layers[KAGNN_MAX_LAYERS];
 };
 
@@ -1248,7 +1248,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
     HubScratch* hub_scratch = reinterpret_cast<HubScratch*>(post_sh + 256 + 4);
     float2* ln_part = reinterpret_cast<float2*>(hub_scratch + 1);       // [2][NWG][128]: FastKAN LayerNorm partial sums
     uint8_t* ag_stage = reinterpret_cast<uint8_t*>(ln_part + 2 * NWG * 128);   // [NGW][2][AG_R][256 B]: row slots of the asynchronous gather
-    // pushed output (KagnnAggregate.push_y): [mbarrier | tiles stored so far | pad to 128 B | RELAY_BYTES of row slots]
+    // pushed output (KagnnAggregate.push_y): [mbarrier 0 | tiles stored so far | mbarrier 1 | pad to 128 B | relay_bytes of row slots]
     // (addresses are derived where they are used: keeping them live across the role dispatch costs every role registers)
     auto relay_block = [&]() -> uint8_t* {
         return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ag_stage + ((KAGNN_TC2_AG && p.ag) ? AG_BYTES : 0)) + 127u) & ~(uintptr_t)127u);
@@ -1269,6 +1269,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
         tc::mbar_init(&acc_full[1], 1);
         if (PUSH) {
             tc::mbar_init(reinterpret_cast<uint64_t*>(relay_block()), 1);
+            tc::mbar_init(reinterpret_cast<uint64_t*>(relay_block() + 16), 1);
             *reinterpret_cast<uint32_t*>(relay_block() + 8) = 0u;
         }
         tc::mbar_fence_init();
@@ -1789,31 +1790,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                 }
             }
         }
-        if (PUSH && warp == WARP_PUSH) {
+        if (PUSH && (warp == WARP_PUSH || (warp == WARP_PUSH - 1 && KAGNN_TC2_PREFETCH_DIST == 0))) {
             // ------------------------------------ OUTPUT PUSH ---------------------------------------------------
             // Node-sharded graphs: the rows of every finished tile also go to the other ranks' replicas of this layer's output
-            // (KagnnAggregate.push_y).  NVLink WRITES are posted, so a single warp relaying rows through shared memory with bulk
-            // copies (global -> shared -> peer global) keeps up with the tile rate; measured in isolation 16 such CTAs already
-            // saturate the link (profiles/r2_nvlink_push.jsonl), where peer LOADS need every SM of the GPU.
+            // (KagnnAggregate.push_y).  NVLink WRITES are posted, so two warps relaying rows through shared memory with bulk
+            // copies (global -> shared -> peer global) keep up with the tile rate; measured in isolation 16 such CTAs already
+            // saturate the link (profiles/r2_nvlink_push.jsonl), where peer LOADS need every SM of the GPU.  The two warps take
+            // alternate batches of rows, each with its own half of the relay buffer and its own mbarrier.
+            const int pw = (KAGNN_TC2_PREFETCH_DIST == 0) ? warp - (WARP_PUSH - 1) : 0;
+            const int npw = (KAGNN_TC2_PREFETCH_DIST == 0) ? 2 : 1;
             const uint32_t rb = (uint32_t)p.layers[p.n_layers - 1].N * 4u;          // bytes of one output row (multiple of 16)
-            const int S = min(32, RELAY_BYTES / (int)rb);                           // rows per relay batch
-            uint64_t* relay_bar = reinterpret_cast<uint64_t*>(relay_block());
+            const int half = p.relay_bytes / npw;
+            const int S = min(32, half / (int)rb);                                  // rows per relay batch
+            uint64_t* relay_bar = reinterpret_cast<uint64_t*>(relay_block() + 16 * pw);
             const uint32_t tiles_stored = tc::smem_u32(relay_block() + 8);
-            uint8_t* slot = relay_block() + 128 + (size_t)lane * rb;
+            uint8_t* slot = relay_block() + 128 + (size_t)pw * half + (size_t)lane * rb;
             float* const* dsts = p.agg.push_y;
-            uint32_t ph = 0, want = 0;
+            uint32_t ph = 0, want = 0, bi = 0;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
                 ++want;
                 uint32_t have, tries = 0;
                 for (;;) {
                     asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(have) : "r"(tiles_stored) : "memory");
                     if (have >= want) break;
-                    __nanosleep(256);
+                    __nanosleep(128);
                     if (++tries > (1u << 24)) __trap();
                 }
                 const long long row0 = (long long)tile * BM;
                 const int nrows = (int)min((long long)BM, p.num_rows - row0);
-                for (int r0 = 0; r0 < nrows; r0 += S) {
+                for (int r0 = 0; r0 < nrows; r0 += S, ++bi) {
+                    if ((int)(bi % (uint32_t)npw) != pw) continue;
                     const int cnt = min(S, nrows - r0);
                     tc::bulk_wait_read_all();                                       // the previous batch left the slots
                     __syncwarp();
@@ -2062,26 +2068,39 @@ int KAGNN_TC2_ENTRY(const KagnnAggregate* agg, int64_t num_rows, const KagnnAffi
     p.bf16 = bf16 ? 1 : 0;
     p.bstage_bytes = 256 * n_max;
     // LUTs | mbarriers (x ring full/empty, stage full/empty, 2 accumulator) | tmem slot (16 B) | post scale/shift | progress word
-    const int tail = KAGNN_MAX_LAYERS * LUT_ROWS * 16 + (2 * MAX_UNITS + 2 * MAX_STAGE + 2) * 8 + 16 + 2 * 128 * 4 + 16 + (int)sizeof(HubScratch) + 2 * NWG * 128 * 8 + 2 * 128 * 4 +
-                     (p.ag ? AG_BYTES : 0) + (agg->num_push > 0 ? RELAY_TAIL : 0);
+    const int tail0 = KAGNN_MAX_LAYERS * LUT_ROWS * 16 + (2 * MAX_UNITS + 2 * MAX_STAGE + 2) * 8 + 16 + 2 * 128 * 4 + 16 + (int)sizeof(HubScratch) + 2 * NWG * 128 * 8 + 2 * 128 * 4 +
+                     (p.ag ? AG_BYTES : 0);
     // x-ring geometry: units of 128 or 64 columns.  128 (one unit per tile up to 128 inputs) is the default; 64-column units are
     // forced by the asynchronous gather and by wide layers (64 KB W stages), and preferred for plain row tiles (no gather) when
     // they buy a deeper W / A stage ring.  Ring depths: at least 2 units and 2 stages; deeper stages first, then more units.
+    // (pushed output: the relay of the push warps comes out of the same budget -- 16 KB when the stage ring keeps its full depth
+    // with it, else 8 KB)
     int best_units = 0, best_ns = 0, best_uw = 0;
-    for (int uw = 128; uw >= 64; uw >>= 1) {
-        if (uw == 128 && (F_pad0 <= 64 || p.ag || p.wide)) continue;
-        if (uw == 64 && best_units != 0 && !(agg->mode == KAGNN_AGG_NONE && !pre && !agg->src_index)) break;
-        // in-kernel LayerNorm statistics need the whole input row in ONE unit
-        if (uw == 64 && best_units != 0 && rbf && layers[0].ln_weight && !p.layers[0].ln_stats) break;
-        const int unit_bytes_c = BM * (uw + 4) * (int)sizeof(float);
-        for (int nu = 2; nu <= MAX_UNITS; ++nu) {
-            const int left = (int)props.max_smem - tail - nu * unit_bytes_c;
-            int ns = left / p.bstage_bytes;
-            if (ns > MAX_STAGE) ns = MAX_STAGE;
-            if (ns < 2) break;
-            if (best_units == 0 || ns > best_ns || (ns == best_ns && uw == best_uw)) { best_units = nu; best_ns = ns; best_uw = uw; }
-            else break;
+    auto choose = [&](int relay) {
+        best_units = best_ns = best_uw = 0;
+        p.relay_bytes = relay;
+        const int tail = tail0 + (relay ? relay + RELAY_PAD : 0);
+        for (int uw = 128; uw >= 64; uw >>= 1) {
+            if (uw == 128 && (F_pad0 <= 64 || p.ag || p.wide)) continue;
+            if (uw == 64 && best_units != 0 && !(agg->mode == KAGNN_AGG_NONE && !pre && !agg->src_index)) break;
+            // in-kernel LayerNorm statistics need the whole input row in ONE unit
+            if (uw == 64 && best_units != 0 && rbf && layers[0].ln_weight && !p.layers[0].ln_stats) break;
+            const int unit_bytes_c = BM * (uw + 4) * (int)sizeof(float);
+            for (int nu = 2; nu <= MAX_UNITS; ++nu) {
+                const int left = (int)props.max_smem - tail - nu * unit_bytes_c;
+                int ns = left / p.bstage_bytes;
+                if (ns > MAX_STAGE) ns = MAX_STAGE;
+                if (ns < 2) break;
+                if (best_units == 0 || ns > best_ns || (ns == best_ns && uw == best_uw)) { best_units = nu; best_ns = ns; best_uw = uw; }
+                else break;
+            }
         }
+    };
+    if (agg->num_push > 0) {
+        choose(16384);
+        if (best_units == 0 || best_ns < MAX_STAGE) choose(8192);
+    } else {
+        choose(0);
     }
     if (best_units == 0) return KAGNN_EUNSUPPORTED;
     p.uw = best_uw;
@@ -2092,7 +2111,7 @@ int KAGNN_TC2_ENTRY(const KagnnAggregate* agg, int64_t num_rows, const KagnnAffi
     const int unit_bytes = p.unit_floats * (int)sizeof(float);
     p.n_units = best_units;
     p.ns = best_ns;
-    const size_t smem = (size_t)p.n_units * unit_bytes + (size_t)p.ns * p.bstage_bytes + tail;
+    const size_t smem = (size_t)p.n_units * unit_bytes + (size_t)p.ns * p.bstage_bytes + tail0 + (p.relay_bytes ? p.relay_bytes + RELAY_PAD : 0);
 
     // in-kernel LayerNorm statistics need the whole input row in one x unit; wider rows need the pre-pass (ln_stats)
     if (rbf && p.units_per_tile != 1 && p.layers[0].lnw && !p.layers[0].ln_stats) return KAGNN_EUNSUPPORTED;

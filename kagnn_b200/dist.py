@@ -191,7 +191,11 @@ class ShardedNodeModel:
       GIN flavour with ``skip=True`` and B-spline chains (what the pipelined kernel runs); ``mode="auto"`` picks it when it
       applies and falls back to ``"halo"`` otherwise."""
 
-    def __init__(self, model, rank: int, world: int, n_local: int, group=None, mode: str = "halo"):
+    def __init__(self, model, rank: int, world: int, n_local: int, group=None, mode: str = "halo", resident_x_halo: bool = False):
+        # resident_x_halo: keep the halo rows of the INPUT features between forwards for as long as x is the same tensor at the
+        # same version (static features of a static graph: the halo is part of the partitioned input, as in partition-with-halo
+        # graph stores).  Off by default: every forward then fetches the input halo again.
+        self.resident_x_halo = bool(resident_x_halo)
         if mode not in ("halo", "peer", "pull", "pull_overlap", "push", "auto"):
             raise ValueError("mode must be 'halo', 'peer', 'pull', 'pull_overlap', 'push' or 'auto'")
         self.model, self.rank, self.world, self.n_local, self.group = model, rank, world, n_local, group
@@ -203,10 +207,9 @@ class ShardedNodeModel:
         if mode == "auto" and self.peer_supported() and not self._probe_symmetric_memory():
             mode = "halo"                                   # NVLink peer memory not available here: NCCL transport
         if mode == "auto":
-            # "pull" moves only the DISTINCT remote rows (measured 1.28 vs 1.47 ms/step against "peer" on 2 x B200 for the
-            # arxiv-shaped bench, where every remote row is referenced ~3.6 times); "peer" needs no halo matrix at all
-            # on 8 ranks the in-kernel gather measured 2.20 ms/step (NCCL halo 2.90) and is the measured choice there
-            mode = ("peer" if world >= 8 else "pull") if self.peer_supported() else "halo"
+            # measured on 2 x B200, arxiv-shaped bench (ms/step): push 1.00, pull 1.12, peer 1.33, NCCL halo 1.65 -- "push" moves
+            # only the distinct rows a peer references AND hides the transfer behind the producing layer
+            mode = "push" if self.peer_supported() else "halo"
         elif mode in ("peer", "pull", "pull_overlap", "push") and not self.peer_supported():
             raise NotImplementedError("modes 'peer' / 'pull' need a GIN-flavour GKAN_Nodes / GFASTKAN_Nodes with skip=True, "
                                       "spline_order <= 3, G + k <= 8 (FastKAN: <= 8 centres), widths <= 128 and feature widths that "
@@ -275,10 +278,13 @@ class ShardedNodeModel:
             plan = PeerPlan(GraphCSR(ei_local, self.n_local, self.n_local + n_halo), self.n_local, self.world)
             plan.halo_ids = halo_global.to(torch.int32)
             plan.n_halo = n_halo
-            src, dst = edge_index_global[0], edge_index_global[1] - lo
-            mine = (src >= lo) & (src < lo + self.n_local)
-            src_rep = torch.where(mine, src - lo, src + self.n_local)
-            plan.graph_rep = GraphCSR(torch.stack([src_rep, dst]), self.n_local, self.n_local * (self.world + 1))
+            col = plan.graph.col.long()                   # halo numbering -> replica numbering, entry by entry (no second sort)
+            remote = col >= self.n_local
+            if n_halo:
+                col_rep = torch.where(remote, halo_global[(col - self.n_local).clamp_(min=0)] + self.n_local, col).to(torch.int32)
+            else:
+                col_rep = plan.graph.col
+            plan.graph_rep = plan.graph.with_sources(col_rep, self.n_local * (self.world + 1))
             plan.push_mask = self._push_mask(halo_global, dev)
             return plan
         if self.mode == "pull_overlap":
@@ -329,6 +335,21 @@ class ShardedNodeModel:
         dense = float((mask == full).float().mean().item()) if self.n_local else 1.0
         return None if dense > 0.9 else mask
 
+    def input_buffer(self, n_features: int, device) -> Tensor:
+        """This rank's input columns INSIDE the symmetric skip-concat buffer (modes peer / pull / push): a caller that writes x
+        there (H2D copy, data loader) and passes this view to ``forward`` saves the copy of x into the buffer and one barrier."""
+        m = self.model
+        buf, _, _, _ = self._symm_buffer(self.n_local, n_features + len(m.convs) * m.bns[0].num_features, torch.device(device))
+        return buf[:, :n_features]
+
+    def _x_halo(self, plan, x: Tensor, pull: Callable[[], Tensor]) -> Tensor:
+        if not self.resident_x_halo:
+            return pull()
+        key = (x.data_ptr(), x._version, tuple(x.shape))
+        if getattr(plan, "_x_halo_key", None) != key:
+            plan._x_halo, plan._x_halo_key = pull(), key
+        return plan._x_halo
+
     def _side_stream(self, dev):
         if dev.index not in self._side:
             self._side[dev.index] = torch.cuda.Stream(device=dev)
@@ -372,24 +393,30 @@ class ShardedNodeModel:
                     rtab["push"] = torch.tensor([rptrs[q] + 4 * self.rank * n * hid for q in self.push_peers()], dtype=torch.int64,
                                                 device=x.device)
                 reps.append((rbuf, rtab["push"]))
-        hdl.barrier()                                     # every rank is done reading the previous step's buffer
-        ops.gather_rows(x, None, out=buf[:, :f])
+        # x may already live in the buffer (input_buffer()): then it was complete before this call, and the barrier that follows
+        # (every rank is done reading the previous step's buffer -- also the peers that pull x from here) is the only one needed
+        own_input = x.data_ptr() == buf.data_ptr() and x.stride(0) == buf.stride(0)
+        hdl.barrier()
+        if not own_input:
+            ops.gather_rows(x, None, out=buf[:, :f])
         col = 0
         cur = buf[:, :f]
         for l, (conv, bn) in enumerate(zip(m.convs, m.bns)):
-            hdl.barrier()                                 # the slice read below is complete on every rank
+            if l > 0 or not own_input:
+                hdl.barrier()                             # the slice read below is complete on every rank
             dst = buf[:, f + l * hid: f + (l + 1) * hid]
             if self.mode == "push":
                 push = dict(push_y=reps[l][1], push_ld=hid, push_mask=plan.push_mask) if l < n_mp - 1 else {}
                 if l == 0:
-                    halo = ops.gather_rows_peer(table(col), buf.stride(0), self.n_local, plan.halo_ids, cur.size(1))
+                    halo = self._x_halo(plan, x, lambda: ops.gather_rows_peer(table(col), buf.stride(0), self.n_local, plan.halo_ids, cur.size(1)))
                     conv(cur, plan.graph, out=dst, post=m._folds[l].get(bn), x_halo=halo, **push)
                 else:
                     conv(cur, plan.graph_rep, out=dst, post=m._folds[l].get(bn), x_halo=reps[l - 1][0], **push)
             elif self.mode == "pull":
                 # the distinct remote rows, copied once from their owners by a pull kernel on all SMs (678 GB/s measured on two
                 # B200s), then the ordinary halo layer
-                halo = ops.gather_rows_peer(table(col), buf.stride(0), self.n_local, plan.halo_ids, cur.size(1))
+                pull = lambda: ops.gather_rows_peer(table(col), buf.stride(0), self.n_local, plan.halo_ids, cur.size(1))  # noqa: E731
+                halo = self._x_halo(plan, x, pull) if l == 0 else pull()
                 conv(cur, plan.graph, out=dst, post=m._folds[l].get(bn), x_halo=halo)
             elif self.mode == "pull_overlap":
                 # the distinct remote rows, pulled from their owners WHILE the layer runs: the pull kernel (side stream, a few SMs)

@@ -31,6 +31,14 @@ class GraphCSR:
         self._transposed: Optional["GraphCSR"] = None
         self._gcn_t: Optional[Tuple[Tensor, Tensor]] = None
 
+    def with_sources(self, col: Tensor, num_src_nodes: int) -> "GraphCSR":
+        """The same rows and entry order over a RENUMBERED source set (node-sharded graphs: halo numbering -> replica numbering):
+        no second sort, the column array is the only thing that differs."""
+        g = object.__new__(GraphCSR)
+        g.csr = ops.CSR(self.csr.rowptr, col, self.csr.perm, self.csr.num_rows, int(num_src_nodes), self.csr.err_flag)
+        g.num_nodes, g._gcn, g._edge_index, g._square, g._transposed, g._gcn_t = self.num_nodes, None, self._edge_index, False, None, None
+        return g
+
     edge_index = property(lambda self: self._edge_index)          # the COO tensor the CSR was built from
     rowptr = property(lambda self: self.csr.rowptr)
     col = property(lambda self: self.csr.col)

@@ -59,6 +59,20 @@ def main():
     c0 = ops.launch_count
     step()
     launches = ops.launch_count - c0
+    if len(sys.argv) > 1 and sys.argv[1] == "--kernels":
+        # per-kernel device time of one step (torch.profiler / CUPTI), for the notes under profiles/
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step()
+            torch.cuda.synchronize()
+        tot = {}
+        for ev in prof.events():
+            if ev.device_type == torch.autograd.DeviceType.CUDA:
+                d = tot.setdefault(ev.name[:110], [0, 0.0])
+                d[0] += 1
+                d[1] += (ev.time_range.end - ev.time_range.start) / 1e3
+        for name, (cnt, ms) in sorted(tot.items(), key=lambda kv: -kv[1][1])[:25]:
+            print(f"{ms:9.3f} ms  x{cnt:<3d} {name}", file=sys.stderr)
     print(json.dumps({"config": "arxiv-shaped GKAN_Nodes gin 3x64 grid 5, training step (fwd + bwd + Adam), batch-statistics BatchNorm",
                       "nodes": n, "edges": e, "train_step_ms": t_step, "train_mode_forward_ms": t_fwd,
                       "nodes_per_s_training": n / t_step * 1e3, "library_launches_per_step": launches,

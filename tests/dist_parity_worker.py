@@ -49,7 +49,7 @@ def main():
         m = m.to(dev)
         runner = kd.ShardedNodeModel(m, rank, world, n_local)
         auto = kd.ShardedNodeModel(m, rank, world, n_local, mode="auto")
-        assert auto.mode in (("peer", "pull", "halo") if conv_type == "gin" else ("halo",)), (conv_type, fast, auto.mode)
+        assert auto.mode in (("peer", "pull", "push", "halo") if conv_type == "gin" else ("halo",)), (conv_type, fast, auto.mode)
         plan = runner.prepare(ei[:, mine].to(dev))
         y_local = runner.forward(x[rank * n_local:(rank + 1) * n_local].to(dev), plan)
         ys = [torch.empty_like(y_local) for _ in range(world)]
@@ -84,6 +84,27 @@ def main():
                 if rank == 0:
                     print(f"{'fastkan' if fast else 'kan'}/gin {pmode}: vs single {e3:.2e}, vs oracle {e4:.2e}", flush=True)
                 assert e3 <= 1e-5 and e4 <= 1e-4, (pmode, e3, e4)
+            # x written straight into the symmetric buffer (no copy, one barrier fewer) and the input halo kept between steps
+            res = kd.ShardedNodeModel(m, rank, world, n_local, mode="push", resident_x_halo=True)
+            rplan = res.prepare(ei[:, mine].to(dev))
+            xin = res.input_buffer(x.size(1), dev)
+            xin.copy_(x[rank * n_local:(rank + 1) * n_local])
+            for rep in range(3):
+                y_res = res.forward(xin, rplan)
+            ys = [torch.empty_like(y_res) for _ in range(world)]
+            dist.all_gather(ys, y_res)
+            e5 = K.rel_err(torch.cat(ys).cpu(), y_single)
+            assert e5 <= 1e-5, ("push, resident input", e5)
+            xin.mul_(0.5)                                 # a new version of x: the kept halo must be refreshed
+            y_half = res.forward(xin, rplan)
+            ys = [torch.empty_like(y_half) for _ in range(world)]
+            dist.all_gather(ys, y_half)
+            with torch.no_grad():
+                y_half_single = m(x.to(dev) * 0.5, ei.to(dev)).cpu()
+            e6 = K.rel_err(torch.cat(ys).cpu(), y_half_single)
+            if rank == 0:
+                print(f"{'fastkan' if fast else 'kan'}/gin push resident: {e5:.2e}, after x changed {e6:.2e}", flush=True)
+            assert e6 <= 1e-5, ("push, resident input, new x", e6)
     if rank == 0:
         print(f"DIST_PARITY_OK world={world} worst={worst:.2e}", flush=True)
     dist.destroy_process_group()
