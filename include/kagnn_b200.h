@@ -215,6 +215,10 @@ int kagnn_fused_layer_fwd(const KagnnAggregate* agg, int64_t num_rows,
  * shapes fit (spline_order <= 3, G+k <= 8 or RBF G <= 8, out <= 256), else the general fp32 kernel.  Both are GPU paths. */
 enum { KAGNN_PATH_AUTO = 0, KAGNN_PATH_FP32 = 1, KAGNN_PATH_TC = 2 };
 int kagnn_set_path(int mode);
+/* Which kernels the KAN-layer gradients (kagnn_kan_bwd_input / kagnn_kan_bwd_weights) may use: 0 (default) = the tcgen05
+ * kernels when the shape fits (at least 128 rows, out <= 256; weights: G + k <= 8), else the fp32 CUDA-core kernels;
+ * 1 = fp32 kernels only (tests compare the two). */
+int kagnn_set_backward_path(int32_t mode);
 int kagnn_get_launch_counters(int64_t* tc_launches, int64_t* fp32_launches);
 /* Arithmetic of the tensor-core path.  KAGNN_PREC_FP32 (default): every product is formed from bf16 hi/lo pairs (three
  * tcgen05.mma per K step, fp32 accumulate) and matches the reference's fp32 forward within 1e-4.  KAGNN_PREC_BF16: operands are

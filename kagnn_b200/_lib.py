@@ -79,6 +79,7 @@ _SIGNATURES = {
     "kagnn_packed_weight_tc_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "kagnn_pack_kan_weights_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "kagnn_set_path": (C.c_int, [C.c_int]),
+    "kagnn_set_backward_path": (C.c_int, [C.c_int32]),
     "kagnn_get_launch_counters": (C.c_int, [C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "kagnn_set_tc_variant": (C.c_int, [C.c_int]),
     "kagnn_set_precision": (C.c_int, [C.c_int]),

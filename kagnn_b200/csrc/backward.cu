@@ -275,6 +275,7 @@ extern "C" int kagnn_kan_bwd_input(const KagnnKanLayer* layer, const float* x, i
     if (rc != KAGNN_OK) return rc;
     if (num_rows < 0 || (num_rows > 0 && (!x || !dy || !dx)) || ldx < g.in_f || ld_dy < g.out_f || ld_dx < g.in_f) return KAGNN_EINVAL;
     if (num_rows == 0) return KAGNN_OK;
+    KAGNN_TRY_TILED(kagnn_kan_bwd_input_tc(layer, x, ldx, dy, ld_dy, num_rows, dx, ld_dx, stream));
     KAGNN_TRY_TILED(kagnn_kan_bwd_input_tiled(layer, x, ldx, dy, ld_dy, num_rows, dx, ld_dx, stream));
     if (g.in_f > 65535) return KAGNN_EUNSUPPORTED;                                  // gridDim.y
     KAGNN_LAUNCH(kan_bwd_input_kernel, dim3((unsigned)ceil_div64(num_rows, kBwdThreads), (unsigned)g.in_f, 1),
@@ -291,6 +292,7 @@ extern "C" int kagnn_kan_bwd_weights(const KagnnKanLayer* layer, const float* x,
     const int rc = geometry(layer, &g);
     if (rc != KAGNN_OK) return rc;
     if (num_rows < 0 || !d_packed || (num_rows > 0 && (!x || !dy)) || ldx < g.in_f || ld_dy < g.out_f) return KAGNN_EINVAL;
+    if (num_rows > 0) KAGNN_TRY_TILED(kagnn_kan_bwd_weights_tc(layer, x, ldx, dy, ld_dy, num_rows, d_packed, stream));
     if (num_rows > 0) KAGNN_TRY_TILED(kagnn_kan_bwd_weights_tiled(layer, x, ldx, dy, ld_dy, num_rows, d_packed, stream));
     KAGNN_CUDA_TRY(cudaMemsetAsync(d_packed, 0, sizeof(float) * (size_t)g.in_f * (size_t)(g.S + 1) * (size_t)g.out_pad, stream));
     if (num_rows == 0) return KAGNN_OK;

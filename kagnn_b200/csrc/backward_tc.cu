@@ -1,0 +1,552 @@
+// tcgen05 backward of the B-spline KAN layer: the two GEMM-shaped gradients of
+// KANLinear.forward (ekan.py:154-162) on the tensor cores, with the same bf16 hi/lo split (three products, fp32 accumulate
+// in tensor memory) that keeps the forward inside the fp32 parity bound.  Packed layouts as in backward_tiled.cu:
+// P[i][c][o], c = 0..S-1 spline slots, c = S the SiLU base column, o padded to a multiple of 4.
+//
+//   dX   dx[n,i] = sum_c D[n,i,c] T[n,(i,c)],   T = dY . P^T          D = d/dx of (B_0..B_{S-1}, silu)(x[n,i])
+//        One GEMM per 128-row tile and pass of 16 features: M = 128 rows, K = out, N = 16 (S+1).  A = the dY tile, split and
+//        written to tensor memory by its own rows (thread = row = TMEM lane, exactly the forward's A path); B = the 16 (S+1)
+//        weight rows of the pass, split on the fly from the fp32 packed weights into the K-major canonical layout in shared
+//        memory (no pre-packed copy, no workspace); the epilogue reads the (S+1) dot products of a (row, feature) back from
+//        tensor memory and contracts them with the derivative vector it evaluates -- the (N, in (S+1)) intermediate never
+//        reaches HBM.
+//   dW   dP[(i,c),o] = sum_n E[n,(i,c)] dY[n,o]                        E = the S + 1 function values
+//        The reduction runs over ROWS, so both operands are MN-major: thread = row writes, for each feature, its eight slot
+//        values as ONE 16-byte vector -- which is precisely the MN-major no-swizzle core-matrix layout ([unit of 8 M][row][8]),
+//        conflict-free.  M = 128 = 14 features x 8 slots + 2 units of base values, N = out, K = 128 rows per step; the
+//        accumulator stays in tensor memory across all row tiles of a slab and is added to HBM once (one float atomic per
+//        element and slab).  Needs S <= 8 (every configuration the forward's pipelined kernel takes).
+//
+// Both kernels are small (128 threads, no warp specialisation): two or three CTAs share an SM and overlap each other's phases.
+// Shapes outside their limits return KAGNN_EUNSUPPORTED and the caller continues with backward_tiled.cu.
+#include <atomic>
+#include <cstdlib>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+constexpr int kMaxOrderB = 3;           // closed forms for k = 1, 2, 3 (the orders the forward's tensor-core kernels take)
+constexpr int kS1MaxB = 9;              // S + 1 <= 9: G + k <= 8
+constexpr int kThreads = 256;           // two warpgroups: both cover the 128 rows (TMEM lanes) of a tile and split its features
+constexpr float kMagicB = 12582912.0f;  // 1.5 * 2^23: u + kMagic (round down) = floor(u) + kMagic
+constexpr float kLog2eB = 1.4426950408889634f;
+
+struct GeomB {
+    int in_f, out_f, out_pad, G, k, S;
+    float t0, inv_h;
+};
+
+__device__ __forceinline__ float ex2_b(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t prmt_b(uint32_t a, uint32_t b, uint32_t sel) {      // full PTX semantics (sign replication)
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+__device__ __forceinline__ uint32_t pack_trunc_b(float lo_elem, float hi_elem) { return prmt_b(__float_as_uint(lo_elem), __float_as_uint(hi_elem), 0x7632u); }
+__device__ __forceinline__ float trunc_res_b(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack_rn_b(float lo_elem, float hi_elem) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+    return r;
+}
+
+// knot interval of one input value: u = (x - t0) / h clamped into [-0.5, lim + 0.5] (out-of-range inputs and NaN land in the
+// sentinel intervals -1 / lim, which carry no basis), idx = floor(u) + 1 in 0..lim+1, fr = fractional position in [0, 1)
+__device__ __forceinline__ void locate_b(const GeomB& g, float x, int& idx, float& fr) {
+    const float lim = (float)(g.G + 2 * g.k);
+    const float u = fminf(fmaxf((x - g.t0) * g.inv_h, -0.5f), lim + 0.5f);
+    const float t = __fadd_rd(u, kMagicB);
+    fr = u - (t - kMagicB);
+    idx = __float_as_int(t) - (0x4B400000 - 1);
+}
+
+// the k + 1 basis values of the interval (ekan.py:79-112 restricted to its live bases: local polynomials of fr)
+template <int K>
+__device__ __forceinline__ void local_values_b(float fr, float (&b)[4]) {
+    b[2] = 0.f;
+    b[3] = 0.f;
+    if (K == 3) {
+        const float omf = 1.0f - fr, f2 = fr * fr;
+        b[0] = omf * omf * (omf * (1.0f / 6.0f));
+        b[3] = f2 * (fr * (1.0f / 6.0f));
+        b[1] = fmaf(f2, fmaf(fr, 0.5f, -1.0f), 2.0f / 3.0f);
+        b[2] = fmaf(fr, fmaf(fr, fmaf(fr, -0.5f, 0.5f), 0.5f), 1.0f / 6.0f);
+    } else if (K == 2) {
+        const float omf = 1.0f - fr;
+        b[0] = 0.5f * omf * omf;
+        b[2] = 0.5f * fr * fr;
+        b[1] = fmaf(fr, omf, 0.5f);
+    } else {
+        b[0] = 1.0f - fr;
+        b[1] = fr;
+    }
+}
+// their derivatives with respect to x: B'_{j,k} = (B_{j,k-1} - B_{j+1,k-1}) / h
+template <int K>
+__device__ __forceinline__ void local_derivs_b(float fr, float inv_h, float (&d)[4]) {
+    d[2] = 0.f;
+    d[3] = 0.f;
+    if (K == 3) {
+        const float omf = 1.0f - fr;
+        const float q0 = 0.5f * omf * omf, q2 = 0.5f * fr * fr, q1 = fmaf(fr, omf, 0.5f);
+        d[0] = -q0 * inv_h;
+        d[1] = (q0 - q1) * inv_h;
+        d[2] = (q1 - q2) * inv_h;
+        d[3] = q2 * inv_h;
+    } else if (K == 2) {
+        const float omf = 1.0f - fr;
+        d[0] = -omf * inv_h;
+        d[1] = (omf - fr) * inv_h;
+        d[2] = fr * inv_h;
+    } else {
+        d[0] = -inv_h;
+        d[1] = inv_h;
+    }
+}
+
+// selector row of the slot placement for interval row q (interval j = q - 1): output byte b of the 16-byte slot vector takes
+// source byte b - 2 (j - K) of (v0 v1 | v2 v3) when that is in 0..7, else the replicated (zero) sign bit of source byte 1
+__device__ __forceinline__ uint4 lut_row_b(int q, int K, int lim) {
+    const int j = q - 1;
+    const bool inside = j >= 0 && j < lim;
+    uint32_t w[4];
+    for (int m = 0; m < 4; ++m) {
+        uint32_t sel = 0;
+        for (int n = 0; n < 4; ++n) {
+            const int src = 4 * m + n - 2 * (j - K);
+            const uint32_t nib = (inside && src >= 0 && src <= 7) ? (uint32_t)src : 9u;
+            sel |= nib << (4 * n);
+        }
+        w[m] = sel;
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+constexpr int kLutRows = 13;
+
+// MN-major no-swizzle operand: units of 8 consecutive M (or N) elements; element (unit u, k-row r) at u * 2048 + r * 16 bytes for
+// a 128-row K extent, i.e. SBO (unit stride) = 2048, LBO (stride between groups of 8 k-rows) = 128
+__host__ __device__ __forceinline__ uint32_t idesc_bf16_f32_mn(int m, int n) { return tc::idesc_bf16_f32(m, n) | (1u << 15) | (1u << 16); }
+
+// =====================================================================================================================
+// dX
+// =====================================================================================================================
+constexpr int kFP = 16;                 // features per pass
+
+template <int K>
+__global__ void __launch_bounds__(kThreads) kan_bwd_input_tc_kernel(GeomB g, const float* __restrict__ w, const float* __restrict__ x,
+                                                                    long long ldx, const float* __restrict__ dy, long long ld_dy,
+                                                                    long long n_rows, int n_tiles, int KK, uint32_t tmem_cols,
+                                                                    float* __restrict__ dx, long long ld_dx) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int S1 = g.S + 1;
+    const int Np = kFP * S1;                             // N of one pass
+    const int kcs = KK / 8;
+    const uint32_t b_bytes = (uint32_t)kcs * (uint32_t)Np * 16u;     // one of hi / lo
+    uint8_t* b_hi = smem;
+    uint8_t* b_lo = smem + b_bytes;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(b_lo + b_bytes);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, wg = warp >> 2, r128 = tid & 127;
+    const uint32_t a_col = (uint32_t)((Np + 31) & ~31);
+
+    if (warp == 0) tc::tmem_alloc(tmem_slot, tmem_cols);
+    if (tid == 32) {
+        tc::mbar_init(bar, 1);
+        tc::mbar_fence_init();
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t idesc = tc::idesc_bf16_f32(128, Np);
+    const uint32_t lbo_b = (uint32_t)Np * 16u;
+    const int n_pass = (g.in_f + kFP - 1) / kFP;
+    const bool w_vec = (g.out_pad % 4 == 0) && ((reinterpret_cast<uintptr_t>(w) & 15u) == 0);
+    const bool dx_vec = (ld_dx % 4 == 0) && ((reinterpret_cast<uintptr_t>(dx) & 15u) == 0);
+    uint32_t phase = 0;
+
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long row = (long long)tile * 128 + r128;
+        const bool row_ok = row < n_rows;
+        // ---- A = this row of dY, split into bf16 hi / lo, into tensor memory (lane = row; hi at a_col, lo at a_col + KK/2);
+        // the two warpgroups take alternate 8-column groups
+        const float* dyr = dy + (row_ok ? row : 0) * ld_dy;
+        for (int kc = wg; kc < kcs; kc += 2) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int o = kc * 8 + i;
+                v[i] = (row_ok && o < g.out_f) ? __ldg(dyr + o) : 0.f;
+            }
+            uint4 hi, lo;
+            tc::split8(v, hi, lo);
+            tc::tmem_st4(tmem_base + lane_base + a_col + 4u * kc, hi.x, hi.y, hi.z, hi.w);
+            tc::tmem_st4(tmem_base + lane_base + a_col + (uint32_t)KK / 2 + 4u * kc, lo.x, lo.y, lo.z, lo.w);
+        }
+        tc::tmem_st_wait();
+        for (int pass = 0; pass < n_pass; ++pass) {
+            const int f0 = pass * kFP;
+            // ---- B = the 16 (S+1) weight rows of the pass (row n = i (S+1) + c <-> P[f0+i][c][.]), split into the canonical
+            // K-major layout: slab kc = Np rows x 8 bf16
+            for (int idx = tid; idx < kcs * Np; idx += kThreads) {
+                const int kc = idx / Np, n = idx - kc * Np;
+                const int f = f0 + n / S1;
+                float v[8];
+                if (f < g.in_f) {
+                    const float* wr = w + ((long long)f0 * S1 + n) * g.out_pad + kc * 8;
+                    if (w_vec && kc * 8 + 8 <= g.out_pad) {
+                        const float4 t0 = __ldg(reinterpret_cast<const float4*>(wr)), t1 = __ldg(reinterpret_cast<const float4*>(wr) + 1);
+                        v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w; v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] = (kc * 8 + i < g.out_pad) ? __ldg(wr + i) : 0.f;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (kc * 8 + i >= g.out_f) v[i] = 0.f;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+                }
+                uint4 hi, lo;
+                tc::split8(v, hi, lo);
+                *reinterpret_cast<uint4*>(b_hi + (size_t)idx * 16) = hi;
+                *reinterpret_cast<uint4*>(b_lo + (size_t)idx * 16) = lo;
+            }
+            tc::fence_proxy_async_smem();
+            tc::tc_fence_before_sync();
+            __syncthreads();
+            if (tid == 0) {
+                tc::tc_fence_after_sync();
+                uint32_t acc = 0;
+                for (int ks = 0; ks < KK / 16; ++ks) {
+                    const uint64_t dbh = tc::smem_desc(tc::smem_u32(b_hi) + ks * 2 * lbo_b, lbo_b, 128);
+                    const uint64_t dbl = tc::smem_desc(tc::smem_u32(b_lo) + ks * 2 * lbo_b, lbo_b, 128);
+                    const uint32_t tah = tmem_base + a_col + 8u * ks, tal = tah + (uint32_t)KK / 2;
+                    tc::umma_bf16_ts(tmem_base, tah, dbh, idesc, acc);
+                    tc::umma_bf16_ts(tmem_base, tah, dbl, idesc, 1);
+                    tc::umma_bf16_ts(tmem_base, tal, dbh, idesc, 1);
+                    acc = 1;
+                }
+                tc::umma_commit(bar);
+            }
+            tc::mbar_wait(bar, phase);
+            phase ^= 1u;
+            tc::tc_fence_after_sync();
+            // ---- epilogue: warpgroup wg contracts features 8 wg .. 8 wg + 7 of the pass for its 128 rows
+            const float* xr = x + (row_ok ? row : 0) * ldx;
+            float res[8];
+#pragma unroll
+            for (int ii = 0; ii < 8; ++ii) {
+                const int i = 8 * wg + ii, f = f0 + i;
+                res[ii] = 0.f;
+                if (f < g.in_f) {                       // uniform over the warpgroup
+                    float t[16];
+                    {
+                        float t0[8];
+                        tc::tmem_ld8(tmem_base + lane_base + (uint32_t)(i * S1), t0);
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) t[c] = t0[c];
+                        tc::tmem_ld8(tmem_base + lane_base + (uint32_t)(i * S1 + 8), t0);   // only column S (<= 8) of these is used
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) t[8 + c] = t0[c];
+                    }
+                    const float xv = row_ok ? __ldg(xr + f) : 0.f;
+                    int idx;
+                    float fr, d[4];
+                    locate_b(g, xv, idx, fr);
+                    local_derivs_b<K>(fr, g.inv_h, d);
+                    const int j = idx - 1;              // interval; its bases sit on slots j - K .. j
+                    const bool live = j >= 0 && j < g.G + 2 * K;
+                    // window of K + 1 consecutive slots starting at j - K (slots outside 0..S-1 count as zero): barrel shift of the
+                    // slot array, padded with K zeros in front, by jj = j in 0..10
+                    float tp[20];
+#pragma unroll
+                    for (int c = 0; c < 20; ++c) tp[c] = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        if (c < kS1MaxB - 1) tp[K + c] = (c < g.S) ? t[c] : 0.f;
+                    const int jj = live ? j : 0;
+                    float s0[12], s1[8], s2[6], s3[4];
+#pragma unroll
+                    for (int c = 0; c < 12; ++c) s0[c] = (jj & 8) ? tp[c + 8] : tp[c];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) s1[c] = (jj & 4) ? s0[c + 4] : s0[c];
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) s2[c] = (jj & 2) ? s1[c + 2] : s1[c];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) s3[c] = (jj & 1) ? s2[c + 1] : s2[c];
+                    float a = 0.f;
+#pragma unroll
+                    for (int r = 0; r <= K; ++r) a = fmaf(d[r], s3[r], a);
+                    if (!live) a = 0.f;
+                    const float sg = __fdividef(1.0f, 1.0f + ex2_b(-kLog2eB * xv));
+                    const float dbase = sg * fmaf(xv, 1.0f - sg, 1.0f);
+                    float tb = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 16; ++c)
+                        if (c == g.S) tb = t[c];
+                    res[ii] = fmaf(dbase, tb, a);
+                }
+            }
+            if (row_ok) {
+                float* dxr = dx + row * ld_dx + f0 + 8 * wg;
+                if (dx_vec && f0 + 8 * wg + 8 <= g.in_f) {
+                    *reinterpret_cast<float4*>(dxr) = make_float4(res[0], res[1], res[2], res[3]);
+                    *reinterpret_cast<float4*>(dxr + 4) = make_float4(res[4], res[5], res[6], res[7]);
+                } else {
+#pragma unroll
+                    for (int ii = 0; ii < 8; ++ii)
+                        if (f0 + 8 * wg + ii < g.in_f) dxr[ii] = res[ii];
+                }
+            }
+            tc::tc_fence_before_sync();
+        }
+        __syncthreads();                               // every thread is done with tensor memory before the next tile's A lands
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// =====================================================================================================================
+// dW
+// =====================================================================================================================
+constexpr int kFB = 14;                 // features per block: 14 units of 8 slots + 2 units of base values = M 128
+
+template <int K>
+__global__ void __launch_bounds__(kThreads) kan_bwd_weights_tc_kernel(GeomB g, const float* __restrict__ x, long long ldx,
+                                                                      const float* __restrict__ dy, long long ld_dy, long long n_rows,
+                                                                      long long rows_per_slab, int N16, uint32_t tmem_cols, int swap_lbo,
+                                                                      float* __restrict__ dP) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    // A (E^T): 16 units x 128 rows x 16 B, hi then lo;  B (dY): N16/8 units x 128 rows x 16 B, hi then lo
+    constexpr uint32_t kABytes = 16u * 2048u;
+    const uint32_t b_bytes = (uint32_t)(N16 / 8) * 2048u;
+    uint8_t* a_hi = smem;
+    uint8_t* a_lo = a_hi + kABytes;
+    uint8_t* b_hi = a_lo + kABytes;
+    uint8_t* b_lo = b_hi + b_bytes;
+    uint4* lut = reinterpret_cast<uint4*>(b_lo + b_bytes);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(lut + kLutRows);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, wg = warp >> 2, r128 = tid & 127;
+    const int f0 = blockIdx.x * kFB;
+    const long long r_beg = (long long)blockIdx.y * rows_per_slab, r_end = min(n_rows, r_beg + rows_per_slab);
+
+    if (warp == 0) tc::tmem_alloc(tmem_slot, tmem_cols);
+    if (tid == 32) {
+        tc::mbar_init(bar, 1);
+        tc::mbar_fence_init();
+    }
+    if (tid >= 64 && tid < 64 + kLutRows) lut[tid - 64] = lut_row_b(tid - 64, K, g.G + 2 * K);
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t idesc = idesc_bf16_f32_mn(128, N16);
+    const uint32_t lbo = swap_lbo ? 2048u : 128u, sbo = swap_lbo ? 128u : 2048u;
+    uint32_t phase = 0, acc = 0;
+    // warpgroup 0: features 0..7 (+ their base values, unit 14) and the first quarter of dY's units;
+    // warpgroup 1: features 8..13 (+ base values, unit 15) and the rest of dY
+    const int fi0 = wg ? 8 : 0, fi1 = wg ? kFB : 8;
+    const int nu = N16 / 8, u_split = nu / 4;
+    const int u0 = wg ? u_split : 0, u1 = wg ? nu : u_split;
+
+    for (long long rt = r_beg; rt < r_end; rt += 128) {
+        const long long row = rt + r128;
+        const bool row_ok = row < r_end;
+        // ---- E^T: this row's slot values, one 16-byte vector per feature (unit u = feature), base values in units 14 / 15
+        const float* xr = x + (row_ok ? row : 0) * ldx;
+        float bb[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) bb[i] = 0.f;
+#pragma unroll
+        for (int ii = 0; ii < 8; ++ii) {
+            const int i = fi0 + ii;
+            if (i < fi1) {                              // uniform over the warpgroup
+                const bool on = row_ok && (f0 + i) < g.in_f;
+                const float xv = on ? __ldg(xr + f0 + i) : 0.f;
+                int idx;
+                float fr, b[4];
+                locate_b(g, xv, idx, fr);
+                local_values_b<K>(fr, b);
+                // every value is >= 0, so hi = truncation to bf16 and lo = bf16(b - hi) are >= 0 too: their sign bits are 0, which lets
+                // the byte permute synthesise the empty slots by sign replication (selector nibble 9)
+                const uint32_t h01 = pack_trunc_b(b[0], b[1]), h23 = pack_trunc_b(b[2], b[3]);
+                const uint32_t l01 = pack_rn_b(trunc_res_b(b[0]), trunc_res_b(b[1])), l23 = pack_rn_b(trunc_res_b(b[2]), trunc_res_b(b[3]));
+                uint4 sel = lut[idx];
+                if (!on) sel = make_uint4(0x9999u, 0x9999u, 0x9999u, 0x9999u);
+                const uint4 hi = make_uint4(prmt_b(h01, h23, sel.x), prmt_b(h01, h23, sel.y), prmt_b(h01, h23, sel.z), prmt_b(h01, h23, sel.w));
+                const uint4 lo = make_uint4(prmt_b(l01, l23, sel.x), prmt_b(l01, l23, sel.y), prmt_b(l01, l23, sel.z), prmt_b(l01, l23, sel.w));
+                *reinterpret_cast<uint4*>(a_hi + (size_t)i * 2048 + r128 * 16) = hi;
+                *reinterpret_cast<uint4*>(a_lo + (size_t)i * 2048 + r128 * 16) = lo;
+                bb[ii] = on ? __fdividef(xv, 1.0f + ex2_b(-kLog2eB * xv)) : 0.f;
+            }
+        }
+        {
+            uint4 hi, lo;
+            tc::split8(bb, hi, lo);
+            *reinterpret_cast<uint4*>(a_hi + (size_t)(kFB + wg) * 2048 + r128 * 16) = hi;
+            *reinterpret_cast<uint4*>(a_lo + (size_t)(kFB + wg) * 2048 + r128 * 16) = lo;
+        }
+        // ---- dY row: N16 / 8 units
+        const float* dyr = dy + (row_ok ? row : 0) * ld_dy;
+        for (int u = u0; u < u1; ++u) {
+            float v[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int o = 8 * u + c;
+                v[c] = (row_ok && o < g.out_f) ? __ldg(dyr + o) : 0.f;
+            }
+            uint4 hi, lo;
+            tc::split8(v, hi, lo);
+            *reinterpret_cast<uint4*>(b_hi + (size_t)u * 2048 + r128 * 16) = hi;
+            *reinterpret_cast<uint4*>(b_lo + (size_t)u * 2048 + r128 * 16) = lo;
+        }
+        tc::fence_proxy_async_smem();
+        tc::tc_fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            tc::tc_fence_after_sync();
+            for (int ks = 0; ks < 8; ++ks) {            // K = 16 rows per step: two groups of 8 k-rows, 256 bytes
+                const uint32_t off = (uint32_t)ks * 256u;
+                const uint64_t dah = tc::smem_desc(tc::smem_u32(a_hi) + off, lbo, sbo), dal = tc::smem_desc(tc::smem_u32(a_lo) + off, lbo, sbo);
+                const uint64_t dbh = tc::smem_desc(tc::smem_u32(b_hi) + off, lbo, sbo), dbl = tc::smem_desc(tc::smem_u32(b_lo) + off, lbo, sbo);
+                tc::umma_bf16(tmem_base, dah, dbh, idesc, acc);
+                tc::umma_bf16(tmem_base, dah, dbl, idesc, 1);
+                tc::umma_bf16(tmem_base, dal, dbh, idesc, 1);
+                acc = 1;
+            }
+            tc::umma_commit(bar);
+        }
+        tc::mbar_wait(bar, phase);                      // the operands in shared memory may be overwritten
+        phase ^= 1u;
+    }
+    // ---- the slab's sums: lane m of tensor memory = row m of the block's 128 gradient rows; the warpgroups split the columns
+    tc::tc_fence_after_sync();
+    if (r_beg < r_end) {
+        const int m = r128, u = m >> 3, c = m & 7;
+        long long dst = -1;
+        if (u < kFB) {
+            if (f0 + u < g.in_f && c < g.S) dst = ((long long)(f0 + u) * (g.S + 1) + c) * g.out_pad;
+        } else {
+            const int i = (u - kFB) * 8 + c;
+            if (i < kFB && f0 + i < g.in_f) dst = ((long long)(f0 + i) * (g.S + 1) + g.S) * g.out_pad;
+        }
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        for (int o0 = 8 * wg; o0 < N16; o0 += 16) {
+            float v[8];
+            tc::tmem_ld8(tmem_base + lane_base + (uint32_t)o0, v);   // warp-collective: every lane takes part
+            if (dst >= 0) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (o0 + q < g.out_f && v[q] != 0.f) atomicAdd(dP + dst + o0 + q, v[q]);
+            }
+        }
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base, tmem_cols);
+}
+
+int geometry_b(const KagnnKanLayer* L, GeomB* g) {
+    if (!L || !L->packed_w || L->basis != KAGNN_BASIS_BSPLINE) return KAGNN_EUNSUPPORTED;
+    if (L->in_features <= 0 || L->out_features <= 0 || L->grid_size < 1 || L->spline_order < 1 || L->spline_order > 4) return KAGNN_EUNSUPPORTED;
+    if (!(L->h > 0.f)) return KAGNN_EUNSUPPORTED;
+    g->in_f = L->in_features;
+    g->out_f = L->out_features;
+    g->out_pad = pad4(L->out_features);
+    g->G = L->grid_size;
+    g->k = L->spline_order;
+    g->S = L->grid_size + L->spline_order;
+    g->t0 = L->t0;
+    g->inv_h = 1.0f / L->h;
+    return KAGNN_OK;
+}
+
+std::atomic<int> g_bwd_path{0};         // 0 = auto (tensor cores first), 1 = fp32 kernels only (tests / comparisons)
+}  // namespace
+
+extern "C" int kagnn_set_backward_path(int32_t mode) {
+    if (mode != 0 && mode != 1) return KAGNN_EINVAL;
+    g_bwd_path.store(mode);
+    return KAGNN_OK;
+}
+
+int kagnn_kan_bwd_input_tc(const KagnnKanLayer* layer, const float* x, int64_t ldx, const float* dy, int64_t ld_dy, int64_t num_rows,
+                           float* dx, int64_t ld_dx, cudaStream_t stream) {
+    if (g_bwd_path.load() != 0) return KAGNN_EUNSUPPORTED;
+    GeomB g;
+    int rc = geometry_b(layer, &g);
+    if (rc != KAGNN_OK) return rc;
+    const int S1 = g.S + 1;
+    if (num_rows < 128 || S1 > kS1MaxB || g.k > kMaxOrderB || g.out_f > 256) return KAGNN_EUNSUPPORTED;   // small batches: not worth a tile
+    DeviceProps props{};
+    rc = kagnn_get_props(&props);
+    if (rc != KAGNN_OK) return rc;
+    if (props.cc_major != 10) return KAGNN_EUNSUPPORTED;
+    const int K = ((g.out_f + 15) / 16) * 16;
+    const int Np = kFP * S1;
+    const uint32_t a_col = (uint32_t)((Np + 31) & ~31);
+    if (a_col + (uint32_t)K > 512u) return KAGNN_EUNSUPPORTED;
+    const uint32_t cols = tc::tmem_cols_pow2(a_col + (uint32_t)K);
+    const size_t smem = (size_t)2 * (K / 8) * Np * 16 + 64;
+    if (smem > (size_t)props.max_smem) return KAGNN_EUNSUPPORTED;
+    const int n_tiles = (int)ceil_div64(num_rows, 128);
+    // CTAs per SM: limited by tensor-memory columns and shared memory (the kernel overlaps its phases only across CTAs)
+    int per_sm = (int)(512u / cols);
+    const int by_smem = (int)((size_t)props.max_smem / (smem + 1024));
+    if (per_sm > by_smem) per_sm = by_smem;
+    if (per_sm > 4) per_sm = 4;
+    if (per_sm < 1) per_sm = 1;
+    const int grid = n_tiles < props.num_sms * per_sm ? n_tiles : props.num_sms * per_sm;
+    auto kern = g.k == 3 ? kan_bwd_input_tc_kernel<3> : (g.k == 2 ? kan_bwd_input_tc_kernel<2> : kan_bwd_input_tc_kernel<1>);
+    KAGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)props.max_smem));
+    kern<<<(unsigned)grid, kThreads, smem, stream>>>(g, layer->packed_w, x, (long long)ldx, dy, (long long)ld_dy, (long long)num_rows, n_tiles, K,
+                                               cols, dx, (long long)ld_dx);
+    KAGNN_LAUNCH_CHECK();
+    return KAGNN_OK;
+}
+
+int kagnn_kan_bwd_weights_tc(const KagnnKanLayer* layer, const float* x, int64_t ldx, const float* dy, int64_t ld_dy, int64_t num_rows,
+                             float* d_packed, cudaStream_t stream) {
+    if (g_bwd_path.load() != 0) return KAGNN_EUNSUPPORTED;
+    GeomB g;
+    int rc = geometry_b(layer, &g);
+    if (rc != KAGNN_OK) return rc;
+    if (num_rows < 128 || g.S > 8 || g.k > kMaxOrderB || g.out_f > 256) return KAGNN_EUNSUPPORTED;
+    DeviceProps props{};
+    rc = kagnn_get_props(&props);
+    if (rc != KAGNN_OK) return rc;
+    if (props.cc_major != 10) return KAGNN_EUNSUPPORTED;
+    const int N16 = ((g.out_f + 15) / 16) * 16;
+    const uint32_t cols = tc::tmem_cols_pow2((uint32_t)N16);
+    const size_t smem = (size_t)2 * 16 * 2048 + (size_t)2 * (N16 / 8) * 2048 + kLutRows * 16 + 64;
+    if (smem > (size_t)props.max_smem) return KAGNN_EUNSUPPORTED;
+    KAGNN_CUDA_TRY(cudaMemsetAsync(d_packed, 0, sizeof(float) * (size_t)g.in_f * (size_t)(g.S + 1) * (size_t)g.out_pad, stream));
+    const int fblocks = (g.in_f + kFB - 1) / kFB;
+    // row slabs: about three CTAs per SM over the whole grid, at least 128 rows each
+    int64_t slabs = ceil_div64((int64_t)props.num_sms * 3, fblocks);
+    if (slabs > ceil_div64(num_rows, 128)) slabs = ceil_div64(num_rows, 128);
+    if (slabs > 65535) slabs = 65535;
+    if (slabs < 1) slabs = 1;
+    int64_t rows_per_slab = ceil_div64(ceil_div64(num_rows, slabs), 128) * 128;
+    slabs = ceil_div64(num_rows, rows_per_slab);
+    int swap = 0;
+#ifdef KAGNN_DEBUG_KNOBS
+    if (const char* e = getenv("KAGNN_DEBUG_DW_SWAP")) swap = atoi(e);
+#endif
+    auto kern = g.k == 3 ? kan_bwd_weights_tc_kernel<3> : (g.k == 2 ? kan_bwd_weights_tc_kernel<2> : kan_bwd_weights_tc_kernel<1>);
+    KAGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)props.max_smem));
+    kern<<<dim3((unsigned)fblocks, (unsigned)slabs, 1), kThreads, smem, stream>>>(
+        g, x, (long long)ldx, dy, (long long)ld_dy, (long long)num_rows, (long long)rows_per_slab, N16, cols, swap, d_packed);
+    KAGNN_LAUNCH_CHECK();
+    return KAGNN_OK;
+}

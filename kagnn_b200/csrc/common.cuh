@@ -46,6 +46,11 @@ int kagnn_fused_fwd_tc2_g16(const KagnnAggregate* agg, int64_t num_rows, const K
 int kagnn_aggregate_only_tc2(const KagnnAggregate* agg, int64_t num_rows, const KagnnAffine* pre, float* agg_out,
                              int64_t ld_agg_out, cudaStream_t stream);
 // shared-memory-tiled B-spline backward (backward_tiled.cu); KAGNN_EUNSUPPORTED -> the general kernels of backward.cu
+// tcgen05 versions (backward_tc.cu): tried first, KAGNN_EUNSUPPORTED outside their limits
+int kagnn_kan_bwd_weights_tc(const KagnnKanLayer* layer, const float* x, int64_t ldx, const float* dy, int64_t ld_dy, int64_t num_rows,
+                             float* d_packed, cudaStream_t stream);
+int kagnn_kan_bwd_input_tc(const KagnnKanLayer* layer, const float* x, int64_t ldx, const float* dy, int64_t ld_dy, int64_t num_rows,
+                           float* dx, int64_t ld_dx, cudaStream_t stream);
 int kagnn_kan_bwd_weights_tiled(const KagnnKanLayer* layer, const float* x, int64_t ldx, const float* dy, int64_t ld_dy, int64_t num_rows,
                                 float* d_packed, cudaStream_t stream);
 int kagnn_kan_bwd_input_tiled(const KagnnKanLayer* layer, const float* x, int64_t ldx, const float* dy, int64_t ld_dy, int64_t num_rows,

@@ -449,6 +449,11 @@ def set_path(mode: int) -> None:
     L.check(L.lib().kagnn_set_path(mode), "set_path")
 
 
+def set_backward_path(mode: int) -> None:
+    """0 = tcgen05 gradient kernels when the shape fits (default), 1 = fp32 CUDA-core kernels only (kagnn_set_backward_path)."""
+    L.check(L.lib().kagnn_set_backward_path(int(mode)), "set_backward_path")
+
+
 def set_precision(mode) -> None:
     """``"fp32"`` (default: bf16 hi/lo split, three products per K step, matches the reference's fp32 forward within 1e-4) or
     ``"bf16"`` (one bf16 product per K step, fp32 accumulate: BASELINE config C5) -- see kagnn_set_precision."""
