@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(kThreads) kan_bwd_input_tc_kernel(GeomB g, con
     const int n_pass = (g.in_f + kFP - 1) / kFP;
     const bool w_vec = (g.out_pad % 4 == 0) && ((reinterpret_cast<uintptr_t>(w) & 15u) == 0);
     const bool dx_vec = (ld_dx % 4 == 0) && ((reinterpret_cast<uintptr_t>(dx) & 15u) == 0);
+    const bool dy_vec = g.out_f % 4 == 0 && ld_dy % 4 == 0 && ((reinterpret_cast<uintptr_t>(dy) & 15u) == 0);
     uint32_t phase = 0;
 
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -177,47 +178,83 @@ __global__ void __launch_bounds__(kThreads) kan_bwd_input_tc_kernel(GeomB g, con
         // ---- A = this row of dY, split into bf16 hi / lo, into tensor memory (lane = row; hi at a_col, lo at a_col + KK/2);
         // the two warpgroups take alternate 8-column groups
         const float* dyr = dy + (row_ok ? row : 0) * ld_dy;
-        for (int kc = wg; kc < kcs; kc += 2) {
-            float v[8];
+        for (int kb = wg; kb < kcs; kb += 8) {          // four 8-column groups per round: their loads are in flight together
+            float4 q[4][2];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int o = kc * 8 + i;
-                v[i] = (row_ok && o < g.out_f) ? __ldg(dyr + o) : 0.f;
+            for (int j = 0; j < 4; ++j) {
+                const int kc = kb + 2 * j;
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (dy_vec) {
+                    q[j][0] = (row_ok && kc < kcs && kc * 8 + 4 <= g.out_f) ? __ldg(reinterpret_cast<const float4*>(dyr + kc * 8)) : z;
+                    q[j][1] = (row_ok && kc < kcs && kc * 8 + 8 <= g.out_f) ? __ldg(reinterpret_cast<const float4*>(dyr + kc * 8 + 4)) : z;
+                } else {
+                    float v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int o = kc * 8 + i;
+                        v[i] = (row_ok && kc < kcs && o < g.out_f) ? __ldg(dyr + o) : 0.f;
+                    }
+                    q[j][0] = make_float4(v[0], v[1], v[2], v[3]);
+                    q[j][1] = make_float4(v[4], v[5], v[6], v[7]);
+                }
             }
-            uint4 hi, lo;
-            tc::split8(v, hi, lo);
-            tc::tmem_st4(tmem_base + lane_base + a_col + 4u * kc, hi.x, hi.y, hi.z, hi.w);
-            tc::tmem_st4(tmem_base + lane_base + a_col + (uint32_t)KK / 2 + 4u * kc, lo.x, lo.y, lo.z, lo.w);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int kc = kb + 2 * j;
+                if (kc < kcs) {
+                    const float v[8] = {q[j][0].x, q[j][0].y, q[j][0].z, q[j][0].w, q[j][1].x, q[j][1].y, q[j][1].z, q[j][1].w};
+                    uint4 hi, lo;
+                    tc::split8(v, hi, lo);
+                    tc::tmem_st4(tmem_base + lane_base + a_col + 4u * kc, hi.x, hi.y, hi.z, hi.w);
+                    tc::tmem_st4(tmem_base + lane_base + a_col + (uint32_t)KK / 2 + 4u * kc, lo.x, lo.y, lo.z, lo.w);
+                }
+            }
         }
         tc::tmem_st_wait();
         for (int pass = 0; pass < n_pass; ++pass) {
             const int f0 = pass * kFP;
             // ---- B = the 16 (S+1) weight rows of the pass (row n = i (S+1) + c <-> P[f0+i][c][.]), split into the canonical
             // K-major layout: slab kc = Np rows x 8 bf16
-            for (int idx = tid; idx < kcs * Np; idx += kThreads) {
-                const int kc = idx / Np, n = idx - kc * Np;
-                const int f = f0 + n / S1;
-                float v[8];
-                if (f < g.in_f) {
-                    const float* wr = w + ((long long)f0 * S1 + n) * g.out_pad + kc * 8;
-                    if (w_vec && kc * 8 + 8 <= g.out_pad) {
-                        const float4 t0 = __ldg(reinterpret_cast<const float4*>(wr)), t1 = __ldg(reinterpret_cast<const float4*>(wr) + 1);
-                        v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w; v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
-                    } else {
+            for (int base = tid; base < kcs * Np; base += 4 * kThreads) {     // four items per round: their loads are in flight together
+                float4 q[4][2];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) v[i] = (kc * 8 + i < g.out_pad) ? __ldg(wr + i) : 0.f;
+                for (int j = 0; j < 4; ++j) {
+                    const int idx = base + j * kThreads;
+                    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                    q[j][0] = z;
+                    q[j][1] = z;
+                    if (idx < kcs * Np) {
+                        const int kc = idx / Np, n = idx - kc * Np;
+                        if (f0 + n / S1 < g.in_f) {
+                            const float* wr = w + ((long long)f0 * S1 + n) * g.out_pad + kc * 8;
+                            if (w_vec && kc * 8 + 8 <= g.out_pad) {
+                                q[j][0] = __ldg(reinterpret_cast<const float4*>(wr));
+                                q[j][1] = __ldg(reinterpret_cast<const float4*>(wr) + 1);
+                            } else {
+                                float v[8];
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) v[i] = (kc * 8 + i < g.out_pad) ? __ldg(wr + i) : 0.f;
+                                q[j][0] = make_float4(v[0], v[1], v[2], v[3]);
+                                q[j][1] = make_float4(v[4], v[5], v[6], v[7]);
+                            }
+                        }
                     }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        if (kc * 8 + i >= g.out_f) v[i] = 0.f;
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = 0.f;
                 }
-                uint4 hi, lo;
-                tc::split8(v, hi, lo);
-                *reinterpret_cast<uint4*>(b_hi + (size_t)idx * 16) = hi;
-                *reinterpret_cast<uint4*>(b_lo + (size_t)idx * 16) = lo;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int idx = base + j * kThreads;
+                    if (idx < kcs * Np) {
+                        const int kc = idx / Np;
+                        float v[8] = {q[j][0].x, q[j][0].y, q[j][0].z, q[j][0].w, q[j][1].x, q[j][1].y, q[j][1].z, q[j][1].w};
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            if (kc * 8 + i >= g.out_f) v[i] = 0.f;
+                        uint4 hi, lo;
+                        tc::split8(v, hi, lo);
+                        *reinterpret_cast<uint4*>(b_hi + (size_t)idx * 16) = hi;
+                        *reinterpret_cast<uint4*>(b_lo + (size_t)idx * 16) = lo;
+                    }
+                }
             }
             tc::fence_proxy_async_smem();
             tc::tc_fence_before_sync();
@@ -236,11 +273,18 @@ __global__ void __launch_bounds__(kThreads) kan_bwd_input_tc_kernel(GeomB g, con
                 }
                 tc::umma_commit(bar);
             }
+            // this warpgroup's x values of the pass: requested before the wait, so the loads fly while the tensor pipe works
+            const float* xr = x + (row_ok ? row : 0) * ldx;
+            float xq[8];
+#pragma unroll
+            for (int ii = 0; ii < 8; ++ii) {
+                const int f = f0 + 8 * wg + ii;
+                xq[ii] = (row_ok && f < g.in_f) ? __ldg(xr + f) : 0.f;
+            }
             tc::mbar_wait(bar, phase);
             phase ^= 1u;
             tc::tc_fence_after_sync();
             // ---- epilogue: warpgroup wg contracts features 8 wg .. 8 wg + 7 of the pass for its 128 rows
-            const float* xr = x + (row_ok ? row : 0) * ldx;
             float res[8];
 #pragma unroll
             for (int ii = 0; ii < 8; ++ii) {
@@ -257,7 +301,7 @@ __global__ void __launch_bounds__(kThreads) kan_bwd_input_tc_kernel(GeomB g, con
 #pragma unroll
                         for (int c = 0; c < 8; ++c) t[8 + c] = t0[c];
                     }
-                    const float xv = row_ok ? __ldg(xr + f) : 0.f;
+                    const float xv = xq[ii];
                     int idx;
                     float fr, d[4];
                     locate_b(g, xv, idx, fr);
@@ -359,11 +403,37 @@ __global__ void __launch_bounds__(kThreads) kan_bwd_weights_tc_kernel(GeomB g, c
     const int nu = N16 / 8, u_split = nu / 4;
     const int u0 = wg ? u_split : 0, u1 = wg ? nu : u_split;
 
+    // operands of a tile are fetched into registers one tile ahead (while the tensor pipe works on the previous one): the x values
+    // of this warpgroup's features and, when dY is at most 64 wide and 16-byte aligned, its dY units
+    constexpr int kPU = 6;
+    const bool dy_pf = nu <= 8 && g.out_f % 4 == 0 && ld_dy % 4 == 0 && ((reinterpret_cast<uintptr_t>(dy) & 15u) == 0);
+    float xq[8];
+    float4 dq[kPU][2];
+    auto load_tile = [&](long long rt_) {
+        const long long row = rt_ + r128;
+        const bool row_ok = row < r_end;
+        const float* xr = x + (row_ok ? row : 0) * ldx;
+#pragma unroll
+        for (int ii = 0; ii < 8; ++ii) {
+            const int i = fi0 + ii;
+            xq[ii] = (row_ok && i < fi1 && (f0 + i) < g.in_f) ? __ldg(xr + f0 + i) : 0.f;
+        }
+        if (dy_pf) {
+            const float* dyr = dy + (row_ok ? row : 0) * ld_dy;
+#pragma unroll
+            for (int q = 0; q < kPU; ++q) {
+                const int u = u0 + q;
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                dq[q][0] = (row_ok && u < u1 && 8 * u + 4 <= g.out_f) ? __ldg(reinterpret_cast<const float4*>(dyr + 8 * u)) : z;
+                dq[q][1] = (row_ok && u < u1 && 8 * u + 8 <= g.out_f) ? __ldg(reinterpret_cast<const float4*>(dyr + 8 * u + 4)) : z;
+            }
+        }
+    };
+    if (r_beg < r_end) load_tile(r_beg);
     for (long long rt = r_beg; rt < r_end; rt += 128) {
         const long long row = rt + r128;
         const bool row_ok = row < r_end;
         // ---- E^T: this row's slot values, one 16-byte vector per feature (unit u = feature), base values in units 14 / 15
-        const float* xr = x + (row_ok ? row : 0) * ldx;
         float bb[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) bb[i] = 0.f;
@@ -372,7 +442,7 @@ __global__ void __launch_bounds__(kThreads) kan_bwd_weights_tc_kernel(GeomB g, c
             const int i = fi0 + ii;
             if (i < fi1) {                              // uniform over the warpgroup
                 const bool on = row_ok && (f0 + i) < g.in_f;
-                const float xv = on ? __ldg(xr + f0 + i) : 0.f;
+                const float xv = xq[ii];
                 int idx;
                 float fr, b[4];
                 locate_b(g, xv, idx, fr);
@@ -397,18 +467,32 @@ __global__ void __launch_bounds__(kThreads) kan_bwd_weights_tc_kernel(GeomB g, c
             *reinterpret_cast<uint4*>(a_lo + (size_t)(kFB + wg) * 2048 + r128 * 16) = lo;
         }
         // ---- dY row: N16 / 8 units
-        const float* dyr = dy + (row_ok ? row : 0) * ld_dy;
-        for (int u = u0; u < u1; ++u) {
-            float v[8];
+        if (dy_pf) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const int o = 8 * u + c;
-                v[c] = (row_ok && o < g.out_f) ? __ldg(dyr + o) : 0.f;
+            for (int q = 0; q < kPU; ++q) {
+                const int u = u0 + q;
+                if (u < u1) {
+                    const float v[8] = {dq[q][0].x, dq[q][0].y, dq[q][0].z, dq[q][0].w, dq[q][1].x, dq[q][1].y, dq[q][1].z, dq[q][1].w};
+                    uint4 hi, lo;
+                    tc::split8(v, hi, lo);
+                    *reinterpret_cast<uint4*>(b_hi + (size_t)u * 2048 + r128 * 16) = hi;
+                    *reinterpret_cast<uint4*>(b_lo + (size_t)u * 2048 + r128 * 16) = lo;
+                }
             }
-            uint4 hi, lo;
-            tc::split8(v, hi, lo);
-            *reinterpret_cast<uint4*>(b_hi + (size_t)u * 2048 + r128 * 16) = hi;
-            *reinterpret_cast<uint4*>(b_lo + (size_t)u * 2048 + r128 * 16) = lo;
+        } else {
+            const float* dyr = dy + (row_ok ? row : 0) * ld_dy;
+            for (int u = u0; u < u1; ++u) {
+                float v[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int o = 8 * u + c;
+                    v[c] = (row_ok && o < g.out_f) ? __ldg(dyr + o) : 0.f;
+                }
+                uint4 hi, lo;
+                tc::split8(v, hi, lo);
+                *reinterpret_cast<uint4*>(b_hi + (size_t)u * 2048 + r128 * 16) = hi;
+                *reinterpret_cast<uint4*>(b_lo + (size_t)u * 2048 + r128 * 16) = lo;
+            }
         }
         tc::fence_proxy_async_smem();
         tc::tc_fence_before_sync();
@@ -426,6 +510,7 @@ __global__ void __launch_bounds__(kThreads) kan_bwd_weights_tc_kernel(GeomB g, c
             }
             tc::umma_commit(bar);
         }
+        if (rt + 128 < r_end) load_tile(rt + 128);      // in flight while the tensor pipe works
         tc::mbar_wait(bar, phase);                      // the operands in shared memory may be overwritten
         phase ^= 1u;
     }
