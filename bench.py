@@ -424,7 +424,7 @@ def main():
         if runner.mode in ("pull", "pull_overlap"):
             rows, what = int(plan.n_halo), "distinct remote rows (pulled once per layer)"
         elif runner.mode == "push":
-            rows, what = int(plan.n_halo), ("distinct remote rows: x pulled before layer 0, hidden rows pushed by their producer layer "
+            rows, what = int(plan.need.sum()), ("distinct remote rows: x pulled before layer 0, hidden rows pushed by their producer layer "
                                             "(masked to the ranks that reference them)")
         elif runner.mode == "peer":
             col = plan.graph.col.long()

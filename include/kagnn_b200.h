@@ -252,6 +252,12 @@ int kagnn_gather_rows(const float* x, int64_t ldx, const int32_t* index, int64_t
 int kagnn_gather_rows_peer(const float* const* peer_x, int64_t ldx, int64_t rows_per_rank, const int32_t* ids,
                            int64_t num_rows, int32_t num_cols, float* out, int64_t ld_out, void* stream);
 
+/* The pull without an id list: every row id in [0, total_rows) with need[id] != 0 is copied from its owner into out[id] -- `out`
+ * is a replica of the whole (total_rows x num_cols) matrix of which only the marked rows are filled.  Lets the sharded forward
+ * plan a transfer with one scatter into a byte map instead of sort / unique / compaction of the remote ids. */
+int kagnn_gather_rows_peer_masked(const float* const* peer_x, int64_t ldx, int64_t rows_per_rank, const uint8_t* need,
+                                  int64_t total_rows, int32_t num_cols, float* out, int64_t ld_out, void* stream);
+
 /* The same pull in first-use order with progress flags (see KagnnAggregate.halo_flags): a persistent kernel of num_ctas blocks
  * copies halo rows [256 c, 256 c + 256) chunk by chunk (block b takes chunks b, b + num_ctas, ...); each of its 16 warps adds 1
  * to chunk_flags[c] (release) when its rows are stored, so a chunk of the epoch-th use is complete at 16 * epoch.  chunk_flags

@@ -96,6 +96,8 @@ _SIGNATURES = {
                                             C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]),
     "kagnn_gather_rows_peer": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64,
                                          C.c_void_p]),
+    "kagnn_gather_rows_peer_masked": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64,
+                                                C.c_void_p]),
     "kagnn_gather_rows_peer_ordered": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64,
                                                  C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "kagnn_bn_dropout_train_workspace": (C.c_size_t, [C.c_int32]),

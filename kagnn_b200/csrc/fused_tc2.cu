@@ -157,6 +157,8 @@ struct Tc2Params {
     int ag;                                               // 1: asynchronous (cp.async ring) gather, 64-column units
     int wide;                                             // 1: one layer up to 256 outputs wide: a single 256-column accumulator region
     int bf16;                                             // 1: single bf16 product (A_hi . W_hi), kagnn_set_precision(KAGNN_PREC_BF16)
+    int n_items;                                          // work items of the persistent loops: n_tiles x n_split
+    int n_split, units_per_item;                          // split-K (few tiles, long rows): an item = one tile x a window of x units; partial sums meet in y by float atomics
     int relay_bytes;                                      // pushed output: shared-memory relay of the push warps (16 KB if the rings keep their depth, else 8 KB)
     LayerT2 layers[KAGNN_MAX_LAYERS];
 };
@@ -166,7 +168,7 @@ struct Tc2Params {
 // (no divisions in the per-chunk paths).
 struct ChunkCursor {
     int group, j, n_oct, octs;
-    __device__ __forceinline__ explicit ChunkCursor(int F_pad) : group(0), j(0), n_oct(min(8, F_pad >> 3)), octs(F_pad >> 3) {}
+    __device__ __forceinline__ explicit ChunkCursor(int F_pad, int g0 = 0) : group(g0), j(0), n_oct(min(8, (F_pad >> 3) - 8 * g0)), octs(F_pad >> 3) {}
     __device__ __forceinline__ bool base() const { return j == n_oct; }
     __device__ __forceinline__ int nk() const { return j == n_oct ? n_oct : 8; }
     __device__ __forceinline__ uint32_t b_off(int N_pad) const { return (uint32_t)(group * 9 + j) * 256u * (uint32_t)N_pad; }
@@ -181,6 +183,38 @@ struct ChunkCursor {
         }
     }
 };
+
+// Work item of the persistent loops: a 128-row tile, or (split-K: one KAN layer, no epilogue affine, fewer tiles than half the
+// SMs) a tile x a window of x units.  ub0 / ub1 = the window in units, g0 = its first 64-feature group, n_chunks = its chunks.
+struct WorkItem {
+    int tile, ub0, ub1, g0, n_chunks;
+};
+#ifdef KAGNN_TC2_VARIANT_G16
+constexpr bool kSplitK = false;            // the gather-heavy build never splits (its launches gather over a CSR) and has no registers to spare
+#else
+constexpr bool kSplitK = true;
+#endif
+__device__ __forceinline__ WorkItem work_item(const Tc2Params& p, int item) {
+    WorkItem w;
+    if (!kSplitK || p.n_split <= 1) {
+        w.tile = item;
+        w.ub0 = 0;
+        w.ub1 = p.units_per_tile;
+        w.g0 = 0;
+        w.n_chunks = p.layers[0].n_chunks;
+        return w;
+    }
+    w.tile = item / p.n_split;
+    const int sp = item - w.tile * p.n_split;
+    w.ub0 = sp * p.units_per_item;
+    w.ub1 = min(p.units_per_tile, w.ub0 + p.units_per_item);
+    const int gpu_ = p.uw >> 6;                            // 64-feature groups per unit
+    const int octs = p.layers[0].F_pad >> 3;
+    w.g0 = w.ub0 * gpu_;
+    const int g1 = min((octs + 7) >> 3, w.ub1 * gpu_);
+    w.n_chunks = (min(octs, 8 * g1) - 8 * w.g0) + (g1 - w.g0);
+    return w;
+}
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -1353,7 +1387,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                             for (int i = 0; i < 8; ++i) v[i] = silu_f(v[i]);
                         }
                     }
-                    if (p.y_vec && 8 * jb + 8 <= L.N) {
+                    if (kSplitK && p.n_split > 1) {         // split-K: this item's partial sums join the others' in y (zeroed by the launcher)
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            if (8 * jb + i < L.N) atomicAdd(yrow + 8 * jb + i, v[i]);
+                    } else if (p.y_vec && 8 * jb + 8 <= L.N) {
                         *reinterpret_cast<float4*>(yrow + 8 * jb) = make_float4(v[0], v[1], v[2], v[3]);
                         *reinterpret_cast<float4*>(yrow + 8 * jb + 4) = make_float4(v[4], v[5], v[6], v[7]);
                     } else {
@@ -1383,13 +1421,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
         long long pend_row0 = 0;
         uint32_t pend_lc = 0;
         bool have_pend = false;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-            const long long row0 = (long long)tile * BM;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            const WorkItem wi = work_item(p, item);
+            const long long row0 = (long long)wi.tile * BM;
             for (int l = 0; l < p.n_layers; ++l, ++lc) {
                 const LayerT2& L = p.layers[l];
                 const float inv_h = L.inv_h, c0f = L.c0, limp = L.lim + 0.5f;
                 const uint4* lutL = lut + l * LUT_ROWS;
-                const int n_chunks = L.n_chunks;
+                const int n_chunks = l == 0 ? wi.n_chunks : L.n_chunks;
                 uint32_t src_t = 0, src_lo = 0;               // src_lo != 0: previous layer's accumulator is stacked
                 int cur_unit = -1;
                 const float* xrow = nullptr;
@@ -1469,7 +1508,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                         ln_rstd = rsqrtf(fmaxf(fmaf(sq, inv_f, -md * md), 0.f) + 1e-5f);
                     }
                 }
-                ChunkCursor c(L.F_pad);
+                ChunkCursor c(L.F_pad, l == 0 ? wi.g0 : 0);
                 for (int q = 0; q < n_chunks; ++q, c.next()) {
                     if (l == 0 && c.j == 0) {
                         // x-tile ring: entering a new unit releases the previous one and waits for the gather warps
@@ -1638,7 +1677,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
         uint32_t uc = 0;
         int it = 0;
         int halo_done = 0;                                            // leading chunks of 256 halo rows known to have landed
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+            const WorkItem wi = work_item(p, item);
+            const int tile = wi.tile;
             const long long row0 = (long long)tile * BM;
             if (gw == 0 && lane == 0) *gather_progress = it;          // paces the L2 prefetch warp
             if (p.agg.halo_flags) {
@@ -1657,7 +1698,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
                     }
                 }
             }
-            for (int ub = 0; ub < p.units_per_tile; ++ub, ++uc) {
+            for (int ub = wi.ub0; ub < wi.ub1; ++ub, ++uc) {
                 const int u = (int)(uc % (uint32_t)p.n_units);
                 if (lane == 0 && gw == 0) TRL(6, uc, 0);
                 tc::mbar_wait_relaxed(&xs_empty[u], ((uc / (uint32_t)p.n_units) & 1u) ^ 1u);
@@ -1715,17 +1756,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
         uint32_t cq = 0, lc = 0;
         int s = 0;
         uint32_t par = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            const WorkItem wi = work_item(p, item);
             for (int l = 0; l < p.n_layers; ++l, ++lc) {
                 const LayerT2& L = p.layers[l];
-                const int n_chunks = L.n_chunks, stack = L.stack;
+                const int n_chunks = l == 0 ? wi.n_chunks : L.n_chunks, stack = L.stack;
                 const uint32_t idesc_n = tc::idesc_bf16_f32(BM, L.N_pad);
                 const uint32_t idesc_2n = tc::idesc_bf16_f32(BM, 2 * L.N_pad);
                 const uint32_t d_tmem = tmem_base + (((lc & 1) && !p.wide) ? 128u : 0u);
                 const uint32_t lbo_b = (uint32_t)L.N_pad * (BF16 ? 16u : 32u);   // k-core slab = hi rows + lo rows (bf16 mode: hi rows only)
                 const uint32_t lo_off = (uint32_t)L.N_pad;               // (N_pad * 16 bytes) >> 4: hi -> lo rows of a slab
                 const uint32_t kk_step = (2u * lbo_b) >> 4;              // two slabs per MMA
-                ChunkCursor c(L.F_pad);
+                ChunkCursor c(L.F_pad, l == 0 ? wi.g0 : 0);
                 for (int q = 0; q < n_chunks; ++q, ++cq, c.next()) {
                     if (lane == 0) TRC(2, cq, 0);
                     tc::mbar_wait(&full[s], par);
@@ -1843,11 +1885,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc2_kernel(const __grid_con
         if (warp == WARP_LOAD && lane == 0) {
             uint32_t cq = 0, par = 1;
             int s = 0;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                const WorkItem wi = work_item(p, item);
                 for (int l = 0; l < p.n_layers; ++l) {
                     const LayerT2& L = p.layers[l];
-                    ChunkCursor c(L.F_pad);
-                    for (int q = 0; q < L.n_chunks; ++q, ++cq, c.next()) {
+                    const int n_chunks = l == 0 ? wi.n_chunks : L.n_chunks;
+                    ChunkCursor c(L.F_pad, l == 0 ? wi.g0 : 0);
+                    for (int q = 0; q < n_chunks; ++q, ++cq, c.next()) {
                         TRC(3, cq, 0);
                         tc::mbar_wait_relaxed(&empty[s], par);
                         TRC(3, cq, 1);
@@ -2129,7 +2173,25 @@ int KAGNN_TC2_ENTRY(const KagnnAggregate* agg, int64_t num_rows, const KagnnAffi
     if (agg->halo_flags && (!agg->x_halo || !agg->halo_need)) return KAGNN_EINVAL;
     int sms = props.num_sms - (agg->reserve_sms > 0 ? agg->reserve_sms : 0);
     if (sms < 1) sms = 1;
-    const int grid = p.n_tiles < sms ? p.n_tiles : sms;
+    // Split-K for launches with few tiles and long rows (BASELINE config C1: 2 708 nodes x 1 433 features = 22 tiles, 203 chunks
+    // each): a tile's x units are dealt to several CTAs, each runs the whole pipeline over its window of input features and
+    // adds its partial sums into y with float atomics.  Only where nothing follows the contraction inside the launch: one
+    // B-spline layer, rows as they are, no epilogue affine, no pushed output.
+    p.n_split = 1;
+    p.units_per_item = p.units_per_tile;
+    const bool can_split = n_layers == 1 && !rbf && agg->mode == KAGNN_AGG_NONE && !pre && !agg_out && !agg->src_index && !post &&
+                           agg->num_push == 0 && !agg->halo_flags;
+    if (kSplitK && can_split && p.units_per_tile >= 4 && p.n_tiles * 2 <= sms) {
+        const int want = sms / p.n_tiles;                  // items per tile that still fit one wave
+        int upi = (p.units_per_tile + want - 1) / want;
+        if (upi < 2) upi = 2;
+        p.units_per_item = upi;
+        p.n_split = (p.units_per_tile + upi - 1) / upi;
+    }
+    p.n_items = p.n_tiles * p.n_split;
+    if (p.n_split > 1)
+        KAGNN_CUDA_TRY(cudaMemset2DAsync(y, (size_t)ldy * sizeof(float), 0, (size_t)width * sizeof(float), (size_t)num_rows, stream));
+    const int grid = p.n_items < sms ? p.n_items : sms;
     kern<<<(unsigned)grid, NTHREADS, smem, stream>>>(p);
     KAGNN_LAUNCH_CHECK();
     return KAGNN_OK;

@@ -130,6 +130,24 @@ __global__ void gather_rows_peer_kernel(const float* const* __restrict__ peer_x,
         *reinterpret_cast<float4*>(dst + c) = __ldg(reinterpret_cast<const float4*>(src + c));
 }
 
+// The pull without an id list: candidate row id in [0, total) is copied from its owner into out[id] (a replica of the whole matrix)
+// when need[id] != 0.  The plan of the sharded forward marks the rows a shard references with one scatter, so no sort / unique /
+// compaction (and no host synchronisation) stands between an edge list and the transfer.
+__global__ void gather_rows_peer_masked_kernel(const float* const* __restrict__ peer_x, int64_t ldx, int64_t rows_per_rank,
+                                               const uint8_t* __restrict__ need, int64_t total, int cols, float* __restrict__ out,
+                                               int64_t ld_out, int nseg) {
+    const int64_t v = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int64_t seg = (total + nseg - 1) / nseg;      // consecutive warps walk `nseg` segments in turn: every peer's link stays busy
+    const int64_t gid = (v % nseg) * seg + v / nseg;
+    if (v >= seg * nseg || gid >= total || !need[gid]) return;
+    const int owner = (int)(gid / rows_per_rank);
+    const float* src = peer_x[owner] + (gid - owner * rows_per_rank) * ldx;
+    float* dst = out + gid * ld_out;
+    for (int c = lane * 4; c < cols; c += 128)
+        *reinterpret_cast<float4*>(dst + c) = __ldg(reinterpret_cast<const float4*>(src + c));
+}
+
 // The same pull as a persistent kernel that publishes its progress: rows are copied in the given order, 256 at a time per block
 // (block b: chunks b, b + gridDim.x, ...), and a finished chunk stores `epoch` into its flag with release semantics.  The fused
 // layer that runs concurrently (fused_tc2.cu, KagnnAggregate.halo_flags) waits on the flags of the prefix its tile needs.
@@ -326,6 +344,20 @@ extern "C" int kagnn_gather_rows_peer(const float* const* peer_x, int64_t ldx, i
     const int64_t seg = ceil_div64(rows, nseg);
     unsigned blocks = (unsigned)ceil_div64(seg * nseg * 32, kThreads);
     gather_rows_peer_kernel<<<blocks, kThreads, 0, stream>>>(peer_x, ldx, rows_per_rank, ids, rows, cols, out, ld_out, nseg);
+    KAGNN_LAUNCH_CHECK();
+    return KAGNN_OK;
+}
+
+extern "C" int kagnn_gather_rows_peer_masked(const float* const* peer_x, int64_t ldx, int64_t rows_per_rank, const uint8_t* need,
+                                             int64_t total_rows, int32_t cols, float* out, int64_t ld_out, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (total_rows < 0 || cols < 0 || rows_per_rank <= 0 || (total_rows > 0 && (!peer_x || !need || !out))) return KAGNN_EINVAL;
+    if (total_rows == 0 || cols == 0) return KAGNN_OK;
+    if (!aligned16(out) || (ldx % 4) || (ld_out % 4) || (cols % 4)) return KAGNN_EALIGN;
+    const int nseg = 16;
+    const int64_t seg = ceil_div64(total_rows, nseg);
+    unsigned blocks = (unsigned)ceil_div64(seg * nseg * 32, kThreads);
+    gather_rows_peer_masked_kernel<<<blocks, kThreads, 0, stream>>>(peer_x, ldx, rows_per_rank, need, total_rows, cols, out, ld_out, nseg);
     KAGNN_LAUNCH_CHECK();
     return KAGNN_OK;
 }

@@ -270,23 +270,7 @@ class ShardedNodeModel:
             plan.n_halo = n_halo
             return plan
         if self.mode == "push":
-            # layer 0 reads x through the compact halo numbering of "pull"; the later layers read the replicas of the hidden
-            # matrices, where the row of global node j is row j (source id n_local + j in the two-matrix addressing of x_halo)
-            lo, dev = self.rank * self.n_local, edge_index_global.device
-            ei_local, halo_global, _ = relabel_edges(edge_index_global, self.rank, self.world, self.n_local)
-            n_halo = int(halo_global.numel())
-            plan = PeerPlan(GraphCSR(ei_local, self.n_local, self.n_local + n_halo), self.n_local, self.world)
-            plan.halo_ids = halo_global.to(torch.int32)
-            plan.n_halo = n_halo
-            col = plan.graph.col.long()                   # halo numbering -> replica numbering, entry by entry (no second sort)
-            remote = col >= self.n_local
-            if n_halo:
-                col_rep = torch.where(remote, halo_global[(col - self.n_local).clamp_(min=0)] + self.n_local, col).to(torch.int32)
-            else:
-                col_rep = plan.graph.col
-            plan.graph_rep = plan.graph.with_sources(col_rep, self.n_local * (self.world + 1))
-            plan.push_mask = self._push_mask(halo_global, dev)
-            return plan
+            return self._prepare_push(edge_index_global)
         if self.mode == "pull_overlap":
             # the same, numbered in first-use order for the pull that runs concurrently with the layer
             ei_local, halo_global, need = relabel_edges_first_use(edge_index_global, self.rank, self.world, self.n_local)
@@ -313,27 +297,29 @@ class ShardedNodeModel:
         """The ranks this one pushes to, in the bit order of the push mask / the order of the destination table."""
         return [q for q in range(self.world) if q != self.rank]
 
-    def _push_mask(self, halo_global: Tensor, dev) -> Optional[Tensor]:
-        """Collective (plan time): byte r has bit i set <=> rank push_peers()[i] references row r of this rank.  None when
-        (nearly) every row goes everywhere -- then the kernel skips the mask load."""
-        grp = self.group
-        cnt = torch.tensor([int(halo_global.numel())], dtype=torch.int64, device=dev)
-        cnts = [torch.zeros_like(cnt) for _ in range(self.world)]
-        dist.all_gather(cnts, cnt, group=grp)
-        mx = max(1, max(int(c.item()) for c in cnts))
-        pad = torch.full((mx,), -1, dtype=torch.int64, device=dev)
-        pad[: halo_global.numel()] = halo_global
-        lists = [torch.empty_like(pad) for _ in range(self.world)]
-        dist.all_gather(lists, pad, group=grp)
-        lo = self.rank * self.n_local
-        mask = torch.zeros(self.n_local, dtype=torch.uint8, device=dev)
-        for i, q in enumerate(self.push_peers()):
-            ids = lists[q][: int(cnts[q].item())]
-            ids = ids[(ids >= lo) & (ids < lo + self.n_local)] - lo
-            mask[ids] |= (1 << i)
-        full = (1 << (self.world - 1)) - 1
-        dense = float((mask == full).float().mean().item()) if self.n_local else 1.0
-        return None if dense > 0.9 else mask
+    def _prepare_push(self, edge_index_global: Tensor):
+        """Plan of mode "push" -- no sort besides the CSR build, no ``unique``, no host synchronisation.  Every layer aggregates
+        over [own rows | replica of the whole matrix]: a local source j becomes j - lo, a remote one n_local + j, so ONE CSR
+        serves the input features and every hidden matrix.  Which remote rows this rank needs is one scatter into a byte map
+        (``need``); the maps of all ranks (one all-gather) give, per own row, the byte of peers that reference it."""
+        n, w, lo = self.n_local, self.world, self.rank * self.n_local
+        n_tot, dev = n * w, edge_index_global.device
+        src, dst = edge_index_global[0], edge_index_global[1] - lo
+        ok = (src >= 0) & (src < n_tot)
+        local = (src >= lo) & (src < lo + n)
+        # an id outside the global range stays out of range (-1) so that the deferred check of the CSR build reports it
+        src_rep = torch.where(ok, torch.where(local, src - lo, src + n), torch.full_like(src, -1))
+        plan = PeerPlan(GraphCSR(torch.stack([src_rep, dst]), n, n + n_tot), n, w)
+        need = torch.zeros(n_tot, dtype=torch.uint8, device=dev)
+        need[src.clamp(0, n_tot - 1)] = 1
+        need[lo:lo + n] = 0
+        maps = torch.empty(w, n_tot, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(maps.view(-1), need, group=self.group)
+        peers = torch.tensor(self.push_peers(), dtype=torch.int64, device=dev)
+        shifts = torch.arange(w - 1, dtype=torch.uint8, device=dev).view(-1, 1)
+        plan.push_mask = torch.bitwise_left_shift(maps[peers, lo:lo + n], shifts).sum(0, dtype=torch.uint8)
+        plan.need = need
+        return plan
 
     def input_buffer(self, n_features: int, device) -> Tensor:
         """This rank's input columns INSIDE the symmetric skip-concat buffer (modes peer / pull / push): a caller that writes x
@@ -408,10 +394,16 @@ class ShardedNodeModel:
             if self.mode == "push":
                 push = dict(push_y=reps[l][1], push_ld=hid, push_mask=plan.push_mask) if l < n_mp - 1 else {}
                 if l == 0:
-                    halo = self._x_halo(plan, x, lambda: ops.gather_rows_peer(table(col), buf.stride(0), self.n_local, plan.halo_ids, cur.size(1)))
+                    # input features: the marked remote rows are pulled into this rank's replica of x (nothing runs before
+                    # layer 0 that could hide a push of x)
+                    key = ("xrep", f, x.device.index)
+                    if key not in self._symm:
+                        self._symm[key] = torch.empty(self.world * n, f, dtype=torch.float32, device=x.device)
+                    xrep = self._symm[key]
+                    halo = self._x_halo(plan, x, lambda: ops.gather_rows_peer_masked(table(col), buf.stride(0), self.n_local, plan.need, f, xrep))
                     conv(cur, plan.graph, out=dst, post=m._folds[l].get(bn), x_halo=halo, **push)
                 else:
-                    conv(cur, plan.graph_rep, out=dst, post=m._folds[l].get(bn), x_halo=reps[l - 1][0], **push)
+                    conv(cur, plan.graph, out=dst, post=m._folds[l].get(bn), x_halo=reps[l - 1][0], **push)
             elif self.mode == "pull":
                 # the distinct remote rows, copied once from their owners by a pull kernel on all SMs (678 GB/s measured on two
                 # B200s), then the ordinary halo layer

@@ -356,6 +356,23 @@ def gather_rows_peer(peer_x: Tensor, ldx: int, rows_per_rank: int, ids: Tensor, 
 
 
 @_on_device
+def gather_rows_peer_masked(peer_x: Tensor, ldx: int, rows_per_rank: int, need: Tensor, num_cols: int, out: Tensor) -> Tensor:
+    """out[id] = row id % rows_per_rank of rank id // rows_per_rank for every id with need[id] != 0, pulled over NVLink
+    (kagnn_gather_rows_peer_masked); ``out`` has one row per id (a replica of the whole matrix)."""
+    global launch_count
+    _need_cuda(peer_x, "peer_x", torch.int64)
+    _need_cuda(need, "need", torch.uint8)
+    if out.size(0) < need.numel():
+        raise ValueError("out needs one row per candidate id")
+    if need.numel() == 0:
+        return out
+    L.check(L.lib().kagnn_gather_rows_peer_masked(_p(peer_x), ldx, rows_per_rank, _p(need), need.numel(), num_cols, _p(out),
+                                                  _rows(out, "out"), _stream()), "gather_rows_peer_masked")
+    launch_count += 1
+    return out
+
+
+@_on_device
 def gat_attention(h: Tensor, csr: CSR, att_src: Tensor, att_dst: Tensor, heads: int, negative_slope: float = 0.2):
     """PyG GATConv's attention coefficients for h = lin(x) of shape (N, heads * C) on a destination-sorted CSR:
     returns (edge_weight (heads, nnz), self_weight (heads, N)) -- per head the operands of the WEIGHTED aggregation

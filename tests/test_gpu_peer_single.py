@@ -208,6 +208,29 @@ def test_pushed_layer_output_single_gpu(fast, hid, masked):
     assert K.rel_err(y, y_single) <= 2e-6
 
 
+def test_masked_pull_fills_exactly_the_marked_rows_single_gpu():
+    """kagnn_gather_rows_peer_masked (the input-halo transfer of mode="push"): rows marked in the byte map are copied from their
+    owner's block into the replica at their own index, everything else is left alone."""
+    from kagnn_b200 import ops
+    world, n_local, f = 4, 3_001, 128
+    g = torch.Generator().manual_seed(21)
+    n = world * n_local
+    x = torch.randn(n, f + 32, generator=g)[:, 16:16 + f]                  # a column slice: leading dimension != width
+    dev = torch.device("cuda")
+    full = x.to(dev)
+    blocks = [full[r * n_local:(r + 1) * n_local] for r in range(world)]    # views with the parent's leading dimension
+    blocks = [torch.empty(n_local, f + 8, device=dev)[:, :f].copy_(b) for b in blocks]   # separate allocations, ld = f + 8
+    table = torch.tensor([b.data_ptr() for b in blocks], dtype=torch.int64, device=dev)
+    need = (torch.rand(n, generator=g) < 0.58).to(torch.uint8)
+    need[n_local:2 * n_local] = 0                                           # "my" range is never pulled
+    rep = torch.full((n, f), float("nan"), device=dev)
+    ops.gather_rows_peer_masked(table, blocks[0].stride(0), n_local, need.to(dev), f, rep)
+    rep = rep.cpu()
+    on = need.bool()
+    assert torch.equal(rep[on], x[on])
+    assert torch.isnan(rep[~on]).all()
+
+
 def _rep_graph(ei_mine, lo, n_local, n, dev):
     """CSR of one rank's destination rows over [own rows | replica of all rows]: local source j -> j - lo, remote -> n_local + j."""
     from kagnn_b200.graph import GraphCSR
