@@ -14,6 +14,7 @@ In training mode (batch-statistics BatchNorm, dropout) each conv still runs fuse
 the fused training epilogue with a Philox mask)."""
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -27,6 +28,47 @@ from .fastkan import FastKANLayer
 from .graph import get_graph
 
 Tensor = torch.Tensor
+
+
+# Small graphs (BASELINE config C1: 2 708 nodes) are bound by launch latency and host work, not by the kernels: six dependent,
+# mostly empty launches.  An eval-mode forward that is repeated on the SAME inputs (the reference's validation / test loops call
+# the model on the one static graph every epoch) is therefore replayed from a CUDA graph: two eager calls, the third
+# captured, later ones replayed.  The key holds the identity AND version of x, edge_index and every parameter / buffer, so any
+# in-place change re-captures; the entry keeps x and edge_index alive, so their addresses cannot be recycled.
+# KAGNN_AUTO_GRAPH_NODES=0 switches it off.
+_AUTO_GRAPH_NODES = int(os.environ.get("KAGNN_AUTO_GRAPH_NODES", "20000"))
+
+
+class _GraphReplay:
+    def __init__(self):
+        self.key = None
+        self.count = 0
+        self.graph = None
+        self.out = None
+        self.keep = None
+        self.failed = False
+
+    def run(self, model, x: Tensor, edge_index: Tensor, eager):
+        key = (x.data_ptr(), tuple(x.shape), x.stride(), x._version, x.dtype, edge_index.data_ptr(), tuple(edge_index.shape),
+               edge_index._version, ops.get_precision(),
+               tuple((t.data_ptr(), t._version) for t in list(model.parameters()) + list(model.buffers())))
+        if key != self.key:
+            self.key, self.count, self.graph, self.out, self.keep = key, 0, None, None, (x, edge_index)
+        self.count += 1
+        if self.count < 3 or self.failed:               # two eager calls first: a validation + test pair per epoch never pays a capture
+            return eager()
+        if self.graph is None:
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    out = eager()
+                self.graph, self.out = g, out
+            except Exception:                           # anything that cannot be captured: stay eager for good
+                self.failed, self.graph, self.out = True, None, None
+                torch.cuda.synchronize()
+                return eager()
+        self.graph.replay()
+        return self.out.clone()
 
 
 class _BNFold:
@@ -112,6 +154,14 @@ class _NodeModel(nn.Module):
         hid = self.bns[0].num_features
         if needs_grad or not self._fusable():
             return self._forward_unfused(x, g, needs_grad)
+        if 0 < n <= _AUTO_GRAPH_NODES and x.is_cuda and not torch.cuda.is_current_stream_capturing() and not getattr(self, "_in_replay", False):
+            if not hasattr(self, "_replay"):
+                object.__setattr__(self, "_replay", _GraphReplay())
+            object.__setattr__(self, "_in_replay", True)
+            try:
+                return self._replay.run(self, x, edge_index, lambda: self.forward(x, edge_index))
+            finally:
+                object.__setattr__(self, "_in_replay", False)
         # skip concat (models.py:196-201) without any copy: every layer writes its column slice of the hidden buffer and
         # lay_out reads two-part rows [x | h_1 .. h_L] (KagnnAggregate.x_head)
         buf = torch.empty(n, n_mp * hid, dtype=torch.float32, device=x.device) if self.skip else None

@@ -65,9 +65,14 @@ def cora(dev, flush, with_cpu=True):
     sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
     m = m.to(dev)
     xd, eid = x.to(dev), ei.to(dev)
+    from kagnn_b200 import models_node
+    auto = models_node._AUTO_GRAPH_NODES
+    models_node._AUTO_GRAPH_NODES = 0                      # launch by launch
+    ms_eager = _time(lambda: m(xd, eid), flush, steps=20)
+    models_node._AUTO_GRAPH_NODES = auto                   # the default: repeated eval forwards on the same inputs replay a CUDA graph
     ms = _time(lambda: m(xd, eid), flush, steps=20)
     out = {"workload": "Cora-shaped KAGCN: GKAN_Nodes('gcn', 2, 1433, 32, 7, skip=True, grid 5, order 3), N 2708, E 10556", "ms": ms,
-           "nodes_per_s": n / ms * 1e3}
+           "ms_launch_by_launch": ms_eager, "nodes_per_s": n / ms * 1e3}
     # the same forward replayed from a CUDA graph (six dependent, mostly empty launches: launch latency is the cost)
     try:
         with torch.no_grad():

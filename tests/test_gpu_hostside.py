@@ -84,3 +84,46 @@ def test_tensors_on_another_device_run_there():
     from kagnn_b200 import ops
     with pytest.raises(RuntimeError):
         ops.fused_layer(ops.AggSpec(L.AGG_NONE, x.to("cuda:0")), 300, m1.kernel_specs())
+
+
+def test_small_graph_forward_is_replayed_from_a_cuda_graph_and_tracks_every_input():
+    """Eval-mode forwards of a small node model on the same inputs are replayed from a CUDA graph from the third call on
+    (kagnn_b200/models_node.py: _GraphReplay); an in-place change of x, of edge_index or of a parameter must show in the result."""
+    import kagnn_b200 as kb
+    from kagnn_b200 import models_node
+    from oracle import kagnn_oracle as K
+    assert models_node._AUTO_GRAPH_NODES > 0
+    torch.manual_seed(0)
+    g = torch.Generator().manual_seed(5)
+    n, f = 900, 70
+    x = torch.randn(n, f, generator=g) * 0.5
+    ei = torch.randint(0, n, (2, 4000), generator=g)
+    m = kb.GKAN_Nodes("gcn", 2, f, 16, 5, skip=True, grid_size=5, spline_order=3, dropout=0.0).eval()
+    md = m.cuda()
+    xd, eid = x.cuda(), ei.cuda()
+
+    def ref():
+        sd = {k: v.detach().cpu().clone() for k, v in md.state_dict().items()}
+        return K.node_model_forward(sd, "gcn", xd.cpu(), eid.cpu(), True)
+
+    with torch.no_grad():
+        ys = [md(xd, eid) for _ in range(5)]
+        assert md._replay.graph is not None                          # calls 4 and 5 were replays
+        assert ys[3].data_ptr() != ys[4].data_ptr()                  # every call returns its own tensor
+        for y in ys:
+            assert K.rel_err(y.cpu(), ref()) <= 1e-4
+        assert torch.equal(ys[0], ys[4])
+        xd.mul_(0.5)                                                 # new version of x
+        y = md(xd, eid)
+        assert K.rel_err(y.cpu(), ref()) <= 1e-4 and not torch.equal(y, ys[4])
+        for _ in range(3):
+            y = md(xd, eid)
+        assert K.rel_err(y.cpu(), ref()) <= 1e-4
+        eid[0, :100] = (eid[0, :100] + 1) % n                        # new version of edge_index
+        for _ in range(4):
+            y = md(xd, eid)
+        assert K.rel_err(y.cpu(), ref()) <= 1e-4
+        md.lay_out.base_weight.mul_(1.5)                             # new version of a parameter
+        for _ in range(4):
+            y = md(xd, eid)
+        assert K.rel_err(y.cpu(), ref()) <= 1e-4
