@@ -229,21 +229,39 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the kagnn_b200 path has no CPU fallback")
     if args.config != "arxiv":
+        # The other BASELINE configurations.  Graph-level batches (zinc, mutag) shard by graph with no exchange: under torchrun
+        # every rank runs its own batch and the line reports the aggregate (max over ranks of the step time); the node-level
+        # ones (cora, rmat) run on rank 0 only.
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        import bench_extras as BX
+        sharded = world > 1 and args.config in ("zinc", "mutag")
+        if rank != 0 and not sharded:
+            return
+        torch.cuda.set_device(local_rank)
+        dev = torch.device("cuda", local_rank)
+        if sharded:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=dev)
+        flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+        fn = getattr(BX, args.config)
+        res = fn(dev, flush) if args.config == "rmat" else fn(dev, flush, with_cpu=(not args.no_cpu_baseline) and rank == 0)
+        ms = res.get("ms", res.get("ms_layer", res.get("ms_fp32")))
+        nodes = {"cora": 2708}.get(args.config, res.get("nodes"))
+        n_ranks = 1
+        if sharded:
+            t = torch.tensor([ms, float(res.get("ms_bf16", 0.0))], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, n_ranks = float(t[0]), world
+            res["ms_bf16_max_over_ranks"] = float(t[1])
+            dist.barrier()
+            dist.destroy_process_group()
         if rank == 0:
-            sys.path.insert(0, os.path.join(ROOT, "scripts"))
-            import bench_extras as BX
-            torch.cuda.set_device(local_rank)
-            dev = torch.device("cuda", local_rank)
-            flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
-            fn = getattr(BX, args.config)
-            res = fn(dev, flush) if args.config == "rmat" else fn(dev, flush, with_cpu=not args.no_cpu_baseline)
             # the same line shape as the headline run (metric = forward nodes/s of that configuration's model or layer)
-            ms = res.get("ms", res.get("ms_layer", res.get("ms_fp32")))
-            nodes = {"cora": 2708}.get(args.config, res.get("nodes"))
-            line = {"metric": METRIC, "value": nodes / ms * 1e3 if (ms and nodes) else None, "unit": "nodes/s", "n_gpus": 1,
+            line = {"metric": METRIC, "value": n_ranks * nodes / ms * 1e3 if (ms and nodes) else None, "unit": "nodes/s", "n_gpus": n_ranks,
                     "steps": 20 if args.config == "cora" else 10, "warmup": 3, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
                     "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                    "config": {"workload": res.get("workload", args.config), "l2": "flushed between iterations (512 MB memset)"},
+                    "config": {"workload": res.get("workload", args.config), "l2": "flushed between iterations (512 MB memset)",
+                               "parallelism": (f"graph batches sharded by graph x{n_ranks}, no exchange" if sharded else "single GPU")},
                     "e2e": ({"value": nodes / res["ms_e2e"] * 1e3, "unit": "nodes/s", "ms_per_step": res["ms_e2e"]} if "ms_e2e" in res else None),
                     "cpu_baseline": ({"value": nodes / res["cpu_port_ms"] * 1e3, "unit": "nodes/s", "cores": res.get("cpu_threads"), "kind": "port",
                                       "sample": "oracle forward of the same model on the same inputs"} if "cpu_port_ms" in res else None),

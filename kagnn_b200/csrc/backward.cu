@@ -558,8 +558,9 @@ extern "C" int kagnn_rbf_bwd_input(const KagnnKanLayer* layer, const float* x, i
     if (rc != KAGNN_OK) return rc;
     if (num_rows < 0 || (num_rows > 0 && (!x || !dy || !dz)) || ldx < g.in_f || ld_dy < g.out_f || ld_dz < g.in_f) return KAGNN_EINVAL;
     if (ln_stats && (!dx_base || ld_dxb < g.in_f)) return KAGNN_EINVAL;       // with a LayerNorm the two branches stay separate
-    if (g.in_f > 65535) return KAGNN_EUNSUPPORTED;
     if (num_rows == 0) return KAGNN_OK;
+    KAGNN_TRY_TILED(kagnn_rbf_bwd_input_tc(layer, x, ldx, ln_stats, dy, ld_dy, num_rows, dz, ld_dz, dx_base, ld_dxb, stream));
+    if (g.in_f > 65535) return KAGNN_EUNSUPPORTED;
     KAGNN_LAUNCH(rbf_bwd_input_kernel, dim3((unsigned)ceil_div64(num_rows, kBwdThreads), (unsigned)g.in_f, 1),
                  dim3((unsigned)kBwdThreads, 1, 1), stream, g, layer->packed_w, x, (long long)ldx, ln_stats, dy, (long long)ld_dy,
                  (long long)num_rows, dz, (long long)ld_dz, ln_stats ? dx_base : (float*)nullptr, (long long)ld_dxb);
@@ -574,6 +575,7 @@ extern "C" int kagnn_rbf_bwd_weights(const KagnnKanLayer* layer, const float* x,
     const int rc = rbf_geometry(layer, ln_stats, &g);
     if (rc != KAGNN_OK) return rc;
     if (num_rows < 0 || !d_packed || (num_rows > 0 && (!x || !dy)) || ldx < g.in_f || ld_dy < g.out_f) return KAGNN_EINVAL;
+    if (num_rows > 0) KAGNN_TRY_TILED(kagnn_rbf_bwd_weights_tc(layer, x, ldx, ln_stats, dy, ld_dy, num_rows, d_packed, stream));
     KAGNN_CUDA_TRY(cudaMemsetAsync(d_packed, 0, sizeof(float) * (size_t)g.in_f * (size_t)(g.G + 1) * (size_t)g.out_pad, stream));
     if (num_rows == 0) return KAGNN_OK;
     const int threads = g.out_f >= 256 ? 256 : ((g.out_f + 31) / 32) * 32;

@@ -33,9 +33,21 @@ constexpr float kMagicB = 12582912.0f;  // 1.5 * 2^23: u + kMagic (round down) =
 constexpr float kLog2eB = 1.4426950408889634f;
 
 struct GeomB {
-    int in_f, out_f, out_pad, G, k, S;
+    int in_f, out_f, out_pad, G, k, S;       // S = slots per feature (B-spline: G + k, RBF: G); slot S = the SiLU base column
     float t0, inv_h;
+    // RBF layers (template K == 0; fastkan.py:76-85): centres c0 + g step, phi_g(z) = exp(-((z - c_g) inv_den)^2), z = LayerNorm(x)
+    float c0, step, inv_den;
+    const float *ln_w, *ln_b, *stats;        // stats = per-row (mean, rstd) or NULL: no LayerNorm, z = x
 };
+
+// RBF: the layer's input after its LayerNorm
+__device__ __forceinline__ float rbf_z_b(const GeomB& g, float xv, float mean, float rstd, int f) {
+    if (!g.stats) return xv;
+    float z = (xv - mean) * rstd;
+    if (g.ln_w) z *= __ldg(g.ln_w + f);
+    if (g.ln_b) z += __ldg(g.ln_b + f);
+    return z;
+}
 
 __device__ __forceinline__ float ex2_b(float x) {
     float y;
@@ -141,7 +153,8 @@ template <int K>
 __global__ void __launch_bounds__(kThreads) kan_bwd_input_tc_kernel(GeomB g, const float* __restrict__ w, const float* __restrict__ x,
                                                                     long long ldx, const float* __restrict__ dy, long long ld_dy,
                                                                     long long n_rows, int n_tiles, int KK, uint32_t tmem_cols,
-                                                                    float* __restrict__ dx, long long ld_dx) {
+                                                                    float* __restrict__ dx, long long ld_dx, float* __restrict__ dxb,
+                                                                    long long ld_dxb) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int S1 = g.S + 1;
     const int Np = kFP * S1;                             // N of one pass
@@ -175,6 +188,11 @@ __global__ void __launch_bounds__(kThreads) kan_bwd_input_tc_kernel(GeomB g, con
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long row = (long long)tile * 128 + r128;
         const bool row_ok = row < n_rows;
+        float mean = 0.f, rstd = 1.f;
+        if (K == 0 && g.stats && row_ok) {
+            mean = __ldg(g.stats + 2 * row);
+            rstd = __ldg(g.stats + 2 * row + 1);
+        }
         // ---- A = this row of dY, split into bf16 hi / lo, into tensor memory (lane = row; hi at a_col, lo at a_col + KK/2);
         // the two warpgroups take alternate 8-column groups
         const float* dyr = dy + (row_ok ? row : 0) * ld_dy;
@@ -285,11 +303,12 @@ __global__ void __launch_bounds__(kThreads) kan_bwd_input_tc_kernel(GeomB g, con
             phase ^= 1u;
             tc::tc_fence_after_sync();
             // ---- epilogue: warpgroup wg contracts features 8 wg .. 8 wg + 7 of the pass for its 128 rows
-            float res[8];
+            float res[8], resb[8];
 #pragma unroll
             for (int ii = 0; ii < 8; ++ii) {
                 const int i = 8 * wg + ii, f = f0 + i;
                 res[ii] = 0.f;
+                resb[ii] = 0.f;
                 if (f < g.in_f) {                       // uniform over the warpgroup
                     float t[16];
                     {
@@ -302,40 +321,56 @@ __global__ void __launch_bounds__(kThreads) kan_bwd_input_tc_kernel(GeomB g, con
                         for (int c = 0; c < 8; ++c) t[8 + c] = t0[c];
                     }
                     const float xv = xq[ii];
-                    int idx;
-                    float fr, d[4];
-                    locate_b(g, xv, idx, fr);
-                    local_derivs_b<K>(fr, g.inv_h, d);
-                    const int j = idx - 1;              // interval; its bases sit on slots j - K .. j
-                    const bool live = j >= 0 && j < g.G + 2 * K;
-                    // window of K + 1 consecutive slots starting at j - K (slots outside 0..S-1 count as zero): barrel shift of the
-                    // slot array, padded with K zeros in front, by jj = j in 0..10
-                    float tp[20];
-#pragma unroll
-                    for (int c = 0; c < 20; ++c) tp[c] = 0.f;
-#pragma unroll
-                    for (int c = 0; c < 8; ++c)
-                        if (c < kS1MaxB - 1) tp[K + c] = (c < g.S) ? t[c] : 0.f;
-                    const int jj = live ? j : 0;
-                    float s0[12], s1[8], s2[6], s3[4];
-#pragma unroll
-                    for (int c = 0; c < 12; ++c) s0[c] = (jj & 8) ? tp[c + 8] : tp[c];
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) s1[c] = (jj & 4) ? s0[c + 4] : s0[c];
-#pragma unroll
-                    for (int c = 0; c < 6; ++c) s2[c] = (jj & 2) ? s1[c + 2] : s1[c];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) s3[c] = (jj & 1) ? s2[c + 1] : s2[c];
                     float a = 0.f;
+                    if (K == 0) {
+                        // RBF: every slot is live; phi_g'(z) = -2 (z - c_g) inv_den^2 phi_g
+                        const float z = rbf_z_b(g, xv, mean, rstd, f);
 #pragma unroll
-                    for (int r = 0; r <= K; ++r) a = fmaf(d[r], s3[r], a);
-                    if (!live) a = 0.f;
+                        for (int q = 0; q < 8; ++q) {
+                            const float tt = (z - (g.c0 + (float)q * g.step)) * g.inv_den;
+                            const float dq = -2.0f * tt * g.inv_den * ex2_b(-kLog2eB * tt * tt);
+                            a = fmaf((q < g.S) ? dq : 0.f, t[q], a);
+                        }
+                    } else {
+                        int idx;
+                        float fr, d[4];
+                        locate_b(g, xv, idx, fr);
+                        local_derivs_b<(K == 0 ? 1 : K)>(fr, g.inv_h, d);
+                        const int j = idx - 1;              // interval; its bases sit on slots j - K .. j
+                        const bool live = j >= 0 && j < g.G + 2 * K;
+                        // window of K + 1 consecutive slots starting at j - K (slots outside 0..S-1 count as zero): barrel shift of the
+                        // slot array, padded with K zeros in front, by jj = j in 0..10
+                        float tp[20];
+#pragma unroll
+                        for (int c = 0; c < 20; ++c) tp[c] = 0.f;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                            if (c < kS1MaxB - 1) tp[K + c] = (c < g.S) ? t[c] : 0.f;
+                        const int jj = live ? j : 0;
+                        float s0[12], s1[8], s2[6], s3[4];
+#pragma unroll
+                        for (int c = 0; c < 12; ++c) s0[c] = (jj & 8) ? tp[c + 8] : tp[c];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) s1[c] = (jj & 4) ? s0[c + 4] : s0[c];
+#pragma unroll
+                        for (int c = 0; c < 6; ++c) s2[c] = (jj & 2) ? s1[c + 2] : s1[c];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) s3[c] = (jj & 1) ? s2[c + 1] : s2[c];
+#pragma unroll
+                        for (int r = 0; r <= K; ++r) a = fmaf(d[r], s3[r], a);
+                        if (!live) a = 0.f;
+                    }
                     const float sg = __fdividef(1.0f, 1.0f + ex2_b(-kLog2eB * xv));
                     const float dbase = sg * fmaf(xv, 1.0f - sg, 1.0f);
                     float tb = 0.f;
 #pragma unroll
                     for (int c = 0; c < 16; ++c)
                         if (c == g.S) tb = t[c];
+                    if (K == 0 && dxb) {                    // with a LayerNorm the two branches stay separate (kagnn_layernorm_bwd joins them)
+                        res[ii] = a;
+                        resb[ii] = dbase * tb;
+                        continue;
+                    }
                     res[ii] = fmaf(dbase, tb, a);
                 }
             }
@@ -348,6 +383,12 @@ __global__ void __launch_bounds__(kThreads) kan_bwd_input_tc_kernel(GeomB g, con
 #pragma unroll
                     for (int ii = 0; ii < 8; ++ii)
                         if (f0 + 8 * wg + ii < g.in_f) dxr[ii] = res[ii];
+                }
+                if (K == 0 && dxb) {
+                    float* br = dxb + row * ld_dxb + f0 + 8 * wg;
+#pragma unroll
+                    for (int ii = 0; ii < 8; ++ii)
+                        if (f0 + 8 * wg + ii < g.in_f) br[ii] = resb[ii];
                 }
             }
             tc::tc_fence_before_sync();
@@ -389,7 +430,7 @@ __global__ void __launch_bounds__(kThreads) kan_bwd_weights_tc_kernel(GeomB g, c
         tc::mbar_init(bar, 1);
         tc::mbar_fence_init();
     }
-    if (tid >= 64 && tid < 64 + kLutRows) lut[tid - 64] = lut_row_b(tid - 64, K, g.G + 2 * K);
+    if (K > 0 && tid >= 64 && tid < 64 + kLutRows) lut[tid - 64] = lut_row_b(tid - 64, K, g.G + 2 * K);
     tc::tc_fence_before_sync();
     __syncthreads();
     tc::tc_fence_after_sync();
@@ -433,6 +474,11 @@ __global__ void __launch_bounds__(kThreads) kan_bwd_weights_tc_kernel(GeomB g, c
     for (long long rt = r_beg; rt < r_end; rt += 128) {
         const long long row = rt + r128;
         const bool row_ok = row < r_end;
+        float mean = 0.f, rstd = 1.f;
+        if (K == 0 && g.stats && row_ok) {
+            mean = __ldg(g.stats + 2 * row);
+            rstd = __ldg(g.stats + 2 * row + 1);
+        }
         // ---- E^T: this row's slot values, one 16-byte vector per feature (unit u = feature), base values in units 14 / 15
         float bb[8];
 #pragma unroll
@@ -443,18 +489,31 @@ __global__ void __launch_bounds__(kThreads) kan_bwd_weights_tc_kernel(GeomB g, c
             if (i < fi1) {                              // uniform over the warpgroup
                 const bool on = row_ok && (f0 + i) < g.in_f;
                 const float xv = xq[ii];
-                int idx;
-                float fr, b[4];
-                locate_b(g, xv, idx, fr);
-                local_values_b<K>(fr, b);
-                // every value is >= 0, so hi = truncation to bf16 and lo = bf16(b - hi) are >= 0 too: their sign bits are 0, which lets
-                // the byte permute synthesise the empty slots by sign replication (selector nibble 9)
-                const uint32_t h01 = pack_trunc_b(b[0], b[1]), h23 = pack_trunc_b(b[2], b[3]);
-                const uint32_t l01 = pack_rn_b(trunc_res_b(b[0]), trunc_res_b(b[1])), l23 = pack_rn_b(trunc_res_b(b[2]), trunc_res_b(b[3]));
-                uint4 sel = lut[idx];
-                if (!on) sel = make_uint4(0x9999u, 0x9999u, 0x9999u, 0x9999u);
-                const uint4 hi = make_uint4(prmt_b(h01, h23, sel.x), prmt_b(h01, h23, sel.y), prmt_b(h01, h23, sel.z), prmt_b(h01, h23, sel.w));
-                const uint4 lo = make_uint4(prmt_b(l01, l23, sel.x), prmt_b(l01, l23, sel.y), prmt_b(l01, l23, sel.z), prmt_b(l01, l23, sel.w));
+                uint4 hi, lo;
+                if (K == 0) {
+                    // RBF: the G Gaussians of z = LayerNorm(x) fill the slots densely
+                    const float z = rbf_z_b(g, xv, mean, rstd, f0 + i);
+                    float e[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float tt = (z - (g.c0 + (float)q * g.step)) * g.inv_den;
+                        e[q] = (on && q < g.S) ? ex2_b(-kLog2eB * tt * tt) : 0.f;
+                    }
+                    tc::split8(e, hi, lo);
+                } else {
+                    int idx;
+                    float fr, b[4];
+                    locate_b(g, xv, idx, fr);
+                    local_values_b<(K == 0 ? 1 : K)>(fr, b);
+                    // every value is >= 0, so hi = truncation to bf16 and lo = bf16(b - hi) are >= 0 too: their sign bits are 0, which
+                    // lets the byte permute synthesise the empty slots by sign replication (selector nibble 9)
+                    const uint32_t h01 = pack_trunc_b(b[0], b[1]), h23 = pack_trunc_b(b[2], b[3]);
+                    const uint32_t l01 = pack_rn_b(trunc_res_b(b[0]), trunc_res_b(b[1])), l23 = pack_rn_b(trunc_res_b(b[2]), trunc_res_b(b[3]));
+                    uint4 sel = lut[idx];
+                    if (!on) sel = make_uint4(0x9999u, 0x9999u, 0x9999u, 0x9999u);
+                    hi = make_uint4(prmt_b(h01, h23, sel.x), prmt_b(h01, h23, sel.y), prmt_b(h01, h23, sel.z), prmt_b(h01, h23, sel.w));
+                    lo = make_uint4(prmt_b(l01, l23, sel.x), prmt_b(l01, l23, sel.y), prmt_b(l01, l23, sel.z), prmt_b(l01, l23, sel.w));
+                }
                 *reinterpret_cast<uint4*>(a_hi + (size_t)i * 2048 + r128 * 16) = hi;
                 *reinterpret_cast<uint4*>(a_lo + (size_t)i * 2048 + r128 * 16) = lo;
                 bb[ii] = on ? __fdividef(xv, 1.0f + ex2_b(-kLog2eB * xv)) : 0.f;
@@ -545,6 +604,7 @@ int geometry_b(const KagnnKanLayer* L, GeomB* g) {
     if (!L || !L->packed_w || L->basis != KAGNN_BASIS_BSPLINE) return KAGNN_EUNSUPPORTED;
     if (L->in_features <= 0 || L->out_features <= 0 || L->grid_size < 1 || L->spline_order < 1 || L->spline_order > 4) return KAGNN_EUNSUPPORTED;
     if (!(L->h > 0.f)) return KAGNN_EUNSUPPORTED;
+    *g = GeomB{};
     g->in_f = L->in_features;
     g->out_f = L->out_features;
     g->out_pad = pad4(L->out_features);
@@ -565,16 +625,13 @@ extern "C" int kagnn_set_backward_path(int32_t mode) {
     return KAGNN_OK;
 }
 
-int kagnn_kan_bwd_input_tc(const KagnnKanLayer* layer, const float* x, int64_t ldx, const float* dy, int64_t ld_dy, int64_t num_rows,
-                           float* dx, int64_t ld_dx, cudaStream_t stream) {
-    if (g_bwd_path.load() != 0) return KAGNN_EUNSUPPORTED;
-    GeomB g;
-    int rc = geometry_b(layer, &g);
-    if (rc != KAGNN_OK) return rc;
+namespace {
+int launch_bwd_input_tc(const GeomB& g, const float* w, const float* x, int64_t ldx, const float* dy, int64_t ld_dy, int64_t num_rows,
+                        float* dx, int64_t ld_dx, float* dxb, int64_t ld_dxb, cudaStream_t stream) {
     const int S1 = g.S + 1;
     if (num_rows < 128 || S1 > kS1MaxB || g.k > kMaxOrderB || g.out_f > 256) return KAGNN_EUNSUPPORTED;   // small batches: not worth a tile
     DeviceProps props{};
-    rc = kagnn_get_props(&props);
+    int rc = kagnn_get_props(&props);
     if (rc != KAGNN_OK) return rc;
     if (props.cc_major != 10) return KAGNN_EUNSUPPORTED;
     const int K = ((g.out_f + 15) / 16) * 16;
@@ -592,23 +649,19 @@ int kagnn_kan_bwd_input_tc(const KagnnKanLayer* layer, const float* x, int64_t l
     if (per_sm > 4) per_sm = 4;
     if (per_sm < 1) per_sm = 1;
     const int grid = n_tiles < props.num_sms * per_sm ? n_tiles : props.num_sms * per_sm;
-    auto kern = g.k == 3 ? kan_bwd_input_tc_kernel<3> : (g.k == 2 ? kan_bwd_input_tc_kernel<2> : kan_bwd_input_tc_kernel<1>);
+    auto kern = g.k == 3 ? kan_bwd_input_tc_kernel<3> : (g.k == 2 ? kan_bwd_input_tc_kernel<2> : (g.k == 1 ? kan_bwd_input_tc_kernel<1> : kan_bwd_input_tc_kernel<0>));
     KAGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)props.max_smem));
-    kern<<<(unsigned)grid, kThreads, smem, stream>>>(g, layer->packed_w, x, (long long)ldx, dy, (long long)ld_dy, (long long)num_rows, n_tiles, K,
-                                               cols, dx, (long long)ld_dx);
+    kern<<<(unsigned)grid, kThreads, smem, stream>>>(g, w, x, (long long)ldx, dy, (long long)ld_dy, (long long)num_rows, n_tiles, K, cols, dx,
+                                                    (long long)ld_dx, dxb, (long long)ld_dxb);
     KAGNN_LAUNCH_CHECK();
     return KAGNN_OK;
 }
 
-int kagnn_kan_bwd_weights_tc(const KagnnKanLayer* layer, const float* x, int64_t ldx, const float* dy, int64_t ld_dy, int64_t num_rows,
-                             float* d_packed, cudaStream_t stream) {
-    if (g_bwd_path.load() != 0) return KAGNN_EUNSUPPORTED;
-    GeomB g;
-    int rc = geometry_b(layer, &g);
-    if (rc != KAGNN_OK) return rc;
+int launch_bwd_weights_tc(const GeomB& g, const float* x, int64_t ldx, const float* dy, int64_t ld_dy, int64_t num_rows, float* d_packed,
+                          cudaStream_t stream) {
     if (num_rows < 128 || g.S > 8 || g.k > kMaxOrderB || g.out_f > 256) return KAGNN_EUNSUPPORTED;
     DeviceProps props{};
-    rc = kagnn_get_props(&props);
+    int rc = kagnn_get_props(&props);
     if (rc != KAGNN_OK) return rc;
     if (props.cc_major != 10) return KAGNN_EUNSUPPORTED;
     const int N16 = ((g.out_f + 15) / 16) * 16;
@@ -628,10 +681,69 @@ int kagnn_kan_bwd_weights_tc(const KagnnKanLayer* layer, const float* x, int64_t
 #ifdef KAGNN_DEBUG_KNOBS
     if (const char* e = getenv("KAGNN_DEBUG_DW_SWAP")) swap = atoi(e);
 #endif
-    auto kern = g.k == 3 ? kan_bwd_weights_tc_kernel<3> : (g.k == 2 ? kan_bwd_weights_tc_kernel<2> : kan_bwd_weights_tc_kernel<1>);
+    auto kern = g.k == 3 ? kan_bwd_weights_tc_kernel<3> : (g.k == 2 ? kan_bwd_weights_tc_kernel<2> : (g.k == 1 ? kan_bwd_weights_tc_kernel<1> : kan_bwd_weights_tc_kernel<0>));
     KAGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)props.max_smem));
     kern<<<dim3((unsigned)fblocks, (unsigned)slabs, 1), kThreads, smem, stream>>>(
         g, x, (long long)ldx, dy, (long long)ld_dy, (long long)num_rows, (long long)rows_per_slab, N16, cols, swap, d_packed);
     KAGNN_LAUNCH_CHECK();
     return KAGNN_OK;
+}
+
+// FastKAN layer -> the kernels' geometry with k = 0
+int geometry_rbf_b(const KagnnKanLayer* L, const float* stats, GeomB* g) {
+    if (!L || !L->packed_w || L->basis != KAGNN_BASIS_RBF) return KAGNN_EUNSUPPORTED;
+    if (L->in_features <= 0 || L->out_features <= 0 || L->grid_size < 1 || L->grid_size > 8) return KAGNN_EUNSUPPORTED;
+    if ((L->ln_weight || L->ln_bias) && !stats) return KAGNN_EINVAL;
+    *g = GeomB{};
+    g->in_f = L->in_features;
+    g->out_f = L->out_features;
+    g->out_pad = pad4(L->out_features);
+    g->G = L->grid_size;
+    g->k = 0;
+    g->S = L->grid_size;
+    g->c0 = L->t0;
+    g->step = L->h;
+    g->inv_den = L->inv_denominator;
+    g->stats = stats;
+    g->ln_w = stats ? L->ln_weight : nullptr;
+    g->ln_b = stats ? L->ln_bias : nullptr;
+    return KAGNN_OK;
+}
+}  // namespace
+
+int kagnn_kan_bwd_input_tc(const KagnnKanLayer* layer, const float* x, int64_t ldx, const float* dy, int64_t ld_dy, int64_t num_rows,
+                           float* dx, int64_t ld_dx, cudaStream_t stream) {
+    if (g_bwd_path.load() != 0) return KAGNN_EUNSUPPORTED;
+    GeomB g;
+    const int rc = geometry_b(layer, &g);
+    if (rc != KAGNN_OK) return rc;
+    return launch_bwd_input_tc(g, layer->packed_w, x, ldx, dy, ld_dy, num_rows, dx, ld_dx, nullptr, 0, stream);
+}
+
+int kagnn_kan_bwd_weights_tc(const KagnnKanLayer* layer, const float* x, int64_t ldx, const float* dy, int64_t ld_dy, int64_t num_rows,
+                             float* d_packed, cudaStream_t stream) {
+    if (g_bwd_path.load() != 0) return KAGNN_EUNSUPPORTED;
+    GeomB g;
+    const int rc = geometry_b(layer, &g);
+    if (rc != KAGNN_OK) return rc;
+    return launch_bwd_weights_tc(g, x, ldx, dy, ld_dy, num_rows, d_packed, stream);
+}
+
+// FastKAN: dz (through the Gaussians) and dx_base (through the SiLU branch) -- one matrix when there is no LayerNorm
+int kagnn_rbf_bwd_input_tc(const KagnnKanLayer* layer, const float* x, int64_t ldx, const float* ln_stats, const float* dy, int64_t ld_dy,
+                           int64_t num_rows, float* dz, int64_t ld_dz, float* dx_base, int64_t ld_dxb, cudaStream_t stream) {
+    if (g_bwd_path.load() != 0) return KAGNN_EUNSUPPORTED;
+    GeomB g;
+    const int rc = geometry_rbf_b(layer, ln_stats, &g);
+    if (rc != KAGNN_OK) return rc;
+    return launch_bwd_input_tc(g, layer->packed_w, x, ldx, dy, ld_dy, num_rows, dz, ld_dz, ln_stats ? dx_base : nullptr, ld_dxb, stream);
+}
+
+int kagnn_rbf_bwd_weights_tc(const KagnnKanLayer* layer, const float* x, int64_t ldx, const float* ln_stats, const float* dy, int64_t ld_dy,
+                             int64_t num_rows, float* d_packed, cudaStream_t stream) {
+    if (g_bwd_path.load() != 0) return KAGNN_EUNSUPPORTED;
+    GeomB g;
+    const int rc = geometry_rbf_b(layer, ln_stats, &g);
+    if (rc != KAGNN_OK) return rc;
+    return launch_bwd_weights_tc(g, x, ldx, dy, ld_dy, num_rows, d_packed, stream);
 }

@@ -51,6 +51,10 @@ int kagnn_kan_bwd_weights_tc(const KagnnKanLayer* layer, const float* x, int64_t
                              float* d_packed, cudaStream_t stream);
 int kagnn_kan_bwd_input_tc(const KagnnKanLayer* layer, const float* x, int64_t ldx, const float* dy, int64_t ld_dy, int64_t num_rows,
                            float* dx, int64_t ld_dx, cudaStream_t stream);
+int kagnn_rbf_bwd_input_tc(const KagnnKanLayer* layer, const float* x, int64_t ldx, const float* ln_stats, const float* dy, int64_t ld_dy,
+                           int64_t num_rows, float* dz, int64_t ld_dz, float* dx_base, int64_t ld_dxb, cudaStream_t stream);
+int kagnn_rbf_bwd_weights_tc(const KagnnKanLayer* layer, const float* x, int64_t ldx, const float* ln_stats, const float* dy, int64_t ld_dy,
+                             int64_t num_rows, float* d_packed, cudaStream_t stream);
 int kagnn_kan_bwd_weights_tiled(const KagnnKanLayer* layer, const float* x, int64_t ldx, const float* dy, int64_t ld_dy, int64_t num_rows,
                                 float* d_packed, cudaStream_t stream);
 int kagnn_kan_bwd_input_tiled(const KagnnKanLayer* layer, const float* x, int64_t ldx, const float* dy, int64_t ld_dy, int64_t num_rows,

@@ -85,3 +85,45 @@ def test_tc_gradients_full_size_strided():
         ops.set_backward_path(0)
     assert K.rel_err(dx_tc.cpu(), dx_32.cpu()) <= TOL_PATHS
     assert K.rel_err(dp_tc.cpu(), dp_32.cpu()) <= TOL_PATHS
+
+
+RBF_SHAPES = [  # (rows, in, out, num_grids, layernorm)
+    (1000, 64, 64, 8, True),
+    (777, 256, 256, 8, True),      # BASELINE C5 width
+    (300, 33, 7, 4, True),
+    (2048, 7, 256, 8, True),
+    (640, 48, 40, 5, False),       # use_layernorm=False: z = x, one output matrix
+]
+
+
+@pytest.mark.parametrize("rows,in_f,out_f,G,ln", RBF_SHAPES)
+def test_tc_gradients_of_the_fastkan_layer_match_the_fp32_kernels(rows, in_f, out_f, G, ln):
+    """FastKANLayer (fastkan.py:76-85): dz / dx_base / dP from the tensor-core kernels against the fp32 ones."""
+    import kagnn_b200 as kb
+    from kagnn_b200 import ops
+    torch.manual_seed(rows + in_f)
+    lay = kb.FastKANLayer(in_f, out_f, num_grids=G, use_layernorm=ln).cuda()
+    if ln:
+        with torch.no_grad():
+            lay.layernorm.weight.uniform_(0.5, 1.5)
+            lay.layernorm.bias.normal_(0, 0.2)
+    spec = lay.kernel_specs()[0]
+    g = torch.Generator(device="cuda").manual_seed(rows)
+    x = torch.randn(rows, in_f, generator=g, device="cuda") * 0.9
+    dy = torch.randn(rows, out_f, generator=g, device="cuda")
+    stats = ops.layernorm_stats(x) if ln else None
+    ops.set_backward_path(0)
+    dz_tc, dxb_tc = ops.rbf_bwd_input(spec, x, stats, dy)
+    dp_tc = ops.rbf_bwd_weights(spec, x, stats, dy)
+    ops.set_backward_path(1)
+    try:
+        dz_32, dxb_32 = ops.rbf_bwd_input(spec, x, stats, dy)
+        dp_32 = ops.rbf_bwd_weights(spec, x, stats, dy)
+    finally:
+        ops.set_backward_path(0)
+    assert K.rel_err(dz_tc.cpu(), dz_32.cpu()) <= TOL_PATHS
+    assert K.rel_err(dp_tc.cpu(), dp_32.cpu()) <= TOL_PATHS
+    if ln:
+        assert K.rel_err(dxb_tc.cpu(), dxb_32.cpu()) <= TOL_PATHS
+    else:
+        assert dxb_tc is None and dxb_32 is None
