@@ -164,6 +164,54 @@ class PeerPlan:
     world: int
 
 
+def push_plan_arrays(edge_index_global: Tensor, rank: int, world: int, n_local: int):
+    """Index arithmetic of the "push" plan (no communication, no sort, no host synchronisation).  Every layer aggregates over
+    [own rows | replica of the whole matrix]: a local source j becomes j - lo, a remote one n_local + j, so ONE edge list serves
+    the input features and every hidden matrix.  Returns (source ids in that numbering, local target ids, need) where
+    ``need`` is a byte map over all node ids: 1 <=> this rank references the (remote) row.  An id outside the global range
+    stays out of range (-1) so that the deferred check of the CSR build reports it."""
+    lo, n_tot = rank * n_local, n_local * world
+    src, dst = edge_index_global[0], edge_index_global[1] - lo
+    ok = (src >= 0) & (src < n_tot)
+    local = (src >= lo) & (src < lo + n_local)
+    src_rep = torch.where(ok, torch.where(local, src - lo, src + n_local), torch.full_like(src, -1))
+    need = torch.zeros(n_tot, dtype=torch.uint8, device=edge_index_global.device)
+    need[src.clamp(0, n_tot - 1)] = 1
+    need[lo:lo + n_local] = 0
+    return src_rep, dst, need
+
+
+def push_peers(rank: int, world: int) -> List[int]:
+    """The ranks a rank pushes to, in the bit order of its push mask / the order of its destination table."""
+    return [q for q in range(world) if q != rank]
+
+
+def push_row_masks(need: Tensor, rank: int, world: int, n_local: int, group=None) -> Tensor:
+    """Collective (one all-gather of the byte maps): byte r of the result has bit i set <=> rank push_peers(rank)[i] references
+    row r of this rank -- the rows the producing layer's kernel copies to that peer."""
+    n_tot = n_local * world
+    if dist.is_available() and dist.is_initialized() and world > 1:
+        if need.is_cuda:
+            maps = torch.empty(world, n_tot, dtype=torch.uint8, device=need.device)
+            dist.all_gather_into_tensor(maps.view(-1), need, group=group)
+        else:                                              # gloo (CPU tests)
+            parts = [torch.empty_like(need) for _ in range(world)]
+            dist.all_gather(parts, need, group=group)
+            maps = torch.stack(parts)
+    else:
+        maps = need.view(1, -1).expand(world, -1)
+    return masks_from_maps(maps, rank, world, n_local)
+
+
+def masks_from_maps(maps: Tensor, rank: int, world: int, n_local: int) -> Tensor:
+    lo = rank * n_local
+    peers = torch.tensor(push_peers(rank, world), dtype=torch.int64, device=maps.device)
+    if peers.numel() == 0:
+        return torch.zeros(n_local, dtype=torch.uint8, device=maps.device)
+    shifts = torch.arange(world - 1, dtype=torch.uint8, device=maps.device).view(-1, 1)
+    return torch.bitwise_left_shift(maps[peers, lo:lo + n_local], shifts).sum(0, dtype=torch.uint8)
+
+
 class ShardedNodeModel:
     """Runs a ``GKAN_Nodes`` / ``GFASTKAN_Nodes`` (eval mode, weights replicated on every rank) on this rank's node
     range: the fused plan of ``models_node._NodeModel.forward`` with the remote source rows of each aggregation fetched
@@ -295,29 +343,15 @@ class ShardedNodeModel:
 
     def push_peers(self):
         """The ranks this one pushes to, in the bit order of the push mask / the order of the destination table."""
-        return [q for q in range(self.world) if q != self.rank]
+        return push_peers(self.rank, self.world)
 
     def _prepare_push(self, edge_index_global: Tensor):
-        """Plan of mode "push" -- no sort besides the CSR build, no ``unique``, no host synchronisation.  Every layer aggregates
-        over [own rows | replica of the whole matrix]: a local source j becomes j - lo, a remote one n_local + j, so ONE CSR
-        serves the input features and every hidden matrix.  Which remote rows this rank needs is one scatter into a byte map
-        (``need``); the maps of all ranks (one all-gather) give, per own row, the byte of peers that reference it."""
-        n, w, lo = self.n_local, self.world, self.rank * self.n_local
-        n_tot, dev = n * w, edge_index_global.device
-        src, dst = edge_index_global[0], edge_index_global[1] - lo
-        ok = (src >= 0) & (src < n_tot)
-        local = (src >= lo) & (src < lo + n)
-        # an id outside the global range stays out of range (-1) so that the deferred check of the CSR build reports it
-        src_rep = torch.where(ok, torch.where(local, src - lo, src + n), torch.full_like(src, -1))
-        plan = PeerPlan(GraphCSR(torch.stack([src_rep, dst]), n, n + n_tot), n, w)
-        need = torch.zeros(n_tot, dtype=torch.uint8, device=dev)
-        need[src.clamp(0, n_tot - 1)] = 1
-        need[lo:lo + n] = 0
-        maps = torch.empty(w, n_tot, dtype=torch.uint8, device=dev)
-        dist.all_gather_into_tensor(maps.view(-1), need, group=self.group)
-        peers = torch.tensor(self.push_peers(), dtype=torch.int64, device=dev)
-        shifts = torch.arange(w - 1, dtype=torch.uint8, device=dev).view(-1, 1)
-        plan.push_mask = torch.bitwise_left_shift(maps[peers, lo:lo + n], shifts).sum(0, dtype=torch.uint8)
+        """Plan of mode "push" -- no sort besides the CSR build, no ``unique``, no host synchronisation (push_plan_arrays /
+        push_row_masks: index arithmetic + one all-gather of byte maps)."""
+        n, w = self.n_local, self.world
+        src_rep, dst, need = push_plan_arrays(edge_index_global, self.rank, w, n)
+        plan = PeerPlan(GraphCSR(torch.stack([src_rep, dst]), n, n + n * w), n, w)
+        plan.push_mask = push_row_masks(need, self.rank, w, n, self.group)
         plan.need = need
         return plan
 

@@ -174,3 +174,64 @@ def test_sharded_model_forward_gloo(conv_type):
     for p in procs:
         p.join(timeout=60)
     assert sorted(results) == [(r, "ok") for r in range(world)], results
+
+
+# ---- plan of the "push" transport (kagnn_b200/dist.py: push_plan_arrays / push_row_masks) --------------------------------------
+def _push_worker(rank, world, port, n_local, e_per_rank, f, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from kagnn_b200 import dist as kd
+        x, eis = _global_problem(world, n_local, e_per_rank, f, seed=3)
+        ei, lo, n = eis[rank], rank * n_local, world * n_local
+        src_rep, dst, need = kd.push_plan_arrays(ei, rank, world, n_local)
+        # the byte map marks exactly the distinct remote sources
+        remote = sorted({int(s) for s in ei[0].tolist() if not (lo <= s < lo + n_local)})
+        assert need.nonzero().view(-1).tolist() == remote
+        # [own rows | replica of everything] + the renumbered edge list reproduce the aggregation over the global graph
+        x_ext = torch.cat([x[lo:lo + n_local], x])
+        agg_local = torch.zeros(n_local, f).index_add_(0, dst, x_ext[src_rep])
+        ei_all = torch.cat(eis, dim=1)
+        agg_global = torch.zeros(n, f).index_add_(0, ei_all[1], x[ei_all[0]])
+        assert torch.allclose(agg_local, agg_global[lo:lo + n_local], atol=1e-5)
+        # masks: bit i of byte r <=> peer i references my row r (checked against every rank's edge list)
+        mask = kd.push_row_masks(need, rank, world, n_local)
+        expect = torch.zeros(n_local, dtype=torch.uint8)
+        for i, q in enumerate(kd.push_peers(rank, world)):
+            refs = eis[q][0]
+            mine = refs[(refs >= lo) & (refs < lo + n_local)] - lo
+            expect[mine.unique()] |= (1 << i)
+        assert torch.equal(mask, expect)
+        # simulated transfer: what the peers push + what I pull of x must cover every row my edge list reads
+        have = torch.zeros(n, dtype=torch.bool)
+        have[need.bool()] = True                                   # masked pull of the input halo fills exactly these rows
+        assert have[ei[0][(ei[0] < lo) | (ei[0] >= lo + n_local)]].all()
+        out.put((rank, "ok"))
+    except Exception as exc:  # pragma: no cover - reported to the parent
+        import traceback
+        out.put((rank, f"{type(exc).__name__}: {exc}\n{traceback.format_exc()}"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_push_plan_gloo(world):
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_push_worker, args=(r, world, port, 40, 300, 5, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [out.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(results) == [(r, "ok") for r in range(world)], results
+
+
+def test_push_plan_flags_out_of_range_sources():
+    from kagnn_b200 import dist as kd
+    ei = torch.tensor([[0, 7, 12, -1], [0, 1, 2, 3]])
+    src_rep, dst, need = kd.push_plan_arrays(ei, 0, 2, 5)
+    assert src_rep.tolist() == [0, 5 + 7, -1, -1]                  # ids outside [0, 10) stay out of range for the CSR build's check
+    assert need.tolist() == [0, 0, 0, 0, 0, 0, 0, 1, 0, 1]         # (clamped ids of the bad entries may mark a row: harmless extra traffic)
