@@ -442,7 +442,7 @@ def main():
                             "traffic = ncu dram bytes of the same launch (profiles/, null if that launch was not captured)"}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:             # the CPU baseline is timed at N = 1 only
         n_s, e_s, ts, threads = cpu_baseline_sample(sd_cpu, 1, steps=2, warmup=1)
         cpu = {"value": n_s / min(ts), "unit": "nodes/s", "cores": threads, "kind": "port",
                "sample": f"oracle forward of the full model on the full {n_s}-node / {e_s}-edge workload graph, best of 2 (1 warm-up)"}
