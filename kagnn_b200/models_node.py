@@ -154,7 +154,8 @@ class _NodeModel(nn.Module):
         hid = self.bns[0].num_features
         if needs_grad or not self._fusable():
             return self._forward_unfused(x, g, needs_grad)
-        if 0 < n <= _AUTO_GRAPH_NODES and x.is_cuda and not torch.cuda.is_current_stream_capturing() and not getattr(self, "_in_replay", False):
+        if (0 < n <= _AUTO_GRAPH_NODES and x.is_cuda and x.device.index == torch.cuda.current_device()
+                and not torch.cuda.is_current_stream_capturing() and not getattr(self, "_in_replay", False)):
             if not hasattr(self, "_replay"):
                 object.__setattr__(self, "_replay", _GraphReplay())
             object.__setattr__(self, "_in_replay", True)
