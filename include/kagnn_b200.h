@@ -371,6 +371,17 @@ int kagnn_layernorm_bwd(const float* x, int64_t ldx, const float* ln_stats, cons
                         int64_t ld_dz, const float* dx_base_or_null, int64_t ld_dxb, int64_t num_rows, int32_t num_cols, float* dx,
                         int64_t ld_dx, float* d_weight_or_null, float* d_bias_or_null, void* stream);
 
+/* Backward of the GAT attention (autograd of PyG GATConv.forward as used by KAGATConv, nc/models.py:39-46): h (N, heads*C) is the
+ * projected input, edge_weight (heads, nnz) / self_weight (heads, N) the coefficients the forward produced (kagnn_gat_edge_softmax).
+ * On entry dh holds the aggregation part sum_i alpha_ij d out[i] (the WEIGHTED aggregation over the reversed edges, one launch per
+ * head); the call adds the part that flows through the attention scores and writes d att_src / d att_dst (heads*C each).
+ * Workspace: kagnn_gat_bwd_workspace(N, nnz, heads). */
+size_t kagnn_gat_bwd_workspace(int64_t num_rows, int64_t nnz, int32_t heads);
+int kagnn_gat_bwd(const int32_t* rowptr, const int32_t* col, int64_t num_rows, int64_t nnz, int32_t heads, int32_t channels,
+                  const float* h, int64_t ldh, const float* dout, int64_t ld_dout, const float* att_src, const float* att_dst,
+                  const float* edge_weight, const float* self_weight, float negative_slope, void* workspace, size_t workspace_bytes,
+                  float* dh, int64_t ld_dh, float* d_att_src, float* d_att_dst, void* stream);
+
 /* Backward of the GINE aggregation a_i = self_scale x_i + sum_{e: dst_e = i} relu(x_{src_e} + ef_e) (PyG GINEConv,
  * graph_regression/models.py:98) on the COO edge list: edge_index is the contiguous (2, E) int64 tensor, edge_feat has one row
  * per edge in the same order.  dx (num_nodes x num_cols) is overwritten; d_edge_feat (E x num_cols) may be NULL. */

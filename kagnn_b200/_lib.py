@@ -80,6 +80,10 @@ _SIGNATURES = {
     "kagnn_pack_kan_weights_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "kagnn_set_path": (C.c_int, [C.c_int]),
     "kagnn_set_backward_path": (C.c_int, [C.c_int32]),
+    "kagnn_gat_bwd_workspace": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int32]),
+    "kagnn_gat_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p,
+                                C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_size_t, C.c_void_p,
+                                C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "kagnn_get_launch_counters": (C.c_int, [C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "kagnn_set_tc_variant": (C.c_int, [C.c_int]),
     "kagnn_set_precision": (C.c_int, [C.c_int]),

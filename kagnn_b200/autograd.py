@@ -185,6 +185,54 @@ def gcn_aggregate(h: Tensor, bias: Optional[Tensor], graph) -> Tensor:
     return _GcnAggFn.apply(h, bias, graph)
 
 
+class _GatAttendFn(torch.autograd.Function):
+    """PyG GATConv after its projection: out[i] = sum_j alpha_ij h[j] + b per head, alpha = edge-softmax of
+    leaky_relu(<h_j, att_src> + <h_i, att_dst>) over the incoming edges and the self loop (node_classification_clean/models.py:39-46).
+    Backward: dh = sum_i alpha_ij d out[i] (WEIGHTED aggregation over the reversed edges, one launch per head) + the part through
+    the scores (kagnn_gat_bwd), d att_src / d att_dst, d b = column sums."""
+
+    @staticmethod
+    def forward(ctx, h, att_src, att_dst, bias, graph, heads, slope):
+        h = _rowmajor(h)
+        n, hc = h.shape
+        c = hc // heads
+        w, sw = ops.gat_attention(h, graph.csr, att_src, att_dst, heads, slope)
+        out = torch.empty(n, hc, dtype=torch.float32, device=h.device)
+        for k in range(heads):
+            sl = slice(k * c, (k + 1) * c)
+            agg = ops.AggSpec(L.AGG_WEIGHTED, h[:, sl], graph.rowptr, graph.col, edge_weight=w[k], self_weight=sw[k])
+            ops.fused_layer(agg, n, [], pre=ops.Affine(shift=bias.detach()[sl]) if bias is not None else None, agg_out=out[:, sl])
+        ctx.save_for_backward(h, att_src, att_dst, w, sw)
+        ctx.graph, ctx.heads, ctx.slope, ctx.has_bias = graph, heads, slope, bias is not None
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        dout = _rowmajor(dout).contiguous()
+        h, att_src, att_dst, w, sw = ctx.saved_tensors
+        g, heads = ctx.graph, ctx.heads
+        n, hc = h.shape
+        c = hc // heads
+        gt = g.transposed()
+        # the coefficients in the entry order of the reversed graph (an edge keeps its coefficient)
+        by_edge = torch.empty_like(w)
+        by_edge[:, g.csr.perm.long()] = w
+        w_t = by_edge[:, gt.csr.perm.long()].contiguous() if w.size(1) else w
+        dh = torch.empty(n, hc, dtype=torch.float32, device=h.device)
+        for k in range(heads):
+            sl = slice(k * c, (k + 1) * c)
+            agg = ops.AggSpec(L.AGG_WEIGHTED, dout[:, sl], gt.rowptr, gt.col, edge_weight=w_t[k], self_weight=sw[k])
+            ops.fused_layer(agg, n, [], agg_out=dh[:, sl])
+        d_as, d_ad = ops.gat_backward(h, g.csr, dout, att_src, att_dst, w, sw, heads, ctx.slope, dh)
+        db = ops.column_sums(dout) if ctx.has_bias and ctx.needs_input_grad[3] else None
+        return dh, d_as.view_as(att_src), d_ad.view_as(att_dst), db, None, None, None
+
+
+def gat_attend(h: Tensor, att_src: Tensor, att_dst: Tensor, bias: Optional[Tensor], graph, heads: int, slope: float) -> Tensor:
+    return _GatAttendFn.apply(h, att_src, att_dst, bias, graph, heads, slope)
+
+
 class _BatchNormFn(torch.autograd.Function):
     """Training-mode BatchNorm1d (batch statistics; running estimates updated by the forward launch)."""
 

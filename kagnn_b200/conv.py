@@ -236,7 +236,7 @@ class GATConv(_MessagePassing):
     dropout=0, add_self_loops=True, bias=True, edge_dim=None) and PyG 2.5's parameter names: one shared projection ``lin``
     (which the KAN-ised subclasses replace), ``att_src`` / ``att_dst`` (1, heads, out_channels), ``bias`` (heads * out_channels).
     Forward = projection launch, attention launches (``ops.gat_attention``), one WEIGHTED aggregation launch per head on the
-    head's column slice.  Inference only: the edge-softmax has no backward here."""
+    head's column slice.  Under autograd the attention + aggregation is one ``autograd.Function`` (``autograd.gat_attend``)."""
 
     def __init__(self, in_channels: int, out_channels: int, heads: int = 1, concat: bool = True, negative_slope: float = 0.2,
                  dropout: float = 0.0, add_self_loops: bool = True, edge_dim=None, fill_value="mean", bias: bool = True, **kwargs):
@@ -279,8 +279,14 @@ class GATConv(_MessagePassing):
                 extra: Optional[ops.Affine] = None) -> Tensor:
         if edge_attr is not None:
             raise NotImplementedError("edge_dim is never used by the reference")
-        _module_backend_guard(x, list(self.parameters()), grad_ok=False)
+        needs_grad = _module_backend_guard(x, list(self.parameters()), grad_ok=True)
         g = self._graph(x, edge_index)
+        if needs_grad:
+            # training: projection (its own autograd Function) -> attention + aggregation with a library backward; the callers'
+            # fused epilogues (``extra``) belong to the inference plan
+            if extra is not None or out is not None:
+                raise NotImplementedError("fused epilogues are part of the inference plan; under autograd call conv(x, edge_index)")
+            return autograd.gat_attend(self.lin(x), self.att_src, self.att_dst, self.bias, g, self.heads, self.negative_slope)
         return self.attend_and_aggregate(self.lin(x).to(torch.float32), g, out=out, extra=extra)
 
 

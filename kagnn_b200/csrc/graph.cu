@@ -477,6 +477,128 @@ extern "C" int kagnn_gat_edge_softmax(const int32_t* rowptr, const int32_t* col,
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Backward of the GAT attention (what autograd derives from PyG GATConv.forward): with
+//   out[i,hd,:] = sum_j alpha_ij h[j,hd,:] (+ bias),  alpha = softmax_j(leaky_relu(a_src[j] + a_dst[i])),  a_* = <h, att_*>
+// and d out given, the caller has already put  dh = sum_i alpha_ij d out[i]  (the aggregation over the reversed edges) into dh.
+//   gat_bwd_edges (warp per destination row i, per head):  g_e = <d out[i], h[j]>,  s = sum_e alpha_e g_e,
+//       d e = alpha_e (g_e - s),  d pre = d e * leaky_relu'(a_src[j] + a_dst[i]);
+//       d a_dst[i] = sum_e d pre_e (row sum),  d a_src[j] += d pre_e (float atomics)
+//   gat_bwd_proj:  dh[n,hd,:] += d a_src[n,hd] att_src[hd,:] + d a_dst[n,hd] att_dst[hd,:];
+//       d att_src[hd,c] = sum_n d a_src[n,hd] h[n,hd,c],  d att_dst likewise
+// ---------------------------------------------------------------------------------------------------
+namespace {
+__global__ void gat_bwd_edges_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t rows, int64_t nnz, int heads,
+                                     int C, const float* __restrict__ h, int64_t ldh, const float* __restrict__ dout, int64_t ldo,
+                                     const float* __restrict__ a_src, const float* __restrict__ a_dst, const float* __restrict__ edge_w,
+                                     const float* __restrict__ self_w, float slope, float* __restrict__ g_tmp, float* __restrict__ da_src,
+                                     float* __restrict__ da_dst) {
+    const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (i >= rows) return;
+    const int beg = rowptr[i], end = rowptr[i + 1];
+    for (int hd = 0; hd < heads; ++hd) {
+        const float* d = dout + i * ldo + hd * C;
+        auto dot_with = [&](int64_t j) {
+            const float* hj = h + j * ldh + hd * C;
+            float t = 0.f;
+            for (int c = lane; c < C; c += 32) t = fmaf(d[c], hj[c], t);
+            for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            return t;
+        };
+        const float al_s = self_w[(int64_t)hd * rows + i];
+        const float g_s = dot_with(i);
+        float s = al_s * g_s;
+        for (int e = beg; e < end; ++e) {
+            const int j = col[e];
+            const float al = edge_w[(int64_t)hd * nnz + e];
+            float g = 0.f;
+            if (j != (int)i) g = dot_with(j);            // a removed self loop carries weight 0
+            if (lane == 0) g_tmp[(int64_t)hd * nnz + e] = g;
+            s = fmaf(al, g, s);
+        }
+        __syncwarp();
+        const float ad = a_dst[i * heads + hd];
+        float row = 0.f;
+        for (int e = beg + lane; e < end; e += 32) {
+            const int j = col[e];
+            if (j == (int)i) continue;
+            const float pre = a_src[(int64_t)j * heads + hd] + ad;
+            const float dpre = edge_w[(int64_t)hd * nnz + e] * (g_tmp[(int64_t)hd * nnz + e] - s) * (pre > 0.f ? 1.0f : slope);
+            atomicAdd(da_src + (int64_t)j * heads + hd, dpre);
+            row += dpre;
+        }
+        for (int o = 16; o; o >>= 1) row += __shfl_xor_sync(0xffffffffu, row, o);
+        if (lane == 0) {
+            const float pre = a_src[i * heads + hd] + ad;
+            const float dpre = al_s * (g_s - s) * (pre > 0.f ? 1.0f : slope);
+            atomicAdd(da_src + i * heads + hd, dpre);
+            da_dst[i * heads + hd] = row + dpre;
+        }
+    }
+}
+
+// block = a slab of rows, threads stride over the heads * C columns (coalesced); partial column sums by one atomic per thread
+__global__ void gat_bwd_proj_kernel(const float* __restrict__ h, int64_t ldh, int64_t rows, int heads, int C, const float* __restrict__ att_src,
+                                    const float* __restrict__ att_dst, const float* __restrict__ da_src, const float* __restrict__ da_dst,
+                                    int64_t rows_per_block, float* __restrict__ dh, int64_t ld_dh, float* __restrict__ d_att_src,
+                                    float* __restrict__ d_att_dst) {
+    const int64_t r0 = blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+    for (int c = threadIdx.x; c < heads * C; c += blockDim.x) {
+        const int hd = c / C;
+        const float ws = att_src[c], wd = att_dst[c];
+        float ps = 0.f, pd = 0.f;
+        for (int64_t r = r0; r < r1; ++r) {
+            const float as = da_src[r * heads + hd], ad = da_dst[r * heads + hd], hv = h[r * ldh + c];
+            dh[r * ld_dh + c] += fmaf(as, ws, ad * wd);
+            ps = fmaf(as, hv, ps);
+            pd = fmaf(ad, hv, pd);
+        }
+        atomicAdd(d_att_src + c, ps);
+        atomicAdd(d_att_dst + c, pd);
+    }
+}
+}  // namespace
+
+extern "C" size_t kagnn_gat_bwd_workspace(int64_t num_rows, int64_t nnz, int32_t heads) {
+    if (num_rows < 0 || nnz < 0 || heads <= 0) return 0;
+    return sizeof(float) * ((size_t)heads * (size_t)nnz + (size_t)4 * (size_t)num_rows * (size_t)heads) + 64;
+}
+
+extern "C" int kagnn_gat_bwd(const int32_t* rowptr, const int32_t* col, int64_t num_rows, int64_t nnz, int32_t heads, int32_t channels,
+                             const float* h, int64_t ldh, const float* dout, int64_t ld_dout, const float* att_src, const float* att_dst,
+                             const float* edge_weight, const float* self_weight, float negative_slope, void* workspace,
+                             size_t workspace_bytes, float* dh, int64_t ld_dh, float* d_att_src, float* d_att_dst, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int64_t hc = (int64_t)heads * channels;
+    if (num_rows < 0 || nnz < 0 || heads <= 0 || channels <= 0 || ldh < hc || ld_dout < hc || ld_dh < hc) return KAGNN_EINVAL;
+    if (!d_att_src || !d_att_dst) return KAGNN_EINVAL;
+    KAGNN_CUDA_TRY(cudaMemsetAsync(d_att_src, 0, sizeof(float) * (size_t)hc, stream));
+    KAGNN_CUDA_TRY(cudaMemsetAsync(d_att_dst, 0, sizeof(float) * (size_t)hc, stream));
+    if (num_rows == 0) return KAGNN_OK;
+    if (!rowptr || !h || !dout || !att_src || !att_dst || !self_weight || !dh || (nnz > 0 && (!col || !edge_weight))) return KAGNN_EINVAL;
+    if (!workspace || workspace_bytes < kagnn_gat_bwd_workspace(num_rows, nnz, heads)) return KAGNN_EWORKSPACE;
+    float* g_tmp = static_cast<float*>(workspace);
+    float* a_src = g_tmp + (size_t)heads * (size_t)nnz;
+    float* a_dst = a_src + (size_t)num_rows * heads;
+    float* da_src = a_dst + (size_t)num_rows * heads;
+    float* da_dst = da_src + (size_t)num_rows * heads;
+    gat_scores_kernel<<<(unsigned)ceil_div64(num_rows * 32, kThreads), kThreads, 0, stream>>>(h, ldh, num_rows, heads, channels, att_src,
+                                                                                              att_dst, a_src, a_dst);
+    KAGNN_LAUNCH_CHECK();
+    KAGNN_CUDA_TRY(cudaMemsetAsync(da_src, 0, sizeof(float) * (size_t)num_rows * heads, stream));
+    gat_bwd_edges_kernel<<<(unsigned)ceil_div64(num_rows * 32, kThreads), kThreads, 0, stream>>>(
+        rowptr, col, num_rows, nnz, heads, channels, h, ldh, dout, ld_dout, a_src, a_dst, edge_weight, self_weight, negative_slope, g_tmp,
+        da_src, da_dst);
+    KAGNN_LAUNCH_CHECK();
+    const int64_t rows_per_block = 256;
+    gat_bwd_proj_kernel<<<(unsigned)ceil_div64(num_rows, rows_per_block), 128, 0, stream>>>(h, ldh, num_rows, heads, channels, att_src, att_dst,
+                                                                                            da_src, da_dst, rows_per_block, dh, ld_dh,
+                                                                                            d_att_src, d_att_dst);
+    KAGNN_LAUNCH_CHECK();
+    return KAGNN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Row-wise log_softmax of the class logits (graph_classification/models.py:119,194) and training-mode
 // BatchNorm1d (node_classification_clean/models.py:197 with model.train(): batch statistics over all
 // rows, biased variance for the normalisation, unbiased for the running estimate, momentum update).

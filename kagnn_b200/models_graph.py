@@ -189,7 +189,9 @@ class _GATGraphModel(_GCNGraphModel):
 
     def _message_passing(self, x: Tensor, g, needs_grad: bool = False) -> Tensor:
         if needs_grad:
-            raise NotImplementedError("the GAT flavour has no backward here (inference / evaluation only)")
+            for i in range(self.n_layers):
+                x = self.dropout(autograd.silu(self.conv[i](x, g)))        # conv = projection + attention, each with a library backward
+            return x
         for i in range(self.n_layers):
             c = self.conv[i]
             x = c(x, g, extra=ops.Affine(shift=c.bias.detach(), act=L.ACT_SILU))

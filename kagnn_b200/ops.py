@@ -396,6 +396,29 @@ def gat_attention(h: Tensor, csr: CSR, att_src: Tensor, att_dst: Tensor, heads: 
     return w[:, :csr.nnz] if csr.nnz else w[:, :0], sw
 
 
+@_on_device
+def gat_backward(h: Tensor, csr: CSR, dout: Tensor, att_src: Tensor, att_dst: Tensor, w: Tensor, sw: Tensor, heads: int,
+                 negative_slope: float, dh: Tensor):
+    """Attention part of PyG GATConv's backward (kagnn_gat_bwd): ``dh`` holds the aggregation part on entry and gets the part
+    that flows through the scores added; returns (d att_src, d att_dst), each (heads * C,)."""
+    global launch_count
+    n, hc = h.shape
+    c = hc // heads
+    dev = h.device
+    ats, atd = att_src.detach().reshape(-1).contiguous(), att_dst.detach().reshape(-1).contiguous()
+    d_as = torch.empty(hc, dtype=torch.float32, device=dev)
+    d_ad = torch.empty(hc, dtype=torch.float32, device=dev)
+    nbytes = int(L.lib().kagnn_gat_bwd_workspace(n, csr.nnz, heads))
+    ws = torch.empty(max(nbytes, 4) // 4 + 1, dtype=torch.float32, device=dev)
+    w = w.contiguous()
+    L.check(L.lib().kagnn_gat_bwd(_p(csr.rowptr), C.c_void_p(_addr(csr.col)), n, csr.nnz, heads, c, _p(h), _rows(h, "h"), _p(dout),
+                                  _rows(dout, "dout"), _p(ats), _p(atd), C.c_void_p(_addr(w)) if csr.nnz else None, _p(sw),
+                                  float(negative_slope), _p(ws), ws.numel() * 4, _p(dh), _rows(dh, "dh"), _p(d_as), _p(d_ad), _stream()),
+            "gat_bwd")
+    launch_count += 3
+    return d_as, d_ad
+
+
 HALO_CHUNK = 256          # rows per progress flag of gather_rows_peer_ordered (kHaloChunk in csrc/graph.cu)
 
 
