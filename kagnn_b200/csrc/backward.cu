@@ -600,6 +600,8 @@ extern "C" int kagnn_layernorm_bwd(const float* x, int64_t ldx, const float* ln_
     if (d_bias) KAGNN_CUDA_TRY(cudaMemsetAsync(d_bias, 0, (size_t)num_cols * sizeof(float), stream));
     if (num_rows == 0) return KAGNN_OK;
     if (!x || !ln_stats || !dz || !dx) return KAGNN_EINVAL;
+    KAGNN_TRY_TILED(kagnn_layernorm_bwd_fast(x, ldx, ln_stats, ln_weight, dz, ld_dz, dx_base, ld_dxb, num_rows, num_cols, dx, ld_dx, d_weight,
+                                             d_bias, stream));
     KAGNN_LAUNCH(layernorm_bwd_rows_kernel, (unsigned)ceil_div64(num_rows, 128), 128, stream, x, (long long)ldx, ln_stats, ln_weight,
                  dz, (long long)ld_dz, dx_base, (long long)ld_dxb, (long long)num_rows, (int)num_cols, dx, (long long)ld_dx);
     KAGNN_LAUNCH_CHECK();

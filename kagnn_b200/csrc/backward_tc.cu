@@ -441,13 +441,15 @@ __global__ void __launch_bounds__(kThreads) kan_bwd_weights_tc_kernel(GeomB g, c
     // warpgroup 0: features 0..7 (+ their base values, unit 14) and the first quarter of dY's units;
     // warpgroup 1: features 8..13 (+ base values, unit 15) and the rest of dY
     const int fi0 = wg ? 8 : 0, fi1 = wg ? kFB : 8;
-    const int nu = N16 / 8, u_split = nu / 4;
+    // share of dY's units per warpgroup: balanced against the features (8 vs 6, ~60 instructions each; a unit ~35)
+    const int nu = N16 / 8, u_split = (35 * nu - 120) > 0 ? (35 * nu - 120) / 70 : 0;
     const int u0 = wg ? u_split : 0, u1 = wg ? nu : u_split;
 
     // operands of a tile are fetched into registers one tile ahead (while the tensor pipe works on the previous one): the x values
     // of this warpgroup's features and, when dY is at most 64 wide and 16-byte aligned, its dY units
     constexpr int kPU = 6;
-    const bool dy_pf = nu <= 8 && g.out_f % 4 == 0 && ld_dy % 4 == 0 && ((reinterpret_cast<uintptr_t>(dy) & 15u) == 0);
+    const bool dy_vec = g.out_f % 4 == 0 && ld_dy % 4 == 0 && ((reinterpret_cast<uintptr_t>(dy) & 15u) == 0);
+    const bool dy_pf = nu <= 8 && dy_vec;
     float xq[8];
     float4 dq[kPU][2];
     auto load_tile = [&](long long rt_) {
@@ -539,18 +541,39 @@ __global__ void __launch_bounds__(kThreads) kan_bwd_weights_tc_kernel(GeomB g, c
                 }
             }
         } else {
+            // wide dY (more than 8 units): no register prefetch, but four units' loads in flight per round
             const float* dyr = dy + (row_ok ? row : 0) * ld_dy;
-            for (int u = u0; u < u1; ++u) {
-                float v[8];
+            for (int ub = u0; ub < u1; ub += 4) {
+                float4 q[4][2];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const int o = 8 * u + c;
-                    v[c] = (row_ok && o < g.out_f) ? __ldg(dyr + o) : 0.f;
+                for (int j = 0; j < 4; ++j) {
+                    const int u = ub + j;
+                    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (dy_vec) {
+                        q[j][0] = (row_ok && u < u1 && 8 * u + 4 <= g.out_f) ? __ldg(reinterpret_cast<const float4*>(dyr + 8 * u)) : z;
+                        q[j][1] = (row_ok && u < u1 && 8 * u + 8 <= g.out_f) ? __ldg(reinterpret_cast<const float4*>(dyr + 8 * u + 4)) : z;
+                    } else {
+                        float v[8];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const int o = 8 * u + c;
+                            v[c] = (row_ok && u < u1 && o < g.out_f) ? __ldg(dyr + o) : 0.f;
+                        }
+                        q[j][0] = make_float4(v[0], v[1], v[2], v[3]);
+                        q[j][1] = make_float4(v[4], v[5], v[6], v[7]);
+                    }
                 }
-                uint4 hi, lo;
-                tc::split8(v, hi, lo);
-                *reinterpret_cast<uint4*>(b_hi + (size_t)u * 2048 + r128 * 16) = hi;
-                *reinterpret_cast<uint4*>(b_lo + (size_t)u * 2048 + r128 * 16) = lo;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int u = ub + j;
+                    if (u < u1) {
+                        const float v[8] = {q[j][0].x, q[j][0].y, q[j][0].z, q[j][0].w, q[j][1].x, q[j][1].y, q[j][1].z, q[j][1].w};
+                        uint4 hi, lo;
+                        tc::split8(v, hi, lo);
+                        *reinterpret_cast<uint4*>(b_hi + (size_t)u * 2048 + r128 * 16) = hi;
+                        *reinterpret_cast<uint4*>(b_lo + (size_t)u * 2048 + r128 * 16) = lo;
+                    }
+                }
             }
         }
         tc::fence_proxy_async_smem();

@@ -303,3 +303,92 @@ int kagnn_kan_bwd_input_tiled(const KagnnKanLayer* layer, const float* x, int64_
     KAGNN_LAUNCH_CHECK();
     return KAGNN_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// LayerNorm backward (FastKANLayer's nn.LayerNorm, fastkan.py:66,78), product versions of backward.cu's thread-per-row kernels:
+//   rows:    warp per row, coalesced column strides, the two row means by warp shuffles
+//            dx = rstd (dz gamma - mean(dz gamma) - xhat mean(dz gamma xhat)) + dx_base
+//   params:  block = a slab of rows x 32 columns, eight row lanes per column, partial sums joined through shared memory,
+//            one float atomic per column and block:  dgamma = sum_n dz xhat, dbeta = sum_n dz
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+__global__ void layernorm_bwd_rows_warp_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ stats,
+                                               const float* __restrict__ ln_w, const float* __restrict__ dz, long long ld_dz,
+                                               const float* __restrict__ dxb, long long ld_dxb, long long n_rows, int cols,
+                                               float* __restrict__ dx, long long ld_dx) {
+    const long long n = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (n >= n_rows) return;
+    const float mean = stats[2 * n], rstd = stats[2 * n + 1];
+    const float *xr = x + n * ldx, *dzr = dz + n * ld_dz;
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = lane; i < cols; i += 32) {
+        const float gz = dzr[i] * (ln_w ? ln_w[i] : 1.0f);
+        s1 += gz;
+        s2 = fmaf(gz, (xr[i] - mean) * rstd, s2);
+    }
+    for (int o = 16; o; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    const float inv_f = 1.0f / (float)cols;
+    s1 *= inv_f;
+    s2 *= inv_f;
+    for (int i = lane; i < cols; i += 32) {
+        const float gz = dzr[i] * (ln_w ? ln_w[i] : 1.0f);
+        float v = rstd * (gz - s1 - (xr[i] - mean) * rstd * s2);
+        if (dxb) v += dxb[n * ld_dxb + i];
+        dx[n * ld_dx + i] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) layernorm_bwd_params_tile_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ stats,
+                                                                        const float* __restrict__ dz, long long ld_dz, long long n_rows, int cols,
+                                                                        long long rows_per_block, float* __restrict__ d_w, float* __restrict__ d_b) {
+    __shared__ float pw[8][33], pb[8][33];
+    const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int c = blockIdx.y * 32 + cl;
+    const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(n_rows, r0 + rows_per_block);
+    float sw = 0.f, sb = 0.f;
+    if (c < cols) {
+        for (long long r = r0 + rl; r < r1; r += 8) {
+            const float d = dz[r * ld_dz + c];
+            sw = fmaf(d, (x[r * ldx + c] - stats[2 * r]) * stats[2 * r + 1], sw);
+            sb += d;
+        }
+    }
+    pw[rl][cl] = sw;
+    pb[rl][cl] = sb;
+    __syncthreads();
+    if (rl == 0 && c < cols) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            a += pw[k][cl];
+            b += pb[k][cl];
+        }
+        if (d_w) atomicAdd(&d_w[c], a);
+        if (d_b) atomicAdd(&d_b[c], b);
+    }
+}
+}  // namespace
+
+// d_weight / d_bias are zeroed by the caller (kagnn_layernorm_bwd); always succeeds for num_rows > 0
+int kagnn_layernorm_bwd_fast(const float* x, int64_t ldx, const float* ln_stats, const float* ln_weight, const float* dz, int64_t ld_dz,
+                             const float* dx_base, int64_t ld_dxb, int64_t num_rows, int32_t num_cols, float* dx, int64_t ld_dx,
+                             float* d_weight, float* d_bias, cudaStream_t stream) {
+    if (num_rows < 1 || num_cols < 1) return KAGNN_EUNSUPPORTED;
+    layernorm_bwd_rows_warp_kernel<<<(unsigned)ceil_div64(num_rows * 32, kT), kT, 0, stream>>>(
+        x, (long long)ldx, ln_stats, ln_weight, dz, (long long)ld_dz, dx_base, (long long)ld_dxb, (long long)num_rows, (int)num_cols, dx,
+        (long long)ld_dx);
+    KAGNN_LAUNCH_CHECK();
+    if (d_weight || d_bias) {
+        const int64_t rows_per_block = 512;
+        const dim3 grid((unsigned)ceil_div64(num_rows, rows_per_block), (unsigned)((num_cols + 31) / 32), 1);
+        layernorm_bwd_params_tile_kernel<<<grid, 256, 0, stream>>>(x, (long long)ldx, ln_stats, dz, (long long)ld_dz, (long long)num_rows,
+                                                                  (int)num_cols, (long long)rows_per_block, d_weight, d_bias);
+        KAGNN_LAUNCH_CHECK();
+    }
+    return KAGNN_OK;
+}

@@ -1,0 +1,5 @@
+#!/bin/bash
+OUT=gpurun_out; mkdir -p $OUT
+timeout 300 python -m pytest tests/test_gpu_backward_tc.py -m gpu -q 2>&1 | tail -3 | cut -c1-200
+timeout 600 python scripts/train_step_c5.py --kernels > $OUT/r2_train_step_c5.json 2> $OUT/r2_train_step_c5_kernels.txt; echo "rc=$?"; cat $OUT/r2_train_step_c5.json | cut -c1-500; grep " ms " $OUT/r2_train_step_c5_kernels.txt | cut -c1-150 | head -5
+timeout 300 python scripts/train_step_time.py > $OUT/s35_train.json 2>/dev/null; cut -c1-300 $OUT/s35_train.json
