@@ -332,6 +332,7 @@ extern "C" int kagnn_batchnorm_train_bwd(const float* x, int64_t ldx, const floa
     if (!workspace || workspace_bytes < kagnn_batchnorm_bwd_workspace(num_cols)) return KAGNN_EWORKSPACE;
     double* sums = static_cast<double*>(workspace);
     KAGNN_CUDA_TRY(cudaMemsetAsync(sums, 0, (size_t)num_cols * 4 * sizeof(double), stream));
+    KAGNN_TRY_TILED(kagnn_batchnorm_train_bwd_fast(x, ldx, dy, ld_dy, num_rows, num_cols, weight, eps, dx, ld_dx, d_weight, d_bias, sums, stream));
     const int64_t rows_per_block = 256;
     KAGNN_LAUNCH(bn_bwd_sums_kernel, (unsigned)ceil_div64(num_rows, rows_per_block), 128, stream, x, (long long)ldx, dy,
                  (long long)ld_dy, (long long)num_rows, (int)num_cols, (long long)rows_per_block, sums);

@@ -392,3 +392,82 @@ int kagnn_layernorm_bwd_fast(const float* x, int64_t ldx, const float* ln_stats,
     }
     return KAGNN_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// BatchNorm1d backward (batch statistics), product versions of backward.cu's kernels with the same tiling as the forward
+// (graph.cu: bn_stats_tile_kernel): sums[0..3][c] = sum x, sum x^2, sum dy, sum dy x in fp64; then
+//   dx = A dy + B (x - mean) + C,   A = gamma rstd,  B = -gamma rstd^2 m2,  C = -A mean(dy),  m2 = mean(dy xhat)
+// with the per-column constants formed once per thread in fp64.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) bn_bwd_sums_tile_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ dy, long long ld_dy,
+                                                               long long rows, int cols, long long rows_per_block, double* __restrict__ sums) {
+    __shared__ double p[4][8][33];
+    const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int c = blockIdx.y * 32 + cl;
+    const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+    double sx = 0.0, sxx = 0.0, sd = 0.0, sdx = 0.0;
+    if (c < cols) {
+        for (long long r = r0 + rl; r < r1; r += 8) {
+            const double v = (double)x[r * ldx + c], d = (double)dy[r * ld_dy + c];
+            sx += v;
+            sxx += v * v;
+            sd += d;
+            sdx += d * v;
+        }
+    }
+    p[0][rl][cl] = sx;
+    p[1][rl][cl] = sxx;
+    p[2][rl][cl] = sd;
+    p[3][rl][cl] = sdx;
+    __syncthreads();
+    if (rl < 4 && c < cols) {                             // row lane q joins sum q of its column
+        double a = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a += p[rl][k][cl];
+        atomicAdd(&sums[(long long)rl * cols + c], a);
+    }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_tile_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ dy, long long ld_dy,
+                                                                long long rows, int cols, const double* __restrict__ sums,
+                                                                const float* __restrict__ weight, float eps, long long rows_per_block,
+                                                                float* __restrict__ dx, long long ld_dx, float* __restrict__ d_weight,
+                                                                float* __restrict__ d_bias) {
+    const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int c = blockIdx.y * 32 + cl;
+    if (c >= cols) return;
+    const double inv_n = 1.0 / (double)rows;
+    const double mean = sums[c] * inv_n;
+    const double var = fmax(sums[cols + c] * inv_n - mean * mean, 0.0);
+    const double rstd = 1.0 / sqrt(var + (double)eps);
+    const double sum_dy = sums[2 * cols + c];
+    const double sum_dy_xhat = (sums[3 * cols + c] - mean * sum_dy) * rstd;
+    const double gamma = weight ? (double)weight[c] : 1.0;
+    const float A = (float)(gamma * rstd), B = (float)(-gamma * rstd * rstd * sum_dy_xhat * inv_n), C = (float)(-gamma * rstd * sum_dy * inv_n);
+    const float mean_f = (float)mean;
+    const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+    for (long long r = r0 + rl; r < r1; r += 8) dx[r * ld_dx + c] = fmaf(A, dy[r * ld_dy + c], fmaf(B, x[r * ldx + c] - mean_f, C));
+    if (blockIdx.x == 0 && rl == 0) {
+        if (d_weight) d_weight[c] = (float)sum_dy_xhat;
+        if (d_bias) d_bias[c] = (float)sum_dy;
+    }
+}
+}  // namespace
+
+// `sums` (4 * num_cols doubles) is zeroed by the caller (kagnn_batchnorm_train_bwd)
+int kagnn_batchnorm_train_bwd_fast(const float* x, int64_t ldx, const float* dy, int64_t ld_dy, int64_t num_rows, int32_t num_cols,
+                                   const float* weight, float eps, float* dx, int64_t ld_dx, float* d_weight, float* d_bias, double* sums,
+                                   cudaStream_t stream) {
+    if (num_rows < 1 || num_cols < 1 || (num_cols + 31) / 32 > 65535) return KAGNN_EUNSUPPORTED;
+    const int64_t rows_per_block = 512;
+    const dim3 grid((unsigned)ceil_div64(num_rows, rows_per_block), (unsigned)((num_cols + 31) / 32), 1);
+    bn_bwd_sums_tile_kernel<<<grid, 256, 0, stream>>>(x, (long long)ldx, dy, (long long)ld_dy, (long long)num_rows, (int)num_cols,
+                                                     (long long)rows_per_block, sums);
+    KAGNN_LAUNCH_CHECK();
+    bn_bwd_apply_tile_kernel<<<grid, 256, 0, stream>>>(x, (long long)ldx, dy, (long long)ld_dy, (long long)num_rows, (int)num_cols, sums, weight,
+                                                      eps, (long long)rows_per_block, dx, (long long)ld_dx, d_weight, d_bias);
+    KAGNN_LAUNCH_CHECK();
+    return KAGNN_OK;
+}

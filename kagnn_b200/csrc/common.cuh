@@ -55,6 +55,9 @@ int kagnn_rbf_bwd_input_tc(const KagnnKanLayer* layer, const float* x, int64_t l
                            int64_t num_rows, float* dz, int64_t ld_dz, float* dx_base, int64_t ld_dxb, cudaStream_t stream);
 int kagnn_rbf_bwd_weights_tc(const KagnnKanLayer* layer, const float* x, int64_t ldx, const float* ln_stats, const float* dy, int64_t ld_dy,
                              int64_t num_rows, float* d_packed, cudaStream_t stream);
+int kagnn_batchnorm_train_bwd_fast(const float* x, int64_t ldx, const float* dy, int64_t ld_dy, int64_t num_rows, int32_t num_cols,
+                                   const float* weight, float eps, float* dx, int64_t ld_dx, float* d_weight, float* d_bias, double* sums,
+                                   cudaStream_t stream);
 int kagnn_layernorm_bwd_fast(const float* x, int64_t ldx, const float* ln_stats, const float* ln_weight, const float* dz, int64_t ld_dz,
                              const float* dx_base, int64_t ld_dxb, int64_t num_rows, int32_t num_cols, float* dx, int64_t ld_dx,
                              float* d_weight, float* d_bias, cudaStream_t stream);

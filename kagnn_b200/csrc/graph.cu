@@ -670,6 +670,67 @@ extern "C" int kagnn_log_softmax_rows(const float* x, int64_t ldx, int64_t rows,
     return KAGNN_OK;
 }
 
+namespace {
+// The same two passes, tiled: block = a slab of rows x 32 columns, eight row lanes per column (coalesced 128-byte rows, several
+// loads in flight per thread); column sums in fp64, joined through shared memory, one fp64 atomic pair per column and block.
+__global__ void __launch_bounds__(256) bn_stats_tile_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int cols, int64_t rows_per_block,
+                                                            double* __restrict__ sums) {
+    __shared__ double ps[8][33], pq[8][33];
+    const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int c = blockIdx.y * 32 + cl;
+    const int64_t r0 = blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+    double s = 0.0, q = 0.0;
+    if (c < cols) {
+        for (int64_t r = r0 + rl; r < r1; r += 8) {
+            const double v = (double)x[r * ldx + c];
+            s += v;
+            q += v * v;
+        }
+    }
+    ps[rl][cl] = s;
+    pq[rl][cl] = q;
+    __syncthreads();
+    if (rl == 0 && c < cols) {
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            a += ps[k][cl];
+            b += pq[k][cl];
+        }
+        atomicAdd(&sums[c], a);
+        atomicAdd(&sums[cols + c], b);
+    }
+}
+
+// normalise + affine + activation: the per-column constants are formed once per thread (fp64), the rows stream in fp32
+__global__ void __launch_bounds__(256) bn_apply_tile_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int cols,
+                                                            const double* __restrict__ sums, const float* __restrict__ weight,
+                                                            const float* __restrict__ bias, float eps, float momentum,
+                                                            float* __restrict__ running_mean, float* __restrict__ running_var, int act,
+                                                            int64_t rows_per_block, float* __restrict__ y, int64_t ldy) {
+    const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int c = blockIdx.y * 32 + cl;
+    if (c >= cols) return;
+    const double mean_d = sums[c] / (double)rows;
+    const double var = fmax(sums[cols + c] / (double)rows - mean_d * mean_d, 0.0);
+    const float mean = (float)mean_d, inv = (float)(1.0 / sqrt(var + (double)eps));
+    const float w = weight ? weight[c] : 1.0f, b = bias ? bias[c] : 0.0f;
+    const int64_t r0 = blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+    for (int64_t r = r0 + rl; r < r1; r += 8) {
+        float v = (x[r * ldx + c] - mean) * inv;
+        if (weight) v *= w;
+        if (bias) v += b;
+        if (act == KAGNN_ACT_SILU) v = v / (1.0f + expf(-v));
+        y[r * ldy + c] = v;
+    }
+    if (blockIdx.x == 0 && rl == 0 && running_mean && running_var) {
+        const double unbiased = rows > 1 ? var * (double)rows / (double)(rows - 1) : var;
+        running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * mean;
+        running_var[c] = (1.0f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+}
+}  // namespace
+
 extern "C" size_t kagnn_batchnorm_train_workspace(int32_t cols) { return cols > 0 ? (size_t)cols * 2 * sizeof(double) : 0; }
 
 extern "C" int kagnn_batchnorm_train_fwd(const float* x, int64_t ldx, int64_t rows, int32_t cols, const float* weight,
@@ -680,8 +741,17 @@ extern "C" int kagnn_batchnorm_train_fwd(const float* x, int64_t ldx, int64_t ro
     if (!workspace || workspace_bytes < kagnn_batchnorm_train_workspace(cols)) return KAGNN_EWORKSPACE;
     double* sums = static_cast<double*>(workspace);
     KAGNN_CUDA_TRY(cudaMemsetAsync(sums, 0, (size_t)cols * 2 * sizeof(double), stream));
-    const int64_t rows_per_block = 256;
-    bn_stats_kernel<<<(unsigned)ceil_div64(rows, rows_per_block), 128, 0, stream>>>(x, ldx, rows, cols, rows_per_block, sums);
+    const int64_t rows_per_block = 512;
+    const dim3 grid((unsigned)ceil_div64(rows, rows_per_block), (unsigned)((cols + 31) / 32), 1);
+    if (grid.x > 0 && grid.y <= 65535) {
+        bn_stats_tile_kernel<<<grid, 256, 0, stream>>>(x, ldx, rows, cols, rows_per_block, sums);
+        KAGNN_LAUNCH_CHECK();
+        bn_apply_tile_kernel<<<grid, 256, 0, stream>>>(x, ldx, rows, cols, sums, weight, bias, eps, momentum, running_mean, running_var, act,
+                                                       rows_per_block, y, ldy);
+        KAGNN_LAUNCH_CHECK();
+        return KAGNN_OK;
+    }
+    bn_stats_kernel<<<(unsigned)ceil_div64(rows, 256), 128, 0, stream>>>(x, ldx, rows, cols, 256, sums);
     KAGNN_LAUNCH_CHECK();
     bn_apply_kernel<<<(unsigned)ceil_div64(rows * (int64_t)cols, kThreads), kThreads, 0, stream>>>(
         x, ldx, rows, cols, sums, weight, bias, eps, momentum, running_mean, running_var, act, y, ldy);
