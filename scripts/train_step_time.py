@@ -59,6 +59,40 @@ def main():
     c0 = ops.launch_count
     step()
     launches = ops.launch_count - c0
+    # host time to enqueue one step (no synchronisation inside): if it is close to the step time, the step is launch-bound
+    import time
+    torch.cuda.synchronize()
+    hs = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        step()
+        hs.append((time.perf_counter() - t0) * 1e3)
+        torch.cuda.synchronize()
+    host_ms = statistics.median(hs)
+    # the same step as ONE CUDA graph (whole-network capture, Adam(capturable=True)): what the kernels alone take
+    graph_ms, graph_err = None, None
+    try:
+        opt2 = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=True)
+
+        def step2():
+            opt2.zero_grad(set_to_none=True)
+            loss = torch.nn.functional.cross_entropy(model(x, ei), y)
+            loss.backward()
+            opt2.step()
+
+        model.train()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                step2()
+        torch.cuda.current_stream().wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            step2()
+        graph_ms = timed(g.replay)
+    except Exception as exc:  # pragma: no cover
+        graph_err = repr(exc)[:200]
     if len(sys.argv) > 1 and sys.argv[1] == "--kernels":
         # per-kernel device time of one step (torch.profiler / CUPTI), for the notes under profiles/
         from torch.profiler import profile, ProfilerActivity
@@ -76,6 +110,7 @@ def main():
     print(json.dumps({"config": "arxiv-shaped GKAN_Nodes gin 3x64 grid 5, training step (fwd + bwd + Adam), batch-statistics BatchNorm",
                       "nodes": n, "edges": e, "train_step_ms": t_step, "train_mode_forward_ms": t_fwd,
                       "nodes_per_s_training": n / t_step * 1e3, "library_launches_per_step": launches,
+                      "host_enqueue_ms_per_step": host_ms, "train_step_ms_cuda_graph": graph_ms, "cuda_graph_error": graph_err,
                       "loss_first": l0, "loss_after_14_steps": l1,
                       "max_memory_gb": torch.cuda.max_memory_allocated() / 2**30}))
 
