@@ -149,27 +149,37 @@ __host__ __device__ __forceinline__ uint32_t idesc_bf16_f32_mn(int m, int n) { r
 // =====================================================================================================================
 constexpr int kFP = 16;                 // features per pass
 
-template <int K>
-__global__ void __launch_bounds__(kThreads) kan_bwd_input_tc_kernel(GeomB g, const float* __restrict__ w, const float* __restrict__ x,
+// PACKED: B comes from the layer's tensor-core weight packing (kagnn_pack_kan_weights_tc, the forward's operand): a slab of that
+// layout -- N_pad output rows x 16 bytes holding the eight slots of one feature -- read as an MN-major operand IS the unit of
+// eight (feature, slot) rows x out that dX needs, so a pass's weights are one bulk copy (two spline chunks = 16 features) plus
+// two slabs of the group's SiLU chunk, double-buffered under the previous pass; nothing is converted per tile.  T columns:
+// feature i of the pass at [8 i, 8 i + 8), its base product at 128 + i.
+template <int K, bool PACKED>
+__global__ void __launch_bounds__(kThreads) kan_bwd_input_tc_kernel(GeomB g, const float* __restrict__ w, const uint8_t* __restrict__ wtc,
+                                                                    int n_stage, const float* __restrict__ x,
                                                                     long long ldx, const float* __restrict__ dy, long long ld_dy,
                                                                     long long n_rows, int n_tiles, int KK, uint32_t tmem_cols,
                                                                     float* __restrict__ dx, long long ld_dx, float* __restrict__ dxb,
                                                                     long long ld_dxb) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const int S1 = g.S + 1;
+    const int S1 = PACKED ? 9 : g.S + 1;                 // columns per feature in T
     const int Np = kFP * S1;                             // N of one pass
     const int kcs = KK / 8;
-    const uint32_t b_bytes = (uint32_t)kcs * (uint32_t)Np * 16u;     // one of hi / lo
+    const uint32_t b_bytes = (uint32_t)kcs * (uint32_t)Np * 16u;     // one of hi / lo (on-the-fly conversion)
+    const uint32_t stage_bytes = 576u * (uint32_t)KK;                 // PACKED: two spline chunks (512 N_pad) + two base slabs (64 N_pad)
     uint8_t* b_hi = smem;
     uint8_t* b_lo = smem + b_bytes;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(b_lo + b_bytes);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(PACKED ? smem + (size_t)n_stage * stage_bytes : b_lo + b_bytes);
+    uint64_t* full = bar + 1;                            // PACKED: weights of a stage have landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 3);
     const int tid = threadIdx.x, warp = tid >> 5, wg = warp >> 2, r128 = tid & 127;
     const uint32_t a_col = (uint32_t)((Np + 31) & ~31);
 
     if (warp == 0) tc::tmem_alloc(tmem_slot, tmem_cols);
     if (tid == 32) {
         tc::mbar_init(bar, 1);
+        tc::mbar_init(&full[0], 1);
+        tc::mbar_init(&full[1], 1);
         tc::mbar_fence_init();
     }
     tc::tc_fence_before_sync();
@@ -184,6 +194,21 @@ __global__ void __launch_bounds__(kThreads) kan_bwd_input_tc_kernel(GeomB g, con
     const bool dx_vec = (ld_dx % 4 == 0) && ((reinterpret_cast<uintptr_t>(dx) & 15u) == 0);
     const bool dy_vec = g.out_f % 4 == 0 && ld_dy % 4 == 0 && ((reinterpret_cast<uintptr_t>(dy) & 15u) == 0);
     uint32_t phase = 0;
+    // PACKED: running pass counter over all tiles of this CTA -> stage and phase of the weight ring; one thread issues the copies
+    uint32_t qi = 0;
+    const int octs_all = ((g.in_f + 15) / 16) * 2;       // feature octets of the packed layout (F_pad / 8)
+    auto load_pass = [&](int pass, uint32_t q) {
+        const int f0 = pass * kFP, grp = f0 >> 6, j = (f0 & 63) >> 3;
+        const int n_oct = min(8, octs_all - 8 * grp);
+        const uint32_t st = (n_stage > 1) ? (q & 1u) : 0u;
+        uint8_t* dst = smem + (size_t)st * stage_bytes;
+        const uint8_t* chunk = wtc + (size_t)(grp * 9 + j) * 256u * (size_t)KK;
+        const uint8_t* base = wtc + (size_t)(grp * 9 + n_oct) * 256u * (size_t)KK + (size_t)j * 32u * (size_t)KK;
+        tc::mbar_arrive_expect_tx(&full[st], stage_bytes);
+        tc::bulk_g2s(dst, chunk, 512u * (uint32_t)KK, &full[st]);
+        tc::bulk_g2s(dst + 512u * (uint32_t)KK, base, 64u * (uint32_t)KK, &full[st]);
+    };
+    if (PACKED && tid == 0 && blockIdx.x < n_tiles) load_pass(0, 0);
 
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long row = (long long)tile * 128 + r128;
@@ -233,7 +258,7 @@ __global__ void __launch_bounds__(kThreads) kan_bwd_input_tc_kernel(GeomB g, con
             const int f0 = pass * kFP;
             // ---- B = the 16 (S+1) weight rows of the pass (row n = i (S+1) + c <-> P[f0+i][c][.]), split into the canonical
             // K-major layout: slab kc = Np rows x 8 bf16
-            for (int base = tid; base < kcs * Np; base += 4 * kThreads) {     // four items per round: their loads are in flight together
+            for (int base = tid; !PACKED && base < kcs * Np; base += 4 * kThreads) {     // four items per round: their loads are in flight together
                 float4 q[4][2];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -277,7 +302,39 @@ __global__ void __launch_bounds__(kThreads) kan_bwd_input_tc_kernel(GeomB g, con
             tc::fence_proxy_async_smem();
             tc::tc_fence_before_sync();
             __syncthreads();
-            if (tid == 0) {
+            if (tid == 0 && PACKED) {
+                // the next pass's weights (same tile or the CTA's next tile) fly while this pass computes
+                const bool more = (pass + 1 < n_pass) || (tile + (int)gridDim.x < n_tiles);
+                if (n_stage > 1 && more) load_pass(pass + 1 < n_pass ? pass + 1 : 0, qi + 1);
+                const uint32_t st = (n_stage > 1) ? (qi & 1u) : 0u;
+                tc::mbar_wait(&full[st], (n_stage > 1) ? ((qi >> 1) & 1u) : (qi & 1u));
+                tc::tc_fence_after_sync();
+                const uint32_t sb = tc::smem_u32(smem) + st * stage_bytes;
+                const uint32_t sbo = 32u * (uint32_t)KK, lo_off = 16u * (uint32_t)KK;
+                const uint32_t idesc_s = tc::idesc_bf16_f32(128, 128) | (1u << 16), idesc_b = tc::idesc_bf16_f32(128, 16) | (1u << 16);
+                uint32_t acc = 0;
+                for (int ks = 0; ks < KK / 16; ++ks) {
+                    const uint32_t off = (uint32_t)ks * 256u;
+                    const uint64_t dsh = tc::smem_desc(sb + off, 128, sbo), dsl = tc::smem_desc(sb + lo_off + off, 128, sbo);
+                    const uint64_t dbh = tc::smem_desc(sb + 512u * (uint32_t)KK + off, 128, sbo);
+                    const uint64_t dbl = tc::smem_desc(sb + 512u * (uint32_t)KK + lo_off + off, 128, sbo);
+                    const uint32_t tah = tmem_base + a_col + 8u * ks, tal = tah + (uint32_t)KK / 2;
+                    tc::umma_bf16_ts(tmem_base, tah, dsh, idesc_s, acc);
+                    tc::umma_bf16_ts(tmem_base, tah, dsl, idesc_s, 1);
+                    tc::umma_bf16_ts(tmem_base, tal, dsh, idesc_s, 1);
+                    tc::umma_bf16_ts(tmem_base + 128u, tah, dbh, idesc_b, acc);
+                    tc::umma_bf16_ts(tmem_base + 128u, tah, dbl, idesc_b, 1);
+                    tc::umma_bf16_ts(tmem_base + 128u, tal, dbh, idesc_b, 1);
+                    acc = 1;
+                }
+                tc::umma_commit(bar);
+                if (n_stage == 1 && more) {
+                    // single stage (256-wide layers): the next copy may start only when these MMAs have read the stage
+                    tc::mbar_wait(bar, phase);
+                    load_pass(pass + 1 < n_pass ? pass + 1 : 0, qi + 1);
+                }
+            }
+            if (tid == 0 && !PACKED) {
                 tc::tc_fence_after_sync();
                 uint32_t acc = 0;
                 for (int ks = 0; ks < KK / 16; ++ks) {
@@ -291,6 +348,7 @@ __global__ void __launch_bounds__(kThreads) kan_bwd_input_tc_kernel(GeomB g, con
                 }
                 tc::umma_commit(bar);
             }
+            ++qi;
             // this warpgroup's x values of the pass: requested before the wait, so the loads fly while the tensor pipe works
             const float* xr = x + (row_ok ? row : 0) * ldx;
             float xq[8];
@@ -303,7 +361,10 @@ __global__ void __launch_bounds__(kThreads) kan_bwd_input_tc_kernel(GeomB g, con
             phase ^= 1u;
             tc::tc_fence_after_sync();
             // ---- epilogue: warpgroup wg contracts features 8 wg .. 8 wg + 7 of the pass for its 128 rows
-            float res[8], resb[8];
+            float res[8], resb[8], tbase[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) tbase[c] = 0.f;
+            if (PACKED) tc::tmem_ld8(tmem_base + lane_base + 128u + 8u * (uint32_t)wg, tbase);
 #pragma unroll
             for (int ii = 0; ii < 8; ++ii) {
                 const int i = 8 * wg + ii, f = f0 + i;
@@ -311,7 +372,14 @@ __global__ void __launch_bounds__(kThreads) kan_bwd_input_tc_kernel(GeomB g, con
                 resb[ii] = 0.f;
                 if (f < g.in_f) {                       // uniform over the warpgroup
                     float t[16];
-                    {
+                    if (PACKED) {
+                        float t0[8];
+                        tc::tmem_ld8(tmem_base + lane_base + (uint32_t)(8 * i), t0);
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) t[c] = t0[c];
+#pragma unroll
+                        for (int c = 8; c < 16; ++c) t[c] = 0.f;
+                    } else {
                         float t0[8];
                         tc::tmem_ld8(tmem_base + lane_base + (uint32_t)(i * S1), t0);
 #pragma unroll
@@ -363,9 +431,13 @@ __global__ void __launch_bounds__(kThreads) kan_bwd_input_tc_kernel(GeomB g, con
                     const float sg = __fdividef(1.0f, 1.0f + ex2_b(-kLog2eB * xv));
                     const float dbase = sg * fmaf(xv, 1.0f - sg, 1.0f);
                     float tb = 0.f;
+                    if (PACKED) {
+                        tb = tbase[ii];
+                    } else {
 #pragma unroll
-                    for (int c = 0; c < 16; ++c)
-                        if (c == g.S) tb = t[c];
+                        for (int c = 0; c < 16; ++c)
+                            if (c == g.S) tb = t[c];
+                    }
                     if (K == 0 && dxb) {                    // with a LayerNorm the two branches stay separate (kagnn_layernorm_bwd joins them)
                         res[ii] = a;
                         resb[ii] = dbase * tb;
@@ -640,29 +712,35 @@ int geometry_b(const KagnnKanLayer* L, GeomB* g) {
 }
 
 std::atomic<int> g_bwd_path{0};         // 0 = auto (tensor cores first), 1 = fp32 kernels only (tests / comparisons)
+std::atomic<int> g_dx_packed{1};        // dX reads the forward's packed weights (1) or splits the fp32 weights per tile (0; mode 2 below)
 }  // namespace
 
 extern "C" int kagnn_set_backward_path(int32_t mode) {
-    if (mode != 0 && mode != 1) return KAGNN_EINVAL;
-    g_bwd_path.store(mode);
+    if (mode < 0 || mode > 2) return KAGNN_EINVAL;      // 2 = tensor cores, but dX without the packed-weight operand (tests)
+    g_bwd_path.store(mode == 1 ? 1 : 0);
+    g_dx_packed.store(mode == 2 ? 0 : 1);
     return KAGNN_OK;
 }
 
 namespace {
-int launch_bwd_input_tc(const GeomB& g, const float* w, const float* x, int64_t ldx, const float* dy, int64_t ld_dy, int64_t num_rows,
-                        float* dx, int64_t ld_dx, float* dxb, int64_t ld_dxb, cudaStream_t stream) {
-    const int S1 = g.S + 1;
-    if (num_rows < 128 || S1 > kS1MaxB || g.k > kMaxOrderB || g.out_f > 256) return KAGNN_EUNSUPPORTED;   // small batches: not worth a tile
+int launch_bwd_input_tc(const GeomB& g, const float* w, const void* wtc, const float* x, int64_t ldx, const float* dy, int64_t ld_dy,
+                        int64_t num_rows, float* dx, int64_t ld_dx, float* dxb, int64_t ld_dxb, cudaStream_t stream) {
+    if (num_rows < 128 || g.S + 1 > kS1MaxB || g.k > kMaxOrderB || g.out_f > 256) return KAGNN_EUNSUPPORTED;   // small batches: not worth a tile
     DeviceProps props{};
     int rc = kagnn_get_props(&props);
     if (rc != KAGNN_OK) return rc;
     if (props.cc_major != 10) return KAGNN_EUNSUPPORTED;
     const int K = ((g.out_f + 15) / 16) * 16;
+    // the layer's tensor-core packing (the forward's operand) doubles as dX's B operand; without it the weights are split per tile
+    const bool packed = wtc != nullptr && aligned16(wtc) && g_dx_packed.load() != 0;
+    const int S1 = packed ? 9 : g.S + 1;
     const int Np = kFP * S1;
     const uint32_t a_col = (uint32_t)((Np + 31) & ~31);
     if (a_col + (uint32_t)K > 512u) return KAGNN_EUNSUPPORTED;
     const uint32_t cols = tc::tmem_cols_pow2(a_col + (uint32_t)K);
-    const size_t smem = (size_t)2 * (K / 8) * Np * 16 + 64;
+    int n_stage = 2;
+    if (packed && (size_t)2 * 576 * K + 128 > (size_t)props.max_smem) n_stage = 1;
+    const size_t smem = packed ? (size_t)n_stage * 576 * K + 128 : (size_t)2 * (K / 8) * Np * 16 + 128;
     if (smem > (size_t)props.max_smem) return KAGNN_EUNSUPPORTED;
     const int n_tiles = (int)ceil_div64(num_rows, 128);
     // CTAs per SM: limited by tensor-memory columns and shared memory (the kernel overlaps its phases only across CTAs)
@@ -672,10 +750,15 @@ int launch_bwd_input_tc(const GeomB& g, const float* w, const float* x, int64_t 
     if (per_sm > 4) per_sm = 4;
     if (per_sm < 1) per_sm = 1;
     const int grid = n_tiles < props.num_sms * per_sm ? n_tiles : props.num_sms * per_sm;
-    auto kern = g.k == 3 ? kan_bwd_input_tc_kernel<3> : (g.k == 2 ? kan_bwd_input_tc_kernel<2> : (g.k == 1 ? kan_bwd_input_tc_kernel<1> : kan_bwd_input_tc_kernel<0>));
+    void (*kern)(GeomB, const float*, const uint8_t*, int, const float*, long long, const float*, long long, long long, int, int, uint32_t,
+                 float*, long long, float*, long long);
+    if (packed)
+        kern = g.k == 3 ? kan_bwd_input_tc_kernel<3, true> : (g.k == 2 ? kan_bwd_input_tc_kernel<2, true> : (g.k == 1 ? kan_bwd_input_tc_kernel<1, true> : kan_bwd_input_tc_kernel<0, true>));
+    else
+        kern = g.k == 3 ? kan_bwd_input_tc_kernel<3, false> : (g.k == 2 ? kan_bwd_input_tc_kernel<2, false> : (g.k == 1 ? kan_bwd_input_tc_kernel<1, false> : kan_bwd_input_tc_kernel<0, false>));
     KAGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)props.max_smem));
-    kern<<<(unsigned)grid, kThreads, smem, stream>>>(g, w, x, (long long)ldx, dy, (long long)ld_dy, (long long)num_rows, n_tiles, K, cols, dx,
-                                                    (long long)ld_dx, dxb, (long long)ld_dxb);
+    kern<<<(unsigned)grid, kThreads, smem, stream>>>(g, w, static_cast<const uint8_t*>(wtc), n_stage, x, (long long)ldx, dy, (long long)ld_dy,
+                                                    (long long)num_rows, n_tiles, K, cols, dx, (long long)ld_dx, dxb, (long long)ld_dxb);
     KAGNN_LAUNCH_CHECK();
     return KAGNN_OK;
 }
@@ -740,7 +823,7 @@ int kagnn_kan_bwd_input_tc(const KagnnKanLayer* layer, const float* x, int64_t l
     GeomB g;
     const int rc = geometry_b(layer, &g);
     if (rc != KAGNN_OK) return rc;
-    return launch_bwd_input_tc(g, layer->packed_w, x, ldx, dy, ld_dy, num_rows, dx, ld_dx, nullptr, 0, stream);
+    return launch_bwd_input_tc(g, layer->packed_w, layer->packed_w_tc, x, ldx, dy, ld_dy, num_rows, dx, ld_dx, nullptr, 0, stream);
 }
 
 int kagnn_kan_bwd_weights_tc(const KagnnKanLayer* layer, const float* x, int64_t ldx, const float* dy, int64_t ld_dy, int64_t num_rows,
@@ -759,7 +842,8 @@ int kagnn_rbf_bwd_input_tc(const KagnnKanLayer* layer, const float* x, int64_t l
     GeomB g;
     const int rc = geometry_rbf_b(layer, ln_stats, &g);
     if (rc != KAGNN_OK) return rc;
-    return launch_bwd_input_tc(g, layer->packed_w, x, ldx, dy, ld_dy, num_rows, dz, ld_dz, ln_stats ? dx_base : nullptr, ld_dxb, stream);
+    return launch_bwd_input_tc(g, layer->packed_w, layer->packed_w_tc, x, ldx, dy, ld_dy, num_rows, dz, ld_dz, ln_stats ? dx_base : nullptr, ld_dxb,
+                               stream);
 }
 
 int kagnn_rbf_bwd_weights_tc(const KagnnKanLayer* layer, const float* x, int64_t ldx, const float* ln_stats, const float* dy, int64_t ld_dy,
