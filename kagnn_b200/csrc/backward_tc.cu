@@ -695,6 +695,180 @@ __global__ void __launch_bounds__(kThreads) kan_bwd_weights_tc_kernel(GeomB g, c
     if (warp == 0) tc::tmem_dealloc(tmem_base, tmem_cols);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// dW for layers up to 64 outputs wide: the same GEMM on 64-row batches.  A batch needs 48 KB of shared memory instead of 96,
+// so three CTAs share an SM and cover each other's phases (operand production / MMA / wait) better than two.  256 threads =
+// 64 rows x 4 parts; part p expands features p, p + 4, p + 8, (p + 12) of the block's 14 and two or three of dY's 8-column
+// units; the base values go into units 14 / 15 element by element.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(kThreads, 3) kan_bwd_weights_tc64_kernel(GeomB g, const float* __restrict__ x, long long ldx,
+                                                                           const float* __restrict__ dy, long long ld_dy, long long n_rows,
+                                                                           long long rows_per_slab, int N16, uint32_t tmem_cols,
+                                                                           float* __restrict__ dP) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr uint32_t kUnit = 64u * 16u;                    // one unit of 8 M (or N) elements x 64 rows
+    constexpr uint32_t kABytes = 16u * kUnit;
+    const int nu = N16 / 8;                                  // <= 8
+    const uint32_t b_bytes = (uint32_t)nu * kUnit;
+    uint8_t* a_hi = smem;
+    uint8_t* a_lo = a_hi + kABytes;
+    uint8_t* b_hi = a_lo + kABytes;
+    uint8_t* b_lo = b_hi + b_bytes;
+    uint4* lut = reinterpret_cast<uint4*>(b_lo + b_bytes);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(lut + kLutRows);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, r64 = tid & 63, part = tid >> 6;
+    const int f0 = blockIdx.x * kFB;
+    const long long r_beg = (long long)blockIdx.y * rows_per_slab, r_end = min(n_rows, r_beg + rows_per_slab);
+
+    if (warp == 0) tc::tmem_alloc(tmem_slot, tmem_cols);
+    if (tid == 32) {
+        tc::mbar_init(bar, 1);
+        tc::mbar_fence_init();
+    }
+    if (K > 0 && tid >= 64 && tid < 64 + kLutRows) lut[tid - 64] = lut_row_b(tid - 64, K, g.G + 2 * K);
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t idesc = idesc_bf16_f32_mn(128, N16);
+    uint32_t phase = 0, acc = 0;
+    // dY units of this part: parts 2 and 3 expand three features and take three units each (of eight), parts 0 and 1 four features
+    // and one unit each: unit u belongs to part kUnitPart[u]
+    const int my_units = (part >= 2) ? 3 : 1;
+
+    float xq[4];
+    float4 dq[3][2];
+    auto unit_of = [&](int q) { return part >= 2 ? (part - 2) + 2 * q : 6 + part; };      // parts 2,3: units 0..5 interleaved; parts 0,1: units 6,7
+    auto load_tile = [&](long long rt_) {
+        const long long row = rt_ + r64;
+        const bool row_ok = row < r_end;
+        const float* xr = x + (row_ok ? row : 0) * ldx;
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) {
+            const int i = part + 4 * ii;
+            xq[ii] = (row_ok && i < kFB && (f0 + i) < g.in_f) ? __ldg(xr + f0 + i) : 0.f;
+        }
+        const float* dyr = dy + (row_ok ? row : 0) * ld_dy;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const int u = unit_of(q);
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            const bool on = row_ok && q < my_units && u < nu;
+            dq[q][0] = (on && 8 * u + 4 <= g.out_f) ? __ldg(reinterpret_cast<const float4*>(dyr + 8 * u)) : z;
+            dq[q][1] = (on && 8 * u + 8 <= g.out_f) ? __ldg(reinterpret_cast<const float4*>(dyr + 8 * u + 4)) : z;
+        }
+    };
+    if (r_beg < r_end) load_tile(r_beg);
+    for (long long rt = r_beg; rt < r_end; rt += 64) {
+        const long long row = rt + r64;
+        const bool row_ok = row < r_end;
+        float mean = 0.f, rstd = 1.f;
+        if (K == 0 && g.stats && row_ok) {
+            mean = __ldg(g.stats + 2 * row);
+            rstd = __ldg(g.stats + 2 * row + 1);
+        }
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) {
+            const int i = part + 4 * ii;
+            if (i < kFB) {                                  // uniform over the part (two warps)
+                const bool on = row_ok && (f0 + i) < g.in_f;
+                const float xv = xq[ii];
+                uint4 hi, lo;
+                if (K == 0) {
+                    const float z = rbf_z_b(g, xv, mean, rstd, f0 + i);
+                    float e[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float tt = (z - (g.c0 + (float)q * g.step)) * g.inv_den;
+                        e[q] = (on && q < g.S) ? ex2_b(-kLog2eB * tt * tt) : 0.f;
+                    }
+                    tc::split8(e, hi, lo);
+                } else {
+                    int idx;
+                    float fr, b[4];
+                    locate_b(g, xv, idx, fr);
+                    local_values_b<(K == 0 ? 1 : K)>(fr, b);
+                    const uint32_t h01 = pack_trunc_b(b[0], b[1]), h23 = pack_trunc_b(b[2], b[3]);
+                    const uint32_t l01 = pack_rn_b(trunc_res_b(b[0]), trunc_res_b(b[1])), l23 = pack_rn_b(trunc_res_b(b[2]), trunc_res_b(b[3]));
+                    uint4 sel = lut[idx];
+                    if (!on) sel = make_uint4(0x9999u, 0x9999u, 0x9999u, 0x9999u);
+                    hi = make_uint4(prmt_b(h01, h23, sel.x), prmt_b(h01, h23, sel.y), prmt_b(h01, h23, sel.z), prmt_b(h01, h23, sel.w));
+                    lo = make_uint4(prmt_b(l01, l23, sel.x), prmt_b(l01, l23, sel.y), prmt_b(l01, l23, sel.z), prmt_b(l01, l23, sel.w));
+                }
+                *reinterpret_cast<uint4*>(a_hi + (size_t)i * kUnit + r64 * 16) = hi;
+                *reinterpret_cast<uint4*>(a_lo + (size_t)i * kUnit + r64 * 16) = lo;
+                // base value: element (i & 7) of unit 14 + (i >> 3), as bf16 hi (truncated) / lo (rounded residual)
+                const float sv = on ? __fdividef(xv, 1.0f + ex2_b(-kLog2eB * xv)) : 0.f;
+                const uint32_t off = (uint32_t)(kFB + (i >> 3)) * kUnit + (uint32_t)r64 * 16u + (uint32_t)(i & 7) * 2u;
+                *reinterpret_cast<uint16_t*>(a_hi + off) = (uint16_t)(__float_as_uint(sv) >> 16);
+                *reinterpret_cast<uint16_t*>(a_lo + off) = (uint16_t)(pack_rn_b(trunc_res_b(sv), 0.f) & 0xffffu);
+            }
+        }
+        if (part < 2) {                                      // the two pad elements (features 14, 15) of unit 15: zero, once per tile by one part each
+            const uint32_t off = (uint32_t)(kFB + 1) * kUnit + (uint32_t)r64 * 16u + (uint32_t)(6 + part) * 2u;
+            *reinterpret_cast<uint16_t*>(a_hi + off) = 0;
+            *reinterpret_cast<uint16_t*>(a_lo + off) = 0;
+        }
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const int u = unit_of(q);
+            if (q < my_units && u < nu) {
+                const float v[8] = {dq[q][0].x, dq[q][0].y, dq[q][0].z, dq[q][0].w, dq[q][1].x, dq[q][1].y, dq[q][1].z, dq[q][1].w};
+                uint4 hi, lo;
+                tc::split8(v, hi, lo);
+                *reinterpret_cast<uint4*>(b_hi + (size_t)u * kUnit + r64 * 16) = hi;
+                *reinterpret_cast<uint4*>(b_lo + (size_t)u * kUnit + r64 * 16) = lo;
+            }
+        }
+        tc::fence_proxy_async_smem();
+        tc::tc_fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            tc::tc_fence_after_sync();
+            for (int ks = 0; ks < 4; ++ks) {            // K = 16 rows per step: two groups of 8 k-rows, 256 bytes
+                const uint32_t off = (uint32_t)ks * 256u;
+                const uint64_t dah = tc::smem_desc(tc::smem_u32(a_hi) + off, 128, kUnit), dal = tc::smem_desc(tc::smem_u32(a_lo) + off, 128, kUnit);
+                const uint64_t dbh = tc::smem_desc(tc::smem_u32(b_hi) + off, 128, kUnit), dbl = tc::smem_desc(tc::smem_u32(b_lo) + off, 128, kUnit);
+                tc::umma_bf16(tmem_base, dah, dbh, idesc, acc);
+                tc::umma_bf16(tmem_base, dah, dbl, idesc, 1);
+                tc::umma_bf16(tmem_base, dal, dbh, idesc, 1);
+                acc = 1;
+            }
+            tc::umma_commit(bar);
+        }
+        if (rt + 64 < r_end) load_tile(rt + 64);        // in flight while the tensor pipe works
+        tc::mbar_wait(bar, phase);                      // the operands in shared memory may be overwritten
+        phase ^= 1u;
+    }
+    // ---- the slab's sums: lane m of tensor memory = row m of the block's 128 gradient rows; the two halves of the CTA split the columns
+    tc::tc_fence_after_sync();
+    if (r_beg < r_end) {
+        const int m = tid & 127, u = m >> 3, c = m & 7, half = tid >> 7;
+        long long dst = -1;
+        if (u < kFB) {
+            if (f0 + u < g.in_f && c < g.S) dst = ((long long)(f0 + u) * (g.S + 1) + c) * g.out_pad;
+        } else {
+            const int i = (u - kFB) * 8 + c;
+            if (i < kFB && f0 + i < g.in_f) dst = ((long long)(f0 + i) * (g.S + 1) + g.S) * g.out_pad;
+        }
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        for (int o0 = 8 * half; o0 < N16; o0 += 16) {
+            float v[8];
+            tc::tmem_ld8(tmem_base + lane_base + (uint32_t)o0, v);   // warp-collective: every lane takes part
+            if (dst >= 0) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (o0 + q < g.out_f && v[q] != 0.f) atomicAdd(dP + dst + o0 + q, v[q]);
+            }
+        }
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base, tmem_cols);
+}
+
 int geometry_b(const KagnnKanLayer* L, GeomB* g) {
     if (!L || !L->packed_w || L->basis != KAGNN_BASIS_BSPLINE) return KAGNN_EUNSUPPORTED;
     if (L->in_features <= 0 || L->out_features <= 0 || L->grid_size < 1 || L->spline_order < 1 || L->spline_order > 4) return KAGNN_EUNSUPPORTED;
@@ -712,6 +886,7 @@ int geometry_b(const KagnnKanLayer* L, GeomB* g) {
 }
 
 std::atomic<int> g_bwd_path{0};         // 0 = auto (tensor cores first), 1 = fp32 kernels only (tests / comparisons)
+std::atomic<int> g_dw_rows64{1};        // dW of layers <= 64 wide on 64-row batches (1) or on the general 128-row kernel (0; mode 2 below)
 std::atomic<int> g_dx_packed{1};        // dX reads the forward's packed weights (1) or splits the fp32 weights per tile (0; mode 2 below)
 }  // namespace
 
@@ -719,6 +894,7 @@ extern "C" int kagnn_set_backward_path(int32_t mode) {
     if (mode < 0 || mode > 2) return KAGNN_EINVAL;      // 2 = tensor cores, but dX without the packed-weight operand (tests)
     g_bwd_path.store(mode == 1 ? 1 : 0);
     g_dx_packed.store(mode == 2 ? 0 : 1);
+    g_dw_rows64.store(mode == 2 ? 0 : 1);
     return KAGNN_OK;
 }
 
@@ -787,6 +963,23 @@ int launch_bwd_weights_tc(const GeomB& g, const float* x, int64_t ldx, const flo
 #ifdef KAGNN_DEBUG_KNOBS
     if (const char* e = getenv("KAGNN_DEBUG_DW_SWAP")) swap = atoi(e);
 #endif
+    const bool dy_vec = g.out_f % 4 == 0 && ld_dy % 4 == 0 && aligned16(dy);
+    if (N16 <= 64 && dy_vec && g_dw_rows64.load() != 0) {
+        // narrow layers: 64-row batches, three CTAs per SM
+        const size_t smem64 = (size_t)2 * 16 * 1024 + (size_t)2 * (N16 / 8) * 1024 + kLutRows * 16 + 64;
+        int64_t slabs64 = ceil_div64((int64_t)props.num_sms * 6, fblocks);
+        if (slabs64 > ceil_div64(num_rows, 64)) slabs64 = ceil_div64(num_rows, 64);
+        if (slabs64 > 65535) slabs64 = 65535;
+        if (slabs64 < 1) slabs64 = 1;
+        int64_t rps = ceil_div64(ceil_div64(num_rows, slabs64), 64) * 64;
+        slabs64 = ceil_div64(num_rows, rps);
+        auto k64 = g.k == 3 ? kan_bwd_weights_tc64_kernel<3> : (g.k == 2 ? kan_bwd_weights_tc64_kernel<2> : (g.k == 1 ? kan_bwd_weights_tc64_kernel<1> : kan_bwd_weights_tc64_kernel<0>));
+        KAGNN_CUDA_TRY(cudaFuncSetAttribute(k64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)props.max_smem));
+        k64<<<dim3((unsigned)fblocks, (unsigned)slabs64, 1), kThreads, smem64, stream>>>(g, x, (long long)ldx, dy, (long long)ld_dy, (long long)num_rows,
+                                                                                         (long long)rps, N16, cols, d_packed);
+        KAGNN_LAUNCH_CHECK();
+        return KAGNN_OK;
+    }
     auto kern = g.k == 3 ? kan_bwd_weights_tc_kernel<3> : (g.k == 2 ? kan_bwd_weights_tc_kernel<2> : (g.k == 1 ? kan_bwd_weights_tc_kernel<1> : kan_bwd_weights_tc_kernel<0>));
     KAGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)props.max_smem));
     kern<<<dim3((unsigned)fblocks, (unsigned)slabs, 1), kThreads, smem, stream>>>(
