@@ -1,26 +1,33 @@
-// kagnn_fused_layer_fwd -- pipelined tensor-core path for B-spline KAN chains (tcgen05, A operand in TMEM), sm_100a.
+// kagnn_fused_layer_fwd -- pipelined tensor-core path for KAN chains (tcgen05, A operand in TMEM), sm_100a.
 //
 // Same contract as fused_fp32.cu / fused_tc.cu (tile = aggregate(x) -> pre-affine -> KAN chain -> post-affine -> y, one
 // persistent launch per GNN layer), restructured so that the three resources of the layer run concurrently:
 //
-//   gather warps   (8)  CSR gather-sum of the NEXT 128-row tile, one "unit" (128 rows x 64/128 feature columns) at a
-//                       time into a shared-memory ring: row pointers and column indices are fetched once per warp
-//                       (16 rows) and the neighbour rows of those 16 rows are streamed as ONE flattened list with 8
-//                       independent 128-bit loads in flight per warp -- L2/HBM latency is paid once per batch, not once
-//                       per row, and is hidden behind the basis producers of the current tile;
-//   producer warps (8)  thread = row.  For every 8 input features the closed-form uniform cubic (or order 1/2) B-spline
-//                       basis (node_classification_clean/ekan.py:79-112 restricted to its k+1 non-zeros), split into
-//                       bf16 hi + lo, is placed into the 8 coefficient slots of the feature with one byte-permute per
-//                       32-bit word (selectors from a 12-row shared LUT indexed by the knot interval) and written with
-//                       tcgen05.st straight into TENSOR MEMORY, which tcgen05.mma reads as its A operand: the expanded
+//   gather warps   (8 | 16)  CSR gather-sum of the NEXT 128-row tile, one "unit" (128 rows x 64/128 feature columns) at a
+//                       time into a shared-memory ring: row pointers and column indices are fetched once per warp and the
+//                       neighbour rows of its rows are streamed as ONE flattened list with 8 independent 128-bit loads in
+//                       flight per warp (units of at most 64 columns: two source rows per load) -- L2/HBM latency is paid
+//                       once per batch, not once per row, and is hidden behind the basis producers of the current tile;
+//   producer warps (16 | 8)  thread = row, two teams taking alternate chunks.  For every 8 input features the closed-form
+//                       uniform B-spline basis (node_classification_clean/ekan.py:79-112 restricted to its k+1
+//                       non-zeros; FastKAN: the eight Gaussians of fastkan.py:46-47), split into bf16 hi + lo, is
+//                       placed into the 8 coefficient slots of the feature with one byte-permute per 32-bit word
+//                       (selectors from a 13-row shared LUT indexed by the knot interval) and written with tcgen05.st
+//                       straight into TENSOR MEMORY, which tcgen05.mma reads as its A operand: the expanded
 //                       (N, in, G+k) tensor of the reference exists neither in HBM nor in shared memory;
-//   MMA warp       (1)  one thread issues, per K = 16 step, A_hi.W_hi + A_hi.W_lo + A_lo.W_hi (bf16 x bf16 -> fp32 in
-//                       TMEM; error ~2^-17, inside BASELINE.json's 1e-4);  W chunks arrive by bulk TMA (loader warp);
+//   MMA warp       (1)  one elected lane issues, per K = 16 step, the products of the bf16 hi / lo split (fp32 accumulate in
+//                       TMEM; error ~2^-17, inside BASELINE.json's 1e-4; bf16 mode: one product);  W chunks arrive by
+//                       bulk TMA (loader warp);
+//   push warps     (2, `PUSH` instantiation)  node-sharded graphs: relay finished output tiles to the peers' replicas;
 //   chained KAN layers read their input rows back from the TMEM accumulator of the previous layer (two accumulator
 //   regions, alternated per layer across tiles so the epilogue of tile t overlaps the first MMAs of tile t+1).
+// The warp split is a compile-time choice: this file is built twice (fused_tc2_g16.cu: 8 producer + 16 gather warps for
+// launches that gather over a CSR; here 16 + 8 for the others), see the note above KAGNN_TC2_ENTRY.
 //
-// Supported here: B-spline layers with one common spline_order k <= 3, G + k <= 8, every width of the chain <= 128
-// outputs.  Anything else returns KAGNN_EUNSUPPORTED and the dispatcher falls back to fused_tc.cu / fused_fp32.cu.
+// Supported here: B-spline layers with one common spline_order k <= 3 and G + k <= 8, or FastKAN layers with at most 8
+// centres; chains of layers up to 128 outputs wide, single layers up to 256; split-K over the input features for launches
+// with few tiles and long rows.  Anything else returns KAGNN_EUNSUPPORTED and the dispatcher falls back to fused_tc.cu /
+// fused_fp32.cu.
 #include "common.cuh"
 #include "stage.cuh"
 #include "tc_common.cuh"

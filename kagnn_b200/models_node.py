@@ -9,9 +9,13 @@ Execution plan in eval mode (BatchNorm folded to an affine, dropout is the ident
   shifted half a layer: launch 0 = KAN_1(x); launch l = [aggregate(A_hat, t_l) + b_l -> BN_l -> store h_l into the
   concat buffer -> KAN_{l+1}(h_l)]; the last launch has no KAN; then ``lay_out``.
 
-In training mode (batch-statistics BatchNorm, dropout) each conv still runs fused; BatchNorm runs as its own launches
-(``ops.batchnorm_forward``) and dropout, being random, stays ``nn.Dropout`` between launches (SURVEY.md section 8f rank 2 is
-the fused training epilogue with a Philox mask)."""
+* ``conv_type='gat'``: projection (KAN launch) -> attention coefficients -> one weighted aggregation per head with bias +
+  BatchNorm folded into it.
+
+In training mode every conv is a chain of ``autograd.Function``s whose forward and backward are library launches, and
+``dropout(bn(x))`` is one fused training epilogue (batch statistics + affine + Philox mask, regenerated in the backward:
+``autograd.batch_norm_dropout_train``).  Eval-mode forwards of small graphs on unchanged inputs are replayed from a CUDA graph
+(``_GraphReplay``)."""
 from __future__ import annotations
 
 import os
