@@ -166,13 +166,50 @@ def main_gine() -> None:
               sd0, y, grads)
 
 
+def main_gat() -> None:
+    """GAT flavour (node and graph-classification models of the reference, GATConv from oracle/pyg_shim.py), own seed."""
+    from . import pyg_shim
+    pyg_shim.install()
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(2024)
+    gen = torch.Generator().manual_seed(2024)
+    ncm = _load(os.path.join(NC, "models.py"), "ref_nc_models_gat_grad")
+    n, e, f, c = 60, 200, 13, 4
+    ei = small_graph(n, e, gen)
+    x = torch.randn(n, f, generator=gen) * 0.7
+    m = ncm.GKAN_Nodes("gat", 2, f, 8, c, skip=True, grid_size=5, spline_order=3, dropout=0.0, heads=3).train()
+    _randomise(m, gen)
+    sd0, y, dy, grads = _backprop(m, lambda t: m(t, ei), x, gen)
+    _save("grad_nc_gkan_gat", dict(kind="node", conv_type="gat", skip=True, fast=False, training=True, mp_layers=2, num_features=f, hidden=8,
+          classes=c, G=5, k=3, hidden_layers=2, heads=3), dict(x=x, edge_index=ei, dy=dy), sd0, y, grads)
+    m = ncm.GFASTKAN_Nodes("gat", 2, f, 6, c, skip=True, grid_size=6, dropout=0.0, heads=2).train()
+    _randomise(m, gen)
+    sd0, y, dy, grads = _backprop(m, lambda t: m(t, ei), x, gen)
+    _save("grad_nc_gfastkan_gat", dict(kind="node", conv_type="gat", skip=True, fast=True, training=True, mp_layers=2, num_features=f,
+          hidden=6, classes=c, G=6, hidden_layers=2, heads=2), dict(x=x, edge_index=ei, dy=dy), sd0, y, grads)
+    gcm = _load(os.path.join(GC, "models.py"), "ref_gc_models_gat_grad")
+    ei, batch, n = batched_graphs(8, gen)
+    x = torch.randn(n, 7, generator=gen)
+    for name, mk, meta in [
+        ("grad_gc_kagat", lambda: gcm.KAGAT(2, 7, 8, 3, 4, 3, 0.0, 2), dict(family="KAGAT", args=[2, 7, 8, 3, 4, 3, 0.0, 2])),
+        ("grad_gc_fastkagat", lambda: gcm.FASTKAGAT(2, 7, 6, 2, 5, 0.0, 2), dict(family="FASTKAGAT", args=[2, 7, 6, 2, 5, 0.0, 2])),
+    ]:
+        m = mk().train()
+        _randomise(m, gen)
+        sd0, y, dy, grads = _backprop(m, lambda t: m(K.Batch(t, ei, batch)), x, gen)
+        _save(name, dict(kind="gc", training=True, **meta), dict(x=x, edge_index=ei, batch=batch, dy=dy), sd0, y, grads)
+
+
 if __name__ == "__main__":
     import sys
     if "--gine-only" in sys.argv:
         main_gine()
     elif "--fastkan-only" in sys.argv:
         main_fastkan()
+    elif "--gat-only" in sys.argv:
+        main_gat()
     else:
         main()
         main_fastkan()
         main_gine()
+        main_gat()

@@ -98,6 +98,29 @@ def _gat_attention(h, csr, att_src, att_dst, heads, negative_slope=0.2):
     return (ex / den[row]).t().contiguous(), (xs / den).t().contiguous()
 
 
+def _gat_backward(h, csr, dout, att_src, att_dst, w, sw, heads, negative_slope, dh):
+    # stand-in of ops.gat_backward (kagnn_gat_bwd): dh holds sum_i alpha_ij d out[i] on entry and gets the part through the
+    # attention scores added; returns (d att_src, d att_dst), each (heads * C,)
+    n = h.size(0)
+    c = h.size(1) // heads
+    hv, dv = h.view(n, heads, c), dout.view(n, heads, c)
+    a_src = att_src.detach().view(1, heads, c)
+    a_dst = att_dst.detach().view(1, heads, c)
+    a_s, a_d = (hv * a_src).sum(-1), (hv * a_dst).sum(-1)
+    row, col = _row_of_entry(csr), csr.col.long()
+    al, al_self = w.t(), sw.t()                                                  # (nnz, H), (n, H)
+    g_e = (dv[row] * hv[col]).sum(-1)
+    g_s = (dv * hv).sum(-1)
+    s = al_self * g_s + torch.zeros(n, heads).index_add_(0, row, al * g_e)
+    slope = lambda pre: torch.where(pre > 0, torch.ones_like(pre), torch.full_like(pre, negative_slope))  # noqa: E731
+    dpre = al * (g_e - s[row]) * slope(a_s[col] + a_d[row])                     # removed self loops carry alpha = 0
+    dpre_self = al_self * (g_s - s) * slope(a_s + a_d)
+    da_dst = dpre_self + torch.zeros(n, heads).index_add_(0, row, dpre)
+    da_src = dpre_self + torch.zeros(n, heads).index_add_(0, col, dpre)
+    dh.add_((da_src.unsqueeze(-1) * a_src + da_dst.unsqueeze(-1) * a_dst).reshape(n, heads * c))
+    return (da_src.unsqueeze(-1) * hv).sum(0).reshape(-1), (da_dst.unsqueeze(-1) * hv).sum(0).reshape(-1)
+
+
 def _gather_rows(x, index, out=None, num_rows=None):
     res = x[index.long()] if index is not None else x[: (x.size(0) if num_rows is None else num_rows)]
     if out is None:
@@ -228,7 +251,7 @@ def cpu_double():
     for name, fn in (("csr_build", _csr_build), ("gcn_norm", _gcn_norm), ("gcn_degree", _gcn_degree), ("gcn_edge_weight", _gcn_edge_weight), ("gather_rows", _gather_rows), ("segment_ptr", _segment_ptr),
                      ("pack_kan_weights", _pack), ("fused_layer", _fused_layer), ("batchnorm_forward", _batchnorm_forward),
                      ("log_softmax", lambda x: torch.log_softmax(x, dim=1)), ("layernorm_stats", _layernorm_stats),
-                     ("gat_attention", _gat_attention)):
+                     ("gat_attention", _gat_attention), ("gat_backward", _gat_backward)):
         patch(ops, name, fn)
     for mod in (ekan, fastkan, conv, models_node, models_graph, models_regr):
         patch(mod, "_module_backend_guard", guard)
