@@ -869,6 +869,315 @@ __global__ void __launch_bounds__(kThreads, 3) kan_bwd_weights_tc64_kernel(GeomB
     if (warp == 0) tc::tmem_dealloc(tmem_base, tmem_cols);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// dW for layers up to 64 outputs wide, several feature blocks per CTA.  One CTA per SM: 16 producer warps, 1 control warp,
+// 4 loader warps.
+//   * the hi / lo split of a dY batch (64 rows) is made ONCE and serves up to eight feature blocks, each with its own
+//     accumulator in tensor memory (8 x 64 columns = all 512);
+//   * producers: 512 threads = 64 rows x 8 parts; part p expands features p and p + 8 of a block's 14 (and one of dY's eight
+//     units at the head of a batch) into a ring of three E^T operands; they only ARRIVE at the named barrier of the stage and
+//     go on -- the mbarrier of the stage three blocks later is the only thing that can stop them;
+//   * the control warp waits on that named barrier, issues the block's 12 MMAs and commits to the stage's mbarrier;
+//   * the loader warps keep the next batch's x and dY rows coming: 16-byte cp.async copies (zero-filled outside the matrix) into
+//     double-buffered, padded staging tiles, completion on an mbarrier: no producer ever waits on a global load;
+//   * the dY operand is double-buffered too, so a batch does not wait for the previous batch's MMAs;
+//   * the slab's sums leave as 16-byte vector reductions, each CTA starting at a different column.
+// grid = (passes of up to 8 feature blocks, row slabs).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kMBlocks = 8;
+constexpr int kMProducers = 512;
+constexpr int kMSync = kMProducers + 32;                     // producers + the control warp: the named barriers of the operand ring
+constexpr int kMLoaders = 128;
+constexpr int kMThreads = kMSync + kMLoaders;
+constexpr int kMStages = 3;
+constexpr int kMXld = kMBlocks * kFB + 4;                    // staged x row: up to 112 values + 2 of alignment slack, 16-byte rows
+constexpr int kMDld = 64 + 4;                                // staged dY row
+
+template <int ID, int COUNT>
+__device__ __forceinline__ void named_arrive() { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(COUNT) : "memory"); }
+template <int ID, int COUNT>
+__device__ __forceinline__ void named_sync() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory"); }
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, bool on) {
+    const uint32_t n = on ? 16u : 0u;                        // src-size 0: the destination is zero-filled, nothing is read
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tc::smem_u32(dst_smem)), "l"(src), "r"(n) : "memory");
+}
+// the mbarrier gets one arrival from this thread once all its earlier cp.async copies have landed
+__device__ __forceinline__ void cp_async_arrive_on(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+struct DwSmem {                                              // carve-up of the dynamic shared memory (offsets in bytes)
+    uint32_t a, b, xs, ds, lut, bars, total;
+};
+__host__ __device__ inline DwSmem dw_smem_layout(int N16) {
+    DwSmem L;
+    const uint32_t unit = 64u * 16u;
+    L.a = 0;
+    L.b = L.a + (uint32_t)kMStages * 2u * 16u * unit;        // [stage][hi | lo]
+    L.xs = L.b + 2u * 2u * (uint32_t)(N16 / 8) * unit;       // [buffer][hi | lo]
+    L.ds = L.xs + 2u * 64u * (uint32_t)kMXld * 4u;
+    L.lut = L.ds + 2u * 64u * (uint32_t)kMDld * 4u;
+    L.bars = L.lut + (uint32_t)kLutRows * 16u;
+    L.total = L.bars + 160u;
+    return L;
+}
+
+template <int K>
+__global__ void __launch_bounds__(kMThreads, 1) kan_bwd_weights_tc64m_kernel(GeomB g, const float* __restrict__ x, long long ldx,
+                                                                             const float* __restrict__ dy, long long ld_dy, long long n_rows,
+                                                                             long long rows_per_slab, int N16, int fblocks,
+                                                                             int blocks_per_pass, uint32_t tmem_cols, float* __restrict__ dP) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr uint32_t kUnit = 64u * 16u;                    // one unit of 8 M (or N) elements x 64 rows
+    constexpr uint32_t kAStage = 2u * 16u * kUnit;           // hi + lo of one E^T operand
+    const DwSmem L = dw_smem_layout(N16);
+    const int nu = N16 / 8;                                  // <= 8
+    const uint32_t b_bytes = (uint32_t)nu * kUnit;
+    uint8_t* a_st = smem + L.a;
+    uint8_t* b_st = smem + L.b;
+    float* x_st = reinterpret_cast<float*>(smem + L.xs);
+    float* d_st = reinterpret_cast<float*>(smem + L.ds);
+    uint4* lut = reinterpret_cast<uint4*>(smem + L.lut);
+    uint64_t* bar_stage = reinterpret_cast<uint64_t*>(smem + L.bars);        // [3]: the MMAs that read A stage s are done
+    uint64_t* bar_batch = bar_stage + kMStages;                              // [2]: all MMAs of a batch are done (its B buffer is free)
+    uint64_t* bar_in = bar_batch + 2;                                        // [2]: x and dY rows of a batch have landed
+    uint64_t* bar_free = bar_in + 2;                                         // [2]: every producer is done with a staging buffer
+    uint64_t* bar_done = bar_free + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_done + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool control = warp == kMProducers / 32, loader = tid >= kMSync;
+    const int fb0 = blockIdx.x * blocks_per_pass, nb = min(blocks_per_pass, fblocks - fb0);
+    const long long r_beg = (long long)blockIdx.y * rows_per_slab, r_end = min(n_rows, r_beg + rows_per_slab);
+    // staged x columns [xc0, xc0 + xcols): the pass's features, widened to 16-byte boundaries (in_f is a multiple of 4 here)
+    const int xc0 = (fb0 * kFB) & ~3, xoff = fb0 * kFB - xc0;
+    const int xcols = min((xoff + nb * kFB + 3) & ~3, g.in_f - xc0);
+
+    if (control) {
+        tc::tmem_alloc(tmem_slot, tmem_cols);
+        if (lane == 0) {
+            for (int i = 0; i < kMStages + 2; ++i) tc::mbar_init(&bar_stage[i], 1);
+            tc::mbar_init(&bar_in[0], kMLoaders);
+            tc::mbar_init(&bar_in[1], kMLoaders);
+            tc::mbar_init(&bar_free[0], 1);
+            tc::mbar_init(&bar_free[1], 1);
+            tc::mbar_init(bar_done, 1);
+            tc::mbar_fence_init();
+        }
+    }
+    if (K > 0 && tid < kLutRows) lut[tid] = lut_row_b(tid, K, g.G + 2 * K);
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (control) {
+        // ================================================== control warp ==================================================
+        const uint32_t idesc = idesc_bf16_f32_mn(128, N16);
+        // descriptors of stage 0 / buffer 0; the others are a constant 16-byte-unit offset away (the address field is the low 14 bits)
+        const uint64_t dah0 = tc::smem_desc(tc::smem_u32(a_st), 128, kUnit), dal0 = tc::smem_desc(tc::smem_u32(a_st + 16u * kUnit), 128, kUnit);
+        const uint64_t dbh0 = tc::smem_desc(tc::smem_u32(b_st), 128, kUnit), dbl0 = tc::smem_desc(tc::smem_u32(b_st + b_bytes), 128, kUnit);
+        int st = 0, bbuf = 0;
+        long long t = 0;
+        for (long long rt = r_beg; rt < r_end; rt += 64, ++t, bbuf ^= 1) {
+            for (int b = 0; b < nb; ++b) {
+                if (st == 0) named_sync<1, kMSync>();
+                else if (st == 1) named_sync<2, kMSync>();
+                else named_sync<3, kMSync>();
+                if (lane == 0) {
+                    tc::tc_fence_after_sync();
+                    const uint32_t d_col = tmem_base + (uint32_t)(b * N16);
+                    const uint64_t a_off = (uint64_t)((uint32_t)st * (kAStage >> 4)), b_off = (uint64_t)((uint32_t)bbuf * ((2u * b_bytes) >> 4));
+                    uint32_t acc = t == 0 ? 0u : 1u;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {        // K = 16 rows per step: two groups of 8 k-rows, 256 bytes
+                        const uint64_t ko = (uint64_t)(ks * 16);
+                        tc::umma_bf16(d_col, dah0 + a_off + ko, dbh0 + b_off + ko, idesc, acc);
+                        tc::umma_bf16(d_col, dah0 + a_off + ko, dbl0 + b_off + ko, idesc, 1);
+                        tc::umma_bf16(d_col, dal0 + a_off + ko, dbh0 + b_off + ko, idesc, 1);
+                        acc = 1;
+                    }
+                    tc::umma_commit(&bar_stage[st]);
+                    if (b == nb - 1) {
+                        tc::umma_commit(&bar_batch[bbuf]);
+                        tc::mbar_arrive(&bar_free[bbuf]);    // every producer is past this batch's last read of the staging tiles
+                    }
+                }
+                __syncwarp();
+                st = st == kMStages - 1 ? 0 : st + 1;
+            }
+        }
+        if (lane == 0) tc::umma_commit(bar_done);
+        __syncwarp();
+    } else if (loader) {
+        // ===================================================== loaders =====================================================
+        const int lt = tid - kMSync;
+        const int xc4 = xcols >> 2, dc4 = g.out_f >> 2;
+        const int xq = kMLoaders / xc4, xr = kMLoaders - xq * xc4, dq = kMLoaders / dc4, dr = kMLoaders - dq * dc4;
+        long long t = 0;
+        for (long long rt = r_beg; rt < r_end; rt += 64, ++t) {
+            const int buf = (int)(t & 1);
+            if (t >= 2) tc::mbar_wait(&bar_free[buf], (uint32_t)((t >> 1) - 1) & 1u);
+            float* xs = x_st + (size_t)buf * 64 * kMXld;
+            float* ds = d_st + (size_t)buf * 64 * kMDld;
+            {   // (row, 16-byte column) pairs, consecutive lanes along the row; e -> e + 128 advances (r, c) by (xq, xr) with one carry
+                int r = lt / xc4, c = lt - r * xc4;
+                while (r < 64) {
+                    const bool on = rt + r < r_end;
+                    cp_async16(xs + r * kMXld + 4 * c, on ? x + (rt + r) * ldx + xc0 + 4 * c : x, on);
+                    r += xq;
+                    c += xr;
+                    if (c >= xc4) {
+                        c -= xc4;
+                        ++r;
+                    }
+                }
+            }
+            {
+                int r = lt / dc4, c = lt - r * dc4;
+                while (r < 64) {
+                    const bool on = rt + r < r_end;
+                    cp_async16(ds + r * kMDld + 4 * c, on ? dy + (rt + r) * ld_dy + 4 * c : dy, on);
+                    r += dq;
+                    c += dr;
+                    if (c >= dc4) {
+                        c -= dc4;
+                        ++r;
+                    }
+                }
+            }
+            cp_async_arrive_on(&bar_in[buf]);
+        }
+    } else {
+        // ==================================================== producers ====================================================
+        const int r64 = tid & 63, part = tid >> 6;
+        int st = 0, bbuf = 0;
+        uint32_t round = 0;                                  // uses of A stage `st` so far
+        long long t = 0;
+        for (long long rt = r_beg; rt < r_end; rt += 64, ++t, bbuf ^= 1) {
+            const long long row = rt + r64;
+            const bool row_ok = row < r_end;
+            float mean = 0.f, rstd = 1.f;
+            if (K == 0 && g.stats && row_ok) {
+                mean = __ldg(g.stats + 2 * row);
+                rstd = __ldg(g.stats + 2 * row + 1);
+            }
+            tc::mbar_wait(&bar_in[bbuf], (uint32_t)(t >> 1) & 1u);            // this batch's x and dY rows are in shared memory
+            if (t >= 2) tc::mbar_wait(&bar_batch[bbuf], (uint32_t)((t >> 1) - 1) & 1u);   // the MMAs that read this B buffer are done
+            if (part < nu) {
+                const float* dr = d_st + ((size_t)bbuf * 64 + r64) * kMDld + 8 * part;
+                float4 d0 = make_float4(0.f, 0.f, 0.f, 0.f), d1 = d0;
+                if (row_ok && 8 * part + 4 <= g.out_f) d0 = *reinterpret_cast<const float4*>(dr);
+                if (row_ok && 8 * part + 8 <= g.out_f) d1 = *reinterpret_cast<const float4*>(dr + 4);
+                const float v[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+                uint4 hi, lo;
+                tc::split8(v, hi, lo);
+                uint8_t* bh = b_st + (size_t)bbuf * 2u * b_bytes;
+                *reinterpret_cast<uint4*>(bh + (size_t)part * kUnit + r64 * 16) = hi;
+                *reinterpret_cast<uint4*>(bh + b_bytes + (size_t)part * kUnit + r64 * 16) = lo;
+            }
+            const float* xrow = x_st + ((size_t)bbuf * 64 + r64) * kMXld + xoff;
+            for (int b = 0; b < nb; ++b) {
+                const int f0 = (fb0 + b) * kFB;
+                if (round) tc::mbar_wait(&bar_stage[st], (round - 1u) & 1u);  // the MMAs of three blocks ago have read this stage
+                uint8_t* a_hi = a_st + (size_t)st * kAStage;
+                uint8_t* a_lo = a_hi + 16u * kUnit;
+#pragma unroll
+                for (int ii = 0; ii < 2; ++ii) {
+                    const int i = part + 8 * ii;
+                    if (i < kFB) {                          // uniform over the part (two warps)
+                        const bool on = row_ok && (f0 + i) < g.in_f;
+                        const float xv = xrow[b * kFB + i];
+                        uint4 hi, lo;
+                        if (K == 0) {
+                            const float z = rbf_z_b(g, xv, mean, rstd, f0 + i);
+                            float e[8];
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const float tt = (z - (g.c0 + (float)q * g.step)) * g.inv_den;
+                                e[q] = (on && q < g.S) ? ex2_b(-kLog2eB * tt * tt) : 0.f;
+                            }
+                            tc::split8(e, hi, lo);
+                        } else {
+                            int idx;
+                            float fr, bv[4];
+                            locate_b(g, xv, idx, fr);
+                            local_values_b<(K == 0 ? 1 : K)>(fr, bv);
+                            const uint32_t h01 = pack_trunc_b(bv[0], bv[1]), h23 = pack_trunc_b(bv[2], bv[3]);
+                            const uint32_t l01 = pack_rn_b(trunc_res_b(bv[0]), trunc_res_b(bv[1])), l23 = pack_rn_b(trunc_res_b(bv[2]), trunc_res_b(bv[3]));
+                            uint4 sel = lut[idx];
+                            if (!on) sel = make_uint4(0x9999u, 0x9999u, 0x9999u, 0x9999u);
+                            hi = make_uint4(prmt_b(h01, h23, sel.x), prmt_b(h01, h23, sel.y), prmt_b(h01, h23, sel.z), prmt_b(h01, h23, sel.w));
+                            lo = make_uint4(prmt_b(l01, l23, sel.x), prmt_b(l01, l23, sel.y), prmt_b(l01, l23, sel.z), prmt_b(l01, l23, sel.w));
+                        }
+                        *reinterpret_cast<uint4*>(a_hi + (size_t)i * kUnit + r64 * 16) = hi;
+                        *reinterpret_cast<uint4*>(a_lo + (size_t)i * kUnit + r64 * 16) = lo;
+                        const float sv = on ? __fdividef(xv, 1.0f + ex2_b(-kLog2eB * xv)) : 0.f;
+                        const uint32_t off = (uint32_t)(kFB + (i >> 3)) * kUnit + (uint32_t)r64 * 16u + (uint32_t)(i & 7) * 2u;
+                        *reinterpret_cast<uint16_t*>(a_hi + off) = (uint16_t)(__float_as_uint(sv) >> 16);
+                        *reinterpret_cast<uint16_t*>(a_lo + off) = (uint16_t)(pack_rn_b(trunc_res_b(sv), 0.f) & 0xffffu);
+                    } else {                                // parts 6, 7: the pad elements (features 14, 15) of unit 15
+                        const uint32_t off = (uint32_t)(kFB + 1) * kUnit + (uint32_t)r64 * 16u + (uint32_t)(i & 7) * 2u;
+                        *reinterpret_cast<uint16_t*>(a_hi + off) = 0;
+                        *reinterpret_cast<uint16_t*>(a_lo + off) = 0;
+                    }
+                }
+                tc::fence_proxy_async_smem();
+                if (st == 0) named_arrive<1, kMSync>();
+                else if (st == 1) named_arrive<2, kMSync>();
+                else named_arrive<3, kMSync>();
+                if (st == kMStages - 1) {
+                    st = 0;
+                    ++round;
+                } else {
+                    ++st;
+                }
+            }
+        }
+        // ---- the slab's sums: every MMA has completed
+        if (r_beg < r_end) {
+            tc::mbar_wait(bar_done, 0);
+            tc::tc_fence_after_sync();
+            const int m = tid & 127, u = m >> 3, c = m & 7, quarter = tid >> 7;     // warps 0-3 / 4-7 / 8-11 / 12-15 take blocks b = quarter, quarter + 4
+            const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+            const int rot = (int)(blockIdx.y % (unsigned)(N16 / 8)) * 8;             // CTAs start at different columns: fewer collisions in L2
+            for (int b = quarter; b < nb; b += 4) {
+                const int f0 = (fb0 + b) * kFB;
+                long long dst = -1;
+                if (u < kFB) {
+                    if (f0 + u < g.in_f && c < g.S) dst = ((long long)(f0 + u) * (g.S + 1) + c) * g.out_pad;
+                } else {
+                    const int i = (u - kFB) * 8 + c;
+                    if (i < kFB && f0 + i < g.in_f) dst = ((long long)(f0 + i) * (g.S + 1) + g.S) * g.out_pad;
+                }
+                for (int oo = 0; oo < N16; oo += 16) {
+                    int o0 = oo + rot;
+                    if (o0 >= N16) o0 -= N16;
+                    int o1 = o0 + 8;
+                    if (o1 >= N16) o1 -= N16;
+                    float v[8], w[8];
+                    tc::tmem_ld8(tmem_base + lane_base + (uint32_t)(b * N16 + o0), v);   // warp-collective: every lane takes part
+                    const bool second = oo + 8 < N16;
+                    if (second) tc::tmem_ld8(tmem_base + lane_base + (uint32_t)(b * N16 + o1), w);
+                    if (dst >= 0) {                         // out_f is a multiple of 4 here: a 4-vector is inside or outside as a whole
+                        if (o0 < g.out_f) red_add_v4(dP + dst + o0, v[0], v[1], v[2], v[3]);
+                        if (o0 + 4 < g.out_f) red_add_v4(dP + dst + o0 + 4, v[4], v[5], v[6], v[7]);
+                        if (second) {
+                            if (o1 < g.out_f) red_add_v4(dP + dst + o1, w[0], w[1], w[2], w[3]);
+                            if (o1 + 4 < g.out_f) red_add_v4(dP + dst + o1 + 4, w[4], w[5], w[6], w[7]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (control) tc::tmem_dealloc(tmem_base, tmem_cols);
+}
+
 int geometry_b(const KagnnKanLayer* L, GeomB* g) {
     if (!L || !L->packed_w || L->basis != KAGNN_BASIS_BSPLINE) return KAGNN_EUNSUPPORTED;
     if (L->in_features <= 0 || L->out_features <= 0 || L->grid_size < 1 || L->spline_order < 1 || L->spline_order > 4) return KAGNN_EUNSUPPORTED;
@@ -891,10 +1200,10 @@ std::atomic<int> g_dx_packed{1};        // dX reads the forward's packed weights
 }  // namespace
 
 extern "C" int kagnn_set_backward_path(int32_t mode) {
-    if (mode < 0 || mode > 2) return KAGNN_EINVAL;      // 2 = tensor cores, but dX without the packed-weight operand (tests)
+    if (mode < 0 || mode > 3) return KAGNN_EINVAL;      // 2, 3 = tensor cores with the alternative kernels (tests): see the header
     g_bwd_path.store(mode == 1 ? 1 : 0);
     g_dx_packed.store(mode == 2 ? 0 : 1);
-    g_dw_rows64.store(mode == 2 ? 0 : 1);
+    g_dw_rows64.store(mode == 2 ? 0 : (mode == 3 ? 2 : 1));
     return KAGNN_OK;
 }
 
@@ -964,8 +1273,30 @@ int launch_bwd_weights_tc(const GeomB& g, const float* x, int64_t ldx, const flo
     if (const char* e = getenv("KAGNN_DEBUG_DW_SWAP")) swap = atoi(e);
 #endif
     const bool dy_vec = g.out_f % 4 == 0 && ld_dy % 4 == 0 && aligned16(dy);
+    const bool x_vec = g.in_f % 4 == 0 && ldx % 4 == 0 && aligned16(x);
     if (N16 <= 64 && dy_vec && g_dw_rows64.load() != 0) {
-        // narrow layers: 64-row batches, three CTAs per SM
+        // narrow layers, several feature blocks per CTA: dY is split once per batch for up to eight blocks, E^T double-buffered
+        int max_blocks = kMBlocks;
+        if (const char* e = getenv("KAGNN_DW_MBLOCKS")) max_blocks = atoi(e);
+        const int passes = (fblocks + max_blocks - 1) / max_blocks;
+        const int bpp = (fblocks + passes - 1) / passes;                  // balanced: 10 blocks -> 5 + 5
+        const uint32_t cols_m = tc::tmem_cols_pow2((uint32_t)(bpp * N16));
+        const size_t smem_m = dw_smem_layout(N16).total;
+        int64_t slabs_m = (int64_t)props.num_sms / passes;              // one CTA (16 warps) per SM, one wave
+        if (slabs_m > ceil_div64(num_rows, 64)) slabs_m = ceil_div64(num_rows, 64);
+        if (slabs_m > 65535) slabs_m = 65535;
+        if (slabs_m < 1) slabs_m = 1;
+        int64_t rps_m = ceil_div64(ceil_div64(num_rows, slabs_m), 64) * 64;
+        slabs_m = ceil_div64(num_rows, rps_m);
+        auto km = g.k == 3 ? kan_bwd_weights_tc64m_kernel<3> : (g.k == 2 ? kan_bwd_weights_tc64m_kernel<2> : (g.k == 1 ? kan_bwd_weights_tc64m_kernel<1> : kan_bwd_weights_tc64m_kernel<0>));
+        KAGNN_CUDA_TRY(cudaFuncSetAttribute(km, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)props.max_smem));
+        if (g_dw_rows64.load() == 1 && x_vec && g.out_pad % 4 == 0 && aligned16(d_packed) && smem_m <= (size_t)props.max_smem) {
+            km<<<dim3((unsigned)passes, (unsigned)slabs_m, 1), kMThreads, smem_m, stream>>>(g, x, (long long)ldx, dy, (long long)ld_dy,
+                                                                                            (long long)num_rows, (long long)rps_m, N16, fblocks, bpp, cols_m, d_packed);
+            KAGNN_LAUNCH_CHECK();
+            return KAGNN_OK;
+        }
+        // (mode 3 of kagnn_set_backward_path: one feature block per CTA) 64-row batches, three CTAs per SM
         const size_t smem64 = (size_t)2 * 16 * 1024 + (size_t)2 * (N16 / 8) * 1024 + kLutRows * 16 + 64;
         int64_t slabs64 = ceil_div64((int64_t)props.num_sms * 6, fblocks);
         if (slabs64 > ceil_div64(num_rows, 64)) slabs64 = ceil_div64(num_rows, 64);

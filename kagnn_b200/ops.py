@@ -490,7 +490,8 @@ def set_path(mode: int) -> None:
 
 
 def set_backward_path(mode: int) -> None:
-    """0 = tcgen05 gradient kernels when the shape fits (default), 1 = fp32 CUDA-core kernels only (kagnn_set_backward_path)."""
+    """0 = tcgen05 gradient kernels when the shape fits (default), 1 = fp32 CUDA-core kernels only, 2 / 3 = the tcgen05 kernels'
+    alternative variants (kagnn_set_backward_path; tests compare them all)."""
     L.check(L.lib().kagnn_set_backward_path(int(mode)), "set_backward_path")
 
 

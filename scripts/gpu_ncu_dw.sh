@@ -1,0 +1,6 @@
+#!/bin/bash
+# ncu --set full (with source-level sampling) of the dW kernel: the first step's seven launches
+OUT=gpurun_out; mkdir -p $OUT
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:bwd_weights -c 3 -f -o $OUT/r2_dw_prof \
+    python scripts/train_step_time.py > $OUT/r2_dw_prof.log 2>&1 ; echo "ncu rc=$?"
+ls -la $OUT | tail -4
