@@ -1277,7 +1277,9 @@ int launch_bwd_weights_tc(const GeomB& g, const float* x, int64_t ldx, const flo
     if (N16 <= 64 && dy_vec && g_dw_rows64.load() != 0) {
         // narrow layers, several feature blocks per CTA: dY is split once per batch for up to eight blocks, E^T double-buffered
         int max_blocks = kMBlocks;
-        if (const char* e = getenv("KAGNN_DW_MBLOCKS")) max_blocks = atoi(e);
+#ifdef KAGNN_DEBUG_KNOBS
+        if (const char* e = getenv("KAGNN_DEBUG_DW_MBLOCKS")) max_blocks = atoi(e) < 1 ? 1 : (atoi(e) > kMBlocks ? kMBlocks : atoi(e));
+#endif
         const int passes = (fblocks + max_blocks - 1) / max_blocks;
         const int bpp = (fblocks + passes - 1) / passes;                  // balanced: 10 blocks -> 5 + 5
         const uint32_t cols_m = tc::tmem_cols_pow2((uint32_t)(bpp * N16));
