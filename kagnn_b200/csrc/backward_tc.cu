@@ -891,7 +891,6 @@ constexpr int kMLoaders = 128;
 constexpr int kMThreads = kMSync + kMLoaders;
 constexpr int kMStages = 3;
 constexpr int kMXld = kMBlocks * kFB + 4;                    // staged x row: up to 112 values + 2 of alignment slack, 16-byte rows
-constexpr int kMDld = 64 + 4;                                // staged dY row
 
 template <int ID, int COUNT>
 __device__ __forceinline__ void named_arrive() { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(COUNT) : "memory"); }
@@ -912,29 +911,31 @@ __device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c
 struct DwSmem {                                              // carve-up of the dynamic shared memory (offsets in bytes)
     uint32_t a, b, xs, ds, lut, bars, total;
 };
-__host__ __device__ inline DwSmem dw_smem_layout(int N16) {
+__host__ __device__ inline DwSmem dw_smem_layout(int N16, int rows) {
     DwSmem L;
-    const uint32_t unit = 64u * 16u;
+    const uint32_t unit = (uint32_t)rows * 16u;
     L.a = 0;
     L.b = L.a + (uint32_t)kMStages * 2u * 16u * unit;        // [stage][hi | lo]
     L.xs = L.b + 2u * 2u * (uint32_t)(N16 / 8) * unit;       // [buffer][hi | lo]
-    L.ds = L.xs + 2u * 64u * (uint32_t)kMXld * 4u;
-    L.lut = L.ds + 2u * 64u * (uint32_t)kMDld * 4u;
+    L.ds = L.xs + 2u * (uint32_t)rows * (uint32_t)kMXld * 4u;
+    L.lut = L.ds + 2u * (uint32_t)rows * (uint32_t)(N16 + 4) * 4u;         // staged dY row: N16 values + 4 (16-byte rows, odd in 16-byte units)
     L.bars = L.lut + (uint32_t)kLutRows * 16u;
     L.total = L.bars + 160u;
     return L;
 }
 
-template <int K>
-__global__ void __launch_bounds__(kMThreads, 1) kan_bwd_weights_tc64m_kernel(GeomB g, const float* __restrict__ x, long long ldx,
+template <int K, int ROWS>
+__global__ void __launch_bounds__(kMThreads, 1) kan_bwd_weights_tcm_kernel(GeomB g, const float* __restrict__ x, long long ldx,
                                                                              const float* __restrict__ dy, long long ld_dy, long long n_rows,
                                                                              long long rows_per_slab, int N16, int fblocks,
                                                                              int blocks_per_pass, uint32_t tmem_cols, float* __restrict__ dP) {
     extern __shared__ __align__(128) uint8_t smem[];
-    constexpr uint32_t kUnit = 64u * 16u;                    // one unit of 8 M (or N) elements x 64 rows
+    constexpr uint32_t kUnit = (uint32_t)ROWS * 16u;         // one unit of 8 M (or N) elements x ROWS rows
     constexpr uint32_t kAStage = 2u * 16u * kUnit;           // hi + lo of one E^T operand
-    const DwSmem L = dw_smem_layout(N16);
-    const int nu = N16 / 8;                                  // <= 8
+    constexpr int kParts = kMProducers / ROWS;               // 8 (64-row batches) or 16 (32-row batches)
+    constexpr int kFeatPerThread = 16 / kParts;              // 2 or 1
+    const DwSmem L = dw_smem_layout(N16, ROWS);
+    const int nu = N16 / 8, dld = N16 + 4;                   // units of dY (<= 8 with 64-row batches, <= 32 with 32-row ones)
     const uint32_t b_bytes = (uint32_t)nu * kUnit;
     uint8_t* a_st = smem + L.a;
     uint8_t* b_st = smem + L.b;
@@ -981,7 +982,7 @@ __global__ void __launch_bounds__(kMThreads, 1) kan_bwd_weights_tc64m_kernel(Geo
         const uint64_t dbh0 = tc::smem_desc(tc::smem_u32(b_st), 128, kUnit), dbl0 = tc::smem_desc(tc::smem_u32(b_st + b_bytes), 128, kUnit);
         int st = 0, bbuf = 0;
         long long t = 0;
-        for (long long rt = r_beg; rt < r_end; rt += 64, ++t, bbuf ^= 1) {
+        for (long long rt = r_beg; rt < r_end; rt += ROWS, ++t, bbuf ^= 1) {
             for (int b = 0; b < nb; ++b) {
                 if (st == 0) named_sync<1, kMSync>();
                 else if (st == 1) named_sync<2, kMSync>();
@@ -992,7 +993,7 @@ __global__ void __launch_bounds__(kMThreads, 1) kan_bwd_weights_tc64m_kernel(Geo
                     const uint64_t a_off = (uint64_t)((uint32_t)st * (kAStage >> 4)), b_off = (uint64_t)((uint32_t)bbuf * ((2u * b_bytes) >> 4));
                     uint32_t acc = t == 0 ? 0u : 1u;
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {        // K = 16 rows per step: two groups of 8 k-rows, 256 bytes
+                    for (int ks = 0; ks < ROWS / 16; ++ks) { // K = 16 rows per step: two groups of 8 k-rows, 256 bytes
                         const uint64_t ko = (uint64_t)(ks * 16);
                         tc::umma_bf16(d_col, dah0 + a_off + ko, dbh0 + b_off + ko, idesc, acc);
                         tc::umma_bf16(d_col, dah0 + a_off + ko, dbl0 + b_off + ko, idesc, 1);
@@ -1017,14 +1018,14 @@ __global__ void __launch_bounds__(kMThreads, 1) kan_bwd_weights_tc64m_kernel(Geo
         const int xc4 = xcols >> 2, dc4 = g.out_f >> 2;
         const int xq = kMLoaders / xc4, xr = kMLoaders - xq * xc4, dq = kMLoaders / dc4, dr = kMLoaders - dq * dc4;
         long long t = 0;
-        for (long long rt = r_beg; rt < r_end; rt += 64, ++t) {
+        for (long long rt = r_beg; rt < r_end; rt += ROWS, ++t) {
             const int buf = (int)(t & 1);
             if (t >= 2) tc::mbar_wait(&bar_free[buf], (uint32_t)((t >> 1) - 1) & 1u);
-            float* xs = x_st + (size_t)buf * 64 * kMXld;
-            float* ds = d_st + (size_t)buf * 64 * kMDld;
+            float* xs = x_st + (size_t)buf * ROWS * kMXld;
+            float* ds = d_st + (size_t)buf * ROWS * dld;
             {   // (row, 16-byte column) pairs, consecutive lanes along the row; e -> e + 128 advances (r, c) by (xq, xr) with one carry
                 int r = lt / xc4, c = lt - r * xc4;
-                while (r < 64) {
+                while (r < ROWS) {
                     const bool on = rt + r < r_end;
                     cp_async16(xs + r * kMXld + 4 * c, on ? x + (rt + r) * ldx + xc0 + 4 * c : x, on);
                     r += xq;
@@ -1037,9 +1038,9 @@ __global__ void __launch_bounds__(kMThreads, 1) kan_bwd_weights_tc64m_kernel(Geo
             }
             {
                 int r = lt / dc4, c = lt - r * dc4;
-                while (r < 64) {
+                while (r < ROWS) {
                     const bool on = rt + r < r_end;
-                    cp_async16(ds + r * kMDld + 4 * c, on ? dy + (rt + r) * ld_dy + 4 * c : dy, on);
+                    cp_async16(ds + r * dld + 4 * c, on ? dy + (rt + r) * ld_dy + 4 * c : dy, on);
                     r += dq;
                     c += dr;
                     if (c >= dc4) {
@@ -1052,11 +1053,11 @@ __global__ void __launch_bounds__(kMThreads, 1) kan_bwd_weights_tc64m_kernel(Geo
         }
     } else {
         // ==================================================== producers ====================================================
-        const int r64 = tid & 63, part = tid >> 6;
+        const int r64 = tid & (ROWS - 1), part = tid / ROWS;       // row of the batch, part of the feature block
         int st = 0, bbuf = 0;
         uint32_t round = 0;                                  // uses of A stage `st` so far
         long long t = 0;
-        for (long long rt = r_beg; rt < r_end; rt += 64, ++t, bbuf ^= 1) {
+        for (long long rt = r_beg; rt < r_end; rt += ROWS, ++t, bbuf ^= 1) {
             const long long row = rt + r64;
             const bool row_ok = row < r_end;
             float mean = 0.f, rstd = 1.f;
@@ -1066,28 +1067,28 @@ __global__ void __launch_bounds__(kMThreads, 1) kan_bwd_weights_tc64m_kernel(Geo
             }
             tc::mbar_wait(&bar_in[bbuf], (uint32_t)(t >> 1) & 1u);            // this batch's x and dY rows are in shared memory
             if (t >= 2) tc::mbar_wait(&bar_batch[bbuf], (uint32_t)((t >> 1) - 1) & 1u);   // the MMAs that read this B buffer are done
-            if (part < nu) {
-                const float* dr = d_st + ((size_t)bbuf * 64 + r64) * kMDld + 8 * part;
+            for (int u = part; u < nu; u += kParts) {            // this thread's 8-column units of dY
+                const float* dr = d_st + ((size_t)bbuf * ROWS + r64) * dld + 8 * u;
                 float4 d0 = make_float4(0.f, 0.f, 0.f, 0.f), d1 = d0;
-                if (row_ok && 8 * part + 4 <= g.out_f) d0 = *reinterpret_cast<const float4*>(dr);
-                if (row_ok && 8 * part + 8 <= g.out_f) d1 = *reinterpret_cast<const float4*>(dr + 4);
+                if (row_ok && 8 * u + 4 <= g.out_f) d0 = *reinterpret_cast<const float4*>(dr);
+                if (row_ok && 8 * u + 8 <= g.out_f) d1 = *reinterpret_cast<const float4*>(dr + 4);
                 const float v[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
                 uint4 hi, lo;
                 tc::split8(v, hi, lo);
                 uint8_t* bh = b_st + (size_t)bbuf * 2u * b_bytes;
-                *reinterpret_cast<uint4*>(bh + (size_t)part * kUnit + r64 * 16) = hi;
-                *reinterpret_cast<uint4*>(bh + b_bytes + (size_t)part * kUnit + r64 * 16) = lo;
+                *reinterpret_cast<uint4*>(bh + (size_t)u * kUnit + r64 * 16) = hi;
+                *reinterpret_cast<uint4*>(bh + b_bytes + (size_t)u * kUnit + r64 * 16) = lo;
             }
-            const float* xrow = x_st + ((size_t)bbuf * 64 + r64) * kMXld + xoff;
+            const float* xrow = x_st + ((size_t)bbuf * ROWS + r64) * kMXld + xoff;
             for (int b = 0; b < nb; ++b) {
                 const int f0 = (fb0 + b) * kFB;
                 if (round) tc::mbar_wait(&bar_stage[st], (round - 1u) & 1u);  // the MMAs of three blocks ago have read this stage
                 uint8_t* a_hi = a_st + (size_t)st * kAStage;
                 uint8_t* a_lo = a_hi + 16u * kUnit;
 #pragma unroll
-                for (int ii = 0; ii < 2; ++ii) {
-                    const int i = part + 8 * ii;
-                    if (i < kFB) {                          // uniform over the part (two warps)
+                for (int ii = 0; ii < kFeatPerThread; ++ii) {
+                    const int i = part + kParts * ii;
+                    if (i < kFB) {                          // uniform over the part (one or two warps)
                         const bool on = row_ok && (f0 + i) < g.in_f;
                         const float xv = xrow[b * kFB + i];
                         uint4 hi, lo;
@@ -1118,7 +1119,7 @@ __global__ void __launch_bounds__(kMThreads, 1) kan_bwd_weights_tc64m_kernel(Geo
                         const uint32_t off = (uint32_t)(kFB + (i >> 3)) * kUnit + (uint32_t)r64 * 16u + (uint32_t)(i & 7) * 2u;
                         *reinterpret_cast<uint16_t*>(a_hi + off) = (uint16_t)(__float_as_uint(sv) >> 16);
                         *reinterpret_cast<uint16_t*>(a_lo + off) = (uint16_t)(pack_rn_b(trunc_res_b(sv), 0.f) & 0xffffu);
-                    } else {                                // parts 6, 7: the pad elements (features 14, 15) of unit 15
+                    } else {                                // the pad elements (features 14, 15) of unit 15
                         const uint32_t off = (uint32_t)(kFB + 1) * kUnit + (uint32_t)r64 * 16u + (uint32_t)(i & 7) * 2u;
                         *reinterpret_cast<uint16_t*>(a_hi + off) = 0;
                         *reinterpret_cast<uint16_t*>(a_lo + off) = 0;
@@ -1140,10 +1141,13 @@ __global__ void __launch_bounds__(kMThreads, 1) kan_bwd_weights_tc64m_kernel(Geo
         if (r_beg < r_end) {
             tc::mbar_wait(bar_done, 0);
             tc::tc_fence_after_sync();
-            const int m = tid & 127, u = m >> 3, c = m & 7, quarter = tid >> 7;     // warps 0-3 / 4-7 / 8-11 / 12-15 take blocks b = quarter, quarter + 4
+            // lane m of tensor memory = row m of a block's 128 gradient rows; the four warpgroups share the (block, 16-column pair) items
+            const int m = tid & 127, u = m >> 3, c = m & 7, quarter = tid >> 7;
             const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-            const int rot = (int)(blockIdx.y % (unsigned)(N16 / 8)) * 8;             // CTAs start at different columns: fewer collisions in L2
-            for (int b = quarter; b < nb; b += 4) {
+            const int npair = N16 / 16;
+            const int rot = (int)(blockIdx.y % (unsigned)npair) * 16;                // CTAs start at different columns: fewer collisions in L2
+            for (int item = quarter; item < nb * npair; item += 4) {
+                const int b = item / npair, oo = (item - b * npair) * 16;
                 const int f0 = (fb0 + b) * kFB;
                 long long dst = -1;
                 if (u < kFB) {
@@ -1152,23 +1156,17 @@ __global__ void __launch_bounds__(kMThreads, 1) kan_bwd_weights_tc64m_kernel(Geo
                     const int i = (u - kFB) * 8 + c;
                     if (i < kFB && f0 + i < g.in_f) dst = ((long long)(f0 + i) * (g.S + 1) + g.S) * g.out_pad;
                 }
-                for (int oo = 0; oo < N16; oo += 16) {
-                    int o0 = oo + rot;
-                    if (o0 >= N16) o0 -= N16;
-                    int o1 = o0 + 8;
-                    if (o1 >= N16) o1 -= N16;
-                    float v[8], w[8];
-                    tc::tmem_ld8(tmem_base + lane_base + (uint32_t)(b * N16 + o0), v);   // warp-collective: every lane takes part
-                    const bool second = oo + 8 < N16;
-                    if (second) tc::tmem_ld8(tmem_base + lane_base + (uint32_t)(b * N16 + o1), w);
-                    if (dst >= 0) {                         // out_f is a multiple of 4 here: a 4-vector is inside or outside as a whole
-                        if (o0 < g.out_f) red_add_v4(dP + dst + o0, v[0], v[1], v[2], v[3]);
-                        if (o0 + 4 < g.out_f) red_add_v4(dP + dst + o0 + 4, v[4], v[5], v[6], v[7]);
-                        if (second) {
-                            if (o1 < g.out_f) red_add_v4(dP + dst + o1, w[0], w[1], w[2], w[3]);
-                            if (o1 + 4 < g.out_f) red_add_v4(dP + dst + o1 + 4, w[4], w[5], w[6], w[7]);
-                        }
-                    }
+                int o0 = oo + rot;
+                if (o0 >= N16) o0 -= N16;
+                const int o1 = o0 + 8;
+                float v[8], w[8];
+                tc::tmem_ld8(tmem_base + lane_base + (uint32_t)(b * N16 + o0), v);   // warp-collective: every lane takes part
+                tc::tmem_ld8(tmem_base + lane_base + (uint32_t)(b * N16 + o1), w);
+                if (dst >= 0) {                             // out_f is a multiple of 4 here: a 4-vector is inside or outside as a whole
+                    if (o0 < g.out_f) red_add_v4(dP + dst + o0, v[0], v[1], v[2], v[3]);
+                    if (o0 + 4 < g.out_f) red_add_v4(dP + dst + o0 + 4, v[4], v[5], v[6], v[7]);
+                    if (o1 < g.out_f) red_add_v4(dP + dst + o1, w[0], w[1], w[2], w[3]);
+                    if (o1 + 4 < g.out_f) red_add_v4(dP + dst + o1 + 4, w[4], w[5], w[6], w[7]);
                 }
             }
         }
@@ -1274,30 +1272,37 @@ int launch_bwd_weights_tc(const GeomB& g, const float* x, int64_t ldx, const flo
 #endif
     const bool dy_vec = g.out_f % 4 == 0 && ld_dy % 4 == 0 && aligned16(dy);
     const bool x_vec = g.in_f % 4 == 0 && ldx % 4 == 0 && aligned16(x);
-    if (N16 <= 64 && dy_vec && g_dw_rows64.load() != 0) {
-        // narrow layers, several feature blocks per CTA: dY is split once per batch for up to eight blocks, E^T double-buffered
-        int max_blocks = kMBlocks;
+    const int dw_mode = g_dw_rows64.load();                   // 1 = default, 2 / 0 = the alternative kernels (kagnn_set_backward_path 3 / 2)
+    if (dw_mode == 1 && dy_vec && x_vec && g.out_pad % 4 == 0 && aligned16(d_packed)) {
+        // several feature blocks per CTA (as many accumulators as tensor memory holds) share one split of the dY batch;
+        // 64-row batches for layers up to 64 wide, 32-row batches above (the dY operand of a batch is N16 x rows x 4 bytes)
+        const bool narrow = N16 <= 64;
+        const int rows = narrow ? 64 : 32;
+        int max_blocks = narrow ? kMBlocks : 512 / N16;
 #ifdef KAGNN_DEBUG_KNOBS
-        if (const char* e = getenv("KAGNN_DEBUG_DW_MBLOCKS")) max_blocks = atoi(e) < 1 ? 1 : (atoi(e) > kMBlocks ? kMBlocks : atoi(e));
+        if (const char* e = getenv("KAGNN_DEBUG_DW_MBLOCKS")) max_blocks = atoi(e) < 1 ? 1 : (atoi(e) > max_blocks ? max_blocks : atoi(e));
 #endif
         const int passes = (fblocks + max_blocks - 1) / max_blocks;
         const int bpp = (fblocks + passes - 1) / passes;                  // balanced: 10 blocks -> 5 + 5
         const uint32_t cols_m = tc::tmem_cols_pow2((uint32_t)(bpp * N16));
-        const size_t smem_m = dw_smem_layout(N16).total;
-        int64_t slabs_m = (int64_t)props.num_sms / passes;              // one CTA (16 warps) per SM, one wave
+        const size_t smem_m = dw_smem_layout(N16, rows).total;
+        int64_t slabs_m = (int64_t)props.num_sms / passes;              // one CTA (21 warps) per SM, one wave
         if (slabs_m > ceil_div64(num_rows, 64)) slabs_m = ceil_div64(num_rows, 64);
         if (slabs_m > 65535) slabs_m = 65535;
         if (slabs_m < 1) slabs_m = 1;
         int64_t rps_m = ceil_div64(ceil_div64(num_rows, slabs_m), 64) * 64;
         slabs_m = ceil_div64(num_rows, rps_m);
-        auto km = g.k == 3 ? kan_bwd_weights_tc64m_kernel<3> : (g.k == 2 ? kan_bwd_weights_tc64m_kernel<2> : (g.k == 1 ? kan_bwd_weights_tc64m_kernel<1> : kan_bwd_weights_tc64m_kernel<0>));
-        KAGNN_CUDA_TRY(cudaFuncSetAttribute(km, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)props.max_smem));
-        if (g_dw_rows64.load() == 1 && x_vec && g.out_pad % 4 == 0 && aligned16(d_packed) && smem_m <= (size_t)props.max_smem) {
+        if (smem_m <= (size_t)props.max_smem && cols_m <= 512) {
+            auto km = narrow ? (g.k == 3 ? kan_bwd_weights_tcm_kernel<3, 64> : (g.k == 2 ? kan_bwd_weights_tcm_kernel<2, 64> : (g.k == 1 ? kan_bwd_weights_tcm_kernel<1, 64> : kan_bwd_weights_tcm_kernel<0, 64>)))
+                             : (g.k == 3 ? kan_bwd_weights_tcm_kernel<3, 32> : (g.k == 2 ? kan_bwd_weights_tcm_kernel<2, 32> : (g.k == 1 ? kan_bwd_weights_tcm_kernel<1, 32> : kan_bwd_weights_tcm_kernel<0, 32>)));
+            KAGNN_CUDA_TRY(cudaFuncSetAttribute(km, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)props.max_smem));
             km<<<dim3((unsigned)passes, (unsigned)slabs_m, 1), kMThreads, smem_m, stream>>>(g, x, (long long)ldx, dy, (long long)ld_dy,
                                                                                             (long long)num_rows, (long long)rps_m, N16, fblocks, bpp, cols_m, d_packed);
             KAGNN_LAUNCH_CHECK();
             return KAGNN_OK;
         }
+    }
+    if (N16 <= 64 && dy_vec && dw_mode != 0) {
         // (mode 3 of kagnn_set_backward_path: one feature block per CTA) 64-row batches, three CTAs per SM
         const size_t smem64 = (size_t)2 * 16 * 1024 + (size_t)2 * (N16 / 8) * 1024 + kLutRows * 16 + 64;
         int64_t slabs64 = ceil_div64((int64_t)props.num_sms * 6, fblocks);
