@@ -219,7 +219,8 @@ int kagnn_set_path(int mode);
  * kernels when the shape fits (at least 128 rows, out <= 256; weights: G + k <= 8), else the fp32 CUDA-core kernels;
  * 1 = fp32 kernels only (tests compare the two); 2 = tcgen05 kernels, but d input splits the fp32 weights per tile instead of
  * reading the layer's tensor-core packing (packed_w_tc) as its operand, and d weights takes 128-row batches (tests);
- * 3 = tcgen05 kernels, d weights with one feature block per CTA instead of up to eight (tests). */
+ * 3 = tcgen05 kernels, d weights with one feature block per CTA instead of as many as tensor memory holds, d input without
+ * look-ahead (tests). */
 int kagnn_set_backward_path(int32_t mode);
 int kagnn_get_launch_counters(int64_t* tc_launches, int64_t* fp32_launches);
 /* Arithmetic of the tensor-core path.  KAGNN_PREC_FP32 (default): every product is formed from bf16 hi/lo pairs (three

@@ -144,6 +144,25 @@ constexpr int kLutRows = 13;
 // a 128-row K extent, i.e. SBO (unit stride) = 2048, LBO (stride between groups of 8 k-rows) = 128
 __host__ __device__ __forceinline__ uint32_t idesc_bf16_f32_mn(int m, int n) { return tc::idesc_bf16_f32(m, n) | (1u << 15) | (1u << 16); }
 
+// 16- / 4-byte asynchronous copies into shared memory; src-size 0 zero-fills the destination and reads nothing
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, bool on) {
+    const uint32_t n = on ? 16u : 0u;                        // src-size 0: the destination is zero-filled, nothing is read
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tc::smem_u32(dst_smem)), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_f32(void* dst_smem, const float* src, bool on) {
+    const uint32_t n = on ? 4u : 0u;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(tc::smem_u32(dst_smem)), "l"(src), "r"(n) : "memory");
+}
+// the mbarrier gets one arrival from this thread once all its earlier cp.async copies have landed
+__device__ __forceinline__ void cp_async_arrive_on(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+// named barriers of the warp-specialised kernels: producers ARRIVE and go on, the control warp SYNCs (ids 1 .. 3; 0 is __syncthreads)
+template <int ID, int COUNT>
+__device__ __forceinline__ void named_arrive() { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(COUNT) : "memory"); }
+template <int ID, int COUNT>
+__device__ __forceinline__ void named_sync() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory"); }
+
 // =====================================================================================================================
 // dX
 // =====================================================================================================================
@@ -466,6 +485,319 @@ __global__ void __launch_bounds__(kThreads) kan_bwd_input_tc_kernel(GeomB g, con
             tc::tc_fence_before_sync();
         }
         __syncthreads();                               // every thread is done with tensor memory before the next tile's A lands
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// dX with look-ahead, for layers up to 64 outputs wide with the packed-weight operand: passes of EIGHT features and two T
+// buffers in tensor memory (2 x (64 spline + 16 base columns), A behind them: 256 columns, two CTAs per SM as before), so the
+// MMAs of pass p + 1 are issued before the epilogue of pass p and complete under it; the barrier in front of an issue only says
+// "everybody is done with the epilogue of pass p - 1".  Weights arrive as before: stages of 16 features (= two passes), a ring
+// of two, the load of chunk n + 2 issued when the last MMA of chunk n has completed.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kFPL = 8;
+constexpr uint32_t kLookT = 96, kLookBase = 64, kLookA = 192;
+constexpr int kLookSync = kThreads + 32;                     // workers + control warp: the named barriers of the T buffers
+constexpr int kLookThreads = kThreads + 64;                  // + the loader warp (barrier 3 is theirs too)
+
+template <int K>
+__global__ void __launch_bounds__(kLookThreads, 2) kan_bwd_input_tc_look_kernel(GeomB g, const uint8_t* __restrict__ wtc, const float* __restrict__ x,
+                                                                         long long ldx, const float* __restrict__ dy, long long ld_dy,
+                                                                         long long n_rows, int n_tiles, int KK, uint32_t tmem_cols,
+                                                                         float* __restrict__ dx, long long ld_dx, float* __restrict__ dxb,
+                                                                         long long ld_dxb) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int kcs = KK / 8;
+    const uint32_t stage_bytes = 576u * (uint32_t)KK;    // two spline chunks (16 features) + two base slabs
+    uint64_t* bar_t = reinterpret_cast<uint64_t*>(smem + 2 * (size_t)stage_bytes);     // [2]: the MMAs into T buffer b are done
+    uint64_t* full = bar_t + 2;                                                         // [2]: weights of a stage have landed
+    uint64_t* bar_dy = full + 2;                                                        // the staged dY tile has landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_dy + 1);
+    float* d_st = reinterpret_cast<float*>(smem + 2 * (size_t)stage_bytes + 128);       // [128][KK + 4]: the tile's dY rows (dy16 only)
+    const int dld = KK + 4;
+    const int tid = threadIdx.x, warp = tid >> 5, wg = warp >> 2, r128 = tid & 127;
+    const bool control = warp == kThreads / 32;          // the ninth warp: weight loads and MMA issue
+    const bool loader = warp == kThreads / 32 + 1;       // the tenth: stages the next tile's dY rows
+
+    if (warp == 0) tc::tmem_alloc(tmem_slot, tmem_cols);
+    if (tid == 32) {
+        for (int i = 0; i < 4; ++i) tc::mbar_init(&bar_t[i], 1);
+        tc::mbar_init(bar_dy, 32);
+        tc::mbar_fence_init();
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const int n_pass = (g.in_f + kFPL - 1) / kFPL, chunks = (g.in_f + 15) / 16;
+    const bool dx_vec = (ld_dx % 4 == 0) && ((reinterpret_cast<uintptr_t>(dx) & 15u) == 0);
+    const bool dy_vec = g.out_f % 4 == 0 && ld_dy % 4 == 0 && ((reinterpret_cast<uintptr_t>(dy) & 15u) == 0);
+    const bool x_vec = g.in_f % 4 == 0 && ldx % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) & 15u) == 0);
+    const int my_tiles = (int)blockIdx.x < n_tiles ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const uint32_t total_chunks = (uint32_t)my_tiles * (uint32_t)chunks;
+    const int octs_all = chunks * 2;                     // feature octets of the packed layout (F_pad / 8)
+    auto load_chunk = [&](uint32_t n) {                  // running chunk n -> stage n & 1
+        const int f0 = (int)(n % (uint32_t)chunks) * 16, grp = f0 >> 6, j = (f0 & 63) >> 3;
+        const int n_oct = min(8, octs_all - 8 * grp);
+        const uint32_t st = n & 1u;
+        uint8_t* dst = smem + (size_t)st * stage_bytes;
+        const uint8_t* chunk = wtc + (size_t)(grp * 9 + j) * 256u * (size_t)KK;
+        const uint8_t* base = wtc + (size_t)(grp * 9 + n_oct) * 256u * (size_t)KK + (size_t)j * 32u * (size_t)KK;
+        tc::mbar_arrive_expect_tx(&full[st], stage_bytes);
+        tc::bulk_g2s(dst, chunk, 512u * (uint32_t)KK, &full[st]);
+        tc::bulk_g2s(dst + 512u * (uint32_t)KK, base, 64u * (uint32_t)KK, &full[st]);
+    };
+    if (control && (tid & 31) == 0) {
+        if (total_chunks > 0) load_chunk(0);
+        if (total_chunks > 1) load_chunk(1);
+    }
+    // one pass's MMAs (thread 0): half h of the stage's 16 features into T buffer qq & 1, its chunk's 16 base products next to them
+    auto issue = [&](int p_local, uint32_t qq, uint32_t cc) {
+        const uint32_t st = cc & 1u;
+        if ((p_local & 1) == 0) tc::mbar_wait(&full[st], (cc >> 1) & 1u);
+        tc::tc_fence_after_sync();
+        const uint32_t sb = tc::smem_u32(smem) + st * stage_bytes + (uint32_t)(p_local & 1) * 256u * (uint32_t)KK;
+        const uint32_t bb = tc::smem_u32(smem) + st * stage_bytes + 512u * (uint32_t)KK;
+        const uint32_t sbo = 32u * (uint32_t)KK, lo_off = 16u * (uint32_t)KK;
+        const uint32_t idesc_s = tc::idesc_bf16_f32(128, 64) | (1u << 16), idesc_b = tc::idesc_bf16_f32(128, 16) | (1u << 16);
+        const uint32_t tb = tmem_base + (qq & 1u) * kLookT;
+        uint32_t acc = 0;
+        for (int ks = 0; ks < KK / 16; ++ks) {
+            const uint32_t off = (uint32_t)ks * 256u;
+            const uint64_t dsh = tc::smem_desc(sb + off, 128, sbo), dsl = tc::smem_desc(sb + lo_off + off, 128, sbo);
+            const uint64_t dbh = tc::smem_desc(bb + off, 128, sbo), dbl = tc::smem_desc(bb + lo_off + off, 128, sbo);
+            const uint32_t tah = tmem_base + kLookA + 8u * ks, tal = tah + (uint32_t)KK / 2;
+            tc::umma_bf16_ts(tb, tah, dsh, idesc_s, acc);
+            tc::umma_bf16_ts(tb, tah, dsl, idesc_s, 1);
+            tc::umma_bf16_ts(tb, tal, dsh, idesc_s, 1);
+            tc::umma_bf16_ts(tb + kLookBase, tah, dbh, idesc_b, acc);
+            tc::umma_bf16_ts(tb + kLookBase, tah, dbl, idesc_b, 1);
+            tc::umma_bf16_ts(tb + kLookBase, tal, dbh, idesc_b, 1);
+            acc = 1;
+        }
+        tc::umma_commit(&bar_t[qq & 1u]);
+    };
+    uint32_t q = 0, cn = 0;                              // running pass / first chunk of the current tile
+
+    if (loader) {
+        // the tile's dY rows -> shared memory (16-byte copies, zero-filled outside the matrix), one tile ahead of the workers
+        auto stage_dy = [&](int tile_) {
+            if (dy_vec) {
+                const int c4n = KK >> 2, lane = tid & 31;
+                const int dq = 32 / c4n, dr = 32 - dq * c4n;
+                int r = lane / c4n, c = lane - r * c4n;
+                while (r < 128) {
+                    const long long row = (long long)tile_ * 128 + r;
+                    const bool on = row < n_rows && 4 * c < g.out_f;
+                    cp_async16(d_st + r * dld + 4 * c, on ? dy + row * ld_dy + 4 * c : dy, on);
+                    r += dq;
+                    c += dr;
+                    if (c >= c4n) {
+                        c -= c4n;
+                        ++r;
+                    }
+                }
+            }
+            cp_async_arrive_on(bar_dy);
+        };
+        if ((int)blockIdx.x < n_tiles) stage_dy((int)blockIdx.x);
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            named_sync<3, kLookThreads>();                // the workers have read the staged tile
+            if (tile + (int)gridDim.x < n_tiles) stage_dy(tile + (int)gridDim.x);
+        }
+    } else if (control) {
+        // ---- control warp: "A is in tensor memory" (barrier 3) -> pass 0; "T buffer b is free" (barriers 1 + b, one arrival
+        // generation per pass) -> the pass two ahead of the one that freed it; every generation is consumed, the last two of a
+        // tile at its end
+        const bool lead = (tid & 31) == 0;
+        auto free_sync = [&](uint32_t b_) {
+            if (b_) named_sync<2, kLookSync>();
+            else named_sync<1, kLookSync>();
+        };
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            named_sync<3, kLookThreads>();                // A is in tensor memory; nobody reads the staged dY tile any more
+            if (lead) issue(0, q, cn);
+            __syncwarp();
+            for (int pass = 0; pass < n_pass; ++pass, ++q) {
+                const uint32_t cc = cn + (uint32_t)(pass >> 1);
+                if (pass + 1 < n_pass) {
+                    if (pass >= 1) free_sync((q + 1u) & 1u);
+                    if (lead) issue(pass + 1, q + 1, cn + (uint32_t)((pass + 1) >> 1));
+                    __syncwarp();
+                }
+                // the last MMA of a chunk has completed: its stage takes the chunk after next
+                if (((pass & 1) == 1 || pass == n_pass - 1) && cc + 2 < total_chunks) {
+                    if (lead) {
+                        tc::mbar_wait(&bar_t[q & 1u], (q >> 1) & 1u);
+                        load_chunk(cc + 2);
+                    }
+                    __syncwarp();
+                }
+            }
+            if (n_pass >= 2) free_sync(q & 1u);          // pass n_pass - 2 (q is already one past the last pass)
+            free_sync((q + 1u) & 1u);                    // pass n_pass - 1
+            cn += (uint32_t)chunks;
+        }
+    } else {
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+        const long long row = (long long)tile * 128 + r128;
+        const bool row_ok = row < n_rows;
+        float mean = 0.f, rstd = 1.f;
+        if (K == 0 && g.stats && row_ok) {
+            mean = __ldg(g.stats + 2 * row);
+            rstd = __ldg(g.stats + 2 * row + 1);
+        }
+        // ---- A = this row of dY, split into bf16 hi / lo, into tensor memory (lane = row); the two warpgroups take alternate
+        // 8-column groups
+        const float* dyr = dy + (row_ok ? row : 0) * ld_dy;
+        tc::mbar_wait(bar_dy, tcount & 1u);
+        {
+            float4 qv[4][2];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int kc = wg + 2 * j;
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (dy_vec) {                           // staged by the control warp
+                    const float* ds = d_st + r128 * dld + kc * 8;
+                    qv[j][0] = kc < kcs ? *reinterpret_cast<const float4*>(ds) : z;
+                    qv[j][1] = kc < kcs ? *reinterpret_cast<const float4*>(ds + 4) : z;
+                } else {
+                    float v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int o = kc * 8 + i;
+                        v[i] = (row_ok && kc < kcs && o < g.out_f) ? __ldg(dyr + o) : 0.f;
+                    }
+                    qv[j][0] = make_float4(v[0], v[1], v[2], v[3]);
+                    qv[j][1] = make_float4(v[4], v[5], v[6], v[7]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int kc = wg + 2 * j;
+                if (kc < kcs) {
+                    const float v[8] = {qv[j][0].x, qv[j][0].y, qv[j][0].z, qv[j][0].w, qv[j][1].x, qv[j][1].y, qv[j][1].z, qv[j][1].w};
+                    uint4 hi, lo;
+                    tc::split8(v, hi, lo);
+                    tc::tmem_st4(tmem_base + lane_base + kLookA + 4u * kc, hi.x, hi.y, hi.z, hi.w);
+                    tc::tmem_st4(tmem_base + lane_base + kLookA + (uint32_t)KK / 2 + 4u * kc, lo.x, lo.y, lo.z, lo.w);
+                }
+            }
+        }
+        tc::tmem_st_wait();
+        tc::tc_fence_before_sync();
+        named_arrive<3, kLookThreads>();
+        const float* xr = x + (row_ok ? row : 0) * ldx;
+        auto load_x4 = [&](int fs, float (&o)[4]) {     // this thread's four x values of a pass: one 16-byte load when the rows allow it
+            if (x_vec) {
+                const float4 v = (row_ok && fs < g.in_f) ? __ldg(reinterpret_cast<const float4*>(xr + fs)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                o[0] = v.x;
+                o[1] = v.y;
+                o[2] = v.z;
+                o[3] = v.w;
+            } else {
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii) o[ii] = (row_ok && fs + ii < g.in_f) ? __ldg(xr + fs + ii) : 0.f;
+            }
+        };
+        float xq[4];
+        load_x4(4 * wg, xq);
+        for (int pass = 0; pass < n_pass; ++pass, ++q) {
+            const int f0 = pass * kFPL;
+            float xn[4] = {0.f, 0.f, 0.f, 0.f};
+            if (pass + 1 < n_pass) load_x4(f0 + kFPL + 4 * wg, xn);
+            tc::mbar_wait(&bar_t[q & 1u], (q >> 1) & 1u);
+            tc::tc_fence_after_sync();
+            // ---- epilogue: warpgroup wg contracts features 4 wg .. 4 wg + 3 of the pass for its 128 rows
+            const uint32_t tb = tmem_base + lane_base + (q & 1u) * kLookT;
+            float res[4], resb[4], tbase[8];
+            tc::tmem_ld8(tb + kLookBase + 8u * (uint32_t)(pass & 1), tbase);
+#pragma unroll
+            for (int ii = 0; ii < 4; ++ii) {
+                const int i = 4 * wg + ii, f = f0 + i;
+                res[ii] = 0.f;
+                resb[ii] = 0.f;
+                if (f < g.in_f) {                       // uniform over the warpgroup
+                    float t[8];
+                    tc::tmem_ld8(tb + (uint32_t)(8 * i), t);
+                    const float xv = xq[ii];
+                    float a = 0.f;
+                    if (K == 0) {
+                        const float z = rbf_z_b(g, xv, mean, rstd, f);
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const float tt = (z - (g.c0 + (float)c * g.step)) * g.inv_den;
+                            const float dq = -2.0f * tt * g.inv_den * ex2_b(-kLog2eB * tt * tt);
+                            a = fmaf((c < g.S) ? dq : 0.f, t[c], a);
+                        }
+                    } else {
+                        int idx;
+                        float fr, d[4];
+                        locate_b(g, xv, idx, fr);
+                        local_derivs_b<(K == 0 ? 1 : K)>(fr, g.inv_h, d);
+                        const int j = idx - 1;              // interval; its bases sit on slots j - K .. j
+                        const bool live = j >= 0 && j < g.G + 2 * K;
+                        float tp[20];
+#pragma unroll
+                        for (int c = 0; c < 20; ++c) tp[c] = 0.f;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                            if (c < kS1MaxB - 1) tp[K + c] = (c < g.S) ? t[c] : 0.f;
+                        const int jj = live ? j : 0;
+                        float s0[12], s1[8], s2[6], s3[4];
+#pragma unroll
+                        for (int c = 0; c < 12; ++c) s0[c] = (jj & 8) ? tp[c + 8] : tp[c];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) s1[c] = (jj & 4) ? s0[c + 4] : s0[c];
+#pragma unroll
+                        for (int c = 0; c < 6; ++c) s2[c] = (jj & 2) ? s1[c + 2] : s1[c];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) s3[c] = (jj & 1) ? s2[c + 1] : s2[c];
+#pragma unroll
+                        for (int r = 0; r <= K; ++r) a = fmaf(d[r], s3[r], a);
+                        if (!live) a = 0.f;
+                    }
+                    const float sg = __fdividef(1.0f, 1.0f + ex2_b(-kLog2eB * xv));
+                    const float dbase = sg * fmaf(xv, 1.0f - sg, 1.0f);
+                    const float tbv = wg ? tbase[4 + ii] : tbase[ii];
+                    if (K == 0 && dxb) {                    // with a LayerNorm the two branches stay separate (kagnn_layernorm_bwd joins them)
+                        res[ii] = a;
+                        resb[ii] = dbase * tbv;
+                    } else {
+                        res[ii] = fmaf(dbase, tbv, a);
+                    }
+                }
+            }
+            if (row_ok) {
+                float* dxr = dx + row * ld_dx + f0 + 4 * wg;
+                if (dx_vec && f0 + 4 * wg + 4 <= g.in_f) {
+                    *reinterpret_cast<float4*>(dxr) = make_float4(res[0], res[1], res[2], res[3]);
+                } else {
+#pragma unroll
+                    for (int ii = 0; ii < 4; ++ii)
+                        if (f0 + 4 * wg + ii < g.in_f) dxr[ii] = res[ii];
+                }
+                if (K == 0 && dxb) {
+                    float* br = dxb + row * ld_dxb + f0 + 4 * wg;
+#pragma unroll
+                    for (int ii = 0; ii < 4; ++ii)
+                        if (f0 + 4 * wg + ii < g.in_f) br[ii] = resb[ii];
+                }
+            }
+#pragma unroll
+            for (int ii = 0; ii < 4; ++ii) xq[ii] = xn[ii];
+            // this T buffer is free again (the control warp issues the pass after next into it)
+            tc::tc_fence_before_sync();
+            if (q & 1u) named_arrive<2, kLookSync>();
+            else named_arrive<1, kLookSync>();
+        }
+        // (the next tile's A may land at once: this thread has seen every pass of the tile complete)
+    }
     }
     tc::tc_fence_before_sync();
     __syncthreads();
@@ -892,18 +1224,6 @@ constexpr int kMThreads = kMSync + kMLoaders;
 constexpr int kMStages = 3;
 constexpr int kMXld = kMBlocks * kFB + 4;                    // staged x row: up to 112 values + 2 of alignment slack, 16-byte rows
 
-template <int ID, int COUNT>
-__device__ __forceinline__ void named_arrive() { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(COUNT) : "memory"); }
-template <int ID, int COUNT>
-__device__ __forceinline__ void named_sync() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory"); }
-__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, bool on) {
-    const uint32_t n = on ? 16u : 0u;                        // src-size 0: the destination is zero-filled, nothing is read
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tc::smem_u32(dst_smem)), "l"(src), "r"(n) : "memory");
-}
-// the mbarrier gets one arrival from this thread once all its earlier cp.async copies have landed
-__device__ __forceinline__ void cp_async_arrive_on(uint64_t* bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
@@ -928,7 +1248,8 @@ template <int K, int ROWS>
 __global__ void __launch_bounds__(kMThreads, 1) kan_bwd_weights_tcm_kernel(GeomB g, const float* __restrict__ x, long long ldx,
                                                                              const float* __restrict__ dy, long long ld_dy, long long n_rows,
                                                                              long long rows_per_slab, int N16, int fblocks,
-                                                                             int blocks_per_pass, uint32_t tmem_cols, float* __restrict__ dP) {
+                                                                             int blocks_per_pass, uint32_t tmem_cols, int x16, int dy16,
+                                                                             float* __restrict__ dP) {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr uint32_t kUnit = (uint32_t)ROWS * 16u;         // one unit of 8 M (or N) elements x ROWS rows
     constexpr uint32_t kAStage = 2u * 16u * kUnit;           // hi + lo of one E^T operand
@@ -952,9 +1273,10 @@ __global__ void __launch_bounds__(kMThreads, 1) kan_bwd_weights_tcm_kernel(GeomB
     const bool control = warp == kMProducers / 32, loader = tid >= kMSync;
     const int fb0 = blockIdx.x * blocks_per_pass, nb = min(blocks_per_pass, fblocks - fb0);
     const long long r_beg = (long long)blockIdx.y * rows_per_slab, r_end = min(n_rows, r_beg + rows_per_slab);
-    // staged x columns [xc0, xc0 + xcols): the pass's features, widened to 16-byte boundaries (in_f is a multiple of 4 here)
-    const int xc0 = (fb0 * kFB) & ~3, xoff = fb0 * kFB - xc0;
-    const int xcols = min((xoff + nb * kFB + 3) & ~3, g.in_f - xc0);
+    // staged x columns [xc0, xc0 + xcols): the pass's features; with 16-byte aligned rows (x16: in_f and the row stride are
+    // multiples of 4) widened to 16-byte boundaries and copied 16 bytes at a time, else exactly those and 4 bytes at a time
+    const int xc0 = x16 ? (fb0 * kFB) & ~3 : fb0 * kFB, xoff = fb0 * kFB - xc0;
+    const int xcols = min(x16 ? (xoff + nb * kFB + 3) & ~3 : nb * kFB, g.in_f - xc0);
 
     if (control) {
         tc::tmem_alloc(tmem_slot, tmem_cols);
@@ -1015,36 +1337,43 @@ __global__ void __launch_bounds__(kMThreads, 1) kan_bwd_weights_tcm_kernel(GeomB
     } else if (loader) {
         // ===================================================== loaders =====================================================
         const int lt = tid - kMSync;
-        const int xc4 = xcols >> 2, dc4 = g.out_f >> 2;
-        const int xq = kMLoaders / xc4, xr = kMLoaders - xq * xc4, dq = kMLoaders / dc4, dr = kMLoaders - dq * dc4;
+        // (row, chunk) pairs, consecutive lanes along the row; e -> e + 128 advances (r, c) by (q, rem) with one carry.  The dY
+        // tile is staged N16 wide: the columns from out_f on are zero-filled (they become zero columns of the operand).
+        const int xsh = x16 ? 2 : 0, dsh = dy16 ? 2 : 0;
+        const int xcn = (xcols + (1 << xsh) - 1) >> xsh, dcn = N16 >> dsh;
+        const int xq = kMLoaders / xcn, xr = kMLoaders - xq * xcn, dq = kMLoaders / dcn, dr = kMLoaders - dq * dcn;
         long long t = 0;
         for (long long rt = r_beg; rt < r_end; rt += ROWS, ++t) {
             const int buf = (int)(t & 1);
             if (t >= 2) tc::mbar_wait(&bar_free[buf], (uint32_t)((t >> 1) - 1) & 1u);
             float* xs = x_st + (size_t)buf * ROWS * kMXld;
             float* ds = d_st + (size_t)buf * ROWS * dld;
-            {   // (row, 16-byte column) pairs, consecutive lanes along the row; e -> e + 128 advances (r, c) by (xq, xr) with one carry
-                int r = lt / xc4, c = lt - r * xc4;
+            {
+                int r = lt / xcn, c = lt - r * xcn;
                 while (r < ROWS) {
                     const bool on = rt + r < r_end;
-                    cp_async16(xs + r * kMXld + 4 * c, on ? x + (rt + r) * ldx + xc0 + 4 * c : x, on);
+                    const float* src = on ? x + (rt + r) * ldx + xc0 + (c << xsh) : x;
+                    if (x16) cp_async16(xs + r * kMXld + 4 * c, src, on);
+                    else cp_async_f32(xs + r * kMXld + c, src, on);
                     r += xq;
                     c += xr;
-                    if (c >= xc4) {
-                        c -= xc4;
+                    if (c >= xcn) {
+                        c -= xcn;
                         ++r;
                     }
                 }
             }
             {
-                int r = lt / dc4, c = lt - r * dc4;
+                int r = lt / dcn, c = lt - r * dcn;
                 while (r < ROWS) {
-                    const bool on = rt + r < r_end;
-                    cp_async16(ds + r * dld + 4 * c, on ? dy + (rt + r) * ld_dy + 4 * c : dy, on);
+                    const bool on = rt + r < r_end && (c << dsh) < g.out_f;
+                    const float* src = on ? dy + (rt + r) * ld_dy + (c << dsh) : dy;
+                    if (dy16) cp_async16(ds + r * dld + 4 * c, src, on);
+                    else cp_async_f32(ds + r * dld + c, src, on);
                     r += dq;
                     c += dr;
-                    if (c >= dc4) {
-                        c -= dc4;
+                    if (c >= dcn) {
+                        c -= dcn;
                         ++r;
                     }
                 }
@@ -1069,9 +1398,7 @@ __global__ void __launch_bounds__(kMThreads, 1) kan_bwd_weights_tcm_kernel(GeomB
             if (t >= 2) tc::mbar_wait(&bar_batch[bbuf], (uint32_t)((t >> 1) - 1) & 1u);   // the MMAs that read this B buffer are done
             for (int u = part; u < nu; u += kParts) {            // this thread's 8-column units of dY
                 const float* dr = d_st + ((size_t)bbuf * ROWS + r64) * dld + 8 * u;
-                float4 d0 = make_float4(0.f, 0.f, 0.f, 0.f), d1 = d0;
-                if (row_ok && 8 * u + 4 <= g.out_f) d0 = *reinterpret_cast<const float4*>(dr);
-                if (row_ok && 8 * u + 8 <= g.out_f) d1 = *reinterpret_cast<const float4*>(dr + 4);
+                const float4 d0 = *reinterpret_cast<const float4*>(dr), d1 = *reinterpret_cast<const float4*>(dr + 4);   // zero outside the matrix
                 const float v[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
                 uint4 hi, lo;
                 tc::split8(v, hi, lo);
@@ -1162,7 +1489,7 @@ __global__ void __launch_bounds__(kMThreads, 1) kan_bwd_weights_tcm_kernel(GeomB
                 float v[8], w[8];
                 tc::tmem_ld8(tmem_base + lane_base + (uint32_t)(b * N16 + o0), v);   // warp-collective: every lane takes part
                 tc::tmem_ld8(tmem_base + lane_base + (uint32_t)(b * N16 + o1), w);
-                if (dst >= 0) {                             // out_f is a multiple of 4 here: a 4-vector is inside or outside as a whole
+                if (dst >= 0) {                             // a 4-vector that straddles out_f adds zeros to the row's pad columns (out_pad = pad4(out_f))
                     if (o0 < g.out_f) red_add_v4(dP + dst + o0, v[0], v[1], v[2], v[3]);
                     if (o0 + 4 < g.out_f) red_add_v4(dP + dst + o0 + 4, v[4], v[5], v[6], v[7]);
                     if (o1 < g.out_f) red_add_v4(dP + dst + o1, w[0], w[1], w[2], w[3]);
@@ -1200,7 +1527,7 @@ std::atomic<int> g_dx_packed{1};        // dX reads the forward's packed weights
 extern "C" int kagnn_set_backward_path(int32_t mode) {
     if (mode < 0 || mode > 3) return KAGNN_EINVAL;      // 2, 3 = tensor cores with the alternative kernels (tests): see the header
     g_bwd_path.store(mode == 1 ? 1 : 0);
-    g_dx_packed.store(mode == 2 ? 0 : 1);
+    g_dx_packed.store(mode == 2 ? 0 : (mode == 3 ? 2 : 1));      // 2 = packed operand, no look-ahead
     g_dw_rows64.store(mode == 2 ? 0 : (mode == 3 ? 2 : 1));
     return KAGNN_OK;
 }
@@ -1233,6 +1560,17 @@ int launch_bwd_input_tc(const GeomB& g, const float* w, const void* wtc, const f
     if (per_sm > 4) per_sm = 4;
     if (per_sm < 1) per_sm = 1;
     const int grid = n_tiles < props.num_sms * per_sm ? n_tiles : props.num_sms * per_sm;
+    if (packed && K <= 64 && g_dx_packed.load() == 1) {
+        // narrow layers: passes of eight features with look-ahead (two T buffers), 256 columns of tensor memory, two CTAs per SM
+        const size_t smem_l = (size_t)2 * 576 * K + 128 + (size_t)128 * (K + 4) * sizeof(float);
+        const int grid_l = n_tiles < props.num_sms * 2 ? n_tiles : props.num_sms * 2;
+        auto kl = g.k == 3 ? kan_bwd_input_tc_look_kernel<3> : (g.k == 2 ? kan_bwd_input_tc_look_kernel<2> : (g.k == 1 ? kan_bwd_input_tc_look_kernel<1> : kan_bwd_input_tc_look_kernel<0>));
+        KAGNN_CUDA_TRY(cudaFuncSetAttribute(kl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)props.max_smem));
+        kl<<<(unsigned)grid_l, kLookThreads, smem_l, stream>>>(g, static_cast<const uint8_t*>(wtc), x, (long long)ldx, dy, (long long)ld_dy, (long long)num_rows,
+                                                          n_tiles, K, 256u, dx, (long long)ld_dx, dxb, (long long)ld_dxb);
+        KAGNN_LAUNCH_CHECK();
+        return KAGNN_OK;
+    }
     void (*kern)(GeomB, const float*, const uint8_t*, int, const float*, long long, const float*, long long, long long, int, int, uint32_t,
                  float*, long long, float*, long long);
     if (packed)
@@ -1271,9 +1609,9 @@ int launch_bwd_weights_tc(const GeomB& g, const float* x, int64_t ldx, const flo
     if (const char* e = getenv("KAGNN_DEBUG_DW_SWAP")) swap = atoi(e);
 #endif
     const bool dy_vec = g.out_f % 4 == 0 && ld_dy % 4 == 0 && aligned16(dy);
-    const bool x_vec = g.in_f % 4 == 0 && ldx % 4 == 0 && aligned16(x);
+    const bool x_vec = g.in_f % 4 == 0 && ldx % 4 == 0 && aligned16(x);            // rows start on 16-byte boundaries
     const int dw_mode = g_dw_rows64.load();                   // 1 = default, 2 / 0 = the alternative kernels (kagnn_set_backward_path 3 / 2)
-    if (dw_mode == 1 && dy_vec && x_vec && g.out_pad % 4 == 0 && aligned16(d_packed)) {
+    if (dw_mode == 1 && g.out_pad % 4 == 0 && aligned16(d_packed)) {
         // several feature blocks per CTA (as many accumulators as tensor memory holds) share one split of the dY batch;
         // 64-row batches for layers up to 64 wide, 32-row batches above (the dY operand of a batch is N16 x rows x 4 bytes)
         const bool narrow = N16 <= 64;
@@ -1292,12 +1630,13 @@ int launch_bwd_weights_tc(const GeomB& g, const float* x, int64_t ldx, const flo
         if (slabs_m < 1) slabs_m = 1;
         int64_t rps_m = ceil_div64(ceil_div64(num_rows, slabs_m), 64) * 64;
         slabs_m = ceil_div64(num_rows, rps_m);
-        if (smem_m <= (size_t)props.max_smem && cols_m <= 512) {
+        // (a wide layer with a single feature block has nothing to share the dY split with: the 128-row kernel below is faster)
+        if (smem_m <= (size_t)props.max_smem && cols_m <= 512 && (narrow || fblocks >= 2)) {
             auto km = narrow ? (g.k == 3 ? kan_bwd_weights_tcm_kernel<3, 64> : (g.k == 2 ? kan_bwd_weights_tcm_kernel<2, 64> : (g.k == 1 ? kan_bwd_weights_tcm_kernel<1, 64> : kan_bwd_weights_tcm_kernel<0, 64>)))
                              : (g.k == 3 ? kan_bwd_weights_tcm_kernel<3, 32> : (g.k == 2 ? kan_bwd_weights_tcm_kernel<2, 32> : (g.k == 1 ? kan_bwd_weights_tcm_kernel<1, 32> : kan_bwd_weights_tcm_kernel<0, 32>)));
             KAGNN_CUDA_TRY(cudaFuncSetAttribute(km, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)props.max_smem));
             km<<<dim3((unsigned)passes, (unsigned)slabs_m, 1), kMThreads, smem_m, stream>>>(g, x, (long long)ldx, dy, (long long)ld_dy,
-                                                                                            (long long)num_rows, (long long)rps_m, N16, fblocks, bpp, cols_m, d_packed);
+                                                                                            (long long)num_rows, (long long)rps_m, N16, fblocks, bpp, cols_m, x_vec ? 1 : 0, dy_vec ? 1 : 0, d_packed);
             KAGNN_LAUNCH_CHECK();
             return KAGNN_OK;
         }

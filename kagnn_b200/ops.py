@@ -22,10 +22,16 @@ launch_count = 0
 fused_timing = None
 
 
+# torch.cuda.current_stream() builds a Stream object through three Python layers (17 us a call, a seventh of the host time of a
+# training step); the raw handle is one C call
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None) or (lambda dev: torch.cuda.current_stream(dev).cuda_stream)
+_current_device = getattr(torch._C, "_cuda_getDevice", None) or torch.cuda.current_device
+
+
 def _stream() -> C.c_void_p:
     """Current stream of the current device; every public op below runs under ``_on_device``, which makes the device of
     its tensor arguments the current one first (the library launches on cudaGetDevice and never switches devices itself)."""
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(_raw_stream(_current_device()))
 
 
 def _devices_of(obj, found: set) -> None:
@@ -65,7 +71,7 @@ def _on_device(fn):
         _devices_of(tuple(kwargs.values()), found)
         if len(found) > 1:
             raise RuntimeError(f"kagnn_b200.{fn.__name__}: tensor arguments live on different CUDA devices {sorted(found)}")
-        if not found or next(iter(found)) == torch.cuda.current_device():
+        if not found or next(iter(found)) == _current_device():
             return fn(*args, **kwargs)
         with torch.cuda.device(next(iter(found))):
             return fn(*args, **kwargs)

@@ -50,14 +50,15 @@ def test_tc_gradients_match_fp32_kernels_and_autograd(rows, in_f, out_f, G, k):
     ops.set_backward_path(2)                                         # d input without the packed-weight operand
     try:
         dx_tc2, dp_tc2 = ops.kan_bwd_input(spec, xd, dyd), ops.kan_bwd_weights(spec, xd, dyd)
-        ops.set_backward_path(3)                                     # d weights: one feature block per CTA
-        dp_tc3 = ops.kan_bwd_weights(spec, xd, dyd)
+        ops.set_backward_path(3)                                     # d weights: one feature block per CTA; d input: no look-ahead
+        dp_tc3, dx_tc3 = ops.kan_bwd_weights(spec, xd, dyd), ops.kan_bwd_input(spec, xd, dyd)
         ops.set_backward_path(1)
         dx_32, dp_32 = ops.kan_bwd_input(spec, xd, dyd), ops.kan_bwd_weights(spec, xd, dyd)
     finally:
         ops.set_backward_path(0)
     assert K.rel_err(dx_tc.cpu(), dx_32.cpu()) <= TOL_PATHS
     assert K.rel_err(dx_tc2.cpu(), dx_32.cpu()) <= TOL_PATHS
+    assert K.rel_err(dx_tc3.cpu(), dx_32.cpu()) <= TOL_PATHS
     assert K.rel_err(dp_tc.cpu(), dp_32.cpu()) <= TOL_PATHS
     assert K.rel_err(dp_tc2.cpu(), dp_32.cpu()) <= TOL_PATHS
     assert K.rel_err(dp_tc3.cpu(), dp_32.cpu()) <= TOL_PATHS
@@ -128,6 +129,7 @@ def test_tc_gradients_of_the_fastkan_layer_match_the_fp32_kernels(rows, in_f, ou
         dp_tc2 = ops.rbf_bwd_weights(spec, x, stats, dy)
         ops.set_backward_path(3)
         dp_tc3 = ops.rbf_bwd_weights(spec, x, stats, dy)
+        dz_tc3, _ = ops.rbf_bwd_input(spec, x, stats, dy)
         ops.set_backward_path(1)
         dz_32, dxb_32 = ops.rbf_bwd_input(spec, x, stats, dy)
         dp_32 = ops.rbf_bwd_weights(spec, x, stats, dy)
@@ -135,6 +137,7 @@ def test_tc_gradients_of_the_fastkan_layer_match_the_fp32_kernels(rows, in_f, ou
         ops.set_backward_path(0)
     assert K.rel_err(dz_tc.cpu(), dz_32.cpu()) <= TOL_PATHS
     assert K.rel_err(dz_tc2.cpu(), dz_32.cpu()) <= TOL_PATHS
+    assert K.rel_err(dz_tc3.cpu(), dz_32.cpu()) <= TOL_PATHS
     assert K.rel_err(dp_tc.cpu(), dp_32.cpu()) <= TOL_PATHS
     assert K.rel_err(dp_tc2.cpu(), dp_32.cpu()) <= TOL_PATHS
     assert K.rel_err(dp_tc3.cpu(), dp_32.cpu()) <= TOL_PATHS
