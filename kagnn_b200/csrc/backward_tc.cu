@@ -6,8 +6,8 @@
 //   dX   dx[n,i] = sum_c D[n,i,c] T[n,(i,c)],   T = dY . P^T          D = d/dx of (B_0..B_{S-1}, silu)(x[n,i])
 //        One GEMM per 128-row tile and pass of 16 features: M = 128 rows, K = out, N = 16 (S+1).  A = the dY tile, split and
 //        written to tensor memory by its own rows (thread = row = TMEM lane, exactly the forward's A path); B = the 16 (S+1)
-//        weight rows of the pass, split on the fly from the fp32 packed weights into the K-major canonical layout in shared
-//        memory (no pre-packed copy, no workspace); the epilogue reads the (S+1) dot products of a (row, feature) back from
+//        weight rows of the pass: the layer's tensor-core packing read as an MN-major operand (see PACKED below), or split on
+//        the fly from the fp32 packed weights into the K-major canonical layout in shared memory; the epilogue reads the (S+1) dot products of a (row, feature) back from
 //        tensor memory and contracts them with the derivative vector it evaluates -- the (N, in (S+1)) intermediate never
 //        reaches HBM.
 //   dW   dP[(i,c),o] = sum_n E[n,(i,c)] dY[n,o]                        E = the S + 1 function values
@@ -17,8 +17,18 @@
 //        accumulator stays in tensor memory across all row tiles of a slab and is added to HBM once (one float atomic per
 //        element and slab).  Needs S <= 8 (every configuration the forward's pipelined kernel takes).
 //
-// Both kernels are small (128 threads, no warp specialisation): two or three CTAs share an SM and overlap each other's phases.
-// Shapes outside their limits return KAGNN_EUNSUPPORTED and the caller continues with backward_tiled.cu.
+// Kernels in this file (kagnn_set_backward_path picks between the variants for the tests):
+//   kan_bwd_input_tc_look_kernel   dX, layers up to 64 wide with the packed-weight operand (default there): passes of eight
+//                                  features, two T buffers, 8 worker warps + a control warp (weight loads, MMA issue one pass
+//                                  ahead) + a loader warp (next tile's dY rows by cp.async)
+//   kan_bwd_input_tc_kernel        dX, every other shape: 256 threads, phases one after the other, two CTAs per SM overlap each
+//                                  other; B from the packed weights (bulk copies) or split per tile from the fp32 weights
+//   kan_bwd_weights_tcm_kernel     dW (default): one CTA per SM, 16 producer warps + control warp + 4 loader warps, as many feature
+//                                  blocks per CTA as tensor memory has accumulators for, batches of 64 rows (<= 64 wide) or 32 rows
+//   kan_bwd_weights_tc64_kernel    dW, <= 64 wide, one feature block per CTA, 64-row batches, three CTAs per SM
+//   kan_bwd_weights_tc_kernel      dW, one feature block per CTA, 128-row batches (also: a wide layer with a single feature block)
+// The K = 0 instantiations are the FastKAN (RBF) layer.  Shapes outside the limits return KAGNN_EUNSUPPORTED and the caller
+// continues with backward_tiled.cu.
 #include <atomic>
 #include <cstdlib>
 
