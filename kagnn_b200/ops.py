@@ -59,6 +59,18 @@ def _devices_of(obj, found: set) -> None:
             _devices_of(t, found)
 
 
+_n_devices = None
+
+
+def _single_device() -> bool:
+    global _n_devices
+    if _n_devices is None:
+        if not torch.cuda.is_initialized():
+            return False                           # not known yet (and nothing launched so far): take the full check
+        _n_devices = torch.cuda.device_count()
+    return _n_devices == 1
+
+
 def _on_device(fn):
     """Device guard of a launch wrapper (what ATen ops do implicitly): all CUDA tensor arguments -- also inside the AggSpec /
     KanLayerSpec / Affine / CSR records and BatchNorm modules -- must live on ONE device, and that device is made current for
@@ -66,6 +78,8 @@ def _on_device(fn):
     happened to be current."""
     @functools.wraps(fn)
     def guarded(*args, **kwargs):
+        if _single_device():                      # one visible GPU: every CUDA tensor lives on it and it is current
+            return fn(*args, **kwargs)
         found: set = set()
         _devices_of(args, found)
         _devices_of(tuple(kwargs.values()), found)
