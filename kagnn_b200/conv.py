@@ -90,7 +90,7 @@ class GCNConv(_MessagePassing):
         return ops.fused_layer(agg, graph.num_nodes, [], pre=pre, agg_out=out)
 
     def forward(self, x: Tensor, edge_index, edge_weight: Optional[Tensor] = None) -> Tensor:
-        needs_grad = _module_backend_guard(x, list(self.parameters()), grad_ok=True)
+        needs_grad = _module_backend_guard(x, self.parameters(), grad_ok=True)
         g = self._graph(x, edge_index)
         if needs_grad:
             if edge_weight is not None:
@@ -132,7 +132,7 @@ class GINConv(_MessagePassing):
 
     def forward(self, x: Tensor, edge_index, size=None, out: Optional[Tensor] = None,
                 post: Optional[ops.Affine] = None, **agg_kw) -> Tensor:
-        needs_grad = _module_backend_guard(x, list(self.parameters()), grad_ok=True)
+        needs_grad = _module_backend_guard(x, self.parameters(), grad_ok=True)
         g = self._graph(x, edge_index)
         if needs_grad:
             if post is not None or out is not None or agg_kw:
@@ -279,7 +279,7 @@ class GATConv(_MessagePassing):
                 extra: Optional[ops.Affine] = None) -> Tensor:
         if edge_attr is not None:
             raise NotImplementedError("edge_dim is never used by the reference")
-        needs_grad = _module_backend_guard(x, list(self.parameters()), grad_ok=True)
+        needs_grad = _module_backend_guard(x, self.parameters(), grad_ok=True)
         g = self._graph(x, edge_index)
         if needs_grad:
             # training: projection (its own autograd Function) -> attention + aggregation with a library backward; the callers'

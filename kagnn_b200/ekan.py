@@ -13,7 +13,7 @@ reference driver and are not provided.
 from __future__ import annotations
 
 import math
-from typing import List, Optional, Sequence
+from typing import Iterable, List, Optional, Sequence
 
 import torch
 from torch import nn
@@ -53,7 +53,7 @@ def _uniform_bspline_design(x: Tensor, t0: float, h: float, grid_size: int, orde
     return out
 
 
-def _module_backend_guard(x: Tensor, params: Sequence[Tensor], grad_ok: bool = False) -> bool:
+def _module_backend_guard(x: Tensor, params: Iterable[Tensor], grad_ok: bool = False) -> bool:
     """Raises for CPU inputs (no fallback).  Returns True when autograd must record this call: modules that have a backward
     (``grad_ok``) then take their ``kagnn_b200.autograd`` path; a caller that cannot be differentiated passes False and raises."""
     if not x.is_cuda:
@@ -206,7 +206,7 @@ class KAN(nn.Module):
     def forward(self, x: Tensor, update_grid: bool = False) -> Tensor:
         if update_grid:
             raise NotImplementedError("update_grid is never used by the reference drivers and is not implemented")
-        if _module_backend_guard(x, list(self.parameters()), grad_ok=True):
+        if _module_backend_guard(x, self.parameters(), grad_ok=True):
             for layer in self.layers:               # one launch per layer: every layer's input is kept for its backward
                 x = layer(x)
             return x

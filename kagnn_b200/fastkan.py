@@ -65,6 +65,24 @@ class FastKANLayer(nn.Module):
             self.base_linear = nn.Linear(input_dim, output_dim)
         self._cache_key = None
         self._cache_spec: Optional[ops.KanLayerSpec] = None
+        self._grid_key = None
+        self._grid_vals = None
+
+    def _grid_params(self):
+        """(G, first centre, spacing) of the frozen centre vector, read back (three device round trips) only when IT changes:
+        the weights change every training step and must not pay for that."""
+        g = self.rbf.grid.detach()
+        key = (g.data_ptr(), g._version, g.device)
+        if key != self._grid_key:
+            G = g.numel()
+            gmin = float(g[0])
+            step = float((g[-1].double() - g[0].double()) / (G - 1)) if G > 1 else 1.0
+            if G > 2:
+                ideal = (gmin + step * torch.arange(G, device=g.device, dtype=torch.float64)).to(torch.float32)
+                if float((g - ideal).abs().max()) > 1e-4 * abs(step):
+                    raise NotImplementedError("non-uniform RBF centres are not supported by the sm_100a path")
+            self._grid_key, self._grid_vals = key, (G, gmin, step)
+        return self._grid_vals
 
     def kernel_spec(self) -> ops.KanLayerSpec:
         ps = [self.spline_linear.weight, self.rbf.grid]
@@ -74,14 +92,7 @@ class FastKANLayer(nn.Module):
             ps += [self.layernorm.weight, self.layernorm.bias]
         key = tuple((p.data_ptr(), p._version) for p in ps)
         if key != self._cache_key:
-            g = self.rbf.grid.detach()
-            G = g.numel()
-            gmin = float(g[0])
-            step = float((g[-1].double() - g[0].double()) / (G - 1)) if G > 1 else 1.0
-            if G > 2:
-                ideal = (gmin + step * torch.arange(G, device=g.device, dtype=torch.float64)).to(torch.float32)
-                if float((g - ideal).abs().max()) > 1e-4 * abs(step):
-                    raise NotImplementedError("non-uniform RBF centres are not supported by the sm_100a path")
+            G, gmin, step = self._grid_params()
             packed = ops.pack_kan_weights(self.base_linear.weight if self.use_base_update else None,
                                           self.spline_linear.weight, None, self.input_dim, self.output_dim, G)
             packed_tc = None
@@ -106,7 +117,7 @@ class FastKANLayer(nn.Module):
         if not use_layernorm and self.layernorm is not None:
             raise NotImplementedError("use_layernorm=False at call time is never used by the reference models")
         lead = x.shape[:-1]
-        if _module_backend_guard(x, list(self.parameters()), grad_ok=True):
+        if _module_backend_guard(x, self.parameters(), grad_ok=True):
             return autograd.fastkan_layer(self, x.reshape(-1, self.input_dim)).view(*lead, self.output_dim)
         y = ops.fused_layer(ops.AggSpec(L.AGG_NONE, x.reshape(-1, self.input_dim).to(torch.float32)),
                             x.numel() // self.input_dim, [self.kernel_spec()])
@@ -128,7 +139,7 @@ class FastKAN(nn.Module):
         return [lay.kernel_spec() for lay in self.layers]
 
     def forward(self, x: Tensor) -> Tensor:
-        if _module_backend_guard(x, list(self.parameters()), grad_ok=True):
+        if _module_backend_guard(x, self.parameters(), grad_ok=True):
             for layer in self.layers:               # one launch per layer: every layer's input is kept for its backward
                 x = layer(x)
             return x

@@ -80,7 +80,7 @@ class _GINGraphModel(nn.Module):
 
     def forward(self, data) -> Tensor:
         x = data.x
-        needs_grad = _module_backend_guard(x, list(self.parameters()), grad_ok=True)
+        needs_grad = _module_backend_guard(x, self.parameters(), grad_ok=True)
         if needs_grad and not self.training:
             return _eval_without_no_grad(self, data)
         x = x.to(torch.float32)
@@ -148,7 +148,7 @@ class _GCNGraphModel(nn.Module):
 
     def forward(self, data) -> Tensor:
         x = data.x
-        needs_grad = _module_backend_guard(x, list(self.parameters()), grad_ok=True)
+        needs_grad = _module_backend_guard(x, self.parameters(), grad_ok=True)
         if needs_grad and not self.training:
             return _eval_without_no_grad(self, data)
         x = self._encode(x)

@@ -142,7 +142,7 @@ class _NodeModel(nn.Module):
         return drop_off and all(bn_is_foldable(bn) for bn in self.bns)
 
     def forward(self, x: Tensor, edge_index: Tensor) -> Tensor:
-        needs_grad = _module_backend_guard(x, list(self.parameters()), grad_ok=True)
+        needs_grad = _module_backend_guard(x, self.parameters(), grad_ok=True)
         if needs_grad and not self.training:
             # model.eval() without torch.no_grad() (the reference's val()/test() loops of graph_classification_utils.py:57-72 do
             # that): the fused inference plan, result detached from autograd

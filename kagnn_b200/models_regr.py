@@ -83,7 +83,7 @@ class _GINERegression(_GINGraphModel):
 
     def forward(self, data) -> Tensor:
         x, edge_attr = data.x, data.edge_attr
-        needs_grad = _module_backend_guard(x, list(self.parameters()), grad_ok=True)
+        needs_grad = _module_backend_guard(x, self.parameters(), grad_ok=True)
         if needs_grad and not self.training:
             # eval() without no_grad (graph_regression/optuna_zinc.py:68-86): inference plan, result detached
             eval_mode_detach_notice(x)

@@ -43,6 +43,33 @@ def main():
             ts.append(a.elapsed_time(b))
         return statistics.median(ts)
 
+    if len(sys.argv) > 1 and sys.argv[1] == "--host-profile":
+        import cProfile
+        import io
+        import pstats
+        import time
+        from kagnn_b200 import ops as _ops
+        c0 = _ops.launch_count
+        step()
+        print("library launches per step", _ops.launch_count - c0, file=sys.stderr)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(20):
+            step()
+        t1 = time.perf_counter()
+        torch.cuda.synchronize()
+        print(f"enqueue {1e3 * (t1 - t0) / 20:.3f} ms/step, with drain {1e3 * (time.perf_counter() - t0) / 20:.3f} ms/step", file=sys.stderr)
+        pr = cProfile.Profile()
+        pr.enable()
+        for _ in range(20):
+            step()
+        pr.disable()
+        torch.cuda.synchronize()
+        for key in ("tottime", "cumtime"):
+            buf = io.StringIO()
+            pstats.Stats(pr, stream=buf).sort_stats(key).print_stats(40)
+            print(buf.getvalue()[:8000], file=sys.stderr)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "--kernels":
         from torch.profiler import profile, ProfilerActivity
         for _ in range(3):

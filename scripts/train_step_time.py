@@ -107,7 +107,18 @@ def main():
                 d[1] += (ev.time_range.end - ev.time_range.start) / 1e3
         for name, (cnt, ms) in sorted(tot.items(), key=lambda kv: -kv[1][1])[:25]:
             print(f"{ms:9.3f} ms  x{cnt:<3d} {name}", file=sys.stderr)
+    # steps back to back (no synchronisation between them: the host runs ahead of the device, as in a loop that reads the
+    # loss only every few steps)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(20):
+        step()
+    b.record()
+    torch.cuda.synchronize()
+    b2b_ms = a.elapsed_time(b) / 20
     print(json.dumps({"config": "arxiv-shaped GKAN_Nodes gin 3x64 grid 5, training step (fwd + bwd + Adam), batch-statistics BatchNorm",
+                      "train_step_ms_back_to_back": b2b_ms,
                       "nodes": n, "edges": e, "train_step_ms": t_step, "train_mode_forward_ms": t_fwd,
                       "nodes_per_s_training": n / t_step * 1e3, "library_launches_per_step": launches,
                       "host_enqueue_ms_per_step": host_ms, "train_step_ms_cuda_graph": graph_ms, "cuda_graph_error": graph_err,
