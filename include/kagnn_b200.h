@@ -249,6 +249,13 @@ int kagnn_tc_selftest(const float* A, const float* B, int32_t N, int32_t K, floa
 int kagnn_gather_rows(const float* x, int64_t ldx, const int32_t* index, int64_t num_rows, int32_t num_cols,
                       float* out, int64_t ld_out, void* stream);
 
+/* Input of a B-spline layer with more than eight coefficients per (in, out) pair (G + k in 9 .. 40), laid out for the tensor-core
+ * kernels: out[r, w*num_cols + c] = x[r, c] - w*shift, w = 0 .. windows-1.  Uniform B-splines are shift invariant
+ * (B_{8w+j}(x) = B_j(x - 8wh)), so such a layer (ekan.py:154-162 with grid_size + spline_order > 8) IS a layer with
+ * windows*in_features inputs, eight slots each and shift = 8h; the host side repacks the weights accordingly. */
+int kagnn_expand_windows(const float* x, int64_t ldx, int64_t num_rows, int32_t num_cols, int32_t windows, float shift,
+                         float* out, int64_t ld_out, void* stream);
+
 /* Halo pull over NVLink (node-sharded graphs): out[r,:] = row (ids[r] % rows_per_rank) of rank (ids[r] / rows_per_rank)'s
  * matrix, read in place through peer_x, a DEVICE array of peer-mapped base pointers (see KagnnAggregate.peer_x).  Replaces
  * pack + all-to-all: only the distinct remote rows cross the link, no send lists, no NCCL.  16-byte aligned, cols % 4 == 0. */

@@ -55,7 +55,10 @@ class _KanLinearFn(torch.autograd.Function):
         d_base = d_spline = d_scaler = None
         if any(ctx.needs_input_grad[1:4]):
             d_packed = ops.kan_bwd_weights(ctx.spec, x, dy)
-            d_base, d_spline, d_scaler = ops.kan_unpack_weight_grads(d_packed, spline_w, scaler)
+            if ctx.spec.windows > 1:
+                d_base, d_spline, d_scaler = ops.kan_unpack_windowed_grads(d_packed, ctx.spec, spline_w.size(2))
+            else:
+                d_base, d_spline, d_scaler = ops.kan_unpack_weight_grads(d_packed, spline_w, scaler)
         return dx, d_base, d_spline, d_scaler, None
 
 

@@ -334,6 +334,35 @@ extern "C" int kagnn_gather_rows(const float* x, int64_t ldx, const int32_t* ind
     return KAGNN_OK;
 }
 
+// out[r, w * cols + c] = x[r, c] - w * shift  (w = 0 .. windows-1): the input of a B-spline layer with more than eight slots per
+// feature, laid out as `windows` virtual features of eight slots each (uniform B-splines are shift invariant:
+// B_{8 w + j}(x) = B_j(x - 8 w h); kagnn_b200/ekan.py: KANLinear.kernel_spec)
+__global__ void expand_windows_kernel(const float* __restrict__ x, long long ldx, long long rows, int cols, int windows, float shift,
+                                      float* __restrict__ out, long long ld_out) {
+    const long long total = rows * (long long)cols;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long r = e / cols;
+        const int c = (int)(e - r * cols);
+        const float v = __ldg(x + r * ldx + c);
+        float* o = out + r * ld_out + c;
+        for (int w = 0; w < windows; ++w) o[(long long)w * cols] = v - (float)w * shift;
+    }
+}
+
+extern "C" int kagnn_expand_windows(const float* x, int64_t ldx, int64_t rows, int32_t cols, int32_t windows, float shift, float* out,
+                                    int64_t ld_out, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (rows < 0 || cols < 0 || windows < 1 || (rows > 0 && cols > 0 && (!x || !out))) return KAGNN_EINVAL;
+    if (rows == 0 || cols == 0) return KAGNN_OK;
+    if (ldx < cols || ld_out < (int64_t)cols * windows) return KAGNN_EINVAL;
+    int64_t blocks = ceil_div64(rows * cols, kThreads);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    expand_windows_kernel<<<(unsigned)blocks, kThreads, 0, stream>>>(x, (long long)ldx, (long long)rows, cols, windows, shift, out,
+                                                                     (long long)ld_out);
+    KAGNN_LAUNCH_CHECK();
+    return KAGNN_OK;
+}
+
 extern "C" int kagnn_gather_rows_peer(const float* const* peer_x, int64_t ldx, int64_t rows_per_rank, const int32_t* ids,
                                       int64_t rows, int32_t cols, float* out, int64_t ld_out, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);

@@ -162,6 +162,9 @@ class KANLinear(nn.Module):
         if key != self._cache_key:
             t0, h = self._knot_params()
             slots = self.grid_size + self.spline_order
+            if slots > 8 and 1 <= self.spline_order <= 3 and ops.tc_supported(L.BASIS_BSPLINE, 8 - self.spline_order, self.spline_order, self.out_features):
+                self._cache_spec, self._cache_key = self._windowed_spec(t0, h, slots), key
+                return self._cache_spec
             packed = ops.pack_kan_weights(self.base_weight, self.spline_weight,
                                           self.spline_scaler if self.enable_standalone_scale_spline else None,
                                           self.in_features, self.out_features, slots)
@@ -174,6 +177,27 @@ class KANLinear(nn.Module):
                                                 self.spline_order, t0, h, 0.0, packed, packed_w_tc=packed_tc)
             self._cache_key = key
         return self._cache_spec
+
+    def _windowed_spec(self, t0: float, h: float, slots: int) -> ops.KanLayerSpec:
+        """More than eight coefficients per (in, out) pair (the reference's search space goes to grid_size 8 + spline_order 3,
+        node_classification/one_experiment.py:45-46): the tensor-core kernels hold eight slots per feature, and a uniform B-spline
+        basis is shift invariant -- B_{8w+j}(x) = B_j(x - 8wh) -- so the layer is evaluated as a layer of grid_size 8 - k over
+        ``windows`` copies of the input, copy w shifted by 8wh and carrying coefficients 8w .. 8w+7 (zero beyond G + k); the SiLU
+        base weight rides on copy 0.  Outside a copy's knot range all of its eight bases are zero, as they should be."""
+        with torch.no_grad():
+            w = (slots + 7) // 8
+            out_f, in_f = self.out_features, self.in_features
+            sp = torch.zeros(out_f, in_f, 8 * w, dtype=torch.float32, device=self.spline_weight.device)
+            sp[:, :, :slots] = self.spline_weight
+            virt_spline = sp.view(out_f, in_f, w, 8).permute(0, 2, 1, 3).reshape(out_f, w * in_f, 8).contiguous()
+            virt_base = torch.zeros(out_f, w * in_f, dtype=torch.float32, device=sp.device)
+            virt_base[:, :in_f] = self.base_weight
+            virt_scaler = self.spline_scaler.detach().repeat(1, w).contiguous() if self.enable_standalone_scale_spline else None
+            g_virtual = 8 - self.spline_order
+            packed = ops.pack_kan_weights(virt_base, virt_spline, virt_scaler, w * in_f, out_f, 8)
+            packed_tc = ops.pack_kan_weights_tc(virt_base, virt_spline, virt_scaler, w * in_f, out_f, 8)
+        return ops.KanLayerSpec(L.BASIS_BSPLINE, w * in_f, out_f, g_virtual, self.spline_order, t0, h, 0.0, packed, packed_w_tc=packed_tc,
+                                windows=w, window_shift=8.0 * h, virt_spline=virt_spline, virt_scaler=virt_scaler)
 
     def kernel_specs(self) -> List[ops.KanLayerSpec]:
         return [self.kernel_spec()]

@@ -250,6 +250,21 @@ def gather_rows(x: Tensor, index: Optional[Tensor], out: Optional[Tensor] = None
 
 
 @_on_device
+def expand_windows(x: Tensor, windows: int, shift: float) -> Tensor:
+    """(rows, windows * cols): copy w of the columns is x - w * shift (kagnn_expand_windows)."""
+    global launch_count
+    _need_cuda(x, "x", torch.float32)
+    ldx = _rows(x, "x")
+    out = torch.empty(x.size(0), windows * x.size(1), dtype=torch.float32, device=x.device)
+    if out.numel() == 0:
+        return out
+    L.check(L.lib().kagnn_expand_windows(_p(x), ldx, x.size(0), x.size(1), int(windows), float(shift), _p(out), out.size(1), _stream()),
+            "expand_windows")
+    launch_count += 1
+    return out
+
+
+@_on_device
 def layernorm_stats(x: Tensor, x_head: Optional[Tensor] = None, eps: float = 1e-5) -> Tensor:
     """(rows, 2) per-row (mean, rstd) of LayerNorm over the two-part rows [x_head | x] (kagnn_layernorm_stats)."""
     global launch_count
@@ -558,6 +573,13 @@ class KanLayerSpec:
     ln_bias: Optional[Tensor] = None
     packed_w_tc: Optional[Tensor] = None
     ln_stats: Optional[Tensor] = None     # per-row (mean, rstd) of the first layer's LayerNorm (layernorm_stats); per call
+    # B-spline layers with more than eight slots per feature (G + k > 8) as `windows` virtual features of eight slots each:
+    # in_features = windows * real inputs, the input is expand_windows(x, windows, window_shift = 8 h) (ekan.KANLinear.kernel_spec);
+    # virt_* = the repacked (out, windows * in, 8) / (out, windows * in) weights, for the chain rule of the backward
+    windows: int = 1
+    window_shift: float = 0.0
+    virt_spline: Optional[Tensor] = None
+    virt_scaler: Optional[Tensor] = None
     _anchors = ("packed_w",)
 
     def fill(self, s: L.KagnnKanLayer) -> None:
@@ -720,6 +742,8 @@ def fused_layer(agg: AggSpec, num_rows: int, layers: Sequence[KanLayerSpec], pre
         agg_out = torch.empty(num_rows, agg.x.size(1), dtype=torch.float32, device=dev)
     if num_rows == 0:
         return out if layers else agg_out
+    if any(sp.windows > 1 for sp in layers):
+        return _windowed_chain(agg, num_rows, layers, pre, post, agg_out, out)
     if len(layers) > 1 and any(sp.out_features > 128 for sp in layers) and all(sp.packed_w_tc is not None for sp in layers) \
             and _tc_variant_is_pipelined():
         return _wide_chain(agg, num_rows, layers, pre, post, agg_out, out)
@@ -756,6 +780,24 @@ _tc_variant = 0
 
 def _tc_variant_is_pipelined() -> bool:
     return _tc_variant == 0
+
+
+def _windowed_chain(agg: AggSpec, num_rows: int, layers, pre, post, agg_out, out):
+    """Chains with a B-spline layer of more than eight slots per feature (KanLayerSpec.windows > 1): the aggregation (if any)
+    and every layer are their own launches, because the input of a windowed layer is expanded in HBM first."""
+    dev = agg.x.device
+    plain = agg.mode == L.AGG_NONE and pre is None and agg.src_index is None and agg.x_head is None
+    if plain and agg_out is None:
+        cur = agg.x
+    else:
+        cur = agg_out if agg_out is not None else torch.empty(num_rows, layers[0].in_features // layers[0].windows, dtype=torch.float32, device=dev)
+        fused_layer(agg, num_rows, [], pre=pre, agg_out=cur)
+    for i, sp in enumerate(layers):
+        last = i == len(layers) - 1
+        xin = expand_windows(cur, sp.windows, sp.window_shift) if sp.windows > 1 else cur
+        y = out if last else torch.empty(num_rows, sp.out_features, dtype=torch.float32, device=dev)
+        cur = fused_layer(AggSpec(L.AGG_NONE, xin), num_rows, [dataclasses.replace(sp, windows=1)], post=post if last else None, out=y)
+    return cur
 
 
 def _wide_chain(agg: AggSpec, num_rows: int, layers, pre, post, agg_out, out):
@@ -813,6 +855,9 @@ def _layer_struct(spec: KanLayerSpec) -> L.KagnnKanLayer:
 def kan_bwd_input(spec: KanLayerSpec, x: Tensor, dy: Tensor) -> Tensor:
     """d loss / d x of one B-spline KAN layer (kagnn_kan_bwd_input)."""
     global launch_count
+    if spec.windows > 1:                     # d x = sum over the windows of d (x - w shift)
+        dxw = kan_bwd_input(dataclasses.replace(spec, windows=1), expand_windows(x, spec.windows, spec.window_shift), dy)
+        return dxw.view(x.size(0), spec.windows, x.size(1)).sum(1)
     ldx, ld_dy = _rows(x, "x"), _rows(dy, "dy")
     dx = torch.empty(x.size(0), spec.in_features, dtype=torch.float32, device=x.device)
     s = _layer_struct(spec)
@@ -824,8 +869,11 @@ def kan_bwd_input(spec: KanLayerSpec, x: Tensor, dy: Tensor) -> Tensor:
 
 @_on_device
 def kan_bwd_weights(spec: KanLayerSpec, x: Tensor, dy: Tensor) -> Tensor:
-    """Gradient of the packed fp32 weights [in][slots+1][out_pad4] (kagnn_kan_bwd_weights)."""
+    """Gradient of the packed fp32 weights [in][slots+1][out_pad4] (kagnn_kan_bwd_weights); of the VIRTUAL layer's packing when the
+    layer is windowed (kan_unpack_windowed_grads folds it back)."""
     global launch_count
+    if spec.windows > 1:
+        return kan_bwd_weights(dataclasses.replace(spec, windows=1), expand_windows(x, spec.windows, spec.window_shift), dy)
     ldx, ld_dy = _rows(x, "x"), _rows(dy, "dy")
     d_packed = torch.empty_like(spec.packed_w)
     s = _layer_struct(spec)
@@ -849,6 +897,19 @@ def kan_unpack_weight_grads(d_packed: Tensor, spline_w: Tensor, scaler: Optional
     L.check(L.lib().kagnn_kan_unpack_weight_grads(_p(d_packed), _p(sw), _p(sc), in_f, out_f, slots, _p(d_base), _p(d_spline),
                                                   _p(d_scaler), _stream()), "kan_unpack_weight_grads")
     launch_count += 1
+    return d_base, d_spline, d_scaler
+
+
+def kan_unpack_windowed_grads(d_packed: Tensor, spec: KanLayerSpec, slots: int):
+    """Gradients of a windowed layer's REAL parameters from the gradient of its virtual packing: the chain rule through
+    scaled_spline_weight on the virtual (out, windows * in, 8) weights, then window w's slots go back to slots 8 w .. 8 w + 7,
+    the base weight is window 0's, the scaler's gradient the sum over the windows."""
+    d_base_v, d_spline_v, d_scaler_v = kan_unpack_weight_grads(d_packed, spec.virt_spline, spec.virt_scaler)
+    out_f, vin, _ = spec.virt_spline.shape
+    w, f = spec.windows, vin // spec.windows
+    d_spline = d_spline_v.view(out_f, w, f, 8).permute(0, 2, 1, 3).reshape(out_f, f, 8 * w)[:, :, :slots].contiguous()
+    d_base = d_base_v[:, :f].contiguous()
+    d_scaler = None if d_scaler_v is None else d_scaler_v.view(out_f, w, f).sum(1)
     return d_base, d_spline, d_scaler
 
 

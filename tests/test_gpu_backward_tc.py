@@ -20,7 +20,9 @@ SHAPES = [  # (rows, in, out, G, k)
     (260, 16, 16, 4, 1),
     (2000, 64, 128, 5, 3),
     (640, 48, 256, 5, 3),          # wide output (BASELINE C5 width)
-    (1500, 24, 32, 8, 3),          # S = 11: dX on the tensor cores, dW stays on the fp32 kernels
+    (1500, 24, 32, 8, 3),          # S = 11: two windows of eight slots (ekan.KANLinear._windowed_spec)
+    (900, 20, 16, 13, 3),          # S = 16: two full windows
+    (700, 12, 24, 20, 2),          # S = 22: three windows
 ]
 
 
@@ -68,7 +70,10 @@ def test_tc_gradients_match_fp32_kernels_and_autograd(rows, in_f, out_f, G, k):
     y = K.kan_linear(xr, params["base_weight"], params["spline_weight"], params.get("spline_scaler"), params["grid"], k)
     y.backward(dy)
     assert K.rel_err(dx_tc.cpu(), xr.grad) <= TOL_AUTOGRAD
-    d_base, d_spline, d_scaler = ops.kan_unpack_weight_grads(dp_tc, lay.spline_weight, lay.spline_scaler)
+    if spec.windows > 1:                                             # G + k > 8: gradient of the virtual (windowed) packing
+        d_base, d_spline, d_scaler = ops.kan_unpack_windowed_grads(dp_tc, spec, G + k)
+    else:
+        d_base, d_spline, d_scaler = ops.kan_unpack_weight_grads(dp_tc, lay.spline_weight, lay.spline_scaler)
     assert K.rel_err(d_base.cpu(), params["base_weight"].grad) <= TOL_AUTOGRAD
     assert K.rel_err(d_spline.cpu(), params["spline_weight"].grad) <= TOL_AUTOGRAD
     assert K.rel_err(d_scaler.cpu(), params["spline_scaler"].grad) <= TOL_AUTOGRAD
