@@ -12,6 +12,8 @@ from __future__ import annotations
 
 from typing import Optional
 
+import dataclasses
+
 import torch
 from torch.autograd.function import once_differentiable
 
@@ -87,19 +89,39 @@ class _FastKanLayerFn(torch.autograd.Function):
         ln_w = ln_w if ctx.ln_affine else None
         dy = _rowmajor(dy)
         spec, lay = ctx.spec, ctx.layer
+        nw, f = spec.windows, x.size(1)
+        if nw > 1:
+            # more than eight centres: the virtual layer over `nw` copies of x (fastkan.FastKANLayer._windowed_spec); the gradient of
+            # a copied input is the sum over its copies, so are those of the LayerNorm vectors; window w holds centres 8w .. 8w+7
+            x = ops.expand_windows(x, nw, spec.window_shift)
+            spec = dataclasses.replace(spec, windows=1)
+            if ctx.ln_affine:
+                ln_w = spec.ln_weight
+
+        def fold(t):                                                     # (.., nw * f) -> (.., f), summed over the windows
+            return t if (t is None or nw == 1) else t.reshape(*t.shape[:-1], nw, f).sum(-2)
+
         stats = ops.layernorm_stats(x) if ctx.has_ln else None          # recomputed, not kept: (rows, 2)
         dx = d_lnw = d_lnb = d_spline = d_base = d_bb = None
         if ctx.needs_input_grad[0] or (ctx.has_ln and any(ctx.needs_input_grad[1:3])):
             dz, dxb = ops.rbf_bwd_input(spec, x, stats, dy)
             if ctx.has_ln:
                 dx, d_lnw, d_lnb = ops.layernorm_backward(x, stats, ln_w, dz, dxb, ctx.ln_affine)
+                dx, d_lnw, d_lnb = fold(dx), fold(d_lnw), fold(d_lnb)
             else:
-                dx = dz
+                dx = fold(dz)
         if ctx.needs_input_grad[3] or (ctx.has_base and ctx.needs_input_grad[4]):
             d_packed = ops.rbf_bwd_weights(spec, x, stats, dy)
-            sw3 = spline_w.detach().view(lay.output_dim, lay.input_dim, -1)
-            d_base, d_spline3, _ = ops.kan_unpack_weight_grads(d_packed, sw3, None, need_base=ctx.has_base)
-            d_spline = d_spline3.view_as(spline_w)
+            if nw > 1:
+                d_base_v, d_spline_v, _ = ops.kan_unpack_weight_grads(d_packed, spec.virt_spline, None, need_base=ctx.has_base)
+                G = spline_w.size(1) // f
+                d_spline = d_spline_v.view(lay.output_dim, nw, f, 8).permute(0, 2, 1, 3).reshape(lay.output_dim, f, 8 * nw)[:, :, :G]
+                d_spline = d_spline.reshape(lay.output_dim, f * G).contiguous()
+                d_base = None if d_base_v is None else d_base_v[:, :f].contiguous()
+            else:
+                sw3 = spline_w.detach().view(lay.output_dim, lay.input_dim, -1)
+                d_base, d_spline3, _ = ops.kan_unpack_weight_grads(d_packed, sw3, None, need_base=ctx.has_base)
+                d_spline = d_spline3.view_as(spline_w)
         if ctx.has_base and ctx.needs_input_grad[5]:
             d_bb = ops.column_sums(dy)
         return dx, d_lnw, d_lnb, d_spline, d_base, d_bb, None

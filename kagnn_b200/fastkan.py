@@ -93,6 +93,10 @@ class FastKANLayer(nn.Module):
         key = tuple((p.data_ptr(), p._version) for p in ps)
         if key != self._cache_key:
             G, gmin, step = self._grid_params()
+            ln = self.layernorm
+            if G > 8 and ops.tc_supported(L.BASIS_RBF, 8, 0, self.output_dim) and (ln is None or ln.elementwise_affine):
+                self._cache_spec, self._cache_key = self._windowed_spec(G, gmin, step), key
+                return self._cache_spec
             packed = ops.pack_kan_weights(self.base_linear.weight if self.use_base_update else None,
                                           self.spline_linear.weight, None, self.input_dim, self.output_dim, G)
             packed_tc = None
@@ -109,6 +113,39 @@ class FastKANLayer(nn.Module):
                 ln_bias=None if ln is None else ln.bias.detach(), packed_w_tc=packed_tc)
             self._cache_key = key
         return self._cache_spec
+
+    def _windowed_spec(self, G: int, gmin: float, step: float) -> ops.KanLayerSpec:
+        """More than eight centres (the reference searches num_grids up to 32, node_classification/one_experiment.py:42): equally
+        spaced Gaussians are shift invariant, phi_{8w+j}(z) = phi_j(z - 8 w step), so the layer is evaluated by the 8-centre
+        tensor-core kernels over ``windows`` copies of the input.  With a LayerNorm the copies are exact duplicates (the row
+        statistics of [x | x | ..] are those of x) and the shift sits in the copy's LayerNorm bias, beta - 8 w step; without one
+        the input itself is shifted.  Copy w carries the spline weights of centres 8w .. 8w+7 (zero beyond G), copy 0 the SiLU
+        base weights (which see the raw x)."""
+        with torch.no_grad():
+            w = (G + 7) // 8
+            out_f, in_f = self.output_dim, self.input_dim
+            dev = self.spline_linear.weight.device
+            sp = torch.zeros(out_f, in_f, 8 * w, dtype=torch.float32, device=dev)
+            sp[:, :, :G] = self.spline_linear.weight.view(out_f, in_f, G)
+            virt_spline = sp.view(out_f, in_f, w, 8).permute(0, 2, 1, 3).reshape(out_f, w * in_f, 8).contiguous()
+            virt_base = None
+            if self.use_base_update:
+                virt_base = torch.zeros(out_f, w * in_f, dtype=torch.float32, device=dev)
+                virt_base[:, :in_f] = self.base_linear.weight
+            ln = self.layernorm
+            ln_w = ln_b = None
+            shift = 8.0 * step
+            if ln is not None:
+                if abs(ln.eps - 1e-5) > 1e-12:
+                    raise NotImplementedError("LayerNorm eps other than 1e-5 is not supported")
+                ln_w = ln.weight.detach().repeat(w).contiguous()
+                ln_b = (ln.bias.detach().unsqueeze(0) - shift * torch.arange(w, device=dev, dtype=torch.float32).unsqueeze(1)).reshape(-1).contiguous()
+                shift = 0.0
+            packed = ops.pack_kan_weights(virt_base, virt_spline.view(out_f, -1), None, w * in_f, out_f, 8)
+            packed_tc = ops.pack_kan_weights_tc(virt_base, virt_spline.view(out_f, -1), None, w * in_f, out_f, 8)
+        return ops.KanLayerSpec(L.BASIS_RBF, w * in_f, out_f, 8, 0, gmin, step, 1.0 / float(self.rbf.denominator), packed,
+                                base_bias=self.base_linear.bias.detach() if self.use_base_update else None,
+                                ln_weight=ln_w, ln_bias=ln_b, packed_w_tc=packed_tc, windows=w, window_shift=shift, virt_spline=virt_spline)
 
     def kernel_specs(self) -> List[ops.KanLayerSpec]:
         return [self.kernel_spec()]

@@ -72,3 +72,46 @@ def test_training_step_through_a_windowed_layer():
     assert K.rel_err(lay.base_weight.grad.cpu(), params["base_weight"].grad) <= 2e-4
     assert K.rel_err(lay.spline_weight.grad.cpu(), params["spline_weight"].grad) <= 2e-4
     assert K.rel_err(lay.spline_scaler.grad.cpu(), params["spline_scaler"].grad) <= 2e-4
+
+
+@pytest.mark.parametrize("rows,in_f,out_f,G,ln", [(600, 24, 32, 12, True), (500, 40, 64, 16, True), (300, 10, 12, 32, True),
+                                                   (400, 16, 20, 20, False), (700, 96, 256, 10, True)])
+def test_windowed_fastkan_layer_forward_and_gradients(rows, in_f, out_f, G, ln):
+    """FastKANLayer with more than eight centres (the reference searches num_grids up to 32): 8-centre tensor-core kernels over
+    copies of the input, the shift in the copies' LayerNorm bias (or in the input when there is no LayerNorm); forward and every
+    gradient against autograd through the oracle's restatement of FastKANLayer.forward."""
+    import kagnn_b200 as kb
+    from kagnn_b200 import ops
+    torch.manual_seed(rows + G)
+    lay = kb.FastKANLayer(in_f, out_f, num_grids=G, use_layernorm=ln)
+    with torch.no_grad():
+        lay.spline_linear.weight.normal_(0, 0.3)
+        if ln:
+            lay.layernorm.weight.uniform_(0.5, 1.5)
+            lay.layernorm.bias.normal_(0, 0.2)
+    sd = {kk: v.detach().clone() for kk, v in lay.state_dict().items()}
+    g = torch.Generator().manual_seed(rows)
+    x = torch.randn(rows, in_f, generator=g) * 0.9
+    dy = torch.randn(rows, out_f, generator=g)
+    lay = lay.cuda().train()
+    spec = lay.kernel_specs()[0]
+    assert spec.windows == (G + 7) // 8 and spec.grid_size == 8 and spec.in_features == spec.windows * in_f
+    c0 = ops.launch_counters()
+    xd = x.cuda().requires_grad_(True)
+    y = lay(xd)
+    c1 = ops.launch_counters()
+    assert c1["fp32"] == c0["fp32"] and (c1["tc"] + c1["tc2"]) > (c0["tc"] + c0["tc2"])
+    y.backward(dy.cuda())
+    xr = x.clone().requires_grad_(True)
+    p = {kk: v.clone().requires_grad_(kk != "rbf.grid") for kk, v in sd.items()}
+    ref = K.fastkan_layer(xr, p.get("layernorm.weight"), p.get("layernorm.bias"), p["rbf.grid"], p["spline_linear.weight"],
+                          p["base_linear.weight"], p["base_linear.bias"])
+    ref.backward(dy)
+    assert K.rel_err(y.detach().cpu(), ref.detach()) <= TOL
+    assert K.rel_err(xd.grad.cpu(), xr.grad) <= 1e-3
+    assert K.rel_err(lay.spline_linear.weight.grad.cpu(), p["spline_linear.weight"].grad) <= 1e-3
+    assert K.rel_err(lay.base_linear.weight.grad.cpu(), p["base_linear.weight"].grad) <= 1e-3
+    assert K.rel_err(lay.base_linear.bias.grad.cpu(), p["base_linear.bias"].grad) <= 1e-3
+    if ln:
+        assert K.rel_err(lay.layernorm.weight.grad.cpu(), p["layernorm.weight"].grad) <= 1e-3
+        assert K.rel_err(lay.layernorm.bias.grad.cpu(), p["layernorm.bias"].grad) <= 1e-3
