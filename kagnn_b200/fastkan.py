@@ -94,7 +94,8 @@ class FastKANLayer(nn.Module):
         if key != self._cache_key:
             G, gmin, step = self._grid_params()
             ln = self.layernorm
-            if G > 8 and ops.tc_supported(L.BASIS_RBF, 8, 0, self.output_dim) and (ln is None or ln.elementwise_affine):
+            if (G > 8 and ops.rbf_windows_enabled() and ops.tc_supported(L.BASIS_RBF, 8, 0, self.output_dim)
+                    and (ln is None or ln.elementwise_affine)):
                 self._cache_spec, self._cache_key = self._windowed_spec(G, gmin, step), key
                 return self._cache_spec
             packed = ops.pack_kan_weights(self.base_linear.weight if self.use_base_update else None,
@@ -115,7 +116,8 @@ class FastKANLayer(nn.Module):
         return self._cache_spec
 
     def _windowed_spec(self, G: int, gmin: float, step: float) -> ops.KanLayerSpec:
-        """More than eight centres (the reference searches num_grids up to 32, node_classification/one_experiment.py:42): equally
+        """OPT-IN (ops.set_rbf_windows / KAGNN_RBF_WINDOWS=1; see the accuracy note there).  More than eight centres (the reference
+        searches num_grids up to 32, node_classification/one_experiment.py:42): equally
         spaced Gaussians are shift invariant, phi_{8w+j}(z) = phi_j(z - 8 w step), so the layer is evaluated by the 8-centre
         tensor-core kernels over ``windows`` copies of the input.  With a LayerNorm the copies are exact duplicates (the row
         statistics of [x | x | ..] are those of x) and the shift sits in the copy's LayerNorm bias, beta - 8 w step; without one

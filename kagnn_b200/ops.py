@@ -7,6 +7,7 @@ from __future__ import annotations
 import ctypes as C
 import dataclasses
 import functools
+import os
 from dataclasses import dataclass
 from typing import Optional, Sequence
 
@@ -492,6 +493,24 @@ def pack_kan_weights(base_w: Optional[Tensor], spline_w: Tensor, scaler: Optiona
                                            _stream()), "pack_kan_weights")
     launch_count += 1
     return packed
+
+
+# FastKAN layers with more than eight centres as slot windows on the tensor-core kernels (fastkan.FastKANLayer._windowed_spec): OFF
+# unless asked for.  The bf16 hi/lo split carries ~17 bits per operand; narrow Gaussians (denominator = range / (G - 1)) amplify
+# that through a deep model: against an fp64 evaluation, a 2 x 2-layer GIN model with 12 centres came out at 1.7e-4 on the tensor
+# cores, 1.0e-5 on the general fp32 kernel and 0.8e-5 in the reference's own fp32 (32 centres: 9e-3 / 1.3e-3 / 0.9e-3;
+# profiles/r2_windows_accuracy.json) -- outside the 1e-4 parity bound, so the default stays the fp32 kernel.  B-spline windows
+# (8.6e-6 on the same model) are always on.
+_rbf_windows = os.environ.get("KAGNN_RBF_WINDOWS", "0") == "1"
+
+
+def set_rbf_windows(on: bool) -> None:
+    global _rbf_windows
+    _rbf_windows = bool(on)
+
+
+def rbf_windows_enabled() -> bool:
+    return _rbf_windows
 
 
 def tc_supported(basis: int, grid_size: int, spline_order: int, out_features: int) -> bool:

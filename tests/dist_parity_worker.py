@@ -105,6 +105,26 @@ def main():
             if rank == 0:
                 print(f"{'fastkan' if fast else 'kan'}/gin push resident: {e5:.2e}, after x changed {e6:.2e}", flush=True)
             assert e6 <= 1e-5, ("push, resident input, new x", e6)
+    # large grids (slot windows, kagnn_b200/ekan.py: _windowed_spec): every layer is its own launch behind the halo exchange
+    for conv_type, fast in (("gin", False), ("gcn", False), ("gin", True)):
+        torch.manual_seed(13)
+        if fast:
+            m = kb.GFASTKAN_Nodes(conv_type, 2, f, 32, 5, skip=True, grid_size=12, hidden_layers=2).eval()
+        else:
+            m = kb.GKAN_Nodes(conv_type, 2, f, 32, 5, skip=True, grid_size=8, spline_order=3, hidden_layers=2).eval()
+        sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+        m = m.to(dev)
+        big = kd.ShardedNodeModel(m, rank, world, n_local, mode="auto")
+        assert big.mode == "halo", big.mode
+        bplan = big.prepare(ei[:, mine].to(dev))
+        y_big = big.forward(x[rank * n_local:(rank + 1) * n_local].to(dev), bplan)
+        ys = [torch.empty_like(y_big) for _ in range(world)]
+        dist.all_gather(ys, y_big)
+        e7 = K.rel_err(torch.cat(ys).cpu(), K.node_model_forward(sd, conv_type, x, ei, True))
+        worst = max(worst, e7)
+        if rank == 0:
+            print(f"{'fastkan grid 12' if fast else 'kan grid 8 order 3'}/{conv_type} (windows, halo): sharded vs oracle {e7:.2e}", flush=True)
+        assert e7 <= 1e-4, (conv_type, fast, e7)
     if rank == 0:
         print(f"DIST_PARITY_OK world={world} worst={worst:.2e}", flush=True)
     dist.destroy_process_group()

@@ -82,6 +82,16 @@ def test_windowed_fastkan_layer_forward_and_gradients(rows, in_f, out_f, G, ln):
     gradient against autograd through the oracle's restatement of FastKANLayer.forward."""
     import kagnn_b200 as kb
     from kagnn_b200 import ops
+    ops.set_rbf_windows(True)                                        # opt-in: see the accuracy note at ops.set_rbf_windows
+    try:
+        _windowed_fastkan_case(rows, in_f, out_f, G, ln)
+    finally:
+        ops.set_rbf_windows(False)
+
+
+def _windowed_fastkan_case(rows, in_f, out_f, G, ln):
+    import kagnn_b200 as kb
+    from kagnn_b200 import ops
     torch.manual_seed(rows + G)
     lay = kb.FastKANLayer(in_f, out_f, num_grids=G, use_layernorm=ln)
     with torch.no_grad():
@@ -115,3 +125,25 @@ def test_windowed_fastkan_layer_forward_and_gradients(rows, in_f, out_f, G, ln):
     if ln:
         assert K.rel_err(lay.layernorm.weight.grad.cpu(), p["layernorm.weight"].grad) <= 1e-3
         assert K.rel_err(lay.layernorm.bias.grad.cpu(), p["layernorm.bias"].grad) <= 1e-3
+
+
+def test_fastkan_with_many_centres_defaults_to_the_fp32_kernel():
+    """Without the opt-in a FastKANLayer with more than eight centres keeps the general fp32 kernel (parity bound of 1e-4 on deep
+    models; ops.set_rbf_windows)."""
+    import kagnn_b200 as kb
+    from kagnn_b200 import ops
+    assert not ops.rbf_windows_enabled()
+    torch.manual_seed(2)
+    lay = kb.FastKANLayer(16, 12, num_grids=12)
+    sd = {kk: v.detach().clone() for kk, v in lay.state_dict().items()}
+    x = torch.randn(300, 16) * 0.8
+    lay = lay.cuda()
+    assert lay.kernel_specs()[0].windows == 1
+    c0 = ops.launch_counters()
+    with torch.no_grad():
+        y = lay(x.cuda())
+    c1 = ops.launch_counters()
+    assert c1["fp32"] > c0["fp32"]
+    ref = K.fastkan_layer(x, sd["layernorm.weight"], sd["layernorm.bias"], sd["rbf.grid"], sd["spline_linear.weight"],
+                          sd["base_linear.weight"], sd["base_linear.bias"])
+    assert K.rel_err(y.cpu(), ref) <= TOL
