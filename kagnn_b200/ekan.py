@@ -87,6 +87,23 @@ def eval_mode_detach_notice(x: Tensor) -> None:
                       "inference plan and is detached from autograd (wrap evaluation in torch.no_grad() to silence this)", stacklevel=3)
 
 
+def windowed_weights(base_w: Optional[Tensor], spline_w: Tensor, scaler: Optional[Tensor], windows: int):
+    """Weights of the virtual layer that evaluates a layer with more than eight slots per feature as ``windows`` copies of its
+    input with eight slots each (KANLinear._windowed_spec, FastKANLayer._windowed_spec): virtual input ``w * in + i`` carries slots
+    8w .. 8w+7 of input i (zero beyond the real slot count), copy 0 the base weights, every copy the scaler.
+    (out, in, S) -> ((out, windows*in) | None, (out, windows*in, 8), (out, windows*in) | None)."""
+    out_f, in_f, slots = spline_w.shape
+    sp = torch.zeros(out_f, in_f, 8 * windows, dtype=torch.float32, device=spline_w.device)
+    sp[:, :, :slots] = spline_w.detach()
+    virt_spline = sp.view(out_f, in_f, windows, 8).permute(0, 2, 1, 3).reshape(out_f, windows * in_f, 8).contiguous()
+    virt_base = None
+    if base_w is not None:
+        virt_base = torch.zeros(out_f, windows * in_f, dtype=torch.float32, device=spline_w.device)
+        virt_base[:, :in_f] = base_w.detach()
+    virt_scaler = None if scaler is None else scaler.detach().repeat(1, windows).contiguous()
+    return virt_base, virt_spline, virt_scaler
+
+
 class KANLinear(nn.Module):
     """Drop-in for ``ekan.KANLinear``: y = silu(x) @ base_weight^T + B(x) @ (spline_weight * spline_scaler)^T."""
 
@@ -187,12 +204,8 @@ class KANLinear(nn.Module):
         with torch.no_grad():
             w = (slots + 7) // 8
             out_f, in_f = self.out_features, self.in_features
-            sp = torch.zeros(out_f, in_f, 8 * w, dtype=torch.float32, device=self.spline_weight.device)
-            sp[:, :, :slots] = self.spline_weight
-            virt_spline = sp.view(out_f, in_f, w, 8).permute(0, 2, 1, 3).reshape(out_f, w * in_f, 8).contiguous()
-            virt_base = torch.zeros(out_f, w * in_f, dtype=torch.float32, device=sp.device)
-            virt_base[:, :in_f] = self.base_weight
-            virt_scaler = self.spline_scaler.detach().repeat(1, w).contiguous() if self.enable_standalone_scale_spline else None
+            virt_base, virt_spline, virt_scaler = windowed_weights(
+                self.base_weight, self.spline_weight, self.spline_scaler if self.enable_standalone_scale_spline else None, w)
             g_virtual = 8 - self.spline_order
             packed = ops.pack_kan_weights(virt_base, virt_spline, virt_scaler, w * in_f, out_f, 8)
             packed_tc = ops.pack_kan_weights_tc(virt_base, virt_spline, virt_scaler, w * in_f, out_f, 8)

@@ -14,7 +14,7 @@ from torch import nn
 
 from . import _lib as L
 from . import autograd, ops
-from .ekan import _module_backend_guard, chain_forward
+from .ekan import _module_backend_guard, chain_forward, windowed_weights
 
 Tensor = torch.Tensor
 
@@ -41,6 +41,15 @@ class RadialBasisFunction(nn.Module):
 
     def forward(self, x):  # pragma: no cover - the fused kernel evaluates the basis; kept for API parity
         raise RuntimeError("RadialBasisFunction is evaluated inside kagnn_fused_layer_fwd; call FastKANLayer instead")
+
+
+def windowed_layernorm(weight: Tensor, bias: Tensor, windows: int, shift: float):
+    """LayerNorm vectors of the virtual FastKAN layer (FastKANLayer._windowed_spec): every copy the weight, copy w the bias minus
+    w * shift (the copy's centres sit w * shift further right)."""
+    w = weight.detach().repeat(windows).contiguous()
+    steps = torch.arange(windows, device=bias.device, dtype=torch.float32).unsqueeze(1)
+    b = (bias.detach().unsqueeze(0) - shift * steps).reshape(-1).contiguous()
+    return w, b
 
 
 class FastKANLayer(nn.Module):
@@ -127,21 +136,15 @@ class FastKANLayer(nn.Module):
             w = (G + 7) // 8
             out_f, in_f = self.output_dim, self.input_dim
             dev = self.spline_linear.weight.device
-            sp = torch.zeros(out_f, in_f, 8 * w, dtype=torch.float32, device=dev)
-            sp[:, :, :G] = self.spline_linear.weight.view(out_f, in_f, G)
-            virt_spline = sp.view(out_f, in_f, w, 8).permute(0, 2, 1, 3).reshape(out_f, w * in_f, 8).contiguous()
-            virt_base = None
-            if self.use_base_update:
-                virt_base = torch.zeros(out_f, w * in_f, dtype=torch.float32, device=dev)
-                virt_base[:, :in_f] = self.base_linear.weight
+            virt_base, virt_spline, _ = windowed_weights(self.base_linear.weight if self.use_base_update else None,
+                                                         self.spline_linear.weight.view(out_f, in_f, G), None, w)
             ln = self.layernorm
             ln_w = ln_b = None
             shift = 8.0 * step
             if ln is not None:
                 if abs(ln.eps - 1e-5) > 1e-12:
                     raise NotImplementedError("LayerNorm eps other than 1e-5 is not supported")
-                ln_w = ln.weight.detach().repeat(w).contiguous()
-                ln_b = (ln.bias.detach().unsqueeze(0) - shift * torch.arange(w, device=dev, dtype=torch.float32).unsqueeze(1)).reshape(-1).contiguous()
+                ln_w, ln_b = windowed_layernorm(ln.weight, ln.bias, w, shift)
                 shift = 0.0
             packed = ops.pack_kan_weights(virt_base, virt_spline.view(out_f, -1), None, w * in_f, out_f, 8)
             packed_tc = ops.pack_kan_weights_tc(virt_base, virt_spline.view(out_f, -1), None, w * in_f, out_f, 8)
