@@ -179,7 +179,13 @@ def _kan_layer(spec, x):
     return torch.einsum("nis,iso->no", bases, w[:, :S]) + F.silu(x) @ w[:, S]
 
 
+def _expand_windows(x, windows, shift):
+    return torch.cat([x - w * shift for w in range(windows)], dim=1).contiguous()
+
+
 def _fused_layer(agg, num_rows, layers, pre=None, post=None, agg_out=None, out=None):
+    if any(sp.windows > 1 for sp in layers):                 # the product's own wiring of windowed layers, leaf launches emulated
+        return ops._windowed_chain(agg, num_rows, layers, pre, post, agg_out, out)
     x = agg.x if agg.x_head is None else torch.cat([agg.x_head, agg.x], dim=1)
     if agg.x_halo is not None:
         x = torch.cat([x, agg.x_halo], dim=0)                # halo rows follow the owned rows in the local numbering
@@ -230,7 +236,10 @@ def _batchnorm_forward(x, bn, act=L.ACT_NONE):
 
 
 @contextlib.contextmanager
-def cpu_double():
+def cpu_double(windows: bool = False):
+    """``windows=True``: layers with more than eight slots / centres per input take the slot-window wiring (ekan._windowed_spec,
+    fastkan._windowed_spec, ops._windowed_chain and the gradient folding in ops / autograd) -- which on the GPU needs the tensor-core
+    kernels -- with every leaf launch emulated like all the others."""
     host = _HostLib()
     saved = []
 
@@ -247,7 +256,11 @@ def cpu_double():
     patch(L, "lib", lambda: host)
     patch(ops, "_need_cuda", lambda t, name, dtype=None: None)
     patch(ops, "_stream", lambda: None)
-    patch(ops, "tc_supported", lambda *a: False)
+    patch(ops, "tc_supported", (lambda *a: True) if windows else (lambda *a: False))
+    if windows:
+        patch(ops, "pack_kan_weights_tc", lambda *a, **k: None)
+        patch(ops, "expand_windows", _expand_windows)
+        patch(ops, "_rbf_windows", True)
     for name, fn in (("csr_build", _csr_build), ("gcn_norm", _gcn_norm), ("gcn_degree", _gcn_degree), ("gcn_edge_weight", _gcn_edge_weight), ("gather_rows", _gather_rows), ("segment_ptr", _segment_ptr),
                      ("pack_kan_weights", _pack), ("fused_layer", _fused_layer), ("batchnorm_forward", _batchnorm_forward),
                      ("log_softmax", lambda x: torch.log_softmax(x, dim=1)), ("layernorm_stats", _layernorm_stats),

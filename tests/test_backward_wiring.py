@@ -49,6 +49,25 @@ def test_module_gradients_match_reference_dry_run(name):
         check_against_fixture(name, "cpu")
 
 
+@pytest.mark.parametrize("name", ["grad_kanlinear_g8_k1_5x9", "grad_fastkan_5_6_7_g32", "grad_kanlinear_g5_k3_33x7", "grad_nc_gkan_gin_skip1",
+                                  "grad_nc_gfastkan_gcn"])
+def test_slot_window_wiring_matches_reference_dry_run(name):
+    """Layers with more than eight coefficients (KANLinear grid 8, order 1) or centres (FastKAN 5-6-7 with 32 grids) through the
+    slot-window wiring -- virtual layer over copies of the input, dx / LayerNorm gradients summed over the copies, weight gradients
+    folded back -- against the gradients the reference's own modules produced; the other fixtures must be untouched by it."""
+    from kagnn_b200 import ops
+    with cpu_double(windows=True):
+        model = check_against_fixture(name, "cpu")
+        specs = [m.kernel_spec() for m in model.modules() if hasattr(m, "kernel_spec")]
+        if "g8_k1" in name:
+            assert [sp.windows for sp in specs] == [2]
+        if "g32" in name:
+            assert [sp.windows for sp in specs] == [4, 4]
+        if "g5_k3" in name or "nc_" in name:
+            assert all(sp.windows == 1 for sp in specs)
+    assert not ops.rbf_windows_enabled()
+
+
 def test_eval_mode_with_autograd_enabled_takes_the_inference_plan():
     """graph_classification_utils.py:57-72 evaluates with model.eval() but without torch.no_grad()."""
     import kagnn_b200 as kb
