@@ -212,6 +212,49 @@ def main() -> None:
           dict(x=xq, edge_index=ei, batch=batch, edge_attr=eq), m.state_dict(), y)
 
 
+def main_large_grids() -> None:
+    """Layers with more than eight coefficients per (in, out) pair -- the upper part of the reference's search space
+    (node_classification_clean/one_experiment.py:45-46) -- from the reference's own KANLinear / GKAN_Nodes: the shapes the product
+    evaluates as slot windows.  Own generator, written next to the other fixtures without touching them
+    (``python -m oracle.make_golden --large-grids-only``)."""
+    from . import pyg_shim
+    pyg_shim.install()
+    torch.manual_seed(2468)
+    gen = torch.Generator().manual_seed(2468)
+    ekan = _load(os.path.join(NC, "ekan.py"), "ref_nc_ekan")
+    for (g, k, fin, fout, n) in [(8, 3, 24, 32, 300), (13, 3, 20, 16, 200), (20, 2, 12, 24, 150), (6, 3, 9, 5, 140)]:
+        lay = ekan.KANLinear(fin, fout, grid_size=g, spline_order=k)
+        x = torch.randn(n, fin, generator=gen) * 0.8
+        knots = lay.grid[0]
+        x[0, :] = knots[torch.arange(fin) % knots.numel()]            # exactly on knots (incl. t_0, t_last)
+        x[1, :] = knots[0] - 1e-3
+        x[2, :] = knots[-1] + 0.5
+        x[3, :] = 0.0
+        x[4, :] = torch.nextafter(knots[-1], torch.tensor(-10.0))
+        x[5, :] = knots[8] if knots.numel() > 8 else 0.0               # the boundary between the first two windows of eight slots
+        with torch.no_grad():
+            y = lay(x)
+            bases = lay.b_splines(x)
+        sd = dict(lay.state_dict())
+        sd["__bases"] = bases
+        _save(f"kanlinear_g{g}_k{k}_{fin}x{fout}", dict(kind="kan_linear", G=g, k=k), dict(x=x), sd, y)
+    ncm = _load(os.path.join(NC, "models.py"), "ref_nc_models")
+    n, e, f, c = 400, 1500, 19, 5
+    ei = small_graph(n, e, gen)
+    x = torch.randn(n, f, generator=gen) * 0.7
+    for conv in ("gcn", "gin"):
+        m = ncm.GKAN_Nodes(conv, 2, f, 12, c, skip=True, grid_size=8, spline_order=3, hidden_layers=2, dropout=0.0).eval()
+        _randomise(m, gen)
+        with torch.no_grad():
+            y = m(x, ei)
+        _save(f"nc_gkan_{conv}_g8k3", dict(kind="node", conv_type=conv, skip=True, fast=False, mp_layers=2, num_features=f, hidden=12,
+              classes=c, G=8, k=3, hidden_layers=2), dict(x=x, edge_index=ei), m.state_dict(), y)
+
+
 if __name__ == "__main__":
     from . import kagnn_oracle as K
-    main()
+    if "--large-grids-only" in sys.argv:
+        main_large_grids()
+    else:
+        main()
+        main_large_grids()
