@@ -123,7 +123,7 @@ def test_shard_batch_by_graph():
 
 
 # ---- the whole sharded forward (ShardedNodeModel, mode="halo") over gloo, library launches replaced by the CPU stand-ins --------
-def _model_worker(rank, world, port, conv_type, out):
+def _model_worker(rank, world, port, conv_type, out, grid_size=5):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -135,15 +135,18 @@ def _model_worker(rank, world, port, conv_type, out):
         x, eis = _global_problem(world, n_local, 120, f, seed=3)
         ei_all = torch.cat(eis, dim=1)
         torch.manual_seed(11)                                         # same replicated weights on every rank
-        model = kb.GKAN_Nodes(conv_type, 2, f, 12, c, skip=True, grid_size=5, spline_order=3, hidden_layers=2).eval()
+        model = kb.GKAN_Nodes(conv_type, 2, f, 12, c, skip=True, grid_size=grid_size, spline_order=3, hidden_layers=2).eval()
         with torch.no_grad():
             for bn in model.bns:                                      # non-trivial eval BatchNorm
                 bn.running_mean.uniform_(-0.3, 0.3)
                 bn.running_var.uniform_(0.5, 1.5)
         sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
         lo = rank * n_local
-        with cpu_double(), torch.no_grad():
+        with cpu_double(windows=grid_size > 5), torch.no_grad():      # grid 8 + order 3: the slot-window wiring behind the halo exchange
             runner = kd.ShardedNodeModel(model, rank, world, n_local, mode="halo")
+            if grid_size > 5:
+                assert max(lay.kernel_spec().windows for conv in model.convs for lay in
+                           (conv.nn.layers if hasattr(conv, "nn") else [conv.lin])) == 2
             plan = runner.prepare(eis[rank])
             y_shard = runner.forward(x[lo:lo + n_local].contiguous(), plan)
             y_shard2 = runner.forward(x[lo:lo + n_local].contiguous(), plan)          # the plan is reusable
@@ -160,14 +163,15 @@ def _model_worker(rank, world, port, conv_type, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("conv_type", ["gin", "gcn"])
-def test_sharded_model_forward_gloo(conv_type):
-    """world_size 2: every rank's rows of the sharded forward == the oracle on the global graph."""
+@pytest.mark.parametrize("conv_type,grid_size", [("gin", 5), ("gcn", 5), ("gin", 8), ("gcn", 8)])
+def test_sharded_model_forward_gloo(conv_type, grid_size):
+    """world_size 2: every rank's rows of the sharded forward == the oracle on the global graph (grid 8: layers of eleven
+    coefficients per pair, evaluated as two slot windows)."""
     world = 2
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_model_worker, args=(r, world, port, conv_type, out)) for r in range(world)]
+    procs = [ctx.Process(target=_model_worker, args=(r, world, port, conv_type, out, grid_size)) for r in range(world)]
     for p in procs:
         p.start()
     results = [out.get(timeout=240) for _ in procs]
