@@ -68,6 +68,10 @@ def model_state(seed=12345):
     return m
 
 
+PRE_WARM_S = 0.3
+PRE_WARM_STEPS = 200                # the same phase as a step count, for sharded runs
+
+
 class ClockSampler:
     """SM clock / throttle reasons DURING the timed region: an NVML polling thread (2 ms period; the timed region of this
     bench is tens of milliseconds, too short for `nvidia-smi -lms`), falling back to the nvidia-smi query of
@@ -76,7 +80,7 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.samples, self.stop_flag, self.proc, self.nvml = [], False, None, None
+        self.samples, self.stop_flag, self.proc, self.nvml, self.index = [], False, None, None, index
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -105,10 +109,18 @@ class ClockSampler:
         while not self.stop_flag:
             try:
                 mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                self.samples.append((time.perf_counter(), mhz, self.max, [n for n, b in names if mask & b]))
             except Exception:
-                pass
+                time.sleep(0.002)
+                continue
+            mask = None                                   # the reasons query is not available on every driver / permission level:
+            for fn in ("nvmlDeviceGetCurrentClocksEventReasons", "nvmlDeviceGetCurrentClocksThrottleReasons"):
+                try:                                      # a clock sample must not be lost with it
+                    mask = getattr(nv, fn)(self.h)
+                    break
+                except Exception:
+                    continue
+            reasons = ["reasons unavailable"] if mask is None else [n for n, b in names if mask & b]
+            self.samples.append((time.perf_counter(), mhz, self.max, reasons))
             time.sleep(0.002)
 
     def _read(self):
@@ -134,6 +146,17 @@ class ClockSampler:
         sel = [q for q in self.samples if t0 is None or (t0 <= q[0] <= t1)]
         if not sel:                                       # region shorter than one period: nearest sample
             sel = sorted(self.samples, key=lambda q: abs(q[0] - (t0 or 0)))[:1]
+        if not sel:                                       # the poller got nothing at all: one query now, the GPU is still warm
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=10).stdout.strip().splitlines()[0]
+                parts = [q.strip() for q in out.split(",")]
+                rs = [n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7])
+                      if v.lower().startswith("active")]
+                return {"sm_mhz": float(parts[0]), "sm_max_mhz": float(parts[1]), "reasons": rs, "samples": 1,
+                        "source": "nvidia-smi, one query right after the timed region (the poller returned nothing)"}
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"], "samples": 0}
         reasons = sorted({r for q in sel for r in q[3]})
         return {"sm_mhz": statistics.median([q[1] for q in sel]) if sel else None, "sm_max_mhz": sel[0][2] if sel else None,
                 "reasons": reasons, "samples": len(sel), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
@@ -310,6 +333,14 @@ def main():
         torch.cuda.synchronize()
 
     with torch.no_grad():
+        # a GPU that has been idle (a fresh box) takes a few hundred milliseconds of load to reach its boost clock: run untimed steps
+        # for PRE_WARM_S first, then the W warm-up steps the command line asks for
+        t_pre, n_pre = time.perf_counter(), 0
+        while (n_pre < PRE_WARM_STEPS) if dist_on else (time.perf_counter() - t_pre < PRE_WARM_S):
+            flush.zero_()                                 # (sharded: a fixed count -- every rank must take part in every step's barriers)
+            step()
+            torch.cuda.synchronize()
+            n_pre += 1
         for _ in range(args.warmup):
             flush.zero_()
             step()
@@ -492,6 +523,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "nodes_per_gpu": n_local, "edges_per_gpu": N_EDGES, "features": N_FEAT,
                    "l2": "flushed between iterations (512 MB memset)", "csr": "cached across steps (static graph)",
+                   "pre_warm": ("%d untimed steps" % PRE_WARM_STEPS if dist_on else "%.2f s of untimed steps" % PRE_WARM_S) + " before the warm-up steps (clock ramp of an idle GPU)",
                    "parallelism": (f"node-range shards x{world}, " + ("remote rows gathered in-kernel over NVLink (symmetric memory), "
                                    "one device barrier per layer" if runner.mode == "peer" else ("distinct remote rows pulled over NVLink from symmetric memory "
                                    "by one copy kernel per layer (no collective)" if runner.mode == "pull" else ("x halo pulled over NVLink before layer 0; hidden rows pushed into the peers' replicas by a relay warp of the producing layer's kernel (bulk copies, masked per row), one device barrier per layer" if runner.mode == "push" else ("distinct remote rows pulled over NVLink by a copy kernel that runs concurrently with the layer (first-use order, progress counters)" if runner.mode == "pull_overlap" else "one NCCL halo all-to-all per layer")))))
