@@ -23,8 +23,12 @@ if HERE not in sys.path:
 import synth_graphs as SG  # noqa: E402
 
 
-def _time(fn, flush, steps=10, warmup=3):
+def _time(fn, flush, steps=10, warmup=3, pre_warm_s=0.2):
     with torch.no_grad():
+        t_pre = time.perf_counter()                     # an idle GPU needs a moment of load to reach its boost clock (bench.py: PRE_WARM_S)
+        while time.perf_counter() - t_pre < pre_warm_s:
+            fn()
+            torch.cuda.synchronize()
         for _ in range(warmup):
             flush.zero_()
             fn()
